@@ -1,0 +1,164 @@
+/* tcar_b200.h -- C ABI of libtcar_b200.so: the B200 (sm_100a) replacement for the TensorFlow kernels that the
+ * reference's TCAR train / full-catalog-eval hot path executes inside `sess.run`
+ * (summmeer/session-based-news-recommendation: model_combine.py:231-234 train, :283-286 eval).
+ *
+ * Conventions:
+ *   - every function returns 0 on success, a cudaError_t (>0) or a TCAR_ERR_* code (<0); nothing throws;
+ *   - all pointers are DEVICE pointers owned by the caller; no function allocates or frees device memory;
+ *   - every function is asynchronous on the caller-supplied stream (`void* stream` is a cudaStream_t) and
+ *     keeps no global mutable state besides cached immutable driver/device queries;
+ *   - index arrays are int32, tables / activations fp32 unless a name says bf16.
+ *
+ * Shapes: B <= 512 sessions per call, T <= 40 clicks, H = 250, Th = 64, N items, Nn negatives.
+ * Trainable / frozen item tables use a 256-float row pitch (TCAR_HP) so rows are 128-bit aligned.
+ */
+#ifndef TCAR_B200_H_
+#define TCAR_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TCAR_H 250        /* hidden_size == content width   (model_combine.py:45, main.py:109)        */
+#define TCAR_HP 256       /* row pitch of item/content tables in floats                                 */
+#define TCAR_TH 64        /* time_hidden_size               (model_combine.py:46, modules.py:138)     */
+#define TCAR_XW 500       /* [item+pos | content]           (model_combine.py:111)                    */
+#define TCAR_PW 320       /* 5 publish-time embeddings      (model_combine.py:84)                     */
+#define TCAR_NBINS 139    /* 13 + 32 + 8 + 25 + 61 rows of the month/day/week/hour/minute tables      */
+#define TCAR_KEXT 640     /* scoring K: 500 + 139 one-hot time bins + 1 zero pad                        */
+#define TCAR_QROWS 512    /* max sessions per scoring call (main.py:101 batch_size default)            */
+#define TCAR_MAXT 40      /* position table rows            (model_combine.py:57)                     */
+#define TCAR_TOPK 20      /* cutoff                          (model_combine.py:296,301)                */
+#define TCAR_CHUNK 8      /* items per eval chunk-max                                                   */
+#define TCAR_NCAND_CHUNKS 32 /* chunks re-scored per query (256 candidate items)                        */
+
+#define TCAR_ERR_ARG (-1)
+#define TCAR_ERR_DRIVER (-2)
+#define TCAR_ERR_TENSORMAP (-3)
+
+/* ------------------------------------------------------------------------------------------------------------
+ * (1) fused gather -- replaces the ten `embedding_lookup(..., max_norm=1)` call sites of model_combine.py:54-107
+ *     (modules.py:36): clip(x) = x / max(||x||_2, 1) per gathered row.
+ *   idx   [7][B*T] : seq (1-based item id), month, day, week, hour, minute, gap      (sampler.py:68-87)
+ *   ctx   [2][B]   : click week, click hour                                          (sampler.py:106-107)
+ *   X [B*T,500] = [clip(item[seq]) + clip(pos[t]) | clip(content[seq])]; P [B*T,320]; D [B*T,64]; CT [B,128]
+ */
+int tcar_gather_fwd(const int32_t* idx, const int32_t* ctx, const float* item, const float* content,
+                    const float* pos, const float* month, const float* day, const float* week, const float* hour,
+                    const float* minute, const float* dur, float* X, float* P, float* D, float* CT, int B, int T,
+                    void* stream);
+
+/* (2) attention pooling forward -- modules.py:72-152 (count_alpha_m / count_alpha_s / *_attention_layer) after
+ *     the linear_3d projections.  U1/U2 hold the pre-activation sums on entry and sigmoid(.) on exit.
+ *     alpha [3][B*T] = nrm(e1), nrm(e2), nrm(e_t) with nrm(x) = exp(x)/(sum exp(x) + 1e-9)  (util.py:92-100). */
+int tcar_pool_fwd(const float* X, const float* P, float* U1, float* U2, const float* q, const float* w_r,
+                  const float* w_t, float* alpha, float* pooled, float* pooled_t, int B, int T, void* stream);
+
+/* (2b) attention pooling backward (gradient of (2) that tf.gradients derives, model_combine.py:156).
+ *      Outputs dU1/dU2 (pre-activation grads), dXi [B*T,250] (item half of dX only -- content is frozen),
+ *      dP [B*T,320], dq [B,500], de [3][B*T]. */
+int tcar_pool_bwd(const float* X, const float* P, const float* S1, const float* S2, const float* q,
+                  const float* w_r, const float* w_t, const float* alpha, const float* dpooled,
+                  const float* dpooled_t, float* dU1, float* dU2, float* dXi, float* dP, float* dq, float* de,
+                  int B, int T, void* stream);
+
+/* (3a) candidate matrix -- model_combine.py:86-92,135-136 restated as Iext [Npad,640] bf16 =
+ *      [item[1:] | content[1:] | one-hot(month,day,week,hour,minute bins) | 0]; rows >= N are zero. */
+int tcar_build_iext(const float* item, const float* content, const int32_t* mwdhm, void* iext_bf16, int N,
+                    int n_pad, void* stream);
+
+/* clip() of the 139 month/day/week/hour/minute rows: CT [139,64] and 1/max(norm,1) [139]. */
+int tcar_clip_time_tables(const float* month, const float* day, const float* week, const float* hour,
+                          const float* minute, float* ct_tab, float* ct_scale, void* stream);
+
+/* (3b) query operand: Tq [B,139] = a_pt . clip(tables)^T (fp32), Q [512,640] bf16 = [a_ic | Tq | 0] (rows >= B
+ *      zero), c_ref [B] = fp32 score of the label item = S[b, label[b]] (model_combine.py:138,145). */
+int tcar_build_query(const float* a_ic, const float* a_pt, const float* ct_tab, const float* item,
+                     const float* content, const int32_t* mwdhm, const int32_t* label, float* Tq, void* q_bf16,
+                     float* c_ref, int B, void* stream);
+
+/* (3c) full-catalog scoring S = Q . Iext^T on tcgen05 (model_combine.py:138), never materialising S.
+ *   mode 0 (train): E [512,n_pad] bf16 = exp(S - c_ref), rowsum_part [n_pad/128][512]
+ *   mode 1 (eval) : chunkmax [512, n_pad/8] fp32 = max of S over 8 consecutive items, rowsum_part as above
+ *   cluster in {1,2,4}: CTAs per cluster sharing each item tile by TMA multicast. */
+int tcar_score_fwd(const void* q_bf16, const void* iext_bf16, const float* c_ref, void* e_out, float* rowsum_part,
+                   float* chunkmax, int n_rows, int n_items, int n_pad, int mode, int cluster, void* stream);
+int tcar_score_fwd_tiles(int n_pad);
+
+/* (4a) softmax cross-entropy from the partial sums (model_combine.py:145): sumexp[b] = sum_tiles part,
+ *      ce[b] = log(sumexp[b]) (because c_ref is the label score). Fixed summation order. */
+int tcar_ce_finish(const float* rowsum_part, float* sumexp, float* ce, int n_tiles, int B, void* stream);
+
+/* (4b) negative-feedback loss (model_combine.py:142-143,147): neg[b] = -log(1 - sigmoid(sum_j I_ic[neg_bj].a_ic[b])
+ *      + 1e-24); loss[b] = ce[b] + 0.01 neg[b]; coef[b] = 0.01 d neg/d z; dA_neg[b,500] = coef[b] sum_j I_ic[neg_bj]. */
+int tcar_neg_loss(const float* a_ic, const float* item, const float* content, const int32_t* neg, const float* ce,
+                  float* negloss, float* loss, float* coef, float* dA_neg, int B, int Nn, void* stream);
+
+/* (3d) scoring backward wrt the query operand: dq_raw [512,640] = E . Iext (split-K partials in `part`,
+ *      [tcar_score_bwd_q_splits()][512][640], reduced in fixed order). */
+int tcar_score_bwd_q_splits(int n_rows, int n_pad);
+int tcar_score_bwd_q(const void* e_bf16, const void* iext_bf16, float* part, float* dq_raw, int n_rows, int n_pad,
+                     void* stream);
+
+/* (3e) assemble d a_ic, d a_pt, dTq from dq_raw (softmax part / sumexp, minus the label one-hot in fp32, plus the
+ *      negative-feedback part) and emit Qs [512,256] bf16 = a_ic[:, :250] / sumexp for (3f). */
+int tcar_score_bwd_finish(const float* dq_raw, const float* sumexp, const float* dA_neg, const float* a_ic,
+                          const float* ct_tab, const float* item, const float* content, const int32_t* mwdhm,
+                          const int32_t* label, float* d_a_ic, float* d_a_pt, float* dTq, void* qs_bf16, int B,
+                          void* stream);
+
+/* (3f) scoring backward wrt the item embeddings: g_item[n+1, :250] = sum_b E[b,n] Qs[b,:] (dense, overwrites). */
+int tcar_score_bwd_i(const void* e_bf16, const void* qs_bf16, float* g_item, int n_rows, int n_items, int n_pad,
+                     void* stream);
+
+/* (5a) gradients of the seven small embedding tables (pos, month, day, week, hour, minute, duration): sums the
+ *      gather-side, click-context-side and scoring-side contributions per table row in a fixed order, applies the
+ *      clip Jacobian once per row and writes g_* (same shapes as the tables). */
+int tcar_small_table_grads(const int32_t* idx, const int32_t* ctx, const float* dXi, const float* dP,
+                           const float* dD, const float* dCT, const float* dTq, const float* a_pt,
+                           const float* pos, const float* month, const float* day, const float* week,
+                           const float* hour, const float* minute, const float* dur, float* g_pos, float* g_month,
+                           float* g_day, float* g_week, float* g_hour, float* g_minute, float* g_dur, int B, int T,
+                           void* stream);
+
+/* (5b) deterministic scatter-add of the sparse item-row gradients into the dense g_item [N+1,256]:
+ *      clicked rows (clip Jacobian of dXi), label rows (-a_ic[:, :250]) and negative rows (coef a_ic[:, :250]).
+ *      Accumulation is exact int64 fixed point (2^-40) in a hash-slotted scratch, so the result does not depend
+ *      on the order in which duplicate rows arrive.  hash_keys [hash_size] int32 must be -1 and hash_acc
+ *      [hash_size][256] int64 must be 0 on entry; both are restored on exit.  hash_size: power of two. */
+int tcar_scatter_add_rows(const int32_t* seq, const int32_t* label, const int32_t* neg, const float* dXi,
+                          const float* a_ic, const float* coef, const float* item, float* g_item,
+                          int32_t* hash_keys, long long* hash_acc, int hash_size, int B, int T, int Nn,
+                          void* stream);
+
+/* (5c) per-tensor squared L2 norms (for tf.clip_by_norm, model_combine.py:158-160). seg_off [nseg+1]. */
+int tcar_sqnorm_segments(const float* flat, const int32_t* seg_off, float* sqnorm, int nseg, void* stream);
+int tcar_sqnorm_big(const float* x, float* partial, float* sqnorm, long long n, void* stream);
+
+/* (5d) clip_by_norm + TF-flavoured Adam (model_combine.py:155-163): lr_t = lr sqrt(1-b2^t)/(1-b1^t),
+ *      theta -= lr_t m / (sqrt(v) + eps).  `step` [1] int32 on device holds t (already incremented). */
+int tcar_adam_small(float* theta, float* m, float* v, const float* g, const int32_t* seg_off, const float* sqnorm,
+                    int nseg, const int32_t* step, float lr, float max_grad, void* stream);
+/* item table [N+1,256]: also refreshes the item columns of Iext (bf16) in the same pass. */
+int tcar_adam_item(float* item, float* m, float* v, const float* g, const float* sqnorm, const int32_t* step,
+                   float lr, float max_grad, void* iext_bf16, int N, void* stream);
+
+/* (6) evaluation (model_combine.py:283-306, util.py:8-18): select the 32 best chunks per query from chunkmax,
+ *     re-score their 256 items exactly in fp32, return top-20 ids/scores ordered by (score desc, id asc) and
+ *     n_greater[b] = #candidates scoring strictly above the label (rank-1 whenever rank <= 20).
+ *     chunkmax covers the N local items of this catalog shard; item/content/mwdhm are the GLOBAL fp32 tables,
+ *     label holds global 0-based ids and item_offset is the global id of local item 0. */
+int tcar_eval_topk(const float* chunkmax, const float* a_ic, const float* Tq, const float* item,
+                   const float* content, const int32_t* mwdhm, const int32_t* label, int32_t* top_ids,
+                   float* top_scores, int32_t* n_greater, int B, int N, int n_pad, int item_offset, void* stream);
+
+/* merge G per-shard top-20 lists [G][B][20] into the global top-20 (score desc, id asc). */
+int tcar_topk_merge(const int32_t* ids, const float* scores, int32_t* out_ids, float* out_scores, int G, int B,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TCAR_B200_H_ */

@@ -1,0 +1,88 @@
+"""ctypes binding of the C ABI declared in include/tcar_b200.h.
+
+There is deliberately NO fallback: if libtcar_b200.so is missing or a call fails, we raise.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtcar_b200.so")
+
+H, HP, TH, XW, PW, NBINS, KEXT, QROWS, MAXT, TOPK, CHUNK, NCAND_CHUNKS = 250, 256, 64, 500, 320, 139, 640, 512, 40, 20, 8, 32
+BIN_OFF = (0, 13, 45, 53, 78, 139)
+
+_P, _I, _F, _LL = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+
+# name -> argtypes (all return int)
+SIGNATURES = {
+    "tcar_gather_fwd": [_P] * 15 + [_I, _I, _P],
+    "tcar_pool_fwd": [_P] * 10 + [_I, _I, _P],
+    "tcar_pool_bwd": [_P] * 16 + [_I, _I, _P],
+    "tcar_build_iext": [_P] * 4 + [_I, _I, _P],
+    "tcar_clip_time_tables": [_P] * 7 + [_P],
+    "tcar_build_query": [_P] * 10 + [_I, _P],
+    "tcar_score_fwd": [_P] * 6 + [_I] * 5 + [_P],
+    "tcar_score_fwd_tiles": [_I],
+    "tcar_ce_finish": [_P] * 3 + [_I, _I, _P],
+    "tcar_neg_loss": [_P] * 9 + [_I, _I, _P],
+    "tcar_score_bwd_q_splits": [_I, _I],
+    "tcar_score_bwd_q": [_P] * 4 + [_I, _I, _P],
+    "tcar_score_bwd_finish": [_P] * 13 + [_I, _P],
+    "tcar_score_bwd_i": [_P] * 3 + [_I, _I, _I, _P],
+    "tcar_small_table_grads": [_P] * 22 + [_I, _I, _P],
+    "tcar_scatter_add_rows": [_P] * 10 + [_I] * 4 + [_P],
+    "tcar_sqnorm_segments": [_P] * 3 + [_I, _P],
+    "tcar_sqnorm_big": [_P] * 3 + [_LL, _P],
+    "tcar_adam_small": [_P] * 6 + [_I, _P, _F, _F, _P],
+    "tcar_adam_item": [_P] * 6 + [_F, _F, _P, _I, _P],
+    "tcar_eval_topk": [_P] * 10 + [_I] * 4 + [_P],
+    "tcar_topk_merge": [_P] * 4 + [_I, _I, _P],
+}
+
+_lib = None
+
+
+class TcarNativeError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise TcarNativeError(
+                f"{LIB_PATH} not found: build it with __graft_entry__.build() -- there is no CPU/PyTorch fallback")
+        l = C.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.argtypes = argtypes
+            fn.restype = C.c_int
+        _lib = l
+    return _lib
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def call(name, *args):
+    """Invoke a C-ABI entry point on the current torch stream; raise on a non-zero return code."""
+    rc = getattr(lib(), name)(*args, stream_ptr())
+    if rc != 0:
+        raise TcarNativeError(f"{name} failed with code {rc}")
+    return rc
+
+
+LAUNCHES = {"count": 0}
+
+
+def counted_call(name, nlaunch, *args):
+    LAUNCHES["count"] += nlaunch
+    return call(name, *args)

@@ -1,0 +1,197 @@
+// Candidate-matrix build, per-tensor gradient norms and the fused clip_by_norm + TF-Adam update.
+// Reference: model_combine.py:86-92,135-136 (candidate matrix), :155-163 (AdamOptimizer + clip_by_norm).
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <math.h>
+#include <stdint.h>
+#include "tcar_b200.h"
+
+namespace tcar {
+
+constexpr int H = TCAR_H, HP = TCAR_HP, KEXT = TCAR_KEXT;
+__device__ __constant__ int kBinOffO[6] = {0, 13, 45, 53, 78, 139};
+
+// Iext row n = [item[n+1, :250] | content[n+1, :250] | one-hot bins | 0]; one warp per row, 16-byte stores.
+__global__ void __launch_bounds__(256)
+build_iext_kernel(const float* __restrict__ item, const float* __restrict__ content,
+                  const int32_t* __restrict__ mwdhm, __nv_bfloat16* __restrict__ iext, int N, int n_pad) {
+    const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (n >= n_pad) return;
+    uint4* dst = reinterpret_cast<uint4*>(iext + (size_t)n * KEXT);  // 80 x 16 B per row
+    int bins[5] = {-1, -1, -1, -1, -1};
+    if (n < N)
+        for (int k = 0; k < 5; ++k) bins[k] = 2 * H + kBinOffO[k] + mwdhm[(size_t)n * 5 + k];
+    for (int g = lane; g < KEXT / 8; g += 32) {
+        __nv_bfloat16 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = g * 8 + j;
+            float x = 0.f;
+            if (n < N) {
+                if (c < H) x = item[((size_t)n + 1) * HP + c];
+                else if (c < 2 * H) x = content[((size_t)n + 1) * HP + (c - H)];
+                else x = (c == bins[0] || c == bins[1] || c == bins[2] || c == bins[3] || c == bins[4]) ? 1.f : 0.f;
+            }
+            v[j] = __float2bfloat16(x);
+        }
+        dst[g] = *reinterpret_cast<uint4*>(v);
+    }
+}
+
+// one CTA per segment (tensor) of a flat fp32 buffer: fixed-order sum of squares
+__global__ void __launch_bounds__(1024)
+sqnorm_segments_kernel(const float* __restrict__ flat, const int32_t* __restrict__ seg_off, float* __restrict__ out) {
+    __shared__ float red[32];
+    const int s = blockIdx.x;
+    const int lo = seg_off[s], hi = seg_off[s + 1];
+    float acc = 0.f;
+    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) acc = fmaf(flat[i], flat[i], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 32; ++i) t += red[i];
+        out[s] = t;
+    }
+}
+
+constexpr int kNormBlocks = 1184;  // 8 x 148 SMs
+__global__ void __launch_bounds__(256)
+sqnorm_big_partial_kernel(const float4* __restrict__ x, float* __restrict__ partial, long long n4) {
+    __shared__ float red[8];
+    float acc = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = x[i];
+        acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        partial[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(1024)
+sqnorm_big_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int n) {
+    __shared__ float red[32];
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partial[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 32; ++i) t += red[i];
+        out[0] = t;
+    }
+}
+
+// tf.clip_by_norm(g, c) = g * c / max(||g||, c);  TF Adam: lr_t = lr sqrt(1-b2^t)/(1-b1^t); p -= lr_t m/(sqrt(v)+eps)
+__device__ __forceinline__ float clip_factor(float sqnorm, float max_grad) {
+    const float n = sqrtf(sqnorm);
+    return max_grad / fmaxf(n, max_grad);
+}
+__device__ __forceinline__ float adam_lr_t(int t, float lr) {
+    const float b1t = powf(0.9f, (float)t), b2t = powf(0.999f, (float)t);
+    return lr * sqrtf(1.f - b2t) / (1.f - b1t);
+}
+__device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g, float lr_t) {
+    m = m + (g - m) * (1.f - 0.9f);
+    v = v + (g * g - v) * (1.f - 0.999f);
+    p -= lr_t * m / (sqrtf(v) + 1e-8f);
+}
+
+__global__ void __launch_bounds__(256)
+adam_small_kernel(float* __restrict__ theta, float* __restrict__ m, float* __restrict__ v,
+                  const float* __restrict__ g, const int32_t* __restrict__ seg_off,
+                  const float* __restrict__ sqnorm, const int32_t* __restrict__ step, float lr, float max_grad) {
+    const int s = blockIdx.y;
+    const int lo = seg_off[s], hi = seg_off[s + 1];
+    const float cf = clip_factor(sqnorm[s], max_grad);
+    const float lr_t = adam_lr_t(step[0], lr);
+    for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
+        float p = theta[i], mm = m[i], vv = v[i];
+        adam_update(p, mm, vv, g[i] * cf, lr_t);
+        theta[i] = p; m[i] = mm; v[i] = vv;
+    }
+}
+
+// item table [N+1, 256]: one float4 per thread per step; also re-quantises the row into Iext (bf16).
+__global__ void __launch_bounds__(256)
+adam_item_kernel(float4* __restrict__ item, float4* __restrict__ m, float4* __restrict__ v,
+                 const float4* __restrict__ g, const float* __restrict__ sqnorm, const int32_t* __restrict__ step,
+                 float lr, float max_grad, __nv_bfloat16* __restrict__ iext, long long n4) {
+    const float cf = clip_factor(sqnorm[0], max_grad);
+    const float lr_t = adam_lr_t(step[0], lr);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 p = item[i], mm = m[i], vv = v[i];
+        const float4 gg = g[i];
+        adam_update(p.x, mm.x, vv.x, gg.x * cf, lr_t);
+        adam_update(p.y, mm.y, vv.y, gg.y * cf, lr_t);
+        adam_update(p.z, mm.z, vv.z, gg.z * cf, lr_t);
+        adam_update(p.w, mm.w, vv.w, gg.w * cf, lr_t);
+        item[i] = p; m[i] = mm; v[i] = vv;
+        const long long row = i >> 6;            // 64 float4 per 256-float row
+        const int c = (int)(i & 63) * 4;
+        if (row >= 1 && c < H) {
+            __nv_bfloat16* dst = iext + (size_t)(row - 1) * KEXT + c;
+            __nv_bfloat162 lo = __floats2bfloat162_rn(p.x, p.y);
+            *reinterpret_cast<__nv_bfloat162*>(dst) = lo;
+            if (c + 2 < H) *reinterpret_cast<__nv_bfloat162*>(dst + 2) = __floats2bfloat162_rn(p.z, p.w);
+        }
+    }
+}
+
+}  // namespace tcar
+
+using namespace tcar;
+#define STREAM static_cast<cudaStream_t>(stream)
+
+extern "C" int tcar_build_iext(const float* item, const float* content, const int32_t* mwdhm, void* iext_bf16, int N,
+                               int n_pad, void* stream) {
+    if (N < 1 || n_pad < N || n_pad % 256) return TCAR_ERR_ARG;
+    build_iext_kernel<<<(n_pad + 7) / 8, 256, 0, STREAM>>>(item, content, mwdhm,
+                                                           static_cast<__nv_bfloat16*>(iext_bf16), N, n_pad);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int tcar_sqnorm_segments(const float* flat, const int32_t* seg_off, float* sqnorm, int nseg,
+                                    void* stream) {
+    if (nseg < 1) return TCAR_ERR_ARG;
+    sqnorm_segments_kernel<<<nseg, 1024, 0, STREAM>>>(flat, seg_off, sqnorm);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int tcar_sqnorm_big(const float* x, float* partial, float* sqnorm, long long n, void* stream) {
+    if (n % 4) return TCAR_ERR_ARG;
+    sqnorm_big_partial_kernel<<<kNormBlocks, 256, 0, STREAM>>>(reinterpret_cast<const float4*>(x), partial, n / 4);
+    int rc = (int)cudaGetLastError();
+    if (rc) return rc;
+    sqnorm_big_final_kernel<<<1, 1024, 0, STREAM>>>(partial, sqnorm, kNormBlocks);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int tcar_adam_small(float* theta, float* m, float* v, const float* g, const int32_t* seg_off,
+                               const float* sqnorm, int nseg, const int32_t* step, float lr, float max_grad,
+                               void* stream) {
+    if (nseg < 1) return TCAR_ERR_ARG;
+    adam_small_kernel<<<dim3(64, nseg), 256, 0, STREAM>>>(theta, m, v, g, seg_off, sqnorm, step, lr, max_grad);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int tcar_adam_item(float* item, float* m, float* v, const float* g, const float* sqnorm,
+                              const int32_t* step, float lr, float max_grad, void* iext_bf16, int N, void* stream) {
+    if (N < 1) return TCAR_ERR_ARG;
+    const long long n4 = (long long)(N + 1) * (HP / 4);
+    adam_item_kernel<<<148 * 16, 256, 0, STREAM>>>(reinterpret_cast<float4*>(item), reinterpret_cast<float4*>(m),
+                                                   reinterpret_cast<float4*>(v), reinterpret_cast<const float4*>(g),
+                                                   sqnorm, step, lr, max_grad,
+                                                   static_cast<__nv_bfloat16*>(iext_bf16), n4);
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,667 @@
+// Full-catalog scoring on 5th-gen tensor cores (tcgen05 + TMEM + TMA), sm_100a only.
+//
+// Replaces the reference's k9/k10/k13 call sites (model_combine.py:132-138 scoring matmul, :145 softmax CE,
+// :283-301 eval scores) and the two scoring-matmul gradients TF derives from them (model_combine.py:156).
+//
+// Data layout:
+//   Q    [512, 640]  bf16  session operand  [a_ic(500) | T(139) | 0]      (T = a_pt . clip(time tables)^T)
+//   Iext [Npad, 640] bf16  item operand     [item(250) | content(250) | onehot(139) | 0], rows >= N are zero
+//   E    [512, Npad] bf16  exp(S - c_b), written by the forward kernel in train mode, read by both backward GEMMs
+//
+//   score_fwd   : S = Q . Iext^T, 128 sessions (TMEM lanes) x 128 items per tile, K = 640 resident in smem for Q,
+//                 item tiles TMA-multicast across a cluster of CL CTAs (CL session tiles share every item tile).
+//                 epilogue TRAIN: E = exp(S - c_b) -> bf16 store, per-(tile,row) partial sums of E
+//                 epilogue EVAL : partial sums of E (for the CE "avg loss") + max over each 8 consecutive items
+//   score_bwd_q : dQ[b,c]   = sum_n E[b,n] Iext[n,c]      (split over n, partials reduced by a second kernel)
+//   score_bwd_i : dItem[n,c] = sum_b E[b,n] Qs[b,c]       (Qs = a_ic / sumexp_b in bf16, c < 256)
+#include "sm100_ptx.cuh"
+#include "tcar_b200.h"
+
+namespace tcar {
+
+constexpr int kThreads = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int KEXT = TCAR_KEXT;  // 640
+constexpr int NKB = KEXT / BK;   // 10
+constexpr int QROWS = TCAR_QROWS;  // 512
+constexpr float kLog2e = 1.4426950408889634f;
+
+// ------------------------------------------------------------------------------------------------ forward
+constexpr int F_BN = 128;
+constexpr int F_STAGES = 4;
+constexpr int F_NACC = 4;
+constexpr int F_A_BYTES = BM * KEXT * 2;        // 163840
+constexpr int F_B_STAGE = F_BN * BK * 2;        // 16384
+constexpr int F_SMEM = F_A_BYTES + F_STAGES * F_B_STAGE + 1024 /*align*/ + 256 /*barriers*/;
+
+struct FwdParams {
+    __nv_bfloat16* E;       // [512, e_pitch] (train) or nullptr
+    float* rowsum_part;     // [n_tiles, 512]
+    float* chunkmax;        // [512, e_pitch/8] (eval) or nullptr
+    const float* c_ref;     // [512] reference score per row (exp argument shift)
+    int n_items;            // valid items N
+    int n_tiles;            // ceil(Npad / F_BN)
+    int n_rows;             // valid sessions B
+    int e_pitch;            // Npad
+    int groups;             // number of session groups (ceil(ceil(B/128)/CL))
+    int mode;               // 0 = train, 1 = eval
+};
+
+template <int CL>
+__global__ void __launch_bounds__(kThreads, 1)
+score_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_i,
+                 const FwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + F_A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + F_STAGES * F_B_STAGE);
+    uint64_t* full = bars;                      // [F_STAGES]
+    uint64_t* empty = bars + F_STAGES;          // [F_STAGES]
+    uint64_t* acc_full = bars + 2 * F_STAGES;   // [F_NACC]
+    uint64_t* acc_empty = acc_full + F_NACC;    // [F_NACC]
+    uint64_t* a_full = acc_empty + F_NACC;      // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
+
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t lane = lane_id();
+    const uint32_t rank = (CL > 1) ? cluster_ctarank() : 0u;
+    const uint32_t cluster_id = blockIdx.x / CL;
+    const uint32_t n_clusters = gridDim.x / CL;
+    // static schedule: cluster -> (session group, strided item tiles) so that Q stays resident
+    const uint32_t grp = cluster_id % p.groups;
+    const uint32_t tile0 = cluster_id / p.groups;
+    const uint32_t tile_step = n_clusters / p.groups;
+    const uint32_t mtile = grp * CL + rank;
+    const uint32_t my_tiles =
+        tile0 < (uint32_t)p.n_tiles ? ((uint32_t)p.n_tiles - tile0 + tile_step - 1) / tile_step : 0u;
+
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&map_q);
+        tma_prefetch_desc(&map_i);
+    }
+    if (warp == 1 && elect_one()) {
+        for (int i = 0; i < F_STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], CL);
+        }
+        for (int i = 0; i < F_NACC; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 4);
+        }
+        mbar_init(a_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    if (CL > 1) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (elect_one()) {
+            mbar_expect_tx(a_full, F_A_BYTES);
+            for (int kb = 0; kb < NKB; ++kb)
+                tma_load_2d(smem_a + kb * (BM * BK * 2), &map_q, a_full, kb * BK, mtile * BM);
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t it = 0; it < my_tiles; ++it) {
+                const int n0 = (tile0 + it * tile_step) * F_BN;
+                for (int kb = 0; kb < NKB; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], F_B_STAGE);
+                    uint8_t* dst = smem_b + stage * F_B_STAGE + rank * (F_B_STAGE / CL);
+                    if (CL > 1)
+                        tma_load_2d_mcast(dst, &map_i, &full[stage], kb * BK, n0 + rank * (F_BN / CL),
+                                          (uint16_t)((1u << CL) - 1));
+                    else
+                        tma_load_2d(dst, &map_i, &full[stage], kb * BK, n0);
+                    if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        constexpr uint32_t idesc = make_idesc_bf16(BM, F_BN, 0, 0);
+        mbar_wait(a_full, 0);
+        tc_fence_after();
+        uint32_t stage = 0, phase = 0;
+        for (uint32_t it = 0; it < my_tiles; ++it) {
+            const uint32_t acc = it % F_NACC;
+            const uint32_t acc_phase = (it / F_NACC) & 1;
+            mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            for (int kb = 0; kb < NKB; ++kb) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t a_addr = smem_u32(smem_a + kb * (BM * BK * 2));
+                    const uint32_t b_addr = smem_u32(smem_b + stage * F_B_STAGE);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_bf16(tmem_base + acc * F_BN, sdesc_kmajor(a_addr + k * 32), sdesc_kmajor(b_addr + k * 32),
+                                  idesc, (kb | k) != 0);
+                    if (CL > 1) umma_commit_mcast(&empty[stage], (uint16_t)((1u << CL) - 1));
+                    else umma_commit(&empty[stage]);
+                    if (kb == NKB - 1) umma_commit(&acc_full[acc]);
+                }
+                __syncwarp();
+                if (++stage == F_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue: thread <-> session row =================
+        const uint32_t q = warp - 4;
+        const uint32_t row = mtile * BM + q * 32 + lane;
+        const bool row_ok = row < (uint32_t)p.n_rows;
+        // rows in [B, round_up(B,64)) are stored as zeros: they are K-padding of the dItem GEMM
+        const bool store_ok = row < (((uint32_t)p.n_rows + 63u) & ~63u);
+        const float cshift = row_ok ? p.c_ref[row] * kLog2e : 0.f;
+        for (uint32_t it = 0; it < my_tiles; ++it) {
+            const uint32_t acc = it % F_NACC;
+            const uint32_t acc_phase = (it / F_NACC) & 1;
+            const uint32_t tile = tile0 + it * tile_step;
+            const int n0 = tile * F_BN;
+            mbar_wait(&acc_full[acc], acc_phase);
+            tc_fence_after();
+            float psum = 0.f;
+            const bool tail = n0 + F_BN > p.n_items;
+#pragma unroll 1
+            for (int ch = 0; ch < F_BN / 32; ++ch) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((q * 32) << 16) + acc * F_BN + ch * 32, v);
+                tmem_ld_wait();
+                const int nb = n0 + ch * 32;
+                float e[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float s = __uint_as_float(v[j]);
+                    float ex = exp2f(fmaf(s, kLog2e, -cshift));
+                    if (!row_ok || (tail && nb + j >= p.n_items)) ex = 0.f;
+                    e[j] = ex;
+                    psum += ex;
+                }
+                if (p.mode == 0) {
+                  if (store_ok) {
+                    uint4* dst = reinterpret_cast<uint4*>(p.E + (size_t)row * p.e_pitch + nb);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint4 o;
+                        o.x = pack_bf16(e[g * 8 + 0], e[g * 8 + 1]);
+                        o.y = pack_bf16(e[g * 8 + 2], e[g * 8 + 3]);
+                        o.z = pack_bf16(e[g * 8 + 4], e[g * 8 + 5]);
+                        o.w = pack_bf16(e[g * 8 + 6], e[g * 8 + 7]);
+                        dst[g] = o;
+                    }
+                  }
+                } else {
+                    float4 m;
+                    float* mm = reinterpret_cast<float*>(&m);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        float mx = -INFINITY;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float s = __uint_as_float(v[g * 8 + j]);
+                            const bool ok = !(tail && nb + g * 8 + j >= p.n_items);
+                            mx = ok ? fmaxf(mx, s) : mx;
+                        }
+                        mm[g] = mx;
+                    }
+                    if (row_ok)
+                        *reinterpret_cast<float4*>(p.chunkmax + (size_t)row * (p.e_pitch / 8) + nb / 8) = m;
+                }
+            }
+            // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+            if (row_ok) p.rowsum_part[(size_t)tile * QROWS + row] = psum;
+        }
+    }
+
+    tc_fence_before();
+    if (CL > 1) cluster_sync_all(); else __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------ dQ = E . Iext
+constexpr int Q_CH = 320;                 // feature columns per CTA (half of KEXT): one N=256 + one N=64 MMA
+constexpr int Q_STAGES = 4;
+constexpr int Q_A_STAGE = BM * BK * 2;    // 16384  E tile [128 b x 64 n], K-major
+constexpr int Q_B_STAGE = Q_CH * BK * 2;  // 40960  Iext tile [64 n x 320 c], MN-major: 5 boxes of [64 c x 64 n]
+constexpr int Q_STAGE = Q_A_STAGE + Q_B_STAGE;
+constexpr int Q_SMEM = Q_STAGES * Q_STAGE + 1024 + 256;
+
+struct BwdQParams {
+    float* part;     // [splits, 512, 640]
+    int kb_total;    // Npad / 64
+    int kb_per;      // K blocks per split
+    int splits;
+    int mtiles;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+score_bwd_q_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant__ CUtensorMap map_i,
+                   const BwdQParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Q_STAGES * Q_STAGE);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + Q_STAGES;
+    uint64_t* acc_full = bars + 2 * Q_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t lane = lane_id();
+    // unit = (split, mtile, chalf)
+    const uint32_t unit = blockIdx.x;
+    const uint32_t chalf = unit & 1;
+    const uint32_t mtile = (unit >> 1) % p.mtiles;
+    const uint32_t split = (unit >> 1) / p.mtiles;
+    const int kb0 = split * p.kb_per;
+    const int kb1 = min(kb0 + p.kb_per, p.kb_total);
+    const int nkb = max(kb1 - kb0, 0);
+
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&map_e);
+        tma_prefetch_desc(&map_i);
+    }
+    if (warp == 1 && elect_one()) {
+        for (int i = 0; i < Q_STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(acc_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            uint32_t stage = 0, phase = 0;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                mbar_expect_tx(&full[stage], Q_STAGE);
+                uint8_t* sa = smem + stage * Q_STAGE;
+                uint8_t* sb = sa + Q_A_STAGE;
+                tma_load_2d(sa, &map_e, &full[stage], kb * BK, mtile * BM);
+#pragma unroll
+                for (int j = 0; j < Q_CH / 64; ++j)
+                    tma_load_2d(sb + j * 8192, &map_i, &full[stage], chalf * Q_CH + j * 64, kb * BK);
+                if (++stage == Q_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc256 = make_idesc_bf16(BM, 256, 0, 1);
+        constexpr uint32_t idesc64 = make_idesc_bf16(BM, 64, 0, 1);
+        uint32_t stage = 0, phase = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t a_addr = smem_u32(smem + stage * Q_STAGE);
+                const uint32_t b_addr = a_addr + Q_A_STAGE;
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    const uint32_t accum = (kb != kb0 || k != 0);
+                    const uint64_t ad = sdesc_kmajor(a_addr + k * 32);
+                    umma_bf16(tmem_base, ad, sdesc_mnmajor(b_addr + k * 2048, 8192), idesc256, accum);
+                    umma_bf16(tmem_base + 256, ad, sdesc_mnmajor(b_addr + 4 * 8192 + k * 2048, 8192), idesc64, accum);
+                }
+                umma_commit(&empty[stage]);
+                if (kb == kb1 - 1) umma_commit(acc_full);
+            }
+            __syncwarp();
+            if (++stage == Q_STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp >= 4) {
+        const uint32_t q = warp - 4;
+        const uint32_t row = mtile * BM + q * 32 + lane;
+        float* dst = p.part + ((size_t)split * QROWS + row) * KEXT + chalf * Q_CH;
+        if (nkb > 0) {
+            mbar_wait(acc_full, 0);
+            tc_fence_after();
+        }
+#pragma unroll 1
+        for (int ch = 0; ch < Q_CH / 32; ++ch) {
+            uint32_t v[32];
+            if (nkb > 0) {
+                tmem_ld32(tmem_base + ((q * 32) << 16) + ch * 32, v);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0u;
+            }
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+                reinterpret_cast<uint4*>(dst + ch * 32)[g] = make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// Fixed-order reduction of the split partials: out[b, c] = sum_s part[s, b, c].
+__global__ void reduce_splits_kernel(const float* __restrict__ part, float* __restrict__ out, int splits,
+                                     int stride, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += part[(size_t)s * stride + i];
+    out[i] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------ dItem = E^T . Qs
+constexpr int I_BN = 128;                   // feature columns per CTA (half of the 256-pitch item row)
+constexpr int I_STAGES = 6;
+constexpr int I_A_STAGE = BM * BK * 2;      // 16384  E tile [64 b x 128 n], MN-major: 2 boxes of [64 n x 64 b]
+constexpr int I_B_KB = I_BN * BK * 2;       // 16384  Qs tile [64 b x 128 c], MN-major: 2 boxes of [64 c x 64 b]
+constexpr int I_NACC = 4;
+constexpr int I_SMEM = 8 * I_B_KB + I_STAGES * I_A_STAGE + 1024 + 256;
+
+struct BwdIParams {
+    float* g_item;   // [N+1, 256] dense item-table gradient (row 0 = pad item)
+    int n_items;
+    int n_tiles;     // ceil(Npad / 128)
+    int nkb;         // ceil(B / 64)
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+score_bwd_i_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant__ CUtensorMap map_qs,
+                   const BwdIParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_b = smem;                         // resident Qs half: nkb x 16 KB
+    uint8_t* smem_a = smem + 8 * I_B_KB;            // E stages
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_a + I_STAGES * I_A_STAGE);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + I_STAGES;
+    uint64_t* acc_full = bars + 2 * I_STAGES;
+    uint64_t* acc_empty = acc_full + I_NACC;
+    uint64_t* b_full = acc_empty + I_NACC;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t lane = lane_id();
+    const uint32_t chalf = blockIdx.x & 1;
+    const uint32_t tile0 = blockIdx.x >> 1;
+    const uint32_t tile_step = gridDim.x >> 1;
+    const uint32_t my_tiles =
+        tile0 < (uint32_t)p.n_tiles ? ((uint32_t)p.n_tiles - tile0 + tile_step - 1) / tile_step : 0u;
+    const int nkb = p.nkb;
+
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&map_e);
+        tma_prefetch_desc(&map_qs);
+    }
+    if (warp == 1 && elect_one()) {
+        for (int i = 0; i < I_STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < I_NACC; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 4);
+        }
+        mbar_init(b_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_expect_tx(b_full, nkb * I_B_KB);
+            for (int kb = 0; kb < nkb; ++kb)
+                for (int j = 0; j < 2; ++j)
+                    tma_load_2d(smem_b + kb * I_B_KB + j * 8192, &map_qs, b_full, chalf * I_BN + j * 64, kb * BK);
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t it = 0; it < my_tiles; ++it) {
+                const int n0 = (tile0 + it * tile_step) * BM;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], I_A_STAGE);
+                    uint8_t* sa = smem_a + stage * I_A_STAGE;
+                    tma_load_2d(sa, &map_e, &full[stage], n0, kb * BK);
+                    tma_load_2d(sa + 8192, &map_e, &full[stage], n0 + 64, kb * BK);
+                    if (++stage == I_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc_bf16(BM, I_BN, 1, 1);
+        mbar_wait(b_full, 0);
+        tc_fence_after();
+        uint32_t stage = 0, phase = 0;
+        for (uint32_t it = 0; it < my_tiles; ++it) {
+            const uint32_t acc = it % I_NACC;
+            const uint32_t acc_phase = (it / I_NACC) & 1;
+            mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t a_addr = smem_u32(smem_a + stage * I_A_STAGE);
+                    const uint32_t b_addr = smem_u32(smem_b + kb * I_B_KB);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_bf16(tmem_base + acc * I_BN, sdesc_mnmajor(a_addr + k * 2048, 8192),
+                                  sdesc_mnmajor(b_addr + k * 2048, 8192), idesc, (kb | k) != 0);
+                    umma_commit(&empty[stage]);
+                    if (kb == nkb - 1) umma_commit(&acc_full[acc]);
+                }
+                __syncwarp();
+                if (++stage == I_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // thread <-> item row
+        const uint32_t q = warp - 4;
+        for (uint32_t it = 0; it < my_tiles; ++it) {
+            const uint32_t acc = it % I_NACC;
+            const uint32_t acc_phase = (it / I_NACC) & 1;
+            const int n = (tile0 + it * tile_step) * BM + q * 32 + lane;
+            mbar_wait(&acc_full[acc], acc_phase);
+            tc_fence_after();
+            float* dst = p.g_item + ((size_t)n + 1) * 256 + chalf * I_BN;
+#pragma unroll 1
+            for (int ch = 0; ch < I_BN / 32; ++ch) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((q * 32) << 16) + acc * I_BN + ch * 32, v);
+                tmem_ld_wait();
+                if (n < p.n_items) {
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        uint4 o = make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                        const int c = chalf * I_BN + ch * 32 + g * 4;
+                        if (c + 0 >= TCAR_H) o.x = 0u;   // pad columns 250..255 carry no parameter
+                        if (c + 1 >= TCAR_H) o.y = 0u;
+                        if (c + 2 >= TCAR_H) o.z = 0u;
+                        if (c + 3 >= TCAR_H) o.w = 0u;
+                        reinterpret_cast<uint4*>(dst + ch * 32)[g] = o;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// 2-D bf16 row-major tensor [rows, cols] (cols contiguous, pitch in elements); box = [box_cols, box_rows], SW128.
+static int make_map_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
+                         uint32_t box_cols, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return TCAR_ERR_DRIVER;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {pitch_elems * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : TCAR_ERR_TENSORMAP;
+}
+
+static int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    }
+    return n;
+}
+
+template <int CL>
+static int launch_fwd(const CUtensorMap& mq, const CUtensorMap& mi, const FwdParams& p, int n_clusters,
+                      cudaStream_t stream) {
+    cudaError_t e = cudaFuncSetAttribute(score_fwd_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_clusters * CL);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = F_SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, score_fwd_kernel<CL>, mq, mi, p);
+    return (int)e;
+}
+
+}  // namespace tcar
+
+using namespace tcar;
+
+extern "C" int tcar_score_fwd(const void* q_bf16, const void* iext_bf16, const float* c_ref, void* e_out,
+                              float* rowsum_part, float* chunkmax, int n_rows, int n_items, int n_pad, int mode,
+                              int cluster, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (n_rows < 1 || n_rows > QROWS || n_pad % 256 != 0 || n_items > n_pad) return TCAR_ERR_ARG;
+    if (cluster != 1 && cluster != 2 && cluster != 4) return TCAR_ERR_ARG;
+    if ((mode == 0 && !e_out) || (mode == 1 && !chunkmax)) return TCAR_ERR_ARG;
+    CUtensorMap mq, mi;
+    int rc = make_map_bf16(&mq, q_bf16, QROWS, KEXT, KEXT, BK, BM);
+    if (rc) return rc;
+    rc = make_map_bf16(&mi, iext_bf16, n_pad, KEXT, KEXT, BK, F_BN / cluster);
+    if (rc) return rc;
+    FwdParams p;
+    p.E = static_cast<__nv_bfloat16*>(e_out);
+    p.rowsum_part = rowsum_part;
+    p.chunkmax = chunkmax;
+    p.c_ref = c_ref;
+    p.n_items = n_items;
+    p.n_tiles = n_pad / F_BN;
+    p.n_rows = n_rows;
+    p.e_pitch = n_pad;
+    const int mtiles = (n_rows + BM - 1) / BM;
+    p.groups = (mtiles + cluster - 1) / cluster;
+    p.mode = mode;
+    // cluster size 4 can only be co-scheduled on 132 of the 148 SMs (GPCs with 18 SMs strand two)
+    int max_clusters = sm_count() / cluster;
+    if (cluster == 4) max_clusters = (sm_count() * 132 / 148) / 4;
+    int n_clusters = (max_clusters / p.groups) * p.groups;
+    if (n_clusters < p.groups) n_clusters = p.groups;
+    const int per_group = n_clusters / p.groups;
+    if (per_group > p.n_tiles) n_clusters = p.n_tiles * p.groups;
+    if (cluster == 1) return launch_fwd<1>(mq, mi, p, n_clusters, stream);
+    if (cluster == 2) return launch_fwd<2>(mq, mi, p, n_clusters, stream);
+    return launch_fwd<4>(mq, mi, p, n_clusters, stream);
+}
+
+extern "C" int tcar_score_fwd_tiles(int n_pad) { return n_pad / F_BN; }
+
+extern "C" int tcar_score_bwd_q_splits(int n_rows, int n_pad) {
+    const int mtiles = (n_rows + BM - 1) / BM;
+    int splits = sm_count() / (2 * mtiles);
+    const int kb_total = n_pad / BK;
+    if (splits > kb_total) splits = kb_total;
+    if (splits < 1) splits = 1;
+    return splits;
+}
+
+extern "C" int tcar_score_bwd_q(const void* e_bf16, const void* iext_bf16, float* part, float* dq, int n_rows,
+                                int n_pad, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (n_rows < 1 || n_rows > QROWS || n_pad % 256 != 0) return TCAR_ERR_ARG;
+    CUtensorMap me, mi;
+    int rc = make_map_bf16(&me, e_bf16, QROWS, n_pad, n_pad, BK, BM);
+    if (rc) return rc;
+    rc = make_map_bf16(&mi, iext_bf16, n_pad, KEXT, KEXT, 64, BK);
+    if (rc) return rc;
+    BwdQParams p;
+    p.part = part;
+    p.mtiles = (n_rows + BM - 1) / BM;
+    p.splits = tcar_score_bwd_q_splits(n_rows, n_pad);
+    p.kb_total = n_pad / BK;
+    p.kb_per = (p.kb_total + p.splits - 1) / p.splits;
+    cudaError_t e = cudaFuncSetAttribute(score_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    score_bwd_q_kernel<<<p.splits * p.mtiles * 2, kThreads, Q_SMEM, stream>>>(me, mi, p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    // partial layout is [split][512][640]; rows of m-tiles that were not computed are never read by callers
+    const int total = p.mtiles * BM * KEXT;
+    reduce_splits_kernel<<<(total + 255) / 256, 256, 0, stream>>>(part, dq, p.splits, QROWS * KEXT, total);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int tcar_score_bwd_i(const void* e_bf16, const void* qs_bf16, float* g_item, int n_rows, int n_items,
+                                int n_pad, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (n_rows < 1 || n_rows > QROWS || n_pad % 256 != 0) return TCAR_ERR_ARG;
+    CUtensorMap me, mq;
+    int rc = make_map_bf16(&me, e_bf16, QROWS, n_pad, n_pad, 64, BK);
+    if (rc) return rc;
+    rc = make_map_bf16(&mq, qs_bf16, QROWS, 256, 256, 64, BK);
+    if (rc) return rc;
+    BwdIParams p;
+    p.g_item = g_item;
+    p.n_items = n_items;
+    p.n_tiles = n_pad / BM;
+    p.nkb = (n_rows + BK - 1) / BK;
+    cudaError_t e = cudaFuncSetAttribute(score_bwd_i_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    int grid = (sm_count() / 2) * 2;
+    if (grid > 2 * p.n_tiles) grid = 2 * p.n_tiles;
+    score_bwd_i_kernel<<<grid, kThreads, I_SMEM, stream>>>(me, mq, p);
+    return (int)cudaGetLastError();
+}

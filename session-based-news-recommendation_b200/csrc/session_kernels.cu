@@ -1,0 +1,669 @@
+// Session-side kernels of the TCAR hot path (HBM / latency bound, fp32): fused gather with max_norm clip,
+// attention pooling forward / backward, query-operand build, losses, and the gradient plumbing around the
+// scoring GEMMs.  Reference call sites are cited per kernel; formulas follow SURVEY.md Appendix A.
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <math.h>
+#include <stdint.h>
+#include "tcar_b200.h"
+
+namespace tcar {
+
+constexpr int H = TCAR_H, HP = TCAR_HP, TH = TCAR_TH, XW = TCAR_XW, PW = TCAR_PW, NB = TCAR_NBINS;
+__device__ __constant__ int kBinOff[6] = {0, 13, 45, 53, 78, 139};  // month, day, week, hour, minute row offsets
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// fixed-order block reduction (result valid in all threads); `red` >= 32 floats of shared memory
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int i = 0; i < nw; ++i) t += red[i];
+    return t;
+}
+// tf.nn.embedding_lookup(max_norm=1) scale: 1 / max(||x||, 1)            (modules.py:36)
+__device__ __forceinline__ float clip_scale(float sq) {
+    const float n = sqrtf(sq);
+    return n > 1.f ? 1.f / n : 1.f;
+}
+
+// ------------------------------------------------------------------------------------------------ (1) gather
+// one warp per click (rows of X/P/D) and one warp per session for the click-time context CT.
+__global__ void __launch_bounds__(256)
+gather_fwd_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ ctx, const float* __restrict__ item,
+                  const float* __restrict__ content, const float* __restrict__ pos,
+                  const float* __restrict__ month, const float* __restrict__ day, const float* __restrict__ week,
+                  const float* __restrict__ hour, const float* __restrict__ minute, const float* __restrict__ dur,
+                  float* __restrict__ X, float* __restrict__ P, float* __restrict__ D, float* __restrict__ CT, int B,
+                  int T) {
+    const int M = B * T;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w < M) {
+        const int m = w, t = m % T;
+        const int id = idx[m];
+        // item + content rows: 256-float pitch, two 128-bit loads per lane each
+        const float4* ir = reinterpret_cast<const float4*>(item + (size_t)id * HP);
+        const float4* cr = reinterpret_cast<const float4*>(content + (size_t)id * HP);
+        const float4 i0 = __ldg(ir + lane), i1 = __ldg(ir + 32 + lane);
+        const float4 c0 = __ldg(cr + lane), c1 = __ldg(cr + 32 + lane);
+        const float si = clip_scale(warp_sum(i0.x * i0.x + i0.y * i0.y + i0.z * i0.z + i0.w * i0.w + i1.x * i1.x +
+                                             i1.y * i1.y + i1.z * i1.z + i1.w * i1.w));
+        const float sc = clip_scale(warp_sum(c0.x * c0.x + c0.y * c0.y + c0.z * c0.z + c0.w * c0.w + c1.x * c1.x +
+                                             c1.y * c1.y + c1.z * c1.z + c1.w * c1.w));
+        // position row t (unpadded [40,250])
+        const float* pr = pos + (size_t)t * H;
+        float pv[8];
+        float psq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = (j < 4) ? lane * 4 + j : 128 + lane * 4 + (j - 4);
+            pv[j] = c < H ? __ldg(pr + c) : 0.f;
+            psq += pv[j] * pv[j];
+        }
+        const float sp = clip_scale(warp_sum(psq));
+        float* xr = X + (size_t)m * XW;
+        const float iv[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+        const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = (j < 4) ? lane * 4 + j : 128 + lane * 4 + (j - 4);
+            if (c < H) {
+                xr[c] = iv[j] * si + pv[j] * sp;
+                xr[H + c] = cv[j] * sc;
+            }
+        }
+        // five publish-time rows and the dwell-time row, 64 floats each: one float2 per lane
+        const float* tabs[6] = {month, day, week, hour, minute, dur};
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const int r = idx[(size_t)(k + 1) * M + m];
+            const float2 v = __ldg(reinterpret_cast<const float2*>(tabs[k] + (size_t)r * TH) + lane);
+            const float s = clip_scale(warp_sum(v.x * v.x + v.y * v.y));
+            float2 o = make_float2(v.x * s, v.y * s);
+            if (k < 5) reinterpret_cast<float2*>(P + (size_t)m * PW + k * TH)[lane] = o;
+            else reinterpret_cast<float2*>(D + (size_t)m * TH)[lane] = o;
+        }
+    } else if (w < M + B) {
+        const int b = w - M;
+        const int cw = ctx[b], ch = ctx[B + b];
+        const float2 a = __ldg(reinterpret_cast<const float2*>(week + (size_t)cw * TH) + lane);
+        const float2 h = __ldg(reinterpret_cast<const float2*>(hour + (size_t)ch * TH) + lane);
+        const float sa = clip_scale(warp_sum(a.x * a.x + a.y * a.y));
+        const float sh = clip_scale(warp_sum(h.x * h.x + h.y * h.y));
+        reinterpret_cast<float2*>(CT + (size_t)b * 2 * TH)[lane] = make_float2(a.x * sa, a.y * sa);
+        reinterpret_cast<float2*>(CT + (size_t)b * 2 * TH + TH)[lane] = make_float2(h.x * sh, h.y * sh);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ (2) pooling fwd
+// one CTA per session.  modules.py:126-142 (count_alpha_m), :94-100 (count_alpha_s), :116-117 / :82-83 (pool).
+__global__ void __launch_bounds__(256)
+pool_fwd_kernel(const float* __restrict__ X, const float* __restrict__ P, float* __restrict__ U1,
+                float* __restrict__ U2, const float* __restrict__ q, const float* __restrict__ w_r,
+                const float* __restrict__ w_t, float* __restrict__ alpha, float* __restrict__ pooled,
+                float* __restrict__ pooled_t, int B, int T) {
+    __shared__ float s_e[3][TCAR_MAXT];
+    __shared__ float s_a[3][TCAR_MAXT];
+    __shared__ float s_q[XW];
+    const int b = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int M = B * T;
+    for (int c = threadIdx.x; c < XW; c += blockDim.x) s_q[c] = q[(size_t)b * XW + c];
+    __syncthreads();
+    for (int t = w; t < T; t += 8) {
+        const size_t m = (size_t)b * T + t;
+        float e1 = 0.f, e2 = 0.f, et = 0.f;
+        for (int c = lane; c < H; c += 32) {
+            const float s1 = 1.f / (1.f + expf(-U1[m * H + c]));
+            const float s2 = 1.f / (1.f + expf(-U2[m * H + c]));
+            U1[m * H + c] = s1;
+            U2[m * H + c] = s2;
+            e1 = fmaf(s1, w_r[c], e1);
+            et = fmaf(s2, w_t[c], et);
+        }
+        for (int c = lane; c < XW; c += 32) e2 = fmaf(X[m * XW + c], s_q[c], e2);
+        e1 = warp_sum(e1); e2 = warp_sum(e2); et = warp_sum(et);
+        if (lane == 0) { s_e[0][t] = e1; s_e[1][t] = e2; s_e[2][t] = et; }
+    }
+    __syncthreads();
+    if (w < 3) {
+        // nrm(x) = exp(x) / (sum exp(x) + 1e-9), no max subtraction            (util.py:92-100)
+        const float x0 = lane < T ? expf(s_e[w][lane]) : 0.f;
+        const float x1 = lane + 32 < T ? expf(s_e[w][lane + 32]) : 0.f;
+        const float sum = warp_sum(x0 + x1) + 1e-9f;
+        if (lane < T) { s_a[w][lane] = x0 / sum; alpha[(size_t)w * M + (size_t)b * T + lane] = x0 / sum; }
+        if (lane + 32 < T) { s_a[w][lane + 32] = x1 / sum; alpha[(size_t)w * M + (size_t)b * T + lane + 32] = x1 / sum; }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < XW + PW; c += blockDim.x) {
+        float acc = 0.f;
+        if (c < XW) {
+            for (int t = 0; t < T; ++t) acc = fmaf(s_a[0][t] + s_a[1][t], X[((size_t)b * T + t) * XW + c], acc);
+            pooled[(size_t)b * XW + c] = acc;
+        } else {
+            const int cc = c - XW;
+            for (int t = 0; t < T; ++t) acc = fmaf(s_a[2][t], P[((size_t)b * T + t) * PW + cc], acc);
+            pooled_t[(size_t)b * PW + cc] = acc;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ (2b) pooling bwd
+__global__ void __launch_bounds__(256)
+pool_bwd_kernel(const float* __restrict__ X, const float* __restrict__ P, const float* __restrict__ S1,
+                const float* __restrict__ S2, const float* __restrict__ q, const float* __restrict__ w_r,
+                const float* __restrict__ w_t, const float* __restrict__ alpha, const float* __restrict__ dpooled,
+                const float* __restrict__ dpooled_t, float* __restrict__ dU1, float* __restrict__ dU2,
+                float* __restrict__ dXi, float* __restrict__ dP, float* __restrict__ dq, float* __restrict__ de,
+                int B, int T) {
+    __shared__ float s_dp[XW], s_dpt[PW], s_q[XW];
+    __shared__ float s_a[3][TCAR_MAXT], s_da[2][TCAR_MAXT], s_de[3][TCAR_MAXT];
+    const int b = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int M = B * T;
+    for (int c = threadIdx.x; c < XW; c += blockDim.x) {
+        s_dp[c] = dpooled[(size_t)b * XW + c];
+        s_q[c] = q[(size_t)b * XW + c];
+    }
+    for (int c = threadIdx.x; c < PW; c += blockDim.x) s_dpt[c] = dpooled_t[(size_t)b * PW + c];
+    for (int i = threadIdx.x; i < 3 * T; i += blockDim.x) s_a[i / T][i % T] = alpha[(size_t)(i / T) * M + (size_t)b * T + i % T];
+    __syncthreads();
+    // d alpha[t] = X[t,:] . dpooled ; d alpha_t[t] = P[t,:] . dpooled_t
+    for (int t = w; t < T; t += 8) {
+        const size_t m = (size_t)b * T + t;
+        float a = 0.f, at = 0.f;
+        for (int c = lane; c < XW; c += 32) a = fmaf(X[m * XW + c], s_dp[c], a);
+        for (int c = lane; c < PW; c += 32) at = fmaf(P[m * PW + c], s_dpt[c], at);
+        a = warp_sum(a); at = warp_sum(at);
+        if (lane == 0) { s_da[0][t] = a; s_da[1][t] = at; }
+    }
+    __syncthreads();
+    // softmax' backward: de[t] = alpha[t] (d alpha[t] - sum_s alpha[s] d alpha[s])
+    if (w < 3) {
+        const int src = (w == 2) ? 1 : 0;
+        const float p0 = lane < T ? s_a[w][lane] * s_da[src][lane] : 0.f;
+        const float p1 = lane + 32 < T ? s_a[w][lane + 32] * s_da[src][lane + 32] : 0.f;
+        const float dot = warp_sum(p0 + p1);
+        if (lane < T) {
+            const float v = s_a[w][lane] * (s_da[src][lane] - dot);
+            s_de[w][lane] = v; de[(size_t)w * M + (size_t)b * T + lane] = v;
+        }
+        if (lane + 32 < T) {
+            const float v = s_a[w][lane + 32] * (s_da[src][lane + 32] - dot);
+            s_de[w][lane + 32] = v; de[(size_t)w * M + (size_t)b * T + lane + 32] = v;
+        }
+    }
+    __syncthreads();
+    for (int t = w; t < T; t += 8) {
+        const size_t m = (size_t)b * T + t;
+        const float de1 = s_de[0][t], de2 = s_de[1][t], det = s_de[2][t];
+        const float a12 = s_a[0][t] + s_a[1][t], at = s_a[2][t];
+        for (int c = lane; c < H; c += 32) {
+            const float s1 = S1[m * H + c], s2 = S2[m * H + c];
+            dU1[m * H + c] = de1 * w_r[c] * s1 * (1.f - s1);
+            dU2[m * H + c] = det * w_t[c] * s2 * (1.f - s2);
+            dXi[m * H + c] = fmaf(a12, s_dp[c], de2 * s_q[c]);
+        }
+        for (int c = lane; c < PW; c += 32) dP[m * PW + c] = at * s_dpt[c];
+    }
+    for (int c = threadIdx.x; c < XW; c += blockDim.x) {
+        float acc = 0.f;
+        for (int t = 0; t < T; ++t) acc = fmaf(s_de[1][t], X[((size_t)b * T + t) * XW + c], acc);
+        dq[(size_t)b * XW + c] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ time tables
+__global__ void clip_time_tables_kernel(const float* __restrict__ month, const float* __restrict__ day,
+                                        const float* __restrict__ week, const float* __restrict__ hour,
+                                        const float* __restrict__ minute, float* __restrict__ ct_tab,
+                                        float* __restrict__ ct_scale) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= NB) return;
+    int k = 0;
+    while (r >= kBinOff[k + 1]) ++k;
+    const float* tabs[5] = {month, day, week, hour, minute};
+    const float2 v = reinterpret_cast<const float2*>(tabs[k] + (size_t)(r - kBinOff[k]) * TH)[lane];
+    const float s = clip_scale(warp_sum(v.x * v.x + v.y * v.y));
+    reinterpret_cast<float2*>(ct_tab + (size_t)r * TH)[lane] = make_float2(v.x * s, v.y * s);
+    if (lane == 0) ct_scale[r] = s;
+}
+
+// exact fp32 score of item n for session vectors in shared memory (warp-cooperative, fixed order).
+// S[b,n] = a_ic . [item[n+1] | content[n+1]] + sum_k Tq[b, off_k + mwdhm[n,k]]     (model_combine.py:132-138)
+__device__ __forceinline__ float exact_score(const float* s_aic, const float* s_tq, const float* __restrict__ item,
+                                             const float* __restrict__ content, const int32_t* __restrict__ mwdhm,
+                                             int n, int lane) {
+    const float4* ir = reinterpret_cast<const float4*>(item + ((size_t)n + 1) * HP);
+    const float4* cr = reinterpret_cast<const float4*>(content + ((size_t)n + 1) * HP);
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int c = j * 128 + lane * 4;
+        const float4 iv = __ldg(ir + j * 32 + lane), cv = __ldg(cr + j * 32 + lane);
+        if (c + 0 < H) { acc = fmaf(iv.x, s_aic[c + 0], acc); acc = fmaf(cv.x, s_aic[H + c + 0], acc); }
+        if (c + 1 < H) { acc = fmaf(iv.y, s_aic[c + 1], acc); acc = fmaf(cv.y, s_aic[H + c + 1], acc); }
+        if (c + 2 < H) { acc = fmaf(iv.z, s_aic[c + 2], acc); acc = fmaf(cv.z, s_aic[H + c + 2], acc); }
+        if (c + 3 < H) { acc = fmaf(iv.w, s_aic[c + 3], acc); acc = fmaf(cv.w, s_aic[H + c + 3], acc); }
+    }
+    acc = warp_sum(acc);
+    float tsum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) tsum += s_tq[kBinOff[k] + mwdhm[(size_t)n * 5 + k]];
+    return acc + tsum;
+}
+
+// ------------------------------------------------------------------------------------------------ (3b) query
+__global__ void __launch_bounds__(256)
+build_query_kernel(const float* __restrict__ a_ic, const float* __restrict__ a_pt, const float* __restrict__ ct_tab,
+                   const float* __restrict__ item, const float* __restrict__ content,
+                   const int32_t* __restrict__ mwdhm, const int32_t* __restrict__ label, float* __restrict__ Tq,
+                   __nv_bfloat16* __restrict__ Q, float* __restrict__ c_ref, int B) {
+    __shared__ float s_aic[XW], s_apt[PW], s_tq[NB + 1];
+    const int b = blockIdx.x;
+    __nv_bfloat16* qr = Q + (size_t)b * TCAR_KEXT;
+    if (b >= B) {
+        for (int c = threadIdx.x; c < TCAR_KEXT; c += blockDim.x) qr[c] = __float2bfloat16(0.f);
+        return;
+    }
+    for (int c = threadIdx.x; c < XW; c += blockDim.x) s_aic[c] = a_ic[(size_t)b * XW + c];
+    for (int c = threadIdx.x; c < PW; c += blockDim.x) s_apt[c] = a_pt[(size_t)b * PW + c];
+    __syncthreads();
+    if (threadIdx.x < NB) {
+        const int r = threadIdx.x;
+        int k = 0;
+        while (r >= kBinOff[k + 1]) ++k;
+        float acc = 0.f;
+        for (int d = 0; d < TH; ++d) acc = fmaf(s_apt[k * TH + d], ct_tab[(size_t)r * TH + d], acc);
+        s_tq[r] = acc;
+        Tq[(size_t)b * NB + r] = acc;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < TCAR_KEXT; c += blockDim.x) {
+        const float v = c < XW ? s_aic[c] : (c < XW + NB ? s_tq[c - XW] : 0.f);
+        qr[c] = __float2bfloat16(v);
+    }
+    if (threadIdx.x < 32) {
+        const float s = exact_score(s_aic, s_tq, item, content, mwdhm, label[b], threadIdx.x);
+        if (threadIdx.x == 0) c_ref[b] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ (4a) CE finish
+// 32 rows per CTA, 8 warps stride over tiles, fixed combine order.
+__global__ void __launch_bounds__(256)
+ce_finish_kernel(const float* __restrict__ part, float* __restrict__ sumexp, float* __restrict__ ce, int n_tiles,
+                 int B) {
+    __shared__ float s[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int b = blockIdx.x * 32 + lane;
+    float acc = 0.f;
+    if (b < B)
+        for (int t = w; t < n_tiles; t += 8) acc += part[(size_t)t * TCAR_QROWS + b];
+    s[w][lane] = acc;
+    __syncthreads();
+    if (w == 0 && b < B) {
+        float tot = 0.f;
+        for (int i = 0; i < 8; ++i) tot += s[i][lane];
+        sumexp[b] = tot;
+        ce[b] = logf(tot);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ (4b) neg loss
+__global__ void __launch_bounds__(256)
+neg_loss_kernel(const float* __restrict__ a_ic, const float* __restrict__ item, const float* __restrict__ content,
+                const int32_t* __restrict__ neg, const float* __restrict__ ce, float* __restrict__ negloss,
+                float* __restrict__ loss, float* __restrict__ coef, float* __restrict__ dA_neg, int B, int Nn) {
+    __shared__ float s_v[XW];
+    __shared__ float red[32];
+    const int b = blockIdx.x;
+    float partial = 0.f;
+    for (int c = threadIdx.x; c < XW; c += blockDim.x) {
+        const float* tab = c < H ? item : content;
+        const int cc = c < H ? c : c - H;
+        float v = 0.f;
+        for (int j = 0; j < Nn; ++j) v += tab[((size_t)neg[(size_t)b * Nn + j] + 1) * HP + cc];
+        s_v[c] = v;
+        partial = fmaf(v, a_ic[(size_t)b * XW + c], partial);
+    }
+    const float z = block_sum(partial, red);
+    const float s = 1.f / (1.f + expf(-z));
+    const float u = (1.f - s) + 1e-24f;
+    const float cf = 0.01f * s * (1.f - s) / u;
+    if (threadIdx.x == 0) {
+        const float nl = -logf(u);
+        negloss[b] = nl;
+        loss[b] = ce[b] + 0.01f * nl;
+        coef[b] = cf;
+    }
+    for (int c = threadIdx.x; c < XW; c += blockDim.x) dA_neg[(size_t)b * XW + c] = cf * s_v[c];
+}
+
+// ------------------------------------------------------------------------------------------------ (3e) finish
+__global__ void __launch_bounds__(256)
+score_bwd_finish_kernel(const float* __restrict__ dq_raw, const float* __restrict__ sumexp,
+                        const float* __restrict__ dA_neg, const float* __restrict__ a_ic,
+                        const float* __restrict__ ct_tab, const float* __restrict__ item,
+                        const float* __restrict__ content, const int32_t* __restrict__ mwdhm,
+                        const int32_t* __restrict__ label, float* __restrict__ d_a_ic, float* __restrict__ d_a_pt,
+                        float* __restrict__ dTq, __nv_bfloat16* __restrict__ Qs, int B) {
+    __shared__ float s_dt[NB + 1];
+    const int b = blockIdx.x;
+    __nv_bfloat16* qs = Qs + (size_t)b * HP;
+    if (b >= B) {
+        for (int c = threadIdx.x; c < HP; c += blockDim.x) qs[c] = __float2bfloat16(0.f);
+        return;
+    }
+    const float inv = 1.f / sumexp[b];
+    const int lab = label[b];
+    for (int c = threadIdx.x; c < XW; c += blockDim.x) {
+        const float lv = c < H ? item[((size_t)lab + 1) * HP + c] : content[((size_t)lab + 1) * HP + (c - H)];
+        d_a_ic[(size_t)b * XW + c] = dq_raw[(size_t)b * TCAR_KEXT + c] * inv - lv + dA_neg[(size_t)b * XW + c];
+    }
+    for (int c = threadIdx.x; c < HP; c += blockDim.x)
+        qs[c] = __float2bfloat16(c < H ? a_ic[(size_t)b * XW + c] * inv : 0.f);
+    if (threadIdx.x < NB) {
+        const int r = threadIdx.x;
+        int k = 0;
+        while (r >= kBinOff[k + 1]) ++k;
+        const float onehot = (mwdhm[(size_t)lab * 5 + k] == r - kBinOff[k]) ? 1.f : 0.f;
+        const float v = dq_raw[(size_t)b * TCAR_KEXT + XW + r] * inv - onehot;
+        s_dt[r] = v;
+        dTq[(size_t)b * NB + r] = v;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < PW; c += blockDim.x) {
+        const int k = c / TH, d = c % TH;
+        float acc = 0.f;
+        for (int r = kBinOff[k]; r < kBinOff[k + 1]; ++r) acc = fmaf(s_dt[r], ct_tab[(size_t)r * TH + d], acc);
+        d_a_pt[(size_t)b * PW + c] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ (5a) small tables
+// clip Jacobian of y = x / max(||x||, 1):  dx = dy (||x|| <= 1)   else   s (dy - y (y . dy)),  s = 1/||x||, y = s x
+// one CTA of 1024 threads per table row; groups of threads split the batch in a fixed pattern, combined in order.
+__global__ void __launch_bounds__(1024)
+small_table_grads_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ ctx,
+                         const float* __restrict__ dXi, const float* __restrict__ dP, const float* __restrict__ dD,
+                         const float* __restrict__ dCT, const float* __restrict__ dTq,
+                         const float* __restrict__ a_pt, const float* __restrict__ pos,
+                         const float* __restrict__ month, const float* __restrict__ day,
+                         const float* __restrict__ week, const float* __restrict__ hour,
+                         const float* __restrict__ minute, const float* __restrict__ dur, float* __restrict__ g_pos,
+                         float* __restrict__ g_month, float* __restrict__ g_day, float* __restrict__ g_week,
+                         float* __restrict__ g_hour, float* __restrict__ g_minute, float* __restrict__ g_dur, int B,
+                         int T) {
+    __shared__ float s_acc[1024];
+    __shared__ float s_g[256];
+    __shared__ float red[32];
+    const int M = B * T;
+    const int row = blockIdx.x;  // [0,40) pos, [40,179) time bins, [179,190) duration
+    const float* x;
+    float* g;
+    int width;
+    float acc = 0.f;
+    if (row < TCAR_MAXT) {
+        // position rows: G[c] = sum_b dXi[b,t,c]
+        width = H;
+        x = pos + (size_t)row * H;
+        g = g_pos + (size_t)row * H;
+        const int c = threadIdx.x & 255, grp = threadIdx.x >> 8;  // 4 groups
+        if (row < T && c < H)
+            for (int b = grp; b < B; b += 4) acc += dXi[((size_t)b * T + row) * H + c];
+        s_acc[threadIdx.x] = acc;
+        __syncthreads();
+        if (threadIdx.x < 256) s_g[threadIdx.x] = s_acc[threadIdx.x] + s_acc[256 + threadIdx.x] + s_acc[512 + threadIdx.x] + s_acc[768 + threadIdx.x];
+    } else {
+        width = TH;
+        const int d = threadIdx.x & 63, grp = threadIdx.x >> 6;  // 16 groups
+        const int r = row - TCAR_MAXT;
+        if (r < NB) {
+            int k = 0;
+            while (r >= kBinOff[k + 1]) ++k;
+            const int rr = r - kBinOff[k];
+            const float* tabs[5] = {month, day, week, hour, minute};
+            float* gs[5] = {g_month, g_day, g_week, g_hour, g_minute};
+            x = tabs[k] + (size_t)rr * TH;
+            g = gs[k] + (size_t)rr * TH;
+            const int32_t* ik = idx + (size_t)(k + 1) * M;
+            for (int m = grp; m < M; m += 16)
+                if (ik[m] == rr) acc += dP[(size_t)m * PW + k * TH + d];
+            if (k == 2)
+                for (int b = grp; b < B; b += 16)
+                    if (ctx[b] == rr) acc += dCT[(size_t)b * 2 * TH + d];
+            if (k == 3)
+                for (int b = grp; b < B; b += 16)
+                    if (ctx[B + b] == rr) acc += dCT[(size_t)b * 2 * TH + TH + d];
+            for (int b = grp; b < B; b += 16) acc = fmaf(dTq[(size_t)b * NB + r], a_pt[(size_t)b * PW + k * TH + d], acc);
+        } else {
+            const int rr = r - NB;
+            x = dur + (size_t)rr * TH;
+            g = g_dur + (size_t)rr * TH;
+            const int32_t* ik = idx + (size_t)6 * M;
+            for (int m = grp; m < M; m += 16)
+                if (ik[m] == rr) acc += dD[(size_t)m * TH + d];
+        }
+        s_acc[threadIdx.x] = acc;
+        __syncthreads();
+        if (threadIdx.x < 64) {
+            float t = 0.f;
+            for (int i = 0; i < 16; ++i) t += s_acc[i * 64 + threadIdx.x];
+            s_g[threadIdx.x] = t;
+        }
+    }
+    __syncthreads();
+    const int c = threadIdx.x;
+    const float xv = c < width ? x[c] : 0.f;
+    const float gv = c < width ? s_g[c] : 0.f;
+    const float sq = block_sum(xv * xv, red);
+    const float n = sqrtf(sq);
+    if (n > 1.f) {
+        const float s = 1.f / n;
+        const float ydg = block_sum(xv * s * gv, red);
+        if (c < width) g[c] = s * (gv - xv * s * ydg);
+    } else if (c < width) {
+        g[c] = gv;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ (5b) scatter-add
+constexpr float kFix = 1099511627776.f;        // 2^40
+constexpr float kInvFix = 1.f / 1099511627776.f;
+
+__device__ __forceinline__ int hash_slot(int32_t* keys, int row, int mask) {
+    uint32_t h = (uint32_t)row * 2654435761u;
+    int slot = (int)((h >> 7) & (uint32_t)mask);
+    while (true) {
+        const int prev = atomicCAS(&keys[slot], -1, row);
+        if (prev == -1 || prev == row) return slot;
+        slot = (slot + 1) & mask;
+    }
+}
+
+// one warp per sparse entry: clicks [0,M), labels [M,M+B), negatives [M+B, M+B+B*Nn)
+__global__ void __launch_bounds__(256)
+scatter_accum_kernel(const int32_t* __restrict__ seq, const int32_t* __restrict__ label,
+                     const int32_t* __restrict__ neg, const float* __restrict__ dXi, const float* __restrict__ a_ic,
+                     const float* __restrict__ coef, const float* __restrict__ item, int32_t* __restrict__ keys,
+                     unsigned long long* __restrict__ acc, int mask, int B, int T, int Nn) {
+    const int M = B * T;
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (e >= M + B + B * Nn) return;
+    int row;
+    float val[8];
+    if (e < M) {
+        row = seq[e];
+        const float4* ir = reinterpret_cast<const float4*>(item + (size_t)row * HP);
+        const float4 i0 = __ldg(ir + lane), i1 = __ldg(ir + 32 + lane);
+        const float xv[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+        float dy[8], sq = 0.f, xdy = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = (j < 4) ? lane * 4 + j : 128 + lane * 4 + (j - 4);
+            dy[j] = c < H ? dXi[(size_t)e * H + c] : 0.f;
+            sq = fmaf(xv[j], xv[j], sq);
+            xdy = fmaf(xv[j], dy[j], xdy);
+        }
+        sq = warp_sum(sq);
+        xdy = warp_sum(xdy);
+        const float n = sqrtf(sq);
+        if (n > 1.f) {
+            const float s = 1.f / n;
+            const float ydy = xdy * s;  // y . dy
+#pragma unroll
+            for (int j = 0; j < 8; ++j) val[j] = s * (dy[j] - xv[j] * s * ydy);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) val[j] = dy[j];
+        }
+    } else {
+        int b;
+        float scale;
+        if (e < M + B) { b = e - M; row = label[b] + 1; scale = -1.f; }
+        else { const int k = e - M - B; b = k / Nn; row = neg[k] + 1; scale = coef[b]; }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = (j < 4) ? lane * 4 + j : 128 + lane * 4 + (j - 4);
+            val[j] = c < H ? scale * a_ic[(size_t)b * XW + c] : 0.f;
+        }
+    }
+    int slot = 0;
+    if (lane == 0) slot = hash_slot(keys, row, mask);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    unsigned long long* dst = acc + (size_t)slot * HP;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = (j < 4) ? lane * 4 + j : 128 + lane * 4 + (j - 4);
+        if (c < H) atomicAdd(dst + c, (unsigned long long)__float2ll_rn(val[j] * kFix));
+    }
+}
+
+// one warp per hash slot: add the exact integer sum to g_item and restore the scratch to its empty state
+__global__ void __launch_bounds__(256)
+scatter_apply_kernel(int32_t* __restrict__ keys, long long* __restrict__ acc, float* __restrict__ g_item,
+                     int hash_size) {
+    const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (slot >= hash_size) return;
+    const int row = keys[slot];
+    if (row < 0) return;
+    long long* src = acc + (size_t)slot * HP;
+    float* dst = g_item + (size_t)row * HP;
+    for (int c = lane; c < H; c += 32) {
+        dst[c] += (float)src[c] * kInvFix;
+        src[c] = 0;
+    }
+    __syncwarp();
+    if (lane == 0) keys[slot] = -1;
+}
+
+}  // namespace tcar
+
+using namespace tcar;
+#define STREAM static_cast<cudaStream_t>(stream)
+#define LAUNCH_RC() ((int)cudaGetLastError())
+
+extern "C" int tcar_gather_fwd(const int32_t* idx, const int32_t* ctx, const float* item, const float* content,
+                               const float* pos, const float* month, const float* day, const float* week,
+                               const float* hour, const float* minute, const float* dur, float* X, float* P, float* D,
+                               float* CT, int B, int T, void* stream) {
+    if (B < 1 || T < 1 || T > TCAR_MAXT) return TCAR_ERR_ARG;
+    const int warps = B * T + B;
+    gather_fwd_kernel<<<(warps + 7) / 8, 256, 0, STREAM>>>(idx, ctx, item, content, pos, month, day, week, hour,
+                                                           minute, dur, X, P, D, CT, B, T);
+    return LAUNCH_RC();
+}
+
+extern "C" int tcar_pool_fwd(const float* X, const float* P, float* U1, float* U2, const float* q, const float* w_r,
+                             const float* w_t, float* alpha, float* pooled, float* pooled_t, int B, int T,
+                             void* stream) {
+    if (B < 1 || T < 1 || T > TCAR_MAXT) return TCAR_ERR_ARG;
+    pool_fwd_kernel<<<B, 256, 0, STREAM>>>(X, P, U1, U2, q, w_r, w_t, alpha, pooled, pooled_t, B, T);
+    return LAUNCH_RC();
+}
+
+extern "C" int tcar_pool_bwd(const float* X, const float* P, const float* S1, const float* S2, const float* q,
+                             const float* w_r, const float* w_t, const float* alpha, const float* dpooled,
+                             const float* dpooled_t, float* dU1, float* dU2, float* dXi, float* dP, float* dq,
+                             float* de, int B, int T, void* stream) {
+    if (B < 1 || T < 1 || T > TCAR_MAXT) return TCAR_ERR_ARG;
+    pool_bwd_kernel<<<B, 256, 0, STREAM>>>(X, P, S1, S2, q, w_r, w_t, alpha, dpooled, dpooled_t, dU1, dU2, dXi, dP,
+                                           dq, de, B, T);
+    return LAUNCH_RC();
+}
+
+extern "C" int tcar_clip_time_tables(const float* month, const float* day, const float* week, const float* hour,
+                                     const float* minute, float* ct_tab, float* ct_scale, void* stream) {
+    clip_time_tables_kernel<<<(NB * 32 + 255) / 256, 256, 0, STREAM>>>(month, day, week, hour, minute, ct_tab,
+                                                                        ct_scale);
+    return LAUNCH_RC();
+}
+
+extern "C" int tcar_build_query(const float* a_ic, const float* a_pt, const float* ct_tab, const float* item,
+                                const float* content, const int32_t* mwdhm, const int32_t* label, float* Tq,
+                                void* q_bf16, float* c_ref, int B, void* stream) {
+    if (B < 1 || B > TCAR_QROWS) return TCAR_ERR_ARG;
+    build_query_kernel<<<TCAR_QROWS, 256, 0, STREAM>>>(a_ic, a_pt, ct_tab, item, content, mwdhm, label, Tq,
+                                                       static_cast<__nv_bfloat16*>(q_bf16), c_ref, B);
+    return LAUNCH_RC();
+}
+
+extern "C" int tcar_ce_finish(const float* rowsum_part, float* sumexp, float* ce, int n_tiles, int B, void* stream) {
+    if (B < 1 || B > TCAR_QROWS) return TCAR_ERR_ARG;
+    ce_finish_kernel<<<(B + 31) / 32, 256, 0, STREAM>>>(rowsum_part, sumexp, ce, n_tiles, B);
+    return LAUNCH_RC();
+}
+
+extern "C" int tcar_neg_loss(const float* a_ic, const float* item, const float* content, const int32_t* neg,
+                             const float* ce, float* negloss, float* loss, float* coef, float* dA_neg, int B, int Nn,
+                             void* stream) {
+    if (B < 1 || Nn < 0) return TCAR_ERR_ARG;
+    neg_loss_kernel<<<B, 256, 0, STREAM>>>(a_ic, item, content, neg, ce, negloss, loss, coef, dA_neg, B, Nn);
+    return LAUNCH_RC();
+}
+
+extern "C" int tcar_score_bwd_finish(const float* dq_raw, const float* sumexp, const float* dA_neg,
+                                     const float* a_ic, const float* ct_tab, const float* item, const float* content,
+                                     const int32_t* mwdhm, const int32_t* label, float* d_a_ic, float* d_a_pt,
+                                     float* dTq, void* qs_bf16, int B, void* stream) {
+    if (B < 1 || B > TCAR_QROWS) return TCAR_ERR_ARG;
+    score_bwd_finish_kernel<<<TCAR_QROWS, 256, 0, STREAM>>>(dq_raw, sumexp, dA_neg, a_ic, ct_tab, item, content,
+                                                            mwdhm, label, d_a_ic, d_a_pt, dTq,
+                                                            static_cast<__nv_bfloat16*>(qs_bf16), B);
+    return LAUNCH_RC();
+}
+
+extern "C" int tcar_small_table_grads(const int32_t* idx, const int32_t* ctx, const float* dXi, const float* dP,
+                                      const float* dD, const float* dCT, const float* dTq, const float* a_pt,
+                                      const float* pos, const float* month, const float* day, const float* week,
+                                      const float* hour, const float* minute, const float* dur, float* g_pos,
+                                      float* g_month, float* g_day, float* g_week, float* g_hour, float* g_minute,
+                                      float* g_dur, int B, int T, void* stream) {
+    if (B < 1 || T < 1 || T > TCAR_MAXT) return TCAR_ERR_ARG;
+    small_table_grads_kernel<<<TCAR_MAXT + NB + 11, 1024, 0, STREAM>>>(
+        idx, ctx, dXi, dP, dD, dCT, dTq, a_pt, pos, month, day, week, hour, minute, dur, g_pos, g_month, g_day,
+        g_week, g_hour, g_minute, g_dur, B, T);
+    return LAUNCH_RC();
+}
+
+extern "C" int tcar_scatter_add_rows(const int32_t* seq, const int32_t* label, const int32_t* neg, const float* dXi,
+                                     const float* a_ic, const float* coef, const float* item, float* g_item,
+                                     int32_t* hash_keys, long long* hash_acc, int hash_size, int B, int T, int Nn,
+                                     void* stream) {
+    const int entries = B * T + B + B * Nn;
+    if (hash_size < 2 * entries || (hash_size & (hash_size - 1))) return TCAR_ERR_ARG;
+    scatter_accum_kernel<<<(entries + 7) / 8, 256, 0, STREAM>>>(
+        seq, label, neg, dXi, a_ic, coef, item, hash_keys, reinterpret_cast<unsigned long long*>(hash_acc),
+        hash_size - 1, B, T, Nn);
+    int rc = LAUNCH_RC();
+    if (rc) return rc;
+    scatter_apply_kernel<<<(hash_size + 7) / 8, 256, 0, STREAM>>>(hash_keys, hash_acc, g_item, hash_size);
+    return LAUNCH_RC();
+}

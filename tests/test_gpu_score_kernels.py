@@ -1,0 +1,113 @@
+"""GPU parity of the three tcgen05 scoring GEMMs (tcar_score_fwd / _bwd_q / _bwd_i) called through the C ABI.
+
+The checker here is a plain torch fp32/fp64 matmul over the SAME bf16-rounded operands (this is a floating-point
+kernel, so a torch reference is the right unit-level oracle; end-to-end parity against oracle/ lives in
+test_gpu_parity.py).  Tolerances: fp32 accumulation of bf16 products -> rtol 2e-3 on sums, bf16 output rounding
+(2^-8) on E.
+"""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+KEXT, QROWS = 640, 512
+
+
+def _mk(B, N, seed):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    n_pad = (N + 255) // 256 * 256
+    Q = torch.zeros(QROWS, KEXT, device="cuda", dtype=torch.bfloat16)
+    Q[:B] = (torch.randn(B, KEXT, device="cuda", generator=g) * 0.5).bfloat16()
+    I = torch.zeros(n_pad, KEXT, device="cuda", dtype=torch.bfloat16)
+    I[:N] = (torch.randn(N, KEXT, device="cuda", generator=g) * 0.1).bfloat16()
+    c = torch.randn(QROWS, device="cuda", generator=g) * 0.3
+    return Q, I, c, n_pad
+
+
+def _fwd(native, Q, I, c, B, N, n_pad, mode, cluster):
+    tiles = native.lib().tcar_score_fwd_tiles(n_pad)
+    part = torch.zeros(tiles, QROWS, device="cuda")
+    E = torch.full((QROWS, n_pad), float("nan"), device="cuda", dtype=torch.bfloat16) if mode == 0 else None
+    cm = torch.full((QROWS, n_pad // 8), float("nan"), device="cuda") if mode == 1 else None
+    native.call("tcar_score_fwd", native.ptr(Q), native.ptr(I), native.ptr(c), native.ptr(E), native.ptr(part),
+                native.ptr(cm), B, N, n_pad, mode, cluster)
+    torch.cuda.synchronize()
+    return E, part, cm
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4])
+@pytest.mark.parametrize("B,N", [(512, 5000), (300, 2333), (64, 20000), (1, 300)])
+def test_score_fwd_train(native, cluster, B, N):
+    Q, I, c, n_pad = _mk(B, N, 7 + B + N)
+    E, part, _ = _fwd(native, Q, I, c, B, N, n_pad, 0, cluster)
+    S = Q[:B].float() @ I[:N].float().t()
+    ref = torch.exp(S - c[:B, None])
+    got = E[:B, :N].float()
+    err = ((got - ref).abs() / (ref.abs() + 1e-6)).max().item()
+    assert err < 1.2e-2, f"E rel err {err}"
+    assert (E[:B, N:].float() == 0).all(), "padded item columns must be exactly zero"
+    kpad = (B + 63) // 64 * 64
+    assert (E[B:kpad].float() == 0).all(), "K-padding rows must be exactly zero"
+    rs = part.sum(0)[:B]
+    rerr = ((rs - ref.sum(1)).abs() / ref.sum(1)).max().item()
+    assert rerr < 2e-3, f"rowsum rel err {rerr}"
+
+
+@pytest.mark.parametrize("cluster", [1, 4])
+def test_score_fwd_eval_chunkmax(native, cluster):
+    B, N = 257, 7001
+    Q, I, c, n_pad = _mk(B, N, 99)
+    _, part, cm = _fwd(native, Q, I, c, B, N, n_pad, 1, cluster)
+    S = Q[:B].float() @ I[:N].float().t()
+    Sp = torch.full((B, (N + 7) // 8 * 8), float("-inf"), device="cuda")
+    Sp[:, :N] = S
+    ref = Sp.view(B, -1, 8).max(-1).values
+    got = cm[:B, : ref.shape[1]]
+    err = (got - ref).abs().max().item()
+    assert err < 2e-3, f"chunkmax abs err {err}"
+    rs = part.sum(0)[:B]
+    rref = torch.exp(S - c[:B, None]).sum(1)
+    assert ((rs - rref).abs() / rref).max().item() < 2e-3
+
+
+@pytest.mark.parametrize("B,N", [(512, 5000), (200, 2333), (64, 40000)])
+def test_score_bwd_q(native, B, N):
+    g = torch.Generator(device="cuda").manual_seed(B + N)
+    n_pad = (N + 255) // 256 * 256
+    E = torch.zeros(QROWS, n_pad, device="cuda", dtype=torch.bfloat16)
+    E[:B, :N] = torch.rand(B, N, device="cuda", generator=g).bfloat16()
+    I = torch.zeros(n_pad, KEXT, device="cuda", dtype=torch.bfloat16)
+    I[:N] = (torch.randn(N, KEXT, device="cuda", generator=g) * 0.1).bfloat16()
+    splits = native.lib().tcar_score_bwd_q_splits(B, n_pad)
+    part = torch.zeros(splits, QROWS, KEXT, device="cuda")
+    dq = torch.zeros(QROWS, KEXT, device="cuda")
+    native.call("tcar_score_bwd_q", native.ptr(E), native.ptr(I), native.ptr(part), native.ptr(dq), B, n_pad)
+    torch.cuda.synchronize()
+    ref = (E[:B].double() @ I.double()).float()
+    scale = ref.abs().max().item()
+    err = (dq[:B] - ref).abs().max().item() / scale
+    assert err < 1e-4, f"dq err {err} (scale {scale})"
+
+
+@pytest.mark.parametrize("B,N", [(512, 5000), (200, 2333), (64, 40000), (5, 300)])
+def test_score_bwd_i(native, B, N):
+    g = torch.Generator(device="cuda").manual_seed(3 * B + N)
+    n_pad = (N + 255) // 256 * 256
+    kpad = (B + 63) // 64 * 64
+    E = torch.zeros(QROWS, n_pad, device="cuda", dtype=torch.bfloat16)
+    E[:B, :N] = torch.rand(B, N, device="cuda", generator=g).bfloat16()
+    E[kpad:] = float("nan")  # rows beyond the K padding must never be read
+    Qs = torch.zeros(QROWS, 256, device="cuda", dtype=torch.bfloat16)
+    Qs[:B, :250] = (torch.randn(B, 250, device="cuda", generator=g) * 0.2).bfloat16()
+    gi = torch.full((N + 1, 256), float("nan"), device="cuda")
+    gi[0] = 0
+    native.call("tcar_score_bwd_i", native.ptr(E), native.ptr(Qs), native.ptr(gi), B, N, n_pad)
+    torch.cuda.synchronize()
+    ref = (E[:B, :N].double().t() @ Qs[:B].double()).float()
+    scale = ref.abs().max().item()
+    err = (gi[1:] - ref).abs().max().item() / scale
+    assert err < 1e-4, f"g_item err {err} (scale {scale})"
+    assert (gi[1:, 250:] == 0).all()
+    assert (gi[0] == 0).all()
