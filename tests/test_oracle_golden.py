@@ -1,0 +1,117 @@
+"""Pin the CPU oracle against golden vectors produced by the REFERENCE's own source (tests/golden/make_golden.py):
+graph forward / gradients / clip + Adam step, sampler index production, and the ranking / diversity metrics."""
+import datetime
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sampler_oracle, tcar_oracle as O
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+FEED = {"seq": "inputs_seq", "pm": "publish_month", "pd": "publish_day", "pw": "publish_week", "ph": "publish_hour",
+        "pmi": "publish_minute", "cw": "click_week", "ch": "click_hour", "label": "lab_input", "neg": "lab_neg",
+        "gap": "active_time"}
+
+
+def load_case(name, dtype=torch.float64):
+    z = np.load(os.path.join(G, name))
+    p = {k: torch.tensor(z["init_" + k], dtype=dtype) for k in O.PARAM_ORDER}
+    batch = {k: torch.tensor(z["feed_" + v].astype(np.int64)) for k, v in FEED.items()}
+    content = torch.tensor(z["content"], dtype=dtype)
+    mwdhm = torch.tensor(z["mwdhm"].astype(np.int64))
+    return z, p, content, mwdhm, batch
+
+
+@pytest.mark.parametrize("name", ["tcar_ref_default.npz", "tcar_ref_clip.npz", "tcar_ref_t1.npz"])
+def test_forward_and_losses_match_reference_graph(name):
+    z, p, content, mwdhm, batch = load_case(name)
+    out = O.forward(p, content, mwdhm, batch)
+    np.testing.assert_allclose(out["softmax_input"].numpy(), z["softmax_input"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(out["cross_loss"].numpy(), z["cross_loss"], rtol=1e-10)
+    np.testing.assert_allclose(out["loss"].numpy(), z["loss"], rtol=1e-10)
+
+
+@pytest.mark.parametrize("name", ["tcar_ref_default.npz", "tcar_ref_clip.npz", "tcar_ref_t1.npz"])
+def test_gradients_clip_and_adam_step_match_reference(name):
+    z, p, content, mwdhm, batch = load_case(name)
+    adam = O.TFAdam(p, float(z["lr"]))
+    init = {k: v.clone() for k, v in p.items()}
+    _, capped = O.train_step(p, adam, content, mwdhm, batch, max_grad=float(z["max_grad"]))
+    _, raw = O.loss_and_grads(init, content, mwdhm, batch)
+    fired = 0
+    for k in O.PARAM_ORDER:
+        g = z["grad_" + k].astype(np.float64)
+        np.testing.assert_allclose(raw[k].numpy(), g, rtol=2e-6, atol=1e-7 * (np.abs(g).max() + 1e-30), err_msg=k)
+        np.testing.assert_allclose(np.linalg.norm(capped[k].numpy()), float(z["capnorm_" + k]), rtol=1e-9, err_msg=k)
+        fired += np.linalg.norm(g) > float(z["max_grad"])
+        d = z["delta_" + k].astype(np.float64)
+        np.testing.assert_allclose((p[k] - init[k]).numpy(), d, rtol=2e-6, atol=1e-12, err_msg=k)
+    if name == "tcar_ref_clip.npz":
+        assert fired >= 3, "this fixture is meant to exercise clip_by_norm"
+
+
+def test_oracle_fp32_close_to_fp64():
+    z, p, content, mwdhm, batch = load_case("tcar_ref_clip.npz", torch.float32)
+    out = O.forward(p, content, mwdhm, batch)
+    np.testing.assert_allclose(out["loss"].numpy(), z["loss"], rtol=2e-5)
+
+
+def _datasets():
+    d = json.load(open(os.path.join(G, "sampler_ref.json")))
+    len_dict = {int(k): list(v) for k, v in d["len_dict"].items()}
+    time_dict = {k: [{"click_t": datetime.datetime.fromisoformat(t["click_t"]),
+                      "publish_t": datetime.datetime.fromisoformat(t["publish_t"]), "active_t": t["active_t"]}
+                     for t in v] for k, v in d["time_dict"].items()}
+    item_dict = {"orig%d" % i: i + 1 for i in range(d["N"])}
+    impressions = {int(k): v for k, v in d["impressions"].items()}
+    return d, len_dict, d["session_dict"], time_dict, item_dict, impressions
+
+
+def test_bucketized_matches_reference():
+    d = _datasets()[0]
+    for sec, b in d["bucketized"].items():
+        assert sampler_oracle.bucketized(int(sec)) == b
+
+
+def test_sampler_matches_reference_batches():
+    d, len_dict, session_dict, time_dict, item_dict, impressions = _datasets()
+    for run in d["runs"]:
+        random.seed(2020)
+        np.random.seed(2020)
+        ld = {k: list(v) for k, v in len_dict.items()}
+        s = sampler_oracle.SamplerOracle(ld, session_dict, time_dict, impressions, item_dict, run["neg_num"],
+                                         batch_size=run["batch_size"])
+        got = []
+        while s.has_next():
+            b_in, b_out, pt, ct, neg, gap = s.next_batch()
+            got.append({"in": b_in, "out": b_out, "pt": [list(x) for x in pt], "ct": [list(x) for x in ct],
+                        "neg": neg, "gap": gap})
+        assert got == run["batches"]
+        assert [s.neg_neighbor_from_impre(i) for i in range(5)] == run["impre"]
+        assert {str(k): v for k, v in ld.items()} == run["shuffled_len_dict"]
+    random.seed(2020)
+    s = sampler_oracle.SamplerOracle({k: list(v) for k, v in len_dict.items()}, session_dict, time_dict, batch_size=16)
+    for ref in d["eval_run"]:
+        b_in, b_out, pt, ct, neg, gap = s.next_batch()
+        assert (b_in, b_out, neg, [list(x) for x in ct]) == (ref["in"], ref["out"], ref["neg"], ref["ct"])
+    assert not s.has_next()
+
+
+def test_metrics_match_reference():
+    m = json.load(open(os.path.join(G, "metrics_ref.json")))
+    preds = np.array(m["preds"], dtype=np.float32)
+    recall, mrr, ndcg = O.cau_metrics(preds, m["labels"], 20)
+    assert [bool(x) for x in recall] == m["recall"]
+    np.testing.assert_allclose(mrr, m["mrr"])
+    np.testing.assert_allclose(ndcg, m["ndcg"])
+    rev = {i: "o%d" % i for i in range(preds.shape[1])}
+    for rec, ild, seq, un in zip(m["recs"], m["ild"], m["seqs"], m["unexp"]):
+        assert O.get_ild(rec, m["category_id"], rev) == ild
+        assert O.get_unexp(seq, rec, m["category_id"], rev) == un
+    # our tie rule (lower id first) agrees with the reference's argsort on tie-free rows
+    for i in range(2, preds.shape[0]):
+        assert list(O.top20(preds[i:i + 1])[0]) == m["recs"][i]
