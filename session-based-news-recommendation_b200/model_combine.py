@@ -1,0 +1,460 @@
+"""TCAR model -- drop-in for the reference's model_combine.Seq2SeqAttNN (model_combine.py:10-315).
+
+Same constructor (`Seq2SeqAttNN(args: dict)`), same `train(sess, item_dict, train_data, neighbor_dict, args,
+test_data, saver, threshold_acc)` / `test(sess, test_data, args)` methods and the same feed-dict vocabulary; the
+TensorFlow graph underneath is replaced by hand-written sm_100a kernels called through the C ABI in
+include/tcar_b200.h.  `sess` / `saver` are accepted and ignored.  PyTorch is used for device memory, streams,
+cuBLAS calls for the small dense projections (plain library GEMMs) and torch.distributed.
+
+There is no CPU path: constructing the model without CUDA + libtcar_b200.so raises.
+"""
+import math
+import os
+import time
+
+import numpy as np
+import torch
+
+from . import _native as nv
+from .params import ParamStore, SMALL
+from .sampler import Sampler, pack_batch
+
+H, TH, XW, PW, NB, KEXT, QROWS, TOPK = nv.H, nv.TH, nv.XW, nv.PW, nv.NBINS, nv.KEXT, nv.QROWS, nv.TOPK
+
+
+class Batch:
+    """One length-bucketed batch on the device: the reference's 11-entry feed dict (model_combine.py:214-227)
+    packed into a single int32 buffer  [7*B*T idx | 2*B ctx | B label | B*Nn neg]."""
+
+    def __init__(self, buf, B, T, Nn):
+        self.buf, self.B, self.T, self.Nn = buf, B, T, Nn
+        M = B * T
+        self.idx = buf[: 7 * M]
+        self.ctx = buf[7 * M: 7 * M + 2 * B]
+        self.label = buf[7 * M + 2 * B: 7 * M + 3 * B]
+        self.neg = buf[7 * M + 3 * B: 7 * M + 3 * B + B * Nn] if Nn > 0 else None
+        self.seq = buf[:M]
+
+
+class Seq2SeqAttNN:
+    def __init__(self, args):
+        if not torch.cuda.is_available():
+            raise RuntimeError("tcar_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        nv.lib()
+        torch.backends.cuda.matmul.allow_tf32 = False
+        self.args = args
+        self.itemnum = args["itemnum"]
+        self.category_id = args.get("category_id")
+        self.item_freq_dict_norm = args.get("item_freq_dict_norm")
+        self.reverse_item = args.get("reverse_item")
+        content = np.asarray(args["content_emb"], dtype=np.float32)
+        self.candidate_n = content.shape[0]
+        self.N = self.candidate_n - 1                       # model_combine.py:42,135
+        self.emb_stddev, self.stddev = args["emb_stddev"], args["stddev"]
+        self.hidden_size, self.time_hidden_size = args["hidden_size"], args["time_hidden_size"]
+        if self.hidden_size != H or content.shape[1] != H or self.time_hidden_size != TH:
+            raise ValueError("this build is specialised for hidden_size=250 (== content width), time_hidden_size=64")
+        self.batch_size, self.epoch, self.neg_num = args["batch_size"], args["epoch"], args["neg_num"]
+        if self.batch_size > QROWS:
+            raise ValueError(f"batch_size <= {QROWS} (one scoring call holds at most {QROWS} sessions)")
+        self.lr = float(args["lr"])
+        self.max_grad = args.get("max_grad")
+        self.max_grad_f = float(self.max_grad) if self.max_grad is not None else 3.0e38
+        # catalog sharding for evaluation / data-parallel training (torch.distributed, NCCL)
+        self.rank = int(args.get("rank", 0))
+        self.world = int(args.get("world_size", 1))
+        self.cluster = int(args.get("cluster", 4))
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.dev = dev
+        self.ps = ParamStore(self.N, content, args["publish_time_MWDHM"], dev)
+        self.ps.init_reference(self.emb_stddev, self.stddev)
+        self.variables_names = ["item"] + [n for n, _ in SMALL]
+        self._alloc()
+        self._cat_array = None
+        self.curEpoch = 0
+        self.error_during_train = False
+        self.global_step = 0
+
+    # ------------------------------------------------------------------------------------------- workspaces
+    def _alloc(self):
+        dev, Bm, Tm = self.dev, QROWS, nv.MAXT
+        Mm = Bm * Tm
+        f = lambda *s: torch.zeros(*s, device=dev)
+        self.X, self.P, self.D, self.CT = f(Mm, XW), f(Mm, PW), f(Mm, TH), f(Bm, 2 * TH)
+        self.U1, self.U2, self.dU1, self.dU2 = f(Mm, H), f(Mm, H), f(Mm, H), f(Mm, H)
+        self.dXi, self.dP, self.dD = f(Mm, H), f(Mm, PW), f(Mm, TH)
+        self.alpha, self.de = f(3, Mm), f(3, Mm)
+        self.h1, self.q, self.dq = f(Bm, H), f(Bm, XW), f(Bm, XW)
+        self.pooled, self.pooled_t = f(Bm, XW), f(Bm, PW)
+        self.a_ic, self.a_pt = f(Bm, XW), f(Bm, PW)
+        self.d_a_ic, self.d_a_pt, self.dA_neg = f(Bm, XW), f(Bm, PW), f(Bm, XW)
+        self.Tq, self.dTq = f(Bm, NB), f(Bm, NB)
+        self.c_ref, self.sumexp, self.ce = f(Bm), f(Bm), f(Bm)
+        self.negloss, self.loss, self.coef = f(Bm), f(Bm), f(Bm)
+        self.Q = torch.zeros(QROWS, KEXT, device=dev, dtype=torch.bfloat16)
+        self.Qs = torch.zeros(QROWS, nv.HP, device=dev, dtype=torch.bfloat16)
+        self.dq_raw = f(QROWS, KEXT)
+        self.dCT = f(Bm, 2 * TH)
+        self._score_ws = {}
+        self.hash_size = 65536
+        self.hash_keys = torch.full((self.hash_size,), -1, device=dev, dtype=torch.int32)
+        self.hash_acc = torch.zeros(self.hash_size, nv.HP, device=dev, dtype=torch.int64)
+        self.top_ids = torch.zeros(Bm, TOPK, device=dev, dtype=torch.int32)
+        self.top_scores = f(Bm, TOPK)
+        self.n_greater = torch.zeros(Bm, device=dev, dtype=torch.int32)
+
+    def _score_buffers(self, n_pad, train):
+        """E / partial-sum / chunk-max buffers sized for a catalog (shard) of n_pad items; allocated once."""
+        key = (n_pad, train)
+        if key not in self._score_ws:
+            dev = self.dev
+            tiles = nv.lib().tcar_score_fwd_tiles(n_pad)
+            ws = {"part": torch.zeros(tiles, QROWS, device=dev), "tiles": tiles}
+            if train:
+                ws["E"] = torch.zeros(QROWS, n_pad, device=dev, dtype=torch.bfloat16)
+                splits = max(nv.lib().tcar_score_bwd_q_splits(b, n_pad) for b in (1, 129, 257, 385))
+                ws["qpart"] = torch.zeros(splits, QROWS, KEXT, device=dev)
+            else:
+                ws["cmax"] = torch.zeros(QROWS, n_pad // nv.CHUNK, device=dev)
+            self._score_ws[key] = ws
+        return self._score_ws[key]
+
+    # ------------------------------------------------------------------------------------------- batches
+    def to_device(self, packed, B, T, Nn):
+        """H2D copy of one packed int32 batch (pinned host buffer -> device)."""
+        buf = torch.empty(packed.numel(), device=self.dev, dtype=torch.int32)
+        buf.copy_(packed, non_blocking=True)
+        return Batch(buf, B, T, Nn)
+
+    def make_batch(self, batch_in, batch_out, batch_pt, batch_ct, neg, gap):
+        """From the reference sampler's 6-tuple of Python lists (sampler.py:113) to a device Batch."""
+        packed, B, T, Nn = pack_batch(batch_in, batch_out, batch_pt, batch_ct, neg, gap)
+        return self.to_device(torch.from_numpy(packed).pin_memory(), B, T, Nn)
+
+    # ------------------------------------------------------------------------------------------- forward
+    def _session_forward(self, bt):
+        """Everything up to a_ic / a_pt / Q: model_combine.py:52-127."""
+        ps, w, B, T = self.ps, self.ps.w, bt.B, bt.T
+        M = B * T
+        p = nv.ptr
+        nv.counted_call("tcar_gather_fwd", 1, p(bt.idx), p(bt.ctx), p(ps.item), p(ps.content), p(w["pos"]),
+                        p(w["month"]), p(w["day"]), p(w["week"]), p(w["hour"]), p(w["minute"]), p(w["dur"]),
+                        p(self.X), p(self.P), p(self.D), p(self.CT), B, T)
+        X, P, D, CT = self.X[:M], self.P[:M], self.D[:M], self.CT[:B]
+        Xc = X[:, H:]
+        U1, U2 = self.U1[:M], self.U2[:M]
+        # linear_3d projections (modules.py:126-131, :94-96): plain library GEMMs (cuBLAS, fp32)
+        torch.mm(X, w["W_in"], out=U1)
+        U1.addmm_(Xc, w["W_c"])
+        U1.addmm_(D, w["W_i"])
+        torch.mm(P, w["W1"], out=U2)
+        U2.addmm_(Xc, w["W2"])
+        # query path (modules.py:138-139)
+        h1, q = self.h1[:B], self.q[:B]
+        torch.addmm(w["bq1"], CT, w["Wq1"], out=h1)
+        h1.relu_()
+        torch.addmm(w["bq2"], h1, w["Wq2"], out=q)
+        q.tanh_()
+        nv.counted_call("tcar_pool_fwd", 1, p(self.X), p(self.P), p(self.U1), p(self.U2), p(self.q), p(w["w_r"]),
+                        p(w["w_t"]), p(self.alpha), p(self.pooled), p(self.pooled_t), B, T)
+        a_ic, a_pt = self.a_ic[:B], self.a_pt[:B]
+        torch.addmm(w["b_a"], self.pooled[:B], w["W_a"], out=a_ic)
+        a_ic.tanh_()
+        torch.addmm(w["b_p"], self.pooled_t[:B], w["W_p"], out=a_pt)
+        a_pt.tanh_()
+        nv.counted_call("tcar_clip_time_tables", 1, p(w["month"]), p(w["day"]), p(w["week"]), p(w["hour"]),
+                        p(w["minute"]), p(ps.ct_tab), p(ps.ct_scale))
+        nv.counted_call("tcar_build_query", 1, p(self.a_ic), p(self.a_pt), p(ps.ct_tab), p(ps.item), p(ps.content),
+                        p(ps.mwdhm), p(bt.label), p(self.Tq), p(self.Q), p(self.c_ref), B)
+
+    def _cluster_for(self, B):
+        mt = (B + 127) // 128
+        c = min(self.cluster, 4)
+        while c > 1 and c > mt:
+            c //= 2
+        return max(c, 1)
+
+    def forward_train(self, bt):
+        """loss [B], cross_loss [B] (model_combine.py:145-147) and everything the backward needs."""
+        ps, p, B = self.ps, nv.ptr, bt.B
+        self._session_forward(bt)
+        ws = self._score_buffers(ps.n_pad, True)
+        nv.counted_call("tcar_score_fwd", 1, p(self.Q), p(ps.iext), p(self.c_ref), p(ws["E"]), p(ws["part"]), None, B,
+                        ps.N, ps.n_pad, 0, self._cluster_for(B))
+        nv.counted_call("tcar_ce_finish", 1, p(ws["part"]), p(self.sumexp), p(self.ce), ws["tiles"], B)
+        nv.counted_call("tcar_neg_loss", 1, p(self.a_ic), p(ps.item), p(ps.content), p(bt.neg), p(self.ce),
+                        p(self.negloss), p(self.loss), p(self.coef), p(self.dA_neg), B, bt.Nn)
+        return self.loss[:B], self.ce[:B]
+
+    def backward(self, bt):
+        """Gradients of sum_b loss_b wrt all 23 tensors (model_combine.py:156) into ps.item_g / ps.theta_g."""
+        ps, w, g, p, B, T = self.ps, self.ps.w, self.ps.g, nv.ptr, bt.B, bt.T
+        M = B * T
+        ws = self._score_buffers(ps.n_pad, True)
+        nv.counted_call("tcar_score_bwd_q", 2, p(ws["E"]), p(ps.iext), p(ws["qpart"]), p(self.dq_raw), B, ps.n_pad)
+        nv.counted_call("tcar_score_bwd_finish", 1, p(self.dq_raw), p(self.sumexp), p(self.dA_neg), p(self.a_ic),
+                        p(ps.ct_tab), p(ps.item), p(ps.content), p(ps.mwdhm), p(bt.label), p(self.d_a_ic),
+                        p(self.d_a_pt), p(self.dTq), p(self.Qs), B)
+        nv.counted_call("tcar_score_bwd_i", 1, p(ws["E"]), p(self.Qs), p(ps.item_g), B, ps.N, ps.n_pad)
+        # linear_2d tails (model_combine.py:119,127)
+        a_ic, a_pt = self.a_ic[:B], self.a_pt[:B]
+        dz_a = self.d_a_ic[:B].mul_(1 - a_ic * a_ic)
+        dz_p = self.d_a_pt[:B].mul_(1 - a_pt * a_pt)
+        torch.mm(self.pooled[:B].t(), dz_a, out=g["W_a"])
+        torch.sum(dz_a, 0, out=g["b_a"])
+        torch.mm(self.pooled_t[:B].t(), dz_p, out=g["W_p"])
+        torch.sum(dz_p, 0, out=g["b_p"])
+        dpooled = torch.mm(dz_a, w["W_a"].t())
+        dpooled_t = torch.mm(dz_p, w["W_p"].t())
+        nv.counted_call("tcar_pool_bwd", 1, p(self.X), p(self.P), p(self.U1), p(self.U2), p(self.q), p(w["w_r"]),
+                        p(w["w_t"]), p(self.alpha), p(dpooled), p(dpooled_t), p(self.dU1), p(self.dU2), p(self.dXi),
+                        p(self.dP), p(self.dq), p(self.de), B, T)
+        X, P, D, CT = self.X[:M], self.P[:M], self.D[:M], self.CT[:B]
+        Xc = X[:, H:]
+        S1, S2, dU1, dU2 = self.U1[:M], self.U2[:M], self.dU1[:M], self.dU2[:M]
+        de = self.de.view(-1)                      # kernel layout: [3][B*T] with the ACTUAL B*T as stride
+        torch.mv(S1.t(), de[:M], out=g["w_r"].view(-1))
+        torch.mv(S2.t(), de[2 * M: 3 * M], out=g["w_t"].view(-1))
+        torch.mm(X.t(), dU1, out=g["W_in"])
+        torch.mm(Xc.t(), dU1, out=g["W_c"])
+        torch.mm(D.t(), dU1, out=g["W_i"])
+        torch.mm(P.t(), dU2, out=g["W1"])
+        torch.mm(Xc.t(), dU2, out=g["W2"])
+        self.dXi[:M].addmm_(dU1, w["W_in"][:H].t())
+        torch.mm(dU1, w["W_i"].t(), out=self.dD[:M])
+        self.dP[:M].addmm_(dU2, w["W1"].t())
+        # query path backward (modules.py:138-139)
+        q, h1 = self.q[:B], self.h1[:B]
+        dzq = self.dq[:B].mul_(1 - q * q)
+        torch.mm(h1.t(), dzq, out=g["Wq2"])
+        torch.sum(dzq, 0, out=g["bq2"])
+        dh1 = torch.mm(dzq, w["Wq2"].t()).mul_(h1 > 0)
+        torch.mm(CT.t(), dh1, out=g["Wq1"])
+        torch.sum(dh1, 0, out=g["bq1"])
+        torch.mm(dh1, w["Wq1"].t(), out=self.dCT[:B])
+        nv.counted_call("tcar_small_table_grads", 1, p(bt.idx), p(bt.ctx), p(self.dXi), p(self.dP), p(self.dD),
+                        p(self.dCT), p(self.dTq), p(self.a_pt), p(w["pos"]), p(w["month"]), p(w["day"]),
+                        p(w["week"]), p(w["hour"]), p(w["minute"]), p(w["dur"]), p(g["pos"]), p(g["month"]),
+                        p(g["day"]), p(g["week"]), p(g["hour"]), p(g["minute"]), p(g["dur"]), B, T)
+        entries = B * T + B + B * bt.Nn
+        if 2 * entries > self.hash_size:
+            raise ValueError("batch too large for the sparse-gradient scratch")
+        nv.counted_call("tcar_scatter_add_rows", 2, p(bt.seq), p(bt.label), p(bt.neg), p(self.dXi), p(self.a_ic),
+                        p(self.coef), p(ps.item), p(ps.item_g), p(self.hash_keys), p(self.hash_acc), self.hash_size,
+                        B, T, bt.Nn)
+
+    def allreduce_grads(self):
+        """Data-parallel training: SUM (not mean -- the loss is a batch sum, model_combine.py:156) over ranks."""
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.ps.item_g, op=dist.ReduceOp.SUM)
+            dist.all_reduce(self.ps.theta_g, op=dist.ReduceOp.SUM)
+
+    def apply_gradients(self):
+        """per-tensor clip_by_norm + TF Adam (model_combine.py:155-163); also refreshes the bf16 scoring operand."""
+        ps, p = self.ps, nv.ptr
+        nv.counted_call("tcar_sqnorm_segments", 1, p(ps.theta_g), p(ps.seg_off), p(ps.sqnorm_small), len(SMALL))
+        nv.counted_call("tcar_sqnorm_big", 2, p(ps.item_g), p(ps.norm_partial), p(ps.sqnorm_item),
+                        ps.item_g.numel())
+        ps.step.add_(1)
+        self.global_step += 1
+        nv.counted_call("tcar_adam_small", 1, p(ps.theta), p(ps.theta_m), p(ps.theta_v), p(ps.theta_g), p(ps.seg_off),
+                        p(ps.sqnorm_small), len(SMALL), p(ps.step), self.lr, self.max_grad_f)
+        nv.counted_call("tcar_adam_item", 1, p(ps.item), p(ps.item_m), p(ps.item_v), p(ps.item_g), p(ps.sqnorm_item),
+                        p(ps.step), self.lr, self.max_grad_f, p(ps.iext), ps.N)
+
+    def train_step(self, bt):
+        """One `sess.run([loss, global_step, train_op])` (model_combine.py:231-234). Returns loss [B] (device)."""
+        loss, _ = self.forward_train(bt)
+        self.backward(bt)
+        self.allreduce_grads()
+        self.apply_gradients()
+        return loss
+
+    # ------------------------------------------------------------------------------------------- evaluation
+    def eval_step(self, bt, shard=None):
+        """Scores every candidate, returns (top20 ids [B,20], n_greater [B], cross_loss [B]) on the device.
+        shard = (item_lo, item_hi, iext_shard) restricts the scoring to a catalog shard (multi-GPU eval)."""
+        ps, p, B = self.ps, nv.ptr, bt.B
+        self._session_forward(bt)
+        if shard is None:
+            lo, n_loc, n_pad, iext = 0, ps.N, ps.n_pad, ps.iext
+        else:
+            lo, hi, iext = shard
+            n_loc, n_pad = hi - lo, iext.shape[0]
+        ws = self._score_buffers(n_pad, False)
+        nv.counted_call("tcar_score_fwd", 1, p(self.Q), p(iext), p(self.c_ref), None, p(ws["part"]), p(ws["cmax"]), B,
+                        n_loc, n_pad, 1, self._cluster_for(B))
+        nv.counted_call("tcar_ce_finish", 1, p(ws["part"]), p(self.sumexp), p(self.ce), ws["tiles"], B)
+        nv.counted_call("tcar_eval_topk", 1, p(ws["cmax"]), p(self.a_ic), p(self.Tq), p(ps.item), p(ps.content),
+                        p(ps.mwdhm), p(bt.label), p(self.top_ids), p(self.top_scores), p(self.n_greater), B, n_loc,
+                        n_pad, lo)
+        if self.world > 1 and shard is not None:
+            import torch.distributed as dist
+            G = self.world
+            ids = torch.empty(G, B, TOPK, device=self.dev, dtype=torch.int32)
+            sc = torch.empty(G, B, TOPK, device=self.dev)
+            dist.all_gather_into_tensor(ids, self.top_ids[:B].contiguous())
+            dist.all_gather_into_tensor(sc, self.top_scores[:B].contiguous())
+            dist.all_reduce(self.n_greater[:B], op=dist.ReduceOp.SUM)
+            dist.all_reduce(self.sumexp[:B], op=dist.ReduceOp.SUM)
+            nv.counted_call("tcar_topk_merge", 1, p(ids), p(sc), p(self.top_ids), p(self.top_scores), G, B)
+            torch.log(self.sumexp[:B], out=self.ce[:B])
+        return self.top_ids[:B], self.n_greater[:B], self.ce[:B]
+
+    def shard_bounds(self, G):
+        """Contiguous item-id ranges [lo, hi) per shard, aligned to 256 rows so that a shard of the bf16 scoring
+        operand is a plain row-slice of ps.iext."""
+        tiles = self.ps.n_pad // 256
+        per = (tiles + G - 1) // G
+        out = []
+        for g in range(G):
+            lo = min(g * per * 256, self.ps.N)
+            hi = min((g + 1) * per * 256, self.ps.N)
+            out.append((lo, hi))
+        return out
+
+    def iext_shard(self, lo, hi):
+        n_pad = max((hi - lo + 255) // 256 * 256, 256)
+        return self.ps.iext[lo: lo + n_pad]
+
+    def eval_step_virtual_shards(self, bt, G):
+        """Single-GPU emulation of the catalog-sharded evaluation: every shard is scored in turn and the per-shard
+        top-20 lists are merged with the same kernel the NCCL path uses (tests the merge logic without G GPUs)."""
+        B, p = bt.B, nv.ptr
+        ids = torch.empty(G, B, TOPK, device=self.dev, dtype=torch.int32)
+        sc = torch.empty(G, B, TOPK, device=self.dev)
+        ngt = torch.zeros(B, device=self.dev, dtype=torch.int32)
+        sumexp = torch.zeros(B, device=self.dev)
+        world, self.world = self.world, 1
+        try:
+            for g, (lo, hi) in enumerate(self.shard_bounds(G)):
+                if hi <= lo:
+                    ids[g].fill_(-1)
+                    sc[g].fill_(float("-inf"))
+                    continue
+                t, n, _ = self.eval_step(bt, shard=(lo, hi, self.iext_shard(lo, hi)))
+                ids[g].copy_(t)
+                sc[g].copy_(self.top_scores[:B])
+                ngt += n
+                sumexp += self.sumexp[:B]
+        finally:
+            self.world = world
+        nv.counted_call("tcar_topk_merge", 1, p(ids), p(sc), p(self.top_ids), p(self.top_scores), G, B)
+        return self.top_ids[:B], ngt, torch.log(sumexp)
+
+    def softmax_input(self, bt):
+        """Debug aid mirroring the reference's `softmax_input` fetch (model_combine.py:138): materialises the
+        [B,N] fp32 scores from the same bf16 operands with a library GEMM.  Not used on the hot path."""
+        self._session_forward(bt)
+        return self.Q[:bt.B].float() @ self.ps.iext[: self.ps.N].float().t()
+
+    # ------------------------------------------------------------------------------------------- metrics
+    def _categories(self):
+        if self._cat_array is None:
+            cat = np.zeros(self.N, dtype=np.int64)
+            codes = {}
+            for i in range(self.N):
+                # items without a category (MIND's extra candidates, mind_preprocess.py:275-280) get their own code
+                c = self.category_id.get(self.reverse_item.get(i, ("?", i)), ("?", i)) \
+                    if hasattr(self.category_id, "get") else self.category_id[self.reverse_item[i]]
+                cat[i] = codes.setdefault(c, len(codes))
+            self._cat_array = cat
+        return self._cat_array
+
+    def getILD(self, recList):
+        """model_combine.py:174-182, vectorised over the category codes."""
+        c = self._categories()[np.asarray(recList)]
+        n = len(c)
+        return float((c[:, None] != c[None, :]).sum()) / (n * (n - 1))
+
+    def getUnexp(self, inSeq, recList):
+        """model_combine.py:184-194."""
+        if len(recList) == 0:
+            return 0
+        cat = self._categories()
+        c, ci = cat[np.asarray(recList)], cat[np.asarray(inSeq) - 1]
+        return float((c[:, None] != ci[None, :]).sum()) / (len(c) * len(ci))
+
+    def printData(self, filename, batch_in, batch_out, batch_pred):
+        os.makedirs("saved", exist_ok=True)
+        with open("saved/CAR+P_Normal_predict_exa_" + filename + ".txt", "a+") as f:
+            for index in range(len(batch_in)):
+                f.write("# batch in: {} # batch out: {} # batch pred: {} \n".format(
+                    str(batch_in[index]), str(batch_out[index]), str(batch_pred[index])))
+
+    # ------------------------------------------------------------------------------------------- loops
+    def train(self, sess, item_dict, train_data, neighbor_dict, args, test_data=None, saver=None, threshold_acc=0.99):
+        """model_combine.py:196-252."""
+        (len_dict_train, session_dict_train, session_time_dict_train) = train_data
+        for epoch in range(self.epoch):
+            self.curEpoch = epoch
+            print("Epoch {}".format(epoch))
+            c = []
+            sampler = Sampler(len_dict_train, session_dict_train, session_time_dict_train, neighbor_dict, item_dict,
+                              args["neg_num"], batch_size=self.batch_size)
+            batch = 0
+            while sampler.has_next():
+                batch += 1
+                packed, B, T, Nn = sampler.next_packed()
+                if batch < 3:
+                    print(sampler.last_neg[0][:10])
+                bt = self.to_device(torch.from_numpy(packed).pin_memory(), B, T, Nn)
+                c.append(self.train_step(bt).clone())
+            avgc = float(torch.cat(c).mean().item()) if c else float("nan")
+            if math.isnan(avgc):
+                print("Epoch {}: NaN error!".format(str(epoch)))
+                self.error_during_train = True
+                return
+            print("\tloss: {:.6f}".format(avgc))
+            if test_data is not None:
+                recall = self.test(sess, test_data, args)
+                if recall > threshold_acc and args.get("save"):
+                    from .util import save_model
+                    print("Model saved - {}".format(save_model(self, args)))
+
+    def test(self, sess, test_data, args):
+        """model_combine.py:254-315."""
+        print("Measuring...")
+        (len_dict_test, session_dict_test, session_time_dict_test) = test_data
+        mrr20, recall20, ndcg20, ild20, unexp20, c_loss = [], [], [], [], [], []
+        sampler = Sampler(len_dict_test, session_dict_test, session_time_dict_test, batch_size=self.batch_size)
+        resultItemDict = {}
+        batch = 0
+        while sampler.has_next():
+            batch += 1
+            packed, B, T, Nn = sampler.next_packed()
+            batch_in, batch_out = sampler.last_in, sampler.last_out
+            bt = self.to_device(torch.from_numpy(packed).pin_memory(), B, T, Nn)
+            top, ngt, ce = self.eval_step(bt)
+            top, ngt, ce = top.cpu().numpy(), ngt.cpu().numpy(), ce.cpu().numpy()
+            if batch < 3:
+                print("batch_in:", batch_in[0])
+                print("batch_out:", batch_out[0])
+                print("batch pred:", top[0][:10].tolist())
+            ranks = ngt.astype(np.int64) + 1                                    # util.py:14
+            hit = ranks <= 20
+            recall20 += hit.tolist()
+            mrr20 += np.where(hit, 1.0 / ranks, 0.0).tolist()
+            ndcg20 += np.where(hit, 1.0 / np.log2(ranks + 1.0), 0.0).tolist()
+            c_loss += ce.tolist()
+            batch_pred = [[int(x) for x in row if x >= 0] for row in top]
+            for idx, pred in enumerate(batch_pred):
+                if self.category_id is not None and len(pred) > 1:
+                    ild20.append(self.getILD(pred))
+                    unexp20.append(self.getUnexp(batch_in[idx], pred))
+                for pi in pred:
+                    resultItemDict[pi] = resultItemDict.get(pi, 0) + 1
+            if args.get("is_print"):
+                self.printData(str(args["foldnum"]) + "_" + str(self.curEpoch), batch_in, batch_out, batch_pred)
+        self.last_metrics = {"loss": float(np.mean(c_loss)), "ild": float(np.mean(ild20)) if ild20 else 0.0,
+                             "unexp": float(np.mean(unexp20)) if unexp20 else 0.0, "coverage": len(resultItemDict),
+                             "mrr": float(np.mean(mrr20)), "recall": float(np.mean(recall20)),
+                             "ndcg": float(np.mean(ndcg20))}
+        print("avg loss...", self.last_metrics["loss"])
+        print("avg ILD...", self.last_metrics["ild"])
+        print("avg unexp...", self.last_metrics["unexp"])
+        print("len of result dict: ", len(resultItemDict))
+        print("MRR@20: {}, Recall@20: {}, nDCG@20: {}".format(self.last_metrics["mrr"], self.last_metrics["recall"],
+                                                                self.last_metrics["ndcg"]))
+        return self.last_metrics["recall"]

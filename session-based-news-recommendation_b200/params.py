@@ -1,0 +1,145 @@
+"""Device-resident parameter store of the TCAR model (layout chosen for B200).
+
+  item / content      [N+1, 256] fp32   256-float row pitch -> 128-bit aligned gathers (cols 250..255 are zero)
+  item Adam m, v, g   [N+1, 256] fp32
+  iext                [Npad, 640] bf16  scoring operand [item | content | one-hot time bins | 0]
+  theta / m / v / g   flat fp32         the 22 small tensors, concatenated in tf.trainable_variables() order
+                                        (model_combine.py:151) with a segment table for per-tensor clip_by_norm
+"""
+import numpy as np
+import torch
+
+from . import _native as nv
+
+H, HP, TH = nv.H, nv.HP, nv.TH
+
+# tf.trainable_variables() order of model_combine.py (item first, then these 22)
+SMALL = [
+    ("pos", (40, H)), ("month", (13, TH)), ("day", (32, TH)), ("week", (8, TH)), ("hour", (25, TH)),
+    ("minute", (61, TH)), ("dur", (11, TH)),
+    ("W_in", (2 * H, H)), ("W_c", (H, H)), ("W_i", (TH, H)), ("w_r", (H, 1)),
+    ("Wq1", (2 * TH, H)), ("bq1", (H,)), ("Wq2", (H, 2 * H)), ("bq2", (2 * H,)),
+    ("W_a", (2 * H, 2 * H)), ("b_a", (2 * H,)),
+    ("W1", (5 * TH, H)), ("W2", (H, H)), ("w_t", (H, 1)),
+    ("W_p", (5 * TH, 5 * TH)), ("b_p", (5 * TH,)),
+]
+PARAM_ORDER = ["item"] + [n for n, _ in SMALL]
+
+
+def _pad4(n):
+    return (n + 3) // 4 * 4
+
+
+class ParamStore:
+    def __init__(self, n_items, content_emb, mwdhm, device="cuda"):
+        """content_emb [N+1, 250] (row 0 = pad), mwdhm [N, 5] int (month, day, isoweekday, hour+1, minute+1)."""
+        self.N = int(n_items)
+        self.n_pad = (self.N + 255) // 256 * 256
+        self.device = torch.device(device)
+        dev = self.device
+        content_emb = np.asarray(content_emb, dtype=np.float32)
+        if content_emb.shape != (self.N + 1, H):
+            raise ValueError(f"content_emb must be [{self.N + 1}, {H}], got {content_emb.shape}")
+        mwdhm = np.asarray(mwdhm)
+        if mwdhm.shape != (self.N, 5):
+            raise ValueError(f"publish_time_MWDHM must be [{self.N}, 5], got {mwdhm.shape}")
+        hi = np.array([12, 31, 7, 24, 60])
+        if (mwdhm < 0).any() or (mwdhm > hi).any():
+            raise ValueError("publish_time_MWDHM out of range for the month/day/week/hour/minute tables")
+        self.content = torch.zeros(self.N + 1, HP, device=dev)
+        self.content[:, :H] = torch.from_numpy(content_emb).to(dev)
+        self.mwdhm = torch.from_numpy(mwdhm.astype(np.int32)).contiguous().to(dev)
+        self.item = torch.zeros(self.N + 1, HP, device=dev)
+        self.item_m = torch.zeros_like(self.item)
+        self.item_v = torch.zeros_like(self.item)
+        self.item_g = torch.zeros_like(self.item)
+        self.iext = torch.zeros(self.n_pad, nv.KEXT, device=dev, dtype=torch.bfloat16)
+        # flat small-parameter buffer; every segment starts 16-byte aligned
+        offs, off = [], 0
+        for _, shp in SMALL:
+            offs.append(off)
+            off += _pad4(int(np.prod(shp)))
+        self.seg_start = offs
+        self.seg_len = [int(np.prod(s)) for _, s in SMALL]
+        self.flat_size = off
+        # clip_by_norm / Adam run per tensor over [start, start+len): pads stay zero because their grads are zero
+        seg = []
+        for s, l in zip(self.seg_start, self.seg_len):
+            seg.append(s)
+        seg_off = np.array(self.seg_start + [off], dtype=np.int32)
+        self.seg_off = torch.from_numpy(seg_off).to(dev)
+        self.theta = torch.zeros(off, device=dev)
+        self.theta_m = torch.zeros_like(self.theta)
+        self.theta_v = torch.zeros_like(self.theta)
+        self.theta_g = torch.zeros_like(self.theta)
+        self.sqnorm_small = torch.zeros(len(SMALL), device=dev)
+        self.sqnorm_item = torch.zeros(1, device=dev)
+        self.norm_partial = torch.zeros(1184, device=dev)
+        self.step = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.w = {n: self._view(self.theta, i) for i, (n, _) in enumerate(SMALL)}
+        self.g = {n: self._view(self.theta_g, i) for i, (n, _) in enumerate(SMALL)}
+        self.ct_tab = torch.zeros(nv.NBINS, TH, device=dev)
+        self.ct_scale = torch.zeros(nv.NBINS, device=dev)
+
+    def _view(self, flat, i):
+        s, l = self.seg_start[i], self.seg_len[i]
+        return flat[s:s + l].view(SMALL[i][1])
+
+    # ------------------------------------------------------------------ initialisation / import / export
+    def init_reference(self, emb_stddev=0.002, stddev=0.05, seed=2020):
+        """Reference initialisers: embedding tables from the GLOBAL legacy NumPy stream in creation order
+        (modules.py:32; main.py:11-12 seeds it with 2020), dense weights ~ N(0, stddev) (modules.py:50-51,65)."""
+        p = {}
+        for name, sd, zero_pad in [("item", emb_stddev, True), ("pos", 0.02, False), ("month", emb_stddev, True),
+                                   ("day", emb_stddev, True), ("week", emb_stddev, True), ("hour", emb_stddev, True),
+                                   ("minute", emb_stddev, True), ("dur", emb_stddev, False)]:
+            shp = (self.N + 1, H) if name == "item" else dict(SMALL)[name]
+            t = np.random.normal(0, sd, shp)
+            if zero_pad:
+                t[0] = 0.0
+            p[name] = t.astype(np.float32)
+        g = np.random.default_rng(seed)
+        for name, shp in SMALL[7:]:
+            p[name] = g.normal(0, stddev, shp).astype(np.float32)
+        self.load(p)
+
+    def load(self, params):
+        """params: dict name -> array/tensor in the reference shapes (item [N+1,250])."""
+        dev = self.device
+        item = torch.as_tensor(np.asarray(params["item"], dtype=np.float32))
+        self.item.zero_()
+        self.item[:, :H] = item.to(dev)
+        for n, shp in SMALL:
+            self.w[n].copy_(torch.as_tensor(np.asarray(params[n], dtype=np.float32)).view(shp).to(dev))
+        for t in (self.item_m, self.item_v, self.theta_m, self.theta_v):
+            t.zero_()
+        self.step.zero_()
+        self.rebuild_iext()
+
+    def export(self):
+        out = {"item": self.item[:, :H].detach().cpu().clone()}
+        for n, _ in SMALL:
+            out[n] = self.w[n].detach().cpu().clone()
+        return out
+
+    def export_grads(self):
+        out = {"item": self.item_g[:, :H].detach().cpu().clone()}
+        for n, _ in SMALL:
+            out[n] = self.g[n].detach().cpu().clone()
+        return out
+
+    def rebuild_iext(self):
+        nv.call("tcar_build_iext", nv.ptr(self.item), nv.ptr(self.content), nv.ptr(self.mwdhm), nv.ptr(self.iext),
+                self.N, self.n_pad)
+
+    def state_dict(self):
+        return {"params": self.export(), "item_m": self.item_m[:, :H].cpu(), "item_v": self.item_v[:, :H].cpu(),
+                "theta_m": self.theta_m.cpu(), "theta_v": self.theta_v.cpu(), "step": int(self.step.item())}
+
+    def load_state_dict(self, sd):
+        self.load(sd["params"])
+        self.item_m[:, :H] = sd["item_m"].to(self.device)
+        self.item_v[:, :H] = sd["item_v"].to(self.device)
+        self.theta_m.copy_(sd["theta_m"].to(self.device))
+        self.theta_v.copy_(sd["theta_v"].to(self.device))
+        self.step.fill_(int(sd["step"]))

@@ -1,0 +1,191 @@
+"""Host-side batch production -- mirrors the reference's sampler.Sampler (sampler.py:23-140) API and RNG use.
+
+`Sampler(len_dict, session_dict, session_time_dict, neighbor_dict, item_dict, neg_num, batch_size)` with
+`has_next()` / `next_batch()` returning the reference's 6-tuple of Python lists, plus `next_packed()`, which emits
+the same indices as ONE contiguous int32 array (the layout `model_combine.Batch` consumes) so that a batch costs a
+single pinned host->device copy.
+
+Differences from the reference, all documented in DESIGN.md:
+  * per-click time features are extracted once per session and cached (the reference re-reads datetime attributes
+    for every click of every epoch); the values are identical;
+  * the dwell-time bucket is clamped to 10: `bucketized` returns 11 for active_t >= 1024 s, which is out of range
+    for the 11-row duration table (sampler.py:18-21; TF-CPU would raise, TF-GPU returns zeros);
+  * negatives of a batch come from one vectorised `np.random.randint` call per session -- the legacy global NumPy
+    stream yields the same values as the reference's scalar calls (tests/test_host_sampler.py).
+"""
+import math
+import random
+
+import numpy as np
+
+_FEATURE_CACHE = {}
+
+
+def bucketized(seconds):
+    """sampler.py:18-21 -- index of the first boundary in [0..10] that is >= log2(seconds + 1)."""
+    return int(np.searchsorted(np.arange(0, 11), np.log2(seconds + 1)))
+
+
+def _session_features(times):
+    """[(month, day, isoweekday, hour+1, minute+1, gap)] per input click and the click context of the last input
+    click (sampler.py:79-87,105-109)."""
+    n = len(times) - 1
+    feats = np.empty((6, n), dtype=np.int32)
+    for j in range(n):
+        t = times[j]
+        p = t["publish_t"]
+        feats[0, j], feats[1, j], feats[2, j] = p.month, p.day, p.isoweekday()
+        feats[3, j], feats[4, j] = p.hour + 1, p.minute + 1
+        feats[5, j] = bucketized(t["active_t"])
+    c = times[n - 1]["click_t"]
+    ctx = (c.month - 1, c.day - 1, c.isoweekday() - 1, c.hour, c.minute)
+    return feats, ctx
+
+
+class Sampler(object):
+    def __init__(self, len_dict, session_dict, session_time_dict=None, neighbor_dict=None, item_dict=None,
+                 neg_num=None, batch_size=1024, negative_mode="uniform", verbose=True):
+        if verbose:
+            print("Sampler init begin...")
+        self.session_num = len(session_dict)
+        self.batch_size = batch_size
+        self.batch_i = 0
+        self.neighbor_dict = neighbor_dict
+        self.item_dict = item_dict
+        if item_dict is not None:
+            self.item_num = len(item_dict)
+        self.neg_num = neg_num
+        self.negative_mode = negative_mode          # "uniform" (shipped, sampler.py:98-99) | "impression" (:96,118-131)
+        self.len_dict = len_dict
+        self.session_dict = session_dict
+        self.session_time_dict = session_time_dict
+        self.session_id_batches = []
+        for _slen, session_ids in self.len_dict.items():
+            random.shuffle(session_ids)             # in place, like the reference (affects later epochs)
+            while len(session_ids) > batch_size:
+                self.session_id_batches.append(session_ids[:batch_size])
+                session_ids = session_ids[batch_size:]
+            if len(session_ids):
+                self.session_id_batches.append(session_ids)
+        self.batch_num = len(self.session_id_batches)
+        random.shuffle(self.session_id_batches)
+        # cache keyed by the dict object (kept alive by the cache entry so the id cannot be recycled)
+        self._cache = _FEATURE_CACHE.setdefault(id(session_time_dict), (session_time_dict, {}))[1] \
+            if session_time_dict else None
+        self.last_in = self.last_out = self.last_neg = None
+        if verbose:
+            print("Sampler init finished, batch size : {}, # batch: {}.".format(self.batch_size, self.batch_num))
+
+    def has_next(self):
+        return self.batch_i < self.batch_num
+
+    def _features(self, sid):
+        f = self._cache.get(sid)
+        if f is None:
+            f = self._cache[sid] = _session_features(self.session_time_dict[sid])
+        return f
+
+    def _negatives(self, sid):
+        if not self.neighbor_dict:
+            return []
+        if self.negative_mode == "impression":
+            return self.neg_neighbor_from_impre(int(str(sid).split("_")[0]))
+        return np.random.randint(0, self.item_num, size=self.neg_num).tolist()
+
+    def next_batch(self):
+        """The reference's return value: (batch_in, batch_out, 5 publish lists, 5 click lists, neg, gap)."""
+        ids = self.session_id_batches[self.batch_i]
+        batch_in, batch_out, neg_all, gap_all = [], [], [], []
+        pt = ([], [], [], [], [])
+        ct = ([], [], [], [], [])
+        for sid in ids:
+            seq = self.session_dict[sid]
+            batch_in.append(seq[:-1])
+            batch_out.append(seq[-1] - 1)
+            neg, gap = [], []
+            if self.session_time_dict:
+                feats, ctx = self._features(sid)
+                for k in range(5):
+                    pt[k].append(feats[k].tolist())
+                    ct[k].append(ctx[k])
+                gap = feats[5].tolist()
+                neg = self._negatives(sid)
+            neg_all.append(neg)
+            gap_all.append(gap)
+        self.batch_i += 1
+        self.last_in, self.last_out, self.last_neg = batch_in, batch_out, neg_all
+        return batch_in, batch_out, pt, ct, neg_all, gap_all
+
+    def next_packed(self):
+        """Same batch as next_batch() as one int32 array [7*B*T | 2*B | B | B*Nn] (see model_combine.Batch)."""
+        ids = self.session_id_batches[self.batch_i]
+        B = len(ids)
+        T = len(self.session_dict[ids[0]]) - 1
+        Nn = self.neg_num if (self.neighbor_dict and self.neg_num) else 0
+        M = B * T
+        out = np.empty(7 * M + 3 * B + B * Nn, dtype=np.int32)
+        idx = out[: 7 * M].reshape(7, B, T)
+        ctx = out[7 * M: 7 * M + 2 * B].reshape(2, B)
+        label = out[7 * M + 2 * B: 7 * M + 3 * B]
+        negs = out[7 * M + 3 * B:].reshape(B, Nn) if Nn else None
+        batch_in, neg_all = [], []
+        for b, sid in enumerate(ids):
+            seq = self.session_dict[sid]
+            batch_in.append(seq[:-1])
+            idx[0, b] = seq[:-1]
+            label[b] = seq[-1] - 1
+            feats, c = self._features(sid)
+            idx[1:6, b] = feats[:5]
+            idx[6, b] = np.minimum(feats[5], 10)
+            ctx[0, b], ctx[1, b] = c[2], c[3]
+            if Nn:
+                neg = self._negatives(sid)
+                negs[b] = neg
+                neg_all.append(neg)
+        self.batch_i += 1
+        self.last_in, self.last_out, self.last_neg = batch_in, label.tolist(), neg_all
+        return out, B, T, Nn
+
+    def neg_neighbor_from_impre(self, sessionid):
+        """sampler.py:118-131."""
+        neighor_set = self.neighbor_dict[sessionid]
+        neg, cnt = [], 0
+        while len(neg) < self.neg_num:
+            cnt += 1
+            randomid = random.choice(neighor_set)
+            if randomid in self.item_dict:
+                neg.append(self.item_dict[randomid] - 1)
+            if cnt > 20:
+                break
+        while len(neg) < self.neg_num:
+            neg.append(int(np.random.randint(0, self.item_num)))
+        return neg
+
+    def neg_neighbor(self, itemid):
+        """sampler.py:133-140 (publish-time neighbours; needs data_process/generate_neighbor.py output)."""
+        neighor_set = self.neighbor_dict[itemid]
+        neg = []
+        while len(neg) < self.neg_num:
+            randomid = random.choice(neighor_set)
+            if randomid != itemid:
+                neg.append(randomid)
+        return neg
+
+
+def pack_batch(batch_in, batch_out, batch_pt, batch_ct, neg, gap):
+    """Reference 6-tuple of lists -> (int32 array, B, T, Nn) in the model_combine.Batch layout."""
+    B, T = len(batch_in), len(batch_in[0])
+    Nn = len(neg[0]) if neg and len(neg[0]) else 0
+    M = B * T
+    out = np.empty(7 * M + 3 * B + B * Nn, dtype=np.int32)
+    idx = out[: 7 * M].reshape(7, B, T)
+    idx[0] = np.asarray(batch_in, dtype=np.int32)
+    for k in range(5):
+        idx[1 + k] = np.asarray(batch_pt[k], dtype=np.int32)
+    idx[6] = np.minimum(np.asarray(gap, dtype=np.int32), 10)
+    out[7 * M: 7 * M + B] = np.asarray(batch_ct[2], dtype=np.int32)
+    out[7 * M + B: 7 * M + 2 * B] = np.asarray(batch_ct[3], dtype=np.int32)
+    out[7 * M + 2 * B: 7 * M + 3 * B] = np.asarray(batch_out, dtype=np.int32)
+    if Nn:
+        out[7 * M + 3 * B:] = np.asarray(neg, dtype=np.int32).reshape(-1)
+    return out, B, T, Nn

@@ -1,0 +1,240 @@
+"""GPU parity of the whole hot path against the CPU oracle (oracle/tcar_oracle.py, fp64), through the C ABI.
+
+Tolerances (stated): the session side is fp32 -> rtol 1e-4 / atol 1e-6 vs the fp64 oracle; everything
+that passes through the bf16 scoring GEMMs (loss, scoring gradients) -> loss atol 2e-2, gradients 2e-2 norm-wise;
+integer results (gather indices, top-20 ids on margin-checked queries, ranks) are exact."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import tcar_oracle as O  # noqa: E402
+
+
+def build(N, emb_scale=1.0, Nn=20, seed=3, max_grad=150, lr=0.001):
+    from tcar_b200 import synth
+    from tcar_b200.model_combine import Seq2SeqAttNN
+    content, mwdhm, category = synth.make_catalog(N, seed=seed)
+    np.random.seed(2020)
+    args = dict(publish_time_MWDHM=mwdhm, itemnum=N, category_id={i: int(category[i]) for i in range(N)},
+                item_freq_dict_norm={}, reverse_item={i: i for i in range(N)}, content_emb=content,
+                emb_stddev=0.002 * emb_scale, stddev=0.05, hidden_size=250, time_hidden_size=64, l2_emb=0.0,
+                batch_size=512, epoch=1, neg_num=Nn, lr=lr, max_grad=max_grad)
+    model = Seq2SeqAttNN(args)
+    return model, content, mwdhm, args
+
+
+def batch_for(model, N, B, T, Nn, mwdhm, seed):
+    from tcar_b200 import synth
+    packed = synth.make_index_batch(N, B, T, Nn, mwdhm, seed=seed)
+    if B > 2 and T > 1:
+        packed[:T] = packed[T]                 # duplicate clicked ids (scatter-add determinism / dedup)
+    bt = model.to_device(torch.from_numpy(packed).pin_memory(), B, T, Nn)
+    batch = {k: torch.from_numpy(v) for k, v in synth.unpack(packed, B, T, Nn).items()}
+    return bt, batch
+
+
+def oracle_inputs(model, content, mwdhm):
+    params = {k: v.double() for k, v in model.ps.export().items()}
+    return params, torch.from_numpy(content).double(), torch.from_numpy(mwdhm.astype(np.int64))
+
+
+@pytest.mark.parametrize("B,T,scale", [(1, 1, 1.0), (7, 3, 100.0), (130, 20, 1.0), (64, 40, 100.0), (512, 2, 100.0)])
+def test_session_forward_fp32(B, T, scale):
+    """gather (clip active when scale=100), pooling, tails: fp32 kernels vs fp64 oracle."""
+    N = 1200
+    model, content, mwdhm, _ = build(N, emb_scale=scale)
+    bt, batch = batch_for(model, N, B, T, 20, mwdhm, seed=B + T)
+    model._session_forward(bt)
+    torch.cuda.synchronize()
+    params, c64, m64 = oracle_inputs(model, content, mwdhm)
+    with torch.no_grad():
+        ref = O.forward(params, c64, m64, batch)
+    M = B * T
+    for name, got, want in [("X", model.X[:M], ref["X"].reshape(M, -1)), ("P", model.P[:M], ref["P"].reshape(M, -1)),
+                            ("D", model.D[:M], ref["D"].reshape(M, -1)), ("ct", model.CT[:B], ref["ct"]),
+                            ("pooled", model.pooled[:B], ref["pooled"]), ("pooled_t", model.pooled_t[:B], ref["pooled_t"]),
+                            ("a_ic", model.a_ic[:B], ref["a_ic"]), ("a_pt", model.a_pt[:B], ref["a_pt"])]:
+        np.testing.assert_allclose(got.cpu().double().numpy(), want.numpy(), rtol=1e-4, atol=2e-6, err_msg=name)
+    al = model.alpha.view(-1)                       # [3][B*T], stride = actual B*T
+    alpha = (al[:M] + al[M:2 * M]).view(B, T)
+    np.testing.assert_allclose(alpha.cpu().double().numpy(), ref["alpha"].numpy(), rtol=1e-4, atol=1e-6)
+    # query operand and the label score (fp32 exact path)
+    S = ref["softmax_input"]
+    lab = batch["label"]
+    np.testing.assert_allclose(model.c_ref[:B].cpu().double().numpy(), S.gather(1, lab[:, None]).squeeze(1).numpy(),
+                               rtol=1e-4, atol=1e-5)
+
+
+def relerr(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.mark.parametrize("B,T,scale,Nn", [(5, 1, 1.0, 20), (130, 3, 100.0, 20), (512, 20, 1.0, 20), (96, 40, 30.0, 7)])
+def test_train_step_loss_and_gradients(B, T, scale, Nn):
+    N = 3000
+    model, content, mwdhm, _ = build(N, emb_scale=scale, Nn=Nn)
+    bt, batch = batch_for(model, N, B, T, Nn, mwdhm, seed=10 + B)
+    params, c64, m64 = oracle_inputs(model, content, mwdhm)
+    out, grads = O.loss_and_grads(params, c64, m64, batch)
+    loss, ce = model.forward_train(bt)
+    model.backward(bt)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(loss.cpu().double().numpy(), out["loss"].numpy().ravel(), rtol=5e-3, atol=2e-2)
+    np.testing.assert_allclose(ce.cpu().double().numpy(), out["cross_loss"].numpy().ravel(), rtol=5e-3, atol=2e-2)
+    np.testing.assert_allclose(model.negloss[:B].cpu().double().numpy(), out["neg_feedback"].numpy().ravel(),
+                               rtol=1e-3, atol=1e-5)
+    got = model.ps.export_grads()
+    # norm-wise: ||g - g_ref|| <= 2e-2 ||g_ref|| + 1e-7 ||g_all||  (the absolute floor covers tensors whose true
+    # gradient is ~1e-9, e.g. the attention weights at T=1 where fp32 rounds alpha to exactly 1)
+    total = float(torch.sqrt(sum((grads[k].double() ** 2).sum() for k in O.PARAM_ORDER)))
+    errs = {k: float((got[k].double() - grads[k].double()).norm()) / (float(grads[k].double().norm()) + 5e-6 * total)
+            for k in O.PARAM_ORDER}
+    bad = {k: v for k, v in errs.items() if v > 2e-2}
+    assert not bad, f"gradient norm-wise rel err too large: {bad} (all: {errs})"
+    assert (model.ps.item_g[:, 250:] == 0).all() and (model.ps.item_g[0] == 0).all()
+    assert (model.hash_keys == -1).all() and (model.hash_acc == 0).all(), "scatter scratch must be restored"
+
+
+def test_adam_clip_kernels_match_oracle_given_same_grads():
+    """clip_by_norm + TF-Adam kernels in isolation: feed the oracle optimiser the GPU's own gradients."""
+    N, B, T = 2000, 64, 4
+    for max_grad in (150, 0.05):
+        model, content, mwdhm, _ = build(N, emb_scale=50.0, max_grad=max_grad)
+        params = {k: v.clone() for k, v in model.ps.export().items()}
+        adam = O.TFAdam(params, 0.001)
+        for step in range(3):
+            bt, _ = batch_for(model, N, B, T, 20, mwdhm, seed=step)
+            model.forward_train(bt)
+            model.backward(bt)
+            g = model.ps.export_grads()
+            model.apply_gradients()
+            torch.cuda.synchronize()
+            adam.step(params, {k: O.clip_by_norm(v, float(max_grad)) for k, v in g.items()})
+            now = model.ps.export()
+            for k in O.PARAM_ORDER:
+                np.testing.assert_allclose(now[k].numpy(), params[k].numpy(), rtol=2e-5, atol=2e-7, err_msg=f"{k} step {step}")
+        # the bf16 scoring operand is refreshed by the Adam kernel
+        it = model.ps.iext[:N, :250].float().cpu()
+        np.testing.assert_allclose(it.numpy(), now["item"][1:].bfloat16().float().numpy(), rtol=0, atol=0)
+
+
+def test_training_trajectory_tracks_oracle():
+    N, B, T = 2000, 128, 3
+    model, content, mwdhm, _ = build(N, emb_scale=1.0, lr=0.001)
+    params, c64, m64 = oracle_inputs(model, content, mwdhm)
+    adam = O.TFAdam(params, 0.001)
+    for step in range(6):
+        bt, batch = batch_for(model, N, B, T, 20, mwdhm, seed=100 + step)
+        loss = model.train_step(bt).cpu().double().numpy()
+        out, _ = O.train_step(params, adam, c64, m64, batch, max_grad=150.0)
+        np.testing.assert_allclose(loss.mean(), out["loss"].numpy().mean(), rtol=5e-3, err_msg=f"step {step}")
+    assert int(model.ps.step.item()) == 6
+
+
+def test_train_step_is_deterministic():
+    N, B, T = 3000, 200, 5
+    outs = []
+    for _ in range(2):
+        model, content, mwdhm, _ = build(N, emb_scale=100.0)
+        bt, _ = batch_for(model, N, B, T, 20, mwdhm, seed=4)
+        model.train_step(bt)
+        torch.cuda.synchronize()
+        outs.append((model.ps.item_g.clone(), model.ps.theta_g.clone(), model.ps.item.clone(), model.loss[:B].clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
+def margin_ok(scores, k=20, rel=2e-5):
+    s = np.sort(scores, axis=1)[:, ::-1]
+    gaps = np.abs(np.diff(s[:, : k + 1], axis=1)).min(1)
+    return gaps > rel * np.abs(s[:, :k + 1]).max(1)
+
+
+@pytest.mark.parametrize("B,T,N", [(3, 1, 300), (200, 4, 5000), (512, 20, 9000)])
+def test_eval_top20_rank_and_loss(B, T, N):
+    model, content, mwdhm, args = build(N, emb_scale=20.0)
+    bt, batch = batch_for(model, N, B, T, 0, mwdhm, seed=B)
+    params, c64, m64 = oracle_inputs(model, content, mwdhm)
+    ref = O.eval_batch(params, c64, m64, batch, args["category_id"], args["reverse_item"])
+    top, ngt, ce = model.eval_step(bt)
+    torch.cuda.synchronize()
+    top, ngt = top.cpu().numpy(), ngt.cpu().numpy()
+    ok = margin_ok(ref["scores"])
+    assert ok.mean() > 0.6, "synthetic eval set must be mostly margin-checked"
+    assert (top[ok] == ref["top20"][ok]).all(), "top-20 ids must be bit-exact on margin-checked queries"
+    # the un-margined queries may only differ by swaps of near-tied neighbours: same id SET at positions 1..19
+    same_set = [set(a[:19]) <= set(b) for a, b in zip(ref["top20"], top)]
+    assert np.mean(same_set) > 0.98
+    labels = batch["label"].numpy()
+    ref_rank = np.array([int((row[l] < row).sum()) + 1 for row, l in zip(ref["scores"], labels)])
+    hit_ref = ref_rank <= 20
+    assert ((ngt + 1 <= 20) == hit_ref)[ok].all()
+    assert (ngt + 1 == ref_rank)[ok & hit_ref].all()
+    np.testing.assert_allclose(ce.cpu().numpy(), ref["cross_loss"].ravel(), rtol=5e-3, atol=2e-2)
+    # Recall / MRR / ILD identical on the margin-checked subset
+    ild = [model.getILD(list(t)) for t in top[ok]]
+    np.testing.assert_allclose(ild, np.array(ref["ild"])[ok])
+    un = [model.getUnexp(list(batch["seq"][i].numpy()), list(top[i])) for i in np.nonzero(ok)[0]]
+    np.testing.assert_allclose(un, np.array(ref["unexp"])[ok])
+
+
+def test_eval_ties_resolve_to_lower_id():
+    """Duplicate catalog rows score identically; both the oracle's defined order and the kernel put the lower id first."""
+    from tcar_b200 import synth
+    N, B, T = 2000, 64, 3
+    model, content, mwdhm, args = build(N, emb_scale=20.0)
+    p = model.ps.export()
+    rs = np.random.RandomState(0)
+    src = rs.choice(N - 1, 300, replace=False)
+    dst = (src + 1)
+    cont = content.copy()
+    mw = mwdhm.copy()
+    for s_, d_ in zip(src, dst):
+        p["item"][d_ + 1] = p["item"][s_ + 1]
+        cont[d_ + 1] = cont[s_ + 1]
+        mw[d_] = mw[s_]
+    from tcar_b200.params import ParamStore
+    model.ps = ParamStore(N, cont, mw, model.dev)
+    model.ps.load(p)
+    bt, batch = batch_for(model, N, B, T, 0, mw, seed=9)
+    params, c64, m64 = oracle_inputs(model, cont, mw)
+    ref = O.eval_batch(params, c64, m64, batch, args["category_id"], args["reverse_item"])
+    top, _, _ = model.eval_step(bt)
+    top = top.cpu().numpy()
+    s = np.sort(ref["scores"], axis=1)[:, ::-1][:, :21]
+    d = np.abs(np.diff(s, axis=1))
+    ok = ((d == 0) | (d > 1e-4 * np.abs(s).max(1, keepdims=True))).all(1)     # exact ties or clear margins only
+    assert ok.mean() > 0.8 and (d[ok] == 0).any(), "fixture must contain exact ties inside the top-20"
+    assert (top[ok] == ref["top20"][ok]).all()
+
+
+@pytest.mark.parametrize("G", [2, 4, 8])
+def test_virtual_shards_equal_single_device(G):
+    N, B, T = 7000, 150, 4
+    model, content, mwdhm, _ = build(N, emb_scale=20.0)
+    bt, _ = batch_for(model, N, B, T, 0, mwdhm, seed=2)
+    top1, n1, ce1 = [x.clone() for x in model.eval_step(bt)]
+    topg, ng, ceg = model.eval_step_virtual_shards(bt, G)
+    torch.cuda.synchronize()
+    assert torch.equal(top1, topg), "sharded top-20 ids must equal the 1-GPU result bit-for-bit"
+    hit = n1 < 20
+    assert torch.equal(hit, ng < 20) and torch.equal(n1[hit], ng[hit])
+    np.testing.assert_allclose(ceg.cpu().numpy(), ce1.cpu().numpy(), rtol=1e-5)
+
+
+def test_softmax_input_debug_fetch_and_reference_loops():
+    """Seq2SeqAttNN.train / .test with the reference signatures on a tiny pickle-layout dataset."""
+    import tempfile
+    from tcar_b200 import main as tmain, synth
+    with tempfile.TemporaryDirectory() as d:
+        root = d + "/synth/TCAR-mid/Normal/"
+        synth.write_dataset(root, N=1500, n_train=700, n_test=150, fold=0)
+        args = tmain.build_parser().parse_args(["--datapath", d + "/", "--dataset", "synth/TCAR-mid/", "--foldnum", "0",
+                                                "--epoch", "1", "--batch_size", "256"])
+        model = tmain.main(args)
+        assert not model.error_during_train
+        m = model.last_metrics
+        assert 0 <= m["recall"] <= 1 and np.isfinite(m["loss"]) and m["coverage"] > 0
