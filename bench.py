@@ -1,0 +1,441 @@
+#!/usr/bin/env python
+"""bench.py -- TCAR train sessions/s (+ full-catalog top-20 eval queries/s) on synthetic Globo-shaped data.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                  this repo's B200 path
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]  the reference's CPU arithmetic (oracle port)
+
+One "step" = one `sess.run([loss, global_step, train_op])` of the reference (model_combine.py:231-234): forward,
+losses, gradients, per-tensor clip and Adam over one length-bucketed batch of 512 sessions against the full
+364 047-article catalog.  N>1 (torchrun, one rank per GPU): data-parallel, every rank owns a batch of 512 sessions
+(weak scaling) and the gradients are summed with one NCCL all-reduce per step.  Rank 0 prints ONE JSON line.
+
+Nothing here reads /root/reference.  oracle/ is executed only by the `cpu_baseline` leg and by `--impl reference`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GLOBO_N = 364047           # Globo articles_metadata.csv row count
+K_REF = 820                # scoring K of the reference graph (2H + 5Th, model_combine.py:132-136)
+K_DITEM = 570              # columns of the candidate matrix that carry trainable parameters (250 item + 320 time)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--items", type=int, default=GLOBO_N)
+    ap.add_argument("--batch", type=int, default=512)
+    ap.add_argument("--session_len", type=int, default=20, help="clicks per session (reference --maxlen)")
+    ap.add_argument("--neg_num", type=int, default=20)
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--no_kernels", action="store_true", help="skip the per-kernel roofline pass")
+    ap.add_argument("--cpu_sample_sessions", type=int, default=512)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------- helpers
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm": float(d["hbm_gbs"]), "tensor_burst": float(d["bf16_tflops"]),
+                "tensor_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "source": "measured"}
+    return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load" = samples in the upper half of the observed power range
+        thr = (max(pw) + min(pw)) / 2
+        load = [s for s, p in zip(sm, pw) if p >= thr] or sm
+        load.sort()
+        return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_batches(synth, N, B, T, Nn, mwdhm, n, seed0):
+    import torch
+    out = []
+    for i in range(n):
+        packed = synth.make_index_batch(N, B, T, Nn, mwdhm, seed=seed0 + i)
+        out.append(torch.from_numpy(packed).pin_memory() if torch.cuda.is_available() else torch.from_numpy(packed))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------- CPU arms
+def oracle_train_rate(N, B, T, Nn, steps, warmup, content, mwdhm, seed=11):
+    """Times the CPU oracle's train step (fwd + bwd + clip + TF-Adam, fp32, all host threads) on batches of B
+    sessions against the full N-item catalog.  Returns (sessions/s, ms/step, threads)."""
+    import numpy as np
+    import torch
+    from oracle import tcar_oracle as O
+    from tcar_b200 import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    p = O.init_params(N)
+    adam = O.TFAdam(p, 0.001)
+    c = torch.from_numpy(content)
+    mw = torch.from_numpy(mwdhm.astype(np.int64))
+    batches = []
+    for i in range(min(steps + warmup, 4)):
+        packed = synth.make_index_batch(N, B, T, Nn, mwdhm, seed=seed + i)
+        batches.append({k: torch.from_numpy(v) for k, v in synth.unpack(packed, B, T, Nn).items()})
+    for i in range(warmup):
+        O.train_step(p, adam, c, mw, batches[i % len(batches)])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        O.train_step(p, adam, c, mw, batches[i % len(batches)])
+    dt = time.perf_counter() - t0
+    return B * steps / dt, dt / steps * 1e3, torch.get_num_threads()
+
+
+def oracle_eval_rate(N, B, T, steps, content, mwdhm, seed=17):
+    """The reference's eval iteration (model_combine.py:283-301): scores, cau_metrics, argsort top-20."""
+    import numpy as np
+    import torch
+    from oracle import tcar_oracle as O
+    from tcar_b200 import synth
+    p = O.init_params(N)
+    c = torch.from_numpy(content)
+    mw = torch.from_numpy(mwdhm.astype(np.int64))
+    packed = synth.make_index_batch(N, B, T, 0, mwdhm, seed=seed)
+    batch = {k: torch.from_numpy(v) for k, v in synth.unpack(packed, B, T, 0).items()}
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        with torch.no_grad():
+            S = O.forward(p, c, mw, batch)["softmax_input"].numpy()
+        O.cau_metrics(S, batch["label"].numpy(), 20)
+        [np.argsort(r)[::-1][:20] for r in S]
+    dt = time.perf_counter() - t0
+    return B * steps / dt
+
+
+def run_reference(a):
+    """`--impl reference`: the reference's own implementation is a TensorFlow-1 graph that cannot run here (no
+    TensorFlow, and model_combine.py:113/115 is a SyntaxError), so this arm times the oracle port of its arithmetic on
+    the host cores, on the same workload config; each step is a bounded sample of `cpu_sample_sessions` sessions."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import __graft_entry__ as ge
+    ge.load_package()
+    from tcar_b200 import synth
+    content, mwdhm, _ = synth.make_catalog(a.items)
+    Bs = a.cpu_sample_sessions
+    rate, ms, threads = oracle_train_rate(a.items, Bs, a.session_len, a.neg_num, a.steps, a.warmup, content, mwdhm)
+    sample = (f"{a.steps} train steps of {Bs} sessions (T={a.session_len}, Nn={a.neg_num}) against the full "
+              f"{a.items}-item catalog, torch CPU fp32")
+    line = {"impl": "reference", "metric": "TCAR train sessions/sec (Globo shape)", "value": rate,
+            "unit": "sessions/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(a, 1),
+            "cpu_baseline": {"value": rate, "unit": "sessions/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": "sessions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(a, world):
+    return {"workload": f"TCAR train step, Globo shape: {a.items} articles x 250-d content, batch {a.batch} "
+                        f"sessions/GPU, session length {a.session_len}, {a.neg_num} negatives",
+            "items": a.items, "batch_per_gpu": a.batch, "global_batch": a.batch * world,
+            "session_len": a.session_len, "neg_num": a.neg_num,
+            "parallelism": f"dp{world}" if world > 1 else "single",
+            "l2": "inputs larger than L2: bf16 candidate matrix %d MB, E %d MB, item table + grad + Adam moments "
+                  "4 x %d MB streamed every step (L2 = 126 MB)" % (a.items * 640 * 2 >> 20, a.items * 1024 >> 20,
+                                                                  a.items * 1024 >> 20)}
+
+
+# ----------------------------------------------------------------------------------------------------- B200 arm
+def time_kernel(torch, fn, iters, flush):
+    """Average CUDA-event duration (ms) of fn() over `iters` launches on the current stream; `flush` (a >L2 buffer)
+    is rewritten before every launch, outside the event pair."""
+    fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(iters):
+        if flush is not None:
+            flush.add_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / iters
+
+
+def kernel_rooflines(torch, nv, model, bt, peaks, traffic):
+    """Per-kernel achieved throughput against the measured roofline (kernels timed alone -> burst peaks)."""
+    ps, p, B, T, Nn = model.ps, nv.ptr, bt.B, bt.T, bt.Nn
+    N = ps.N
+    M = B * T
+    model.forward_train(bt)
+    model.backward(bt)
+    torch.cuda.synchronize()
+    ws = model._score_buffers(ps.n_pad, True)
+    wse = model._score_buffers(ps.n_pad, False)
+    flush = torch.zeros(64 * 1024 * 1024, device=model.dev, dtype=torch.int32)        # 256 MB > 126 MB L2
+    cl = model._cluster_for(B)
+    w = ps.w
+    specs = [
+        ("score_fwd_train", "tensor", 2.0 * B * N * K_REF,
+         lambda: nv.call("tcar_score_fwd", p(model.Q), p(ps.iext), p(model.c_ref), p(ws["E"]), p(ws["part"]), None, B,
+                         N, ps.n_pad, 0, cl)),
+        ("score_fwd_eval", "tensor", 2.0 * B * N * K_REF,
+         lambda: nv.call("tcar_score_fwd", p(model.Q), p(ps.iext), p(model.c_ref), None, p(wse["part"]),
+                         p(wse["cmax"]), B, N, ps.n_pad, 1, cl)),
+        ("score_bwd_q", "tensor", 2.0 * B * N * K_REF,
+         lambda: nv.call("tcar_score_bwd_q", p(ws["E"]), p(ps.iext), p(ws["qpart"]), p(model.dq_raw), B, ps.n_pad)),
+        ("score_bwd_i", "tensor", 2.0 * B * N * K_DITEM,
+         lambda: nv.call("tcar_score_bwd_i", p(ws["E"]), p(model.Qs), p(ps.item_g), B, N, ps.n_pad)),
+        # reads p, m, v, g and writes p, m, v (7 x 250 floats per row) + the bf16 refresh of the scoring operand
+        ("adam_item", "hbm", (N + 1) * (7.0 * 250 * 4 + 250 * 2),
+         lambda: nv.call("tcar_adam_item", p(ps.item), p(ps.item_m), p(ps.item_v), p(ps.item_g), p(ps.sqnorm_item),
+                         p(ps.step), 0.0, model.max_grad_f, p(ps.iext), N)),
+        ("sqnorm_item_grad", "hbm", (N + 1) * 250 * 4.0,
+         lambda: nv.call("tcar_sqnorm_big", p(ps.item_g), p(ps.norm_partial), p(ps.sqnorm_item), ps.item_g.numel())),
+        # table rows read + X/P/D/CT written + the index words
+        ("gather_fwd", "hbm", M * (2 * 250 + 250 + 6 * 64) * 4.0 + M * (500 + 320 + 64) * 4.0 + B * 4 * 128 * 4.0
+         + (7 * M + 2 * B) * 4.0,
+         lambda: nv.call("tcar_gather_fwd", p(bt.idx), p(bt.ctx), p(ps.item), p(ps.content), p(w["pos"]),
+                         p(w["month"]), p(w["day"]), p(w["week"]), p(w["hour"]), p(w["minute"]), p(w["dur"]),
+                         p(model.X), p(model.P), p(model.D), p(model.CT), B, T)),
+        # reads X, P, U1, U2 and rewrites U1, U2 (sigmoid) + alpha + pooled
+        ("pool_fwd", "hbm", M * (500 + 320 + 4 * 250 + 3) * 4.0 + B * (500 + 500 + 320) * 4.0,
+         lambda: nv.call("tcar_pool_fwd", p(model.X), p(model.P), p(model.U1), p(model.U2), p(model.q), p(w["w_r"]),
+                         p(w["w_t"]), p(model.alpha), p(model.pooled), p(model.pooled_t), B, T)),
+        # sparse rows: read dXi / a_ic rows + item rows, RMW of the touched g_item rows
+        ("scatter_add_rows", "hbm", (M * 3 + (B + B * Nn) * 3) * 250 * 4.0,
+         lambda: nv.call("tcar_scatter_add_rows", p(bt.seq), p(bt.label), p(bt.neg), p(model.dXi), p(model.a_ic),
+                         p(model.coef), p(ps.item), p(ps.item_g), p(model.hash_keys), p(model.hash_acc),
+                         model.hash_size, B, T, Nn)),
+    ]
+    out = {}
+    for name, bound, work, fn in specs:
+        ms = time_kernel(torch, fn, 10, flush)
+        if bound == "tensor":
+            ach, peak, unit = work / (ms * 1e-3) / 1e12, peaks["tensor_burst"], "TFLOP/s"
+        else:
+            ach, peak, unit = work / (ms * 1e-3) / 1e9, peaks["hbm"], "GB/s"
+        out[name] = {"bound": bound, "ms": ms, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                     "peak_source": peaks["source"], "work_per_launch": work, "traffic": traffic.get(name)}
+    del flush
+    return out
+
+
+def run_b200(a):
+    import numpy as np
+    import torch
+    import __graft_entry__ as ge
+    ge.load_package()
+    from tcar_b200 import _native as nv, synth
+    from tcar_b200.model_combine import Seq2SeqAttNN
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    N, B, T, Nn, K, W = a.items, a.batch, a.session_len, a.neg_num, a.steps, a.warmup
+    content, mwdhm, category = synth.make_catalog(N)
+    np.random.seed(2020)
+    margs = dict(publish_time_MWDHM=mwdhm, itemnum=N, category_id=None, item_freq_dict_norm={}, reverse_item=None,
+                 content_emb=content, emb_stddev=0.002, stddev=0.05, hidden_size=250, time_hidden_size=64, l2_emb=0.0,
+                 batch_size=B, epoch=1, neg_num=Nn, lr=0.001, max_grad=150, rank=rank, world_size=world)
+    model = Seq2SeqAttNN(margs)
+    peaks = load_peaks()
+    nbatch = 4
+    host = make_batches(synth, N, B, T, Nn, mwdhm, nbatch, seed0=1000 * (rank + 1))
+    dev = [model.to_device(h, B, T, Nn) for h in host]
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], device=model.dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- kernel-resident train throughput: inputs already in HBM --------------------------------------------
+    for i in range(W):
+        model.train_step(dev[i % nbatch])
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    nv.LAUNCHES["count"] = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(K):
+        model.train_step(dev[i % nbatch])
+    e1.record()
+    barrier()
+    train_ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = nv.LAUNCHES["count"]
+    loss_last = float(model.loss[:B].mean().item())
+
+    # ---- end to end through the public API: pinned host batch -> H2D -> train_step -> D2H of the loss -------
+    for i in range(2):
+        model.train_step(model.to_device(host[i % nbatch], B, T, Nn)).cpu()
+    barrier()
+    e0.record()
+    for i in range(K):
+        bt = model.to_device(host[i % nbatch], B, T, Nn)
+        loss_host = model.train_step(bt).cpu()
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    clk = clocks.stop() if rank == 0 else None
+    h2d = host[0].numel() * 4
+    d2h = B * 4
+
+    # ---- evaluation: full-catalog top-20, catalog sharded across ranks when N > 1 ----------------------------
+    ehost = make_batches(synth, N, B, T, 0, mwdhm, nbatch, seed0=77)       # same queries on every rank
+    edev = [model.to_device(h, B, T, 0) for h in ehost]
+    shard = None
+    if world > 1:
+        lo, hi = model.shard_bounds(world)[rank]
+        shard = (lo, hi, model.iext_shard(lo, hi))
+    for i in range(W):
+        model.eval_step(edev[i % nbatch], shard=shard)
+    barrier()
+    e0.record()
+    for i in range(K):
+        model.eval_step(edev[i % nbatch], shard=shard)
+    e1.record()
+    barrier()
+    eval_ms = max_over_ranks(e0.elapsed_time(e1))
+    e0.record()
+    for i in range(K):
+        bt = model.to_device(ehost[i % nbatch], B, T, 0)
+        top, ngt, ce = model.eval_step(bt, shard=shard)
+        top.cpu(); ngt.cpu(); ce.cpu()
+    e1.record()
+    barrier()
+    eval_e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+
+    kernels = {}
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f)
+    if rank == 0 and not a.no_kernels:
+        kernels = kernel_rooflines(torch, nv, model, dev[0], peaks, traffic)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        del model
+        torch.cuda.empty_cache()
+        Bs = a.cpu_sample_sessions
+        rate, ms, threads = oracle_train_rate(N, Bs, T, Nn, 3, 1, content, mwdhm)
+        erate = oracle_eval_rate(N, Bs, T, 1, content, mwdhm)
+        cpu_baseline = {"value": rate, "unit": "sessions/s", "cores": threads, "kind": "port",
+                        "sample": f"3 train steps of {Bs} sessions (T={T}, Nn={Nn}) against the full {N}-item "
+                                  f"catalog after 1 warm-up, torch CPU fp32 oracle ({ms:.0f} ms/step)",
+                        "eval_queries_per_s": erate}
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    sessions = world * B * K
+    value = sessions / (train_ms * 1e-3)
+    # dominant kernel of the step = largest share of the isolated kernel times
+    roof = None
+    if kernels:
+        step_k = ["score_fwd_train", "score_bwd_q", "score_bwd_i", "adam_item", "sqnorm_item_grad", "gather_fwd",
+                  "pool_fwd", "scatter_add_rows"]
+        top = max(step_k, key=lambda k: kernels[k]["ms"])
+        kk = kernels[top]
+        roof = {"kernel": top, "bound": kk["bound"], "achieved": kk["achieved"], "peak": kk["peak"],
+                "unit": kk["unit"], "frac": kk["frac"], "traffic": kk["traffic"], "peak_source": kk["peak_source"],
+                "ms_per_launch": kk["ms"]}
+    line = {"metric": "TCAR train sessions/sec (Globo shape)", "value": value, "unit": "sessions/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": train_ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16 tensor-core scoring GEMMs (fp32 accumulate), fp32 elsewhere",
+            "data": "synthetic", "config": workload_config(a, world),
+            "e2e": {"value": sessions / (e2e_ms * 1e-3), "unit": "sessions/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K},
+            "eval": {"metric": "full-catalog top-20 eval queries/sec", "value": B * K / (eval_ms * 1e-3),
+                     "unit": "queries/s", "ms_per_step": eval_ms / K,
+                     "scaling": "strong (catalog sharded across ranks)" if world > 1 else "single",
+                     "e2e": {"value": B * K / (eval_e2e_ms * 1e-3), "unit": "queries/s",
+                             "h2d_bytes_per_step": ehost[0].numel() * 4, "d2h_bytes_per_step": B * (20 + 1 + 1) * 4}},
+            "gpu_launches": launches, "launches_per_step": launches / K, "loss_last_step": loss_last,
+            "clocks": clk, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu_baseline}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

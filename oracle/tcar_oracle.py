@@ -268,3 +268,22 @@ def eval_batch(p, content, mwdhm, batch, category_id, reverse_item):
     unexp = [get_unexp(list(batch["seq"][i].numpy()), list(t), category_id, reverse_item) for i, t in enumerate(tops)]
     return {"recall": recall, "mrr": mrr, "ndcg": ndcg, "top20": tops, "ild": ild, "unexp": unexp,
             "cross_loss": out["cross_loss"].numpy(), "scores": S}
+
+
+# ----------------------------------------------------------------------------------------------- sharded evaluation
+def merge_topk(ids: np.ndarray, scores: np.ndarray, k: int = 20):
+    """Merge G per-shard top-k lists [G,B,k] into the global top-k ordered by (score desc, id asc); id < 0 marks an
+    empty slot.  This is the defined order of top20() above applied to the union of the shard lists, i.e. what
+    `np.argsort(pred)[::-1][:20]` (model_combine.py:301) yields on tie-free rows of the unsharded score matrix."""
+    G, B, kk = ids.shape
+    out_i = np.full((B, k), -1, dtype=np.int32)
+    out_s = np.full((B, k), -np.inf, dtype=np.float32)
+    for b in range(B):
+        i = ids[:, b].reshape(-1).astype(np.int64)
+        s = scores[:, b].reshape(-1).astype(np.float32)
+        keep = i >= 0
+        i, s = i[keep], s[keep]
+        order = np.lexsort((i, -s))[:k]
+        out_i[b, : len(order)] = i[order]
+        out_s[b, : len(order)] = s[order]
+    return out_i, out_s

@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from . import _native as nv
+from . import parallel
 from .params import ParamStore, SMALL
 from .sampler import Sampler, pack_batch
 
@@ -245,10 +246,7 @@ class Seq2SeqAttNN:
 
     def allreduce_grads(self):
         """Data-parallel training: SUM (not mean -- the loss is a batch sum, model_combine.py:156) over ranks."""
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.ps.item_g, op=dist.ReduceOp.SUM)
-            dist.all_reduce(self.ps.theta_g, op=dist.ReduceOp.SUM)
+        parallel.allreduce_sum((self.ps.item_g, self.ps.theta_g), self.world)
 
     def apply_gradients(self):
         """per-tensor clip_by_norm + TF Adam (model_combine.py:155-163); also refreshes the bf16 scoring operand."""
@@ -289,30 +287,20 @@ class Seq2SeqAttNN:
         nv.counted_call("tcar_eval_topk", 1, p(ws["cmax"]), p(self.a_ic), p(self.Tq), p(ps.item), p(ps.content),
                         p(ps.mwdhm), p(bt.label), p(self.top_ids), p(self.top_scores), p(self.n_greater), B, n_loc,
                         n_pad, lo)
-        if self.world > 1 and shard is not None:
-            import torch.distributed as dist
-            G = self.world
-            ids = torch.empty(G, B, TOPK, device=self.dev, dtype=torch.int32)
-            sc = torch.empty(G, B, TOPK, device=self.dev)
-            dist.all_gather_into_tensor(ids, self.top_ids[:B].contiguous())
-            dist.all_gather_into_tensor(sc, self.top_scores[:B].contiguous())
-            dist.all_reduce(self.n_greater[:B], op=dist.ReduceOp.SUM)
-            dist.all_reduce(self.sumexp[:B], op=dist.ReduceOp.SUM)
-            nv.counted_call("tcar_topk_merge", 1, p(ids), p(sc), p(self.top_ids), p(self.top_scores), G, B)
+        if shard is not None and parallel.is_distributed(self.world):
+            def merge(ids, sc):
+                nv.counted_call("tcar_topk_merge", 1, p(ids), p(sc), p(self.top_ids), p(self.top_scores),
+                                self.world, B)
+                return self.top_ids[:B], self.top_scores[:B]
+            parallel.gather_merge_topk(self.top_ids[:B], self.top_scores[:B], self.n_greater[:B], self.sumexp[:B],
+                                       self.world, merge)
             torch.log(self.sumexp[:B], out=self.ce[:B])
         return self.top_ids[:B], self.n_greater[:B], self.ce[:B]
 
     def shard_bounds(self, G):
         """Contiguous item-id ranges [lo, hi) per shard, aligned to 256 rows so that a shard of the bf16 scoring
         operand is a plain row-slice of ps.iext."""
-        tiles = self.ps.n_pad // 256
-        per = (tiles + G - 1) // G
-        out = []
-        for g in range(G):
-            lo = min(g * per * 256, self.ps.N)
-            hi = min((g + 1) * per * 256, self.ps.N)
-            out.append((lo, hi))
-        return out
+        return parallel.shard_bounds(self.ps.N, self.ps.n_pad, G)
 
     def iext_shard(self, lo, hi):
         n_pad = max((hi - lo + 255) // 256 * 256, 256)

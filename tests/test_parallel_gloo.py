@@ -1,0 +1,130 @@
+"""Host-side multi-GPU logic on CPU: world_size 2 over gloo.  The CUDA merge kernel is replaced by the
+oracle's merge here -- the same callable slot the product fills with tcar_topk_merge."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import tcar_oracle as O
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, fn, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import __graft_entry__ as ge
+    ge.load_package()
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ret[rank] = fn(rank, world)
+    finally:
+        dist.destroy_process_group()
+
+
+def _spawn(fn, world=2):
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), fn, ret), nprocs=world, join=True)
+    return [ret[r] for r in range(world)]
+
+
+# ---------------------------------------------------------------------------------------------- pure host logic
+@pytest.mark.parametrize("B,world", [(512, 2), (7, 4), (3, 8), (1, 2), (512, 8)])
+def test_shard_sessions_partition(B, world):
+    from tcar_b200 import parallel
+    spans = [parallel.shard_sessions(B, r, world) for r in range(world)]
+    assert spans[0][0] == 0 and spans[-1][1] == B
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    sizes = [hi - lo for lo, hi in spans]
+    assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.parametrize("B,T,Nn,world", [(10, 3, 4, 2), (5, 1, 0, 4), (64, 20, 20, 8)])
+def test_shard_packed_reassembles(B, T, Nn, world):
+    from tcar_b200 import parallel, synth
+    N = 500
+    _, mwdhm, _ = synth.make_catalog(N, seed=1)
+    packed = synth.make_index_batch(N, B, T, Nn, mwdhm, seed=3)
+    whole = synth.unpack(packed, B, T, Nn)
+    parts = []
+    for r in range(world):
+        pl, Bl, Tl, Nl = parallel.shard_packed(packed, B, T, Nn, r, world)
+        assert pl.dtype == np.int32 and pl.size == 7 * Bl * T + 3 * Bl + Bl * Nn
+        if Bl:
+            parts.append(synth.unpack(pl, Bl, Tl, Nl))
+    for k in whole:
+        np.testing.assert_array_equal(np.concatenate([p[k] for p in parts]), whole[k])
+
+
+@pytest.mark.parametrize("N,G", [(364047, 8), (364047, 2), (1000, 8), (300, 4)])
+def test_shard_bounds_cover_catalog(N, G):
+    from tcar_b200 import parallel
+    n_pad = (N + 255) // 256 * 256
+    b = parallel.shard_bounds(N, n_pad, G)
+    assert b[0][0] == 0 and max(hi for _, hi in b) == N
+    covered = sum(hi - lo for lo, hi in b)
+    assert covered == N
+    assert all(lo % 256 == 0 for lo, hi in b if hi > lo)
+
+
+# ---------------------------------------------------------------------------------------------- world_size 2, gloo
+def _dp_allreduce(rank, world):
+    from tcar_b200 import parallel
+    g = torch.full((5, 3), float(rank + 1))
+    h = torch.arange(4, dtype=torch.float32) * (rank + 1)
+    parallel.allreduce_sum((g, h), world)
+    return g.numpy().copy(), h.numpy().copy()
+
+
+def test_gradient_allreduce_is_a_sum():
+    out = _spawn(_dp_allreduce, 2)
+    for g, h in out:
+        np.testing.assert_array_equal(g, np.full((5, 3), 3.0))
+        np.testing.assert_array_equal(h, np.arange(4) * 3.0)
+
+
+def _sharded_eval(rank, world):
+    """Every rank scores all queries against its catalog shard (numpy stand-in for the kernels), then the product's
+    gather/merge plumbing must reproduce the unsharded top-20, rank counts and softmax denominators."""
+    from tcar_b200 import parallel
+    rs = np.random.RandomState(0)
+    B, N = 37, 3000
+    S = rs.normal(size=(B, N)).astype(np.float32)
+    S[:, 100:140] = S[:, 200:240]                    # exact ties across and inside shards
+    label = rs.randint(0, N, B)
+    lo, hi = parallel.shard_bounds(N, (N + 255) // 256 * 256, world)[rank]
+    loc = S[:, lo:hi]
+    ids = np.arange(lo, hi)
+    top_i = np.full((B, 20), -1, np.int32)
+    top_s = np.full((B, 20), -np.inf, np.float32)
+    for b in range(B):
+        o = np.lexsort((ids, -loc[b]))[:20]
+        top_i[b, : len(o)] = ids[o]
+        top_s[b, : len(o)] = loc[b, o]
+    ngt = torch.from_numpy((loc > S[np.arange(B), label][:, None]).sum(1).astype(np.int32))
+    sumexp = torch.from_numpy(np.exp(loc.astype(np.float64)).sum(1).astype(np.float32))
+
+    def merge(i, s):
+        oi, os_ = O.merge_topk(i.numpy(), s.numpy())
+        return torch.from_numpy(oi), torch.from_numpy(os_)
+
+    oi, os_, ngt, sumexp = parallel.gather_merge_topk(torch.from_numpy(top_i), torch.from_numpy(top_s), ngt, sumexp,
+                                                      world, merge)
+    return oi.numpy(), ngt.numpy(), sumexp.numpy(), S, label
+
+
+def test_catalog_sharded_eval_equals_unsharded():
+    out = _spawn(_sharded_eval, 2)
+    for oi, ngt, sumexp, S, label in out:
+        np.testing.assert_array_equal(oi, O.top20(S))
+        ref_rank = np.array([int((row[l] < row).sum()) for row, l in zip(S, label)])
+        np.testing.assert_array_equal(ngt, ref_rank)
+        np.testing.assert_allclose(sumexp, np.exp(S.astype(np.float64)).sum(1), rtol=1e-5)
