@@ -34,6 +34,8 @@ extern "C" {
 #define TCAR_CHUNK 8      /* items per eval chunk-max                                                   */
 #define TCAR_NCAND_CHUNKS 32 /* chunks re-scored per query (256 candidate items)                        */
 
+#define TCAR_CLUSTER_PAIR (-2) /* tcar_score_fwd `cluster` value: CTA pair, tcgen05.mma.cta_group::2 (M = 256)   */
+
 #define TCAR_ERR_ARG (-1)
 #define TCAR_ERR_DRIVER (-2)
 #define TCAR_ERR_TENSORMAP (-3)
@@ -82,7 +84,9 @@ int tcar_build_query(const float* a_ic, const float* a_pt, const float* ct_tab, 
 /* (3c) full-catalog scoring S = Q . Iext^T on tcgen05 (model_combine.py:138), never materialising S.
  *   mode 0 (train): E [512,n_pad] bf16 = exp(S - c_ref), rowsum_part [n_pad/128][512]
  *   mode 1 (eval) : chunkmax [512, n_pad/8] fp32 = max of S over 8 consecutive items, rowsum_part as above
- *   cluster in {1,2,4}: CTAs per cluster sharing each item tile by TMA multicast. */
+ *   cluster in {1,2,4}: CTAs per cluster sharing each item tile by TMA multicast (one 128x128 UMMA per CTA);
+ *   cluster == TCAR_CLUSTER_PAIR: CTA pairs issuing 256x256 cta_group::2 UMMAs, each CTA streaming half of every
+ *   item tile (the production configuration: twice the pipeline depth per byte of shared memory). */
 int tcar_score_fwd(const void* q_bf16, const void* iext_bf16, const float* c_ref, void* e_out, float* rowsum_part,
                    float* chunkmax, int n_rows, int n_items, int n_pad, int mode, int cluster, void* stream);
 int tcar_score_fwd_tiles(int n_pad);

@@ -226,6 +226,208 @@ score_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------------ forward, CTA pair
+// Same contract as score_fwd_kernel, restructured for pipeline depth: the 160 KB resident session operand leaves
+// only 64 KB of shared memory for the streamed item operand, which is ~0.5 us of MMA work per SM with 128-item
+// tiles -- less than the TMA round trip under load.  Here two CTAs (one TPC) issue tcgen05.mma.cta_group::2 with
+// M = 256 sessions x N = 256 items: each CTA keeps its own 128 session rows resident and streams only HALF of every
+// item tile (128 items x 64 k = 16 KB per stage), so the same 64 KB hold 4 x 512 = 2048 clks of MMA work and each
+// SM ingests half the bytes per FLOP.  Two 256-column accumulators fill TMEM (double buffered); 8 epilogue warps
+// (2 per 32-lane TMEM quarter, 128 columns each) run exp / bf16-pack / partial row sums under the next tile's MMAs.
+constexpr int P_THREADS = 384;   // warp0 TMA, warp1 MMA (leader CTA only), warp2 TMEM alloc, warp3 idle, warps4-11 epilogue
+constexpr int P_BN = 256;        // items per tile (both CTAs)
+constexpr int P_HALF = 128;      // items per CTA per tile
+constexpr int P_STAGES = 4;
+constexpr int P_NACC = 2;
+constexpr int P_B_STAGE = P_HALF * BK * 2;      // 16384
+constexpr int P_SMEM = F_A_BYTES + P_STAGES * P_B_STAGE + 1024 /*align*/ + 256 /*barriers*/;
+
+template <int MODE>
+__device__ __forceinline__ void fwd_epilogue_chunk(const uint32_t (&v)[32], const FwdParams& p, float cshift,
+                                                   bool row_ok, bool store_ok, bool tail, uint32_t row, int nb,
+                                                   float& psum) {
+    float e[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        float ex = ex2_approx(fmaf(__uint_as_float(v[j]), kLog2e, -cshift));
+        if (!row_ok || (tail && nb + j >= p.n_items)) ex = 0.f;
+        e[j] = ex;
+        psum += ex;
+    }
+    if (MODE == 0) {
+        if (store_ok) {
+            uint4* dst = reinterpret_cast<uint4*>(p.E + (size_t)row * p.e_pitch + nb);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                uint4 o;
+                o.x = pack_bf16(e[g * 8 + 0], e[g * 8 + 1]);
+                o.y = pack_bf16(e[g * 8 + 2], e[g * 8 + 3]);
+                o.z = pack_bf16(e[g * 8 + 4], e[g * 8 + 5]);
+                o.w = pack_bf16(e[g * 8 + 6], e[g * 8 + 7]);
+                dst[g] = o;
+            }
+        }
+    } else {
+        float4 m;
+        float* mm = reinterpret_cast<float*>(&m);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float sv = __uint_as_float(v[g * 8 + j]);
+                const bool ok = !(tail && nb + g * 8 + j >= p.n_items);
+                mx = ok ? fmaxf(mx, sv) : mx;
+            }
+            mm[g] = mx;
+        }
+        if (row_ok) *reinterpret_cast<float4*>(p.chunkmax + (size_t)row * (p.e_pitch / 8) + nb / 8) = m;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(P_THREADS, 1)
+score_fwd_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_i,
+                      const FwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + F_A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + P_STAGES * P_B_STAGE);
+    uint64_t* full = bars;                      // [P_STAGES]  used in the leader CTA (tx from both CTAs' loads)
+    uint64_t* empty = bars + P_STAGES;          // [P_STAGES]  one per CTA, MMA commit multicast
+    uint64_t* acc_full = bars + 2 * P_STAGES;   // [P_NACC]    one per CTA, MMA commit multicast
+    uint64_t* acc_empty = acc_full + P_NACC;    // [P_NACC]    used in the leader CTA, 16 epilogue-warp arrivals
+    uint64_t* a_full = acc_empty + P_NACC;      // [1]         leader CTA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
+
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t lane = lane_id();
+    const uint32_t rank = cluster_ctarank();    // 0 = leader
+    const uint32_t pair_id = blockIdx.x >> 1;
+    const uint32_t n_pairs = gridDim.x >> 1;
+    const uint32_t grp = pair_id % p.groups;
+    const uint32_t tile0 = pair_id / p.groups;
+    const uint32_t tile_step = n_pairs / p.groups;
+    const uint32_t mtile = grp * 2 + rank;
+    const uint32_t my_tiles =
+        tile0 < (uint32_t)p.n_tiles ? ((uint32_t)p.n_tiles - tile0 + tile_step - 1) / tile_step : 0u;
+
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&map_q);
+        tma_prefetch_desc(&map_i);
+    }
+    if (warp == 1 && elect_one()) {
+        for (int i = 0; i < P_STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < P_NACC; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 16);
+        }
+        mbar_init(a_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc_pair(tmem_slot, 512);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer (both CTAs; completion bytes land on the LEADER's barriers) =================
+        if (elect_one()) {
+            const uint32_t a_full_l = mapa_u32(a_full, 0);
+            if (rank == 0) mbar_expect_tx(a_full, 2 * F_A_BYTES);
+            for (int kb = 0; kb < NKB; ++kb)
+                tma_load_2d_pair(smem_a + kb * (BM * BK * 2), &map_q, a_full_l, kb * BK, mtile * BM);
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t it = 0; it < my_tiles; ++it) {
+                const int n0 = (tile0 + it * tile_step) * P_BN + rank * P_HALF;
+                for (int kb = 0; kb < NKB; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    if (rank == 0) mbar_expect_tx(&full[stage], 2 * P_B_STAGE);
+                    tma_load_2d_pair(smem_b + stage * P_B_STAGE, &map_i, mapa_u32(&full[stage], 0), kb * BK, n0);
+                    if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader CTA only) =================
+        if (rank == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(2 * BM, P_BN, 0, 0);
+            mbar_wait(a_full, 0);
+            tc_fence_after();
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t it = 0; it < my_tiles; ++it) {
+                const uint32_t acc = it % P_NACC;
+                const uint32_t acc_phase = (it / P_NACC) & 1;
+                mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < NKB; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a_addr = smem_u32(smem_a + kb * (BM * BK * 2));
+                        const uint32_t b_addr = smem_u32(smem_b + stage * P_B_STAGE);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_bf16_pair(tmem_base + acc * P_BN, sdesc_kmajor(a_addr + k * 32),
+                                           sdesc_kmajor(b_addr + k * 32), idesc, (kb | k) != 0);
+                        umma_commit_pair(&empty[stage], 3);
+                        if (kb == NKB - 1) umma_commit_pair(&acc_full[acc], 3);
+                    }
+                    __syncwarp();
+                    if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue: thread <-> session row, warp <-> (TMEM lane quarter, column half) =================
+        const uint32_t e = warp - 4;
+        const uint32_t q = e & 3, h = e >> 2;
+        const uint32_t row = mtile * BM + q * 32 + lane;
+        const bool row_ok = row < (uint32_t)p.n_rows;
+        const bool store_ok = row < (((uint32_t)p.n_rows + 63u) & ~63u);
+        const float cshift = row_ok ? p.c_ref[row] * kLog2e : 0.f;
+        const uint32_t acc_empty_l = mapa_u32(acc_empty, 0);
+        for (uint32_t it = 0; it < my_tiles; ++it) {
+            const uint32_t acc = it % P_NACC;
+            const uint32_t acc_phase = (it / P_NACC) & 1;
+            const uint32_t tile = tile0 + it * tile_step;
+            const int n0 = tile * P_BN + h * 128;
+            mbar_wait(&acc_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((q * 32) << 16) + acc * P_BN + h * 128;
+            const bool tail = n0 + 128 > p.n_items;
+            float psum = 0.f;
+            uint32_t va[32], vb[32];
+            tmem_ld32(taddr, va);
+            tmem_ld_wait();
+            tmem_ld32(taddr + 32, vb);
+            fwd_epilogue_chunk<MODE>(va, p, cshift, row_ok, store_ok, tail, row, n0, psum);
+            tmem_ld_wait();
+            tmem_ld32(taddr + 64, va);
+            fwd_epilogue_chunk<MODE>(vb, p, cshift, row_ok, store_ok, tail, row, n0 + 32, psum);
+            tmem_ld_wait();
+            tmem_ld32(taddr + 96, vb);
+            fwd_epilogue_chunk<MODE>(va, p, cshift, row_ok, store_ok, tail, row, n0 + 64, psum);
+            tmem_ld_wait();
+            // every TMEM read of this accumulator half is in registers -> hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc_empty_l + acc * 8);
+            fwd_epilogue_chunk<MODE>(vb, p, cshift, row_ok, store_ok, tail, row, n0 + 96, psum);
+            if (row_ok) p.rowsum_part[(size_t)(tile * 2 + h) * QROWS + row] = psum;
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) tmem_dealloc_pair(tmem_base, 512);
+}
+
 // ------------------------------------------------------------------------------------------------ dQ = E . Iext
 constexpr int Q_CH = 320;                 // feature columns per CTA (half of KEXT): one N=256 + one N=64 MMA
 constexpr int Q_STAGES = 4;
@@ -567,6 +769,27 @@ static int launch_fwd(const CUtensorMap& mq, const CUtensorMap& mi, const FwdPar
     return (int)e;
 }
 
+template <int MODE>
+static int launch_fwd_pair(const CUtensorMap& mq, const CUtensorMap& mi, const FwdParams& p, int n_pairs,
+                           cudaStream_t stream) {
+    cudaError_t e =
+        cudaFuncSetAttribute(score_fwd_pair_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_pairs * 2);
+    cfg.blockDim = dim3(P_THREADS);
+    cfg.dynamicSmemBytes = P_SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, score_fwd_pair_kernel<MODE>, mq, mi, p);
+}
+
 }  // namespace tcar
 
 using namespace tcar;
@@ -576,11 +799,31 @@ extern "C" int tcar_score_fwd(const void* q_bf16, const void* iext_bf16, const f
                               int cluster, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (n_rows < 1 || n_rows > QROWS || n_pad % 256 != 0 || n_items > n_pad) return TCAR_ERR_ARG;
-    if (cluster != 1 && cluster != 2 && cluster != 4) return TCAR_ERR_ARG;
-    if ((mode == 0 && !e_out) || (mode == 1 && !chunkmax)) return TCAR_ERR_ARG;
+    if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != TCAR_CLUSTER_PAIR) return TCAR_ERR_ARG;
+    if ((mode == 0 && !e_out) || (mode == 1 && !chunkmax) || (mode != 0 && mode != 1)) return TCAR_ERR_ARG;
     CUtensorMap mq, mi;
     int rc = make_map_bf16(&mq, q_bf16, QROWS, KEXT, KEXT, BK, BM);
     if (rc) return rc;
+    if (cluster == TCAR_CLUSTER_PAIR) {
+        rc = make_map_bf16(&mi, iext_bf16, n_pad, KEXT, KEXT, BK, P_HALF);
+        if (rc) return rc;
+        FwdParams p;
+        p.E = static_cast<__nv_bfloat16*>(e_out);
+        p.rowsum_part = rowsum_part;
+        p.chunkmax = chunkmax;
+        p.c_ref = c_ref;
+        p.n_items = n_items;
+        p.n_tiles = n_pad / P_BN;
+        p.n_rows = n_rows;
+        p.e_pitch = n_pad;
+        const int mtiles = (n_rows + BM - 1) / BM;
+        p.groups = (mtiles + 1) / 2;
+        p.mode = mode;
+        int n_pairs = ((sm_count() / 2) / p.groups) * p.groups;
+        if (n_pairs < p.groups) n_pairs = p.groups;
+        if (n_pairs / p.groups > p.n_tiles) n_pairs = p.n_tiles * p.groups;
+        return mode == 0 ? launch_fwd_pair<0>(mq, mi, p, n_pairs, stream) : launch_fwd_pair<1>(mq, mi, p, n_pairs, stream);
+    }
     rc = make_map_bf16(&mi, iext_bf16, n_pad, KEXT, KEXT, BK, F_BN / cluster);
     if (rc) return rc;
     FwdParams p;

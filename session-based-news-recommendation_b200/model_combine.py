@@ -64,7 +64,7 @@ class Seq2SeqAttNN:
         # catalog sharding for evaluation / data-parallel training (torch.distributed, NCCL)
         self.rank = int(args.get("rank", 0))
         self.world = int(args.get("world_size", 1))
-        self.cluster = int(args.get("cluster", 4))
+        self.cluster = int(args.get("cluster", nv.CLUSTER_PAIR))
         dev = torch.device("cuda", torch.cuda.current_device())
         self.dev = dev
         self.ps = ParamStore(self.N, content, args["publish_time_MWDHM"], dev)
@@ -169,6 +169,8 @@ class Seq2SeqAttNN:
                         p(ps.mwdhm), p(bt.label), p(self.Tq), p(self.Q), p(self.c_ref), B)
 
     def _cluster_for(self, B):
+        if self.cluster == nv.CLUSTER_PAIR:
+            return nv.CLUSTER_PAIR
         mt = (B + 127) // 128
         c = min(self.cluster, 4)
         while c > 1 and c > mt:
@@ -263,8 +265,14 @@ class Seq2SeqAttNN:
 
     def train_step(self, bt):
         """One `sess.run([loss, global_step, train_op])` (model_combine.py:231-234). Returns loss [B] (device)."""
-        loss, _ = self.forward_train(bt)
-        self.backward(bt)
+        if bt.B == 0:
+            # data-parallel tail batch with fewer sessions than ranks: contribute a zero gradient to the all-reduce
+            self.ps.item_g.zero_()
+            self.ps.theta_g.zero_()
+            loss = self.loss[:0]
+        else:
+            loss, _ = self.forward_train(bt)
+            self.backward(bt)
         self.allreduce_grads()
         self.apply_gradients()
         return loss
@@ -280,13 +288,20 @@ class Seq2SeqAttNN:
         else:
             lo, hi, iext = shard
             n_loc, n_pad = hi - lo, iext.shape[0]
-        ws = self._score_buffers(n_pad, False)
-        nv.counted_call("tcar_score_fwd", 1, p(self.Q), p(iext), p(self.c_ref), None, p(ws["part"]), p(ws["cmax"]), B,
-                        n_loc, n_pad, 1, self._cluster_for(B))
-        nv.counted_call("tcar_ce_finish", 1, p(ws["part"]), p(self.sumexp), p(self.ce), ws["tiles"], B)
-        nv.counted_call("tcar_eval_topk", 1, p(ws["cmax"]), p(self.a_ic), p(self.Tq), p(ps.item), p(ps.content),
-                        p(ps.mwdhm), p(bt.label), p(self.top_ids), p(self.top_scores), p(self.n_greater), B, n_loc,
-                        n_pad, lo)
+        if n_loc <= 0:
+            # this rank's slice of a small catalog is empty: contribute empty lists to the merge
+            self.top_ids[:B].fill_(-1)
+            self.top_scores[:B].fill_(float("-inf"))
+            self.n_greater[:B].zero_()
+            self.sumexp[:B].zero_()
+        else:
+            ws = self._score_buffers(n_pad, False)
+            nv.counted_call("tcar_score_fwd", 1, p(self.Q), p(iext), p(self.c_ref), None, p(ws["part"]), p(ws["cmax"]),
+                            B, n_loc, n_pad, 1, self._cluster_for(B))
+            nv.counted_call("tcar_ce_finish", 1, p(ws["part"]), p(self.sumexp), p(self.ce), ws["tiles"], B)
+            nv.counted_call("tcar_eval_topk", 1, p(ws["cmax"]), p(self.a_ic), p(self.Tq), p(ps.item), p(ps.content),
+                            p(ps.mwdhm), p(bt.label), p(self.top_ids), p(self.top_scores), p(self.n_greater), B, n_loc,
+                            n_pad, lo)
         if shard is not None and parallel.is_distributed(self.world):
             def merge(ids, sc):
                 nv.counted_call("tcar_topk_merge", 1, p(ids), p(sc), p(self.top_ids), p(self.top_scores),
@@ -387,9 +402,15 @@ class Seq2SeqAttNN:
                 packed, B, T, Nn = sampler.next_packed()
                 if batch < 3:
                     print(sampler.last_neg[0][:10])
+                if self.world > 1:
+                    # every rank draws the same batch (same seeds, main.py:9-12) and keeps its slice of the sessions
+                    packed, B, T, Nn = parallel.shard_packed(packed, B, T, Nn, self.rank, self.world)
                 bt = self.to_device(torch.from_numpy(packed).pin_memory(), B, T, Nn)
                 c.append(self.train_step(bt).clone())
-            avgc = float(torch.cat(c).mean().item()) if c else float("nan")
+            tot = torch.stack([torch.cat(c).sum(), torch.tensor(float(sum(len(x) for x in c)), device=self.dev)]) \
+                if c else torch.zeros(2, device=self.dev)
+            parallel.allreduce_sum((tot,), self.world)
+            avgc = float((tot[0] / tot[1]).item()) if float(tot[1].item()) > 0 else float("nan")
             if math.isnan(avgc):
                 print("Epoch {}: NaN error!".format(str(epoch)))
                 self.error_during_train = True

@@ -37,8 +37,8 @@ def _fwd(native, Q, I, c, B, N, n_pad, mode, cluster):
     return E, part, cm
 
 
-@pytest.mark.parametrize("cluster", [1, 2, 4])
-@pytest.mark.parametrize("B,N", [(512, 5000), (300, 2333), (64, 20000), (1, 300)])
+@pytest.mark.parametrize("cluster", [1, 2, 4, -2])
+@pytest.mark.parametrize("B,N", [(512, 5000), (300, 2333), (64, 20000), (1, 300), (129, 70000)])
 def test_score_fwd_train(native, cluster, B, N):
     Q, I, c, n_pad = _mk(B, N, 7 + B + N)
     E, part, _ = _fwd(native, Q, I, c, B, N, n_pad, 0, cluster)
@@ -55,7 +55,7 @@ def test_score_fwd_train(native, cluster, B, N):
     assert rerr < 2e-3, f"rowsum rel err {rerr}"
 
 
-@pytest.mark.parametrize("cluster", [1, 4])
+@pytest.mark.parametrize("cluster", [1, 4, -2])
 def test_score_fwd_eval_chunkmax(native, cluster):
     B, N = 257, 7001
     Q, I, c, n_pad = _mk(B, N, 99)

@@ -1,0 +1,77 @@
+"""Run under torchrun on G GPUs: data-parallel train step and catalog-sharded eval must equal the single-GPU result.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as ge  # noqa: E402
+
+ge.load_package()
+from tcar_b200 import parallel, synth  # noqa: E402
+from tcar_b200.model_combine import Seq2SeqAttNN  # noqa: E402
+
+
+def build(N, rank, world):
+    content, mwdhm, _ = synth.make_catalog(N, seed=3)
+    np.random.seed(2020)
+    args = dict(publish_time_MWDHM=mwdhm, itemnum=N, category_id=None, item_freq_dict_norm={}, reverse_item=None,
+                content_emb=content, emb_stddev=0.04, stddev=0.05, hidden_size=250, time_hidden_size=64, l2_emb=0.0,
+                batch_size=512, epoch=1, neg_num=20, lr=0.001, max_grad=150, rank=rank, world_size=world)
+    return Seq2SeqAttNN(args), mwdhm
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    N, B, T, Nn = 20000, 301, 5, 20
+    res = {}
+    # ---- data-parallel train step vs the same global batch on one GPU
+    model, mwdhm = build(N, rank, world)
+    packed = synth.make_index_batch(N, B, T, Nn, mwdhm, seed=5)
+    pl, Bl, _, _ = parallel.shard_packed(packed, B, T, Nn, rank, world)
+    bt = model.to_device(torch.from_numpy(pl).pin_memory(), Bl, T, Nn)
+    loss_local = model.train_step(bt).clone()
+    torch.cuda.synchronize()
+    g_item, g_theta, item_after = model.ps.item_g.clone(), model.ps.theta_g.clone(), model.ps.item.clone()
+    single, _ = build(N, 0, 1)
+    btf = single.to_device(torch.from_numpy(packed).pin_memory(), B, T, Nn)
+    loss_full = single.train_step(btf).clone()
+    torch.cuda.synchronize()
+    lo, hi = parallel.shard_sessions(B, rank, world)
+    rel = lambda a, b: float((a - b).double().norm() / (b.double().norm() + 1e-30))
+    res["loss_maxabs"] = float((loss_local - loss_full[lo:hi]).abs().max())
+    res["g_item_rel"] = rel(g_item, single.ps.item_g)
+    res["g_theta_rel"] = rel(g_theta, single.ps.theta_g)
+    res["item_after_rel"] = rel(item_after, single.ps.item)
+    # ---- catalog-sharded eval vs single GPU
+    epacked = synth.make_index_batch(N, B, T, 0, mwdhm, seed=8)
+    ebt = single.to_device(torch.from_numpy(epacked).pin_memory(), B, T, 0)
+    top1, n1, ce1 = [x.clone() for x in single.eval_step(ebt)]
+    single.world, single.rank = world, rank
+    slo, shi = single.shard_bounds(world)[rank]
+    topg, ng, ceg = single.eval_step(ebt, shard=(slo, shi, single.iext_shard(slo, shi)))
+    torch.cuda.synchronize()
+    res["top20_equal"] = bool(torch.equal(top1, topg))
+    hit = n1 < 20
+    res["rank_equal"] = bool(torch.equal(hit, ng < 20) and torch.equal(n1[hit], ng[hit]))
+    res["ce_maxabs"] = float((ce1 - ceg).abs().max())
+    ok = (res["loss_maxabs"] < 1e-5 and res["g_item_rel"] < 1e-5 and res["g_theta_rel"] < 1e-5
+          and res["item_after_rel"] < 1e-6 and res["top20_equal"] and res["rank_equal"] and res["ce_maxabs"] < 1e-4)
+    res["ok"] = ok
+    print(f"rank {rank}/{world}: " + json.dumps(res), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
