@@ -33,6 +33,7 @@ extern "C" {
 #define TCAR_TOPK 20      /* cutoff                          (model_combine.py:296,301)                */
 #define TCAR_CHUNK 8      /* items per eval chunk-max                                                   */
 #define TCAR_NCAND_CHUNKS 32 /* chunks re-scored per query (256 candidate items)                        */
+#define TCAR_NORM_SPLIT 8    /* partial sums per tensor written by tcar_sqnorm_segments                     */
 
 #define TCAR_CLUSTER_PAIR (-2) /* tcar_score_fwd `cluster` value: CTA pair, tcgen05.mma.cta_group::2 (M = 256)   */
 
@@ -127,6 +128,12 @@ int tcar_small_table_grads(const int32_t* idx, const int32_t* ctx, const float* 
                            float* g_day, float* g_week, float* g_hour, float* g_minute, float* g_dur, int B, int T,
                            void* stream);
 
+/* (5a') backward of an elementwise activation fused with the bias gradient (linear_2d, modules.py:43-55):
+ *      dz[r,c] = dy[r,c] * act'(y[r,c]) with act' expressed through the OUTPUT y (mode 0: tanh -> 1 - y^2,
+ *      mode 1: relu -> y > 0); gb[c] = sum_r dz[r,c] in a fixed order.  dz may alias dy. */
+int tcar_act_bwd_colsum(const float* dy, const float* y, float* dz, float* gb, int rows, int cols, int mode,
+                        void* stream);
+
 /* (5b) deterministic scatter-add of the sparse item-row gradients into the dense g_item [N+1,256]:
  *      clicked rows (clip Jacobian of dXi), label rows (-a_ic[:, :250]) and negative rows (coef a_ic[:, :250]).
  *      Accumulation is exact int64 fixed point (2^-40) in a hash-slotted scratch, so the result does not depend
@@ -137,7 +144,9 @@ int tcar_scatter_add_rows(const int32_t* seq, const int32_t* label, const int32_
                           int32_t* hash_keys, long long* hash_acc, int hash_size, int B, int T, int Nn,
                           void* stream);
 
-/* (5c) per-tensor squared L2 norms (for tf.clip_by_norm, model_combine.py:158-160). seg_off [nseg+1]. */
+/* (5c) per-tensor squared L2 norms (for tf.clip_by_norm, model_combine.py:158-160). seg_off [nseg+1], every
+ *      segment start 16-byte aligned and zero padded to a multiple of 4 floats.  tcar_sqnorm_segments writes
+ *      sqnorm [nseg][TCAR_NORM_SPLIT] partial sums (tcar_adam_small adds them in index order). */
 int tcar_sqnorm_segments(const float* flat, const int32_t* seg_off, float* sqnorm, int nseg, void* stream);
 int tcar_sqnorm_big(const float* x, float* partial, float* sqnorm, long long n, void* stream);
 

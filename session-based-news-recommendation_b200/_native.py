@@ -9,6 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtcar_b200.so")
 
 H, HP, TH, XW, PW, NBINS, KEXT, QROWS, MAXT, TOPK, CHUNK, NCAND_CHUNKS = 250, 256, 64, 500, 320, 139, 640, 512, 40, 20, 8, 32
+NORM_SPLIT = 8
 BIN_OFF = (0, 13, 45, 53, 78, 139)
 CLUSTER_PAIR = -2      # TCAR_CLUSTER_PAIR: tcar_score_fwd with tcgen05.mma.cta_group::2 CTA pairs
 
@@ -31,6 +32,7 @@ SIGNATURES = {
     "tcar_score_bwd_finish": [_P] * 13 + [_I, _P],
     "tcar_score_bwd_i": [_P] * 3 + [_I, _I, _I, _P],
     "tcar_small_table_grads": [_P] * 22 + [_I, _I, _P],
+    "tcar_act_bwd_colsum": [_P] * 4 + [_I, _I, _I, _P],
     "tcar_scatter_add_rows": [_P] * 10 + [_I] * 4 + [_P],
     "tcar_sqnorm_segments": [_P] * 3 + [_I, _P],
     "tcar_sqnorm_big": [_P] * 3 + [_LL, _P],

@@ -38,22 +38,38 @@ build_iext_kernel(const float* __restrict__ item, const float* __restrict__ cont
     }
 }
 
-// one CTA per segment (tensor) of a flat fp32 buffer: fixed-order sum of squares
-__global__ void __launch_bounds__(1024)
+// TCAR_NORM_SPLIT CTAs per segment (tensor) of a flat fp32 buffer: each reduces a contiguous slice in a fixed order
+// and writes one partial; the consumer (adam_small_kernel) adds the partials in index order.
+constexpr int kSplit = TCAR_NORM_SPLIT;
+__global__ void __launch_bounds__(512)
 sqnorm_segments_kernel(const float* __restrict__ flat, const int32_t* __restrict__ seg_off, float* __restrict__ out) {
-    __shared__ float red[32];
-    const int s = blockIdx.x;
-    const int lo = seg_off[s], hi = seg_off[s + 1];
-    float acc = 0.f;
-    for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) acc = fmaf(flat[i], flat[i], acc);
+    __shared__ float red[16];
+    const int s = blockIdx.y, j = blockIdx.x;
+    const int lo = seg_off[s], hi = seg_off[s + 1];           // 16-byte aligned starts (params.py pads to 4 floats)
+    const int n4 = (hi - lo) >> 2;                            // pads are zero, so whole float4s are safe
+    const int per = (n4 + kSplit - 1) / kSplit;
+    const int a = j * per, b = min(a + per, n4);
+    const float4* x = reinterpret_cast<const float4*>(flat + lo);
+    float acc0 = 0.f, acc1 = 0.f;
+    int i = a + threadIdx.x;
+    for (; i + 512 < b; i += 1024) {
+        const float4 u = x[i], v = x[i + 512];
+        acc0 += u.x * u.x + u.y * u.y + u.z * u.z + u.w * u.w;
+        acc1 += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    if (i < b) {
+        const float4 u = x[i];
+        acc0 += u.x * u.x + u.y * u.y + u.z * u.z + u.w * u.w;
+    }
+    float acc = acc0 + acc1;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
     __syncthreads();
     if (threadIdx.x == 0) {
         float t = 0.f;
-        for (int i = 0; i < 32; ++i) t += red[i];
-        out[s] = t;
+        for (int k = 0; k < 16; ++k) t += red[k];
+        out[s * kSplit + j] = t;
     }
 }
 
@@ -113,7 +129,10 @@ adam_small_kernel(float* __restrict__ theta, float* __restrict__ m, float* __res
                   const float* __restrict__ sqnorm, const int32_t* __restrict__ step, float lr, float max_grad) {
     const int s = blockIdx.y;
     const int lo = seg_off[s], hi = seg_off[s + 1];
-    const float cf = clip_factor(sqnorm[s], max_grad);
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < kSplit; ++j) sq += sqnorm[s * kSplit + j];
+    const float cf = clip_factor(sq, max_grad);
     const float lr_t = adam_lr_t(step[0], lr);
     for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
         float p = theta[i], mm = m[i], vv = v[i];
@@ -164,7 +183,7 @@ extern "C" int tcar_build_iext(const float* item, const float* content, const in
 extern "C" int tcar_sqnorm_segments(const float* flat, const int32_t* seg_off, float* sqnorm, int nseg,
                                     void* stream) {
     if (nseg < 1) return TCAR_ERR_ARG;
-    sqnorm_segments_kernel<<<nseg, 1024, 0, STREAM>>>(flat, seg_off, sqnorm);
+    sqnorm_segments_kernel<<<dim3(kSplit, nseg), 512, 0, STREAM>>>(flat, seg_off, sqnorm);
     return (int)cudaGetLastError();
 }
 

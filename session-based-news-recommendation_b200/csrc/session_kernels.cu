@@ -296,23 +296,58 @@ build_query_kernel(const float* __restrict__ a_ic, const float* __restrict__ a_p
 }
 
 // ------------------------------------------------------------------------------------------------ (4a) CE finish
-// 32 rows per CTA, 8 warps stride over tiles, fixed combine order.
-__global__ void __launch_bounds__(256)
+// 32 rows per CTA, 32 warps stride over the tiles with 4 independent loads in flight, fixed combine order.
+__global__ void __launch_bounds__(1024)
 ce_finish_kernel(const float* __restrict__ part, float* __restrict__ sumexp, float* __restrict__ ce, int n_tiles,
                  int B) {
-    __shared__ float s[8][32];
+    __shared__ float s[32][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int b = blockIdx.x * 32 + lane;
-    float acc = 0.f;
-    if (b < B)
-        for (int t = w; t < n_tiles; t += 8) acc += part[(size_t)t * TCAR_QROWS + b];
-    s[w][lane] = acc;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (b < B) {
+        int t = w;
+        for (; t + 96 < n_tiles; t += 128) {
+            a0 += part[(size_t)t * TCAR_QROWS + b];
+            a1 += part[(size_t)(t + 32) * TCAR_QROWS + b];
+            a2 += part[(size_t)(t + 64) * TCAR_QROWS + b];
+            a3 += part[(size_t)(t + 96) * TCAR_QROWS + b];
+        }
+        for (; t < n_tiles; t += 32) a0 += part[(size_t)t * TCAR_QROWS + b];
+    }
+    s[w][lane] = (a0 + a1) + (a2 + a3);
     __syncthreads();
     if (w == 0 && b < B) {
         float tot = 0.f;
-        for (int i = 0; i < 8; ++i) tot += s[i][lane];
+        for (int i = 0; i < 32; ++i) tot += s[i][lane];
         sumexp[b] = tot;
         ce[b] = logf(tot);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ (5a') act bwd
+// 32 columns per CTA (lane = column), 8 warps stride over the rows; column sums combined in warp order.
+__global__ void __launch_bounds__(256)
+act_bwd_colsum_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dz,
+                      float* __restrict__ gb, int rows, int cols, int mode) {
+    __shared__ float s[8][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
+    float acc = 0.f;
+    if (c < cols) {
+        for (int r = w; r < rows; r += 8) {
+            const size_t i = (size_t)r * cols + c;
+            const float yv = y[i];
+            const float d = dy[i] * (mode == 0 ? (1.f - yv * yv) : (yv > 0.f ? 1.f : 0.f));
+            dz[i] = d;
+            acc += d;
+        }
+    }
+    s[w][lane] = acc;
+    __syncthreads();
+    if (w == 0 && c < cols) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += s[i][lane];
+        gb[c] = t;
     }
 }
 
@@ -617,7 +652,14 @@ extern "C" int tcar_build_query(const float* a_ic, const float* a_pt, const floa
 
 extern "C" int tcar_ce_finish(const float* rowsum_part, float* sumexp, float* ce, int n_tiles, int B, void* stream) {
     if (B < 1 || B > TCAR_QROWS) return TCAR_ERR_ARG;
-    ce_finish_kernel<<<(B + 31) / 32, 256, 0, STREAM>>>(rowsum_part, sumexp, ce, n_tiles, B);
+    ce_finish_kernel<<<(B + 31) / 32, 1024, 0, STREAM>>>(rowsum_part, sumexp, ce, n_tiles, B);
+    return LAUNCH_RC();
+}
+
+extern "C" int tcar_act_bwd_colsum(const float* dy, const float* y, float* dz, float* gb, int rows, int cols, int mode,
+                                   void* stream) {
+    if (rows < 1 || cols < 1 || (mode != 0 && mode != 1)) return TCAR_ERR_ARG;
+    act_bwd_colsum_kernel<<<(cols + 31) / 32, 256, 0, STREAM>>>(dy, y, dz, gb, rows, cols, mode);
     return LAUNCH_RC();
 }
 

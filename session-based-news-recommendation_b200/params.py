@@ -72,7 +72,7 @@ class ParamStore:
         self.theta_m = torch.zeros_like(self.theta)
         self.theta_v = torch.zeros_like(self.theta)
         self.theta_g = torch.zeros_like(self.theta)
-        self.sqnorm_small = torch.zeros(len(SMALL), device=dev)
+        self.sqnorm_small = torch.zeros(len(SMALL), nv.NORM_SPLIT, device=dev)
         self.sqnorm_item = torch.zeros(1, device=dev)
         self.norm_partial = torch.zeros(1184, device=dev)
         self.step = torch.zeros(1, device=dev, dtype=torch.int32)
