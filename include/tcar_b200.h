@@ -134,6 +134,30 @@ int tcar_small_table_grads(const int32_t* idx, const int32_t* ctx, const float* 
 int tcar_act_bwd_colsum(const float* dy, const float* y, float* dz, float* gb, int rows, int cols, int mode,
                         void* stream);
 
+/* (2c) dense projections on the tensor cores (tcgen05.mma.kind::tf32) -- the matmuls of linear_2d / linear_3d
+ *      (modules.py:43-70) and their weight / data gradients:
+ *          C[M,N] = act( sum_{s<nseg} A_s[M,K_s] . B_s[K_s,N] + bias )         act: 0 none, 1 relu, 2 tanh
+ *      A_s is given K-major (row-major [M,K_s], a_mn_major = 0) or MN-major (row-major [K_s,M], a_mn_major = 1);
+ *      B_s K-major (row-major [N,K_s]) or MN-major (row-major [K_s,N]).  Row pitches (lda/ldb, in floats) must be
+ *      multiples of 4 and base pointers 16-byte aligned (TMA).  precise = 1: 3xTF32 (fp32-class accuracy), needs
+ *      b = tf32(B), b_lo = tf32(B - b) with the same layout (tcar_prep_weights); precise = 0: single-pass TF32.
+ *      splits > 1 splits the reduction over CTAs: `part` [tcar_gemm_tf32_part_elems(M,N,splits)] floats, reduced in
+ *      a fixed order (no bias / act / accumulate / precise in that mode).  accumulate = 1: C += result. */
+typedef struct tcar_gemm_seg {
+    const float* a;
+    const float* b;
+    const float* b_lo;
+    int lda, ldb, k, a_mn_major, b_mn_major;
+    int a_koff; /* first K index of this segment inside `a` (a column / row offset that keeps `a` 16-byte aligned) */
+} tcar_gemm_seg;
+int tcar_gemm_tf32(const tcar_gemm_seg* segs, int nseg, int M, int N, const float* bias, int act, float* C, int ldc,
+                   int accumulate, int precise, int splits, float* part, void* stream);
+int tcar_gemm_tf32_splits(int M, int N, int k_total, int want);
+long long tcar_gemm_tf32_part_elems(int M, int N, int splits);
+/* hi/lo split of the dense weights into padded layouts: table [ntensors][5] = {src_off, rows, cols, dst_off,
+ * dst_pitch} (int32, device); hi = tf32(w) rounded to nearest, lo = tf32(w - hi); pad columns zero. */
+int tcar_prep_weights(const float* theta, const int32_t* table, int ntensors, float* hi, float* lo, void* stream);
+
 /* (5b) deterministic scatter-add of the sparse item-row gradients into the dense g_item [N+1,256]:
  *      clicked rows (clip Jacobian of dXi), label rows (-a_ic[:, :250]) and negative rows (coef a_ic[:, :250]).
  *      Accumulation is exact int64 fixed point (2^-40) in a hash-slotted scratch, so the result does not depend

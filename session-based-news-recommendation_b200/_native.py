@@ -33,6 +33,10 @@ SIGNATURES = {
     "tcar_score_bwd_i": [_P] * 3 + [_I, _I, _I, _P],
     "tcar_small_table_grads": [_P] * 22 + [_I, _I, _P],
     "tcar_act_bwd_colsum": [_P] * 4 + [_I, _I, _I, _P],
+    "tcar_gemm_tf32": [_P, _I, _I, _I, _P, _I, _P, _I, _I, _I, _I, _P, _P],
+    "tcar_gemm_tf32_splits": [_I, _I, _I, _I],
+    "tcar_gemm_tf32_part_elems": [_I, _I, _I],
+    "tcar_prep_weights": [_P, _P, _I, _P, _P, _P],
     "tcar_scatter_add_rows": [_P] * 10 + [_I] * 4 + [_P],
     "tcar_sqnorm_segments": [_P] * 3 + [_I, _P],
     "tcar_sqnorm_big": [_P] * 3 + [_LL, _P],
@@ -60,7 +64,7 @@ def lib():
         for name, argtypes in SIGNATURES.items():
             fn = getattr(l, name)
             fn.argtypes = argtypes
-            fn.restype = C.c_int
+            fn.restype = C.c_longlong if name == "tcar_gemm_tf32_part_elems" else C.c_int
         _lib = l
     return _lib
 
@@ -81,6 +85,25 @@ def call(name, *args):
     if rc != 0:
         raise TcarNativeError(f"{name} failed with code {rc}")
     return rc
+
+
+class GemmSeg(C.Structure):
+    """tcar_gemm_seg of include/tcar_b200.h."""
+    _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("b_lo", C.c_void_p), ("lda", C.c_int), ("ldb", C.c_int),
+                ("k", C.c_int), ("a_mn_major", C.c_int), ("b_mn_major", C.c_int), ("a_koff", C.c_int)]
+
+
+def gemm(segs, M, N, out, ldc, bias=None, act=0, accumulate=False, precise=False, splits=1, part=None):
+    """C[M,N] = act(sum_s A_s . B_s + bias) on the tensor cores.  segs: list of
+    (a, lda, a_mn, b, b_lo, ldb, b_mn, k[, a_koff]) with a / b / b_lo torch tensors (data_ptr = operand origin)."""
+    arr = (GemmSeg * len(segs))()
+    for i, sg in enumerate(segs):
+        a, lda, a_mn, b, b_lo, ldb, b_mn, k = sg[:8]
+        arr[i] = GemmSeg(a.data_ptr(), b.data_ptr(), b_lo.data_ptr() if b_lo is not None else None, lda, ldb, k,
+                         int(a_mn), int(b_mn), sg[8] if len(sg) > 8 else 0)
+    LAUNCHES["count"] += 1 + (1 if splits > 1 else 0)
+    return call("tcar_gemm_tf32", C.cast(arr, C.c_void_p), len(segs), M, N, ptr(bias), act, ptr(out), ldc,
+                int(accumulate), int(precise), splits, ptr(part))
 
 
 LAUNCHES = {"count": 0}

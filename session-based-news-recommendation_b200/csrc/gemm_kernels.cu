@@ -1,0 +1,463 @@
+// Session-side dense projections on 5th-gen tensor cores (tcgen05.mma.kind::tf32 + TMEM + TMA), sm_100a only.
+//
+// Replaces the TF matmuls behind linear_2d / linear_3d (modules.py:43-70) and the weight / data gradients TF derives
+// from them (model_combine.py:156):
+//
+//   C[M,N] = act( sum_seg A_seg[M,K_seg] . B_seg[K_seg,N] + bias )         (or  C += ...)
+//
+// * `precise` (forward): 3xTF32 -- every fp32 operand is split into hi = top 19 bits and lo = a - hi, and each K step
+//   issues  A_hi.B_hi + A_lo.B_hi + A_hi.B_lo  into the same fp32 TMEM accumulator (error ~2^-21, i.e. fp32-class;
+//   the exact re-scoring of the evaluation top-20 depends on fp32-accurate session vectors).  The B operand (weights)
+//   is pre-split by prep_weights_kernel once per step; the A operand (activations) is split in shared memory by the
+//   four epilogue warps while the tensor core works on the previous stage.
+// * fast (backward): single-pass TF32 on operands as they are (gradients carry a 2e-2 tolerance).
+// * operands may be K-major or MN-major (UMMA descriptors take both), so X.W, X^T.dU and dU.W^T all map onto the same
+//   kernel without transposes; the reduction dimension can be split across CTAs (fixed-order second pass).
+#include "sm100_ptx.cuh"
+#include "tcar_b200.h"
+
+namespace tcar {
+
+constexpr int G_THREADS = 256;   // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 split + epilogue
+constexpr int G_BM = 128;
+constexpr int G_BK = 32;         // 32 fp32 = one 128-byte swizzle span
+constexpr int G_A_TILE = G_BM * G_BK * 4;   // 16384
+constexpr int G_MAX_SEG = 3;
+constexpr int G_SMEM_BUDGET = 196608;       // stage memory (192 KB)
+constexpr int G_SMEM = G_SMEM_BUDGET + 1024 + 256;
+
+struct GemmSegDev {
+    int nkb;          // K blocks of this segment
+    int a_mn;         // 1: A operand is MN-major (tensor [K, M]), 0: K-major (tensor [M, K])
+    int b_mn;         // 1: B operand is MN-major (tensor [K, N]), 0: K-major (tensor [N, K])
+    int a_koff;       // first K index of the segment inside the A tensor (TMA coordinate offset)
+};
+
+struct GemmParams {
+    GemmSegDev seg[G_MAX_SEG];
+    int nseg;
+    int M, N, bn;          // bn = UMMA N (64 | 128 | 256)
+    int precise;           // 1: 3xTF32
+    int stages, stage_bytes, b_tile_bytes;
+    int splits, kb_per_split, kb_total;
+    const float* bias;     // [N] or null
+    int act;               // 0 none, 1 relu, 2 tanh
+    float* C;              // [M, ldc]   (or partials [splits][M_pad][ldc] when splits > 1)
+    int ldc;
+    int accumulate;        // C += result
+    long long part_stride; // elements between split partials
+};
+
+struct GemmMaps {
+    CUtensorMap a[G_MAX_SEG];
+    CUtensorMap b[G_MAX_SEG];
+    CUtensorMap blo[G_MAX_SEG];
+};
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// kind::tf32 instruction descriptor: D fp32, A/B tf32 (format 2), majors, N >> 3, M >> 4
+__device__ __forceinline__ uint32_t make_idesc_tf32(uint32_t M, uint32_t N, uint32_t a_mn, uint32_t b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+// MN-major tf32 operands exist only in the "128B swizzle with 32-byte atomicity" layout (descriptor layout type 1,
+// TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): atoms of [32 mn (128 B, contiguous) x 4 k]; one UMMA (K = 8) spans two
+// atoms along K (SBO = 512 B apart inside a [32 mn x 32 k] TMA box); MN atoms are one box (4096 B) apart (LBO).
+__device__ __forceinline__ uint64_t sdesc_mnmajor_tf32(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFFu);
+    d |= static_cast<uint64_t>((4096u >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>((512u >> 4) & 0x3FFFu) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(1) << 61;
+    return d;
+}
+// fp32 -> tf32 with round-to-nearest (low 13 bits zero afterwards, so the tensor core's own truncation is a no-op)
+__device__ __forceinline__ float tf32_rn(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(G_THREADS, 1)
+gemm_tf32_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_SMEM_BUDGET);
+    uint64_t* full = bars;            // [8]  TMA bytes landed
+    uint64_t* conv = bars + 8;        // [8]  A operand split done (precise mode)
+    uint64_t* empty = bars + 16;      // [8]  MMAs of the stage retired
+    uint64_t* acc_full = bars + 24;   // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
+
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t lane = lane_id();
+    const int mtile = blockIdx.x, ntile = blockIdx.y, split = blockIdx.z;
+    const int kb0 = split * p.kb_per_split;
+    const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
+    const int nkb = max(kb1 - kb0, 0);
+    // stage layout: [A hi 16K][A lo 16K (precise)][B hi b_tile][B lo b_tile (precise)]
+    const int a_lo_off = G_A_TILE;
+    const int b_off = p.precise ? 2 * G_A_TILE : G_A_TILE;
+    const int b_lo_off = b_off + p.b_tile_bytes;
+
+    if (warp == 0 && elect_one()) {
+        for (int s = 0; s < p.nseg; ++s) {
+            tma_prefetch_desc(&maps.a[s]);
+            tma_prefetch_desc(&maps.b[s]);
+            if (p.precise) tma_prefetch_desc(&maps.blo[s]);
+        }
+    }
+    if (warp == 1 && elect_one()) {
+        for (int i = 0; i < p.stages; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&conv[i], 4);
+            mbar_init(&empty[i], 1);
+        }
+        mbar_init(acc_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (elect_one()) {
+            uint32_t stage = 0, phase = 0;
+            int kb = 0;  // global K-block index over all segments
+            for (int s = 0; s < p.nseg; ++s) {
+                const GemmSegDev sg = p.seg[s];
+                for (int j = 0; j < sg.nkb; ++j, ++kb) {
+                    if (kb < kb0 || kb >= kb1) continue;
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    uint8_t* st = smem + (size_t)stage * p.stage_bytes;
+                    const uint32_t bytes = G_A_TILE + p.b_tile_bytes * (p.precise ? 2 : 1);
+                    mbar_expect_tx(&full[stage], bytes);
+                    const int k0 = j * G_BK;
+                    const int ka = sg.a_koff + k0;
+                    if (sg.a_mn) {
+                        // tensor [K, M]: boxes of [32 m x 32 k]
+#pragma unroll
+                        for (int i = 0; i < G_BM / 32; ++i)
+                            tma_load_2d(st + i * 4096, &maps.a[s], &full[stage], mtile * G_BM + i * 32, ka);
+                    } else {
+                        tma_load_2d(st, &maps.a[s], &full[stage], ka, mtile * G_BM);
+                    }
+                    if (sg.b_mn) {
+                        for (int i = 0; i < p.bn / 32; ++i) {
+                            tma_load_2d(st + b_off + i * 4096, &maps.b[s], &full[stage], ntile * p.bn + i * 32, k0);
+                            if (p.precise)
+                                tma_load_2d(st + b_lo_off + i * 4096, &maps.blo[s], &full[stage],
+                                            ntile * p.bn + i * 32, k0);
+                        }
+                    } else {
+                        tma_load_2d(st + b_off, &maps.b[s], &full[stage], k0, ntile * p.bn);
+                        if (p.precise) tma_load_2d(st + b_lo_off, &maps.blo[s], &full[stage], k0, ntile * p.bn);
+                    }
+                    if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        uint32_t stage = 0, phase = 0;
+        int kb = 0, issued = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+            const GemmSegDev sg = p.seg[s];
+            const uint32_t idesc = make_idesc_tf32(G_BM, p.bn, sg.a_mn, sg.b_mn);
+            for (int j = 0; j < sg.nkb; ++j, ++kb) {
+                if (kb < kb0 || kb >= kb1) continue;
+                mbar_wait(p.precise ? &conv[stage] : &full[stage], phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t a_addr = smem_u32(smem + (size_t)stage * p.stage_bytes);
+                    const uint32_t b_addr = a_addr + b_off;
+#pragma unroll
+                    for (int k = 0; k < G_BK / 8; ++k) {
+                        // K-major: 8 tf32 = 32 bytes along the swizzle span; MN-major: 8 k-rows of 128 bytes
+                        const uint32_t ao = sg.a_mn ? k * 1024 : k * 32;
+                        const uint32_t bo = sg.b_mn ? k * 1024 : k * 32;
+                        const uint64_t ad = sg.a_mn ? sdesc_mnmajor_tf32(a_addr + ao) : sdesc_kmajor(a_addr + ao);
+                        const uint64_t bd = sg.b_mn ? sdesc_mnmajor_tf32(b_addr + bo) : sdesc_kmajor(b_addr + bo);
+                        umma_tf32(tmem_base, ad, bd, idesc, (issued | k) != 0);
+                        if (p.precise) {
+                            const uint64_t adl = sg.a_mn ? sdesc_mnmajor_tf32(a_addr + a_lo_off + ao)
+                                                         : sdesc_kmajor(a_addr + a_lo_off + ao);
+                            const uint64_t bdl = sg.b_mn ? sdesc_mnmajor_tf32(a_addr + b_lo_off + bo)
+                                                         : sdesc_kmajor(a_addr + b_lo_off + bo);
+                            umma_tf32(tmem_base, adl, bd, idesc, 1);
+                            umma_tf32(tmem_base, ad, bdl, idesc, 1);
+                        }
+                    }
+                    umma_commit(&empty[stage]);
+                    if (kb == kb1 - 1) umma_commit(acc_full);
+                }
+                __syncwarp();
+                ++issued;
+                if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        const uint32_t q = warp - 4;
+        const uint32_t tid = threadIdx.x - 128;
+        if (p.precise) {
+            // ================= operand split: A tile -> (hi in place, lo next to it) =================
+            uint32_t stage = 0, phase = 0;
+            for (int it = 0; it < nkb; ++it) {
+                mbar_wait(&full[stage], phase);
+                float4* hi = reinterpret_cast<float4*>(smem + (size_t)stage * p.stage_bytes);
+                float4* lo = reinterpret_cast<float4*>(smem + (size_t)stage * p.stage_bytes + a_lo_off);
+#pragma unroll
+                for (int i = 0; i < G_A_TILE / 16 / 128; ++i) {
+                    const float4 v = hi[tid + i * 128];
+                    float4 h, l;
+                    h.x = tf32_rn(v.x); l.x = tf32_rn(v.x - h.x);
+                    h.y = tf32_rn(v.y); l.y = tf32_rn(v.y - h.y);
+                    h.z = tf32_rn(v.z); l.z = tf32_rn(v.z - h.z);
+                    h.w = tf32_rn(v.w); l.w = tf32_rn(v.w - h.w);
+                    hi[tid + i * 128] = h;
+                    lo[tid + i * 128] = l;
+                }
+                fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&conv[stage]);
+                if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+        // ================= epilogue: thread <-> output row =================
+        const int row = mtile * G_BM + q * 32 + lane;
+        if (nkb > 0) {
+            mbar_wait(acc_full, 0);
+            tc_fence_after();
+        }
+        float* crow = p.C + (size_t)split * p.part_stride + (size_t)row * p.ldc;
+        const bool vec = (p.ldc & 3) == 0;
+#pragma unroll 1
+        for (int ch = 0; ch < p.bn / 32; ++ch) {
+            uint32_t v[32];
+            if (nkb > 0) {
+                tmem_ld32(tmem_base + ((q * 32) << 16) + ch * 32, v);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0u;
+            }
+            const int c0 = ntile * p.bn + ch * 32;
+            if (row < p.M && c0 < p.N) {
+                float o[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float x = __uint_as_float(v[j]);
+                    if (p.bias && c0 + j < p.N) x += p.bias[c0 + j];
+                    if (p.act == 1) x = fmaxf(x, 0.f);
+                    else if (p.act == 2) x = tanhf(x);
+                    o[j] = x;
+                }
+                if (vec && c0 + 32 <= p.N) {
+                    float4* dst = reinterpret_cast<float4*>(crow + c0);
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        float4 t = make_float4(o[g * 4], o[g * 4 + 1], o[g * 4 + 2], o[g * 4 + 3]);
+                        if (p.accumulate) {
+                            const float4 old = dst[g];
+                            t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
+                        }
+                        dst[g] = t;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (c0 + j < p.N) crow[c0 + j] = p.accumulate ? crow[c0 + j] + o[j] : o[j];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 256);
+}
+
+// out[r, c] = sum_s part[s][r][c]  (fixed order), rows x cols with source pitch ldp and destination pitch ldc
+__global__ void gemm_reduce_splits_kernel(const float* __restrict__ part, float* __restrict__ out, int splits,
+                                          long long stride, int rows, int cols, int ldp, int ldc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const int r = i / cols, c = i % cols;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += part[(size_t)s * stride + (size_t)r * ldp + c];
+    out[(size_t)r * ldc + c] = acc;
+}
+
+// Pre-split of the dense weights (once per step, after Adam): for every tensor t of the table
+//   hi[dst_off + r*dst_pitch + c] = tf32(w) (round to nearest),   lo[...] = tf32(w - hi)   (pad columns are zero).
+// table rows: {src_off, rows, cols, dst_off, dst_pitch}
+__global__ void __launch_bounds__(256)
+prep_weights_kernel(const float* __restrict__ theta, const int32_t* __restrict__ table, float* __restrict__ hi,
+                    float* __restrict__ lo) {
+    const int32_t* t = table + blockIdx.y * 5;
+    const int src = t[0], rows = t[1], cols = t[2], dst = t[3], pitch = t[4];
+    const int n = rows * pitch;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int r = i / pitch, c = i % pitch;
+        const float w = c < cols ? theta[src + r * cols + c] : 0.f;
+        const float h = tf32_rn(w);
+        hi[dst + i] = h;
+        lo[dst + i] = tf32_rn(w - h);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn32)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn32 get_encode_fn32() {
+    static EncodeTiledFn32 fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<EncodeTiledFn32>(ptr);
+    }
+    return fn;
+}
+
+// 2-D fp32 row-major tensor [rows, cols] (cols contiguous, pitch in elements); box = [box_cols, box_rows], SW128,
+// out-of-bounds elements read as zero (this is what pads K and the M / N edges).
+static int make_map_f32(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
+                        uint32_t box_cols, uint32_t box_rows, bool mn_major = false) {
+    EncodeTiledFn32 fn = get_encode_fn32();
+    if (!fn) return TCAR_ERR_DRIVER;
+    if ((pitch_elems * 4) % 16 != 0 || (reinterpret_cast<uintptr_t>(base) & 15)) return TCAR_ERR_ARG;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {pitch_elems * 4};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : TCAR_ERR_TENSORMAP;
+}
+
+}  // namespace tcar
+
+using namespace tcar;
+
+extern "C" int tcar_gemm_tf32_splits(int M, int N, int k_total, int want) {
+    (void)M; (void)N;
+    const int kb = (k_total + G_BK - 1) / G_BK;
+    int s = want < 1 ? 1 : want;
+    if (s > kb) s = kb;
+    return s;
+}
+
+extern "C" int tcar_gemm_tf32(const tcar_gemm_seg* segs, int nseg, int M, int N, const float* bias, int act, float* C,
+                              int ldc, int accumulate, int precise, int splits, float* part, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (nseg < 1 || nseg > G_MAX_SEG || M < 1 || N < 1 || !C) return TCAR_ERR_ARG;
+    if (splits < 1 || (splits > 1 && (!part || bias || act || precise))) return TCAR_ERR_ARG;
+    GemmParams p = {};
+    GemmMaps maps;
+    p.nseg = nseg;
+    p.M = M;
+    p.N = N;
+    p.precise = precise ? 1 : 0;
+    // UMMA N: one tile when N <= 256, else 256-wide tiles; narrow outputs use the smallest legal tile
+    p.bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+    if (precise && p.bn == 256 && M <= 1024) p.bn = 128;     // more CTAs for the small-batch projections
+    p.b_tile_bytes = p.bn * G_BK * 4;
+    p.stage_bytes = (G_A_TILE + p.b_tile_bytes) * (precise ? 2 : 1);
+    p.stages = G_SMEM_BUDGET / p.stage_bytes;
+    if (p.stages > 8) p.stages = 8;
+    if (p.stages < 2) return TCAR_ERR_ARG;
+    int kb_total = 0;
+    for (int s = 0; s < nseg; ++s) {
+        const tcar_gemm_seg& g = segs[s];
+        if (!g.a || !g.b || g.k < 1 || (precise && !g.b_lo)) return TCAR_ERR_ARG;
+        p.seg[s].nkb = (g.k + G_BK - 1) / G_BK;
+        p.seg[s].a_mn = g.a_mn_major ? 1 : 0;
+        p.seg[s].b_mn = g.b_mn_major ? 1 : 0;
+        p.seg[s].a_koff = g.a_koff;
+        if (g.a_koff < 0) return TCAR_ERR_ARG;
+        kb_total += p.seg[s].nkb;
+        int rc;
+        // the tensor extent along K ends at a_koff + k, so the last K block is zero-filled beyond it
+        if (g.a_mn_major) rc = make_map_f32(&maps.a[s], g.a, g.a_koff + g.k, M, g.lda, 32, G_BK, true);  // [K, M]
+        else rc = make_map_f32(&maps.a[s], g.a, M, g.a_koff + g.k, g.lda, G_BK, G_BM);             // [M, K]
+        if (rc) return rc;
+        if (g.b_mn_major) rc = make_map_f32(&maps.b[s], g.b, g.k, N, g.ldb, 32, G_BK, true);       // tensor [K, N]
+        else rc = make_map_f32(&maps.b[s], g.b, N, g.k, g.ldb, G_BK, p.bn);                 // tensor [N, K]
+        if (rc) return rc;
+        if (precise) {
+            if (g.b_mn_major) rc = make_map_f32(&maps.blo[s], g.b_lo, g.k, N, g.ldb, 32, G_BK, true);
+            else rc = make_map_f32(&maps.blo[s], g.b_lo, N, g.k, g.ldb, G_BK, p.bn);
+            if (rc) return rc;
+        } else {
+            maps.blo[s] = maps.b[s];
+        }
+    }
+    for (int s = nseg; s < G_MAX_SEG; ++s) {
+        maps.a[s] = maps.a[0];
+        maps.b[s] = maps.b[0];
+        maps.blo[s] = maps.blo[0];
+    }
+    p.kb_total = kb_total;
+    if (splits > kb_total) splits = kb_total;
+    p.splits = splits;
+    p.kb_per_split = (kb_total + splits - 1) / splits;
+    p.bias = bias;
+    p.act = act;
+    p.accumulate = accumulate ? 1 : 0;
+    const int mtiles = (M + G_BM - 1) / G_BM, ntiles = (N + p.bn - 1) / p.bn;
+    if (splits > 1) {
+        p.C = part;
+        p.ldc = ntiles * p.bn;
+        p.part_stride = (long long)mtiles * G_BM * p.ldc;
+        p.accumulate = 0;
+    } else {
+        p.C = C;
+        p.ldc = ldc;
+        p.part_stride = 0;
+    }
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    gemm_tf32_kernel<<<dim3(mtiles, ntiles, splits), G_THREADS, G_SMEM, stream>>>(maps, p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    if (splits > 1) {
+        if (accumulate) return TCAR_ERR_ARG;
+        const int total = M * N;
+        gemm_reduce_splits_kernel<<<(total + 255) / 256, 256, 0, stream>>>(part, C, splits, p.part_stride, M, N, p.ldc,
+                                                                           ldc);
+        e = cudaGetLastError();
+    }
+    return (int)e;
+}
+
+extern "C" long long tcar_gemm_tf32_part_elems(int M, int N, int splits) {
+    const int bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+    const long long mt = (M + G_BM - 1) / G_BM, nt = (N + bn - 1) / bn;
+    return (long long)splits * mt * G_BM * nt * bn;
+}
+
+extern "C" int tcar_prep_weights(const float* theta, const int32_t* table, int ntensors, float* hi, float* lo,
+                                 void* stream_) {
+    if (ntensors < 1) return TCAR_ERR_ARG;
+    prep_weights_kernel<<<dim3(16, ntensors), 256, 0, static_cast<cudaStream_t>(stream_)>>>(theta, table, hi, lo);
+    return (int)cudaGetLastError();
+}

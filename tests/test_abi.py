@@ -12,13 +12,13 @@ HEADER = os.path.join(ROOT, "include", "tcar_b200.h")
 def declared_functions():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\bint\s+(tcar_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(?:int|long long)\s+(tcar_[a-z0-9_]+)\s*\(", src)))
 
 
 def declared_arg_counts():
     src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
     out = {}
-    for name, args in re.findall(r"\bint\s+(tcar_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+    for name, args in re.findall(r"\b(?:int|long long)\s+(tcar_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
         out[name] = len([a for a in args.split(",") if a.strip()])
     return out
 
