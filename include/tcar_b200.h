@@ -54,13 +54,14 @@ int tcar_gather_fwd(const int32_t* idx, const int32_t* ctx, const float* item, c
                     void* stream);
 
 /* (2) attention pooling forward -- modules.py:72-152 (count_alpha_m / count_alpha_s / *_attention_layer) after
- *     the linear_3d projections.  U1/U2 hold the pre-activation sums on entry and sigmoid(.) on exit.
+ *     the linear_3d projections.  U1/U2 [B*T, 256-float pitch] hold the pre-activation sums on entry and
+ *     sigmoid(.) on exit (S1/S2/dU1/dU2 of the backward use the same pitch).
  *     alpha [3][B*T] = nrm(e1), nrm(e2), nrm(e_t) with nrm(x) = exp(x)/(sum exp(x) + 1e-9)  (util.py:92-100). */
 int tcar_pool_fwd(const float* X, const float* P, float* U1, float* U2, const float* q, const float* w_r,
                   const float* w_t, float* alpha, float* pooled, float* pooled_t, int B, int T, void* stream);
 
 /* (2b) attention pooling backward (gradient of (2) that tf.gradients derives, model_combine.py:156).
- *      Outputs dU1/dU2 (pre-activation grads), dXi [B*T,250] (item half of dX only -- content is frozen),
+ *      Outputs dU1/dU2 (pre-activation grads), dXi [B*T, 256-float pitch] (item half of dX only -- content is frozen),
  *      dP [B*T,320], dq [B,500], de [3][B*T]. */
 int tcar_pool_bwd(const float* X, const float* P, const float* S1, const float* S2, const float* q,
                   const float* w_r, const float* w_t, const float* alpha, const float* dpooled,
@@ -130,8 +131,9 @@ int tcar_small_table_grads(const int32_t* idx, const int32_t* ctx, const float* 
 
 /* (5a') backward of an elementwise activation fused with the bias gradient (linear_2d, modules.py:43-55):
  *      dz[r,c] = dy[r,c] * act'(y[r,c]) with act' expressed through the OUTPUT y (mode 0: tanh -> 1 - y^2,
- *      mode 1: relu -> y > 0); gb[c] = sum_r dz[r,c] in a fixed order.  dz may alias dy. */
-int tcar_act_bwd_colsum(const float* dy, const float* y, float* dz, float* gb, int rows, int cols, int mode,
+ *      mode 1: relu -> y > 0); gb[c] = sum_r dz[r,c] in a fixed order.  dz may alias dy; `ld` = row pitch of all
+ *      three matrices. */
+int tcar_act_bwd_colsum(const float* dy, const float* y, float* dz, float* gb, int rows, int cols, int ld, int mode,
                         void* stream);
 
 /* (2c) dense projections on the tensor cores (tcgen05.mma.kind::tf32) -- the matmuls of linear_2d / linear_3d
@@ -152,10 +154,25 @@ typedef struct tcar_gemm_seg {
 } tcar_gemm_seg;
 int tcar_gemm_tf32(const tcar_gemm_seg* segs, int nseg, int M, int N, const float* bias, int act, float* C, int ldc,
                    int accumulate, int precise, int splits, float* part, void* stream);
+/* Several independent problems in ONE launch (each launch costs ~7 us of fixed latency on the GPU): e.g. all weight
+ * gradients that consume dU1 / dU2.  Split problems of one group need disjoint `part` buffers. */
+#define TCAR_GEMM_MAX_GROUP 8
+typedef struct tcar_gemm_problem {
+    tcar_gemm_seg segs[3];
+    int nseg, M, N;
+    const float* bias;
+    int act;
+    float* C;
+    int ldc, accumulate, precise, splits;
+    float* part;
+} tcar_gemm_problem;
+int tcar_gemm_tf32_group(const tcar_gemm_problem* probs, int nprob, void* stream);
 int tcar_gemm_tf32_splits(int M, int N, int k_total, int want);
 long long tcar_gemm_tf32_part_elems(int M, int N, int splits);
-/* hi/lo split of the dense weights into padded layouts: table [ntensors][5] = {src_off, rows, cols, dst_off,
- * dst_pitch} (int32, device); hi = tf32(w) rounded to nearest, lo = tf32(w - hi); pad columns zero. */
+/* hi/lo split of the dense weights into padded layouts: table [ntensors][7] = {src_off, rows, cols, dst_off,
+ * dst_pitch, src2_off, src2_row0} (int32, device); w = theta[src] (+ theta[src2] for rows >= src2_row0 when
+ * src2_off >= 0 -- folds W_c into the bottom half of W_in); hi = tf32(w) rounded to nearest, lo = tf32(w - hi);
+ * pad columns zero. */
 int tcar_prep_weights(const float* theta, const int32_t* table, int ntensors, float* hi, float* lo, void* stream);
 
 /* (5b) deterministic scatter-add of the sparse item-row gradients into the dense g_item [N+1,256]:

@@ -32,8 +32,9 @@ SIGNATURES = {
     "tcar_score_bwd_finish": [_P] * 13 + [_I, _P],
     "tcar_score_bwd_i": [_P] * 3 + [_I, _I, _I, _P],
     "tcar_small_table_grads": [_P] * 22 + [_I, _I, _P],
-    "tcar_act_bwd_colsum": [_P] * 4 + [_I, _I, _I, _P],
+    "tcar_act_bwd_colsum": [_P] * 4 + [_I, _I, _I, _I, _P],
     "tcar_gemm_tf32": [_P, _I, _I, _I, _P, _I, _P, _I, _I, _I, _I, _P, _P],
+    "tcar_gemm_tf32_group": [_P, _I, _P],
     "tcar_gemm_tf32_splits": [_I, _I, _I, _I],
     "tcar_gemm_tf32_part_elems": [_I, _I, _I],
     "tcar_prep_weights": [_P, _P, _I, _P, _P, _P],
@@ -91,6 +92,39 @@ class GemmSeg(C.Structure):
     """tcar_gemm_seg of include/tcar_b200.h."""
     _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("b_lo", C.c_void_p), ("lda", C.c_int), ("ldb", C.c_int),
                 ("k", C.c_int), ("a_mn_major", C.c_int), ("b_mn_major", C.c_int), ("a_koff", C.c_int)]
+
+
+class GemmProblem(C.Structure):
+    """tcar_gemm_problem of include/tcar_b200.h."""
+    _fields_ = [("segs", GemmSeg * 3), ("nseg", C.c_int), ("M", C.c_int), ("N", C.c_int), ("bias", C.c_void_p),
+                ("act", C.c_int), ("C", C.c_void_p), ("ldc", C.c_int), ("accumulate", C.c_int), ("precise", C.c_int),
+                ("splits", C.c_int), ("part", C.c_void_p)]
+
+
+def _seg(sg):
+    a, lda, a_mn, b, b_lo, ldb, b_mn, k = sg[:8]
+    return GemmSeg(a.data_ptr(), b.data_ptr(), b_lo.data_ptr() if b_lo is not None else None, lda, ldb, k,
+                   int(a_mn), int(b_mn), sg[8] if len(sg) > 8 else 0)
+
+
+def problem(segs, M, N, out, ldc, bias=None, act=0, accumulate=False, precise=False, splits=1, part=None):
+    """One tcar_gemm_problem; segs as in gemm()."""
+    q = GemmProblem()
+    for i, sg in enumerate(segs):
+        q.segs[i] = _seg(sg)
+    q.nseg, q.M, q.N = len(segs), M, N
+    q.bias = bias.data_ptr() if bias is not None else None
+    q.act, q.C, q.ldc = act, out.data_ptr(), ldc
+    q.accumulate, q.precise, q.splits = int(accumulate), int(precise), splits
+    q.part = part.data_ptr() if part is not None else None
+    return q
+
+
+def gemm_group(problems):
+    """Launch several independent problems (built with problem()) as one kernel (+ one split-reduction kernel)."""
+    arr = (GemmProblem * len(problems))(*problems)
+    LAUNCHES["count"] += 1 + (1 if any(q.splits > 1 for q in problems) else 0)
+    return call("tcar_gemm_tf32_group", C.cast(arr, C.c_void_p), len(problems))
 
 
 def gemm(segs, M, N, out, ldc, bias=None, act=0, accumulate=False, precise=False, splits=1, part=None):

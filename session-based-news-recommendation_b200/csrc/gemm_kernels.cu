@@ -40,18 +40,32 @@ struct GemmParams {
     int precise;           // 1: 3xTF32
     int stages, stage_bytes, b_tile_bytes;
     int splits, kb_per_split, kb_total;
+    int mtiles, ntiles;
     const float* bias;     // [N] or null
     int act;               // 0 none, 1 relu, 2 tanh
     float* C;              // [M, ldc]   (or partials [splits][M_pad][ldc] when splits > 1)
     int ldc;
     int accumulate;        // C += result
     long long part_stride; // elements between split partials
+    float* out;            // final destination of the split reduction
+    int ld_out;
 };
 
 struct GemmMaps {
     CUtensorMap a[G_MAX_SEG];
     CUtensorMap b[G_MAX_SEG];
     CUtensorMap blo[G_MAX_SEG];
+};
+
+// One launch = up to G_MAX_PROB independent problems (e.g. every weight gradient that consumes dU1 / dU2); CTAs are
+// numbered problem after problem: [cta_start[g], cta_start[g+1]).
+constexpr int G_MAX_PROB = TCAR_GEMM_MAX_GROUP;
+struct GemmGroup {
+    GemmMaps maps[G_MAX_PROB];
+    GemmParams prm[G_MAX_PROB];
+    int cta_start[G_MAX_PROB + 1];
+    int red_start[G_MAX_PROB + 1];   // CTA ranges of the split-reduction kernel
+    int nprob;
 };
 
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -90,7 +104,11 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 }
 
 __global__ void __launch_bounds__(G_THREADS, 1)
-gemm_tf32_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
+gemm_tf32_kernel(const __grid_constant__ GemmGroup grp) {
+    int gi = 0;
+    while (gi + 1 < grp.nprob && (int)blockIdx.x >= grp.cta_start[gi + 1]) ++gi;
+    const GemmMaps& maps = grp.maps[gi];
+    const GemmParams& p = grp.prm[gi];
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_SMEM_BUDGET);
@@ -102,7 +120,8 @@ gemm_tf32_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
 
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t lane = lane_id();
-    const int mtile = blockIdx.x, ntile = blockIdx.y, split = blockIdx.z;
+    const int local = (int)blockIdx.x - grp.cta_start[gi];
+    const int mtile = local % p.mtiles, ntile = (local / p.mtiles) % p.ntiles, split = local / (p.mtiles * p.ntiles);
     const int kb0 = split * p.kb_per_split;
     const int kb1 = min(kb0 + p.kb_per_split, p.kb_total);
     const int nkb = max(kb1 - kb0, 0);
@@ -290,29 +309,34 @@ gemm_tf32_kernel(const __grid_constant__ GemmMaps maps, const GemmParams p) {
     if (warp == 2) tmem_dealloc(tmem_base, 256);
 }
 
-// out[r, c] = sum_s part[s][r][c]  (fixed order), rows x cols with source pitch ldp and destination pitch ldc
-__global__ void gemm_reduce_splits_kernel(const float* __restrict__ part, float* __restrict__ out, int splits,
-                                          long long stride, int rows, int cols, int ldp, int ldc) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows * cols) return;
-    const int r = i / cols, c = i % cols;
+// out[r, c] = sum_s part[s][r][c]  (fixed order) for every split problem of the group
+__global__ void __launch_bounds__(256)
+gemm_reduce_splits_kernel(const __grid_constant__ GemmGroup grp) {
+    int gi = 0;
+    while (gi + 1 < grp.nprob && (int)blockIdx.x >= grp.red_start[gi + 1]) ++gi;
+    const GemmParams& p = grp.prm[gi];
+    const int i = ((int)blockIdx.x - grp.red_start[gi]) * blockDim.x + threadIdx.x;
+    if (p.splits <= 1 || i >= p.M * p.N) return;
+    const int r = i / p.N, c = i % p.N;
     float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += part[(size_t)s * stride + (size_t)r * ldp + c];
-    out[(size_t)r * ldc + c] = acc;
+    for (int s = 0; s < p.splits; ++s) acc += p.C[(size_t)s * p.part_stride + (size_t)r * p.ldc + c];
+    p.out[(size_t)r * p.ld_out + c] = acc;
 }
 
 // Pre-split of the dense weights (once per step, after Adam): for every tensor t of the table
 //   hi[dst_off + r*dst_pitch + c] = tf32(w) (round to nearest),   lo[...] = tf32(w - hi)   (pad columns are zero).
-// table rows: {src_off, rows, cols, dst_off, dst_pitch}
+// table rows: {src_off, rows, cols, dst_off, dst_pitch, src2_off, src2_row0}: a second tensor (same column count) is
+// added to rows >= src2_row0 when src2_off >= 0.
 __global__ void __launch_bounds__(256)
 prep_weights_kernel(const float* __restrict__ theta, const int32_t* __restrict__ table, float* __restrict__ hi,
                     float* __restrict__ lo) {
-    const int32_t* t = table + blockIdx.y * 5;
-    const int src = t[0], rows = t[1], cols = t[2], dst = t[3], pitch = t[4];
+    const int32_t* t = table + blockIdx.y * 7;
+    const int src = t[0], rows = t[1], cols = t[2], dst = t[3], pitch = t[4], src2 = t[5], row0 = t[6];
     const int n = rows * pitch;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int r = i / pitch, c = i % pitch;
-        const float w = c < cols ? theta[src + r * cols + c] : 0.f;
+        float w = c < cols ? theta[src + r * cols + c] : 0.f;
+        if (src2 >= 0 && r >= row0 && c < cols) w += theta[src2 + (r - row0) * cols + c];
         const float h = tf32_rn(w);
         hi[dst + i] = h;
         lo[dst + i] = tf32_rn(w - h);
@@ -366,20 +390,22 @@ extern "C" int tcar_gemm_tf32_splits(int M, int N, int k_total, int want) {
     return s;
 }
 
-extern "C" int tcar_gemm_tf32(const tcar_gemm_seg* segs, int nseg, int M, int N, const float* bias, int act, float* C,
-                              int ldc, int accumulate, int precise, int splits, float* part, void* stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (nseg < 1 || nseg > G_MAX_SEG || M < 1 || N < 1 || !C) return TCAR_ERR_ARG;
-    if (splits < 1 || (splits > 1 && (!part || bias || act || precise))) return TCAR_ERR_ARG;
-    GemmParams p = {};
-    GemmMaps maps;
+static int setup_problem(const tcar_gemm_problem& q, GemmParams& p, GemmMaps& maps, int group_ctas_hint) {
+    const int M = q.M, N = q.N, nseg = q.nseg, precise = q.precise;
+    int splits = q.splits;
+    if (nseg < 1 || nseg > G_MAX_SEG || M < 1 || N < 1 || !q.C) return TCAR_ERR_ARG;
+    if (splits < 1 || (splits > 1 && (!q.part || q.bias || q.act || precise || q.accumulate))) return TCAR_ERR_ARG;
+    p = GemmParams{};
     p.nseg = nseg;
     p.M = M;
     p.N = N;
     p.precise = precise ? 1 : 0;
-    // UMMA N: one tile when N <= 256, else 256-wide tiles; narrow outputs use the smallest legal tile
+    // UMMA N: one tile when N <= 256, else 256-wide tiles; narrow outputs use the smallest legal tile.  Small
+    // problems are bound by the per-SM operand ingest (~64 B/clk), not by the tensor pipe: narrower tiles spread
+    // them over more SMs.
     p.bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
-    if (precise && p.bn == 256 && M <= 1024) p.bn = 128;     // more CTAs for the small-batch projections
+    const int mt0 = (M + G_BM - 1) / G_BM;
+    while (p.bn > 64 && group_ctas_hint + mt0 * ((N + p.bn - 1) / p.bn) * splits < 74) p.bn >>= 1;
     p.b_tile_bytes = p.bn * G_BK * 4;
     p.stage_bytes = (G_A_TILE + p.b_tile_bytes) * (precise ? 2 : 1);
     p.stages = G_SMEM_BUDGET / p.stage_bytes;
@@ -387,13 +413,12 @@ extern "C" int tcar_gemm_tf32(const tcar_gemm_seg* segs, int nseg, int M, int N,
     if (p.stages < 2) return TCAR_ERR_ARG;
     int kb_total = 0;
     for (int s = 0; s < nseg; ++s) {
-        const tcar_gemm_seg& g = segs[s];
-        if (!g.a || !g.b || g.k < 1 || (precise && !g.b_lo)) return TCAR_ERR_ARG;
+        const tcar_gemm_seg& g = q.segs[s];
+        if (!g.a || !g.b || g.k < 1 || (precise && !g.b_lo) || g.a_koff < 0) return TCAR_ERR_ARG;
         p.seg[s].nkb = (g.k + G_BK - 1) / G_BK;
         p.seg[s].a_mn = g.a_mn_major ? 1 : 0;
         p.seg[s].b_mn = g.b_mn_major ? 1 : 0;
         p.seg[s].a_koff = g.a_koff;
-        if (g.a_koff < 0) return TCAR_ERR_ARG;
         kb_total += p.seg[s].nkb;
         int rc;
         // the tensor extent along K ends at a_koff + k, so the last K block is zero-filled beyond it
@@ -420,44 +445,87 @@ extern "C" int tcar_gemm_tf32(const tcar_gemm_seg* segs, int nseg, int M, int N,
     if (splits > kb_total) splits = kb_total;
     p.splits = splits;
     p.kb_per_split = (kb_total + splits - 1) / splits;
-    p.bias = bias;
-    p.act = act;
-    p.accumulate = accumulate ? 1 : 0;
-    const int mtiles = (M + G_BM - 1) / G_BM, ntiles = (N + p.bn - 1) / p.bn;
+    p.bias = q.bias;
+    p.act = q.act;
+    p.accumulate = q.accumulate ? 1 : 0;
+    p.mtiles = mt0;
+    p.ntiles = (N + p.bn - 1) / p.bn;
+    p.out = q.C;
+    p.ld_out = q.ldc;
     if (splits > 1) {
-        p.C = part;
-        p.ldc = ntiles * p.bn;
-        p.part_stride = (long long)mtiles * G_BM * p.ldc;
-        p.accumulate = 0;
+        p.C = q.part;
+        p.ldc = p.ntiles * p.bn;
+        p.part_stride = (long long)p.mtiles * G_BM * p.ldc;
     } else {
-        p.C = C;
-        p.ldc = ldc;
+        p.C = q.C;
+        p.ldc = q.ldc;
         p.part_stride = 0;
+    }
+    return 0;
+}
+
+extern "C" int tcar_gemm_tf32_group(const tcar_gemm_problem* probs, int nprob, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (nprob < 1 || nprob > G_MAX_PROB || !probs) return TCAR_ERR_ARG;
+    static thread_local GemmGroup grp;      // ~11 KB of kernel parameters, rebuilt per call
+    grp.nprob = nprob;
+    int ctas = 0, red = 0;
+    bool any_split = false;
+    for (int g = 0; g < nprob; ++g) {
+        int rc = setup_problem(probs[g], grp.prm[g], grp.maps[g], ctas);
+        if (rc) return rc;
+        grp.cta_start[g] = ctas;
+        grp.red_start[g] = red;
+        ctas += grp.prm[g].mtiles * grp.prm[g].ntiles * grp.prm[g].splits;
+        if (grp.prm[g].splits > 1) {
+            red += (probs[g].M * probs[g].N + 255) / 256;
+            any_split = true;
+        }
+    }
+    for (int g = nprob; g <= G_MAX_PROB; ++g) {
+        grp.cta_start[g] = ctas;
+        grp.red_start[g] = red;
     }
     cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
     if (e != cudaSuccess) return (int)e;
-    gemm_tf32_kernel<<<dim3(mtiles, ntiles, splits), G_THREADS, G_SMEM, stream>>>(maps, p);
+    gemm_tf32_kernel<<<ctas, G_THREADS, G_SMEM, stream>>>(grp);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
-    if (splits > 1) {
-        if (accumulate) return TCAR_ERR_ARG;
-        const int total = M * N;
-        gemm_reduce_splits_kernel<<<(total + 255) / 256, 256, 0, stream>>>(part, C, splits, p.part_stride, M, N, p.ldc,
-                                                                           ldc);
+    if (any_split) {
+        gemm_reduce_splits_kernel<<<red, 256, 0, stream>>>(grp);
         e = cudaGetLastError();
     }
     return (int)e;
 }
 
+extern "C" int tcar_gemm_tf32(const tcar_gemm_seg* segs, int nseg, int M, int N, const float* bias, int act, float* C,
+                              int ldc, int accumulate, int precise, int splits, float* part, void* stream_) {
+    if (nseg < 1 || nseg > G_MAX_SEG || !segs) return TCAR_ERR_ARG;
+    tcar_gemm_problem q = {};
+    for (int s = 0; s < nseg; ++s) q.segs[s] = segs[s];
+    q.nseg = nseg;
+    q.M = M;
+    q.N = N;
+    q.bias = bias;
+    q.act = act;
+    q.C = C;
+    q.ldc = ldc;
+    q.accumulate = accumulate;
+    q.precise = precise;
+    q.splits = splits;
+    q.part = part;
+    return tcar_gemm_tf32_group(&q, 1, stream_);
+}
+
 extern "C" long long tcar_gemm_tf32_part_elems(int M, int N, int splits) {
-    const int bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
-    const long long mt = (M + G_BM - 1) / G_BM, nt = (N + bn - 1) / bn;
-    return (long long)splits * mt * G_BM * nt * bn;
+    // upper bound over every tile width the launcher may pick (N rounded up to 256 columns)
+    const long long mt = (M + G_BM - 1) / G_BM, nt = (N + 255) / 256;
+    return (long long)splits * mt * G_BM * nt * 256;
 }
 
 extern "C" int tcar_prep_weights(const float* theta, const int32_t* table, int ntensors, float* hi, float* lo,
                                  void* stream_) {
     if (ntensors < 1) return TCAR_ERR_ARG;
-    prep_weights_kernel<<<dim3(16, ntensors), 256, 0, static_cast<cudaStream_t>(stream_)>>>(theta, table, hi, lo);
+    prep_weights_kernel<<<dim3(74, ntensors), 256, 0, static_cast<cudaStream_t>(stream_)>>>(theta, table, hi, lo);
     return (int)cudaGetLastError();
 }

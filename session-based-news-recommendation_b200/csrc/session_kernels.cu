@@ -121,10 +121,10 @@ pool_fwd_kernel(const float* __restrict__ X, const float* __restrict__ P, float*
         const size_t m = (size_t)b * T + t;
         float e1 = 0.f, e2 = 0.f, et = 0.f;
         for (int c = lane; c < H; c += 32) {
-            const float s1 = 1.f / (1.f + expf(-U1[m * H + c]));
-            const float s2 = 1.f / (1.f + expf(-U2[m * H + c]));
-            U1[m * H + c] = s1;
-            U2[m * H + c] = s2;
+            const float s1 = 1.f / (1.f + expf(-U1[m * HP + c]));
+            const float s2 = 1.f / (1.f + expf(-U2[m * HP + c]));
+            U1[m * HP + c] = s1;
+            U2[m * HP + c] = s2;
             e1 = fmaf(s1, w_r[c], e1);
             et = fmaf(s2, w_t[c], et);
         }
@@ -205,10 +205,10 @@ pool_bwd_kernel(const float* __restrict__ X, const float* __restrict__ P, const 
         const float de1 = s_de[0][t], de2 = s_de[1][t], det = s_de[2][t];
         const float a12 = s_a[0][t] + s_a[1][t], at = s_a[2][t];
         for (int c = lane; c < H; c += 32) {
-            const float s1 = S1[m * H + c], s2 = S2[m * H + c];
-            dU1[m * H + c] = de1 * w_r[c] * s1 * (1.f - s1);
-            dU2[m * H + c] = det * w_t[c] * s2 * (1.f - s2);
-            dXi[m * H + c] = fmaf(a12, s_dp[c], de2 * s_q[c]);
+            const float s1 = S1[m * HP + c], s2 = S2[m * HP + c];
+            dU1[m * HP + c] = de1 * w_r[c] * s1 * (1.f - s1);
+            dU2[m * HP + c] = det * w_t[c] * s2 * (1.f - s2);
+            dXi[m * HP + c] = fmaf(a12, s_dp[c], de2 * s_q[c]);
         }
         for (int c = lane; c < PW; c += 32) dP[m * PW + c] = at * s_dpt[c];
     }
@@ -325,17 +325,17 @@ ce_finish_kernel(const float* __restrict__ part, float* __restrict__ sumexp, flo
 }
 
 // ------------------------------------------------------------------------------------------------ (5a') act bwd
-// 32 columns per CTA (lane = column), 8 warps stride over the rows; column sums combined in warp order.
-__global__ void __launch_bounds__(256)
+// 32 columns per CTA (lane = column), 32 warps stride over the rows; column sums combined in warp order.
+__global__ void __launch_bounds__(1024)
 act_bwd_colsum_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dz,
-                      float* __restrict__ gb, int rows, int cols, int mode) {
-    __shared__ float s[8][32];
+                      float* __restrict__ gb, int rows, int cols, int ld, int mode) {
+    __shared__ float s[32][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + lane;
     float acc = 0.f;
     if (c < cols) {
-        for (int r = w; r < rows; r += 8) {
-            const size_t i = (size_t)r * cols + c;
+        for (int r = w; r < rows; r += 32) {
+            const size_t i = (size_t)r * ld + c;
             const float yv = y[i];
             const float d = dy[i] * (mode == 0 ? (1.f - yv * yv) : (yv > 0.f ? 1.f : 0.f));
             dz[i] = d;
@@ -346,7 +346,7 @@ act_bwd_colsum_kernel(const float* __restrict__ dy, const float* __restrict__ y,
     __syncthreads();
     if (w == 0 && c < cols) {
         float t = 0.f;
-        for (int i = 0; i < 8; ++i) t += s[i][lane];
+        for (int i = 0; i < 32; ++i) t += s[i][lane];
         gb[c] = t;
     }
 }
@@ -451,8 +451,19 @@ small_table_grads_kernel(const int32_t* __restrict__ idx, const int32_t* __restr
         x = pos + (size_t)row * H;
         g = g_pos + (size_t)row * H;
         const int c = threadIdx.x & 255, grp = threadIdx.x >> 8;  // 4 groups
-        if (row < T && c < H)
-            for (int b = grp; b < B; b += 4) acc += dXi[((size_t)b * T + row) * H + c];
+        if (row < T && c < H) {
+            // 4 groups x 4 independent partial sums, combined in a fixed order
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            int b = grp;
+            for (; b + 12 < B; b += 16) {
+                a0 += dXi[((size_t)b * T + row) * HP + c];
+                a1 += dXi[((size_t)(b + 4) * T + row) * HP + c];
+                a2 += dXi[((size_t)(b + 8) * T + row) * HP + c];
+                a3 += dXi[((size_t)(b + 12) * T + row) * HP + c];
+            }
+            for (; b < B; b += 4) a0 += dXi[((size_t)b * T + row) * HP + c];
+            acc = (a0 + a1) + (a2 + a3);
+        }
         s_acc[threadIdx.x] = acc;
         __syncthreads();
         if (threadIdx.x < 256) s_g[threadIdx.x] = s_acc[threadIdx.x] + s_acc[256 + threadIdx.x] + s_acc[512 + threadIdx.x] + s_acc[768 + threadIdx.x];
@@ -469,8 +480,20 @@ small_table_grads_kernel(const int32_t* __restrict__ idx, const int32_t* __restr
             x = tabs[k] + (size_t)rr * TH;
             g = gs[k] + (size_t)rr * TH;
             const int32_t* ik = idx + (size_t)(k + 1) * M;
-            for (int m = grp; m < M; m += 16)
-                if (ik[m] == rr) acc += dP[(size_t)m * PW + k * TH + d];
+            {
+                // index words are fetched 8 at a time so the (rare) matching rows do not serialise the scan
+                int m = grp;
+                for (; m + 112 < M; m += 128) {
+                    int id[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) id[u] = ik[m + 16 * u];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (id[u] == rr) acc += dP[(size_t)(m + 16 * u) * PW + k * TH + d];
+                }
+                for (; m < M; m += 16)
+                    if (ik[m] == rr) acc += dP[(size_t)m * PW + k * TH + d];
+            }
             if (k == 2)
                 for (int b = grp; b < B; b += 16)
                     if (ctx[b] == rr) acc += dCT[(size_t)b * 2 * TH + d];
@@ -483,7 +506,16 @@ small_table_grads_kernel(const int32_t* __restrict__ idx, const int32_t* __restr
             x = dur + (size_t)rr * TH;
             g = g_dur + (size_t)rr * TH;
             const int32_t* ik = idx + (size_t)6 * M;
-            for (int m = grp; m < M; m += 16)
+            int m = grp;
+            for (; m + 112 < M; m += 128) {
+                int id[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) id[u] = ik[m + 16 * u];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (id[u] == rr) acc += dD[(size_t)(m + 16 * u) * TH + d];
+            }
+            for (; m < M; m += 16)
                 if (ik[m] == rr) acc += dD[(size_t)m * TH + d];
         }
         s_acc[threadIdx.x] = acc;
@@ -543,7 +575,7 @@ scatter_accum_kernel(const int32_t* __restrict__ seq, const int32_t* __restrict_
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = (j < 4) ? lane * 4 + j : 128 + lane * 4 + (j - 4);
-            dy[j] = c < H ? dXi[(size_t)e * H + c] : 0.f;
+            dy[j] = c < H ? dXi[(size_t)e * HP + c] : 0.f;
             sq = fmaf(xv[j], xv[j], sq);
             xdy = fmaf(xv[j], dy[j], xdy);
         }
@@ -656,10 +688,10 @@ extern "C" int tcar_ce_finish(const float* rowsum_part, float* sumexp, float* ce
     return LAUNCH_RC();
 }
 
-extern "C" int tcar_act_bwd_colsum(const float* dy, const float* y, float* dz, float* gb, int rows, int cols, int mode,
-                                   void* stream) {
-    if (rows < 1 || cols < 1 || (mode != 0 && mode != 1)) return TCAR_ERR_ARG;
-    act_bwd_colsum_kernel<<<(cols + 31) / 32, 256, 0, STREAM>>>(dy, y, dz, gb, rows, cols, mode);
+extern "C" int tcar_act_bwd_colsum(const float* dy, const float* y, float* dz, float* gb, int rows, int cols, int ld,
+                                   int mode, void* stream) {
+    if (rows < 1 || cols < 1 || ld < cols || (mode != 0 && mode != 1)) return TCAR_ERR_ARG;
+    act_bwd_colsum_kernel<<<(cols + 31) / 32, 1024, 0, STREAM>>>(dy, y, dz, gb, rows, cols, ld, mode);
     return LAUNCH_RC();
 }
 

@@ -82,10 +82,15 @@ class Seq2SeqAttNN:
         Mm = Bm * Tm
         f = lambda *s: torch.zeros(*s, device=dev)
         self.X, self.P, self.D, self.CT = f(Mm, XW), f(Mm, PW), f(Mm, TH), f(Bm, 2 * TH)
-        self.U1, self.U2, self.dU1, self.dU2 = f(Mm, H), f(Mm, H), f(Mm, H), f(Mm, H)
-        self.dXi, self.dP, self.dD = f(Mm, H), f(Mm, PW), f(Mm, TH)
+        HP = nv.HP
+        self.U1, self.U2, self.dU1, self.dU2 = f(Mm, HP), f(Mm, HP), f(Mm, HP), f(Mm, HP)   # 256-float pitch (TMA)
+        self.dXi, self.dP, self.dD = f(Mm, HP), f(Mm, PW), f(Mm, TH)
         self.alpha, self.de = f(3, Mm), f(3, Mm)
-        self.h1, self.q, self.dq = f(Bm, H), f(Bm, XW), f(Bm, XW)
+        self.h1, self.dh1, self.q, self.dq = f(Bm, HP), f(Bm, HP), f(Bm, XW), f(Bm, XW)
+        self.dpooled, self.dpooled_t = f(Bm, XW), f(Bm, PW)
+        self.gW_tmp = f(XW, H)
+        self.gemm_part = f(int(nv.lib().tcar_gemm_tf32_part_elems(XW, XW, 8)) * 2)     # split-reduction scratch
+        self._part_off = 0
         self.pooled, self.pooled_t = f(Bm, XW), f(Bm, PW)
         self.a_ic, self.a_pt = f(Bm, XW), f(Bm, PW)
         self.d_a_ic, self.d_a_pt, self.dA_neg = f(Bm, XW), f(Bm, PW), f(Bm, XW)
@@ -103,6 +108,17 @@ class Seq2SeqAttNN:
         self.top_ids = torch.zeros(Bm, TOPK, device=dev, dtype=torch.int32)
         self.top_scores = f(Bm, TOPK)
         self.n_greater = torch.zeros(Bm, device=dev, dtype=torch.int32)
+
+    def _part(self, M, N, splits):
+        """Carve a disjoint split-reduction scratch for one problem of a GEMM group (None when not split)."""
+        if splits <= 1:
+            return None
+        n = int(nv.lib().tcar_gemm_tf32_part_elems(M, N, splits))
+        if self._part_off + n > self.gemm_part.numel():
+            raise ValueError("GEMM split scratch exhausted")
+        out = self.gemm_part[self._part_off:]
+        self._part_off += n
+        return out
 
     def _score_buffers(self, n_pad, train):
         """E / partial-sum / chunk-max buffers sized for a catalog (shard) of n_pad items; allocated once."""
@@ -141,28 +157,25 @@ class Seq2SeqAttNN:
         nv.counted_call("tcar_gather_fwd", 1, p(bt.idx), p(bt.ctx), p(ps.item), p(ps.content), p(w["pos"]),
                         p(w["month"]), p(w["day"]), p(w["week"]), p(w["hour"]), p(w["minute"]), p(w["dur"]),
                         p(self.X), p(self.P), p(self.D), p(self.CT), B, T)
-        X, P, D, CT = self.X[:M], self.P[:M], self.D[:M], self.CT[:B]
-        Xc = X[:, H:]
-        U1, U2 = self.U1[:M], self.U2[:M]
-        # linear_3d projections (modules.py:126-131, :94-96): plain library GEMMs (cuBLAS, fp32)
-        torch.mm(X, w["W_in"], out=U1)
-        U1.addmm_(Xc, w["W_c"])
-        U1.addmm_(D, w["W_i"])
-        torch.mm(P, w["W1"], out=U2)
-        U2.addmm_(Xc, w["W2"])
-        # query path (modules.py:138-139)
-        h1, q = self.h1[:B], self.q[:B]
-        torch.addmm(w["bq1"], CT, w["Wq1"], out=h1)
-        h1.relu_()
-        torch.addmm(w["bq2"], h1, w["Wq2"], out=q)
-        q.tanh_()
+        # linear_3d / linear_2d projections (modules.py:126-131, :94-96, :138-139; model_combine.py:119,127) on the
+        # tensor cores in 3xTF32 (fp32-class accuracy); bias + activation fused into the GEMM epilogue
+        wh, wl, pr = ps.wh, ps.wl, nv.problem
+        nv.gemm_group([
+            pr([(self.X, XW, 0, wh["W_in1"], wl["W_in1"], 256, 1, XW), (self.D, TH, 0, wh["W_i"], wl["W_i"], 256, 1, TH)],
+               M, H, self.U1, nv.HP, precise=True),
+            pr([(self.P, PW, 0, wh["W1"], wl["W1"], 256, 1, PW), (self.X, XW, 0, wh["W2x"], wl["W2x"], 256, 1, XW)],
+               M, H, self.U2, nv.HP, precise=True),
+            pr([(self.CT, 2 * TH, 0, wh["Wq1"], wl["Wq1"], 256, 1, 2 * TH)], B, H, self.h1, nv.HP, bias=w["bq1"], act=1,
+               precise=True)])
+        nv.gemm([(self.h1, nv.HP, 0, wh["Wq2"], wl["Wq2"], 512, 1, H)], B, XW, self.q, XW, bias=w["bq2"], act=2,
+                precise=True)
         nv.counted_call("tcar_pool_fwd", 1, p(self.X), p(self.P), p(self.U1), p(self.U2), p(self.q), p(w["w_r"]),
                         p(w["w_t"]), p(self.alpha), p(self.pooled), p(self.pooled_t), B, T)
-        a_ic, a_pt = self.a_ic[:B], self.a_pt[:B]
-        torch.addmm(w["b_a"], self.pooled[:B], w["W_a"], out=a_ic)
-        a_ic.tanh_()
-        torch.addmm(w["b_p"], self.pooled_t[:B], w["W_p"], out=a_pt)
-        a_pt.tanh_()
+        nv.gemm_group([
+            pr([(self.pooled, XW, 0, wh["W_a"], wl["W_a"], 512, 1, XW)], B, XW, self.a_ic, XW, bias=w["b_a"], act=2,
+               precise=True),
+            pr([(self.pooled_t, PW, 0, wh["W_p"], wl["W_p"], 320, 1, PW)], B, PW, self.a_pt, PW, bias=w["b_p"], act=2,
+               precise=True)])
         nv.counted_call("tcar_clip_time_tables", 1, p(w["month"]), p(w["day"]), p(w["week"]), p(w["hour"]),
                         p(w["minute"]), p(ps.ct_tab), p(ps.ct_scale))
         nv.counted_call("tcar_build_query", 1, p(self.a_ic), p(self.a_pt), p(ps.ct_tab), p(ps.item), p(ps.content),
@@ -191,12 +204,6 @@ class Seq2SeqAttNN:
 
     def backward(self, bt):
         """Gradients of sum_b loss_b wrt all 23 tensors (model_combine.py:156) into ps.item_g / ps.theta_g."""
-        try:
-            self._backward(bt)
-        finally:
-            torch.backends.cuda.matmul.allow_tf32 = False
-
-    def _backward(self, bt):
         ps, w, g, p, B, T = self.ps, self.ps.w, self.ps.g, nv.ptr, bt.B, bt.T
         M = B * T
         ws = self._score_buffers(ps.n_pad, True)
@@ -205,44 +212,55 @@ class Seq2SeqAttNN:
                         p(ps.ct_tab), p(ps.item), p(ps.content), p(ps.mwdhm), p(bt.label), p(self.d_a_ic),
                         p(self.d_a_pt), p(self.dTq), p(self.Qs), B)
         nv.counted_call("tcar_score_bwd_i", 1, p(ws["E"]), p(self.Qs), p(ps.item_g), B, ps.N, ps.n_pad)
-        # linear_2d tails (model_combine.py:119,127)
-        # the session-side weight / data gradient GEMMs run on the tensor cores in TF32 (cuBLAS, fp32 accumulate):
-        # gradients carry a 2e-2 norm-wise tolerance, dominated by the bf16 scoring GEMMs anyway.  The forward
-        # projections stay fp32 so that the exact re-scoring of the top-20 keeps its 2e-5 margin against the oracle.
-        torch.backends.cuda.matmul.allow_tf32 = True
-        dz_a, dz_p = self.d_a_ic[:B], self.d_a_pt[:B]
-        nv.counted_call("tcar_act_bwd_colsum", 1, p(dz_a), p(self.a_ic), p(dz_a), p(g["b_a"]), B, XW, 0)
-        nv.counted_call("tcar_act_bwd_colsum", 1, p(dz_p), p(self.a_pt), p(dz_p), p(g["b_p"]), B, PW, 0)
-        torch.mm(self.pooled[:B].t(), dz_a, out=g["W_a"])
-        torch.mm(self.pooled_t[:B].t(), dz_p, out=g["W_p"])
-        dpooled = torch.mm(dz_a, w["W_a"].t())
-        dpooled_t = torch.mm(dz_p, w["W_p"].t())
+        # ---- session-side backward: weight / data gradients on the tensor cores in single-pass TF32 (gradients carry
+        # a 2e-2 norm-wise tolerance, dominated by the bf16 scoring GEMMs); operands are consumed in place, K-major or
+        # MN-major as they lie, so no transposes are materialised.
+        wh, pr, HPp = ps.wh, nv.problem, nv.HP
+        self._part_off = 0
+        dz_a, dz_p = self.d_a_ic, self.d_a_pt
+        nv.counted_call("tcar_act_bwd_colsum", 1, p(dz_a), p(self.a_ic), p(dz_a), p(g["b_a"]), B, XW, XW, 0)
+        nv.counted_call("tcar_act_bwd_colsum", 1, p(dz_p), p(self.a_pt), p(dz_p), p(g["b_p"]), B, PW, PW, 0)
+        ksp = 4 if B > 128 else 1
+        nv.gemm_group([
+            pr([(self.pooled, XW, 1, dz_a, None, XW, 1, B)], XW, XW, g["W_a"], XW, splits=ksp, part=self._part(XW, XW, ksp)),
+            pr([(self.pooled_t, PW, 1, dz_p, None, PW, 1, B)], PW, PW, g["W_p"], PW, splits=ksp, part=self._part(PW, PW, ksp)),
+            pr([(dz_a, XW, 0, wh["W_a"], None, 512, 0, XW)], B, XW, self.dpooled, XW),
+            pr([(dz_p, PW, 0, wh["W_p"], None, 320, 0, PW)], B, PW, self.dpooled_t, PW)])
         nv.counted_call("tcar_pool_bwd", 1, p(self.X), p(self.P), p(self.U1), p(self.U2), p(self.q), p(w["w_r"]),
-                        p(w["w_t"]), p(self.alpha), p(dpooled), p(dpooled_t), p(self.dU1), p(self.dU2), p(self.dXi),
-                        p(self.dP), p(self.dq), p(self.de), B, T)
-        X, P, D, CT = self.X[:M], self.P[:M], self.D[:M], self.CT[:B]
-        Xc = X[:, H:]
-        S1, S2, dU1, dU2 = self.U1[:M], self.U2[:M], self.dU1[:M], self.dU2[:M]
+                        p(w["w_t"]), p(self.alpha), p(self.dpooled), p(self.dpooled_t), p(self.dU1), p(self.dU2),
+                        p(self.dXi), p(self.dP), p(self.dq), p(self.de), B, T)
+        S1, S2 = self.U1[:M, :H], self.U2[:M, :H]
         de = self.de.view(-1)                      # kernel layout: [3][B*T] with the ACTUAL B*T as stride
         torch.mv(S1.t(), de[:M], out=g["w_r"].view(-1))
         torch.mv(S2.t(), de[2 * M: 3 * M], out=g["w_t"].view(-1))
-        torch.mm(X.t(), dU1, out=g["W_in"])
-        torch.mm(Xc.t(), dU1, out=g["W_c"])
-        torch.mm(D.t(), dU1, out=g["W_i"])
-        torch.mm(P.t(), dU2, out=g["W1"])
-        torch.mm(Xc.t(), dU2, out=g["W2"])
-        self.dXi[:M].addmm_(dU1, w["W_in"][:H].t())
-        torch.mm(dU1, w["W_i"].t(), out=self.dD[:M])
-        self.dP[:M].addmm_(dU2, w["W1"].t())
+        # every gradient that consumes dU1 / dU2, one launch: four weight gradients (reduction over the B*T clicks
+        # split across CTAs) and three data gradients
+        msp = max(1, min(8, M // 512))
+        self._part_off = 0
+        nv.gemm_group([
+            pr([(self.X, XW, 1, self.dU1, None, HPp, 1, M)], XW, H, g["W_in"], H, splits=msp, part=self._part(XW, H, msp)),
+            pr([(self.D, TH, 1, self.dU1, None, HPp, 1, M)], TH, H, g["W_i"], H, splits=msp, part=self._part(TH, H, msp)),
+            pr([(self.P, PW, 1, self.dU2, None, HPp, 1, M)], PW, H, g["W1"], H, splits=msp, part=self._part(PW, H, msp)),
+            pr([(self.X, XW, 1, self.dU2, None, HPp, 1, M)], XW, H, self.gW_tmp, H, splits=msp,
+               part=self._part(XW, H, msp)),
+            pr([(self.dU1, HPp, 0, wh["W_in1"], None, 256, 0, H)], M, H, self.dXi, HPp, accumulate=True),
+            pr([(self.dU1, HPp, 0, wh["W_i"], None, 256, 0, H)], M, TH, self.dD, TH),
+            pr([(self.dU2, HPp, 0, wh["W1"], None, 256, 0, H)], M, PW, self.dP, PW, accumulate=True)])
+        g["W_c"].copy_(g["W_in"][H:])              # Xc^T dU1 is the bottom half of X^T dU1
+        g["W2"].copy_(self.gW_tmp[H:])             # Xc^T dU2 likewise
         # query path backward (modules.py:138-139)
-        q, h1 = self.q[:B], self.h1[:B]
-        dzq = self.dq[:B]
-        nv.counted_call("tcar_act_bwd_colsum", 1, p(dzq), p(self.q), p(dzq), p(g["bq2"]), B, XW, 0)
-        torch.mm(h1.t(), dzq, out=g["Wq2"])
-        dh1 = torch.mm(dzq, w["Wq2"].t())
-        nv.counted_call("tcar_act_bwd_colsum", 1, p(dh1), p(self.h1), p(dh1), p(g["bq1"]), B, H, 1)
-        torch.mm(CT.t(), dh1, out=g["Wq1"])
-        torch.mm(dh1, w["Wq1"].t(), out=self.dCT[:B])
+        dzq = self.dq
+        nv.counted_call("tcar_act_bwd_colsum", 1, p(dzq), p(self.q), p(dzq), p(g["bq2"]), B, XW, XW, 0)
+        self._part_off = 0
+        nv.gemm_group([
+            pr([(self.h1, HPp, 1, dzq, None, XW, 1, B)], H, XW, g["Wq2"], XW, splits=ksp, part=self._part(H, XW, ksp)),
+            pr([(dzq, XW, 0, wh["Wq2"], None, 512, 0, XW)], B, H, self.dh1, HPp)])
+        nv.counted_call("tcar_act_bwd_colsum", 1, p(self.dh1), p(self.h1), p(self.dh1), p(g["bq1"]), B, H, HPp, 1)
+        self._part_off = 0
+        nv.gemm_group([
+            pr([(self.CT, 2 * TH, 1, self.dh1, None, HPp, 1, B)], 2 * TH, H, g["Wq1"], H, splits=ksp,
+               part=self._part(2 * TH, H, ksp)),
+            pr([(self.dh1, HPp, 0, wh["Wq1"], None, 256, 0, H)], B, 2 * TH, self.dCT, 2 * TH)])
         nv.counted_call("tcar_small_table_grads", 1, p(bt.idx), p(bt.ctx), p(self.dXi), p(self.dP), p(self.dD),
                         p(self.dCT), p(self.dTq), p(self.a_pt), p(w["pos"]), p(w["month"]), p(w["day"]),
                         p(w["week"]), p(w["hour"]), p(w["minute"]), p(w["dur"]), p(g["pos"]), p(g["month"]),
@@ -270,6 +288,7 @@ class Seq2SeqAttNN:
                         p(ps.sqnorm_small), len(SMALL), p(ps.step), self.lr, self.max_grad_f)
         nv.counted_call("tcar_adam_item", 1, p(ps.item), p(ps.item_m), p(ps.item_v), p(ps.item_g), p(ps.sqnorm_item),
                         p(ps.step), self.lr, self.max_grad_f, p(ps.iext), ps.N)
+        ps.prep_weights()
 
     def train_step(self, bt):
         """One `sess.run([loss, global_step, train_op])` (model_combine.py:231-234). Returns loss [B] (device)."""

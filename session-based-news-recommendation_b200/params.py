@@ -25,6 +25,16 @@ SMALL = [
 ]
 PARAM_ORDER = ["item"] + [n for n, _ in SMALL]
 
+# Pre-split (tf32 hi / lo), padded copies of the dense weights that feed tcar_gemm_tf32:
+#   name -> (source tensor, rows of the padded tensor, first destination row, pitch, folded second source)
+# "W_in1" = W_in + [0; W_c]   (X.W_in + Xc.W_c = X.W_in1: Xc = X[:, 250:] is not 16-byte aligned for TMA)
+# "W2x"   = [0; W2]           (Xc.W2 = X.W2x for the same reason)
+PREPPED = [
+    ("W_in1", "W_in", 2 * H, 0, 256, "W_c"), ("W_i", "W_i", TH, 0, 256, None), ("W1", "W1", 5 * TH, 0, 256, None),
+    ("W2x", "W2", 2 * H, H, 256, None), ("Wq1", "Wq1", 2 * TH, 0, 256, None), ("Wq2", "Wq2", H, 0, 512, None),
+    ("W_a", "W_a", 2 * H, 0, 512, None), ("W_p", "W_p", 5 * TH, 0, 320, None),
+]
+
 
 def _pad4(n):
     return (n + 3) // 4 * 4
@@ -80,6 +90,21 @@ class ParamStore:
         self.g = {n: self._view(self.theta_g, i) for i, (n, _) in enumerate(SMALL)}
         self.ct_tab = torch.zeros(nv.NBINS, TH, device=dev)
         self.ct_scale = torch.zeros(nv.NBINS, device=dev)
+        # pre-split weight copies
+        shapes, index = dict(SMALL), {n: i for i, (n, _) in enumerate(SMALL)}
+        table, off = [], 0
+        self.wp_off, self.wp_pitch = {}, {}
+        for name, src, rows, row0, pitch, fold in PREPPED:
+            srows, scols = shapes[src]
+            self.wp_off[name], self.wp_pitch[name] = off, pitch
+            table.append([self.seg_start[index[src]], srows, scols, off + row0 * pitch, pitch,
+                          self.seg_start[index[fold]] if fold else -1, srows - shapes[fold][0] if fold else 0])
+            off += rows * pitch
+        self.wp_table = torch.tensor(table, dtype=torch.int32, device=dev)
+        self.wp_hi = torch.zeros(off, device=dev)
+        self.wp_lo = torch.zeros(off, device=dev)
+        self.wh = {n: self.wp_hi[self.wp_off[n]:] for n, *_ in PREPPED}
+        self.wl = {n: self.wp_lo[self.wp_off[n]:] for n, *_ in PREPPED}
 
     def _view(self, flat, i):
         s, l = self.seg_start[i], self.seg_len[i]
@@ -115,6 +140,7 @@ class ParamStore:
             t.zero_()
         self.step.zero_()
         self.rebuild_iext()
+        self.prep_weights()
 
     def export(self):
         out = {"item": self.item[:, :H].detach().cpu().clone()}
@@ -127,6 +153,11 @@ class ParamStore:
         for n, _ in SMALL:
             out[n] = self.g[n].detach().cpu().clone()
         return out
+
+    def prep_weights(self):
+        """Refresh the tf32 hi/lo copies of the dense weights (after load and after every Adam step)."""
+        nv.counted_call("tcar_prep_weights", 1, nv.ptr(self.theta), nv.ptr(self.wp_table), len(PREPPED),
+                        nv.ptr(self.wp_hi), nv.ptr(self.wp_lo))
 
     def rebuild_iext(self):
         nv.call("tcar_build_iext", nv.ptr(self.item), nv.ptr(self.content), nv.ptr(self.mwdhm), nv.ptr(self.iext),

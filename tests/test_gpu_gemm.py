@@ -107,7 +107,8 @@ def test_data_gradient_kmajor_both_accumulate(native, M, Ko, Ni):
 
 def test_prep_weights_split_is_exact(native):
     theta = _rand(1000 + 64 * 250, seed=14)
-    table = torch.tensor([[0, 10, 100, 0, 128], [1000, 64, 250, 10 * 128, 256]], dtype=torch.int32, device="cuda")
+    table = torch.tensor([[0, 10, 100, 0, 128, -1, 0], [1000, 64, 250, 10 * 128, 256, -1, 0]], dtype=torch.int32,
+                         device="cuda")
     n = 10 * 128 + 64 * 256
     hi, lo = torch.full((n,), float("nan"), device="cuda"), torch.full((n,), float("nan"), device="cuda")
     native.call("tcar_prep_weights", native.ptr(theta), native.ptr(table), 2, native.ptr(hi), native.ptr(lo))
