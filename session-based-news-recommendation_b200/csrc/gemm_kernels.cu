@@ -405,7 +405,10 @@ static int setup_problem(const tcar_gemm_problem& q, GemmParams& p, GemmMaps& ma
     // them over more SMs.
     p.bn = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
     const int mt0 = (M + G_BM - 1) / G_BM;
-    while (p.bn > 64 && group_ctas_hint + mt0 * ((N + p.bn - 1) / p.bn) * splits < 74) p.bn >>= 1;
+    // 3xTF32 streams hi+lo of both operands: 128-wide tiles keep three 64 KB stages in flight instead of two 96 KB ones
+    if (precise && p.bn > 128) p.bn = 128;
+    // (split problems get their parallelism from the split factor: narrowing them would only re-read A more often)
+    while (splits == 1 && p.bn > 64 && group_ctas_hint + mt0 * ((N + p.bn - 1) / p.bn) < 74) p.bn >>= 1;
     p.b_tile_bytes = p.bn * G_BK * 4;
     p.stage_bytes = (G_A_TILE + p.b_tile_bytes) * (precise ? 2 : 1);
     p.stages = G_SMEM_BUDGET / p.stage_bytes;

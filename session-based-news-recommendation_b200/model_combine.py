@@ -89,7 +89,7 @@ class Seq2SeqAttNN:
         self.h1, self.dh1, self.q, self.dq = f(Bm, HP), f(Bm, HP), f(Bm, XW), f(Bm, XW)
         self.dpooled, self.dpooled_t = f(Bm, XW), f(Bm, PW)
         self.gW_tmp = f(XW, H)
-        self.gemm_part = f(int(nv.lib().tcar_gemm_tf32_part_elems(XW, XW, 8)) * 2)     # split-reduction scratch
+        self.gemm_part = f(int(nv.lib().tcar_gemm_tf32_part_elems(XW, H, 16)) * 4)     # split-reduction scratch
         self._part_off = 0
         self.pooled, self.pooled_t = f(Bm, XW), f(Bm, PW)
         self.a_ic, self.a_pt = f(Bm, XW), f(Bm, PW)
@@ -235,7 +235,7 @@ class Seq2SeqAttNN:
         torch.mv(S2.t(), de[2 * M: 3 * M], out=g["w_t"].view(-1))
         # every gradient that consumes dU1 / dU2, one launch: four weight gradients (reduction over the B*T clicks
         # split across CTAs) and three data gradients
-        msp = max(1, min(8, M // 512))
+        msp = max(1, min(16, M // 512))
         self._part_off = 0
         nv.gemm_group([
             pr([(self.X, XW, 1, self.dU1, None, HPp, 1, M)], XW, H, g["W_in"], H, splits=msp, part=self._part(XW, H, msp)),
