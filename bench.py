@@ -35,7 +35,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--items", type=int, default=GLOBO_N)
     ap.add_argument("--batch", type=int, default=512)
-    ap.add_argument("--session_len", type=int, default=20, help="clicks per session (reference --maxlen)")
+    ap.add_argument("--session_len", type=int, default=0,
+                    help="clicks per session; 0 = SURVEY 8d mix: one length per batch drawn from P(T) ~ 0.55^T, "
+                         "T in [1,20] (Globo-like, prefix-augmented sessions are short); 20 = the reference --maxlen")
     ap.add_argument("--neg_num", type=int, default=20)
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_kernels", action="store_true", help="skip the per-kernel roofline pass")
@@ -108,17 +110,30 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_batches(synth, N, B, T, Nn, mwdhm, n, seed0):
+NBATCH = 16
+
+
+def session_lengths(a, n=NBATCH):
+    """One session length per length-bucketed batch (sampler.py:40-49 buckets by exact length)."""
+    import numpy as np
+    if a.session_len > 0:
+        return [a.session_len] * n
+    rs = np.random.RandomState(2020)
+    pr = 0.55 ** np.arange(1, 21)
+    return [int(t) for t in rs.choice(np.arange(1, 21), size=n, p=pr / pr.sum())]
+
+
+def make_batches(synth, N, B, Ts, Nn, mwdhm, seed0):
     import torch
     out = []
-    for i in range(n):
+    for i, T in enumerate(Ts):
         packed = synth.make_index_batch(N, B, T, Nn, mwdhm, seed=seed0 + i)
         out.append(torch.from_numpy(packed).pin_memory() if torch.cuda.is_available() else torch.from_numpy(packed))
     return out
 
 
 # ----------------------------------------------------------------------------------------------------- CPU arms
-def oracle_train_rate(N, B, T, Nn, steps, warmup, content, mwdhm, seed=11):
+def oracle_train_rate(N, B, Ts, Nn, steps, warmup, content, mwdhm, seed=11):
     """Times the CPU oracle's train step (fwd + bwd + clip + TF-Adam, fp32, all host threads) on batches of B
     sessions against the full N-item catalog.  Returns (sessions/s, ms/step, threads)."""
     import numpy as np
@@ -131,11 +146,11 @@ def oracle_train_rate(N, B, T, Nn, steps, warmup, content, mwdhm, seed=11):
     c = torch.from_numpy(content)
     mw = torch.from_numpy(mwdhm.astype(np.int64))
     batches = []
-    for i in range(min(steps + warmup, 4)):
-        packed = synth.make_index_batch(N, B, T, Nn, mwdhm, seed=seed + i)
-        batches.append({k: torch.from_numpy(v) for k, v in synth.unpack(packed, B, T, Nn).items()})
+    for i in range(min(steps, len(Ts))):
+        packed = synth.make_index_batch(N, B, Ts[i], Nn, mwdhm, seed=seed + i)
+        batches.append({k: torch.from_numpy(v) for k, v in synth.unpack(packed, B, Ts[i], Nn).items()})
     for i in range(warmup):
-        O.train_step(p, adam, c, mw, batches[i % len(batches)])
+        O.train_step(p, adam, c, mw, batches[-1 - i % len(batches)])
     t0 = time.perf_counter()
     for i in range(steps):
         O.train_step(p, adam, c, mw, batches[i % len(batches)])
@@ -176,9 +191,10 @@ def run_reference(a):
     from tcar_b200 import synth
     content, mwdhm, _ = synth.make_catalog(a.items)
     Bs = a.cpu_sample_sessions
-    rate, ms, threads = oracle_train_rate(a.items, Bs, a.session_len, a.neg_num, a.steps, a.warmup, content, mwdhm)
-    sample = (f"{a.steps} train steps of {Bs} sessions (T={a.session_len}, Nn={a.neg_num}) against the full "
-              f"{a.items}-item catalog, torch CPU fp32")
+    Ts = session_lengths(a)
+    rate, ms, threads = oracle_train_rate(a.items, Bs, Ts, a.neg_num, a.steps, a.warmup, content, mwdhm)
+    sample = (f"{a.steps} train steps of {Bs} sessions (session lengths {Ts[:min(a.steps, len(Ts))]}, Nn={a.neg_num}) "
+              f"against the full {a.items}-item catalog, torch CPU fp32")
     line = {"impl": "reference", "metric": "TCAR train sessions/sec (Globo shape)", "value": rate,
             "unit": "sessions/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -190,10 +206,14 @@ def run_reference(a):
 
 
 def workload_config(a, world):
+    Ts = session_lengths(a)
+    tdesc = (f"session length {a.session_len} for every batch" if a.session_len > 0 else
+             f"one session length per batch drawn from P(T)~0.55^T on [1,20] (SURVEY 8d; cycle {Ts})")
     return {"workload": f"TCAR train step, Globo shape: {a.items} articles x 250-d content, batch {a.batch} "
-                        f"sessions/GPU, session length {a.session_len}, {a.neg_num} negatives",
+                        f"sessions/GPU, {tdesc}, {a.neg_num} negatives",
             "items": a.items, "batch_per_gpu": a.batch, "global_batch": a.batch * world,
-            "session_len": a.session_len, "neg_num": a.neg_num,
+            "session_len": a.session_len if a.session_len > 0 else "mix", "mean_session_len": sum(Ts) / len(Ts),
+            "neg_num": a.neg_num,
             "parallelism": f"dp{world}" if world > 1 else "single",
             "l2": "inputs larger than L2: bf16 candidate matrix %d MB, E %d MB, item table + grad + Adam moments "
                   "4 x %d MB streamed every step (L2 = 126 MB)" % (a.items * 640 * 2 >> 20, a.items * 1024 >> 20,
@@ -242,7 +262,8 @@ def kernel_rooflines(torch, nv, model, bt, peaks, traffic):
         ("score_bwd_q", "tensor", 2.0 * B * N * K_REF,
          lambda: nv.call("tcar_score_bwd_q", p(ws["E"]), p(ps.iext), p(ws["qpart"]), p(model.dq_raw), B, ps.n_pad)),
         ("score_bwd_i", "tensor", 2.0 * B * N * K_DITEM,
-         lambda: nv.call("tcar_score_bwd_i", p(ws["E"]), p(model.Qs), p(ps.item_g), B, N, ps.n_pad)),
+         lambda: nv.call("tcar_score_bwd_i", p(ws["E"]), p(model.Qs), p(ps.item_g), p(model.sq_partial), B, N,
+                         ps.n_pad)),
         # reads p, m, v, g and writes p, m, v (7 x 250 floats per row) + the bf16 refresh of the scoring operand
         ("adam_item", "hbm", (N + 1) * (7.0 * 250 * 4 + 250 * 2),
          lambda: nv.call("tcar_adam_item", p(ps.item), p(ps.item_m), p(ps.item_v), p(ps.item_g), p(ps.sqnorm_item),
@@ -262,8 +283,8 @@ def kernel_rooflines(torch, nv, model, bt, peaks, traffic):
         # sparse rows: read dXi / a_ic rows + item rows, RMW of the touched g_item rows
         ("scatter_add_rows", "hbm", (M * 3 + (B + B * Nn) * 3) * 250 * 4.0,
          lambda: nv.call("tcar_scatter_add_rows", p(bt.seq), p(bt.label), p(bt.neg), p(model.dXi), p(model.a_ic),
-                         p(model.coef), p(ps.item), p(ps.item_g), p(model.hash_keys), p(model.hash_acc),
-                         model.hash_size, B, T, Nn)),
+                         p(model.coef), p(ps.item), p(ps.item_g), p(model.hash_keys), p(model.hash_cnt),
+                         p(model.hash_acc), p(model.entry_slot), p(model.slot_sq), model.hash_size, B, T, Nn)),
     ]
     out = {}
     for name, bound, work, fn in specs:
@@ -296,7 +317,9 @@ def run_b200(a):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    N, B, T, Nn, K, W = a.items, a.batch, a.session_len, a.neg_num, a.steps, a.warmup
+    N, B, Nn, K, W = a.items, a.batch, a.neg_num, a.steps, a.warmup
+    Ts = session_lengths(a)
+    T = 20                     # worst-case length, used for the per-kernel pass and the `t20` line
     content, mwdhm, category = synth.make_catalog(N)
     np.random.seed(2020)
     margs = dict(publish_time_MWDHM=mwdhm, itemnum=N, category_id=None, item_freq_dict_norm={}, reverse_item=None,
@@ -304,9 +327,11 @@ def run_b200(a):
                  batch_size=B, epoch=1, neg_num=Nn, lr=0.001, max_grad=150, rank=rank, world_size=world)
     model = Seq2SeqAttNN(margs)
     peaks = load_peaks()
-    nbatch = 4
-    host = make_batches(synth, N, B, T, Nn, mwdhm, nbatch, seed0=1000 * (rank + 1))
-    dev = [model.to_device(h, B, T, Nn) for h in host]
+    nbatch = len(Ts)
+    host = make_batches(synth, N, B, Ts, Nn, mwdhm, seed0=1000 * (rank + 1))
+    dev = [model.to_device(h, B, t, Nn) for h, t in zip(host, Ts)]
+    host20 = make_batches(synth, N, B, [T] * 4, Nn, mwdhm, seed0=5000 * (rank + 1))
+    dev20 = [model.to_device(h, B, T, Nn) for h in host20]
     torch.cuda.synchronize()
 
     def barrier():
@@ -342,21 +367,37 @@ def run_b200(a):
 
     # ---- end to end through the public API: pinned host batch -> H2D -> train_step -> D2H of the loss -------
     for i in range(2):
-        model.train_step(model.to_device(host[i % nbatch], B, T, Nn)).cpu()
+        model.train_step(model.to_device(host[i % nbatch], B, Ts[i % nbatch], Nn)).cpu()
     barrier()
     e0.record()
     for i in range(K):
-        bt = model.to_device(host[i % nbatch], B, T, Nn)
+        bt = model.to_device(host[i % nbatch], B, Ts[i % nbatch], Nn)
         loss_host = model.train_step(bt).cpu()
     e1.record()
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
-    h2d = host[0].numel() * 4
+    h2d = sum(host[i % nbatch].numel() for i in range(K)) * 4 / K
     d2h = B * 4
+    # ---- the same two measurements at the reference's --maxlen (every batch T = 20): the heaviest session side
+    for i in range(2):
+        model.train_step(dev20[i % 4])
+    barrier()
+    e0.record()
+    for i in range(K):
+        model.train_step(dev20[i % 4])
+    e1.record()
+    barrier()
+    t20_ms = max_over_ranks(e0.elapsed_time(e1))
+    e0.record()
+    for i in range(K):
+        model.train_step(model.to_device(host20[i % 4], B, T, Nn)).cpu()
+    e1.record()
+    barrier()
+    t20_e2e_ms = max_over_ranks(e0.elapsed_time(e1))
 
     # ---- evaluation: full-catalog top-20, catalog sharded across ranks when N > 1 ----------------------------
-    ehost = make_batches(synth, N, B, T, 0, mwdhm, nbatch, seed0=77)       # same queries on every rank
-    edev = [model.to_device(h, B, T, 0) for h in ehost]
+    ehost = make_batches(synth, N, B, Ts, 0, mwdhm, seed0=77)               # same queries on every rank
+    edev = [model.to_device(h, B, t, 0) for h, t in zip(ehost, Ts)]
     shard = None
     if world > 1:
         lo, hi = model.shard_bounds(world)[rank]
@@ -372,7 +413,7 @@ def run_b200(a):
     eval_ms = max_over_ranks(e0.elapsed_time(e1))
     e0.record()
     for i in range(K):
-        bt = model.to_device(ehost[i % nbatch], B, T, 0)
+        bt = model.to_device(ehost[i % nbatch], B, Ts[i % nbatch], 0)
         top, ngt, ce = model.eval_step(bt, shard=shard)
         top.cpu(); ngt.cpu(); ce.cpu()
     e1.record()
@@ -387,17 +428,17 @@ def run_b200(a):
         with open(tpath) as f:
             traffic = json.load(f)
     if rank == 0 and not a.no_kernels:
-        kernels = kernel_rooflines(torch, nv, model, dev[0], peaks, traffic)
+        kernels = kernel_rooflines(torch, nv, model, dev20[0], peaks, traffic)
     cpu_baseline = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         del model
         torch.cuda.empty_cache()
         Bs = a.cpu_sample_sessions
-        rate, ms, threads = oracle_train_rate(N, Bs, T, Nn, 3, 1, content, mwdhm)
-        erate = oracle_eval_rate(N, Bs, T, 1, content, mwdhm)
+        rate, ms, threads = oracle_train_rate(N, Bs, Ts, Nn, 3, 1, content, mwdhm)
+        erate = oracle_eval_rate(N, Bs, Ts[0], 1, content, mwdhm)
         cpu_baseline = {"value": rate, "unit": "sessions/s", "cores": threads, "kind": "port",
-                        "sample": f"3 train steps of {Bs} sessions (T={T}, Nn={Nn}) against the full {N}-item "
-                                  f"catalog after 1 warm-up, torch CPU fp32 oracle ({ms:.0f} ms/step)",
+                        "sample": f"3 train steps of {Bs} sessions (session lengths {Ts[:3]}, Nn={Nn}) against the full "
+                                  f"{N}-item catalog after 1 warm-up, torch CPU fp32 oracle ({ms:.0f} ms/step)",
                         "eval_queries_per_s": erate}
     if rank != 0:
         if dist is not None:
@@ -425,7 +466,11 @@ def run_b200(a):
                      "unit": "queries/s", "ms_per_step": eval_ms / K,
                      "scaling": "strong (catalog sharded across ranks)" if world > 1 else "single",
                      "e2e": {"value": B * K / (eval_e2e_ms * 1e-3), "unit": "queries/s",
-                             "h2d_bytes_per_step": ehost[0].numel() * 4, "d2h_bytes_per_step": B * (20 + 1 + 1) * 4}},
+                             "h2d_bytes_per_step": sum(ehost[i % nbatch].numel() for i in range(K)) * 4 / K,
+                             "d2h_bytes_per_step": B * (20 + 1 + 1) * 4}},
+            "t20": {"note": "same measurement with every batch at the reference --maxlen (T = 20)",
+                    "value": sessions / (t20_ms * 1e-3), "ms_per_step": t20_ms / K,
+                    "e2e_value": sessions / (t20_e2e_ms * 1e-3), "unit": "sessions/s"},
             "gpu_launches": launches, "launches_per_step": launches / K, "loss_last_step": loss_last,
             "clocks": clk, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu_baseline}
     print(json.dumps(line), flush=True)

@@ -115,9 +115,11 @@ int tcar_score_bwd_finish(const float* dq_raw, const float* sumexp, const float*
                           const int32_t* label, float* d_a_ic, float* d_a_pt, float* dTq, void* qs_bf16, int B,
                           void* stream);
 
-/* (3f) scoring backward wrt the item embeddings: g_item[n+1, :250] = sum_b E[b,n] Qs[b,:] (dense, overwrites). */
-int tcar_score_bwd_i(const void* e_bf16, const void* qs_bf16, float* g_item, int n_rows, int n_items, int n_pad,
-                     void* stream);
+/* (3f) scoring backward wrt the item embeddings: g_item[n+1, :250] = sum_b E[b,n] Qs[b,:] (dense, overwrites).
+ *      sq_partial [tcar_score_bwd_i_ctas(n_pad)] (nullable): per-CTA sum of squares of what was written. */
+int tcar_score_bwd_i(const void* e_bf16, const void* qs_bf16, float* g_item, float* sq_partial, int n_rows,
+                     int n_items, int n_pad, void* stream);
+int tcar_score_bwd_i_ctas(int n_pad);
 
 /* (5a) gradients of the seven small embedding tables (pos, month, day, week, hour, minute, duration): sums the
  *      gather-side, click-context-side and scoring-side contributions per table row in a fixed order, applies the
@@ -177,19 +179,26 @@ int tcar_prep_weights(const float* theta, const int32_t* table, int ntensors, fl
 
 /* (5b) deterministic scatter-add of the sparse item-row gradients into the dense g_item [N+1,256]:
  *      clicked rows (clip Jacobian of dXi), label rows (-a_ic[:, :250]) and negative rows (coef a_ic[:, :250]).
- *      Accumulation is exact int64 fixed point (2^-40) in a hash-slotted scratch, so the result does not depend
- *      on the order in which duplicate rows arrive.  hash_keys [hash_size] int32 must be -1 and hash_acc
- *      [hash_size][256] int64 must be 0 on entry; both are restored on exit.  hash_size: power of two. */
+ *      Three passes: claim a hash slot per row and count its entries; rows with ONE entry are updated in place
+ *      (128-bit read-modify-write), rows shared by several entries accumulate in exact int64 fixed point (2^-40),
+ *      so the result never depends on the order in which duplicates arrive; finally the shared rows are applied.
+ *      Scratch, all restored on exit: hash_keys [hash_size] int32 = -1, hash_cnt [hash_size] int32 = 0, hash_acc
+ *      [hash_size][256] int64 = 0; entry_slot [B*T + B + B*Nn] int32 (no initial state).  hash_size: power of two,
+ *      >= 2 x entries.  slot_sq [hash_size] (nullable) receives, per slot, the change of ||g_item||^2 caused by the
+ *      rows of that slot (0 for empty slots) -- input of tcar_sqnorm_combine. */
 int tcar_scatter_add_rows(const int32_t* seq, const int32_t* label, const int32_t* neg, const float* dXi,
                           const float* a_ic, const float* coef, const float* item, float* g_item,
-                          int32_t* hash_keys, long long* hash_acc, int hash_size, int B, int T, int Nn,
-                          void* stream);
+                          int32_t* hash_keys, int32_t* hash_cnt, long long* hash_acc, int32_t* entry_slot,
+                          float* slot_sq, int hash_size, int B, int T, int Nn, void* stream);
 
 /* (5c) per-tensor squared L2 norms (for tf.clip_by_norm, model_combine.py:158-160). seg_off [nseg+1], every
  *      segment start 16-byte aligned and zero padded to a multiple of 4 floats.  tcar_sqnorm_segments writes
  *      sqnorm [nseg][TCAR_NORM_SPLIT] partial sums (tcar_adam_small adds them in index order). */
 int tcar_sqnorm_segments(const float* flat, const int32_t* seg_off, float* sqnorm, int nseg, void* stream);
 int tcar_sqnorm_big(const float* x, float* partial, float* sqnorm, long long n, void* stream);
+/* squared norm of the item gradient WITHOUT re-reading it: out[0] = sum(a[0..na)) + sum(b[0..nb)) in a fixed order,
+ * a = per-CTA sums of squares written by tcar_score_bwd_i, b = slot_sq of tcar_scatter_add_rows. */
+int tcar_sqnorm_combine(const float* a, int na, const float* b, int nb, float* out, void* stream);
 
 /* (5d) clip_by_norm + TF-flavoured Adam (model_combine.py:155-163): lr_t = lr sqrt(1-b2^t)/(1-b1^t),
  *      theta -= lr_t m / (sqrt(v) + eps).  `step` [1] int32 on device holds t (already incremented). */

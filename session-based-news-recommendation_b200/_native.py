@@ -30,7 +30,9 @@ SIGNATURES = {
     "tcar_score_bwd_q_splits": [_I, _I],
     "tcar_score_bwd_q": [_P] * 4 + [_I, _I, _P],
     "tcar_score_bwd_finish": [_P] * 13 + [_I, _P],
-    "tcar_score_bwd_i": [_P] * 3 + [_I, _I, _I, _P],
+    "tcar_score_bwd_i": [_P] * 4 + [_I, _I, _I, _P],
+    "tcar_score_bwd_i_ctas": [_I],
+    "tcar_sqnorm_combine": [_P, _I, _P, _I, _P, _P],
     "tcar_small_table_grads": [_P] * 22 + [_I, _I, _P],
     "tcar_act_bwd_colsum": [_P] * 4 + [_I, _I, _I, _I, _P],
     "tcar_gemm_tf32": [_P, _I, _I, _I, _P, _I, _P, _I, _I, _I, _I, _P, _P],
@@ -38,7 +40,7 @@ SIGNATURES = {
     "tcar_gemm_tf32_splits": [_I, _I, _I, _I],
     "tcar_gemm_tf32_part_elems": [_I, _I, _I],
     "tcar_prep_weights": [_P, _P, _I, _P, _P, _P],
-    "tcar_scatter_add_rows": [_P] * 10 + [_I] * 4 + [_P],
+    "tcar_scatter_add_rows": [_P] * 13 + [_I] * 4 + [_P],
     "tcar_sqnorm_segments": [_P] * 3 + [_I, _P],
     "tcar_sqnorm_big": [_P] * 3 + [_LL, _P],
     "tcar_adam_small": [_P] * 6 + [_I, _P, _F, _F, _P],

@@ -108,6 +108,27 @@ sqnorm_big_final_kernel(const float* __restrict__ partial, float* __restrict__ o
     }
 }
 
+// out = sum(a) + sum(b), each thread sums a fixed strided subset, then a fixed-order block reduction
+__global__ void __launch_bounds__(1024)
+sqnorm_combine_kernel(const float* __restrict__ a, int na, const float* __restrict__ b, int nb,
+                      float* __restrict__ out) {
+    __shared__ float red[32];
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < na; i += blockDim.x) acc += a[i];
+    float acc2 = 0.f;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) acc2 += b[i];
+    acc += acc2;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 32; ++i) t += red[i];
+        out[0] = t;
+    }
+}
+
 // tf.clip_by_norm(g, c) = g * c / max(||g||, c);  TF Adam: lr_t = lr sqrt(1-b2^t)/(1-b1^t); p -= lr_t m/(sqrt(v)+eps)
 __device__ __forceinline__ float clip_factor(float sqnorm, float max_grad) {
     const float n = sqrtf(sqnorm);
@@ -193,6 +214,12 @@ extern "C" int tcar_sqnorm_big(const float* x, float* partial, float* sqnorm, lo
     int rc = (int)cudaGetLastError();
     if (rc) return rc;
     sqnorm_big_final_kernel<<<1, 1024, 0, STREAM>>>(partial, sqnorm, kNormBlocks);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int tcar_sqnorm_combine(const float* a, int na, const float* b, int nb, float* out, void* stream) {
+    if (na < 0 || nb < 0 || !out) return TCAR_ERR_ARG;
+    sqnorm_combine_kernel<<<1, 1024, 0, STREAM>>>(a, na, b, nb, out);
     return (int)cudaGetLastError();
 }
 

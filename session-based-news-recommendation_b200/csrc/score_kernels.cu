@@ -569,6 +569,7 @@ constexpr int I_NACC = 4;
 constexpr int I_SMEM = 8 * I_B_KB + I_STAGES * I_A_STAGE + 1024 + 256;
 
 struct BwdIParams {
+    float* sq_partial;  // [gridDim.x] per-CTA sum of squares of the written gradient (nullable)
     float* g_item;   // [N+1, 256] dense item-table gradient (row 0 = pad item)
     int n_items;
     int n_tiles;     // ceil(Npad / 128)
@@ -578,6 +579,7 @@ struct BwdIParams {
 __global__ void __launch_bounds__(kThreads, 1)
 score_bwd_i_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant__ CUtensorMap map_qs,
                    const BwdIParams p) {
+    __shared__ float sq_red[4];
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_b = smem;                         // resident Qs half: nkb x 16 KB
@@ -670,6 +672,7 @@ score_bwd_i_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_const
     } else if (warp >= 4) {
         // thread <-> item row
         const uint32_t q = warp - 4;
+        float sq = 0.f;
         for (uint32_t it = 0; it < my_tiles; ++it) {
             const uint32_t acc = it % I_NACC;
             const uint32_t acc_phase = (it / I_NACC) & 1;
@@ -692,6 +695,9 @@ score_bwd_i_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_const
                         if (c + 2 >= TCAR_H) o.z = 0u;
                         if (c + 3 >= TCAR_H) o.w = 0u;
                         reinterpret_cast<uint4*>(dst + ch * 32)[g] = o;
+                        const float f0 = __uint_as_float(o.x), f1 = __uint_as_float(o.y);
+                        const float f2 = __uint_as_float(o.z), f3 = __uint_as_float(o.w);
+                        sq += (f0 * f0 + f1 * f1) + (f2 * f2 + f3 * f3);
                     }
                 }
             }
@@ -699,6 +705,13 @@ score_bwd_i_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[acc]);
         }
+        // fixed-order reduction of the 128 per-thread sums of squares -> one partial per CTA
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (lane == 0) sq_red[q] = sq;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (q == 0 && lane == 0 && p.sq_partial)
+            p.sq_partial[blockIdx.x] = (sq_red[0] + sq_red[1]) + (sq_red[2] + sq_red[3]);
     }
     tc_fence_before();
     __syncthreads();
@@ -887,8 +900,17 @@ extern "C" int tcar_score_bwd_q(const void* e_bf16, const void* iext_bf16, float
     return (int)cudaGetLastError();
 }
 
-extern "C" int tcar_score_bwd_i(const void* e_bf16, const void* qs_bf16, float* g_item, int n_rows, int n_items,
-                                int n_pad, void* stream_) {
+static int bwd_i_grid(int n_pad) {
+    int grid = (sm_count() / 2) * 2;
+    const int n_tiles = n_pad / BM;
+    if (grid > 2 * n_tiles) grid = 2 * n_tiles;
+    return grid;
+}
+
+extern "C" int tcar_score_bwd_i_ctas(int n_pad) { return bwd_i_grid(n_pad); }
+
+extern "C" int tcar_score_bwd_i(const void* e_bf16, const void* qs_bf16, float* g_item, float* sq_partial, int n_rows,
+                                int n_items, int n_pad, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (n_rows < 1 || n_rows > QROWS || n_pad % 256 != 0) return TCAR_ERR_ARG;
     CUtensorMap me, mq;
@@ -897,14 +919,14 @@ extern "C" int tcar_score_bwd_i(const void* e_bf16, const void* qs_bf16, float* 
     rc = make_map_bf16(&mq, qs_bf16, QROWS, 256, 256, 64, BK);
     if (rc) return rc;
     BwdIParams p;
+    p.sq_partial = sq_partial;
     p.g_item = g_item;
     p.n_items = n_items;
     p.n_tiles = n_pad / BM;
     p.nkb = (n_rows + BK - 1) / BK;
     cudaError_t e = cudaFuncSetAttribute(score_bwd_i_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I_SMEM);
     if (e != cudaSuccess) return (int)e;
-    int grid = (sm_count() / 2) * 2;
-    if (grid > 2 * p.n_tiles) grid = 2 * p.n_tiles;
+    const int grid = bwd_i_grid(n_pad);
     score_bwd_i_kernel<<<grid, kThreads, I_SMEM, stream>>>(me, mq, p);
     return (int)cudaGetLastError();
 }

@@ -555,27 +555,53 @@ __device__ __forceinline__ int hash_slot(int32_t* keys, int row, int mask) {
     }
 }
 
-// one warp per sparse entry: clicks [0,M), labels [M,M+B), negatives [M+B, M+B+B*Nn)
+__device__ __forceinline__ int entry_row(int e, int M, int B, const int32_t* __restrict__ seq,
+                                         const int32_t* __restrict__ label, const int32_t* __restrict__ neg) {
+    if (e < M) return seq[e];
+    if (e < M + B) return label[e - M] + 1;
+    return neg[e - M - B] + 1;
+}
+
+// pass 1 -- one thread per sparse entry (clicks [0,M), labels [M,M+B), negatives [M+B, M+B+B*Nn)): claim the hash
+// slot of its item row and count how many entries share it.
+__global__ void __launch_bounds__(256)
+scatter_count_kernel(const int32_t* __restrict__ seq, const int32_t* __restrict__ label,
+                     const int32_t* __restrict__ neg, int32_t* __restrict__ keys, int32_t* __restrict__ cnt,
+                     int32_t* __restrict__ entry_slot, int mask, int B, int T, int Nn) {
+    const int M = B * T;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= M + B + B * Nn) return;
+    const int slot = hash_slot(keys, entry_row(e, M, B, seq, label, neg), mask);
+    atomicAdd(&cnt[slot], 1);
+    entry_slot[e] = slot;
+}
+
+// pass 2 -- one warp per entry.  A row touched by exactly one entry (the common case: uniform negatives, labels, tail
+// items) is updated in place with plain 128-bit read-modify-writes; rows shared by several entries accumulate in exact
+// int64 fixed point (2^-40) so that the sum does not depend on the arrival order.
 __global__ void __launch_bounds__(256)
 scatter_accum_kernel(const int32_t* __restrict__ seq, const int32_t* __restrict__ label,
                      const int32_t* __restrict__ neg, const float* __restrict__ dXi, const float* __restrict__ a_ic,
-                     const float* __restrict__ coef, const float* __restrict__ item, int32_t* __restrict__ keys,
-                     unsigned long long* __restrict__ acc, int mask, int B, int T, int Nn) {
+                     const float* __restrict__ coef, const float* __restrict__ item, float* __restrict__ g_item,
+                     const int32_t* __restrict__ cnt, const int32_t* __restrict__ entry_slot,
+                     unsigned long long* __restrict__ acc, float* __restrict__ slot_sq, int B, int T, int Nn) {
     const int M = B * T;
     const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (e >= M + B + B * Nn) return;
-    int row;
+    const int row = entry_row(e, M, B, seq, label, neg);
     float val[8];
     if (e < M) {
-        row = seq[e];
         const float4* ir = reinterpret_cast<const float4*>(item + (size_t)row * HP);
         const float4 i0 = __ldg(ir + lane), i1 = __ldg(ir + 32 + lane);
+        const float4* dr = reinterpret_cast<const float4*>(dXi + (size_t)e * HP);
+        const float4 d0 = __ldg(dr + lane), d1 = __ldg(dr + 32 + lane);
         const float xv[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
-        float dy[8], sq = 0.f, xdy = 0.f;
+        float dy[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        float sq = 0.f, xdy = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = (j < 4) ? lane * 4 + j : 128 + lane * 4 + (j - 4);
-            dy[j] = c < H ? dXi[(size_t)e * HP + c] : 0.f;
+            if (c >= H) dy[j] = 0.f;          // dXi pad columns are never written
             sq = fmaf(xv[j], xv[j], sq);
             xdy = fmaf(xv[j], dy[j], xdy);
         }
@@ -594,41 +620,66 @@ scatter_accum_kernel(const int32_t* __restrict__ seq, const int32_t* __restrict_
     } else {
         int b;
         float scale;
-        if (e < M + B) { b = e - M; row = label[b] + 1; scale = -1.f; }
-        else { const int k = e - M - B; b = k / Nn; row = neg[k] + 1; scale = coef[b]; }
+        if (e < M + B) { b = e - M; scale = -1.f; }
+        else { b = (e - M - B) / Nn; scale = coef[b]; }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = (j < 4) ? lane * 4 + j : 128 + lane * 4 + (j - 4);
             val[j] = c < H ? scale * a_ic[(size_t)b * XW + c] : 0.f;
         }
     }
-    int slot = 0;
-    if (lane == 0) slot = hash_slot(keys, row, mask);
-    slot = __shfl_sync(0xffffffffu, slot, 0);
-    unsigned long long* dst = acc + (size_t)slot * HP;
+    const int slot = entry_slot[e];
+    if (cnt[slot] == 1) {
+        float4* dst = reinterpret_cast<float4*>(g_item + (size_t)row * HP);
+        float4 o0 = dst[lane], o1 = dst[32 + lane];
+        const float4 n0 = make_float4(o0.x + val[0], o0.y + val[1], o0.z + val[2], o0.w + val[3]);
+        const float4 n1 = make_float4(o1.x + val[4], o1.y + val[5], o1.z + val[6], o1.w + val[7]);
+        dst[lane] = n0;
+        dst[32 + lane] = n1;
+        // change of the squared gradient norm caused by this row (see tcar_sqnorm_combine)
+        float d = (n0.x * n0.x - o0.x * o0.x) + (n0.y * n0.y - o0.y * o0.y) + (n0.z * n0.z - o0.z * o0.z) +
+                  (n0.w * n0.w - o0.w * o0.w) + (n1.x * n1.x - o1.x * o1.x) + (n1.y * n1.y - o1.y * o1.y) +
+                  (n1.z * n1.z - o1.z * o1.z) + (n1.w * n1.w - o1.w * o1.w);
+        d = warp_sum(d);
+        if (lane == 0 && slot_sq) slot_sq[slot] = d;
+    } else {
+        unsigned long long* dst = acc + (size_t)slot * HP;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int c = (j < 4) ? lane * 4 + j : 128 + lane * 4 + (j - 4);
-        if (c < H) atomicAdd(dst + c, (unsigned long long)__float2ll_rn(val[j] * kFix));
+        for (int j = 0; j < 8; ++j) {
+            const int c = (j < 4) ? lane * 4 + j : 128 + lane * 4 + (j - 4);
+            if (c < H) atomicAdd(dst + c, (unsigned long long)__float2ll_rn(val[j] * kFix));
+        }
     }
 }
 
-// one warp per hash slot: add the exact integer sum to g_item and restore the scratch to its empty state
+// pass 3 -- one warp per hash slot: add the exact integer sums of the shared rows to g_item, record the change of the
+// squared norm, and restore the scratch (keys = -1, counts = 0, accumulators = 0).
 __global__ void __launch_bounds__(256)
-scatter_apply_kernel(int32_t* __restrict__ keys, long long* __restrict__ acc, float* __restrict__ g_item,
-                     int hash_size) {
+scatter_apply_kernel(int32_t* __restrict__ keys, int32_t* __restrict__ cnt, long long* __restrict__ acc,
+                     float* __restrict__ g_item, float* __restrict__ slot_sq, int hash_size) {
     const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (slot >= hash_size) return;
     const int row = keys[slot];
-    if (row < 0) return;
-    long long* src = acc + (size_t)slot * HP;
-    float* dst = g_item + (size_t)row * HP;
-    for (int c = lane; c < H; c += 32) {
-        dst[c] += (float)src[c] * kInvFix;
-        src[c] = 0;
+    if (row < 0) {
+        if (lane == 0 && slot_sq) slot_sq[slot] = 0.f;
+        return;
+    }
+    if (cnt[slot] > 1) {
+        long long* src = acc + (size_t)slot * HP;
+        float* dst = g_item + (size_t)row * HP;
+        float d = 0.f;
+        for (int c = lane; c < H; c += 32) {
+            const float o = dst[c];
+            const float nv = o + (float)src[c] * kInvFix;
+            dst[c] = nv;
+            d += nv * nv - o * o;
+            src[c] = 0;
+        }
+        d = warp_sum(d);
+        if (lane == 0 && slot_sq) slot_sq[slot] = d;
     }
     __syncwarp();
-    if (lane == 0) keys[slot] = -1;
+    if (lane == 0) { keys[slot] = -1; cnt[slot] = 0; }
 }
 
 }  // namespace tcar
@@ -729,15 +780,20 @@ extern "C" int tcar_small_table_grads(const int32_t* idx, const int32_t* ctx, co
 
 extern "C" int tcar_scatter_add_rows(const int32_t* seq, const int32_t* label, const int32_t* neg, const float* dXi,
                                      const float* a_ic, const float* coef, const float* item, float* g_item,
-                                     int32_t* hash_keys, long long* hash_acc, int hash_size, int B, int T, int Nn,
-                                     void* stream) {
+                                     int32_t* hash_keys, int32_t* hash_cnt, long long* hash_acc, int32_t* entry_slot,
+                                     float* slot_sq, int hash_size, int B, int T, int Nn, void* stream) {
     const int entries = B * T + B + B * Nn;
     if (hash_size < 2 * entries || (hash_size & (hash_size - 1))) return TCAR_ERR_ARG;
-    scatter_accum_kernel<<<(entries + 7) / 8, 256, 0, STREAM>>>(
-        seq, label, neg, dXi, a_ic, coef, item, hash_keys, reinterpret_cast<unsigned long long*>(hash_acc),
-        hash_size - 1, B, T, Nn);
+    scatter_count_kernel<<<(entries + 255) / 256, 256, 0, STREAM>>>(seq, label, neg, hash_keys, hash_cnt, entry_slot,
+                                                                    hash_size - 1, B, T, Nn);
     int rc = LAUNCH_RC();
     if (rc) return rc;
-    scatter_apply_kernel<<<(hash_size + 7) / 8, 256, 0, STREAM>>>(hash_keys, hash_acc, g_item, hash_size);
+    scatter_accum_kernel<<<(entries + 7) / 8, 256, 0, STREAM>>>(
+        seq, label, neg, dXi, a_ic, coef, item, g_item, hash_cnt, entry_slot,
+        reinterpret_cast<unsigned long long*>(hash_acc), slot_sq, B, T, Nn);
+    rc = LAUNCH_RC();
+    if (rc) return rc;
+    scatter_apply_kernel<<<(hash_size + 7) / 8, 256, 0, STREAM>>>(hash_keys, hash_cnt, hash_acc, g_item, slot_sq,
+                                                                  hash_size);
     return LAUNCH_RC();
 }

@@ -105,6 +105,10 @@ class Seq2SeqAttNN:
         self.hash_size = 65536
         self.hash_keys = torch.full((self.hash_size,), -1, device=dev, dtype=torch.int32)
         self.hash_acc = torch.zeros(self.hash_size, nv.HP, device=dev, dtype=torch.int64)
+        self.hash_cnt = torch.zeros(self.hash_size, device=dev, dtype=torch.int32)
+        self.entry_slot = torch.zeros(self.hash_size // 2, device=dev, dtype=torch.int32)
+        self.slot_sq = f(self.hash_size)
+        self.sq_partial = f(256)
         self.top_ids = torch.zeros(Bm, TOPK, device=dev, dtype=torch.int32)
         self.top_scores = f(Bm, TOPK)
         self.n_greater = torch.zeros(Bm, device=dev, dtype=torch.int32)
@@ -211,7 +215,8 @@ class Seq2SeqAttNN:
         nv.counted_call("tcar_score_bwd_finish", 1, p(self.dq_raw), p(self.sumexp), p(self.dA_neg), p(self.a_ic),
                         p(ps.ct_tab), p(ps.item), p(ps.content), p(ps.mwdhm), p(bt.label), p(self.d_a_ic),
                         p(self.d_a_pt), p(self.dTq), p(self.Qs), B)
-        nv.counted_call("tcar_score_bwd_i", 1, p(ws["E"]), p(self.Qs), p(ps.item_g), B, ps.N, ps.n_pad)
+        nv.counted_call("tcar_score_bwd_i", 1, p(ws["E"]), p(self.Qs), p(ps.item_g), p(self.sq_partial), B, ps.N,
+                        ps.n_pad)
         # ---- session-side backward: weight / data gradients on the tensor cores in single-pass TF32 (gradients carry
         # a 2e-2 norm-wise tolerance, dominated by the bf16 scoring GEMMs); operands are consumed in place, K-major or
         # MN-major as they lie, so no transposes are materialised.
@@ -268,9 +273,10 @@ class Seq2SeqAttNN:
         entries = B * T + B + B * bt.Nn
         if 2 * entries > self.hash_size:
             raise ValueError("batch too large for the sparse-gradient scratch")
-        nv.counted_call("tcar_scatter_add_rows", 2, p(bt.seq), p(bt.label), p(bt.neg), p(self.dXi), p(self.a_ic),
-                        p(self.coef), p(ps.item), p(ps.item_g), p(self.hash_keys), p(self.hash_acc), self.hash_size,
-                        B, T, bt.Nn)
+        nv.counted_call("tcar_scatter_add_rows", 3, p(bt.seq), p(bt.label), p(bt.neg), p(self.dXi), p(self.a_ic),
+                        p(self.coef), p(ps.item), p(ps.item_g), p(self.hash_keys), p(self.hash_cnt), p(self.hash_acc),
+                        p(self.entry_slot), p(self.slot_sq), self.hash_size, B, T, bt.Nn)
+        self._fused_norm = True
 
     def allreduce_grads(self):
         """Data-parallel training: SUM (not mean -- the loss is a batch sum, model_combine.py:156) over ranks."""
@@ -280,8 +286,16 @@ class Seq2SeqAttNN:
         """per-tensor clip_by_norm + TF Adam (model_combine.py:155-163); also refreshes the bf16 scoring operand."""
         ps, p = self.ps, nv.ptr
         nv.counted_call("tcar_sqnorm_segments", 1, p(ps.theta_g), p(ps.seg_off), p(ps.sqnorm_small), len(SMALL))
-        nv.counted_call("tcar_sqnorm_big", 2, p(ps.item_g), p(ps.norm_partial), p(ps.sqnorm_item),
-                        ps.item_g.numel())
+        if self.world == 1 and getattr(self, "_fused_norm", False):
+            # ||g_item||^2 from the per-CTA sums of the dense gradient GEMM + the per-row corrections of the scatter:
+            # no extra pass over the 364 MB gradient
+            nv.counted_call("tcar_sqnorm_combine", 1, p(self.sq_partial), nv.lib().tcar_score_bwd_i_ctas(ps.n_pad),
+                            p(self.slot_sq), self.hash_size, p(ps.sqnorm_item))
+        else:
+            # data parallel: the clip norm is the norm of the all-reduced gradient
+            nv.counted_call("tcar_sqnorm_big", 2, p(ps.item_g), p(ps.norm_partial), p(ps.sqnorm_item),
+                            ps.item_g.numel())
+        self._fused_norm = False
         ps.step.add_(1)
         self.global_step += 1
         nv.counted_call("tcar_adam_small", 1, p(ps.theta), p(ps.theta_m), p(ps.theta_v), p(ps.theta_g), p(ps.seg_off),

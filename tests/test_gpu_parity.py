@@ -12,6 +12,11 @@ pytestmark = pytest.mark.gpu
 from oracle import tcar_oracle as O  # noqa: E402
 
 
+def nv_lib():
+    from tcar_b200 import _native
+    return _native.lib()
+
+
 def build(N, emb_scale=1.0, Nn=20, seed=3, max_grad=150, lr=0.001):
     from tcar_b200 import synth
     from tcar_b200.model_combine import Seq2SeqAttNN
@@ -95,7 +100,13 @@ def test_train_step_loss_and_gradients(B, T, scale, Nn):
     bad = {k: v for k, v in errs.items() if v > 2e-2}
     assert not bad, f"gradient norm-wise rel err too large: {bad} (all: {errs})"
     assert (model.ps.item_g[:, 250:] == 0).all() and (model.ps.item_g[0] == 0).all()
-    assert (model.hash_keys == -1).all() and (model.hash_acc == 0).all(), "scatter scratch must be restored"
+    assert (model.hash_keys == -1).all() and (model.hash_acc == 0).all() and (model.hash_cnt == 0).all(), \
+        "scatter scratch must be restored"
+    # fused squared norm (dense GEMM partials + scatter corrections) == norm of the final item gradient
+    ctas = nv_lib().tcar_score_bwd_i_ctas(model.ps.n_pad)
+    fused = float(model.sq_partial[:ctas].double().sum() + model.slot_sq.double().sum())
+    want = float((model.ps.item_g.double() ** 2).sum())
+    assert abs(fused - want) <= 1e-4 * want + 1e-12, (fused, want)
 
 
 def test_adam_clip_kernels_match_oracle_given_same_grads():

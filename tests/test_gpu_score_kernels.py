@@ -103,7 +103,8 @@ def test_score_bwd_i(native, B, N):
     Qs[:B, :250] = (torch.randn(B, 250, device="cuda", generator=g) * 0.2).bfloat16()
     gi = torch.full((N + 1, 256), float("nan"), device="cuda")
     gi[0] = 0
-    native.call("tcar_score_bwd_i", native.ptr(E), native.ptr(Qs), native.ptr(gi), B, N, n_pad)
+    sqp = torch.full((native.lib().tcar_score_bwd_i_ctas(n_pad),), float("nan"), device="cuda")
+    native.call("tcar_score_bwd_i", native.ptr(E), native.ptr(Qs), native.ptr(gi), native.ptr(sqp), B, N, n_pad)
     torch.cuda.synchronize()
     ref = (E[:B, :N].double().t() @ Qs[:B].double()).float()
     scale = ref.abs().max().item()
@@ -111,3 +112,6 @@ def test_score_bwd_i(native, B, N):
     assert err < 1e-4, f"g_item err {err} (scale {scale})"
     assert (gi[1:, 250:] == 0).all()
     assert (gi[0] == 0).all()
+    # the fused per-CTA sums of squares add up to ||g_item||^2
+    want = float((gi.double() ** 2).sum())
+    assert abs(float(sqp.double().sum()) - want) <= 1e-5 * want
