@@ -34,6 +34,8 @@ extern "C" {
 #define TCAR_CHUNK 8      /* items per eval chunk-max                                                   */
 #define TCAR_NCAND_CHUNKS 32 /* chunks re-scored per query (256 candidate items)                        */
 #define TCAR_NORM_SPLIT 8    /* partial sums per tensor written by tcar_sqnorm_segments                     */
+#define TCAR_TABLE_GRAD_CHUNKS 148   /* max click chunks (CTAs) of tcar_small_table_grads pass 1               */
+#define TCAR_TABLE_GRAD_PART 19600   /* floats of partial sums per chunk: 139x64 + 11x64 + 40x250              */
 
 #define TCAR_CLUSTER_PAIR (-2) /* tcar_score_fwd `cluster` value: CTA pair, tcgen05.mma.cta_group::2 (M = 256)   */
 
@@ -84,7 +86,9 @@ int tcar_build_query(const float* a_ic, const float* a_pt, const float* ct_tab, 
                      float* c_ref, int B, void* stream);
 
 /* (3c) full-catalog scoring S = Q . Iext^T on tcgen05 (model_combine.py:138), never materialising S.
- *   mode 0 (train): E [512,n_pad] bf16 = exp(S - c_ref), rowsum_part [n_pad/128][512]
+ *   mode 0 (train): E = exp(S - c_ref) in bf16, logically [512, n_pad], stored in blocks of 8 items:
+ *                   E[b, n] at element ((n / 8) * 512 + b) * 8 + n % 8 (coalesced epilogue stores; the backward
+ *                   kernels read it through a 3-D tensor map); rowsum_part [n_pad/128][512]
  *   mode 1 (eval) : chunkmax [512, n_pad/8] fp32 = max of S over 8 consecutive items, rowsum_part as above
  *   cluster in {1,2,4}: CTAs per cluster sharing each item tile by TMA multicast (one 128x128 UMMA per CTA);
  *   cluster == TCAR_CLUSTER_PAIR: CTA pairs issuing 256x256 cta_group::2 UMMAs, each CTA streaming half of every
@@ -123,13 +127,15 @@ int tcar_score_bwd_i_ctas(int n_pad);
 
 /* (5a) gradients of the seven small embedding tables (pos, month, day, week, hour, minute, duration): sums the
  *      gather-side, click-context-side and scoring-side contributions per table row in a fixed order, applies the
- *      clip Jacobian once per row and writes g_* (same shapes as the tables). */
+ *      clip Jacobian once per row and writes g_* (same shapes as the tables).  dXi has a 256-float row pitch.
+ *      part: scratch of TCAR_TABLE_GRAD_CHUNKS x TCAR_TABLE_GRAD_PART floats (per-chunk partial sums, no initial
+ *      state). */
 int tcar_small_table_grads(const int32_t* idx, const int32_t* ctx, const float* dXi, const float* dP,
                            const float* dD, const float* dCT, const float* dTq, const float* a_pt,
                            const float* pos, const float* month, const float* day, const float* week,
                            const float* hour, const float* minute, const float* dur, float* g_pos, float* g_month,
-                           float* g_day, float* g_week, float* g_hour, float* g_minute, float* g_dur, int B, int T,
-                           void* stream);
+                           float* g_day, float* g_week, float* g_hour, float* g_minute, float* g_dur, float* part,
+                           int B, int T, void* stream);
 
 /* (5a') backward of an elementwise activation fused with the bias gradient (linear_2d, modules.py:43-55):
  *      dz[r,c] = dy[r,c] * act'(y[r,c]) with act' expressed through the OUTPUT y (mode 0: tanh -> 1 - y^2,

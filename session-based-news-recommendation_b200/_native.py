@@ -33,7 +33,7 @@ SIGNATURES = {
     "tcar_score_bwd_i": [_P] * 4 + [_I, _I, _I, _P],
     "tcar_score_bwd_i_ctas": [_I],
     "tcar_sqnorm_combine": [_P, _I, _P, _I, _P, _P],
-    "tcar_small_table_grads": [_P] * 22 + [_I, _I, _P],
+    "tcar_small_table_grads": [_P] * 23 + [_I, _I, _P],
     "tcar_act_bwd_colsum": [_P] * 4 + [_I, _I, _I, _I, _P],
     "tcar_gemm_tf32": [_P, _I, _I, _I, _P, _I, _P, _I, _I, _I, _I, _P, _P],
     "tcar_gemm_tf32_group": [_P, _I, _P],

@@ -99,6 +99,12 @@ __device__ __forceinline__ float tf32_rn(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+// tanh(x) = 1 - 2 / (exp(2x) + 1) with ex2.approx / rcp.approx: absolute error < 3e-7 (the epilogue thread owns a
+// whole output row, so the ~30-instruction libm tanhf would dominate the small projections)
+__device__ __forceinline__ float tanh_fast(float x) {
+    const float e = ex2_approx(x * 2.8853900817779268f);     // exp(2x)
+    return 1.f - __fdividef(2.f, e + 1.f);
+}
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -282,7 +288,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmGroup grp) {
                     float x = __uint_as_float(v[j]);
                     if (p.bias && c0 + j < p.N) x += p.bias[c0 + j];
                     if (p.act == 1) x = fmaxf(x, 0.f);
-                    else if (p.act == 2) x = tanhf(x);
+                    else if (p.act == 2) x = tanh_fast(x);
                     o[j] = x;
                 }
                 if (vec && c0 + 32 <= p.N) {

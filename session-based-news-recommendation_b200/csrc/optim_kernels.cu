@@ -108,23 +108,33 @@ sqnorm_big_final_kernel(const float* __restrict__ partial, float* __restrict__ o
     }
 }
 
-// out = sum(a) + sum(b), each thread sums a fixed strided subset, then a fixed-order block reduction
+// out = sum(a) + sum(b): each thread sums a fixed strided subset (128-bit loads, independent accumulators), then a
+// fixed-order block reduction.  nb must be a multiple of 4 and b 16-byte aligned.
 __global__ void __launch_bounds__(1024)
-sqnorm_combine_kernel(const float* __restrict__ a, int na, const float* __restrict__ b, int nb,
+sqnorm_combine_kernel(const float* __restrict__ a, int na, const float4* __restrict__ b, int nb4,
                       float* __restrict__ out) {
     __shared__ float red[32];
     float acc = 0.f;
     for (int i = threadIdx.x; i < na; i += blockDim.x) acc += a[i];
-    float acc2 = 0.f;
-    for (int i = threadIdx.x; i < nb; i += blockDim.x) acc2 += b[i];
-    acc += acc2;
+    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+    int i = threadIdx.x;
+    for (; i + 1024 < nb4; i += 2048) {
+        const float4 u = b[i], v = b[i + 1024];
+        s0.x += u.x; s0.y += u.y; s0.z += u.z; s0.w += u.w;
+        s1.x += v.x; s1.y += v.y; s1.z += v.z; s1.w += v.w;
+    }
+    if (i < nb4) {
+        const float4 u = b[i];
+        s0.x += u.x; s0.y += u.y; s0.z += u.z; s0.w += u.w;
+    }
+    acc += ((s0.x + s0.y) + (s0.z + s0.w)) + ((s1.x + s1.y) + (s1.z + s1.w));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
     __syncthreads();
     if (threadIdx.x == 0) {
         float t = 0.f;
-        for (int i = 0; i < 32; ++i) t += red[i];
+        for (int k = 0; k < 32; ++k) t += red[k];
         out[0] = t;
     }
 }
@@ -218,8 +228,8 @@ extern "C" int tcar_sqnorm_big(const float* x, float* partial, float* sqnorm, lo
 }
 
 extern "C" int tcar_sqnorm_combine(const float* a, int na, const float* b, int nb, float* out, void* stream) {
-    if (na < 0 || nb < 0 || !out) return TCAR_ERR_ARG;
-    sqnorm_combine_kernel<<<1, 1024, 0, STREAM>>>(a, na, b, nb, out);
+    if (na < 0 || nb < 0 || (nb & 3) || !out) return TCAR_ERR_ARG;
+    sqnorm_combine_kernel<<<1, 1024, 0, STREAM>>>(a, na, reinterpret_cast<const float4*>(b), nb / 4, out);
     return (int)cudaGetLastError();
 }
 

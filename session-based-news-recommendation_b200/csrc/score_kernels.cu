@@ -6,7 +6,13 @@
 // Data layout:
 //   Q    [512, 640]  bf16  session operand  [a_ic(500) | T(139) | 0]      (T = a_pt . clip(time tables)^T)
 //   Iext [Npad, 640] bf16  item operand     [item(250) | content(250) | onehot(139) | 0], rows >= N are zero
-//   E    [512, Npad] bf16  exp(S - c_b), written by the forward kernel in train mode, read by both backward GEMMs
+//   E    [Npad/8][512][8] bf16  exp(S - c_b), written by the forward kernel in train mode, read by both backward
+//        GEMMs.  Logically E[b, n]; stored in blocks of 8 items so that the forward epilogue (thread <-> session
+//        row, 8 items = one 16-byte store) writes 512 contiguous bytes per warp instruction instead of 32 scattered
+//        16-byte pieces (23 M single-sector L2 write requests per call with the row-major layout).  The backward
+//        kernels read it through a 3-D tensor map (8 items | session | item block) WITHOUT swizzle: a box lands in
+//        shared memory as [item block][session][8 items], which is exactly UMMA's no-swizzle canonical layout
+//        (8 x 16-byte core matrices) -- K-major for dQ (K = items), MN-major for dItem (K = sessions).
 //
 //   score_fwd   : S = Q . Iext^T, 128 sessions (TMEM lanes) x 128 items per tile, K = 640 resident in smem for Q,
 //                 item tiles TMA-multicast across a cluster of CL CTAs (CL session tiles share every item tile).
@@ -184,7 +190,7 @@ score_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 }
                 if (p.mode == 0) {
                   if (store_ok) {
-                    uint4* dst = reinterpret_cast<uint4*>(p.E + (size_t)row * p.e_pitch + nb);
+                    uint4* dst = reinterpret_cast<uint4*>(p.E) + (size_t)(nb >> 3) * QROWS + row;
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         uint4 o;
@@ -192,7 +198,7 @@ score_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                         o.y = pack_bf16(e[g * 8 + 2], e[g * 8 + 3]);
                         o.z = pack_bf16(e[g * 8 + 4], e[g * 8 + 5]);
                         o.w = pack_bf16(e[g * 8 + 6], e[g * 8 + 7]);
-                        dst[g] = o;
+                        dst[(size_t)g * QROWS] = o;
                     }
                   }
                 } else {
@@ -256,7 +262,8 @@ __device__ __forceinline__ void fwd_epilogue_chunk(const uint32_t (&v)[32], cons
     }
     if (MODE == 0) {
         if (store_ok) {
-            uint4* dst = reinterpret_cast<uint4*>(p.E + (size_t)row * p.e_pitch + nb);
+            // block-of-8-items layout: the 32 lanes (consecutive session rows) of one store are contiguous
+            uint4* dst = reinterpret_cast<uint4*>(p.E) + (size_t)(nb >> 3) * QROWS + row;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
                 uint4 o;
@@ -264,7 +271,7 @@ __device__ __forceinline__ void fwd_epilogue_chunk(const uint32_t (&v)[32], cons
                 o.y = pack_bf16(e[g * 8 + 2], e[g * 8 + 3]);
                 o.z = pack_bf16(e[g * 8 + 4], e[g * 8 + 5]);
                 o.w = pack_bf16(e[g * 8 + 6], e[g * 8 + 7]);
-                dst[g] = o;
+                dst[(size_t)g * QROWS] = o;
             }
         }
     } else {
@@ -492,7 +499,7 @@ score_bwd_q_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_const
                 mbar_expect_tx(&full[stage], Q_STAGE);
                 uint8_t* sa = smem + stage * Q_STAGE;
                 uint8_t* sb = sa + Q_A_STAGE;
-                tma_load_2d(sa, &map_e, &full[stage], kb * BK, mtile * BM);
+                tma_load_3d(sa, &map_e, &full[stage], 0, mtile * BM, kb * (BK / 8));
 #pragma unroll
                 for (int j = 0; j < Q_CH / 64; ++j)
                     tma_load_2d(sb + j * 8192, &map_i, &full[stage], chalf * Q_CH + j * 64, kb * BK);
@@ -512,7 +519,8 @@ score_bwd_q_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_const
 #pragma unroll
                 for (int k = 0; k < BK / 16; ++k) {
                     const uint32_t accum = (kb != kb0 || k != 0);
-                    const uint64_t ad = sdesc_kmajor(a_addr + k * 32);
+                    // E tile [8 item blocks][128 sessions][8 items]: core matrices 2048 B apart along K, 128 B along M
+                    const uint64_t ad = make_sdesc_nosw(a_addr + k * 4096, 2048, 128);
                     umma_bf16(tmem_base, ad, sdesc_mnmajor(b_addr + k * 2048, 8192), idesc256, accum);
                     umma_bf16(tmem_base + 256, ad, sdesc_mnmajor(b_addr + 4 * 8192 + k * 2048, 8192), idesc64, accum);
                 }
@@ -636,8 +644,7 @@ score_bwd_i_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_const
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_expect_tx(&full[stage], I_A_STAGE);
                     uint8_t* sa = smem_a + stage * I_A_STAGE;
-                    tma_load_2d(sa, &map_e, &full[stage], n0, kb * BK);
-                    tma_load_2d(sa + 8192, &map_e, &full[stage], n0 + 64, kb * BK);
+                    tma_load_3d(sa, &map_e, &full[stage], 0, kb * BK, n0 / 8);
                     if (++stage == I_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -660,7 +667,9 @@ score_bwd_i_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_const
                     const uint32_t b_addr = smem_u32(smem_b + kb * I_B_KB);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
-                        umma_bf16(tmem_base + acc * I_BN, sdesc_mnmajor(a_addr + k * 2048, 8192),
+                        // E tile [16 item blocks][64 sessions][8 items]: MN-major, core matrices 1024 B apart along
+                        // M (items), 128 B apart along K (sessions); one UMMA (K = 16 sessions) advances 256 B
+                        umma_bf16(tmem_base + acc * I_BN, make_sdesc_nosw(a_addr + k * 256, 128, 1024),
                                   sdesc_mnmajor(b_addr + k * 2048, 8192), idesc, (kb | k) != 0);
                     umma_commit(&empty[stage]);
                     if (kb == nkb - 1) umma_commit(&acc_full[acc]);
@@ -747,6 +756,22 @@ static int make_map_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : TCAR_ERR_TENSORMAP;
+}
+
+// E in its block-of-8-items layout [n_pad/8][512][8] bf16 as a 3-D tensor (8 items | session row | item block); the
+// box (8, box_rows sessions, box_blocks item blocks) lands in shared memory, unswizzled, as
+// [box_blocks][box_rows][8 items].
+static int make_map_e(CUtensorMap* m, const void* base, uint64_t n_pad, uint32_t box_rows, uint32_t box_blocks) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return TCAR_ERR_DRIVER;
+    cuuint64_t dims[3] = {8, (cuuint64_t)QROWS, n_pad / 8};
+    cuuint64_t strides[2] = {16, (cuuint64_t)QROWS * 16};
+    cuuint32_t box[3] = {8, box_rows, box_blocks};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : TCAR_ERR_TENSORMAP;
 }
@@ -879,7 +904,7 @@ extern "C" int tcar_score_bwd_q(const void* e_bf16, const void* iext_bf16, float
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (n_rows < 1 || n_rows > QROWS || n_pad % 256 != 0) return TCAR_ERR_ARG;
     CUtensorMap me, mi;
-    int rc = make_map_bf16(&me, e_bf16, QROWS, n_pad, n_pad, BK, BM);
+    int rc = make_map_e(&me, e_bf16, n_pad, BM, BK / 8);
     if (rc) return rc;
     rc = make_map_bf16(&mi, iext_bf16, n_pad, KEXT, KEXT, 64, BK);
     if (rc) return rc;
@@ -914,7 +939,7 @@ extern "C" int tcar_score_bwd_i(const void* e_bf16, const void* qs_bf16, float* 
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (n_rows < 1 || n_rows > QROWS || n_pad % 256 != 0) return TCAR_ERR_ARG;
     CUtensorMap me, mq;
-    int rc = make_map_bf16(&me, e_bf16, QROWS, n_pad, n_pad, 64, BK);
+    int rc = make_map_e(&me, e_bf16, n_pad, BK, BM / 8);
     if (rc) return rc;
     rc = make_map_bf16(&mq, qs_bf16, QROWS, 256, 256, 64, BK);
     if (rc) return rc;

@@ -424,53 +424,105 @@ score_bwd_finish_kernel(const float* __restrict__ dq_raw, const float* __restric
 
 // ------------------------------------------------------------------------------------------------ (5a) small tables
 // clip Jacobian of y = x / max(||x||, 1):  dx = dy (||x|| <= 1)   else   s (dy - y (y . dy)),  s = 1/||x||, y = s x
-// one CTA of 1024 threads per table row; groups of threads split the batch in a fixed pattern, combined in order.
-__global__ void __launch_bounds__(1024)
-small_table_grads_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ ctx,
-                         const float* __restrict__ dXi, const float* __restrict__ dP, const float* __restrict__ dD,
-                         const float* __restrict__ dCT, const float* __restrict__ dTq,
-                         const float* __restrict__ a_pt, const float* __restrict__ pos,
-                         const float* __restrict__ month, const float* __restrict__ day,
-                         const float* __restrict__ week, const float* __restrict__ hour,
-                         const float* __restrict__ minute, const float* __restrict__ dur, float* __restrict__ g_pos,
-                         float* __restrict__ g_month, float* __restrict__ g_day, float* __restrict__ g_week,
-                         float* __restrict__ g_hour, float* __restrict__ g_minute, float* __restrict__ g_dur, int B,
-                         int T) {
-    __shared__ float s_acc[1024];
+//
+// Two passes.  Pass 1: every CTA owns a contiguous chunk of the B*T clicks (and of the B sessions) and accumulates,
+// in click order, per-table-row partial sums in shared memory -- thread (k, d) owns column d of table k, so no two
+// threads ever touch the same accumulator and no atomics are needed.  Pass 2: one CTA per table row adds the chunk
+// partials in chunk order, the scoring-side term sum_b dTq[b,r] a_pt[b,:] and applies the clip Jacobian.
+constexpr int TG_BIN_FLOATS = NB * TH;                  // 139 x 64
+constexpr int TG_DUR_FLOATS = 11 * TH;                  // 11 x 64
+constexpr int TG_POS_FLOATS = TCAR_MAXT * H;            // 40 x 250
+constexpr int TG_PART_FLOATS = TG_BIN_FLOATS + TG_DUR_FLOATS + TG_POS_FLOATS;   // 19600 floats = 78.4 KB per chunk
+constexpr int TG_THREADS = 640;                          // 320 time (k,d) + 64 duration + 250 position (+6 idle)
+constexpr int TG_MAX_CHUNKS = TCAR_TABLE_GRAD_CHUNKS;
+
+__global__ void __launch_bounds__(TG_THREADS)
+table_partial_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ ctx, const float* __restrict__ dXi,
+                     const float* __restrict__ dP, const float* __restrict__ dD, const float* __restrict__ dCT,
+                     float* __restrict__ part, int B, int T) {
+    extern __shared__ float s_tab[];                    // [bins 139x64 | dur 11x64 | pos 40x250]
+    const int M = B * T, tid = threadIdx.x, nchunk = gridDim.x;
+    for (int i = tid; i < TG_PART_FLOATS; i += TG_THREADS) s_tab[i] = 0.f;
+    __syncthreads();
+    const int per = (M + nchunk - 1) / nchunk;
+    const int m0 = blockIdx.x * per, m1 = min(m0 + per, M);
+    const int bper = (B + nchunk - 1) / nchunk;
+    const int b0 = blockIdx.x * bper, b1 = min(b0 + bper, B);
+    if (tid < 5 * TH) {
+        const int k = tid >> 6, d = tid & 63;
+        float* acc = s_tab + (size_t)kBinOff[k] * TH + d;
+        const int32_t* ik = idx + (size_t)(k + 1) * M;
+        const float* src = dP + k * TH + d;
+        int m = m0;
+        for (; m + 4 <= m1; m += 4) {                     // 4 independent loads in flight, adds in click order
+            const int r0 = ik[m], r1 = ik[m + 1], r2 = ik[m + 2], r3 = ik[m + 3];
+            const float v0 = src[(size_t)m * PW], v1 = src[(size_t)(m + 1) * PW];
+            const float v2 = src[(size_t)(m + 2) * PW], v3 = src[(size_t)(m + 3) * PW];
+            acc[r0 * TH] += v0; acc[r1 * TH] += v1; acc[r2 * TH] += v2; acc[r3 * TH] += v3;
+        }
+        for (; m < m1; ++m) acc[ik[m] * TH] += src[(size_t)m * PW];
+        // click-time context (sampler.py:106-107): week table by ctx[0][b], hour table by ctx[1][b]
+        if (k == 2) for (int b = b0; b < b1; ++b) acc[ctx[b] * TH] += dCT[(size_t)b * 2 * TH + d];
+        if (k == 3) for (int b = b0; b < b1; ++b) acc[ctx[B + b] * TH] += dCT[(size_t)b * 2 * TH + TH + d];
+    } else if (tid < 6 * TH) {
+        const int d = tid - 5 * TH;
+        float* acc = s_tab + TG_BIN_FLOATS + d;
+        const int32_t* ik = idx + (size_t)6 * M;
+        int m = m0;
+        for (; m + 4 <= m1; m += 4) {
+            const int r0 = ik[m], r1 = ik[m + 1], r2 = ik[m + 2], r3 = ik[m + 3];
+            const float v0 = dD[(size_t)m * TH + d], v1 = dD[(size_t)(m + 1) * TH + d];
+            const float v2 = dD[(size_t)(m + 2) * TH + d], v3 = dD[(size_t)(m + 3) * TH + d];
+            acc[r0 * TH] += v0; acc[r1 * TH] += v1; acc[r2 * TH] += v2; acc[r3 * TH] += v3;
+        }
+        for (; m < m1; ++m) acc[ik[m] * TH] += dD[(size_t)m * TH + d];
+    } else if (tid < 6 * TH + H) {
+        const int c = tid - 6 * TH;
+        float* acc = s_tab + TG_BIN_FLOATS + TG_DUR_FLOATS + c;
+        int m = m0;
+        for (; m + 4 <= m1; m += 4) {
+            const float v0 = dXi[(size_t)m * HP + c], v1 = dXi[(size_t)(m + 1) * HP + c];
+            const float v2 = dXi[(size_t)(m + 2) * HP + c], v3 = dXi[(size_t)(m + 3) * HP + c];
+            acc[(m % T) * H] += v0; acc[((m + 1) % T) * H] += v1;
+            acc[((m + 2) % T) * H] += v2; acc[((m + 3) % T) * H] += v3;
+        }
+        for (; m < m1; ++m) acc[(m % T) * H] += dXi[(size_t)m * HP + c];
+    }
+    __syncthreads();
+    float* dst = part + (size_t)blockIdx.x * TG_PART_FLOATS;
+    for (int i = tid; i < TG_PART_FLOATS; i += TG_THREADS) dst[i] = s_tab[i];
+}
+
+__global__ void __launch_bounds__(256)
+table_finish_kernel(const float* __restrict__ part, int nchunk, const float* __restrict__ dTq,
+                    const float* __restrict__ a_pt, const float* __restrict__ pos, const float* __restrict__ month,
+                    const float* __restrict__ day, const float* __restrict__ week, const float* __restrict__ hour,
+                    const float* __restrict__ minute, const float* __restrict__ dur, float* __restrict__ g_pos,
+                    float* __restrict__ g_month, float* __restrict__ g_day, float* __restrict__ g_week,
+                    float* __restrict__ g_hour, float* __restrict__ g_minute, float* __restrict__ g_dur, int B,
+                    int T) {
+    __shared__ float s_acc[256];
     __shared__ float s_g[256];
     __shared__ float red[32];
-    const int M = B * T;
     const int row = blockIdx.x;  // [0,40) pos, [40,179) time bins, [179,190) duration
     const float* x;
     float* g;
     int width;
-    float acc = 0.f;
     if (row < TCAR_MAXT) {
-        // position rows: G[c] = sum_b dXi[b,t,c]
         width = H;
         x = pos + (size_t)row * H;
         g = g_pos + (size_t)row * H;
-        const int c = threadIdx.x & 255, grp = threadIdx.x >> 8;  // 4 groups
-        if (row < T && c < H) {
-            // 4 groups x 4 independent partial sums, combined in a fixed order
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-            int b = grp;
-            for (; b + 12 < B; b += 16) {
-                a0 += dXi[((size_t)b * T + row) * HP + c];
-                a1 += dXi[((size_t)(b + 4) * T + row) * HP + c];
-                a2 += dXi[((size_t)(b + 8) * T + row) * HP + c];
-                a3 += dXi[((size_t)(b + 12) * T + row) * HP + c];
-            }
-            for (; b < B; b += 4) a0 += dXi[((size_t)b * T + row) * HP + c];
-            acc = (a0 + a1) + (a2 + a3);
-        }
-        s_acc[threadIdx.x] = acc;
-        __syncthreads();
-        if (threadIdx.x < 256) s_g[threadIdx.x] = s_acc[threadIdx.x] + s_acc[256 + threadIdx.x] + s_acc[512 + threadIdx.x] + s_acc[768 + threadIdx.x];
+        const int c = threadIdx.x;
+        float acc = 0.f;
+        if (row < T && c < H)
+            for (int j = 0; j < nchunk; ++j)
+                acc += part[(size_t)j * TG_PART_FLOATS + TG_BIN_FLOATS + TG_DUR_FLOATS + (size_t)row * H + c];
+        s_g[threadIdx.x] = acc;
     } else {
         width = TH;
-        const int d = threadIdx.x & 63, grp = threadIdx.x >> 6;  // 16 groups
+        const int d = threadIdx.x & 63, grp = threadIdx.x >> 6;  // 4 groups
         const int r = row - TCAR_MAXT;
+        float acc = 0.f;
         if (r < NB) {
             int k = 0;
             while (r >= kBinOff[k + 1]) ++k;
@@ -479,52 +531,20 @@ small_table_grads_kernel(const int32_t* __restrict__ idx, const int32_t* __restr
             float* gs[5] = {g_month, g_day, g_week, g_hour, g_minute};
             x = tabs[k] + (size_t)rr * TH;
             g = gs[k] + (size_t)rr * TH;
-            const int32_t* ik = idx + (size_t)(k + 1) * M;
-            {
-                // index words are fetched 8 at a time so the (rare) matching rows do not serialise the scan
-                int m = grp;
-                for (; m + 112 < M; m += 128) {
-                    int id[8];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) id[u] = ik[m + 16 * u];
-#pragma unroll
-                    for (int u = 0; u < 8; ++u)
-                        if (id[u] == rr) acc += dP[(size_t)(m + 16 * u) * PW + k * TH + d];
-                }
-                for (; m < M; m += 16)
-                    if (ik[m] == rr) acc += dP[(size_t)m * PW + k * TH + d];
-            }
-            if (k == 2)
-                for (int b = grp; b < B; b += 16)
-                    if (ctx[b] == rr) acc += dCT[(size_t)b * 2 * TH + d];
-            if (k == 3)
-                for (int b = grp; b < B; b += 16)
-                    if (ctx[B + b] == rr) acc += dCT[(size_t)b * 2 * TH + TH + d];
-            for (int b = grp; b < B; b += 16) acc = fmaf(dTq[(size_t)b * NB + r], a_pt[(size_t)b * PW + k * TH + d], acc);
+            for (int j = grp; j < nchunk; j += 4) acc += part[(size_t)j * TG_PART_FLOATS + (size_t)r * TH + d];
+            // scoring side: d/d clip(table)[r] of sum_b Tq[b,r] = sum_b dTq[b,r] a_pt[b, 64k:64k+64]
+            for (int b = grp; b < B; b += 4) acc = fmaf(dTq[(size_t)b * NB + r], a_pt[(size_t)b * PW + k * TH + d], acc);
         } else {
             const int rr = r - NB;
             x = dur + (size_t)rr * TH;
             g = g_dur + (size_t)rr * TH;
-            const int32_t* ik = idx + (size_t)6 * M;
-            int m = grp;
-            for (; m + 112 < M; m += 128) {
-                int id[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) id[u] = ik[m + 16 * u];
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    if (id[u] == rr) acc += dD[(size_t)(m + 16 * u) * TH + d];
-            }
-            for (; m < M; m += 16)
-                if (ik[m] == rr) acc += dD[(size_t)m * TH + d];
+            for (int j = grp; j < nchunk; j += 4)
+                acc += part[(size_t)j * TG_PART_FLOATS + TG_BIN_FLOATS + (size_t)rr * TH + d];
         }
         s_acc[threadIdx.x] = acc;
         __syncthreads();
-        if (threadIdx.x < 64) {
-            float t = 0.f;
-            for (int i = 0; i < 16; ++i) t += s_acc[i * 64 + threadIdx.x];
-            s_g[threadIdx.x] = t;
-        }
+        if (threadIdx.x < 64)
+            s_g[threadIdx.x] = (s_acc[threadIdx.x] + s_acc[64 + threadIdx.x]) + (s_acc[128 + threadIdx.x] + s_acc[192 + threadIdx.x]);
     }
     __syncthreads();
     const int c = threadIdx.x;
@@ -770,11 +790,20 @@ extern "C" int tcar_small_table_grads(const int32_t* idx, const int32_t* ctx, co
                                       const float* pos, const float* month, const float* day, const float* week,
                                       const float* hour, const float* minute, const float* dur, float* g_pos,
                                       float* g_month, float* g_day, float* g_week, float* g_hour, float* g_minute,
-                                      float* g_dur, int B, int T, void* stream) {
-    if (B < 1 || T < 1 || T > TCAR_MAXT) return TCAR_ERR_ARG;
-    small_table_grads_kernel<<<TCAR_MAXT + NB + 11, 1024, 0, STREAM>>>(
-        idx, ctx, dXi, dP, dD, dCT, dTq, a_pt, pos, month, day, week, hour, minute, dur, g_pos, g_month, g_day,
-        g_week, g_hour, g_minute, g_dur, B, T);
+                                      float* g_dur, float* part, int B, int T, void* stream) {
+    if (B < 1 || T < 1 || T > TCAR_MAXT || !part) return TCAR_ERR_ARG;
+    const int M = B * T;
+    int nchunk = (M + 31) / 32;                      // >= 32 clicks per chunk
+    if (nchunk > TG_MAX_CHUNKS) nchunk = TG_MAX_CHUNKS;
+    const int smem = TG_PART_FLOATS * 4;
+    cudaError_t e = cudaFuncSetAttribute(table_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return (int)e;
+    table_partial_kernel<<<nchunk, TG_THREADS, smem, STREAM>>>(idx, ctx, dXi, dP, dD, dCT, part, B, T);
+    int rc = LAUNCH_RC();
+    if (rc) return rc;
+    table_finish_kernel<<<TCAR_MAXT + NB + 11, 256, 0, STREAM>>>(part, nchunk, dTq, a_pt, pos, month, day, week, hour,
+                                                                  minute, dur, g_pos, g_month, g_day, g_week, g_hour,
+                                                                  g_minute, g_dur, B, T);
     return LAUNCH_RC();
 }
 

@@ -86,6 +86,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
+                                            int32_t c1, int32_t c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 // Same, multicast to every CTA of the cluster whose bit is set in `mask` (same smem / mbarrier offsets).
 __device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
                                                   int32_t c1, uint16_t mask) {
@@ -209,6 +217,18 @@ __device__ __forceinline__ uint64_t sdesc_kmajor(uint32_t saddr) { return make_s
 // apart (LBO) -- i.e. one TMA box [64 mn x BK k] per MN atom.
 __device__ __forceinline__ uint64_t sdesc_mnmajor(uint32_t saddr, uint32_t mn_atom_bytes) {
     return make_sdesc_sw128(saddr, mn_atom_bytes, 1024);
+}
+
+// No-swizzle ("interleaved") canonical layouts: 8 x 16-byte core matrices stored contiguously (128 B each).
+//   K-major : core matrices `lbo` bytes apart along K, `sbo` bytes apart along M/N
+//   MN-major: core matrices `sbo` bytes apart along M/N, `lbo` bytes apart along K
+__device__ __forceinline__ uint64_t make_sdesc_nosw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFFu);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    return d;
 }
 
 // Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.

@@ -109,6 +109,7 @@ class Seq2SeqAttNN:
         self.entry_slot = torch.zeros(self.hash_size // 2, device=dev, dtype=torch.int32)
         self.slot_sq = f(self.hash_size)
         self.sq_partial = f(256)
+        self.table_part = f(148 * 19600)            # TCAR_TABLE_GRAD_CHUNKS x TCAR_TABLE_GRAD_PART
         self.top_ids = torch.zeros(Bm, TOPK, device=dev, dtype=torch.int32)
         self.top_scores = f(Bm, TOPK)
         self.n_greater = torch.zeros(Bm, device=dev, dtype=torch.int32)
@@ -266,10 +267,10 @@ class Seq2SeqAttNN:
             pr([(self.CT, 2 * TH, 1, self.dh1, None, HPp, 1, B)], 2 * TH, H, g["Wq1"], H, splits=ksp,
                part=self._part(2 * TH, H, ksp)),
             pr([(self.dh1, HPp, 0, wh["Wq1"], None, 256, 0, H)], B, 2 * TH, self.dCT, 2 * TH)])
-        nv.counted_call("tcar_small_table_grads", 1, p(bt.idx), p(bt.ctx), p(self.dXi), p(self.dP), p(self.dD),
+        nv.counted_call("tcar_small_table_grads", 2, p(bt.idx), p(bt.ctx), p(self.dXi), p(self.dP), p(self.dD),
                         p(self.dCT), p(self.dTq), p(self.a_pt), p(w["pos"]), p(w["month"]), p(w["day"]),
                         p(w["week"]), p(w["hour"]), p(w["minute"]), p(w["dur"]), p(g["pos"]), p(g["month"]),
-                        p(g["day"]), p(g["week"]), p(g["hour"]), p(g["minute"]), p(g["dur"]), B, T)
+                        p(g["day"]), p(g["week"]), p(g["hour"]), p(g["minute"]), p(g["dur"]), p(self.table_part), B, T)
         entries = B * T + B + B * bt.Nn
         if 2 * entries > self.hash_size:
             raise ValueError("batch too large for the sparse-gradient scratch")

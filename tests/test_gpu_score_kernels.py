@@ -15,6 +15,15 @@ pytestmark = pytest.mark.gpu
 KEXT, QROWS = 640, 512
 
 
+def e_to_blocked(E):
+    """logical [512, n_pad] -> stored [n_pad/8][512][8] (include/tcar_b200.h, tcar_score_fwd)."""
+    return E.view(QROWS, -1, 8).permute(1, 0, 2).contiguous()
+
+
+def e_from_blocked(Eb, n_pad):
+    return Eb.view(n_pad // 8, QROWS, 8).permute(1, 0, 2).reshape(QROWS, n_pad)
+
+
 def _mk(B, N, seed):
     g = torch.Generator(device="cuda").manual_seed(seed)
     n_pad = (N + 255) // 256 * 256
@@ -34,7 +43,7 @@ def _fwd(native, Q, I, c, B, N, n_pad, mode, cluster):
     native.call("tcar_score_fwd", native.ptr(Q), native.ptr(I), native.ptr(c), native.ptr(E), native.ptr(part),
                 native.ptr(cm), B, N, n_pad, mode, cluster)
     torch.cuda.synchronize()
-    return E, part, cm
+    return (e_from_blocked(E, n_pad) if E is not None else None), part, cm
 
 
 @pytest.mark.parametrize("cluster", [1, 2, 4, -2])
@@ -83,7 +92,8 @@ def test_score_bwd_q(native, B, N):
     splits = native.lib().tcar_score_bwd_q_splits(B, n_pad)
     part = torch.zeros(splits, QROWS, KEXT, device="cuda")
     dq = torch.zeros(QROWS, KEXT, device="cuda")
-    native.call("tcar_score_bwd_q", native.ptr(E), native.ptr(I), native.ptr(part), native.ptr(dq), B, n_pad)
+    native.call("tcar_score_bwd_q", native.ptr(e_to_blocked(E)), native.ptr(I), native.ptr(part), native.ptr(dq), B,
+                n_pad)
     torch.cuda.synchronize()
     ref = (E[:B].double() @ I.double()).float()
     scale = ref.abs().max().item()
@@ -104,7 +114,8 @@ def test_score_bwd_i(native, B, N):
     gi = torch.full((N + 1, 256), float("nan"), device="cuda")
     gi[0] = 0
     sqp = torch.full((native.lib().tcar_score_bwd_i_ctas(n_pad),), float("nan"), device="cuda")
-    native.call("tcar_score_bwd_i", native.ptr(E), native.ptr(Qs), native.ptr(gi), native.ptr(sqp), B, N, n_pad)
+    native.call("tcar_score_bwd_i", native.ptr(e_to_blocked(E)), native.ptr(Qs), native.ptr(gi), native.ptr(sqp), B, N,
+                n_pad)
     torch.cuda.synchronize()
     ref = (E[:B, :N].double().t() @ Qs[:B].double()).float()
     scale = ref.abs().max().item()
