@@ -499,7 +499,7 @@ score_bwd_q_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_const
                 mbar_expect_tx(&full[stage], Q_STAGE);
                 uint8_t* sa = smem + stage * Q_STAGE;
                 uint8_t* sb = sa + Q_A_STAGE;
-                tma_load_3d(sa, &map_e, &full[stage], 0, mtile * BM, kb * (BK / 8));
+                tma_load_3d(sa, &map_e, &full[stage], 0, mtile * (BM / 8), kb * (BK / 8));
 #pragma unroll
                 for (int j = 0; j < Q_CH / 64; ++j)
                     tma_load_2d(sb + j * 8192, &map_i, &full[stage], chalf * Q_CH + j * 64, kb * BK);
@@ -644,7 +644,7 @@ score_bwd_i_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_const
                     mbar_wait(&empty[stage], phase ^ 1);
                     mbar_expect_tx(&full[stage], I_A_STAGE);
                     uint8_t* sa = smem_a + stage * I_A_STAGE;
-                    tma_load_3d(sa, &map_e, &full[stage], 0, kb * BK, n0 / 8);
+                    tma_load_3d(sa, &map_e, &full[stage], 0, kb * (BK / 8), n0 / 8);
                     if (++stage == I_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -760,15 +760,17 @@ static int make_map_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64
     return r == CUDA_SUCCESS ? 0 : TCAR_ERR_TENSORMAP;
 }
 
-// E in its block-of-8-items layout [n_pad/8][512][8] bf16 as a 3-D tensor (8 items | session row | item block); the
-// box (8, box_rows sessions, box_blocks item blocks) lands in shared memory, unswizzled, as
+// E in its block-of-8-items layout [n_pad/8][512][8] bf16 as a 3-D tensor (8 sessions x 8 items | session group |
+// item block); the box (64, box_rows / 8, box_blocks) lands in shared memory, unswizzled, as
 // [box_blocks][box_rows][8 items].
 static int make_map_e(CUtensorMap* m, const void* base, uint64_t n_pad, uint32_t box_rows, uint32_t box_blocks) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return TCAR_ERR_DRIVER;
-    cuuint64_t dims[3] = {8, (cuuint64_t)QROWS, n_pad / 8};
-    cuuint64_t strides[2] = {16, (cuuint64_t)QROWS * 16};
-    cuuint32_t box[3] = {8, box_rows, box_blocks};
+    // 8 consecutive session rows of one item block are 128 contiguous bytes (one UMMA core matrix): use that as the
+    // innermost TMA dimension (a 16-byte inner dimension makes the copy engine crawl)
+    cuuint64_t dims[3] = {64, (cuuint64_t)QROWS / 8, n_pad / 8};
+    cuuint64_t strides[2] = {128, (cuuint64_t)QROWS * 16};
+    cuuint32_t box[3] = {64, box_rows / 8, box_blocks};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
