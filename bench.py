@@ -254,11 +254,11 @@ def kernel_rooflines(torch, nv, model, bt, peaks, traffic):
     w = ps.w
     specs = [
         ("score_fwd_train", "tensor", 2.0 * B * N * K_REF,
-         lambda: nv.call("tcar_score_fwd", p(model.Q), p(ps.iext), p(model.c_ref), p(ws["E"]), p(ws["part"]), None, B,
-                         N, ps.n_pad, 0, cl)),
+         lambda: nv.call("tcar_score_fwd", p(model.Q), p(ps.iext), p(model.c_ref), p(ws["E"]), p(ws["part"]), None, None,
+                         B, N, ps.n_pad, 0, cl)),
         ("score_fwd_eval", "tensor", 2.0 * B * N * K_REF,
          lambda: nv.call("tcar_score_fwd", p(model.Q), p(ps.iext), p(model.c_ref), None, p(wse["part"]),
-                         p(wse["cmax"]), B, N, ps.n_pad, 1, cl)),
+                         p(wse["cmax"]), p(wse["tmax"]), B, N, ps.n_pad, 1, cl)),
         ("score_bwd_q", "tensor", 2.0 * B * N * K_REF,
          lambda: nv.call("tcar_score_bwd_q", p(ws["E"]), p(ps.iext), p(ws["qpart"]), p(model.dq_raw), B, ps.n_pad)),
         ("score_bwd_i", "tensor", 2.0 * B * N * K_DITEM,
@@ -267,7 +267,7 @@ def kernel_rooflines(torch, nv, model, bt, peaks, traffic):
         # reads p, m, v, g and writes p, m, v (7 x 250 floats per row) + the bf16 refresh of the scoring operand
         ("adam_item", "hbm", (N + 1) * (7.0 * 250 * 4 + 250 * 2),
          lambda: nv.call("tcar_adam_item", p(ps.item), p(ps.item_m), p(ps.item_v), p(ps.item_g), p(ps.sqnorm_item),
-                         p(ps.step), 0.0, model.max_grad_f, p(ps.iext), N)),
+                         p(ps.step), 0.0, model.max_grad_f, p(ps.iext), 0, N + 1)),
         ("sqnorm_item_grad", "hbm", (N + 1) * 250 * 4.0,
          lambda: nv.call("tcar_sqnorm_big", p(ps.item_g), p(ps.norm_partial), p(ps.sqnorm_item), ps.item_g.numel())),
         # table rows read + X/P/D/CT written + the index words
@@ -286,6 +286,11 @@ def kernel_rooflines(torch, nv, model, bt, peaks, traffic):
                          p(model.coef), p(ps.item), p(ps.item_g), p(model.hash_keys), p(model.hash_cnt),
                          p(model.hash_acc), p(model.entry_slot), p(model.slot_sq), model.hash_size, B, T, Nn)),
     ]
+    # eval top-k: reads tilemax [B, n_pad/128] + 512 chunk maxima and re-scores 256 candidates x 2 KB of fp32 rows
+    specs.append(("eval_topk", "hbm", B * (ps.n_pad / 128 + 512) * 4.0 + B * 256 * 2 * 250 * 4.0,
+                  lambda: nv.call("tcar_eval_topk", p(wse["cmax"]), p(wse["tmax"]), p(model.a_ic), p(model.Tq), p(ps.item),
+                                  p(ps.content), p(ps.mwdhm), p(bt.label), p(model.top_ids), p(model.top_scores),
+                                  p(model.n_greater), B, N, ps.n_pad, 0)))
     out = {}
     for name, bound, work, fn in specs:
         ms = time_kernel(torch, fn, 10, flush)

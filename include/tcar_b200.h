@@ -89,12 +89,15 @@ int tcar_build_query(const float* a_ic, const float* a_pt, const float* ct_tab, 
  *   mode 0 (train): E = exp(S - c_ref) in bf16, logically [512, n_pad], stored in blocks of 8 items:
  *                   E[b, n] at element ((n / 8) * 512 + b) * 8 + n % 8 (coalesced epilogue stores; the backward
  *                   kernels read it through a 3-D tensor map); rowsum_part [n_pad/128][512]
- *   mode 1 (eval) : chunkmax [512, n_pad/8] fp32 = max of S over 8 consecutive items, rowsum_part as above
+ *   mode 1 (eval) : chunkmax [512, n_pad/8] fp32 = max of S over 8 consecutive items, tilemax [512, n_pad/128]
+ *                   fp32 = max over 128 consecutive items (first selection level of tcar_eval_topk), rowsum_part
+ *                   as above
  *   cluster in {1,2,4}: CTAs per cluster sharing each item tile by TMA multicast (one 128x128 UMMA per CTA);
  *   cluster == TCAR_CLUSTER_PAIR: CTA pairs issuing 256x256 cta_group::2 UMMAs, each CTA streaming half of every
  *   item tile (the production configuration: twice the pipeline depth per byte of shared memory). */
 int tcar_score_fwd(const void* q_bf16, const void* iext_bf16, const float* c_ref, void* e_out, float* rowsum_part,
-                   float* chunkmax, int n_rows, int n_items, int n_pad, int mode, int cluster, void* stream);
+                   float* chunkmax, float* tilemax, int n_rows, int n_items, int n_pad, int mode, int cluster,
+                   void* stream);
 int tcar_score_fwd_tiles(int n_pad);
 
 /* (4a) softmax cross-entropy from the partial sums (model_combine.py:145): sumexp[b] = sum_tiles part,
@@ -210,16 +213,21 @@ int tcar_sqnorm_combine(const float* a, int na, const float* b, int nb, float* o
  *      theta -= lr_t m / (sqrt(v) + eps).  `step` [1] int32 on device holds t (already incremented). */
 int tcar_adam_small(float* theta, float* m, float* v, const float* g, const int32_t* seg_off, const float* sqnorm,
                     int nseg, const int32_t* step, float lr, float max_grad, void* stream);
-/* item table [N+1,256]: also refreshes the item columns of Iext (bf16) in the same pass. */
+/* item table rows [row0, row0 + nrows) of [N+1,256] (the pointers address the first row of the slice; iext is the
+ * whole operand): also refreshes the item columns of Iext (bf16) in the same pass.  Whole table: row0 = 0,
+ * nrows = N + 1; data-parallel training updates one contiguous slice per rank (parallel.py). */
 int tcar_adam_item(float* item, float* m, float* v, const float* g, const float* sqnorm, const int32_t* step,
-                   float lr, float max_grad, void* iext_bf16, int N, void* stream);
+                   float lr, float max_grad, void* iext_bf16, int row0, int nrows, void* stream);
+/* item columns of Iext from the fp32 item table (after all-gathering slices updated by other ranks). */
+int tcar_refresh_iext_items(const float* item, void* iext_bf16, int N, void* stream);
 
-/* (6) evaluation (model_combine.py:283-306, util.py:8-18): select the 32 best chunks per query from chunkmax,
- *     re-score their 256 items exactly in fp32, return top-20 ids/scores ordered by (score desc, id asc) and
+/* (6) evaluation (model_combine.py:283-306, util.py:8-18): select the 32 best 128-item tiles per query from tilemax,
+ *     then the 32 best 8-item chunks among their 512 chunks from chunkmax (exactly the 32 best chunks overall, ties
+ *     to the lower index), re-score their 256 items exactly in fp32, return top-20 ids/scores ordered by (score desc, id asc) and
  *     n_greater[b] = #candidates scoring strictly above the label (rank-1 whenever rank <= 20).
  *     chunkmax covers the N local items of this catalog shard; item/content/mwdhm are the GLOBAL fp32 tables,
  *     label holds global 0-based ids and item_offset is the global id of local item 0. */
-int tcar_eval_topk(const float* chunkmax, const float* a_ic, const float* Tq, const float* item,
+int tcar_eval_topk(const float* chunkmax, const float* tilemax, const float* a_ic, const float* Tq, const float* item,
                    const float* content, const int32_t* mwdhm, const int32_t* label, int32_t* top_ids,
                    float* top_scores, int32_t* n_greater, int B, int N, int n_pad, int item_offset, void* stream);
 

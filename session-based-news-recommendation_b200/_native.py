@@ -23,7 +23,7 @@ SIGNATURES = {
     "tcar_build_iext": [_P] * 4 + [_I, _I, _P],
     "tcar_clip_time_tables": [_P] * 7 + [_P],
     "tcar_build_query": [_P] * 10 + [_I, _P],
-    "tcar_score_fwd": [_P] * 6 + [_I] * 5 + [_P],
+    "tcar_score_fwd": [_P] * 7 + [_I] * 5 + [_P],
     "tcar_score_fwd_tiles": [_I],
     "tcar_ce_finish": [_P] * 3 + [_I, _I, _P],
     "tcar_neg_loss": [_P] * 9 + [_I, _I, _P],
@@ -44,8 +44,9 @@ SIGNATURES = {
     "tcar_sqnorm_segments": [_P] * 3 + [_I, _P],
     "tcar_sqnorm_big": [_P] * 3 + [_LL, _P],
     "tcar_adam_small": [_P] * 6 + [_I, _P, _F, _F, _P],
-    "tcar_adam_item": [_P] * 6 + [_F, _F, _P, _I, _P],
-    "tcar_eval_topk": [_P] * 10 + [_I] * 4 + [_P],
+    "tcar_adam_item": [_P] * 6 + [_F, _F, _P, _I, _I, _P],
+    "tcar_refresh_iext_items": [_P, _P, _I, _P],
+    "tcar_eval_topk": [_P] * 11 + [_I] * 4 + [_P],
     "tcar_topk_merge": [_P] * 4 + [_I, _I, _P],
 }
 

@@ -56,82 +56,127 @@ __device__ __forceinline__ bool before(float sa, int ia, float sb, int ib) {
     return sa > sb || (sa == sb && ia < ib);
 }
 
-// one CTA (256 threads) per query
+// Block-wide selection of the NCH largest of vals[0..n) (n > NCH) by (value desc, index asc): 4 x 8-bit radix passes
+// on the order-preserving key find the NCH-th largest key, then strictly-greater entries are taken in any order and
+// equal-key entries lowest index first.  256 threads; s_sel receives NCH indices.
+__device__ __forceinline__ void select_top(const float* __restrict__ vals, int n, int* s_sel, int* s_hist, int* s_warp,
+                                           int* s_misc /* [4]: cnt, need, digit, above */) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    uint32_t prefix = 0, mask = 0;
+    int kth = NCH;
+    if (tid == 0) s_misc[0] = 0;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        s_hist[tid] = 0;
+        __syncthreads();
+        for (int i = tid; i < n; i += 256) {
+            const uint32_t k = fkey(vals[i]);
+            if ((k & mask) == prefix) atomicAdd(&s_hist[(k >> shift) & 255u], 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int above = 0, d = 255;
+            for (; d > 0; --d) {
+                if (above + s_hist[d] >= kth) break;
+                above += s_hist[d];
+            }
+            s_misc[2] = d;
+            s_misc[3] = above;
+        }
+        __syncthreads();
+        prefix |= (uint32_t)s_misc[2] << shift;
+        mask |= 255u << shift;
+        kth -= s_misc[3];
+        __syncthreads();
+    }
+    // prefix = key of the NCH-th largest; kth = how many keys equal to it are still needed
+    for (int i = tid; i < n; i += 256)
+        if (fkey(vals[i]) > prefix) s_sel[atomicAdd(&s_misc[0], 1)] = i;
+    __syncthreads();
+    int base = s_misc[0];
+    __syncthreads();
+    for (int i0 = 0; i0 < n && base < NCH; i0 += 256) {
+        const int i = i0 + tid;
+        const bool eq = i < n && fkey(vals[i]) == prefix;
+        const uint32_t bal = __ballot_sync(0xffffffffu, eq);
+        if (lane == 0) s_warp[w] = __popc(bal);
+        __syncthreads();
+        int off = base;
+        for (int j = 0; j < w; ++j) off += s_warp[j];
+        int tot = 0;
+        for (int j = 0; j < 8; ++j) tot += s_warp[j];
+        const int pos = off + __popc(bal & ((1u << lane) - 1u));
+        if (eq && pos < NCH) s_sel[pos] = i;
+        base += tot;
+        __syncthreads();
+    }
+    __syncthreads();
+}
+
+constexpr int TILE_CH = 128 / CH;          // 16 chunks per 128-item tile
+constexpr int NCC = NCH * TILE_CH;         // 512 candidate chunks after the tile-level selection
+
+// one CTA (256 threads) per query.  Two-level selection: the 32 best 128-item tiles by tile max (every one of the 32
+// best chunks lives in one of them: the 32 largest tile maxima are 32 distinct chunk values, so the 32nd largest chunk
+// is >= the 32nd largest tile max), then the 32 best of their 512 chunks, then the exact fp32 re-scoring.
 __global__ void __launch_bounds__(256)
-eval_topk_kernel(const float* __restrict__ chunkmax, const float* __restrict__ a_ic, const float* __restrict__ Tq,
-                 const float* __restrict__ item, const float* __restrict__ content,
+eval_topk_kernel(const float* __restrict__ chunkmax, const float* __restrict__ tilemax, const float* __restrict__ a_ic,
+                 const float* __restrict__ Tq, const float* __restrict__ item, const float* __restrict__ content,
                  const int32_t* __restrict__ mwdhm, const int32_t* __restrict__ label, int32_t* __restrict__ top_ids,
                  float* __restrict__ top_scores, int32_t* __restrict__ n_greater, int N, int n_pad, int item_offset) {
     __shared__ float s_aic[XW], s_tq[NB + 1];
     __shared__ int s_hist[256];
     __shared__ int s_sel[NCH];
-    __shared__ int s_cnt, s_need, s_digit, s_above;
+    __shared__ int s_misc[4];
+    __shared__ float s_cv[NCC];
+    __shared__ int s_ci[NCC];
     __shared__ float s_sc[NCAND];
     __shared__ int s_id[NCAND];
     __shared__ int s_warp[8];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int nchunks = (N + CH - 1) / CH;
+    const int ntiles = (N + 127) / 128;
     const float* cm = chunkmax + (size_t)b * (n_pad / CH);
+    const float* tm = tilemax + (size_t)b * (n_pad / 128);
     for (int c = tid; c < XW; c += 256) s_aic[c] = a_ic[(size_t)b * XW + c];
     for (int c = tid; c < NB; c += 256) s_tq[c] = Tq[(size_t)b * NB + c];
     for (int i = tid; i < NCH; i += 256) s_sel[i] = -1;
-    if (tid == 0) s_cnt = 0;
     __syncthreads();
 
-    if (nchunks <= NCH) {
-        for (int i = tid; i < nchunks; i += 256) s_sel[i] = i;
-    } else {
-        // radix select (4 x 8 bits, MSB first) of the NCH-th largest key
-        uint32_t prefix = 0, mask = 0;
-        int kth = NCH;
-        for (int shift = 24; shift >= 0; shift -= 8) {
-            s_hist[tid] = 0;
+    if (nchunks > NCH) {
+        // ---- level 1: tiles
+        if (ntiles <= NCH) {
+            for (int i = tid; i < ntiles; i += 256) s_sel[i] = i;
             __syncthreads();
-            for (int i = tid; i < nchunks; i += 256) {
-                const uint32_t k = fkey(cm[i]);
-                if ((k & mask) == prefix) atomicAdd(&s_hist[(k >> shift) & 255u], 1);
-            }
-            __syncthreads();
-            if (tid == 0) {
-                int above = 0, d = 255;
-                for (; d > 0; --d) {
-                    if (above + s_hist[d] >= kth) break;
-                    above += s_hist[d];
+        } else {
+            select_top(tm, ntiles, s_sel, s_hist, s_warp, s_misc);
+        }
+        // ---- level 2: the 16 chunks of every selected tile, sorted by (max desc, chunk index asc)
+        for (int i = tid; i < NCC; i += 256) {
+            const int tile = s_sel[i / TILE_CH];
+            const int chunk = tile * TILE_CH + (i % TILE_CH);
+            const bool ok = tile >= 0 && chunk < nchunks;
+            s_cv[i] = ok ? cm[chunk] : -INFINITY;
+            s_ci[i] = ok ? chunk : 0x7fffffff;
+        }
+        for (int k = 2; k <= NCC; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                __syncthreads();
+                for (int i = tid; i < NCC; i += 256) {
+                    const int ixj = i ^ j;
+                    if (ixj > i) {
+                        const float sa = s_cv[i], sb = s_cv[ixj];
+                        const int ia = s_ci[i], ib = s_ci[ixj];
+                        const bool up = (i & k) == 0;
+                        const bool swap = up ? before(sb, ib, sa, ia) : before(sa, ia, sb, ib);
+                        if (swap) { s_cv[i] = sb; s_cv[ixj] = sa; s_ci[i] = ib; s_ci[ixj] = ia; }
+                    }
                 }
-                s_digit = d;
-                s_above = above;
             }
-            __syncthreads();
-            prefix |= (uint32_t)s_digit << shift;
-            mask |= 255u << shift;
-            kth -= s_above;
-            __syncthreads();
         }
-        // prefix = key of the NCH-th largest; kth = how many keys equal to it are still needed
-        if (tid == 0) s_need = kth;
         __syncthreads();
-        // strictly greater: any order (candidates are sorted afterwards)
-        for (int i = tid; i < nchunks; i += 256)
-            if (fkey(cm[i]) > prefix) s_sel[atomicAdd(&s_cnt, 1)] = i;
-        __syncthreads();
-        // equal keys: lowest chunk index first (ordered block scan)
-        int base = s_cnt;
-        __syncthreads();
-        for (int i0 = 0; i0 < nchunks && base < NCH; i0 += 256) {
-            const int i = i0 + tid;
-            const bool eq = i < nchunks && fkey(cm[i]) == prefix;
-            const uint32_t bal = __ballot_sync(0xffffffffu, eq);
-            if (lane == 0) s_warp[w] = __popc(bal);
-            __syncthreads();
-            int off = base;
-            for (int j = 0; j < w; ++j) off += s_warp[j];
-            int tot = 0;
-            for (int j = 0; j < 8; ++j) tot += s_warp[j];
-            const int pos = off + __popc(bal & ((1u << lane) - 1u));
-            if (eq && pos < NCH) s_sel[pos] = i;
-            base += tot;
-            __syncthreads();
-        }
+        if (tid < NCH) s_sel[tid] = s_ci[tid] == 0x7fffffff ? -1 : s_ci[tid];
+    } else {
+        for (int i = tid; i < nchunks; i += 256) s_sel[i] = i;
     }
     __syncthreads();
 
@@ -228,12 +273,13 @@ topk_merge_kernel(const int32_t* __restrict__ ids, const float* __restrict__ sco
 using namespace tcar;
 #define STREAM static_cast<cudaStream_t>(stream)
 
-extern "C" int tcar_eval_topk(const float* chunkmax, const float* a_ic, const float* Tq, const float* item,
+extern "C" int tcar_eval_topk(const float* chunkmax, const float* tilemax, const float* a_ic, const float* Tq,
+                              const float* item,
                               const float* content, const int32_t* mwdhm, const int32_t* label, int32_t* top_ids,
                               float* top_scores, int32_t* n_greater, int B, int N, int n_pad, int item_offset,
                               void* stream) {
-    if (B < 1 || B > TCAR_QROWS || N < 1 || n_pad < N) return TCAR_ERR_ARG;
-    eval_topk_kernel<<<B, 256, 0, STREAM>>>(chunkmax, a_ic, Tq, item, content, mwdhm, label, top_ids, top_scores,
+    if (B < 1 || B > TCAR_QROWS || N < 1 || n_pad < N || !tilemax) return TCAR_ERR_ARG;
+    eval_topk_kernel<<<B, 256, 0, STREAM>>>(chunkmax, tilemax, a_ic, Tq, item, content, mwdhm, label, top_ids, top_scores,
                                             n_greater, N, n_pad, item_offset);
     return (int)cudaGetLastError();
 }

@@ -73,6 +73,21 @@ sqnorm_segments_kernel(const float* __restrict__ flat, const int32_t* __restrict
     }
 }
 
+// item columns of Iext from the fp32 item table (rows owned by OTHER ranks after the sharded Adam + all-gather)
+__global__ void __launch_bounds__(256)
+refresh_iext_items_kernel(const float4* __restrict__ item, __nv_bfloat16* __restrict__ iext, long long n4) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i >> 6;
+        const int c = (int)(i & 63) * 4;
+        if (row >= 1 && c < H) {
+            const float4 p = item[i];
+            __nv_bfloat16* dst = iext + (size_t)(row - 1) * KEXT + c;
+            *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(p.x, p.y);
+            if (c + 2 < H) *reinterpret_cast<__nv_bfloat162*>(dst + 2) = __floats2bfloat162_rn(p.z, p.w);
+        }
+    }
+}
+
 constexpr int kNormBlocks = 1184;  // 8 x 148 SMs
 __global__ void __launch_bounds__(256)
 sqnorm_big_partial_kernel(const float4* __restrict__ x, float* __restrict__ partial, long long n4) {
@@ -176,7 +191,7 @@ adam_small_kernel(float* __restrict__ theta, float* __restrict__ m, float* __res
 __global__ void __launch_bounds__(256)
 adam_item_kernel(float4* __restrict__ item, float4* __restrict__ m, float4* __restrict__ v,
                  const float4* __restrict__ g, const float* __restrict__ sqnorm, const int32_t* __restrict__ step,
-                 float lr, float max_grad, __nv_bfloat16* __restrict__ iext, long long n4) {
+                 float lr, float max_grad, __nv_bfloat16* __restrict__ iext, long long n4, long long row0) {
     const float cf = clip_factor(sqnorm[0], max_grad);
     const float lr_t = adam_lr_t(step[0], lr);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -187,7 +202,7 @@ adam_item_kernel(float4* __restrict__ item, float4* __restrict__ m, float4* __re
         adam_update(p.z, mm.z, vv.z, gg.z * cf, lr_t);
         adam_update(p.w, mm.w, vv.w, gg.w * cf, lr_t);
         item[i] = p; m[i] = mm; v[i] = vv;
-        const long long row = i >> 6;            // 64 float4 per 256-float row
+        const long long row = row0 + (i >> 6);   // 64 float4 per 256-float row; row0 = first row of this slice
         const int c = (int)(i & 63) * 4;
         if (row >= 1 && c < H) {
             __nv_bfloat16* dst = iext + (size_t)(row - 1) * KEXT + c;
@@ -227,6 +242,14 @@ extern "C" int tcar_sqnorm_big(const float* x, float* partial, float* sqnorm, lo
     return (int)cudaGetLastError();
 }
 
+extern "C" int tcar_refresh_iext_items(const float* item, void* iext_bf16, int N, void* stream) {
+    if (N < 1) return TCAR_ERR_ARG;
+    refresh_iext_items_kernel<<<148 * 16, 256, 0, STREAM>>>(reinterpret_cast<const float4*>(item),
+                                                            static_cast<__nv_bfloat16*>(iext_bf16),
+                                                            (long long)(N + 1) * (HP / 4));
+    return (int)cudaGetLastError();
+}
+
 extern "C" int tcar_sqnorm_combine(const float* a, int na, const float* b, int nb, float* out, void* stream) {
     if (na < 0 || nb < 0 || (nb & 3) || !out) return TCAR_ERR_ARG;
     sqnorm_combine_kernel<<<1, 1024, 0, STREAM>>>(a, na, reinterpret_cast<const float4*>(b), nb / 4, out);
@@ -242,12 +265,13 @@ extern "C" int tcar_adam_small(float* theta, float* m, float* v, const float* g,
 }
 
 extern "C" int tcar_adam_item(float* item, float* m, float* v, const float* g, const float* sqnorm,
-                              const int32_t* step, float lr, float max_grad, void* iext_bf16, int N, void* stream) {
-    if (N < 1) return TCAR_ERR_ARG;
-    const long long n4 = (long long)(N + 1) * (HP / 4);
+                              const int32_t* step, float lr, float max_grad, void* iext_bf16, int row0, int nrows,
+                              void* stream) {
+    if (row0 < 0 || nrows < 1) return TCAR_ERR_ARG;
+    const long long n4 = (long long)nrows * (HP / 4);
     adam_item_kernel<<<148 * 16, 256, 0, STREAM>>>(reinterpret_cast<float4*>(item), reinterpret_cast<float4*>(m),
                                                    reinterpret_cast<float4*>(v), reinterpret_cast<const float4*>(g),
                                                    sqnorm, step, lr, max_grad,
-                                                   static_cast<__nv_bfloat16*>(iext_bf16), n4);
+                                                   static_cast<__nv_bfloat16*>(iext_bf16), n4, (long long)row0);
     return (int)cudaGetLastError();
 }

@@ -45,6 +45,7 @@ struct FwdParams {
     __nv_bfloat16* E;       // [512, e_pitch] (train) or nullptr
     float* rowsum_part;     // [n_tiles, 512]
     float* chunkmax;        // [512, e_pitch/8] (eval) or nullptr
+    float* tilemax;         // [512, e_pitch/128] (eval, nullable): max of S over each 128 consecutive items
     const float* c_ref;     // [512] reference score per row (exp argument shift)
     int n_items;            // valid items N
     int n_tiles;            // ceil(Npad / F_BN)
@@ -171,7 +172,7 @@ score_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             const int n0 = tile * F_BN;
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
-            float psum = 0.f;
+            float psum = 0.f, tmax = -INFINITY;
             const bool tail = n0 + F_BN > p.n_items;
 #pragma unroll 1
             for (int ch = 0; ch < F_BN / 32; ++ch) {
@@ -214,6 +215,7 @@ score_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                             mx = ok ? fmaxf(mx, s) : mx;
                         }
                         mm[g] = mx;
+                        tmax = fmaxf(tmax, mx);
                     }
                     if (row_ok)
                         *reinterpret_cast<float4*>(p.chunkmax + (size_t)row * (p.e_pitch / 8) + nb / 8) = m;
@@ -224,6 +226,7 @@ score_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[acc]);
             if (row_ok) p.rowsum_part[(size_t)tile * QROWS + row] = psum;
+            if (row_ok && p.mode == 1 && p.tilemax) p.tilemax[(size_t)row * (p.e_pitch / 128) + tile] = tmax;
         }
     }
 
@@ -251,7 +254,7 @@ constexpr int P_SMEM = F_A_BYTES + P_STAGES * P_B_STAGE + 1024 /*align*/ + 256 /
 template <int MODE>
 __device__ __forceinline__ void fwd_epilogue_chunk(const uint32_t (&v)[32], const FwdParams& p, float cshift,
                                                    bool row_ok, bool store_ok, bool tail, uint32_t row, int nb,
-                                                   float& psum) {
+                                                   float& psum, float& tmax) {
     float e[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -287,6 +290,7 @@ __device__ __forceinline__ void fwd_epilogue_chunk(const uint32_t (&v)[32], cons
                 mx = ok ? fmaxf(mx, sv) : mx;
             }
             mm[g] = mx;
+            tmax = fmaxf(tmax, mx);
         }
         if (row_ok) *reinterpret_cast<float4*>(p.chunkmax + (size_t)row * (p.e_pitch / 8) + nb / 8) = m;
     }
@@ -408,25 +412,26 @@ score_fwd_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((q * 32) << 16) + acc * P_BN + h * 128;
             const bool tail = n0 + 128 > p.n_items;
-            float psum = 0.f;
+            float psum = 0.f, tmax = -INFINITY;
             uint32_t va[32], vb[32];
             tmem_ld32(taddr, va);
             tmem_ld_wait();
             tmem_ld32(taddr + 32, vb);
-            fwd_epilogue_chunk<MODE>(va, p, cshift, row_ok, store_ok, tail, row, n0, psum);
+            fwd_epilogue_chunk<MODE>(va, p, cshift, row_ok, store_ok, tail, row, n0, psum, tmax);
             tmem_ld_wait();
             tmem_ld32(taddr + 64, va);
-            fwd_epilogue_chunk<MODE>(vb, p, cshift, row_ok, store_ok, tail, row, n0 + 32, psum);
+            fwd_epilogue_chunk<MODE>(vb, p, cshift, row_ok, store_ok, tail, row, n0 + 32, psum, tmax);
             tmem_ld_wait();
             tmem_ld32(taddr + 96, vb);
-            fwd_epilogue_chunk<MODE>(va, p, cshift, row_ok, store_ok, tail, row, n0 + 64, psum);
+            fwd_epilogue_chunk<MODE>(va, p, cshift, row_ok, store_ok, tail, row, n0 + 64, psum, tmax);
             tmem_ld_wait();
             // every TMEM read of this accumulator half is in registers -> hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(acc_empty_l + acc * 8);
-            fwd_epilogue_chunk<MODE>(vb, p, cshift, row_ok, store_ok, tail, row, n0 + 96, psum);
+            fwd_epilogue_chunk<MODE>(vb, p, cshift, row_ok, store_ok, tail, row, n0 + 96, psum, tmax);
             if (row_ok) p.rowsum_part[(size_t)(tile * 2 + h) * QROWS + row] = psum;
+            if (MODE == 1 && row_ok && p.tilemax) p.tilemax[(size_t)row * (p.e_pitch / 128) + tile * 2 + h] = tmax;
         }
     }
 
@@ -835,8 +840,8 @@ static int launch_fwd_pair(const CUtensorMap& mq, const CUtensorMap& mi, const F
 using namespace tcar;
 
 extern "C" int tcar_score_fwd(const void* q_bf16, const void* iext_bf16, const float* c_ref, void* e_out,
-                              float* rowsum_part, float* chunkmax, int n_rows, int n_items, int n_pad, int mode,
-                              int cluster, void* stream_) {
+                              float* rowsum_part, float* chunkmax, float* tilemax, int n_rows, int n_items, int n_pad,
+                              int mode, int cluster, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (n_rows < 1 || n_rows > QROWS || n_pad % 256 != 0 || n_items > n_pad) return TCAR_ERR_ARG;
     if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != TCAR_CLUSTER_PAIR) return TCAR_ERR_ARG;
@@ -851,6 +856,7 @@ extern "C" int tcar_score_fwd(const void* q_bf16, const void* iext_bf16, const f
         p.E = static_cast<__nv_bfloat16*>(e_out);
         p.rowsum_part = rowsum_part;
         p.chunkmax = chunkmax;
+        p.tilemax = tilemax;
         p.c_ref = c_ref;
         p.n_items = n_items;
         p.n_tiles = n_pad / P_BN;
@@ -870,6 +876,7 @@ extern "C" int tcar_score_fwd(const void* q_bf16, const void* iext_bf16, const f
     p.E = static_cast<__nv_bfloat16*>(e_out);
     p.rowsum_part = rowsum_part;
     p.chunkmax = chunkmax;
+    p.tilemax = tilemax;
     p.c_ref = c_ref;
     p.n_items = n_items;
     p.n_tiles = n_pad / F_BN;

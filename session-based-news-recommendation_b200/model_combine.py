@@ -138,6 +138,7 @@ class Seq2SeqAttNN:
                 ws["qpart"] = torch.zeros(splits, QROWS, KEXT, device=dev)
             else:
                 ws["cmax"] = torch.zeros(QROWS, n_pad // nv.CHUNK, device=dev)
+                ws["tmax"] = torch.zeros(QROWS, n_pad // 128, device=dev)
             self._score_ws[key] = ws
         return self._score_ws[key]
 
@@ -200,8 +201,8 @@ class Seq2SeqAttNN:
         ps, p, B = self.ps, nv.ptr, bt.B
         self._session_forward(bt)
         ws = self._score_buffers(ps.n_pad, True)
-        nv.counted_call("tcar_score_fwd", 1, p(self.Q), p(ps.iext), p(self.c_ref), p(ws["E"]), p(ws["part"]), None, B,
-                        ps.N, ps.n_pad, 0, self._cluster_for(B))
+        nv.counted_call("tcar_score_fwd", 1, p(self.Q), p(ps.iext), p(self.c_ref), p(ws["E"]), p(ws["part"]), None, None,
+                        B, ps.N, ps.n_pad, 0, self._cluster_for(B))
         nv.counted_call("tcar_ce_finish", 1, p(ws["part"]), p(self.sumexp), p(self.ce), ws["tiles"], B)
         nv.counted_call("tcar_neg_loss", 1, p(self.a_ic), p(ps.item), p(ps.content), p(bt.neg), p(self.ce),
                         p(self.negloss), p(self.loss), p(self.coef), p(self.dA_neg), B, bt.Nn)
@@ -279,13 +280,49 @@ class Seq2SeqAttNN:
                         p(self.entry_slot), p(self.slot_sq), self.hash_size, B, T, bt.Nn)
         self._fused_norm = True
 
+    def _sharded_update(self):
+        """True when the data-parallel step uses reduce-scatter -> per-rank Adam slice -> all-gather (the two halves of
+        an all-reduce with the optimiser in between) instead of all-reduce + replicated Adam."""
+        return parallel.is_distributed(self.world) and self.ps.rows_alloc % self.world == 0
+
     def allreduce_grads(self):
         """Data-parallel training: SUM (not mean -- the loss is a batch sum, model_combine.py:156) over ranks."""
-        parallel.allreduce_sum((self.ps.item_g, self.ps.theta_g), self.world)
+        if self._sharded_update():
+            parallel.allreduce_sum((self.ps.theta_g,), self.world)      # the item gradient is reduce-scattered later
+        else:
+            parallel.allreduce_sum((self.ps.item_g, self.ps.theta_g), self.world)
+
+    def _apply_item_sharded(self):
+        """Item table update of the data-parallel step: every rank reduces and owns one contiguous slice of rows."""
+        import torch.distributed as dist
+        ps, p = self.ps, nv.ptr
+        per = ps.rows_alloc // self.world
+        lo = self.rank * per
+        if getattr(self, "_g_slice", None) is None or self._g_slice.shape[0] != per:
+            self._g_slice = torch.empty(per, nv.HP, device=self.dev)
+        dist.reduce_scatter_tensor(self._g_slice, ps.item_g_full, op=dist.ReduceOp.SUM)
+        # clip norm of the WHOLE reduced gradient: per-slice sums of squares, summed over ranks
+        nv.counted_call("tcar_sqnorm_big", 2, p(self._g_slice), p(ps.norm_partial), p(ps.sqnorm_item),
+                        self._g_slice.numel())
+        dist.all_reduce(ps.sqnorm_item, op=dist.ReduceOp.SUM)
+        nv.counted_call("tcar_adam_item", 1, p(ps.item_full[lo:]), p(ps.item_m_full[lo:]), p(ps.item_v_full[lo:]),
+                        p(self._g_slice), p(ps.sqnorm_item), p(ps.step), self.lr, self.max_grad_f, p(ps.iext), lo, per)
+        dist.all_gather_into_tensor(ps.item_full, ps.item_full[lo: lo + per])
+        nv.counted_call("tcar_refresh_iext_items", 1, p(ps.item), p(ps.iext), ps.N)
 
     def apply_gradients(self):
         """per-tensor clip_by_norm + TF Adam (model_combine.py:155-163); also refreshes the bf16 scoring operand."""
         ps, p = self.ps, nv.ptr
+        if self._sharded_update():
+            nv.counted_call("tcar_sqnorm_segments", 1, p(ps.theta_g), p(ps.seg_off), p(ps.sqnorm_small), len(SMALL))
+            ps.step.add_(1)
+            self.global_step += 1
+            nv.counted_call("tcar_adam_small", 1, p(ps.theta), p(ps.theta_m), p(ps.theta_v), p(ps.theta_g),
+                            p(ps.seg_off), p(ps.sqnorm_small), len(SMALL), p(ps.step), self.lr, self.max_grad_f)
+            self._apply_item_sharded()
+            ps.prep_weights()
+            self._fused_norm = False
+            return
         nv.counted_call("tcar_sqnorm_segments", 1, p(ps.theta_g), p(ps.seg_off), p(ps.sqnorm_small), len(SMALL))
         if self.world == 1 and getattr(self, "_fused_norm", False):
             # ||g_item||^2 from the per-CTA sums of the dense gradient GEMM + the per-row corrections of the scatter:
@@ -302,14 +339,14 @@ class Seq2SeqAttNN:
         nv.counted_call("tcar_adam_small", 1, p(ps.theta), p(ps.theta_m), p(ps.theta_v), p(ps.theta_g), p(ps.seg_off),
                         p(ps.sqnorm_small), len(SMALL), p(ps.step), self.lr, self.max_grad_f)
         nv.counted_call("tcar_adam_item", 1, p(ps.item), p(ps.item_m), p(ps.item_v), p(ps.item_g), p(ps.sqnorm_item),
-                        p(ps.step), self.lr, self.max_grad_f, p(ps.iext), ps.N)
+                        p(ps.step), self.lr, self.max_grad_f, p(ps.iext), 0, ps.N + 1)
         ps.prep_weights()
 
     def train_step(self, bt):
         """One `sess.run([loss, global_step, train_op])` (model_combine.py:231-234). Returns loss [B] (device)."""
         if bt.B == 0:
             # data-parallel tail batch with fewer sessions than ranks: contribute a zero gradient to the all-reduce
-            self.ps.item_g.zero_()
+            self.ps.item_g_full.zero_()
             self.ps.theta_g.zero_()
             loss = self.loss[:0]
         else:
@@ -339,9 +376,10 @@ class Seq2SeqAttNN:
         else:
             ws = self._score_buffers(n_pad, False)
             nv.counted_call("tcar_score_fwd", 1, p(self.Q), p(iext), p(self.c_ref), None, p(ws["part"]), p(ws["cmax"]),
-                            B, n_loc, n_pad, 1, self._cluster_for(B))
+                            p(ws["tmax"]), B, n_loc, n_pad, 1, self._cluster_for(B))
             nv.counted_call("tcar_ce_finish", 1, p(ws["part"]), p(self.sumexp), p(self.ce), ws["tiles"], B)
-            nv.counted_call("tcar_eval_topk", 1, p(ws["cmax"]), p(self.a_ic), p(self.Tq), p(ps.item), p(ps.content),
+            nv.counted_call("tcar_eval_topk", 1, p(ws["cmax"]), p(ws["tmax"]), p(self.a_ic), p(self.Tq), p(ps.item),
+                            p(ps.content),
                             p(ps.mwdhm), p(bt.label), p(self.top_ids), p(self.top_scores), p(self.n_greater), B, n_loc,
                             n_pad, lo)
         if shard is not None and parallel.is_distributed(self.world):

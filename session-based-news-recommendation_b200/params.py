@@ -59,10 +59,14 @@ class ParamStore:
         self.content = torch.zeros(self.N + 1, HP, device=dev)
         self.content[:, :H] = torch.from_numpy(content_emb).to(dev)
         self.mwdhm = torch.from_numpy(mwdhm.astype(np.int32)).contiguous().to(dev)
-        self.item = torch.zeros(self.N + 1, HP, device=dev)
-        self.item_m = torch.zeros_like(self.item)
-        self.item_v = torch.zeros_like(self.item)
-        self.item_g = torch.zeros_like(self.item)
+        # backing rows padded to a multiple of 8 so that the table splits evenly over 1/2/4/8 data-parallel ranks
+        self.rows_alloc = (self.N + 1 + 7) // 8 * 8
+        self.item_full = torch.zeros(self.rows_alloc, HP, device=dev)
+        self.item_m_full = torch.zeros_like(self.item_full)
+        self.item_v_full = torch.zeros_like(self.item_full)
+        self.item_g_full = torch.zeros_like(self.item_full)
+        self.item, self.item_m = self.item_full[: self.N + 1], self.item_m_full[: self.N + 1]
+        self.item_v, self.item_g = self.item_v_full[: self.N + 1], self.item_g_full[: self.N + 1]
         self.iext = torch.zeros(self.n_pad, nv.KEXT, device=dev, dtype=torch.bfloat16)
         # flat small-parameter buffer; every segment starts 16-byte aligned
         offs, off = [], 0

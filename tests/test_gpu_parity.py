@@ -164,7 +164,7 @@ def margin_ok(scores, k=20, rel=2e-5):
     return gaps > rel * np.abs(s[:, :k + 1]).max(1)
 
 
-@pytest.mark.parametrize("B,T,N", [(3, 1, 300), (200, 4, 5000), (512, 20, 9000)])
+@pytest.mark.parametrize("B,T,N", [(3, 1, 300), (200, 4, 5000), (512, 20, 9000), (64, 3, 70000)])
 def test_eval_top20_rank_and_loss(B, T, N):
     model, content, mwdhm, args = build(N, emb_scale=20.0)
     bt, batch = batch_for(model, N, B, T, 0, mwdhm, seed=B)

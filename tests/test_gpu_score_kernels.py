@@ -40,9 +40,13 @@ def _fwd(native, Q, I, c, B, N, n_pad, mode, cluster):
     part = torch.zeros(tiles, QROWS, device="cuda")
     E = torch.full((QROWS, n_pad), float("nan"), device="cuda", dtype=torch.bfloat16) if mode == 0 else None
     cm = torch.full((QROWS, n_pad // 8), float("nan"), device="cuda") if mode == 1 else None
+    tmx = torch.full((QROWS, n_pad // 128), float("nan"), device="cuda") if mode == 1 else None
     native.call("tcar_score_fwd", native.ptr(Q), native.ptr(I), native.ptr(c), native.ptr(E), native.ptr(part),
-                native.ptr(cm), B, N, n_pad, mode, cluster)
+                native.ptr(cm), native.ptr(tmx), B, N, n_pad, mode, cluster)
     torch.cuda.synchronize()
+    if mode == 1:
+        # the per-128-item maxima are the maxima of their 16 chunk maxima
+        assert torch.equal(tmx[:B], cm[:B].view(B, -1, 16).max(-1).values)
     return (e_from_blocked(E, n_pad) if E is not None else None), part, cm
 
 
