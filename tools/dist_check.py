@@ -41,7 +41,13 @@ def main():
     bt = model.to_device(torch.from_numpy(pl).pin_memory(), Bl, T, Nn)
     loss_local = model.train_step(bt).clone()
     torch.cuda.synchronize()
-    g_item, g_theta, item_after = model.ps.item_g.clone(), model.ps.theta_g.clone(), model.ps.item.clone()
+    g_theta, item_after = model.ps.theta_g.clone(), model.ps.item.clone()
+    if model._sharded_update():
+        # reduce-scatter path: every rank holds the reduced gradient of its own row slice only
+        per = model.ps.rows_alloc // world
+        g_item, g_rows = model._g_slice.clone(), slice(rank * per, (rank + 1) * per)
+    else:
+        g_item, g_rows = model.ps.item_g_full.clone(), slice(0, model.ps.rows_alloc)
     single, _ = build(N, 0, 1)
     btf = single.to_device(torch.from_numpy(packed).pin_memory(), B, T, Nn)
     loss_full = single.train_step(btf).clone()
@@ -49,7 +55,8 @@ def main():
     lo, hi = parallel.shard_sessions(B, rank, world)
     rel = lambda a, b: float((a - b).double().norm() / (b.double().norm() + 1e-30))
     res["loss_maxabs"] = float((loss_local - loss_full[lo:hi]).abs().max())
-    res["g_item_rel"] = rel(g_item, single.ps.item_g)
+    res["g_item_rel"] = rel(g_item, single.ps.item_g_full[g_rows])
+    res["iext_equal"] = bool(torch.equal(model.ps.iext, single.ps.iext))
     res["g_theta_rel"] = rel(g_theta, single.ps.theta_g)
     res["item_after_rel"] = rel(item_after, single.ps.item)
     # ---- catalog-sharded eval vs single GPU
@@ -65,7 +72,7 @@ def main():
     res["rank_equal"] = bool(torch.equal(hit, ng < 20) and torch.equal(n1[hit], ng[hit]))
     res["ce_maxabs"] = float((ce1 - ceg).abs().max())
     ok = (res["loss_maxabs"] < 1e-5 and res["g_item_rel"] < 1e-5 and res["g_theta_rel"] < 1e-5
-          and res["item_after_rel"] < 1e-6 and res["top20_equal"] and res["rank_equal"] and res["ce_maxabs"] < 1e-4)
+          and res["item_after_rel"] < 1e-6 and res["iext_equal"] and res["top20_equal"] and res["rank_equal"] and res["ce_maxabs"] < 1e-4)
     res["ok"] = ok
     print(f"rank {rank}/{world}: " + json.dumps(res), flush=True)
     dist.barrier()
