@@ -56,7 +56,11 @@ def main():
     rel = lambda a, b: float((a - b).double().norm() / (b.double().norm() + 1e-30))
     res["loss_maxabs"] = float((loss_local - loss_full[lo:hi]).abs().max())
     res["g_item_rel"] = rel(g_item, single.ps.item_g_full[g_rows])
-    res["iext_equal"] = bool(torch.equal(model.ps.iext, single.ps.iext))
+    # gradients differ in the last bits (different summation order), so a few bf16 roundings of the refreshed scoring
+    # operand may flip: require them to be rare and one ulp at most
+    diff = (model.ps.iext.float() - single.ps.iext.float()).abs()
+    res["iext_mismatch_frac"] = float((diff > 0).float().mean())
+    res["iext_equal"] = bool(res["iext_mismatch_frac"] < 1e-3 and float(diff.max()) <= 2 ** -7 * float(single.ps.iext.float().abs().max()))
     res["g_theta_rel"] = rel(g_theta, single.ps.theta_g)
     res["item_after_rel"] = rel(item_after, single.ps.item)
     # ---- catalog-sharded eval vs single GPU
