@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_kernels", action="store_true", help="skip the per-kernel roofline pass")
     ap.add_argument("--cpu_sample_sessions", type=int, default=512)
+    ap.add_argument("--profile_region", action="store_true",
+                    help="for `ncu --profile-from-start off`: warm up, then ONE train step (T=20) and ONE eval step "
+                         "between cudaProfilerStart/Stop; prints nothing")
     return ap.parse_args()
 
 
@@ -344,6 +347,20 @@ def run_b200(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if a.profile_region:
+        pb = model.to_device(make_batches(synth, N, B, [T], Nn, mwdhm, seed0=3)[0], B, T, Nn)
+        eb = model.to_device(make_batches(synth, N, B, [T], 0, mwdhm, seed0=4)[0], B, T, 0)
+        for _ in range(2):
+            model.train_step(pb)
+            model.eval_step(eb)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        model.train_step(pb)
+        model.eval_step(eb)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
+
     def max_over_ranks(ms):
         if dist is None:
             return ms
@@ -424,6 +441,18 @@ def run_b200(a):
     e1.record()
     barrier()
     eval_e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    eval_qp_ms = None
+    if world > 1:
+        # for comparison: query-parallel evaluation (every rank scores its own queries against the whole catalog)
+        for i in range(2):
+            model.eval_step(edev[(i + rank) % nbatch])
+        barrier()
+        e0.record()
+        for i in range(K):
+            model.eval_step(edev[(i + rank) % nbatch])
+        e1.record()
+        barrier()
+        eval_qp_ms = max_over_ranks(e0.elapsed_time(e1))
     clk = clocks.stop() if rank == 0 else None
 
     kernels = {}
@@ -473,6 +502,9 @@ def run_b200(a):
                      "e2e": {"value": B * K / (eval_e2e_ms * 1e-3), "unit": "queries/s",
                              "h2d_bytes_per_step": sum(ehost[i % nbatch].numel() for i in range(K)) * 4 / K,
                              "d2h_bytes_per_step": B * (20 + 1 + 1) * 4}},
+            "eval_query_parallel": None if eval_qp_ms is None else {
+                "note": "queries sharded across ranks instead of the catalog (no collective); not the north_star layout",
+                "value": world * B * K / (eval_qp_ms * 1e-3), "unit": "queries/s", "ms_per_step": eval_qp_ms / K},
             "t20": {"note": "same measurement with every batch at the reference --maxlen (T = 20)",
                     "value": sessions / (t20_ms * 1e-3), "ms_per_step": t20_ms / K,
                     "e2e_value": sessions / (t20_e2e_ms * 1e-3), "unit": "sessions/s"},

@@ -1,8 +1,12 @@
 #!/bin/bash
-# one `ncu --set full` capture of the hot kernels of the second train step
+# `ncu --set full` capture of every hot kernel of ONE train step (T = 20) + ONE eval step (bench.py --profile_region)
 mkdir -p gpurun_out
-timeout -s KILL 1200 ncu --set full --clock-control none --import-source on \
-  -k 'regex:gemm_tf32_kernel|score_fwd_pair|score_bwd_q_kernel|score_bwd_i_kernel|adam_item|gather_fwd|pool_fwd|pool_bwd|scatter_accum|small_table' \
-  --launch-skip ${1:-34} --launch-count ${2:-34} -f -o gpurun_out/prof_step \
-  python bench.py --steps 1 --warmup 2 --no_cpu_baseline --no_kernels > gpurun_out/ncu_full.log 2>&1
-echo "ncu exit $?"; tail -3 gpurun_out/ncu_full.log; ls -la gpurun_out/prof_step.ncu-rep
+K='regex:score_fwd_pair|score_bwd_i_kernel|adam_item|gather_fwd|pool_fwd|pool_bwd|scatter_accum|table_partial|gemm_tf32_kernel|eval_topk|build_query'
+timeout -s KILL 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k "$K" -f -o gpurun_out/prof_step \
+  python bench.py --profile_region > gpurun_out/ncu_full.log 2>&1
+echo "ncu A exit $?"; tail -2 gpurun_out/ncu_full.log
+# score_bwd_q fails to launch under the full set's instrumentation (it owns all 227 KB of shared memory): lighter sections
+timeout -s KILL 600 ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section LaunchStats --section Occupancy --clock-control none --profile-from-start off \
+  -k regex:score_bwd_q_kernel -f -o gpurun_out/prof_bwd_q python bench.py --profile_region > gpurun_out/ncu_bwd_q.log 2>&1
+echo "ncu B exit $?"; tail -2 gpurun_out/ncu_bwd_q.log
+ls -la gpurun_out/*.ncu-rep
