@@ -194,21 +194,35 @@ adam_item_kernel(float4* __restrict__ item, float4* __restrict__ m, float4* __re
                  float lr, float max_grad, __nv_bfloat16* __restrict__ iext, long long n4, long long row0) {
     const float cf = clip_factor(sqnorm[0], max_grad);
     const float lr_t = adam_lr_t(step[0], lr);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        float4 p = item[i], mm = m[i], vv = v[i];
-        const float4 gg = g[i];
-        adam_update(p.x, mm.x, vv.x, gg.x * cf, lr_t);
-        adam_update(p.y, mm.y, vv.y, gg.y * cf, lr_t);
-        adam_update(p.z, mm.z, vv.z, gg.z * cf, lr_t);
-        adam_update(p.w, mm.w, vv.w, gg.w * cf, lr_t);
-        item[i] = p; m[i] = mm; v[i] = vv;
-        const long long row = row0 + (i >> 6);   // 64 float4 per 256-float row; row0 = first row of this slice
-        const int c = (int)(i & 63) * 4;
-        if (row >= 1 && c < H) {
-            __nv_bfloat16* dst = iext + (size_t)(row - 1) * KEXT + c;
-            __nv_bfloat162 lo = __floats2bfloat162_rn(p.x, p.y);
-            *reinterpret_cast<__nv_bfloat162*>(dst) = lo;
-            if (c + 2 < H) *reinterpret_cast<__nv_bfloat162*>(dst + 2) = __floats2bfloat162_rn(p.z, p.w);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += 2 * stride) {
+        // two independent float4 streams per thread: all eight loads are in flight before the first use
+        const long long i1 = i0 + stride;
+        const bool two = i1 < n4;
+        float4 p0 = item[i0], m0 = m[i0], v0 = v[i0];
+        const float4 g0 = g[i0];
+        float4 p1 = p0, m1 = m0, v1 = v0, g1 = g0;
+        if (two) { p1 = item[i1]; m1 = m[i1]; v1 = v[i1]; g1 = g[i1]; }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !two) break;
+            const long long i = u ? i1 : i0;
+            float4& p = u ? p1 : p0;
+            float4& mm = u ? m1 : m0;
+            float4& vv = u ? v1 : v0;
+            const float4 gg = u ? g1 : g0;
+            adam_update(p.x, mm.x, vv.x, gg.x * cf, lr_t);
+            adam_update(p.y, mm.y, vv.y, gg.y * cf, lr_t);
+            adam_update(p.z, mm.z, vv.z, gg.z * cf, lr_t);
+            adam_update(p.w, mm.w, vv.w, gg.w * cf, lr_t);
+            item[i] = p; m[i] = mm; v[i] = vv;
+            const long long row = row0 + (i >> 6);   // 64 float4 per 256-float row; row0 = first row of this slice
+            const int c = (int)(i & 63) * 4;
+            if (row >= 1 && c < H) {
+                __nv_bfloat16* dst = iext + (size_t)(row - 1) * KEXT + c;
+                *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(p.x, p.y);
+                if (c + 2 < H) *reinterpret_cast<__nv_bfloat162*>(dst + 2) = __floats2bfloat162_rn(p.z, p.w);
+            }
         }
     }
 }

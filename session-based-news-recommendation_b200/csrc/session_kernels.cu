@@ -105,6 +105,13 @@ gather_fwd_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ c
 
 // ------------------------------------------------------------------------------------------------ (2) pooling fwd
 // one CTA per session.  modules.py:126-142 (count_alpha_m), :94-100 (count_alpha_s), :116-117 / :82-83 (pool).
+// Every row is fetched with 128-bit loads that are all issued before the first use (8 independent loads per lane and
+// click), so a click costs one memory round trip instead of ~30 dependent ones.
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float dot4(const float4 a, const float4 b) {
+    return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+
 __global__ void __launch_bounds__(256)
 pool_fwd_kernel(const float* __restrict__ X, const float* __restrict__ P, float* __restrict__ U1,
                 float* __restrict__ U2, const float* __restrict__ q, const float* __restrict__ w_r,
@@ -112,23 +119,38 @@ pool_fwd_kernel(const float* __restrict__ X, const float* __restrict__ P, float*
                 float* __restrict__ pooled_t, int B, int T) {
     __shared__ float s_e[3][TCAR_MAXT];
     __shared__ float s_a[3][TCAR_MAXT];
-    __shared__ float s_q[XW];
+    __shared__ __align__(16) float s_q[XW + 12];
+    __shared__ __align__(16) float s_wr[HP], s_wt[HP];
     const int b = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int M = B * T;
-    for (int c = threadIdx.x; c < XW; c += blockDim.x) s_q[c] = q[(size_t)b * XW + c];
+    for (int c = threadIdx.x; c < XW + 12; c += blockDim.x) s_q[c] = c < XW ? q[(size_t)b * XW + c] : 0.f;
+    for (int c = threadIdx.x; c < HP; c += blockDim.x) {
+        s_wr[c] = c < H ? w_r[c] : 0.f;          // zero weights on the 6 pad columns of the 256-float pitch
+        s_wt[c] = c < H ? w_t[c] : 0.f;
+    }
     __syncthreads();
+    const float4* q4 = reinterpret_cast<const float4*>(s_q);
+    const float4* wr4 = reinterpret_cast<const float4*>(s_wr);
+    const float4* wt4 = reinterpret_cast<const float4*>(s_wt);
     for (int t = w; t < T; t += 8) {
         const size_t m = (size_t)b * T + t;
-        float e1 = 0.f, e2 = 0.f, et = 0.f;
-        for (int c = lane; c < H; c += 32) {
-            const float s1 = 1.f / (1.f + expf(-U1[m * HP + c]));
-            const float s2 = 1.f / (1.f + expf(-U2[m * HP + c]));
-            U1[m * HP + c] = s1;
-            U2[m * HP + c] = s2;
-            e1 = fmaf(s1, w_r[c], e1);
-            et = fmaf(s2, w_t[c], et);
-        }
-        for (int c = lane; c < XW; c += 32) e2 = fmaf(X[m * XW + c], s_q[c], e2);
+        float4* u1 = reinterpret_cast<float4*>(U1 + m * HP);
+        float4* u2 = reinterpret_cast<float4*>(U2 + m * HP);
+        const float4* x4 = reinterpret_cast<const float4*>(X + m * XW);       // 125 float4 per row
+        const float4 a0 = u1[lane], a1 = u1[lane + 32], c0 = u2[lane], c1 = u2[lane + 32];
+        const float4 x0 = x4[lane], x1 = x4[lane + 32], x2 = x4[lane + 64];
+        const float4 x3 = lane + 96 < XW / 4 ? x4[lane + 96] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 s0 = make_float4(sigmoidf_(a0.x), sigmoidf_(a0.y), sigmoidf_(a0.z), sigmoidf_(a0.w));
+        float4 s1 = make_float4(sigmoidf_(a1.x), sigmoidf_(a1.y), sigmoidf_(a1.z), sigmoidf_(a1.w));
+        float4 r0 = make_float4(sigmoidf_(c0.x), sigmoidf_(c0.y), sigmoidf_(c0.z), sigmoidf_(c0.w));
+        float4 r1 = make_float4(sigmoidf_(c1.x), sigmoidf_(c1.y), sigmoidf_(c1.z), sigmoidf_(c1.w));
+        if (lane == 30) { s1.z = s1.w = 0.f; r1.z = r1.w = 0.f; }               // columns 250, 251
+        if (lane == 31) { s1 = make_float4(0.f, 0.f, 0.f, 0.f); r1 = s1; }      // columns 252..255
+        u1[lane] = s0; u1[lane + 32] = s1;
+        u2[lane] = r0; u2[lane + 32] = r1;
+        float e1 = dot4(s0, wr4[lane]) + dot4(s1, wr4[lane + 32]);
+        float et = dot4(r0, wt4[lane]) + dot4(r1, wt4[lane + 32]);
+        float e2 = (dot4(x0, q4[lane]) + dot4(x1, q4[lane + 32])) + (dot4(x2, q4[lane + 64]) + dot4(x3, q4[lane + 96]));
         e1 = warp_sum(e1); e2 = warp_sum(e2); et = warp_sum(et);
         if (lane == 0) { s_e[0][t] = e1; s_e[1][t] = e2; s_e[2][t] = et; }
     }
@@ -142,16 +164,33 @@ pool_fwd_kernel(const float* __restrict__ X, const float* __restrict__ P, float*
         if (lane + 32 < T) { s_a[w][lane + 32] = x1 / sum; alpha[(size_t)w * M + (size_t)b * T + lane + 32] = x1 / sum; }
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < XW + PW; c += blockDim.x) {
-        float acc = 0.f;
-        if (c < XW) {
-            for (int t = 0; t < T; ++t) acc = fmaf(s_a[0][t] + s_a[1][t], X[((size_t)b * T + t) * XW + c], acc);
-            pooled[(size_t)b * XW + c] = acc;
-        } else {
-            const int cc = c - XW;
-            for (int t = 0; t < T; ++t) acc = fmaf(s_a[2][t], P[((size_t)b * T + t) * PW + cc], acc);
-            pooled_t[(size_t)b * PW + cc] = acc;
+    // pooled = sum_t (alpha1 + alpha2)[t] X[t, :] (125 float4 columns), pooled_t = sum_t alpha_t[t] P[t, :] (80)
+    for (int c = threadIdx.x; c < XW / 4 + PW / 4; c += blockDim.x) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool isx = c < XW / 4;
+        const float4* src = isx ? reinterpret_cast<const float4*>(X + (size_t)b * T * XW) + c
+                                : reinterpret_cast<const float4*>(P + (size_t)b * T * PW) + (c - XW / 4);
+        const int stride = isx ? XW / 4 : PW / 4;
+        int t = 0;
+        for (; t + 4 <= T; t += 4) {
+            const float4 v0 = src[(size_t)t * stride], v1 = src[(size_t)(t + 1) * stride];
+            const float4 v2 = src[(size_t)(t + 2) * stride], v3 = src[(size_t)(t + 3) * stride];
+            const float g0 = isx ? s_a[0][t] + s_a[1][t] : s_a[2][t];
+            const float g1 = isx ? s_a[0][t + 1] + s_a[1][t + 1] : s_a[2][t + 1];
+            const float g2 = isx ? s_a[0][t + 2] + s_a[1][t + 2] : s_a[2][t + 2];
+            const float g3 = isx ? s_a[0][t + 3] + s_a[1][t + 3] : s_a[2][t + 3];
+            acc.x = fmaf(g0, v0.x, acc.x); acc.y = fmaf(g0, v0.y, acc.y); acc.z = fmaf(g0, v0.z, acc.z); acc.w = fmaf(g0, v0.w, acc.w);
+            acc.x = fmaf(g1, v1.x, acc.x); acc.y = fmaf(g1, v1.y, acc.y); acc.z = fmaf(g1, v1.z, acc.z); acc.w = fmaf(g1, v1.w, acc.w);
+            acc.x = fmaf(g2, v2.x, acc.x); acc.y = fmaf(g2, v2.y, acc.y); acc.z = fmaf(g2, v2.z, acc.z); acc.w = fmaf(g2, v2.w, acc.w);
+            acc.x = fmaf(g3, v3.x, acc.x); acc.y = fmaf(g3, v3.y, acc.y); acc.z = fmaf(g3, v3.z, acc.z); acc.w = fmaf(g3, v3.w, acc.w);
         }
+        for (; t < T; ++t) {
+            const float4 v0 = src[(size_t)t * stride];
+            const float g0 = isx ? s_a[0][t] + s_a[1][t] : s_a[2][t];
+            acc.x = fmaf(g0, v0.x, acc.x); acc.y = fmaf(g0, v0.y, acc.y); acc.z = fmaf(g0, v0.z, acc.z); acc.w = fmaf(g0, v0.w, acc.w);
+        }
+        if (isx) reinterpret_cast<float4*>(pooled + (size_t)b * XW)[c] = acc;
+        else reinterpret_cast<float4*>(pooled_t + (size_t)b * PW)[c - XW / 4] = acc;
     }
 }
 
@@ -163,23 +202,38 @@ pool_bwd_kernel(const float* __restrict__ X, const float* __restrict__ P, const 
                 const float* __restrict__ dpooled_t, float* __restrict__ dU1, float* __restrict__ dU2,
                 float* __restrict__ dXi, float* __restrict__ dP, float* __restrict__ dq, float* __restrict__ de,
                 int B, int T) {
-    __shared__ float s_dp[XW], s_dpt[PW], s_q[XW];
+    __shared__ __align__(16) float s_dp[XW + 12], s_dpt[PW], s_q[XW + 12];
+    __shared__ __align__(16) float s_wr[HP], s_wt[HP];
     __shared__ float s_a[3][TCAR_MAXT], s_da[2][TCAR_MAXT], s_de[3][TCAR_MAXT];
     const int b = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int M = B * T;
-    for (int c = threadIdx.x; c < XW; c += blockDim.x) {
-        s_dp[c] = dpooled[(size_t)b * XW + c];
-        s_q[c] = q[(size_t)b * XW + c];
+    for (int c = threadIdx.x; c < XW + 12; c += blockDim.x) {
+        s_dp[c] = c < XW ? dpooled[(size_t)b * XW + c] : 0.f;
+        s_q[c] = c < XW ? q[(size_t)b * XW + c] : 0.f;
     }
     for (int c = threadIdx.x; c < PW; c += blockDim.x) s_dpt[c] = dpooled_t[(size_t)b * PW + c];
+    for (int c = threadIdx.x; c < HP; c += blockDim.x) {
+        s_wr[c] = c < H ? w_r[c] : 0.f;
+        s_wt[c] = c < H ? w_t[c] : 0.f;
+    }
     for (int i = threadIdx.x; i < 3 * T; i += blockDim.x) s_a[i / T][i % T] = alpha[(size_t)(i / T) * M + (size_t)b * T + i % T];
     __syncthreads();
+    const float4* dp4 = reinterpret_cast<const float4*>(s_dp);
+    const float4* dpt4 = reinterpret_cast<const float4*>(s_dpt);
+    const float4* q4 = reinterpret_cast<const float4*>(s_q);
+    const float4* wr4 = reinterpret_cast<const float4*>(s_wr);
+    const float4* wt4 = reinterpret_cast<const float4*>(s_wt);
     // d alpha[t] = X[t,:] . dpooled ; d alpha_t[t] = P[t,:] . dpooled_t
     for (int t = w; t < T; t += 8) {
         const size_t m = (size_t)b * T + t;
-        float a = 0.f, at = 0.f;
-        for (int c = lane; c < XW; c += 32) a = fmaf(X[m * XW + c], s_dp[c], a);
-        for (int c = lane; c < PW; c += 32) at = fmaf(P[m * PW + c], s_dpt[c], at);
+        const float4* x4 = reinterpret_cast<const float4*>(X + m * XW);
+        const float4* p4 = reinterpret_cast<const float4*>(P + m * PW);       // 80 float4 per row
+        const float4 x0 = x4[lane], x1 = x4[lane + 32], x2 = x4[lane + 64];
+        const float4 x3 = lane + 96 < XW / 4 ? x4[lane + 96] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 p0 = p4[lane], p1 = p4[lane + 32];
+        const float4 p2 = lane + 64 < PW / 4 ? p4[lane + 64] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float a = (dot4(x0, dp4[lane]) + dot4(x1, dp4[lane + 32])) + (dot4(x2, dp4[lane + 64]) + dot4(x3, dp4[lane + 96]));
+        float at = dot4(p0, dpt4[lane]) + dot4(p1, dpt4[lane + 32]) + (lane + 64 < PW / 4 ? dot4(p2, dpt4[lane + 64]) : 0.f);
         a = warp_sum(a); at = warp_sum(at);
         if (lane == 0) { s_da[0][t] = a; s_da[1][t] = at; }
     }
@@ -204,18 +258,54 @@ pool_bwd_kernel(const float* __restrict__ X, const float* __restrict__ P, const 
         const size_t m = (size_t)b * T + t;
         const float de1 = s_de[0][t], de2 = s_de[1][t], det = s_de[2][t];
         const float a12 = s_a[0][t] + s_a[1][t], at = s_a[2][t];
-        for (int c = lane; c < H; c += 32) {
-            const float s1 = S1[m * HP + c], s2 = S2[m * HP + c];
-            dU1[m * HP + c] = de1 * w_r[c] * s1 * (1.f - s1);
-            dU2[m * HP + c] = det * w_t[c] * s2 * (1.f - s2);
-            dXi[m * HP + c] = fmaf(a12, s_dp[c], de2 * s_q[c]);
+        const float4* s1r = reinterpret_cast<const float4*>(S1 + m * HP);
+        const float4* s2r = reinterpret_cast<const float4*>(S2 + m * HP);
+        float4* du1 = reinterpret_cast<float4*>(dU1 + m * HP);
+        float4* du2 = reinterpret_cast<float4*>(dU2 + m * HP);
+        float4* dxi = reinterpret_cast<float4*>(dXi + m * HP);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int i = lane + 32 * h;                 // float4 index within the 256-float pitch (pads give zeros)
+            const float4 s1 = s1r[i], s2 = s2r[i], wr = wr4[i], wt = wt4[i];
+            // dXi uses columns 0..249 of dpooled / q (the item half of X)
+            const float4 dpv = i < 63 ? dp4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 qv = i < 63 ? q4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 o1, o2, ox;
+            o1.x = de1 * wr.x * s1.x * (1.f - s1.x); o1.y = de1 * wr.y * s1.y * (1.f - s1.y);
+            o1.z = de1 * wr.z * s1.z * (1.f - s1.z); o1.w = de1 * wr.w * s1.w * (1.f - s1.w);
+            o2.x = det * wt.x * s2.x * (1.f - s2.x); o2.y = det * wt.y * s2.y * (1.f - s2.y);
+            o2.z = det * wt.z * s2.z * (1.f - s2.z); o2.w = det * wt.w * s2.w * (1.f - s2.w);
+            ox.x = fmaf(a12, dpv.x, de2 * qv.x); ox.y = fmaf(a12, dpv.y, de2 * qv.y);
+            ox.z = fmaf(a12, dpv.z, de2 * qv.z); ox.w = fmaf(a12, dpv.w, de2 * qv.w);
+            if (i == 62) { ox.z = ox.w = 0.f; }            // columns 250, 251 belong to the content half
+            du1[i] = o1; du2[i] = o2; dxi[i] = ox;
         }
-        for (int c = lane; c < PW; c += 32) dP[m * PW + c] = at * s_dpt[c];
+        float4* dp_out = reinterpret_cast<float4*>(dP + m * PW);
+        for (int i = lane; i < PW / 4; i += 32) {
+            const float4 v = dpt4[i];
+            dp_out[i] = make_float4(at * v.x, at * v.y, at * v.z, at * v.w);
+        }
     }
-    for (int c = threadIdx.x; c < XW; c += blockDim.x) {
-        float acc = 0.f;
-        for (int t = 0; t < T; ++t) acc = fmaf(s_de[1][t], X[((size_t)b * T + t) * XW + c], acc);
-        dq[(size_t)b * XW + c] = acc;
+    // dq[c] = sum_t de2[t] X[t, c]
+    for (int c = threadIdx.x; c < XW / 4; c += blockDim.x) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* src = reinterpret_cast<const float4*>(X + (size_t)b * T * XW) + c;
+        int t = 0;
+        for (; t + 4 <= T; t += 4) {
+            const float4 v0 = src[(size_t)t * (XW / 4)], v1 = src[(size_t)(t + 1) * (XW / 4)];
+            const float4 v2 = src[(size_t)(t + 2) * (XW / 4)], v3 = src[(size_t)(t + 3) * (XW / 4)];
+            const float g0 = s_de[1][t], g1 = s_de[1][t + 1], g2 = s_de[1][t + 2], g3 = s_de[1][t + 3];
+            acc.x = fmaf(g0, v0.x, acc.x); acc.y = fmaf(g0, v0.y, acc.y); acc.z = fmaf(g0, v0.z, acc.z); acc.w = fmaf(g0, v0.w, acc.w);
+            acc.x = fmaf(g1, v1.x, acc.x); acc.y = fmaf(g1, v1.y, acc.y); acc.z = fmaf(g1, v1.z, acc.z); acc.w = fmaf(g1, v1.w, acc.w);
+            acc.x = fmaf(g2, v2.x, acc.x); acc.y = fmaf(g2, v2.y, acc.y); acc.z = fmaf(g2, v2.z, acc.z); acc.w = fmaf(g2, v2.w, acc.w);
+            acc.x = fmaf(g3, v3.x, acc.x); acc.y = fmaf(g3, v3.y, acc.y); acc.z = fmaf(g3, v3.z, acc.z); acc.w = fmaf(g3, v3.w, acc.w);
+        }
+        for (; t < T; ++t) {
+            const float4 v0 = src[(size_t)t * (XW / 4)];
+            const float g0 = s_de[1][t];
+            acc.x = fmaf(g0, v0.x, acc.x); acc.y = fmaf(g0, v0.y, acc.y); acc.z = fmaf(g0, v0.z, acc.z); acc.w = fmaf(g0, v0.w, acc.w);
+        }
+        reinterpret_cast<float4*>(dq + (size_t)b * XW)[c] = acc;
     }
 }
 

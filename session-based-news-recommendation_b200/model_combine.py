@@ -515,7 +515,12 @@ class Seq2SeqAttNN:
             packed, B, T, Nn = sampler.next_packed()
             batch_in, batch_out = sampler.last_in, sampler.last_out
             bt = self.to_device(torch.from_numpy(packed).pin_memory(), B, T, Nn)
-            top, ngt, ce = self.eval_step(bt)
+            shard = None
+            if parallel.is_distributed(self.world):
+                # catalog-sharded evaluation: every rank scores all queries against its own item range
+                lo, hi = self.shard_bounds(self.world)[self.rank]
+                shard = (lo, hi, self.iext_shard(lo, hi))
+            top, ngt, ce = self.eval_step(bt, shard=shard)
             top, ngt, ce = top.cpu().numpy(), ngt.cpu().numpy(), ce.cpu().numpy()
             if batch < 3:
                 print("batch_in:", batch_in[0])
