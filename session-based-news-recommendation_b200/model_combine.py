@@ -102,17 +102,27 @@ class Seq2SeqAttNN:
         self.dq_raw = f(QROWS, KEXT)
         self.dCT = f(Bm, 2 * TH)
         self._score_ws = {}
-        self.hash_size = 65536
-        self.hash_keys = torch.full((self.hash_size,), -1, device=dev, dtype=torch.int32)
-        self.hash_acc = torch.zeros(self.hash_size, nv.HP, device=dev, dtype=torch.int64)
-        self.hash_cnt = torch.zeros(self.hash_size, device=dev, dtype=torch.int32)
-        self.entry_slot = torch.zeros(self.hash_size // 2, device=dev, dtype=torch.int32)
-        self.slot_sq = f(self.hash_size)
+        self.hash_size = 0
+        self._alloc_scatter(Bm * 20 + Bm + Bm * max(int(self.neg_num or 0), 20))   # reference defaults: T<=20, Nn=20
         self.sq_partial = f(256)
         self.table_part = f(148 * 19600)            # TCAR_TABLE_GRAD_CHUNKS x TCAR_TABLE_GRAD_PART
         self.top_ids = torch.zeros(Bm, TOPK, device=dev, dtype=torch.int32)
         self.top_scores = f(Bm, TOPK)
         self.n_greater = torch.zeros(Bm, device=dev, dtype=torch.int32)
+
+    def _alloc_scatter(self, entries):
+        """Scratch of the deterministic scatter-add, sized for `entries` sparse rows (clicks + labels + negatives):
+        a power-of-two hash with load factor <= 1/2.  Grows on demand (MIND-shaped runs use up to 100 negatives)."""
+        need = 1 << max(16, (2 * entries - 1).bit_length())
+        if need <= self.hash_size:
+            return
+        dev = self.dev
+        self.hash_size = need
+        self.hash_keys = torch.full((need,), -1, device=dev, dtype=torch.int32)
+        self.hash_acc = torch.zeros(need, nv.HP, device=dev, dtype=torch.int64)
+        self.hash_cnt = torch.zeros(need, device=dev, dtype=torch.int32)
+        self.entry_slot = torch.zeros(need // 2, device=dev, dtype=torch.int32)
+        self.slot_sq = torch.zeros(need, device=dev)
 
     def _part(self, M, N, splits):
         """Carve a disjoint split-reduction scratch for one problem of a GEMM group (None when not split)."""
@@ -273,8 +283,7 @@ class Seq2SeqAttNN:
                         p(w["week"]), p(w["hour"]), p(w["minute"]), p(w["dur"]), p(g["pos"]), p(g["month"]),
                         p(g["day"]), p(g["week"]), p(g["hour"]), p(g["minute"]), p(g["dur"]), p(self.table_part), B, T)
         entries = B * T + B + B * bt.Nn
-        if 2 * entries > self.hash_size:
-            raise ValueError("batch too large for the sparse-gradient scratch")
+        self._alloc_scatter(entries)
         nv.counted_call("tcar_scatter_add_rows", 3, p(bt.seq), p(bt.label), p(bt.neg), p(self.dXi), p(self.a_ic),
                         p(self.coef), p(ps.item), p(ps.item_g), p(self.hash_keys), p(self.hash_cnt), p(self.hash_acc),
                         p(self.entry_slot), p(self.slot_sq), self.hash_size, B, T, bt.Nn)

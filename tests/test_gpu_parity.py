@@ -77,7 +77,9 @@ def relerr(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-@pytest.mark.parametrize("B,T,scale,Nn", [(5, 1, 1.0, 20), (130, 3, 100.0, 20), (512, 20, 1.0, 20), (96, 40, 30.0, 7)])
+@pytest.mark.parametrize("B,T,scale,Nn", [(5, 1, 1.0, 20), (130, 3, 100.0, 20), (512, 20, 1.0, 20), (96, 40, 30.0, 7),
+                                          (256, 10, 1.0, 100),      # MIND shape: heavier negative sampling (cfg 4)
+                                          (512, 40, 1.0, 50)])      # Adressa shape: longest sessions (cfg 5)
 def test_train_step_loss_and_gradients(B, T, scale, Nn):
     N = 3000
     model, content, mwdhm, _ = build(N, emb_scale=scale, Nn=Nn)

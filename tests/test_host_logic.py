@@ -1,0 +1,142 @@
+"""Host-side mirror of the reference interface (no GPU): the product Sampler / util / main against the golden vectors
+that tests/golden/make_golden.py produced by running the reference's own sampler.py / util.py, and the on-disk
+pickle layout round trip."""
+import datetime
+import json
+import os
+import random
+import tempfile
+
+import numpy as np
+import pytest
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _datasets():
+    d = json.load(open(os.path.join(G, "sampler_ref.json")))
+    len_dict = {int(k): list(v) for k, v in d["len_dict"].items()}
+    time_dict = {k: [{"click_t": datetime.datetime.fromisoformat(t["click_t"]),
+                      "publish_t": datetime.datetime.fromisoformat(t["publish_t"]), "active_t": t["active_t"]}
+                     for t in v] for k, v in d["time_dict"].items()}
+    item_dict = {"orig%d" % i: i + 1 for i in range(d["N"])}
+    impressions = {int(k): v for k, v in d["impressions"].items()}
+    return d, len_dict, d["session_dict"], time_dict, item_dict, impressions
+
+
+def test_product_sampler_reproduces_reference_batches():
+    """Same RNG streams, same shuffles, same negatives, same time features as sampler.py (bit-exact lists)."""
+    from tcar_b200.sampler import Sampler
+    d, len_dict, session_dict, time_dict, item_dict, impressions = _datasets()
+    for run in d["runs"]:
+        random.seed(2020)
+        np.random.seed(2020)
+        ld = {k: list(v) for k, v in len_dict.items()}
+        s = Sampler(ld, session_dict, time_dict, impressions, item_dict, run["neg_num"], batch_size=run["batch_size"],
+                    verbose=False)
+        got = []
+        while s.has_next():
+            b_in, b_out, pt, ct, neg, gap = s.next_batch()
+            got.append({"in": b_in, "out": b_out, "pt": [list(x) for x in pt], "ct": [list(x) for x in ct],
+                        "neg": neg, "gap": gap})
+        assert got == run["batches"]
+        assert [s.neg_neighbor_from_impre(i) for i in range(5)] == run["impre"]
+        assert {str(k): v for k, v in ld.items()} == run["shuffled_len_dict"]
+
+
+def test_next_packed_is_the_same_batch_in_one_buffer():
+    from tcar_b200.sampler import Sampler, pack_batch
+    d, len_dict, session_dict, time_dict, item_dict, impressions = _datasets()
+    run = d["runs"][0]
+    twins = []
+    for _ in range(2):
+        random.seed(7)
+        np.random.seed(7)
+        twins.append(Sampler({k: list(v) for k, v in len_dict.items()}, session_dict, time_dict, impressions, item_dict,
+                             run["neg_num"], batch_size=run["batch_size"], verbose=False))
+    a, b = twins
+    n = 0
+    while a.has_next():
+        # the two samplers share the global NumPy stream: draw them one after the other from the same state
+        state = np.random.get_state()
+        ref = a.next_batch()
+        np.random.set_state(state)
+        packed, B, T, Nn = b.next_packed()
+        want, B2, T2, Nn2 = pack_batch(*ref)
+        assert (B, T, Nn) == (B2, T2, Nn2)
+        np.testing.assert_array_equal(packed, want)
+        assert packed.dtype == np.int32 and packed.size == 7 * B * T + 3 * B + B * Nn
+        n += 1
+    assert n == len(run["batches"]) and not b.has_next()
+
+
+def test_dwell_bucket_is_clamped_to_the_table():
+    """bucketized(active_t >= 1024 s) = 11 is out of range for the 11-row duration table (sampler.py:18-21):
+    next_packed / pack_batch clamp it to 10 (documented deviation)."""
+    from tcar_b200.sampler import bucketized, pack_batch
+    assert bucketized(1023) == 10 and bucketized(1024) == 11
+    packed, B, T, Nn = pack_batch([[1, 2]], [0], ([[1, 1]], [[1, 1]], [[1, 1]], [[1, 1]], [[1, 1]]),
+                                  ([0], [0], [3], [5], [0]), [[]], [[11, 4]])
+    assert (B, T, Nn) == (1, 2, 0)
+    assert packed[6 * 2: 7 * 2].tolist() == [10, 4]
+    assert packed[7 * 2: 7 * 2 + 2].tolist() == [3, 5]          # click week, click hour
+
+
+def test_cau_metrics_match_reference():
+    from tcar_b200.util import cau_metrics
+    m = json.load(open(os.path.join(G, "metrics_ref.json")))
+    recall, mrr, ndcg = cau_metrics(np.array(m["preds"], dtype=np.float32), m["labels"], 20)
+    assert [bool(x) for x in recall] == m["recall"]
+    np.testing.assert_allclose(mrr, m["mrr"])
+    np.testing.assert_allclose(ndcg, m["ndcg"])
+
+
+def test_cli_keeps_the_reference_flags_and_defaults():
+    """main.py:94-123 -- 23 flags, names and defaults."""
+    from tcar_b200.main import build_parser
+    ref = {"datapath": "./data/", "dataset": "mind/TCAR-mid/", "split_way": "Normal/", "foldnum": 1,
+           "batch_size": 512, "lr": 0.001, "epoch": 10, "maxlen": 20, "neg_num": 20, "model": "model_combine",
+           "hidden_size": 250, "time_hidden_size": 64, "max_grad": 150, "stddev": 0.05, "emb_stddev": 0.002,
+           "dropout_rate": 0.5, "l2_emb": 0.0, "save": False, "is_print": False, "train": True,
+           "modelpath": "./ckpt/", "inputdata": "test", "threshold_acc": 0.27}
+    got = vars(build_parser().parse_args([]))
+    for k, v in ref.items():
+        assert got[k] == v, k
+    assert len(ref) == 23
+    # type=bool flags keep the reference quirk: any non-empty string is True (main.py:118-120)
+    assert build_parser().parse_args(["--train", "False"]).train is True
+
+
+def test_pickle_layout_round_trip():
+    """synth.write_dataset emits the reference's on-disk layout; util.data_partition / main.load_datas
+    read it back with the reference's 7-tuple / args keys."""
+    from tcar_b200 import main as tmain, synth
+    from tcar_b200.util import data_partition
+    with tempfile.TemporaryDirectory() as d:
+        root = d + "/synth/TCAR-mid/Normal/"
+        synth.write_dataset(root, N=300, n_train=120, n_test=40, fold=0)
+        train, test, item_dict, neighbor, content, publish, _ = data_partition(root, 0)
+        len_dict, session_dict, time_dict = train
+        assert len(item_dict) == 300 and content.shape == (301, 250) and np.all(content[0] == 0)
+        assert publish[1].shape == (300, 5) and len(publish[0]) == 300
+        for L, keys in len_dict.items():
+            for k in keys:
+                assert len(session_dict[k]) == L + 1 and len(time_dict[k]) == L + 1      # inputs + target
+                assert str(k).endswith("_%d" % L)                                        # train key "<sid>_<len>"
+        assert all(isinstance(k, int) for k in test[1])                                  # test key = sid
+        args = tmain.build_parser().parse_args(["--datapath", d + "/", "--dataset", "synth/TCAR-mid/", "--foldnum", "0"])
+        _, _, _, a, _ = tmain.load_datas(args)
+        for key in ("itemnum", "reverse_item", "category_id", "item_freq_dict_norm", "publish_time_MWDHM",
+                    "content_emb"):
+            assert key in a
+        assert a["reverse_item"][0] == "a0" and a["itemnum"] == 300
+
+
+def test_model_refuses_to_run_without_cuda():
+    """No CPU fallback: constructing the product model on a GPU-less host fails loudly."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("needs a GPU-less host")
+    from tcar_b200.model_combine import Seq2SeqAttNN
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Seq2SeqAttNN({"itemnum": 1})
