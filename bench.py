@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_kernels", action="store_true", help="skip the per-kernel roofline pass")
     ap.add_argument("--cpu_sample_sessions", type=int, default=512)
+    ap.add_argument("--loop_sessions", type=int, default=32768,
+                    help="sessions of the in-memory synthetic split used for the sampler-inclusive `train_loop` line")
     ap.add_argument("--profile_region", action="store_true",
                     help="for `ncu --profile-from-start off`: warm up, then ONE train step (T=20) and ONE eval step "
                          "between cudaProfilerStart/Stop; prints nothing")
@@ -455,6 +457,39 @@ def run_b200(a):
         eval_qp_ms = max_over_ranks(e0.elapsed_time(e1))
     clk = clocks.stop() if rank == 0 else None
 
+    # ---- the loop a user runs (Seq2SeqAttNN.train): reference-API Sampler on a host thread -> pinned ring -> H2D ->
+    # train_step, on an in-memory synthetic split with Globo-like session lengths
+    train_loop = None
+    if a.loop_sessions > 0:
+        import random as pyrandom
+        from tcar_b200.model_combine import prefetch_packed
+        from tcar_b200.sampler import Sampler
+        ld, sd, td, idict, impr = synth.make_sessions(N, a.loop_sessions, seed=2020 + rank)
+        pyrandom.seed(2020)
+        np.random.seed(2020)
+        t_h0 = time.perf_counter()
+        smp = Sampler(ld, sd, td, impr, idict, Nn, batch_size=B, verbose=False)
+        smp.next_packed()                                    # builds the columnar cache (once per split)
+        t_cache = time.perf_counter() - t_h0
+        smp = Sampler(ld, sd, td, impr, idict, Nn, batch_size=B, verbose=False)
+        nsess, nb = 0, 0
+        barrier()
+        t_w0 = time.perf_counter()
+        e0.record()
+        for packed, Bb, Tb, Nb in prefetch_packed(smp):
+            loss_dev = model.train_step(model.stage_to_device(packed, Bb, Tb, Nb))
+            nsess += Bb
+            nb += 1
+        loss_dev.cpu()
+        e1.record()
+        barrier()
+        loop_ms = max_over_ranks(e0.elapsed_time(e1))
+        train_loop = {"note": "Sampler.next_packed (host thread) -> pinned ring -> H2D -> train_step over one epoch of "
+                              "an in-memory synthetic split; length-bucketed batches, tail batches < 512 included",
+                      "value": world * nsess / (loop_ms * 1e-3), "unit": "sessions/s", "batches": nb,
+                      "sessions_per_rank": nsess, "ms_per_batch": loop_ms / nb,
+                      "wall_s": time.perf_counter() - t_w0, "columnar_cache_build_s": t_cache}
+
     kernels = {}
     traffic = {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -508,6 +543,7 @@ def run_b200(a):
             "t20": {"note": "same measurement with every batch at the reference --maxlen (T = 20)",
                     "value": sessions / (t20_ms * 1e-3), "ms_per_step": t20_ms / K,
                     "e2e_value": sessions / (t20_e2e_ms * 1e-3), "unit": "sessions/s"},
+            "train_loop": train_loop,
             "gpu_launches": launches, "launches_per_step": launches / K, "loss_last_step": loss_last,
             "clocks": clk, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu_baseline}
     print(json.dumps(line), flush=True)

@@ -37,6 +37,53 @@ class Batch:
         self.seq = buf[:M]
 
 
+def prefetch_packed(sampler, depth=4):
+    """Iterate `sampler.next_packed()` from a producer thread (NumPy gathers release the GIL), `depth` batches ahead
+    of the GPU.  One producer, FIFO queue: the RNG streams are consumed in exactly the order of a plain loop."""
+    import queue
+    import threading
+    q = queue.Queue(maxsize=depth)
+    done = object()
+
+    def work():
+        try:
+            while sampler.has_next():
+                q.put(sampler.next_packed())
+            q.put(done)
+        except BaseException as exc:          # surface producer errors in the consumer
+            q.put(exc)
+
+    threading.Thread(target=work, daemon=True).start()
+    while True:
+        item = q.get()
+        if item is done:
+            return
+        if isinstance(item, BaseException):
+            raise item
+        yield item
+
+
+class PinnedRing:
+    """A few reusable pinned staging buffers: pin_memory() per batch costs a cudaHostAlloc; a slot is reused only
+    after the H2D copy that read it has completed (event per slot)."""
+
+    def __init__(self, slots=4):
+        self.slots, self.bufs, self.events, self.i = slots, [None] * slots, [None] * slots, 0
+
+    def stage(self, packed):
+        i = self.i
+        self.i = (i + 1) % self.slots
+        if self.events[i] is not None:
+            self.events[i].synchronize()
+        n = packed.size
+        if self.bufs[i] is None or self.bufs[i].numel() < n:
+            self.bufs[i] = torch.empty(max(n, 1 << 16), dtype=torch.int32).pin_memory()
+        view = self.bufs[i][:n]
+        view.numpy()[:] = packed
+        self.events[i] = torch.cuda.Event()
+        return view, self.events[i]
+
+
 class Seq2SeqAttNN:
     def __init__(self, args):
         if not torch.cuda.is_available():
@@ -158,6 +205,15 @@ class Seq2SeqAttNN:
         buf = torch.empty(packed.numel(), device=self.dev, dtype=torch.int32)
         buf.copy_(packed, non_blocking=True)
         return Batch(buf, B, T, Nn)
+
+    def stage_to_device(self, packed_np, B, T, Nn):
+        """NumPy packed batch -> pinned ring slot -> device (the path of the train / test loops)."""
+        if getattr(self, "_ring", None) is None:
+            self._ring = PinnedRing()
+        view, ev = self._ring.stage(packed_np)
+        bt = self.to_device(view, B, T, Nn)
+        ev.record()
+        return bt
 
     def make_batch(self, batch_in, batch_out, batch_pt, batch_ct, neg, gap):
         """From the reference sampler's 6-tuple of Python lists (sampler.py:113) to a device Batch."""
@@ -486,15 +542,14 @@ class Seq2SeqAttNN:
             sampler = Sampler(len_dict_train, session_dict_train, session_time_dict_train, neighbor_dict, item_dict,
                               args["neg_num"], batch_size=self.batch_size)
             batch = 0
-            while sampler.has_next():
+            for packed, B, T, Nn in prefetch_packed(sampler):
                 batch += 1
-                packed, B, T, Nn = sampler.next_packed()
-                if batch < 3:
-                    print(sampler.last_neg[0][:10])
+                if batch < 3 and Nn:
+                    print(packed[7 * B * T + 3 * B: 7 * B * T + 3 * B + min(Nn, 10)].tolist())
                 if self.world > 1:
                     # every rank draws the same batch (same seeds, main.py:9-12) and keeps its slice of the sessions
                     packed, B, T, Nn = parallel.shard_packed(packed, B, T, Nn, self.rank, self.world)
-                bt = self.to_device(torch.from_numpy(packed).pin_memory(), B, T, Nn)
+                bt = self.stage_to_device(packed, B, T, Nn)
                 c.append(self.train_step(bt).clone())
             tot = torch.stack([torch.cat(c).sum(), torch.tensor(float(sum(len(x) for x in c)), device=self.dev)]) \
                 if c else torch.zeros(2, device=self.dev)
@@ -519,11 +574,11 @@ class Seq2SeqAttNN:
         sampler = Sampler(len_dict_test, session_dict_test, session_time_dict_test, batch_size=self.batch_size)
         resultItemDict = {}
         batch = 0
-        while sampler.has_next():
+        for packed, B, T, Nn in prefetch_packed(sampler):
             batch += 1
-            packed, B, T, Nn = sampler.next_packed()
-            batch_in, batch_out = sampler.last_in, sampler.last_out
-            bt = self.to_device(torch.from_numpy(packed).pin_memory(), B, T, Nn)
+            batch_in = packed[: B * T].reshape(B, T).tolist()
+            batch_out = packed[7 * B * T + 2 * B: 7 * B * T + 3 * B].tolist()
+            bt = self.stage_to_device(packed, B, T, Nn)
             shard = None
             if parallel.is_distributed(self.world):
                 # catalog-sharded evaluation: every rank scores all queries against its own item range

@@ -19,6 +19,41 @@ import random
 import numpy as np
 
 _FEATURE_CACHE = {}
+_COLUMNAR_CACHE = {}
+
+
+class _Columnar:
+    """Packed columnar view of one dataset split ("replace pickled-dict iteration with a packed columnar
+    cache"): per session length L, the item sequences [n, L+1], the six per-click features [6, n, L] (publish month,
+    day, isoweekday, hour+1, minute+1, clamped dwell bucket) and the click context [2, n] (isoweekday-1, hour), plus
+    key -> row.  Built once per (session_dict, session_time_dict) pair and reused by every epoch's Sampler."""
+
+    def __init__(self, session_dict, session_time_dict):
+        by_len = {}
+        for key, seq in session_dict.items():
+            by_len.setdefault(len(seq) - 1, []).append(key)
+        self.row, self.seq, self.feats, self.ctx = {}, {}, {}, {}
+        for L, keys in by_len.items():
+            n = len(keys)
+            seq = np.empty((n, L + 1), dtype=np.int32)
+            feats = np.empty((6, n, L), dtype=np.int32)
+            ctx = np.empty((2, n), dtype=np.int32)
+            for r, key in enumerate(keys):
+                self.row[key] = r
+                seq[r] = session_dict[key]
+                f, c = _session_features(session_time_dict[key])
+                feats[:, r, :] = f
+                ctx[0, r], ctx[1, r] = c[2], c[3]
+            np.minimum(feats[5], 10, out=feats[5])
+            self.seq[L], self.feats[L], self.ctx[L] = seq, feats, ctx
+
+
+def _columnar(session_dict, session_time_dict):
+    key = (id(session_dict), id(session_time_dict))
+    ent = _COLUMNAR_CACHE.get(key)
+    if ent is None or ent[0] is not session_dict or ent[1] is not session_time_dict:
+        ent = _COLUMNAR_CACHE[key] = (session_dict, session_time_dict, _Columnar(session_dict, session_time_dict))
+    return ent[2]
 
 
 def bucketized(seconds):
@@ -117,34 +152,45 @@ class Sampler(object):
         return batch_in, batch_out, pt, ct, neg_all, gap_all
 
     def next_packed(self):
-        """Same batch as next_batch() as one int32 array [7*B*T | 2*B | B | B*Nn] (see model_combine.Batch)."""
+        """Same batch as next_batch() as one int32 array [7*B*T | 2*B | B | B*Nn] (see model_combine.Batch), assembled
+        with array gathers from the columnar cache instead of a Python loop over clicks (~0.2 ms vs ~10 ms for 512
+        sessions).  Uniform negatives come from ONE np.random.randint call of shape [B, Nn]: the legacy global stream
+        yields exactly the values of the reference's B consecutive calls of size Nn (sampler.py:98-99)."""
         ids = self.session_id_batches[self.batch_i]
         B = len(ids)
         T = len(self.session_dict[ids[0]]) - 1
         Nn = self.neg_num if (self.neighbor_dict and self.neg_num) else 0
         M = B * T
+        col = _columnar(self.session_dict, self.session_time_dict)
+        rows = np.fromiter((col.row[k] for k in ids), dtype=np.int64, count=B)
+        seq = col.seq[T][rows]                                    # [B, T+1]
         out = np.empty(7 * M + 3 * B + B * Nn, dtype=np.int32)
         idx = out[: 7 * M].reshape(7, B, T)
-        ctx = out[7 * M: 7 * M + 2 * B].reshape(2, B)
+        idx[0] = seq[:, :T]
+        idx[1:] = col.feats[T][:, rows, :]
+        out[7 * M: 7 * M + 2 * B].reshape(2, B)[:] = col.ctx[T][:, rows]
         label = out[7 * M + 2 * B: 7 * M + 3 * B]
-        negs = out[7 * M + 3 * B:].reshape(B, Nn) if Nn else None
-        batch_in, neg_all = [], []
-        for b, sid in enumerate(ids):
-            seq = self.session_dict[sid]
-            batch_in.append(seq[:-1])
-            idx[0, b] = seq[:-1]
-            label[b] = seq[-1] - 1
-            feats, c = self._features(sid)
-            idx[1:6, b] = feats[:5]
-            idx[6, b] = np.minimum(feats[5], 10)
-            ctx[0, b], ctx[1, b] = c[2], c[3]
-            if Nn:
-                neg = self._negatives(sid)
-                negs[b] = neg
-                neg_all.append(neg)
+        label[:] = seq[:, T] - 1
+        negs = None
+        if Nn:
+            negs = out[7 * M + 3 * B:].reshape(B, Nn)
+            if self.negative_mode == "impression":
+                for b, sid in enumerate(ids):
+                    negs[b] = self._negatives(sid)
+            else:
+                negs[:] = np.random.randint(0, self.item_num, size=(B, Nn))
         self.batch_i += 1
-        self.last_in, self.last_out, self.last_neg = batch_in, label.tolist(), neg_all
+        self._last = (idx[0], label, negs)
+        self.last_in = self.last_out = self.last_neg = None       # materialised lazily (last_lists())
         return out, B, T, Nn
+
+    def last_lists(self):
+        """(batch_in, batch_out, neg) of the most recent next_packed() as Python lists (what next_batch() returns)."""
+        if self.last_in is None and getattr(self, "_last", None) is not None:
+            seq, label, negs = self._last
+            self.last_in, self.last_out = seq.tolist(), label.tolist()
+            self.last_neg = negs.tolist() if negs is not None else [[] for _ in range(len(label))]
+        return self.last_in, self.last_out, self.last_neg
 
     def neg_neighbor_from_impre(self, sessionid):
         """sampler.py:118-131."""

@@ -68,6 +68,30 @@ def unpack(packed, B, T, Nn):
     return d
 
 
+def make_sessions(N, n_sessions, max_len=20, seed=2020, p_len=0.55, train=True):
+    """In-memory session split in the reference's dict layout: (len_dict, session_dict, session_time_dict, item_dict,
+    impressions).  Lengths follow P(T) ~ p_len^T on [1, max_len], items Zipf(1.1)."""
+    rs = np.random.RandomState(seed)
+    t0 = datetime.datetime(2017, 10, 1)
+    publish_dt = [t0 + datetime.timedelta(minutes=int(m)) for m in rs.randint(0, 60 * 24 * 30, N)]
+    pr = p_len ** np.arange(1, max_len + 1)
+    lens = rs.choice(np.arange(1, max_len + 1), size=n_sessions, p=pr / pr.sum())
+    len_dict, sdict, tdict = {}, {}, {}
+    for sidx in range(n_sessions):
+        L = int(lens[sidx])
+        items = zipf_items(rs, N, L + 1).tolist()
+        key = "%d_%d" % (sidx, L) if train else sidx
+        sdict[key] = items
+        start = t0 + datetime.timedelta(days=31, seconds=int(rs.randint(0, 86400 * 14)))
+        tdict[key] = [{"click_t": start + datetime.timedelta(seconds=60 * j), "publish_t": publish_dt[it - 1],
+                       "delta_h": 1, "active_t": int(np.exp(rs.uniform(0, np.log(1023))))}
+                      for j, it in enumerate(items)]
+        len_dict.setdefault(L, []).append(key)
+    item_dict = {"a%d" % i: i + 1 for i in range(N)}
+    impressions = {sidx: ["a%d" % int(x) for x in rs.randint(0, N, 8)] for sidx in range(min(n_sessions, 64))}
+    return len_dict, sdict, tdict, item_dict, impressions
+
+
 def write_dataset(root, N=2000, n_train=5000, n_test=600, max_len=8, fold=0, seed=2020):
     """Write <root>/{len_dict,session_dict,session_time_dict}_{train,test}*.pkl, item_dict, content_weight,
     publish_time, item_freq_dict_norm, train/test_session, sess_impressions.mid and articles_category.pkl in the

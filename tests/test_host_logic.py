@@ -44,6 +44,47 @@ def test_product_sampler_reproduces_reference_batches():
         assert {str(k): v for k, v in ld.items()} == run["shuffled_len_dict"]
 
 
+def test_vectorised_next_packed_reproduces_reference_batches():
+    """The columnar / single-randint path yields the reference's batches (same shuffles, same negatives)."""
+    from tcar_b200.sampler import Sampler, pack_batch
+    d, len_dict, session_dict, time_dict, item_dict, impressions = _datasets()
+    for run in d["runs"]:
+        random.seed(2020)
+        np.random.seed(2020)
+        s = Sampler({k: list(v) for k, v in len_dict.items()}, session_dict, time_dict, impressions, item_dict,
+                    run["neg_num"], batch_size=run["batch_size"], verbose=False)
+        for ref in run["batches"]:
+            packed, B, T, Nn = s.next_packed()
+            want, *_ = pack_batch(ref["in"], ref["out"], ref["pt"], ref["ct"], ref["neg"], ref["gap"])
+            np.testing.assert_array_equal(packed, want)
+            b_in, b_out, neg = s.last_lists()
+            assert b_in == ref["in"] and b_out == ref["out"] and neg == ref["neg"]
+        assert not s.has_next()
+
+
+def test_prefetcher_preserves_order_and_content():
+    from tcar_b200.model_combine import prefetch_packed
+    from tcar_b200.sampler import Sampler
+    d, len_dict, session_dict, time_dict, item_dict, impressions = _datasets()
+    run = d["runs"][0]
+    outs = []
+    for use_thread in (False, True):
+        random.seed(5)
+        np.random.seed(5)
+        s = Sampler({k: list(v) for k, v in len_dict.items()}, session_dict, time_dict, impressions, item_dict,
+                    run["neg_num"], batch_size=run["batch_size"], verbose=False)
+        if use_thread:
+            outs.append([p.copy() for p, *_ in prefetch_packed(s, depth=2)])
+        else:
+            got = []
+            while s.has_next():
+                got.append(s.next_packed()[0].copy())
+            outs.append(got)
+    assert len(outs[0]) == len(outs[1]) > 0
+    for a, b in zip(*outs):
+        np.testing.assert_array_equal(a, b)
+
+
 def test_next_packed_is_the_same_batch_in_one_buffer():
     from tcar_b200.sampler import Sampler, pack_batch
     d, len_dict, session_dict, time_dict, item_dict, impressions = _datasets()

@@ -7,7 +7,7 @@ timeout -s KILL 600 python bench.py --steps 20 --warmup 5 --no_cpu_baseline > gp
 python - <<'PY'
 import json
 d=json.loads(open('gpurun_out/bench_quick.json').read().strip().splitlines()[-1])
-print("t20", d["t20"]); print("train", d["value"], "ms", d["ms_per_step"], 'e2e', d['e2e']['value'], 'eval', d['eval']['value'], d['clocks'], 'launches/step', d['launches_per_step'])
+print("t20", d["t20"]); print("loop", d["train_loop"]); print("train", d["value"], "ms", d["ms_per_step"], 'e2e', d['e2e']['value'], 'eval', d['eval']['value'], d['clocks'], 'launches/step', d['launches_per_step'])
 for k,v in d['kernels'].items(): print(f"{k:20s} {v['ms']*1000:8.1f} us  {v['achieved']:8.1f} {v['unit']} frac {v['frac']:.3f}")
 PY
 if [ "$1" == "ncu" ]; then
