@@ -41,6 +41,8 @@ def parse():
     ap.add_argument("--neg_num", type=int, default=20)
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_kernels", action="store_true", help="skip the per-kernel roofline pass")
+    ap.add_argument("--no_lookahead", action="store_true",
+                    help="call train_step(bt) without the next batch (no overlap of Adam with the next session forward)")
     ap.add_argument("--cpu_sample_sessions", type=int, default=512)
     ap.add_argument("--loop_sessions", type=int, default=32768,
                     help="sessions of the in-memory synthetic split used for the sampler-inclusive `train_loop` line")
@@ -272,7 +274,7 @@ def kernel_rooflines(torch, nv, model, bt, peaks, traffic):
         # reads p, m, v, g and writes p, m, v (7 x 250 floats per row) + the bf16 refresh of the scoring operand
         ("adam_item", "hbm", (N + 1) * (7.0 * 250 * 4 + 250 * 2),
          lambda: nv.call("tcar_adam_item", p(ps.item), p(ps.item_m), p(ps.item_v), p(ps.item_g), p(ps.sqnorm_item),
-                         p(ps.step), 0.0, model.max_grad_f, p(ps.iext), 0, N + 1)),
+                         p(ps.step), 0.0, model.max_grad_f, p(ps.iext), 0, N + 1, None, 0)),
         ("sqnorm_item_grad", "hbm", (N + 1) * 250 * 4.0,
          lambda: nv.call("tcar_sqnorm_big", p(ps.item_g), p(ps.norm_partial), p(ps.sqnorm_item), ps.item_g.numel())),
         # table rows read + X/P/D/CT written + the index words
@@ -374,15 +376,22 @@ def run_b200(a):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()           # samples cover warm-up + every timed loop below (a timed loop alone is ~60 ms)
+    # train_step(bt, next_bt): the train loop's one-batch look-ahead (Seq2SeqAttNN.train) -- the session forward of the
+    # next batch overlaps this step's table-wide Adam pass.  Every timed step therefore contains exactly one session
+    # forward (its successor's) and the step after the last timed one is launched the same way.
+    pipe = world == 1 and not a.no_lookahead
+    nxt = (lambda lst, i: lst[(i + 1) % len(lst)]) if pipe else (lambda lst, i: None)
     for i in range(W):
-        model.train_step(dev[i % nbatch])
+        model.train_step(dev[i % nbatch], nxt(dev, i))
+    model.sync_updates()
     barrier()
     nv.LAUNCHES["count"] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for i in range(K):
-        model.train_step(dev[i % nbatch])
+    for i in range(W, W + K):
+        model.train_step(dev[i % nbatch], nxt(dev, i))
+    model.sync_updates()
     e1.record()
     barrier()
     train_ms = max_over_ranks(e0.elapsed_time(e1))
@@ -390,13 +399,21 @@ def run_b200(a):
     loss_last = float(model.loss[:B].mean().item())
 
     # ---- end to end through the public API: pinned host batch -> H2D -> train_step -> D2H of the loss -------
-    for i in range(2):
-        model.train_step(model.to_device(host[i % nbatch], B, Ts[i % nbatch], Nn)).cpu()
+    def e2e_loop(hosts, lens, n):
+        """n steps, each: H2D of the NEXT batch (pinned -> device), train_step, D2H of this step's loss."""
+        bt = model.to_device(hosts[0], B, lens[0], Nn)
+        for i in range(n):
+            j = (i + 1) % len(hosts)
+            nb = model.to_device(hosts[j], B, lens[j], Nn)
+            loss_host = model.train_step(bt, nb if pipe else None).cpu()
+            bt = nb
+        model.sync_updates()
+        return loss_host
+
+    e2e_loop(host, Ts, 2)
     barrier()
     e0.record()
-    for i in range(K):
-        bt = model.to_device(host[i % nbatch], B, Ts[i % nbatch], Nn)
-        loss_host = model.train_step(bt).cpu()
+    e2e_loop(host, Ts, K)
     e1.record()
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
@@ -404,17 +421,18 @@ def run_b200(a):
     d2h = B * 4
     # ---- the same two measurements at the reference's --maxlen (every batch T = 20): the heaviest session side
     for i in range(2):
-        model.train_step(dev20[i % 4])
+        model.train_step(dev20[i % 4], nxt(dev20, i))
+    model.sync_updates()
     barrier()
     e0.record()
-    for i in range(K):
-        model.train_step(dev20[i % 4])
+    for i in range(2, 2 + K):
+        model.train_step(dev20[i % 4], nxt(dev20, i))
+    model.sync_updates()
     e1.record()
     barrier()
     t20_ms = max_over_ranks(e0.elapsed_time(e1))
     e0.record()
-    for i in range(K):
-        model.train_step(model.to_device(host20[i % 4], B, T, Nn)).cpu()
+    e2e_loop(host20, [T] * 4, K)
     e1.record()
     barrier()
     t20_e2e_ms = max_over_ranks(e0.elapsed_time(e1))
@@ -476,10 +494,15 @@ def run_b200(a):
         barrier()
         t_w0 = time.perf_counter()
         e0.record()
-        for packed, Bb, Tb, Nb in prefetch_packed(smp):
-            loss_dev = model.train_step(model.stage_to_device(packed, Bb, Tb, Nb))
-            nsess += Bb
+        staged = (model.stage_to_device(*x) for x in prefetch_packed(smp))
+        cur = next(staged, None)
+        while cur is not None:
+            nx = next(staged, None)
+            loss_dev = model.train_step(cur, nx if pipe else None)
+            nsess += cur.B
             nb += 1
+            cur = nx
+        model.sync_updates()
         loss_dev.cpu()
         e1.record()
         barrier()

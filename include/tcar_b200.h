@@ -215,9 +215,20 @@ int tcar_adam_small(float* theta, float* m, float* v, const float* g, const int3
                     int nseg, const int32_t* step, float lr, float max_grad, void* stream);
 /* item table rows [row0, row0 + nrows) of [N+1,256] (the pointers address the first row of the slice; iext is the
  * whole operand): also refreshes the item columns of Iext (bf16) in the same pass.  Whole table: row0 = 0,
- * nrows = N + 1; data-parallel training updates one contiguous slice per rank (parallel.py). */
+ * nrows = N + 1; data-parallel training updates one contiguous slice per rank (parallel.py).
+ * The six pad columns of the 256-float pitch are not touched.  `row_flags` (optional, [N+1] int32, indexed by
+ * absolute row): rows whose flag equals the step number t were already updated by tcar_adam_item_rows and are skipped.
+ * `ctas_per_sm`: 0 = default grid (16 CTAs per SM); a small value (1..4) leaves SM resources free for kernels running
+ * concurrently on another stream (the next batch's session forward, Seq2SeqAttNN.train_step). */
 int tcar_adam_item(float* item, float* m, float* v, const float* g, const float* sqnorm, const int32_t* step,
-                   float lr, float max_grad, void* iext_bf16, int row0, int nrows, void* stream);
+                   float lr, float max_grad, void* iext_bf16, int row0, int nrows, const int32_t* row_flags,
+                   int ctas_per_sm, void* stream);
+/* The same update (same arithmetic, so bit-identical results) for the rows the NEXT batch will gather before the
+ * table-wide pass has finished: rows seq[0..n_seq) and label[0..n_label) + 1 of the whole [n_rows,256] table.  Each
+ * listed row is claimed once by writing t into row_flags[row]; duplicates and out-of-range ids are ignored. */
+int tcar_adam_item_rows(float* item, float* m, float* v, const float* g, const float* sqnorm, const int32_t* step,
+                        float lr, float max_grad, void* iext_bf16, const int32_t* seq, int n_seq,
+                        const int32_t* label, int n_label, int32_t* row_flags, int n_rows, void* stream);
 /* item columns of Iext from the fp32 item table (after all-gathering slices updated by other ranks). */
 int tcar_refresh_iext_items(const float* item, void* iext_bf16, int N, void* stream);
 

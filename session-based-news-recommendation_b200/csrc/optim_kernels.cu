@@ -188,42 +188,97 @@ adam_small_kernel(float* __restrict__ theta, float* __restrict__ m, float* __res
 }
 
 // item table [N+1, 256]: one float4 per thread per step; also re-quantises the row into Iext (bf16).
+// The six pad columns of the 256-float pitch (float4 slot 63 of every row) are neither read nor written.
+// `flags` (optional, one int32 per table row): rows whose flag equals the current step number were already updated by
+// adam_item_rows_kernel (the rows the next batch gathers, see Seq2SeqAttNN.train_step) and are skipped here.
+__device__ __forceinline__ void store_iext_items(__nv_bfloat16* __restrict__ iext, long long row, int c, const float4 p) {
+    if (row >= 1) {
+        __nv_bfloat16* dst = iext + (size_t)(row - 1) * KEXT + c;
+        *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(p.x, p.y);
+        if (c + 2 < H) *reinterpret_cast<__nv_bfloat162*>(dst + 2) = __floats2bfloat162_rn(p.z, p.w);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 adam_item_kernel(float4* __restrict__ item, float4* __restrict__ m, float4* __restrict__ v,
                  const float4* __restrict__ g, const float* __restrict__ sqnorm, const int32_t* __restrict__ step,
-                 float lr, float max_grad, __nv_bfloat16* __restrict__ iext, long long n4, long long row0) {
+                 float lr, float max_grad, __nv_bfloat16* __restrict__ iext, long long n4, long long row0,
+                 const int32_t* __restrict__ flags) {
+    const int t = step[0];
     const float cf = clip_factor(sqnorm[0], max_grad);
-    const float lr_t = adam_lr_t(step[0], lr);
+    const float lr_t = adam_lr_t(t, lr);
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += 2 * stride) {
         // two independent float4 streams per thread: all eight loads are in flight before the first use
         const long long i1 = i0 + stride;
-        const bool two = i1 < n4;
-        float4 p0 = item[i0], m0 = m[i0], v0 = v[i0];
-        const float4 g0 = g[i0];
-        float4 p1 = p0, m1 = m0, v1 = v0, g1 = g0;
-        if (two) { p1 = item[i1]; m1 = m[i1]; v1 = v[i1]; g1 = g[i1]; }
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (u == 1 && !two) break;
-            const long long i = u ? i1 : i0;
-            float4& p = u ? p1 : p0;
-            float4& mm = u ? m1 : m0;
-            float4& vv = u ? v1 : v0;
-            const float4 gg = u ? g1 : g0;
-            adam_update(p.x, mm.x, vv.x, gg.x * cf, lr_t);
-            adam_update(p.y, mm.y, vv.y, gg.y * cf, lr_t);
-            adam_update(p.z, mm.z, vv.z, gg.z * cf, lr_t);
-            adam_update(p.w, mm.w, vv.w, gg.w * cf, lr_t);
-            item[i] = p; m[i] = mm; v[i] = vv;
-            const long long row = row0 + (i >> 6);   // 64 float4 per 256-float row; row0 = first row of this slice
-            const int c = (int)(i & 63) * 4;
-            if (row >= 1 && c < H) {
-                __nv_bfloat16* dst = iext + (size_t)(row - 1) * KEXT + c;
-                *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(p.x, p.y);
-                if (c + 2 < H) *reinterpret_cast<__nv_bfloat162*>(dst + 2) = __floats2bfloat162_rn(p.z, p.w);
-            }
+        bool on0 = (i0 & 63) != 63, on1 = i1 < n4 && (i1 & 63) != 63;
+        if (flags) {
+            if (on0 && flags[row0 + (i0 >> 6)] == t) on0 = false;
+            if (on1 && flags[row0 + (i1 >> 6)] == t) on1 = false;
         }
+        float4 p0, m0, v0, g0, p1, m1, v1, g1;
+        if (on0) { p0 = item[i0]; m0 = m[i0]; v0 = v[i0]; g0 = g[i0]; }
+        if (on1) { p1 = item[i1]; m1 = m[i1]; v1 = v[i1]; g1 = g[i1]; }
+        if (on0) {
+            adam_update(p0.x, m0.x, v0.x, g0.x * cf, lr_t);
+            adam_update(p0.y, m0.y, v0.y, g0.y * cf, lr_t);
+            adam_update(p0.z, m0.z, v0.z, g0.z * cf, lr_t);
+            adam_update(p0.w, m0.w, v0.w, g0.w * cf, lr_t);
+            item[i0] = p0; m[i0] = m0; v[i0] = v0;
+            store_iext_items(iext, row0 + (i0 >> 6), (int)(i0 & 63) * 4, p0);
+        }
+        if (on1) {
+            adam_update(p1.x, m1.x, v1.x, g1.x * cf, lr_t);
+            adam_update(p1.y, m1.y, v1.y, g1.y * cf, lr_t);
+            adam_update(p1.z, m1.z, v1.z, g1.z * cf, lr_t);
+            adam_update(p1.w, m1.w, v1.w, g1.w * cf, lr_t);
+            item[i1] = p1; m[i1] = m1; v[i1] = v1;
+            store_iext_items(iext, row0 + (i1 >> 6), (int)(i1 & 63) * 4, p1);
+        }
+    }
+}
+
+// The same update for a short list of rows, ahead of the table-wide pass: one warp per entry (the clicked items of
+// the NEXT batch, then its labels + 1).  A row listed several times is claimed once (atomicExch of the step number
+// into its flag); adam_item_kernel skips every claimed row, so each row is updated exactly once per step by the same
+// arithmetic whichever kernel does it.
+__global__ void __launch_bounds__(256)
+adam_item_rows_kernel(float4* __restrict__ item, float4* __restrict__ m, float4* __restrict__ v,
+                      const float4* __restrict__ g, const float* __restrict__ sqnorm,
+                      const int32_t* __restrict__ step, float lr, float max_grad, __nv_bfloat16* __restrict__ iext,
+                      const int32_t* __restrict__ seq, int n_seq, const int32_t* __restrict__ label, int n_label,
+                      int32_t* __restrict__ flags, int n_rows) {
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (e >= n_seq + n_label) return;
+    const int row = e < n_seq ? seq[e] : label[e - n_seq] + 1;
+    if (row < 0 || row >= n_rows) return;
+    const int t = step[0];
+    int old = 0;
+    if (lane == 0) old = atomicExch(&flags[row], t);
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if (old == t) return;
+    const float cf = clip_factor(sqnorm[0], max_grad);
+    const float lr_t = adam_lr_t(t, lr);
+    const size_t base = (size_t)row * (HP / 4);
+    const bool two = lane < 31;                       // float4 slot 63 = pad columns
+    const size_t i0 = base + lane, i1 = base + 32 + lane;
+    float4 p0 = item[i0], m0 = m[i0], v0 = v[i0];
+    const float4 g0 = g[i0];
+    float4 p1 = p0, m1 = m0, v1 = v0, g1 = g0;
+    if (two) { p1 = item[i1]; m1 = m[i1]; v1 = v[i1]; g1 = g[i1]; }
+    adam_update(p0.x, m0.x, v0.x, g0.x * cf, lr_t);
+    adam_update(p0.y, m0.y, v0.y, g0.y * cf, lr_t);
+    adam_update(p0.z, m0.z, v0.z, g0.z * cf, lr_t);
+    adam_update(p0.w, m0.w, v0.w, g0.w * cf, lr_t);
+    item[i0] = p0; m[i0] = m0; v[i0] = v0;
+    store_iext_items(iext, row, lane * 4, p0);
+    if (two) {
+        adam_update(p1.x, m1.x, v1.x, g1.x * cf, lr_t);
+        adam_update(p1.y, m1.y, v1.y, g1.y * cf, lr_t);
+        adam_update(p1.z, m1.z, v1.z, g1.z * cf, lr_t);
+        adam_update(p1.w, m1.w, v1.w, g1.w * cf, lr_t);
+        item[i1] = p1; m[i1] = m1; v[i1] = v1;
+        store_iext_items(iext, row, (32 + lane) * 4, p1);
     }
 }
 
@@ -280,12 +335,27 @@ extern "C" int tcar_adam_small(float* theta, float* m, float* v, const float* g,
 
 extern "C" int tcar_adam_item(float* item, float* m, float* v, const float* g, const float* sqnorm,
                               const int32_t* step, float lr, float max_grad, void* iext_bf16, int row0, int nrows,
-                              void* stream) {
-    if (row0 < 0 || nrows < 1) return TCAR_ERR_ARG;
+                              const int32_t* row_flags, int ctas_per_sm, void* stream) {
+    if (row0 < 0 || nrows < 1 || ctas_per_sm < 0 || ctas_per_sm > 32) return TCAR_ERR_ARG;
     const long long n4 = (long long)nrows * (HP / 4);
-    adam_item_kernel<<<148 * 16, 256, 0, STREAM>>>(reinterpret_cast<float4*>(item), reinterpret_cast<float4*>(m),
-                                                   reinterpret_cast<float4*>(v), reinterpret_cast<const float4*>(g),
-                                                   sqnorm, step, lr, max_grad,
-                                                   static_cast<__nv_bfloat16*>(iext_bf16), n4, (long long)row0);
+    const int grid = 148 * (ctas_per_sm ? ctas_per_sm : 16);
+    adam_item_kernel<<<grid, 256, 0, STREAM>>>(reinterpret_cast<float4*>(item), reinterpret_cast<float4*>(m),
+                                               reinterpret_cast<float4*>(v), reinterpret_cast<const float4*>(g),
+                                               sqnorm, step, lr, max_grad, static_cast<__nv_bfloat16*>(iext_bf16), n4,
+                                               (long long)row0, row_flags);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int tcar_adam_item_rows(float* item, float* m, float* v, const float* g, const float* sqnorm,
+                                   const int32_t* step, float lr, float max_grad, void* iext_bf16,
+                                   const int32_t* seq, int n_seq, const int32_t* label, int n_label,
+                                   int32_t* row_flags, int n_rows, void* stream) {
+    if (n_seq < 0 || n_label < 0 || n_rows < 1 || !row_flags) return TCAR_ERR_ARG;
+    const int entries = n_seq + n_label;
+    if (entries == 0) return 0;
+    adam_item_rows_kernel<<<(entries + 7) / 8, 256, 0, STREAM>>>(
+        reinterpret_cast<float4*>(item), reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v),
+        reinterpret_cast<const float4*>(g), sqnorm, step, lr, max_grad, static_cast<__nv_bfloat16*>(iext_bf16), seq,
+        n_seq, label, n_label, row_flags, n_rows);
     return (int)cudaGetLastError();
 }

@@ -36,7 +36,14 @@ __device__ __forceinline__ float clip_scale(float sq) {
 
 // ------------------------------------------------------------------------------------------------ (1) gather
 // one warp per click (rows of X/P/D) and one warp per session for the click-time context CT.
-__global__ void __launch_bounds__(256)
+// A row of X is 125 aligned float4 slots: slots 0..61 hold item+pos columns 0..247, slot 62 holds item+pos columns
+// 248,249 and content columns 0,1, slots 63..124 hold content columns 2..249.  Lane l owns slots l, l+32, l+64, l+96,
+// fetches exactly the source words that land in them (float4 / float2 loads, all issued before the first use) and
+// writes each slot with one 128-bit store, so a warp store instruction covers 512 contiguous bytes.
+__device__ __forceinline__ float sq4(const float4 v) { return v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w; }
+__device__ __forceinline__ float4 join2(const float2 a, const float2 b) { return make_float4(a.x, a.y, b.x, b.y); }
+
+__global__ void __launch_bounds__(128)
 gather_fwd_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ ctx, const float* __restrict__ item,
                   const float* __restrict__ content, const float* __restrict__ pos,
                   const float* __restrict__ month, const float* __restrict__ day, const float* __restrict__ week,
@@ -48,46 +55,78 @@ gather_fwd_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ c
     const int lane = threadIdx.x & 31;
     if (w < M) {
         const int m = w, t = m % T;
-        const int id = idx[m];
-        // item + content rows: 256-float pitch, two 128-bit loads per lane each
-        const float4* ir = reinterpret_cast<const float4*>(item + (size_t)id * HP);
-        const float4* cr = reinterpret_cast<const float4*>(content + (size_t)id * HP);
-        const float4 i0 = __ldg(ir + lane), i1 = __ldg(ir + 32 + lane);
-        const float4 c0 = __ldg(cr + lane), c1 = __ldg(cr + 32 + lane);
-        const float si = clip_scale(warp_sum(i0.x * i0.x + i0.y * i0.y + i0.z * i0.z + i0.w * i0.w + i1.x * i1.x +
-                                             i1.y * i1.y + i1.z * i1.z + i1.w * i1.w));
-        const float sc = clip_scale(warp_sum(c0.x * c0.x + c0.y * c0.y + c0.z * c0.z + c0.w * c0.w + c1.x * c1.x +
-                                             c1.y * c1.y + c1.z * c1.z + c1.w * c1.w));
-        // position row t (unpadded [40,250])
-        const float* pr = pos + (size_t)t * H;
-        float pv[8];
-        float psq = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = (j < 4) ? lane * 4 + j : 128 + lane * 4 + (j - 4);
-            pv[j] = c < H ? __ldg(pr + c) : 0.f;
-            psq += pv[j] * pv[j];
-        }
-        const float sp = clip_scale(warp_sum(psq));
-        float* xr = X + (size_t)m * XW;
-        const float iv[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
-        const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = (j < 4) ? lane * 4 + j : 128 + lane * 4 + (j - 4);
-            if (c < H) {
-                xr[c] = iv[j] * si + pv[j] * sp;
-                xr[H + c] = cv[j] * sc;
-            }
-        }
-        // five publish-time rows and the dwell-time row, 64 floats each: one float2 per lane
+        // the seven index words of the click: lanes 0..6 fetch one each
+        const int my = lane < 7 ? __ldg(idx + (size_t)lane * M + m) : 0;
+        const int id = __shfl_sync(0xffffffffu, my, 0);
+        const float4* ir4 = reinterpret_cast<const float4*>(item + (size_t)id * HP);
+        const float2* ir2 = reinterpret_cast<const float2*>(item + (size_t)id * HP);
+        const float2* cr2 = reinterpret_cast<const float2*>(content + (size_t)id * HP);
+        const float2* pr2 = reinterpret_cast<const float2*>(pos + (size_t)t * H);     // rows of 1000 B: 8-byte aligned
         const float* tabs[6] = {month, day, week, hour, minute, dur};
+        float2 tv[6];
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
-            const int r = idx[(size_t)(k + 1) * M + m];
-            const float2 v = __ldg(reinterpret_cast<const float2*>(tabs[k] + (size_t)r * TH) + lane);
-            const float s = clip_scale(warp_sum(v.x * v.x + v.y * v.y));
-            float2 o = make_float2(v.x * s, v.y * s);
+            const int r = __shfl_sync(0xffffffffu, my, k + 1);
+            tv[k] = __ldg(reinterpret_cast<const float2*>(tabs[k] + (size_t)r * TH) + lane);
+        }
+        // slot 0 (item + pos), slot 1 (item + pos | mixed | content), slots 2, 3 (content)
+        const float4 a0 = __ldg(ir4 + lane);
+        const float4 p0 = join2(__ldg(pr2 + 2 * lane), __ldg(pr2 + 2 * lane + 1));
+        float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = a1;
+        float sqi = sq4(a0), sqp = sq4(p0), sqc = 0.f;
+        if (lane < 30) {
+            a1 = __ldg(ir4 + 32 + lane);
+            p1 = join2(__ldg(pr2 + 64 + 2 * lane), __ldg(pr2 + 65 + 2 * lane));
+            sqi += sq4(a1);
+            sqp += sq4(p1);
+        } else if (lane == 30) {
+            const float2 i2 = __ldg(ir2 + 124), q2 = __ldg(pr2 + 124), c2 = __ldg(cr2);
+            a1 = join2(i2, c2);
+            p1 = make_float4(q2.x, q2.y, 0.f, 0.f);
+            sqi += i2.x * i2.x + i2.y * i2.y;
+            sqp += q2.x * q2.x + q2.y * q2.y;
+            sqc += c2.x * c2.x + c2.y * c2.y;
+        } else {
+            a1 = join2(__ldg(cr2 + 1), __ldg(cr2 + 2));                                  // slot 63: content 2..5
+            sqc += sq4(a1);
+        }
+        // slot f >= 63 holds content columns 4 (f - 63) + 2 .. + 5  =  float2 words 2 (f - 63) + 1, + 2
+        const float4 a2 = join2(__ldg(cr2 + 2 * lane + 3), __ldg(cr2 + 2 * lane + 4));   // f = 64 + lane
+        float4 a3 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < 29) a3 = join2(__ldg(cr2 + 2 * lane + 67), __ldg(cr2 + 2 * lane + 68));   // f = 96 + lane
+        sqc += sq4(a2) + sq4(a3);
+        float tsq[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) tsq[k] = tv[k].x * tv[k].x + tv[k].y * tv[k].y;
+        // nine independent butterfly reductions, interleaved
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sqi += __shfl_xor_sync(0xffffffffu, sqi, o);
+            sqp += __shfl_xor_sync(0xffffffffu, sqp, o);
+            sqc += __shfl_xor_sync(0xffffffffu, sqc, o);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) tsq[k] += __shfl_xor_sync(0xffffffffu, tsq[k], o);
+        }
+        const float si = clip_scale(sqi), sp = clip_scale(sqp), sc = clip_scale(sqc);
+        float4* x4 = reinterpret_cast<float4*>(X + (size_t)m * XW);
+        x4[lane] = make_float4(fmaf(p0.x, sp, a0.x * si), fmaf(p0.y, sp, a0.y * si), fmaf(p0.z, sp, a0.z * si),
+                               fmaf(p0.w, sp, a0.w * si));
+        float4 o1;
+        if (lane < 30)
+            o1 = make_float4(fmaf(p1.x, sp, a1.x * si), fmaf(p1.y, sp, a1.y * si), fmaf(p1.z, sp, a1.z * si),
+                             fmaf(p1.w, sp, a1.w * si));
+        else if (lane == 30)
+            o1 = make_float4(fmaf(p1.x, sp, a1.x * si), fmaf(p1.y, sp, a1.y * si), a1.z * sc, a1.w * sc);
+        else
+            o1 = make_float4(a1.x * sc, a1.y * sc, a1.z * sc, a1.w * sc);
+        x4[32 + lane] = o1;
+        x4[64 + lane] = make_float4(a2.x * sc, a2.y * sc, a2.z * sc, a2.w * sc);
+        if (lane < 29) x4[96 + lane] = make_float4(a3.x * sc, a3.y * sc, a3.z * sc, a3.w * sc);
+        // five publish-time rows and the dwell-time row, 64 floats each: one float2 per lane
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            const float s = clip_scale(tsq[k]);
+            const float2 o = make_float2(tv[k].x * s, tv[k].y * s);
             if (k < 5) reinterpret_cast<float2*>(P + (size_t)m * PW + k * TH)[lane] = o;
             else reinterpret_cast<float2*>(D + (size_t)m * TH)[lane] = o;
         }
@@ -112,7 +151,7 @@ __device__ __forceinline__ float dot4(const float4 a, const float4 b) {
     return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 pool_fwd_kernel(const float* __restrict__ X, const float* __restrict__ P, float* __restrict__ U1,
                 float* __restrict__ U2, const float* __restrict__ q, const float* __restrict__ w_r,
                 const float* __restrict__ w_t, float* __restrict__ alpha, float* __restrict__ pooled,
@@ -195,7 +234,7 @@ pool_fwd_kernel(const float* __restrict__ X, const float* __restrict__ P, float*
 }
 
 // ------------------------------------------------------------------------------------------------ (2b) pooling bwd
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 pool_bwd_kernel(const float* __restrict__ X, const float* __restrict__ P, const float* __restrict__ S1,
                 const float* __restrict__ S2, const float* __restrict__ q, const float* __restrict__ w_r,
                 const float* __restrict__ w_t, const float* __restrict__ alpha, const float* __restrict__ dpooled,
@@ -365,14 +404,17 @@ build_query_kernel(const float* __restrict__ a_ic, const float* __restrict__ a_p
     for (int c = threadIdx.x; c < XW; c += blockDim.x) s_aic[c] = a_ic[(size_t)b * XW + c];
     for (int c = threadIdx.x; c < PW; c += blockDim.x) s_apt[c] = a_pt[(size_t)b * PW + c];
     __syncthreads();
-    if (threadIdx.x < NB) {
-        const int r = threadIdx.x;
-        int k = 0;
-        while (r >= kBinOff[k + 1]) ++k;
-        float acc = 0.f;
-        for (int d = 0; d < TH; ++d) acc = fmaf(s_apt[k * TH + d], ct_tab[(size_t)r * TH + d], acc);
-        s_tq[r] = acc;
-        Tq[(size_t)b * NB + r] = acc;
+    {
+        // Tq[b, r] = a_pt[b, 64 k : 64 k + 64] . clip(table_k)[r]: one warp per table row, coalesced 256-byte row
+        // reads, six rows in flight per warp (the 139 rows are spread over the 8 warps)
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll 6
+        for (int r = w; r < NB; r += 8) {
+            const int k = (r >= 13) + (r >= 45) + (r >= 53) + (r >= 78);
+            const float v0 = __ldg(ct_tab + (size_t)r * TH + lane), v1 = __ldg(ct_tab + (size_t)r * TH + 32 + lane);
+            const float acc = warp_sum(fmaf(v0, s_apt[k * TH + lane], v1 * s_apt[k * TH + 32 + lane]));
+            if (lane == 0) { s_tq[r] = acc; Tq[(size_t)b * NB + r] = acc; }
+        }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < TCAR_KEXT; c += blockDim.x) {
@@ -504,11 +546,21 @@ score_bwd_finish_kernel(const float* __restrict__ dq_raw, const float* __restric
         dTq[(size_t)b * NB + r] = v;
     }
     __syncthreads();
+    // d a_pt[b, 64 k + d] = sum_{r in table k} dTq[b, r] clip(table_k)[r, d]: four independent partial sums per
+    // thread so that the (L1-resident) table reads overlap
     for (int c = threadIdx.x; c < PW; c += blockDim.x) {
         const int k = c / TH, d = c % TH;
-        float acc = 0.f;
-        for (int r = kBinOff[k]; r < kBinOff[k + 1]; ++r) acc = fmaf(s_dt[r], ct_tab[(size_t)r * TH + d], acc);
-        d_a_pt[(size_t)b * PW + c] = acc;
+        const int r1 = kBinOff[k + 1];
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        int r = kBinOff[k];
+        for (; r + 4 <= r1; r += 4) {
+            const float t0 = __ldg(ct_tab + (size_t)r * TH + d), t1 = __ldg(ct_tab + (size_t)(r + 1) * TH + d);
+            const float t2 = __ldg(ct_tab + (size_t)(r + 2) * TH + d), t3 = __ldg(ct_tab + (size_t)(r + 3) * TH + d);
+            a0 = fmaf(s_dt[r], t0, a0); a1 = fmaf(s_dt[r + 1], t1, a1);
+            a2 = fmaf(s_dt[r + 2], t2, a2); a3 = fmaf(s_dt[r + 3], t3, a3);
+        }
+        for (; r < r1; ++r) a0 = fmaf(s_dt[r], __ldg(ct_tab + (size_t)r * TH + d), a0);
+        d_a_pt[(size_t)b * PW + c] = (a0 + a1) + (a2 + a3);
     }
 }
 
@@ -604,9 +656,18 @@ table_finish_kernel(const float* __restrict__ part, int nchunk, const float* __r
         g = g_pos + (size_t)row * H;
         const int c = threadIdx.x;
         float acc = 0.f;
-        if (row < T && c < H)
-            for (int j = 0; j < nchunk; ++j)
-                acc += part[(size_t)j * TG_PART_FLOATS + TG_BIN_FLOATS + TG_DUR_FLOATS + (size_t)row * H + c];
+        if (row < T && c < H) {
+            // chunk partials in a fixed order, four independent running sums so that the loads overlap
+            const float* src = part + TG_BIN_FLOATS + TG_DUR_FLOATS + (size_t)row * H + c;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            int j = 0;
+            for (; j + 4 <= nchunk; j += 4) {
+                a0 += src[(size_t)j * TG_PART_FLOATS]; a1 += src[(size_t)(j + 1) * TG_PART_FLOATS];
+                a2 += src[(size_t)(j + 2) * TG_PART_FLOATS]; a3 += src[(size_t)(j + 3) * TG_PART_FLOATS];
+            }
+            for (; j < nchunk; ++j) a0 += src[(size_t)j * TG_PART_FLOATS];
+            acc = (a0 + a1) + (a2 + a3);
+        }
         s_g[threadIdx.x] = acc;
     } else {
         width = TH;
@@ -621,15 +682,42 @@ table_finish_kernel(const float* __restrict__ part, int nchunk, const float* __r
             float* gs[5] = {g_month, g_day, g_week, g_hour, g_minute};
             x = tabs[k] + (size_t)rr * TH;
             g = gs[k] + (size_t)rr * TH;
-            for (int j = grp; j < nchunk; j += 4) acc += part[(size_t)j * TG_PART_FLOATS + (size_t)r * TH + d];
+            {
+                const float* src = part + (size_t)r * TH + d;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                int j = grp;
+                for (; j + 12 < nchunk; j += 16) {
+                    a0 += src[(size_t)j * TG_PART_FLOATS]; a1 += src[(size_t)(j + 4) * TG_PART_FLOATS];
+                    a2 += src[(size_t)(j + 8) * TG_PART_FLOATS]; a3 += src[(size_t)(j + 12) * TG_PART_FLOATS];
+                }
+                for (; j < nchunk; j += 4) a0 += src[(size_t)j * TG_PART_FLOATS];
+                acc = (a0 + a1) + (a2 + a3);
+            }
             // scoring side: d/d clip(table)[r] of sum_b Tq[b,r] = sum_b dTq[b,r] a_pt[b, 64k:64k+64]
-            for (int b = grp; b < B; b += 4) acc = fmaf(dTq[(size_t)b * NB + r], a_pt[(size_t)b * PW + k * TH + d], acc);
+            {
+                const float* dq = dTq + r;
+                const float* ap = a_pt + k * TH + d;
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                int b = grp;
+                for (; b + 12 < B; b += 16) {
+                    a0 = fmaf(dq[(size_t)b * NB], ap[(size_t)b * PW], a0);
+                    a1 = fmaf(dq[(size_t)(b + 4) * NB], ap[(size_t)(b + 4) * PW], a1);
+                    a2 = fmaf(dq[(size_t)(b + 8) * NB], ap[(size_t)(b + 8) * PW], a2);
+                    a3 = fmaf(dq[(size_t)(b + 12) * NB], ap[(size_t)(b + 12) * PW], a3);
+                }
+                for (; b < B; b += 4) a0 = fmaf(dq[(size_t)b * NB], ap[(size_t)b * PW], a0);
+                acc += (a0 + a1) + (a2 + a3);
+            }
         } else {
             const int rr = r - NB;
             x = dur + (size_t)rr * TH;
             g = g_dur + (size_t)rr * TH;
-            for (int j = grp; j < nchunk; j += 4)
-                acc += part[(size_t)j * TG_PART_FLOATS + TG_BIN_FLOATS + (size_t)rr * TH + d];
+            const float* src = part + TG_BIN_FLOATS + (size_t)rr * TH + d;
+            float a0 = 0.f, a1 = 0.f;
+            int j = grp;
+            for (; j + 4 < nchunk; j += 8) { a0 += src[(size_t)j * TG_PART_FLOATS]; a1 += src[(size_t)(j + 4) * TG_PART_FLOATS]; }
+            for (; j < nchunk; j += 4) a0 += src[(size_t)j * TG_PART_FLOATS];
+            acc = a0 + a1;
         }
         s_acc[threadIdx.x] = acc;
         __syncthreads();
@@ -700,6 +788,9 @@ scatter_accum_kernel(const int32_t* __restrict__ seq, const int32_t* __restrict_
     if (e >= M + B + B * Nn) return;
     const int row = entry_row(e, M, B, seq, label, neg);
     float val[8];
+    bool jac_on = false;
+    float jac_s = 1.f, jac_ydy = 0.f, sc_b = 0.f;
+    int b_idx = 0;
     if (e < M) {
         const float4* ir = reinterpret_cast<const float4*>(item + (size_t)row * HP);
         const float4 i0 = __ldg(ir + lane), i1 = __ldg(ir + 32 + lane);
@@ -721,6 +812,7 @@ scatter_accum_kernel(const int32_t* __restrict__ seq, const int32_t* __restrict_
         if (n > 1.f) {
             const float s = 1.f / n;
             const float ydy = xdy * s;  // y . dy
+            jac_on = true; jac_s = s; jac_ydy = ydy;
 #pragma unroll
             for (int j = 0; j < 8; ++j) val[j] = s * (dy[j] - xv[j] * s * ydy);
         } else {
@@ -732,6 +824,7 @@ scatter_accum_kernel(const int32_t* __restrict__ seq, const int32_t* __restrict_
         float scale;
         if (e < M + B) { b = e - M; scale = -1.f; }
         else { b = (e - M - B) / Nn; scale = coef[b]; }
+        b_idx = b; sc_b = scale;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int c = (j < 4) ? lane * 4 + j : 128 + lane * 4 + (j - 4);
@@ -753,43 +846,62 @@ scatter_accum_kernel(const int32_t* __restrict__ seq, const int32_t* __restrict_
         d = warp_sum(d);
         if (lane == 0 && slot_sq) slot_sq[slot] = d;
     } else {
+        // shared row: exact fixed-point accumulation.  Values are re-derived with lane <-> consecutive column (the
+        // operands were just fetched, so these are L1 hits): one warp-wide atomic instruction then covers 256
+        // contiguous bytes (8 sectors) instead of 32 scattered sectors.
         unsigned long long* dst = acc + (size_t)slot * HP;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = (j < 4) ? lane * 4 + j : 128 + lane * 4 + (j - 4);
-            if (c < H) atomicAdd(dst + c, (unsigned long long)__float2ll_rn(val[j] * kFix));
+        for (int k = 0; k < 8; ++k) {
+            const int c = k * 32 + lane;
+            if (c < H) {
+                float vv;
+                if (e < M) {
+                    const float dyc = dXi[(size_t)e * HP + c];
+                    vv = jac_on ? jac_s * (dyc - item[(size_t)row * HP + c] * jac_s * jac_ydy) : dyc;
+                } else {
+                    vv = sc_b * a_ic[(size_t)b_idx * XW + c];
+                }
+                atomicAdd(dst + c, (unsigned long long)__float2ll_rn(vv * kFix));
+            }
         }
     }
 }
 
-// pass 3 -- one warp per hash slot: add the exact integer sums of the shared rows to g_item, record the change of the
-// squared norm, and restore the scratch (keys = -1, counts = 0, accumulators = 0).
+// pass 3 -- one thread per hash slot (most slots are empty or hold a row touched once: nothing to add); the slots of
+// a warp that hold a shared row are then processed by the whole warp one after the other: add the exact integer sums
+// to g_item, record the change of the squared norm, and restore the scratch (keys = -1, counts = 0, accumulators = 0).
 __global__ void __launch_bounds__(256)
 scatter_apply_kernel(int32_t* __restrict__ keys, int32_t* __restrict__ cnt, long long* __restrict__ acc,
                      float* __restrict__ g_item, float* __restrict__ slot_sq, int hash_size) {
-    const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (slot >= hash_size) return;
-    const int row = keys[slot];
-    if (row < 0) {
-        if (lane == 0 && slot_sq) slot_sq[slot] = 0.f;
-        return;
-    }
-    if (cnt[slot] > 1) {
-        long long* src = acc + (size_t)slot * HP;
+    const int slot0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31, lane = threadIdx.x & 31;
+    const int mine = slot0 + lane;
+    const int row_mine = mine < hash_size ? keys[mine] : -1;
+    const int cnt_mine = row_mine >= 0 ? cnt[mine] : 0;
+    if (mine < hash_size && row_mine < 0 && slot_sq) slot_sq[mine] = 0.f;
+    unsigned shared = __ballot_sync(0xffffffffu, cnt_mine > 1);
+    while (shared) {
+        const int src = __ffs(shared) - 1;
+        shared &= shared - 1;
+        const int slot = slot0 + src;
+        const int row = __shfl_sync(0xffffffffu, row_mine, src);
+        long long* a = acc + (size_t)slot * HP;
         float* dst = g_item + (size_t)row * HP;
         float d = 0.f;
-        for (int c = lane; c < H; c += 32) {
-            const float o = dst[c];
-            const float nv = o + (float)src[c] * kInvFix;
-            dst[c] = nv;
-            d += nv * nv - o * o;
-            src[c] = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = k * 32 + lane;
+            if (c < H) {
+                const float o = dst[c];
+                const float nv = o + (float)a[c] * kInvFix;
+                dst[c] = nv;
+                d += nv * nv - o * o;
+                a[c] = 0;
+            }
         }
         d = warp_sum(d);
         if (lane == 0 && slot_sq) slot_sq[slot] = d;
     }
-    __syncwarp();
-    if (lane == 0) { keys[slot] = -1; cnt[slot] = 0; }
+    if (row_mine >= 0) { keys[mine] = -1; cnt[mine] = 0; }
 }
 
 }  // namespace tcar
@@ -804,7 +916,7 @@ extern "C" int tcar_gather_fwd(const int32_t* idx, const int32_t* ctx, const flo
                                float* CT, int B, int T, void* stream) {
     if (B < 1 || T < 1 || T > TCAR_MAXT) return TCAR_ERR_ARG;
     const int warps = B * T + B;
-    gather_fwd_kernel<<<(warps + 7) / 8, 256, 0, STREAM>>>(idx, ctx, item, content, pos, month, day, week, hour,
+    gather_fwd_kernel<<<(warps + 3) / 4, 128, 0, STREAM>>>(idx, ctx, item, content, pos, month, day, week, hour,
                                                            minute, dur, X, P, D, CT, B, T);
     return LAUNCH_RC();
 }
@@ -912,7 +1024,7 @@ extern "C" int tcar_scatter_add_rows(const int32_t* seq, const int32_t* label, c
         reinterpret_cast<unsigned long long*>(hash_acc), slot_sq, B, T, Nn);
     rc = LAUNCH_RC();
     if (rc) return rc;
-    scatter_apply_kernel<<<(hash_size + 7) / 8, 256, 0, STREAM>>>(hash_keys, hash_cnt, hash_acc, g_item, slot_sq,
+    scatter_apply_kernel<<<(hash_size + 255) / 256, 256, 0, STREAM>>>(hash_keys, hash_cnt, hash_acc, g_item, slot_sq,
                                                                   hash_size);
     return LAUNCH_RC();
 }

@@ -122,6 +122,12 @@ class Seq2SeqAttNN:
         self.curEpoch = 0
         self.error_during_train = False
         self.global_step = 0
+        # software pipelining of the train loop (train_step(bt, next_bt)): the table-wide item Adam of step s runs on a
+        # side stream while the session forward of step s+1 runs on the caller's stream
+        self._side = torch.cuda.Stream(device=dev)
+        self._update_done = None           # event recorded on the side stream after the pending item update
+        self._prefetched = None            # the Batch whose session forward has already been launched
+        self.adam_overlap_ctas = int(os.environ.get("TCAR_ADAM_OVERLAP_CTAS", "2"))
 
     # ------------------------------------------------------------------------------------------- workspaces
     def _alloc(self):
@@ -221,8 +227,20 @@ class Seq2SeqAttNN:
         return self.to_device(torch.from_numpy(packed).pin_memory(), B, T, Nn)
 
     # ------------------------------------------------------------------------------------------- forward
-    def _session_forward(self, bt):
-        """Everything up to a_ic / a_pt / Q: model_combine.py:52-127."""
+    def sync_updates(self):
+        """Make the caller's stream wait for an item-table update still running on the side stream (only pending after
+        train_step(bt, next_bt)).  Every entry point that reads parameters calls this first."""
+        if self._update_done is not None:
+            torch.cuda.current_stream().wait_event(self._update_done)
+            self._update_done = None
+
+    def _session_forward(self, bt, prefetch=False):
+        """Everything up to a_ic / a_pt / Q: model_combine.py:52-127.  With prefetch=True the caller guarantees that
+        the rows of the item table this batch reads (clicks, labels) are already up to date, so the pending table-wide
+        update is NOT waited for."""
+        if not prefetch:
+            self.sync_updates()
+            self._prefetched = None
         ps, w, B, T = self.ps, self.ps.w, bt.B, bt.T
         M = B * T
         p = nv.ptr
@@ -265,7 +283,11 @@ class Seq2SeqAttNN:
     def forward_train(self, bt):
         """loss [B], cross_loss [B] (model_combine.py:145-147) and everything the backward needs."""
         ps, p, B = self.ps, nv.ptr, bt.B
-        self._session_forward(bt)
+        if self._prefetched is bt:
+            self._prefetched = None        # session forward already launched by the previous train_step
+            self.sync_updates()            # the scoring operand / negative rows need the whole table
+        else:
+            self._session_forward(bt)
         ws = self._score_buffers(ps.n_pad, True)
         nv.counted_call("tcar_score_fwd", 1, p(self.Q), p(ps.iext), p(self.c_ref), p(ws["E"]), p(ws["part"]), None, None,
                         B, ps.N, ps.n_pad, 0, self._cluster_for(B))
@@ -371,12 +393,15 @@ class Seq2SeqAttNN:
                         self._g_slice.numel())
         dist.all_reduce(ps.sqnorm_item, op=dist.ReduceOp.SUM)
         nv.counted_call("tcar_adam_item", 1, p(ps.item_full[lo:]), p(ps.item_m_full[lo:]), p(ps.item_v_full[lo:]),
-                        p(self._g_slice), p(ps.sqnorm_item), p(ps.step), self.lr, self.max_grad_f, p(ps.iext), lo, per)
+                        p(self._g_slice), p(ps.sqnorm_item), p(ps.step), self.lr, self.max_grad_f, p(ps.iext), lo, per,
+                        None, 0)
         dist.all_gather_into_tensor(ps.item_full, ps.item_full[lo: lo + per])
         nv.counted_call("tcar_refresh_iext_items", 1, p(ps.item), p(ps.iext), ps.N)
 
-    def apply_gradients(self):
-        """per-tensor clip_by_norm + TF Adam (model_combine.py:155-163); also refreshes the bf16 scoring operand."""
+    def apply_gradients(self, next_bt=None):
+        """per-tensor clip_by_norm + TF Adam (model_combine.py:155-163); also refreshes the bf16 scoring operand.
+        With next_bt (single GPU): the item rows next_bt gathers are updated first, then the table-wide item update is
+        forked onto the side stream and next_bt's session forward is launched behind it on the caller's stream."""
         ps, p = self.ps, nv.ptr
         if self._sharded_update():
             nv.counted_call("tcar_sqnorm_segments", 1, p(ps.theta_g), p(ps.seg_off), p(ps.sqnorm_small), len(SMALL))
@@ -403,14 +428,35 @@ class Seq2SeqAttNN:
         self.global_step += 1
         nv.counted_call("tcar_adam_small", 1, p(ps.theta), p(ps.theta_m), p(ps.theta_v), p(ps.theta_g), p(ps.seg_off),
                         p(ps.sqnorm_small), len(SMALL), p(ps.step), self.lr, self.max_grad_f)
-        nv.counted_call("tcar_adam_item", 1, p(ps.item), p(ps.item_m), p(ps.item_v), p(ps.item_g), p(ps.sqnorm_item),
-                        p(ps.step), self.lr, self.max_grad_f, p(ps.iext), 0, ps.N + 1)
         ps.prep_weights()
+        item_args = (p(ps.item), p(ps.item_m), p(ps.item_v), p(ps.item_g), p(ps.sqnorm_item), p(ps.step), self.lr,
+                     self.max_grad_f, p(ps.iext))
+        if next_bt is None or next_bt.B == 0 or self.world != 1 or self.adam_overlap_ctas <= 0:
+            nv.counted_call("tcar_adam_item", 1, *item_args, 0, ps.N + 1, None, 0)
+            return
+        nv.counted_call("tcar_adam_item_rows", 1, *item_args, p(next_bt.seq), next_bt.B * next_bt.T, p(next_bt.label),
+                        next_bt.B, p(ps.row_flags), ps.N + 1)
+        main = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        self._side.wait_event(fork)
+        with torch.cuda.stream(self._side):
+            nv.counted_call("tcar_adam_item", 1, *item_args, 0, ps.N + 1, p(ps.row_flags), self.adam_overlap_ctas)
+            done = torch.cuda.Event()
+            done.record(self._side)
+        self._update_done = done
+        self._session_forward(next_bt, prefetch=True)
+        self._prefetched = next_bt
 
-    def train_step(self, bt):
-        """One `sess.run([loss, global_step, train_op])` (model_combine.py:231-234). Returns loss [B] (device)."""
+    def train_step(self, bt, next_bt=None):
+        """One `sess.run([loss, global_step, train_op])` (model_combine.py:231-234). Returns loss [B] (device).
+        next_bt (optional) is the batch of the following call: its session forward is overlapped with this step's
+        table-wide Adam pass.  Results are bit-identical with and without it; after a call with next_bt, parameters
+        must be read through this object's methods (or after sync_updates())."""
         if bt.B == 0:
             # data-parallel tail batch with fewer sessions than ranks: contribute a zero gradient to the all-reduce
+            self.sync_updates()
+            self._prefetched = None
             self.ps.item_g_full.zero_()
             self.ps.theta_g.zero_()
             loss = self.loss[:0]
@@ -418,7 +464,7 @@ class Seq2SeqAttNN:
             loss, _ = self.forward_train(bt)
             self.backward(bt)
         self.allreduce_grads()
-        self.apply_gradients()
+        self.apply_gradients(next_bt)
         return loss
 
     # ------------------------------------------------------------------------------------------- evaluation
@@ -542,15 +588,27 @@ class Seq2SeqAttNN:
             sampler = Sampler(len_dict_train, session_dict_train, session_time_dict_train, neighbor_dict, item_dict,
                               args["neg_num"], batch_size=self.batch_size)
             batch = 0
-            for packed, B, T, Nn in prefetch_packed(sampler):
-                batch += 1
-                if batch < 3 and Nn:
-                    print(packed[7 * B * T + 3 * B: 7 * B * T + 3 * B + min(Nn, 10)].tolist())
-                if self.world > 1:
-                    # every rank draws the same batch (same seeds, main.py:9-12) and keeps its slice of the sessions
-                    packed, B, T, Nn = parallel.shard_packed(packed, B, T, Nn, self.rank, self.world)
-                bt = self.stage_to_device(packed, B, T, Nn)
-                c.append(self.train_step(bt).clone())
+
+            def staged():
+                nonlocal batch
+                for packed, B, T, Nn in prefetch_packed(sampler):
+                    batch += 1
+                    if batch < 3 and Nn:
+                        print(packed[7 * B * T + 3 * B: 7 * B * T + 3 * B + min(Nn, 10)].tolist())
+                    if self.world > 1:
+                        # every rank draws the same batch (same seeds, main.py:9-12) and keeps its slice of the sessions
+                        packed, B, T, Nn = parallel.shard_packed(packed, B, T, Nn, self.rank, self.world)
+                    yield self.stage_to_device(packed, B, T, Nn)
+
+            # one batch of look-ahead: batch i+1 is on the device before step i is launched, so that its session
+            # forward can overlap step i's table-wide Adam pass (train_step(bt, next_bt))
+            it = staged()
+            bt = next(it, None)
+            while bt is not None:
+                nxt = next(it, None)
+                c.append(self.train_step(bt, nxt).clone())
+                bt = nxt
+            self.sync_updates()
             tot = torch.stack([torch.cat(c).sum(), torch.tensor(float(sum(len(x) for x in c)), device=self.dev)]) \
                 if c else torch.zeros(2, device=self.dev)
             parallel.allreduce_sum((tot,), self.world)

@@ -90,6 +90,8 @@ class ParamStore:
         self.sqnorm_item = torch.zeros(1, device=dev)
         self.norm_partial = torch.zeros(1184, device=dev)
         self.step = torch.zeros(1, device=dev, dtype=torch.int32)
+        # per-row "already updated in step t" marks of tcar_adam_item_rows (cleared whenever `step` is set from outside)
+        self.row_flags = torch.zeros(self.rows_alloc, device=dev, dtype=torch.int32)
         self.w = {n: self._view(self.theta, i) for i, (n, _) in enumerate(SMALL)}
         self.g = {n: self._view(self.theta_g, i) for i, (n, _) in enumerate(SMALL)}
         self.ct_tab = torch.zeros(nv.NBINS, TH, device=dev)
@@ -143,6 +145,7 @@ class ParamStore:
         for t in (self.item_m, self.item_v, self.theta_m, self.theta_v):
             t.zero_()
         self.step.zero_()
+        self.row_flags.zero_()
         self.rebuild_iext()
         self.prep_weights()
 
@@ -178,3 +181,4 @@ class ParamStore:
         self.theta_m.copy_(sd["theta_m"].to(self.device))
         self.theta_v.copy_(sd["theta_v"].to(self.device))
         self.step.fill_(int(sd["step"]))
+        self.row_flags.zero_()

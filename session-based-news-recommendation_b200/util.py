@@ -54,10 +54,12 @@ def save_model(model, args, saver=None):
         "-" + args["split_way"].strip("/") + "-" + str(args["foldnum"])
     os.makedirs(args["modelpath"], exist_ok=True)
     path = os.path.join(args["modelpath"], "model.ckpt-" + suf)
+    model.sync_updates()
     torch.save(model.ps.state_dict(), path)
     return path
 
 
 def restore_model(model, path):
     import torch
+    model.sync_updates()
     model.ps.load_state_dict(torch.load(path, weights_only=False))

@@ -160,6 +160,49 @@ def test_train_step_is_deterministic():
         assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("overlap_ctas", [2, 16])
+def test_lookahead_train_steps_are_bit_identical(overlap_ctas):
+    """train_step(bt, next_bt) -- rows of the next batch updated first, table-wide Adam on a side stream, next session
+    forward launched early -- must give exactly the results of the plain sequence train_step(bt)."""
+    N, B = 20000, 160
+    lens = [3, 1, 7, 2, 20, 1]
+    runs = []
+    for lookahead in (False, True):
+        model, content, mwdhm, _ = build(N, emb_scale=100.0)
+        model.adam_overlap_ctas = overlap_ctas
+        bts = [batch_for(model, N, B, T, 20, mwdhm, seed=50 + i)[0] for i, T in enumerate(lens)]
+        # the next batch repeats some of this batch's rows and lists a row several times
+        losses = []
+        for i, bt in enumerate(bts):
+            nxt = bts[i + 1] if lookahead and i + 1 < len(bts) else None
+            losses.append(model.train_step(bt, nxt).clone())
+        model.sync_updates()
+        torch.cuda.synchronize()
+        top, ngt, ce = model.eval_step(bts[0])
+        runs.append((torch.cat(losses), model.ps.item.clone(), model.ps.item_m.clone(), model.ps.item_v.clone(),
+                     model.ps.theta.clone(), model.ps.iext.clone(), top.clone(), ngt.clone(), ce.clone()))
+    for a, b in zip(*runs):
+        assert torch.equal(a, b)
+    assert int(model.ps.step.item()) == len(lens)
+
+
+def test_lookahead_mismatched_next_batch_is_recomputed():
+    """If the caller passes a next_bt but then trains on a different batch, the prefetched forward is discarded."""
+    N, B = 5000, 64
+    outs = []
+    for lookahead in (False, True):
+        model, content, mwdhm, _ = build(N)
+        b0 = batch_for(model, N, B, 4, 20, mwdhm, seed=1)[0]
+        b1 = batch_for(model, N, B, 2, 20, mwdhm, seed=2)[0]
+        b2 = batch_for(model, N, B, 6, 20, mwdhm, seed=3)[0]
+        model.train_step(b0, b1 if lookahead else None)
+        loss = model.train_step(b2).clone()              # not b1
+        torch.cuda.synchronize()
+        outs.append((loss, model.ps.item.clone(), model.ps.theta.clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
 def margin_ok(scores, k=20, rel=2e-5):
     s = np.sort(scores, axis=1)[:, ::-1]
     gaps = np.abs(np.diff(s[:, : k + 1], axis=1)).min(1)
