@@ -209,6 +209,11 @@ int tcar_sqnorm_big(const float* x, float* partial, float* sqnorm, long long n, 
  * a = per-CTA sums of squares written by tcar_score_bwd_i, b = slot_sq of tcar_scatter_add_rows. */
 int tcar_sqnorm_combine(const float* a, int na, const float* b, int nb, float* out, void* stream);
 
+/* Debug aid (not thread-safe, not used on the product path): when trace_buf != NULL every CTA of the following
+ * tcar_gemm_tf32* launches writes 8 clock64() stamps to trace_buf[8 * cta + k]: 0 start, 1 prologue done, 2 last TMA
+ * issued, 3 first stage landed, 4 last MMA committed, 5 accumulator ready, 6 epilogue stores issued, 7 end. */
+int tcar_debug_gemm_trace(long long* trace_buf);
+
 /* (5d) clip_by_norm + TF-flavoured Adam (model_combine.py:155-163): lr_t = lr sqrt(1-b2^t)/(1-b1^t),
  *      theta -= lr_t m / (sqrt(v) + eps).  `step` [1] int32 on device holds t (already incremented). */
 int tcar_adam_small(float* theta, float* m, float* v, const float* g, const int32_t* seg_off, const float* sqnorm,
@@ -218,8 +223,9 @@ int tcar_adam_small(float* theta, float* m, float* v, const float* g, const int3
  * nrows = N + 1; data-parallel training updates one contiguous slice per rank (parallel.py).
  * The six pad columns of the 256-float pitch are not touched.  `row_flags` (optional, [N+1] int32, indexed by
  * absolute row): rows whose flag equals the step number t were already updated by tcar_adam_item_rows and are skipped.
- * `ctas_per_sm`: 0 = default grid (16 CTAs per SM); a small value (1..4) leaves SM resources free for kernels running
- * concurrently on another stream (the next batch's session forward, Seq2SeqAttNN.train_step). */
+ * `ctas_per_sm`: grid = 148 x ctas_per_sm CTAs of 256 threads (0 = 16).  A large value (64..256) makes every CTA
+ * short-lived, so that kernels of a higher-priority stream (the next batch's session forward,
+ * Seq2SeqAttNN.train_step) are dispatched into the SM resources retiring CTAs free within a few microseconds. */
 int tcar_adam_item(float* item, float* m, float* v, const float* g, const float* sqnorm, const int32_t* step,
                    float lr, float max_grad, void* iext_bf16, int row0, int nrows, const int32_t* row_flags,
                    int ctas_per_sm, void* stream);

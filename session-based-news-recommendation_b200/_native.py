@@ -39,6 +39,7 @@ SIGNATURES = {
     "tcar_gemm_tf32_group": [_P, _I, _P],
     "tcar_gemm_tf32_splits": [_I, _I, _I, _I],
     "tcar_gemm_tf32_part_elems": [_I, _I, _I],
+    "tcar_debug_gemm_trace": [_P],
     "tcar_prep_weights": [_P, _P, _I, _P, _P, _P],
     "tcar_scatter_add_rows": [_P] * 13 + [_I] * 4 + [_P],
     "tcar_sqnorm_segments": [_P] * 3 + [_I, _P],

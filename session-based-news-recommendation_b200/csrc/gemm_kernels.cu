@@ -18,7 +18,7 @@
 
 namespace tcar {
 
-constexpr int G_THREADS = 256;   // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 split + epilogue
+constexpr int G_THREADS = 384;   // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-11 split + epilogue
 constexpr int G_BM = 128;
 constexpr int G_BK = 32;         // 32 fp32 = one 128-byte swizzle span
 constexpr int G_A_TILE = G_BM * G_BK * 4;   // 16384
@@ -66,7 +66,9 @@ struct GemmGroup {
     int cta_start[G_MAX_PROB + 1];
     int red_start[G_MAX_PROB + 1];   // CTA ranges of the split-reduction kernel
     int nprob;
+    long long* trace;                // debug (tcar_debug_gemm_trace): 8 clock64() stamps per CTA, else null
 };
+#define G_TRACE(slot) do { if (grp.trace) grp.trace[(size_t)blockIdx.x * 8 + (slot)] = clock64(); } while (0)
 
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -115,6 +117,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmGroup grp) {
     while (gi + 1 < grp.nprob && (int)blockIdx.x >= grp.cta_start[gi + 1]) ++gi;
     const GemmMaps& maps = grp.maps[gi];
     const GemmParams& p = grp.prm[gi];
+    if (threadIdx.x == 0) G_TRACE(0);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G_SMEM_BUDGET);
@@ -146,7 +149,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmGroup grp) {
     if (warp == 1 && elect_one()) {
         for (int i = 0; i < p.stages; ++i) {
             mbar_init(&full[i], 1);
-            mbar_init(&conv[i], 4);
+            mbar_init(&conv[i], 8);
             mbar_init(&empty[i], 1);
         }
         mbar_init(acc_full, 1);
@@ -157,6 +160,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmGroup grp) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) G_TRACE(1);
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -195,6 +199,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmGroup grp) {
                     if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
                 }
             }
+            G_TRACE(2);
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
@@ -207,6 +212,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmGroup grp) {
                 if (kb < kb0 || kb >= kb1) continue;
                 mbar_wait(p.precise ? &conv[stage] : &full[stage], phase);
                 tc_fence_after();
+                if (issued == 0 && lane == 0) G_TRACE(3);
                 if (elect_one()) {
                     const uint32_t a_addr = smem_u32(smem + (size_t)stage * p.stage_bytes);
                     const uint32_t b_addr = a_addr + b_off;
@@ -228,7 +234,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmGroup grp) {
                         }
                     }
                     umma_commit(&empty[stage]);
-                    if (kb == kb1 - 1) umma_commit(acc_full);
+                    if (kb == kb1 - 1) { umma_commit(acc_full); G_TRACE(4); }
                 }
                 __syncwarp();
                 ++issued;
@@ -236,8 +242,9 @@ gemm_tf32_kernel(const __grid_constant__ GemmGroup grp) {
             }
         }
     } else if (warp >= 4) {
-        const uint32_t q = warp - 4;
-        const uint32_t tid = threadIdx.x - 128;
+        const uint32_t q = warp & 3;              // TMEM lane quarter this warp may read (warp id mod 4)
+        const int half = (int)(warp - 4) >> 2;    // which of the two warps of the quarter
+        const uint32_t tid = threadIdx.x - 128;   // 0..255
         if (p.precise) {
             // ================= operand split: A tile -> (hi in place, lo next to it) =================
             uint32_t stage = 0, phase = 0;
@@ -246,15 +253,15 @@ gemm_tf32_kernel(const __grid_constant__ GemmGroup grp) {
                 float4* hi = reinterpret_cast<float4*>(smem + (size_t)stage * p.stage_bytes);
                 float4* lo = reinterpret_cast<float4*>(smem + (size_t)stage * p.stage_bytes + a_lo_off);
 #pragma unroll
-                for (int i = 0; i < G_A_TILE / 16 / 128; ++i) {
-                    const float4 v = hi[tid + i * 128];
+                for (int i = 0; i < G_A_TILE / 16 / 256; ++i) {
+                    const float4 v = hi[tid + i * 256];
                     float4 h, l;
                     h.x = tf32_rn(v.x); l.x = tf32_rn(v.x - h.x);
                     h.y = tf32_rn(v.y); l.y = tf32_rn(v.y - h.y);
                     h.z = tf32_rn(v.z); l.z = tf32_rn(v.z - h.z);
                     h.w = tf32_rn(v.w); l.w = tf32_rn(v.w - h.w);
-                    hi[tid + i * 128] = h;
-                    lo[tid + i * 128] = l;
+                    hi[tid + i * 256] = h;
+                    lo[tid + i * 256] = l;
                 }
                 fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core (async proxy)
                 __syncwarp();
@@ -262,57 +269,70 @@ gemm_tf32_kernel(const __grid_constant__ GemmGroup grp) {
                 if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
             }
         }
-        // ================= epilogue: thread <-> output row =================
+        // ================= epilogue: thread <-> output row, the two warps of a TMEM lane quarter alternate over the
+        // 32-column chunks.  (Measured with tcar_debug_gemm_trace: the epilogue of the small projections is bound by
+        // the issue latency of ONE warp per scheduler walking its chunks -- about 1 us per chunk -- not by the store
+        // pattern; a shared-memory transpose for coalesced stores was slower.  Hence: twice the warps, one bias load
+        // per lane instead of 32 per thread.)
         const int row = mtile * G_BM + q * 32 + lane;
         if (nkb > 0) {
             mbar_wait(acc_full, 0);
             tc_fence_after();
         }
+        if (tid == 0) G_TRACE(5);
         float* crow = p.C + (size_t)split * p.part_stride + (size_t)row * p.ldc;
         const bool vec = (p.ldc & 3) == 0;
+        const float* bias = p.bias;
+        const int act = p.act, accumulate = p.accumulate, Ncols = p.N;
 #pragma unroll 1
-        for (int ch = 0; ch < p.bn / 32; ++ch) {
+        for (int ch = half; ch < p.bn / 32; ch += 2) {
+            const int c0 = ntile * p.bn + ch * 32;
+            if (c0 >= Ncols) break;
             uint32_t v[32];
             if (nkb > 0) {
                 tmem_ld32(tmem_base + ((q * 32) << 16) + ch * 32, v);
-                tmem_ld_wait();
             } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = 0u;
             }
-            const int c0 = ntile * p.bn + ch * 32;
-            if (row < p.M && c0 < p.N) {
-                float o[32];
+            const float bl = (bias && c0 + (int)lane < Ncols) ? __ldg(bias + c0 + lane) : 0.f;
+            if (nkb > 0) tmem_ld_wait();
+            float o[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = __uint_as_float(v[j]);
-                    if (p.bias && c0 + j < p.N) x += p.bias[c0 + j];
-                    if (p.act == 1) x = fmaxf(x, 0.f);
-                    else if (p.act == 2) x = tanh_fast(x);
-                    o[j] = x;
-                }
-                if (vec && c0 + 32 <= p.N) {
+            for (int j = 0; j < 32; ++j) {
+                float x = __uint_as_float(v[j]) + __shfl_sync(0xffffffffu, bl, j);
+                if (act == 1) x = fmaxf(x, 0.f);
+                else if (act == 2) x = tanh_fast(x);
+                o[j] = x;
+            }
+            if (row < p.M) {
+                if (vec && c0 + 32 <= Ncols) {
                     float4* dst = reinterpret_cast<float4*>(crow + c0);
+                    if (accumulate) {
+                        float4 old[8];
 #pragma unroll
-                    for (int g = 0; g < 8; ++g) {
-                        float4 t = make_float4(o[g * 4], o[g * 4 + 1], o[g * 4 + 2], o[g * 4 + 3]);
-                        if (p.accumulate) {
-                            const float4 old = dst[g];
-                            t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
-                        }
-                        dst[g] = t;
+                        for (int g = 0; g < 8; ++g) old[g] = dst[g];
+#pragma unroll
+                        for (int g = 0; g < 8; ++g)
+                            dst[g] = make_float4(o[g * 4] + old[g].x, o[g * 4 + 1] + old[g].y, o[g * 4 + 2] + old[g].z,
+                                                 o[g * 4 + 3] + old[g].w);
+                    } else {
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) dst[g] = make_float4(o[g * 4], o[g * 4 + 1], o[g * 4 + 2], o[g * 4 + 3]);
                     }
                 } else {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (c0 + j < p.N) crow[c0 + j] = p.accumulate ? crow[c0 + j] + o[j] : o[j];
+                        if (c0 + j < Ncols) crow[c0 + j] = accumulate ? crow[c0 + j] + o[j] : o[j];
                 }
             }
         }
     }
+    if (threadIdx.x == 128) G_TRACE(6);
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, 256);
+    if (threadIdx.x == 0) G_TRACE(7);
 }
 
 // out[r, c] = sum_s part[s][r][c]  (fixed order) for every split problem of the group
@@ -473,11 +493,18 @@ static int setup_problem(const tcar_gemm_problem& q, GemmParams& p, GemmMaps& ma
     return 0;
 }
 
+static long long* g_gemm_trace = nullptr;
+extern "C" int tcar_debug_gemm_trace(long long* trace_buf) {
+    g_gemm_trace = trace_buf;
+    return 0;
+}
+
 extern "C" int tcar_gemm_tf32_group(const tcar_gemm_problem* probs, int nprob, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (nprob < 1 || nprob > G_MAX_PROB || !probs) return TCAR_ERR_ARG;
     static thread_local GemmGroup grp;      // ~11 KB of kernel parameters, rebuilt per call
     grp.nprob = nprob;
+    grp.trace = g_gemm_trace;
     int ctas = 0, red = 0;
     bool any_split = false;
     for (int g = 0; g < nprob; ++g) {

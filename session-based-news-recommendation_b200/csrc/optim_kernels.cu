@@ -336,7 +336,7 @@ extern "C" int tcar_adam_small(float* theta, float* m, float* v, const float* g,
 extern "C" int tcar_adam_item(float* item, float* m, float* v, const float* g, const float* sqnorm,
                               const int32_t* step, float lr, float max_grad, void* iext_bf16, int row0, int nrows,
                               const int32_t* row_flags, int ctas_per_sm, void* stream) {
-    if (row0 < 0 || nrows < 1 || ctas_per_sm < 0 || ctas_per_sm > 32) return TCAR_ERR_ARG;
+    if (row0 < 0 || nrows < 1 || ctas_per_sm < 0 || ctas_per_sm > 1024) return TCAR_ERR_ARG;
     const long long n4 = (long long)nrows * (HP / 4);
     const int grid = 148 * (ctas_per_sm ? ctas_per_sm : 16);
     adam_item_kernel<<<grid, 256, 0, STREAM>>>(reinterpret_cast<float4*>(item), reinterpret_cast<float4*>(m),

@@ -124,10 +124,15 @@ class Seq2SeqAttNN:
         self.global_step = 0
         # software pipelining of the train loop (train_step(bt, next_bt)): the table-wide item Adam of step s runs on a
         # side stream while the session forward of step s+1 runs on the caller's stream
+        # `_side`: the table-wide Adam; `_ahead` (high priority, so that its CTAs are dispatched as soon as Adam CTAs
+        # retire): the next batch's session forward
         self._side = torch.cuda.Stream(device=dev)
-        self._update_done = None           # event recorded on the side stream after the pending item update
+        self._ahead = torch.cuda.Stream(device=dev, priority=-1)
+        self._update_done = None           # event recorded on `_side` after the pending item update
+        self._ahead_done = None            # event recorded on `_ahead` after the prefetched session forward
         self._prefetched = None            # the Batch whose session forward has already been launched
-        self.adam_overlap_ctas = int(os.environ.get("TCAR_ADAM_OVERLAP_CTAS", "2"))
+        self.adam_overlap_ctas = int(os.environ.get("TCAR_ADAM_OVERLAP_CTAS", "64"))
+        self.ahead_priority = os.environ.get("TCAR_AHEAD_PRIORITY", "1") != "0"
 
     # ------------------------------------------------------------------------------------------- workspaces
     def _alloc(self):
@@ -230,9 +235,13 @@ class Seq2SeqAttNN:
     def sync_updates(self):
         """Make the caller's stream wait for an item-table update still running on the side stream (only pending after
         train_step(bt, next_bt)).  Every entry point that reads parameters calls this first."""
+        cur = torch.cuda.current_stream()
         if self._update_done is not None:
-            torch.cuda.current_stream().wait_event(self._update_done)
+            cur.wait_event(self._update_done)
             self._update_done = None
+        if self._ahead_done is not None:
+            cur.wait_event(self._ahead_done)
+            self._ahead_done = None
 
     def _session_forward(self, bt, prefetch=False):
         """Everything up to a_ic / a_pt / Q: model_combine.py:52-127.  With prefetch=True the caller guarantees that
@@ -445,7 +454,15 @@ class Seq2SeqAttNN:
             done = torch.cuda.Event()
             done.record(self._side)
         self._update_done = done
-        self._session_forward(next_bt, prefetch=True)
+        if self.ahead_priority:
+            self._ahead.wait_event(fork)
+            with torch.cuda.stream(self._ahead):
+                self._session_forward(next_bt, prefetch=True)
+                adone = torch.cuda.Event()
+                adone.record(self._ahead)
+            self._ahead_done = adone
+        else:
+            self._session_forward(next_bt, prefetch=True)
         self._prefetched = next_bt
 
     def train_step(self, bt, next_bt=None):

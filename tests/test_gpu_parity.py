@@ -160,7 +160,7 @@ def test_train_step_is_deterministic():
         assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("overlap_ctas", [2, 16])
+@pytest.mark.parametrize("overlap_ctas", [3, 64, 512])
 def test_lookahead_train_steps_are_bit_identical(overlap_ctas):
     """train_step(bt, next_bt) -- rows of the next batch updated first, table-wide Adam on a side stream, next session
     forward launched early -- must give exactly the results of the plain sequence train_step(bt)."""
