@@ -18,7 +18,11 @@
 
 namespace tcar {
 
-constexpr int G_THREADS = 384;   // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-11 split + epilogue
+#ifndef TCAR_GEMM_EPI_WARPS
+#define TCAR_GEMM_EPI_WARPS 16
+#endif
+constexpr int G_EPI_WARPS = TCAR_GEMM_EPI_WARPS;  // a multiple of 4: G_EPI_WARPS / 4 warps per TMEM lane quarter
+constexpr int G_THREADS = 128 + 32 * G_EPI_WARPS;   // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, then split + epilogue warps
 constexpr int G_BM = 128;
 constexpr int G_BK = 32;         // 32 fp32 = one 128-byte swizzle span
 constexpr int G_A_TILE = G_BM * G_BK * 4;   // 16384
@@ -149,7 +153,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmGroup grp) {
     if (warp == 1 && elect_one()) {
         for (int i = 0; i < p.stages; ++i) {
             mbar_init(&full[i], 1);
-            mbar_init(&conv[i], 8);
+            mbar_init(&conv[i], G_EPI_WARPS);
             mbar_init(&empty[i], 1);
         }
         mbar_init(acc_full, 1);
@@ -243,8 +247,8 @@ gemm_tf32_kernel(const __grid_constant__ GemmGroup grp) {
         }
     } else if (warp >= 4) {
         const uint32_t q = warp & 3;              // TMEM lane quarter this warp may read (warp id mod 4)
-        const int half = (int)(warp - 4) >> 2;    // which of the two warps of the quarter
-        const uint32_t tid = threadIdx.x - 128;   // 0..255
+        const int half = (int)(warp - 4) >> 2;    // which of the G_EPI_WARPS / 4 warps of the quarter
+        const uint32_t tid = threadIdx.x - 128;   // 0 .. 32 * G_EPI_WARPS - 1
         if (p.precise) {
             // ================= operand split: A tile -> (hi in place, lo next to it) =================
             uint32_t stage = 0, phase = 0;
@@ -253,15 +257,15 @@ gemm_tf32_kernel(const __grid_constant__ GemmGroup grp) {
                 float4* hi = reinterpret_cast<float4*>(smem + (size_t)stage * p.stage_bytes);
                 float4* lo = reinterpret_cast<float4*>(smem + (size_t)stage * p.stage_bytes + a_lo_off);
 #pragma unroll
-                for (int i = 0; i < G_A_TILE / 16 / 256; ++i) {
-                    const float4 v = hi[tid + i * 256];
+                for (int i = 0; i < G_A_TILE / 16 / (32 * G_EPI_WARPS); ++i) {
+                    const float4 v = hi[tid + i * 32 * G_EPI_WARPS];
                     float4 h, l;
                     h.x = tf32_rn(v.x); l.x = tf32_rn(v.x - h.x);
                     h.y = tf32_rn(v.y); l.y = tf32_rn(v.y - h.y);
                     h.z = tf32_rn(v.z); l.z = tf32_rn(v.z - h.z);
                     h.w = tf32_rn(v.w); l.w = tf32_rn(v.w - h.w);
-                    hi[tid + i * 256] = h;
-                    lo[tid + i * 256] = l;
+                    hi[tid + i * 32 * G_EPI_WARPS] = h;
+                    lo[tid + i * 32 * G_EPI_WARPS] = l;
                 }
                 fence_proxy_async_smem();     // generic-proxy writes -> visible to the tensor core (async proxy)
                 __syncwarp();
@@ -285,7 +289,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmGroup grp) {
         const float* bias = p.bias;
         const int act = p.act, accumulate = p.accumulate, Ncols = p.N;
 #pragma unroll 1
-        for (int ch = half; ch < p.bn / 32; ch += 2) {
+        for (int ch = half; ch < p.bn / 32; ch += G_EPI_WARPS / 4) {
             const int c0 = ntile * p.bn + ch * 32;
             if (c0 >= Ncols) break;
             uint32_t v[32];

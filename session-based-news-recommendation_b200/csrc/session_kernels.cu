@@ -428,29 +428,31 @@ build_query_kernel(const float* __restrict__ a_ic, const float* __restrict__ a_p
 }
 
 // ------------------------------------------------------------------------------------------------ (4a) CE finish
-// 32 rows per CTA, 32 warps stride over the tiles with 4 independent loads in flight, fixed combine order.
+// 16 rows per CTA (half-warp = 16 consecutive rows of one partial, the two half-warps take alternate partials), 32 warps
+// stride over the partials with 8 independent loads in flight per thread, fixed combine order.
 __global__ void __launch_bounds__(1024)
 ce_finish_kernel(const float* __restrict__ part, float* __restrict__ sumexp, float* __restrict__ ce, int n_tiles,
                  int B) {
     __shared__ float s[32][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int b = blockIdx.x * 32 + lane;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const int b = blockIdx.x * 16 + (lane & 15);
+    float a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = 0.f;
     if (b < B) {
-        int t = w;
-        for (; t + 96 < n_tiles; t += 128) {
-            a0 += part[(size_t)t * TCAR_QROWS + b];
-            a1 += part[(size_t)(t + 32) * TCAR_QROWS + b];
-            a2 += part[(size_t)(t + 64) * TCAR_QROWS + b];
-            a3 += part[(size_t)(t + 96) * TCAR_QROWS + b];
+        const float* src = part + b;
+        int t = 2 * w + (lane >> 4);
+        for (; t + 7 * 64 < n_tiles; t += 8 * 64) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] += src[(size_t)(t + 64 * k) * TCAR_QROWS];
         }
-        for (; t < n_tiles; t += 32) a0 += part[(size_t)t * TCAR_QROWS + b];
+        for (; t < n_tiles; t += 64) a[0] += src[(size_t)t * TCAR_QROWS];
     }
-    s[w][lane] = (a0 + a1) + (a2 + a3);
+    s[w][lane] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
     __syncthreads();
-    if (w == 0 && b < B) {
+    if (w == 0 && lane < 16 && b < B) {
         float tot = 0.f;
-        for (int i = 0; i < 32; ++i) tot += s[i][lane];
+        for (int i = 0; i < 32; ++i) tot += s[i][lane] + s[i][lane + 16];
         sumexp[b] = tot;
         ce[b] = logf(tot);
     }
@@ -567,173 +569,160 @@ score_bwd_finish_kernel(const float* __restrict__ dq_raw, const float* __restric
 // ------------------------------------------------------------------------------------------------ (5a) small tables
 // clip Jacobian of y = x / max(||x||, 1):  dx = dy (||x|| <= 1)   else   s (dy - y (y . dy)),  s = 1/||x||, y = s x
 //
-// Two passes.  Pass 1: every CTA owns a contiguous chunk of the B*T clicks (and of the B sessions) and accumulates,
-// in click order, per-table-row partial sums in shared memory -- thread (k, d) owns column d of table k, so no two
-// threads ever touch the same accumulator and no atomics are needed.  Pass 2: one CTA per table row adds the chunk
-// partials in chunk order, the scoring-side term sum_b dTq[b,r] a_pt[b,:] and applies the clip Jacobian.
-constexpr int TG_BIN_FLOATS = NB * TH;                  // 139 x 64
-constexpr int TG_DUR_FLOATS = 11 * TH;                  // 11 x 64
-constexpr int TG_POS_FLOATS = TCAR_MAXT * H;            // 40 x 250
-constexpr int TG_PART_FLOATS = TG_BIN_FLOATS + TG_DUR_FLOATS + TG_POS_FLOATS;   // 19600 floats = 78.4 KB per chunk
-constexpr int TG_THREADS = 640;                          // 320 time (k,d) + 64 duration + 250 position (+6 idle)
-constexpr int TG_MAX_CHUNKS = TCAR_TABLE_GRAD_CHUNKS;
+// One CTA per table row (40 position rows, 139 publish-time rows, 11 dwell rows), 16 warps.  A time / dwell row scans
+// the index column of its table (lane <-> click, 512 clicks per sweep of the CTA), and every warp adds the gradient
+// rows of its matching clicks in increasing click order; the 16 warp partials, the click-context matches (week / hour
+// rows), and the scoring-side term sum_b dTq[b,r] a_pt[b,:] are then combined in a fixed order and the clip Jacobian
+// is applied.  No atomics, no scratch: the result does not depend on scheduling.
+constexpr int TGD_THREADS = 512;
+constexpr int TGD_WARPS = TGD_THREADS / 32;
 
-__global__ void __launch_bounds__(TG_THREADS)
-table_partial_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ ctx, const float* __restrict__ dXi,
-                     const float* __restrict__ dP, const float* __restrict__ dD, const float* __restrict__ dCT,
-                     float* __restrict__ part, int B, int T) {
-    extern __shared__ float s_tab[];                    // [bins 139x64 | dur 11x64 | pos 40x250]
-    const int M = B * T, tid = threadIdx.x, nchunk = gridDim.x;
-    for (int i = tid; i < TG_PART_FLOATS; i += TG_THREADS) s_tab[i] = 0.f;
-    __syncthreads();
-    const int per = (M + nchunk - 1) / nchunk;
-    const int m0 = blockIdx.x * per, m1 = min(m0 + per, M);
-    const int bper = (B + nchunk - 1) / nchunk;
-    const int b0 = blockIdx.x * bper, b1 = min(b0 + bper, B);
-    if (tid < 5 * TH) {
-        const int k = tid >> 6, d = tid & 63;
-        float* acc = s_tab + (size_t)kBinOff[k] * TH + d;
-        const int32_t* ik = idx + (size_t)(k + 1) * M;
-        const float* src = dP + k * TH + d;
-        int m = m0;
-        for (; m + 4 <= m1; m += 4) {                     // 4 independent loads in flight, adds in click order
-            const int r0 = ik[m], r1 = ik[m + 1], r2 = ik[m + 2], r3 = ik[m + 3];
-            const float v0 = src[(size_t)m * PW], v1 = src[(size_t)(m + 1) * PW];
-            const float v2 = src[(size_t)(m + 2) * PW], v3 = src[(size_t)(m + 3) * PW];
-            acc[r0 * TH] += v0; acc[r1 * TH] += v1; acc[r2 * TH] += v2; acc[r3 * TH] += v3;
+// adds src[m * pitch + lane], src[m * pitch + 32 + lane] for every m in [0, count) with key[m] == want, visiting the
+// warp's clicks (32 consecutive ones every 32 * TGD_WARPS) in increasing order; up to four matches are fetched at once
+__device__ __forceinline__ void match_accumulate(const int32_t* __restrict__ key, int want, int count,
+                                                 const float* __restrict__ src, size_t pitch, int w, int lane,
+                                                 float& acc0, float& acc1) {
+    for (int m0 = w * 32; m0 < count; m0 += 32 * TGD_WARPS) {
+        const int m = m0 + lane;
+        unsigned bits = __ballot_sync(0xffffffffu, m < count && __ldg(key + m) == want);
+        while (bits) {
+            int j[4];
+            float v0[4], v1[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                j[u] = bits ? __ffs(bits) - 1 : -1;
+                if (bits) bits &= bits - 1;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float* r = src + (size_t)(m0 + max(j[u], 0)) * pitch;
+                v0[u] = j[u] >= 0 ? r[lane] : 0.f;
+                v1[u] = j[u] >= 0 ? r[32 + lane] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { acc0 += v0[u]; acc1 += v1[u]; }
         }
-        for (; m < m1; ++m) acc[ik[m] * TH] += src[(size_t)m * PW];
-        // click-time context (sampler.py:106-107): week table by ctx[0][b], hour table by ctx[1][b]
-        if (k == 2) for (int b = b0; b < b1; ++b) acc[ctx[b] * TH] += dCT[(size_t)b * 2 * TH + d];
-        if (k == 3) for (int b = b0; b < b1; ++b) acc[ctx[B + b] * TH] += dCT[(size_t)b * 2 * TH + TH + d];
-    } else if (tid < 6 * TH) {
-        const int d = tid - 5 * TH;
-        float* acc = s_tab + TG_BIN_FLOATS + d;
-        const int32_t* ik = idx + (size_t)6 * M;
-        int m = m0;
-        for (; m + 4 <= m1; m += 4) {
-            const int r0 = ik[m], r1 = ik[m + 1], r2 = ik[m + 2], r3 = ik[m + 3];
-            const float v0 = dD[(size_t)m * TH + d], v1 = dD[(size_t)(m + 1) * TH + d];
-            const float v2 = dD[(size_t)(m + 2) * TH + d], v3 = dD[(size_t)(m + 3) * TH + d];
-            acc[r0 * TH] += v0; acc[r1 * TH] += v1; acc[r2 * TH] += v2; acc[r3 * TH] += v3;
-        }
-        for (; m < m1; ++m) acc[ik[m] * TH] += dD[(size_t)m * TH + d];
-    } else if (tid < 6 * TH + H) {
-        const int c = tid - 6 * TH;
-        float* acc = s_tab + TG_BIN_FLOATS + TG_DUR_FLOATS + c;
-        int m = m0;
-        for (; m + 4 <= m1; m += 4) {
-            const float v0 = dXi[(size_t)m * HP + c], v1 = dXi[(size_t)(m + 1) * HP + c];
-            const float v2 = dXi[(size_t)(m + 2) * HP + c], v3 = dXi[(size_t)(m + 3) * HP + c];
-            acc[(m % T) * H] += v0; acc[((m + 1) % T) * H] += v1;
-            acc[((m + 2) % T) * H] += v2; acc[((m + 3) % T) * H] += v3;
-        }
-        for (; m < m1; ++m) acc[(m % T) * H] += dXi[(size_t)m * HP + c];
     }
-    __syncthreads();
-    float* dst = part + (size_t)blockIdx.x * TG_PART_FLOATS;
-    for (int i = tid; i < TG_PART_FLOATS; i += TG_THREADS) dst[i] = s_tab[i];
 }
 
-__global__ void __launch_bounds__(256)
-table_finish_kernel(const float* __restrict__ part, int nchunk, const float* __restrict__ dTq,
-                    const float* __restrict__ a_pt, const float* __restrict__ pos, const float* __restrict__ month,
-                    const float* __restrict__ day, const float* __restrict__ week, const float* __restrict__ hour,
-                    const float* __restrict__ minute, const float* __restrict__ dur, float* __restrict__ g_pos,
-                    float* __restrict__ g_month, float* __restrict__ g_day, float* __restrict__ g_week,
-                    float* __restrict__ g_hour, float* __restrict__ g_minute, float* __restrict__ g_dur, int B,
-                    int T) {
-    __shared__ float s_acc[256];
+__global__ void __launch_bounds__(TGD_THREADS)
+table_grads_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ ctx, const float* __restrict__ dXi,
+                   const float* __restrict__ dP, const float* __restrict__ dD, const float* __restrict__ dCT,
+                   const float* __restrict__ dTq, const float* __restrict__ a_pt, const float* __restrict__ pos,
+                   const float* __restrict__ month, const float* __restrict__ day, const float* __restrict__ week,
+                   const float* __restrict__ hour, const float* __restrict__ minute, const float* __restrict__ dur,
+                   float* __restrict__ g_pos, float* __restrict__ g_month, float* __restrict__ g_day,
+                   float* __restrict__ g_week, float* __restrict__ g_hour, float* __restrict__ g_minute,
+                   float* __restrict__ g_dur, int B, int T) {
+    __shared__ __align__(16) float s_part[TGD_WARPS][256];
     __shared__ float s_g[256];
     __shared__ float red[32];
     const int row = blockIdx.x;  // [0,40) pos, [40,179) time bins, [179,190) duration
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int M = B * T;
     const float* x;
     float* g;
     int width;
     if (row < TCAR_MAXT) {
+        // position row t: sum over the sessions of dXi[b * T + t, :] -- thread <-> (float4 column, session group)
         width = H;
         x = pos + (size_t)row * H;
         g = g_pos + (size_t)row * H;
-        const int c = threadIdx.x;
-        float acc = 0.f;
-        if (row < T && c < H) {
-            // chunk partials in a fixed order, four independent running sums so that the loads overlap
-            const float* src = part + TG_BIN_FLOATS + TG_DUR_FLOATS + (size_t)row * H + c;
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-            int j = 0;
-            for (; j + 4 <= nchunk; j += 4) {
-                a0 += src[(size_t)j * TG_PART_FLOATS]; a1 += src[(size_t)(j + 1) * TG_PART_FLOATS];
-                a2 += src[(size_t)(j + 2) * TG_PART_FLOATS]; a3 += src[(size_t)(j + 3) * TG_PART_FLOATS];
+        const int c4 = tid & 63, grp = tid >> 6;                    // 64 float4 columns x 8 session groups
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+        if (row < T) {
+            const float4* src = reinterpret_cast<const float4*>(dXi + (size_t)row * HP) + c4;
+            const size_t step = (size_t)T * (HP / 4);               // float4 stride between sessions
+            int bb = grp;
+            for (; bb + 24 < B; bb += 32) {
+                const float4 u0 = src[(size_t)bb * step], u1 = src[(size_t)(bb + 8) * step];
+                const float4 u2 = src[(size_t)(bb + 16) * step], u3 = src[(size_t)(bb + 24) * step];
+                a0.x += u0.x; a0.y += u0.y; a0.z += u0.z; a0.w += u0.w;
+                a1.x += u1.x; a1.y += u1.y; a1.z += u1.z; a1.w += u1.w;
+                a2.x += u2.x; a2.y += u2.y; a2.z += u2.z; a2.w += u2.w;
+                a3.x += u3.x; a3.y += u3.y; a3.z += u3.z; a3.w += u3.w;
             }
-            for (; j < nchunk; ++j) a0 += src[(size_t)j * TG_PART_FLOATS];
-            acc = (a0 + a1) + (a2 + a3);
+            for (; bb < B; bb += 8) {
+                const float4 u0 = src[(size_t)bb * step];
+                a0.x += u0.x; a0.y += u0.y; a0.z += u0.z; a0.w += u0.w;
+            }
         }
-        s_g[threadIdx.x] = acc;
+        float4 t4;
+        t4.x = (a0.x + a1.x) + (a2.x + a3.x); t4.y = (a0.y + a1.y) + (a2.y + a3.y);
+        t4.z = (a0.z + a1.z) + (a2.z + a3.z); t4.w = (a0.w + a1.w) + (a2.w + a3.w);
+        reinterpret_cast<float4*>(&s_part[grp][0])[c4] = t4;
+        __syncthreads();
+        if (tid < 256) {
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc += s_part[i][tid];
+            s_g[tid] = tid < H ? acc : 0.f;                          // dXi pad columns are never written
+        }
     } else {
         width = TH;
-        const int d = threadIdx.x & 63, grp = threadIdx.x >> 6;  // 4 groups
         const int r = row - TCAR_MAXT;
-        float acc = 0.f;
+        float acc0 = 0.f, acc1 = 0.f;
+        int k = -1;
         if (r < NB) {
-            int k = 0;
-            while (r >= kBinOff[k + 1]) ++k;
+            k = (r >= 13) + (r >= 45) + (r >= 53) + (r >= 78);
             const int rr = r - kBinOff[k];
             const float* tabs[5] = {month, day, week, hour, minute};
             float* gs[5] = {g_month, g_day, g_week, g_hour, g_minute};
             x = tabs[k] + (size_t)rr * TH;
             g = gs[k] + (size_t)rr * TH;
-            {
-                const float* src = part + (size_t)r * TH + d;
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                int j = grp;
-                for (; j + 12 < nchunk; j += 16) {
-                    a0 += src[(size_t)j * TG_PART_FLOATS]; a1 += src[(size_t)(j + 4) * TG_PART_FLOATS];
-                    a2 += src[(size_t)(j + 8) * TG_PART_FLOATS]; a3 += src[(size_t)(j + 12) * TG_PART_FLOATS];
-                }
-                for (; j < nchunk; j += 4) a0 += src[(size_t)j * TG_PART_FLOATS];
-                acc = (a0 + a1) + (a2 + a3);
-            }
-            // scoring side: d/d clip(table)[r] of sum_b Tq[b,r] = sum_b dTq[b,r] a_pt[b, 64k:64k+64]
-            {
-                const float* dq = dTq + r;
-                const float* ap = a_pt + k * TH + d;
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                int b = grp;
-                for (; b + 12 < B; b += 16) {
-                    a0 = fmaf(dq[(size_t)b * NB], ap[(size_t)b * PW], a0);
-                    a1 = fmaf(dq[(size_t)(b + 4) * NB], ap[(size_t)(b + 4) * PW], a1);
-                    a2 = fmaf(dq[(size_t)(b + 8) * NB], ap[(size_t)(b + 8) * PW], a2);
-                    a3 = fmaf(dq[(size_t)(b + 12) * NB], ap[(size_t)(b + 12) * PW], a3);
-                }
-                for (; b < B; b += 4) a0 = fmaf(dq[(size_t)b * NB], ap[(size_t)b * PW], a0);
-                acc += (a0 + a1) + (a2 + a3);
-            }
+            match_accumulate(idx + (size_t)(k + 1) * M, rr, M, dP + k * TH, PW, w, lane, acc0, acc1);
+            // click-time context (sampler.py:106-107): week table by ctx[0][b], hour table by ctx[1][b]
+            if (k == 2) match_accumulate(ctx, rr, B, dCT, 2 * TH, w, lane, acc0, acc1);
+            if (k == 3) match_accumulate(ctx + B, rr, B, dCT + TH, 2 * TH, w, lane, acc0, acc1);
         } else {
             const int rr = r - NB;
             x = dur + (size_t)rr * TH;
             g = g_dur + (size_t)rr * TH;
-            const float* src = part + TG_BIN_FLOATS + (size_t)rr * TH + d;
-            float a0 = 0.f, a1 = 0.f;
-            int j = grp;
-            for (; j + 4 < nchunk; j += 8) { a0 += src[(size_t)j * TG_PART_FLOATS]; a1 += src[(size_t)(j + 4) * TG_PART_FLOATS]; }
-            for (; j < nchunk; j += 4) a0 += src[(size_t)j * TG_PART_FLOATS];
-            acc = a0 + a1;
+            match_accumulate(idx + (size_t)6 * M, rr, M, dD, TH, w, lane, acc0, acc1);
         }
-        s_acc[threadIdx.x] = acc;
+        s_part[w][lane] = acc0;
+        s_part[w][32 + lane] = acc1;
+        // scoring side: d/d clip(table)[r] of sum_b Tq[b,r] = sum_b dTq[b,r] a_pt[b, 64k:64k+64]; thread <-> (d, group)
+        float sc = 0.f;
+        if (k >= 0) {
+            const int d = tid & 63, grp = tid >> 6;                  // 8 session groups
+            const float* dq = dTq + r;
+            const float* ap = a_pt + k * TH + d;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            int bb = grp;
+            for (; bb + 24 < B; bb += 32) {
+                a0 = fmaf(dq[(size_t)bb * NB], ap[(size_t)bb * PW], a0);
+                a1 = fmaf(dq[(size_t)(bb + 8) * NB], ap[(size_t)(bb + 8) * PW], a1);
+                a2 = fmaf(dq[(size_t)(bb + 16) * NB], ap[(size_t)(bb + 16) * PW], a2);
+                a3 = fmaf(dq[(size_t)(bb + 24) * NB], ap[(size_t)(bb + 24) * PW], a3);
+            }
+            for (; bb < B; bb += 8) a0 = fmaf(dq[(size_t)bb * NB], ap[(size_t)bb * PW], a0);
+            sc = (a0 + a1) + (a2 + a3);
+        }
+        // thread (d, grp) parks its scoring partial in row grp, columns 128 + d
+        if (k >= 0) s_part[tid >> 6][128 + (tid & 63)] = sc;
         __syncthreads();
-        if (threadIdx.x < 64)
-            s_g[threadIdx.x] = (s_acc[threadIdx.x] + s_acc[64 + threadIdx.x]) + (s_acc[128 + threadIdx.x] + s_acc[192 + threadIdx.x]);
+        if (tid < 64) {
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < TGD_WARPS; ++i) acc += s_part[i][tid];
+            if (k >= 0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc += s_part[i][128 + tid];
+            }
+            s_g[tid] = acc;
+        }
     }
     __syncthreads();
-    const int c = threadIdx.x;
+    const int c = tid;
     const float xv = c < width ? x[c] : 0.f;
     const float gv = c < width ? s_g[c] : 0.f;
     const float sq = block_sum(xv * xv, red);
     const float n = sqrtf(sq);
     if (n > 1.f) {
-        const float s = 1.f / n;
-        const float ydg = block_sum(xv * s * gv, red);
-        if (c < width) g[c] = s * (gv - xv * s * ydg);
+        const float sI = 1.f / n;
+        const float ydg = block_sum(xv * sI * gv, red);
+        if (c < width) g[c] = sI * (gv - xv * sI * ydg);
     } else if (c < width) {
         g[c] = gv;
     }
@@ -957,7 +946,7 @@ extern "C" int tcar_build_query(const float* a_ic, const float* a_pt, const floa
 
 extern "C" int tcar_ce_finish(const float* rowsum_part, float* sumexp, float* ce, int n_tiles, int B, void* stream) {
     if (B < 1 || B > TCAR_QROWS) return TCAR_ERR_ARG;
-    ce_finish_kernel<<<(B + 31) / 32, 1024, 0, STREAM>>>(rowsum_part, sumexp, ce, n_tiles, B);
+    ce_finish_kernel<<<(B + 15) / 16, 1024, 0, STREAM>>>(rowsum_part, sumexp, ce, n_tiles, B);
     return LAUNCH_RC();
 }
 
@@ -993,19 +982,11 @@ extern "C" int tcar_small_table_grads(const int32_t* idx, const int32_t* ctx, co
                                       const float* hour, const float* minute, const float* dur, float* g_pos,
                                       float* g_month, float* g_day, float* g_week, float* g_hour, float* g_minute,
                                       float* g_dur, float* part, int B, int T, void* stream) {
-    if (B < 1 || T < 1 || T > TCAR_MAXT || !part) return TCAR_ERR_ARG;
-    const int M = B * T;
-    int nchunk = (M + 31) / 32;                      // >= 32 clicks per chunk
-    if (nchunk > TG_MAX_CHUNKS) nchunk = TG_MAX_CHUNKS;
-    const int smem = TG_PART_FLOATS * 4;
-    cudaError_t e = cudaFuncSetAttribute(table_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return (int)e;
-    table_partial_kernel<<<nchunk, TG_THREADS, smem, STREAM>>>(idx, ctx, dXi, dP, dD, dCT, part, B, T);
-    int rc = LAUNCH_RC();
-    if (rc) return rc;
-    table_finish_kernel<<<TCAR_MAXT + NB + 11, 256, 0, STREAM>>>(part, nchunk, dTq, a_pt, pos, month, day, week, hour,
-                                                                  minute, dur, g_pos, g_month, g_day, g_week, g_hour,
-                                                                  g_minute, g_dur, B, T);
+    (void)part;      // scratch of the former two-pass version; kept in the signature, no longer touched
+    if (B < 1 || T < 1 || T > TCAR_MAXT) return TCAR_ERR_ARG;
+    table_grads_kernel<<<TCAR_MAXT + NB + 11, TGD_THREADS, 0, STREAM>>>(
+        idx, ctx, dXi, dP, dD, dCT, dTq, a_pt, pos, month, day, week, hour, minute, dur, g_pos, g_month, g_day, g_week,
+        g_hour, g_minute, g_dur, B, T);
     return LAUNCH_RC();
 }
 
