@@ -146,6 +146,22 @@ int tcar_small_table_grads(const int32_t* idx, const int32_t* ctx, const float* 
  *      three matrices. */
 int tcar_act_bwd_colsum(const float* dy, const float* y, float* dz, float* gb, int rows, int cols, int ld, int mode,
                         void* stream);
+/* Several such column reductions in ONE launch.  mode 0 / 1 as above (a = dy [rows, ld]); mode 2: the weight-vector
+ * gradients of count_alpha_* (modules.py:99,134): out[c] = sum_r y[r,c] * a[r] (a = [rows] vector, dz unused).
+ * scratch (optional): TCAR_COL_SCRATCH(cols) floats, ZERO before the first use (the kernel leaves its ticket counters
+ * at zero); with it, jobs of more than 1024 rows are split across CTAs and combined in a fixed order. */
+#define TCAR_COL_JOBS 4
+#define TCAR_COL_MAX_SPLIT 32
+#define TCAR_COL_SCRATCH(cols) (TCAR_COL_MAX_SPLIT * (cols) + ((cols) + 31) / 32)
+typedef struct tcar_col_job {
+    const float* a;
+    const float* y;
+    float* dz;
+    float* out;
+    float* scratch;
+    int rows, cols, ld, mode;
+} tcar_col_job;
+int tcar_col_jobs(const tcar_col_job* jobs, int njobs, void* stream);
 
 /* (2c) dense projections on the tensor cores (tcgen05.mma.kind::tf32) -- the matmuls of linear_2d / linear_3d
  *      (modules.py:43-70) and their weight / data gradients:
@@ -176,6 +192,8 @@ typedef struct tcar_gemm_problem {
     float* C;
     int ldc, accumulate, precise, splits;
     float* part;
+    float* C2;      /* optional second destination: rows >= c2_row0 of the result are ALSO written to               */
+    int c2_row0;    /* C2[(row - c2_row0) * ldc + col] (W_c's gradient is the bottom half of X^T dU1: no copy kernel) */
 } tcar_gemm_problem;
 int tcar_gemm_tf32_group(const tcar_gemm_problem* probs, int nprob, void* stream);
 int tcar_gemm_tf32_splits(int M, int N, int k_total, int want);

@@ -35,6 +35,7 @@ SIGNATURES = {
     "tcar_sqnorm_combine": [_P, _I, _P, _I, _P, _P],
     "tcar_small_table_grads": [_P] * 23 + [_I, _I, _P],
     "tcar_act_bwd_colsum": [_P] * 4 + [_I, _I, _I, _I, _P],
+    "tcar_col_jobs": [_P, _I, _P],
     "tcar_gemm_tf32": [_P, _I, _I, _I, _P, _I, _P, _I, _I, _I, _I, _P, _P],
     "tcar_gemm_tf32_group": [_P, _I, _P],
     "tcar_gemm_tf32_splits": [_I, _I, _I, _I],
@@ -103,7 +104,7 @@ class GemmProblem(C.Structure):
     """tcar_gemm_problem of include/tcar_b200.h."""
     _fields_ = [("segs", GemmSeg * 3), ("nseg", C.c_int), ("M", C.c_int), ("N", C.c_int), ("bias", C.c_void_p),
                 ("act", C.c_int), ("C", C.c_void_p), ("ldc", C.c_int), ("accumulate", C.c_int), ("precise", C.c_int),
-                ("splits", C.c_int), ("part", C.c_void_p)]
+                ("splits", C.c_int), ("part", C.c_void_p), ("C2", C.c_void_p), ("c2_row0", C.c_int)]
 
 
 def _seg(sg):
@@ -112,8 +113,9 @@ def _seg(sg):
                    int(a_mn), int(b_mn), sg[8] if len(sg) > 8 else 0)
 
 
-def problem(segs, M, N, out, ldc, bias=None, act=0, accumulate=False, precise=False, splits=1, part=None):
-    """One tcar_gemm_problem; segs as in gemm()."""
+def problem(segs, M, N, out, ldc, bias=None, act=0, accumulate=False, precise=False, splits=1, part=None, out2=None,
+            out2_row0=0):
+    """One tcar_gemm_problem; segs as in gemm().  out2: rows >= out2_row0 are also written to out2 (pitch ldc)."""
     q = GemmProblem()
     for i, sg in enumerate(segs):
         q.segs[i] = _seg(sg)
@@ -122,6 +124,8 @@ def problem(segs, M, N, out, ldc, bias=None, act=0, accumulate=False, precise=Fa
     q.act, q.C, q.ldc = act, out.data_ptr(), ldc
     q.accumulate, q.precise, q.splits = int(accumulate), int(precise), splits
     q.part = part.data_ptr() if part is not None else None
+    q.C2 = out2.data_ptr() if out2 is not None else None
+    q.c2_row0 = out2_row0
     return q
 
 
@@ -143,6 +147,24 @@ def gemm(segs, M, N, out, ldc, bias=None, act=0, accumulate=False, precise=False
     LAUNCHES["count"] += 1 + (1 if splits > 1 else 0)
     return call("tcar_gemm_tf32", C.cast(arr, C.c_void_p), len(segs), M, N, ptr(bias), act, ptr(out), ldc,
                 int(accumulate), int(precise), splits, ptr(part))
+
+
+class ColJob(C.Structure):
+    """tcar_col_job of include/tcar_b200.h."""
+    _fields_ = [("a", C.c_void_p), ("y", C.c_void_p), ("dz", C.c_void_p), ("out", C.c_void_p),
+                ("scratch", C.c_void_p), ("rows", C.c_int), ("cols", C.c_int), ("ld", C.c_int), ("mode", C.c_int)]
+
+
+def col_jobs(jobs):
+    """jobs: list of (a, y, dz | None, out, rows, cols, ld, mode[, scratch]) -- one launch (tcar_col_jobs)."""
+    arr = (ColJob * len(jobs))()
+    for i, job in enumerate(jobs):
+        a, y, dz, out, rows, cols, ld, mode = job[:8]
+        scratch = job[8] if len(job) > 8 else None
+        arr[i] = ColJob(a.data_ptr(), y.data_ptr(), dz.data_ptr() if dz is not None else None, out.data_ptr(),
+                        scratch.data_ptr() if scratch is not None else None, rows, cols, ld, mode)
+    LAUNCHES["count"] += 1
+    return call("tcar_col_jobs", C.cast(arr, C.c_void_p), len(jobs))
 
 
 LAUNCHES = {"count": 0}

@@ -53,6 +53,8 @@ struct GemmParams {
     long long part_stride; // elements between split partials
     float* out;            // final destination of the split reduction
     int ld_out;
+    float* out2;           // optional second destination for rows >= out2_row0 (same pitch as the first)
+    int out2_row0;
 };
 
 struct GemmMaps {
@@ -285,6 +287,9 @@ gemm_tf32_kernel(const __grid_constant__ GemmGroup grp) {
         }
         if (tid == 0) G_TRACE(5);
         float* crow = p.C + (size_t)split * p.part_stride + (size_t)row * p.ldc;
+        // second destination (unsplit problems only; split ones apply it in the reduction kernel)
+        float* crow2 = (p.out2 && p.splits == 1 && row >= p.out2_row0) ? p.out2 + (size_t)(row - p.out2_row0) * p.ldc
+                                                                       : nullptr;
         const bool vec = (p.ldc & 3) == 0;
         const float* bias = p.bias;
         const int act = p.act, accumulate = p.accumulate, Ncols = p.N;
@@ -329,6 +334,11 @@ gemm_tf32_kernel(const __grid_constant__ GemmGroup grp) {
                     for (int j = 0; j < 32; ++j)
                         if (c0 + j < Ncols) crow[c0 + j] = accumulate ? crow[c0 + j] + o[j] : o[j];
                 }
+                if (crow2) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (c0 + j < Ncols) crow2[c0 + j] = o[j];
+                }
             }
         }
     }
@@ -351,6 +361,7 @@ gemm_reduce_splits_kernel(const __grid_constant__ GemmGroup grp) {
     float acc = 0.f;
     for (int s = 0; s < p.splits; ++s) acc += p.C[(size_t)s * p.part_stride + (size_t)r * p.ldc + c];
     p.out[(size_t)r * p.ld_out + c] = acc;
+    if (p.out2 && r >= p.out2_row0) p.out2[(size_t)(r - p.out2_row0) * p.ld_out + c] = acc;
 }
 
 // Pre-split of the dense weights (once per step, after Adam): for every tensor t of the table
@@ -485,6 +496,9 @@ static int setup_problem(const tcar_gemm_problem& q, GemmParams& p, GemmMaps& ma
     p.ntiles = (N + p.bn - 1) / p.bn;
     p.out = q.C;
     p.ld_out = q.ldc;
+    p.out2 = q.C2;
+    p.out2_row0 = q.c2_row0;
+    if (q.C2 && (q.accumulate || q.c2_row0 < 0 || q.c2_row0 >= M)) return TCAR_ERR_ARG;
     if (splits > 1) {
         p.C = q.part;
         p.ldc = p.ntiles * p.bn;

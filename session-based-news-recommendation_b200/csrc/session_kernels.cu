@@ -458,30 +458,74 @@ ce_finish_kernel(const float* __restrict__ part, float* __restrict__ sumexp, flo
     }
 }
 
-// ------------------------------------------------------------------------------------------------ (5a') act bwd
-// 32 columns per CTA (lane = column), 32 warps stride over the rows; column sums combined in warp order.
+// ------------------------------------------------------------------------------------------------ (5a') column jobs
+// Up to TCAR_COL_JOBS independent column reductions in one launch (blockIdx.y = job): 32 columns per CTA (lane =
+// column), 32 warps stride over the rows with four rows in flight per thread; column sums combined in a fixed order.
+//   mode 0 / 1: dz[r,c] = a[r,c] * act'(y[r,c]) (tanh: 1 - y^2, relu: y > 0), out[c] = sum_r dz[r,c]
+//   mode 2    : out[c] = sum_r y[r,c] * a[r]          (weight-vector gradients of count_alpha_*, modules.py:99,134)
+// Long jobs (rows > 512, given a scratch) are split over blockIdx.z: every CTA parks its partial sums in the scratch,
+// and the CTA that arrives last (ticket counter behind the partials) adds them in split order -- the result does not
+// depend on which CTA that is.
+struct ColJobs { tcar_col_job j[TCAR_COL_JOBS]; int rsplit[TCAR_COL_JOBS]; };
+
+__device__ __forceinline__ float col_term(const tcar_col_job& q, int r, int c) {
+    const size_t i = (size_t)r * q.ld + c;
+    const float yv = q.y[i];
+    if (q.mode == 2) return yv * q.a[r];
+    const float d = q.a[i] * (q.mode == 0 ? (1.f - yv * yv) : (yv > 0.f ? 1.f : 0.f));
+    q.dz[i] = d;
+    return d;
+}
+
 __global__ void __launch_bounds__(1024)
-act_bwd_colsum_kernel(const float* __restrict__ dy, const float* __restrict__ y, float* __restrict__ dz,
-                      float* __restrict__ gb, int rows, int cols, int ld, int mode) {
+col_jobs_kernel(const __grid_constant__ ColJobs jobs) {
+    const tcar_col_job& q = jobs.j[blockIdx.y];
+    const int rsplit = jobs.rsplit[blockIdx.y];
+    if ((int)blockIdx.x * 32 >= q.cols || (int)blockIdx.z >= rsplit) return;
     __shared__ float s[32][33];
+    __shared__ int s_last;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + lane;
-    float acc = 0.f;
-    if (c < cols) {
-        for (int r = w; r < rows; r += 32) {
-            const size_t i = (size_t)r * ld + c;
-            const float yv = y[i];
-            const float d = dy[i] * (mode == 0 ? (1.f - yv * yv) : (yv > 0.f ? 1.f : 0.f));
-            dz[i] = d;
-            acc += d;
+    const int per = (q.rows + rsplit - 1) / rsplit;
+    const int r0 = blockIdx.z * per, r1 = min(r0 + per, q.rows);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (c < q.cols) {
+        int r = r0 + w;
+        for (; r + 96 < r1; r += 128) {
+            a0 += col_term(q, r, c); a1 += col_term(q, r + 32, c);
+            a2 += col_term(q, r + 64, c); a3 += col_term(q, r + 96, c);
         }
+        for (; r < r1; r += 32) a0 += col_term(q, r, c);
     }
-    s[w][lane] = acc;
+    s[w][lane] = (a0 + a1) + (a2 + a3);
     __syncthreads();
-    if (w == 0 && c < cols) {
-        float t = 0.f;
+    float t = 0.f;
+    if (w == 0) {
         for (int i = 0; i < 32; ++i) t += s[i][lane];
-        gb[c] = t;
+    }
+    if (rsplit == 1) {
+        if (w == 0 && c < q.cols) q.out[c] = t;
+        return;
+    }
+    // scratch: [rsplit][cols] partials, then one ticket counter per column block
+    float* part = q.scratch;
+    int* ticket = reinterpret_cast<int*>(q.scratch + (size_t)rsplit * q.cols) + blockIdx.x;
+    if (w == 0) {
+        if (c < q.cols) part[(size_t)blockIdx.z * q.cols + c] = t;
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) s_last = atomicAdd(ticket, 1) == rsplit - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    if (w == 0) {
+        __threadfence();
+        if (c < q.cols) {
+            float tot = 0.f;
+            for (int z = 0; z < rsplit; ++z) tot += __ldcg(part + (size_t)z * q.cols + c);
+            q.out[c] = tot;
+        }
+        if (lane == 0) *ticket = 0;          // ready for the next launch
     }
 }
 
@@ -950,11 +994,32 @@ extern "C" int tcar_ce_finish(const float* rowsum_part, float* sumexp, float* ce
     return LAUNCH_RC();
 }
 
+extern "C" int tcar_col_jobs(const tcar_col_job* jobs, int njobs, void* stream) {
+    if (!jobs || njobs < 1 || njobs > TCAR_COL_JOBS) return TCAR_ERR_ARG;
+    ColJobs js = {};
+    int maxcols = 0, maxsplit = 1;
+    for (int i = 0; i < njobs; ++i) {
+        const tcar_col_job& q = jobs[i];
+        if (q.rows < 1 || q.cols < 1 || q.ld < q.cols || q.mode < 0 || q.mode > 2 || !q.a || !q.y || !q.out ||
+            (q.mode != 2 && !q.dz))
+            return TCAR_ERR_ARG;
+        js.j[i] = q;
+        int rs = q.scratch ? q.rows / 512 : 1;
+        if (rs < 1) rs = 1;
+        if (rs > TCAR_COL_MAX_SPLIT) rs = TCAR_COL_MAX_SPLIT;
+        js.rsplit[i] = rs;
+        if (q.cols > maxcols) maxcols = q.cols;
+        if (rs > maxsplit) maxsplit = rs;
+    }
+    col_jobs_kernel<<<dim3((maxcols + 31) / 32, njobs, maxsplit), 1024, 0, STREAM>>>(js);
+    return LAUNCH_RC();
+}
+
 extern "C" int tcar_act_bwd_colsum(const float* dy, const float* y, float* dz, float* gb, int rows, int cols, int ld,
                                    int mode, void* stream) {
-    if (rows < 1 || cols < 1 || ld < cols || (mode != 0 && mode != 1)) return TCAR_ERR_ARG;
-    act_bwd_colsum_kernel<<<(cols + 31) / 32, 1024, 0, STREAM>>>(dy, y, dz, gb, rows, cols, ld, mode);
-    return LAUNCH_RC();
+    if (mode != 0 && mode != 1) return TCAR_ERR_ARG;
+    tcar_col_job q = {dy, y, dz, gb, nullptr, rows, cols, ld, mode};
+    return tcar_col_jobs(&q, 1, stream);
 }
 
 extern "C" int tcar_neg_loss(const float* a_ic, const float* item, const float* content, const int32_t* neg,

@@ -147,6 +147,7 @@ class Seq2SeqAttNN:
         self.h1, self.dh1, self.q, self.dq = f(Bm, HP), f(Bm, HP), f(Bm, XW), f(Bm, XW)
         self.dpooled, self.dpooled_t = f(Bm, XW), f(Bm, PW)
         self.gW_tmp = f(XW, H)
+        self.col_scratch = f(2, 32 * H + 8)         # TCAR_COL_SCRATCH(250) floats per long column job
         self.gemm_part = f(int(nv.lib().tcar_gemm_tf32_part_elems(XW, H, 16)) * 4)     # split-reduction scratch
         self._part_off = 0
         self.pooled, self.pooled_t = f(Bm, XW), f(Bm, PW)
@@ -280,6 +281,10 @@ class Seq2SeqAttNN:
         nv.counted_call("tcar_build_query", 1, p(self.a_ic), p(self.a_pt), p(ps.ct_tab), p(ps.item), p(ps.content),
                         p(ps.mwdhm), p(bt.label), p(self.Tq), p(self.Q), p(self.c_ref), B)
 
+    @staticmethod
+    def _splits_for(k):
+        return max(1, min(16, (k // 32) // 24))
+
     def _cluster_for(self, B):
         if self.cluster == nv.CLUSTER_PAIR:
             return nv.CLUSTER_PAIR
@@ -322,9 +327,11 @@ class Seq2SeqAttNN:
         wh, pr, HPp = ps.wh, nv.problem, nv.HP
         self._part_off = 0
         dz_a, dz_p = self.d_a_ic, self.d_a_pt
-        nv.counted_call("tcar_act_bwd_colsum", 1, p(dz_a), p(self.a_ic), p(dz_a), p(g["b_a"]), B, XW, XW, 0)
-        nv.counted_call("tcar_act_bwd_colsum", 1, p(dz_p), p(self.a_pt), p(dz_p), p(g["b_p"]), B, PW, PW, 0)
-        ksp = 4 if B > 128 else 1
+        nv.col_jobs([(dz_a, self.a_ic, dz_a, g["b_a"], B, XW, XW, 0), (dz_p, self.a_pt, dz_p, g["b_p"], B, PW, PW, 0)])
+        # split the reduction dimension across CTAs only when one CTA would walk more than ~48 K blocks of 32: a split
+        # costs a second (reduction) launch, which is worth it for long reductions only
+        old_policy = os.environ.get("TCAR_OLD_SPLITS") == "1"
+        ksp = (4 if B > 128 else 1) if old_policy else self._splits_for(B)
         nv.gemm_group([
             pr([(self.pooled, XW, 1, dz_a, None, XW, 1, B)], XW, XW, g["W_a"], XW, splits=ksp, part=self._part(XW, XW, ksp)),
             pr([(self.pooled_t, PW, 1, dz_p, None, PW, 1, B)], PW, PW, g["W_p"], PW, splits=ksp, part=self._part(PW, PW, ksp)),
@@ -333,28 +340,29 @@ class Seq2SeqAttNN:
         nv.counted_call("tcar_pool_bwd", 1, p(self.X), p(self.P), p(self.U1), p(self.U2), p(self.q), p(w["w_r"]),
                         p(w["w_t"]), p(self.alpha), p(self.dpooled), p(self.dpooled_t), p(self.dU1), p(self.dU2),
                         p(self.dXi), p(self.dP), p(self.dq), p(self.de), B, T)
-        S1, S2 = self.U1[:M, :H], self.U2[:M, :H]
         de = self.de.view(-1)                      # kernel layout: [3][B*T] with the ACTUAL B*T as stride
-        torch.mv(S1.t(), de[:M], out=g["w_r"].view(-1))
-        torch.mv(S2.t(), de[2 * M: 3 * M], out=g["w_t"].view(-1))
+        dzq = self.dq
+        # one launch: w_r / w_t gradients (S1^T de1, S2^T de_t) and the tanh backward of the query projection
+        nv.col_jobs([(de[:M], self.U1, None, g["w_r"], M, H, HPp, 2, self.col_scratch[0]),
+                     (de[2 * M: 3 * M], self.U2, None, g["w_t"], M, H, HPp, 2, self.col_scratch[1]),
+                     (dzq, self.q, dzq, g["bq2"], B, XW, XW, 0)])
         # every gradient that consumes dU1 / dU2, one launch: four weight gradients (reduction over the B*T clicks
         # split across CTAs) and three data gradients
-        msp = max(1, min(16, M // 512))
+        msp = max(1, min(16, M // 512)) if old_policy else self._splits_for(M)
         self._part_off = 0
         nv.gemm_group([
-            pr([(self.X, XW, 1, self.dU1, None, HPp, 1, M)], XW, H, g["W_in"], H, splits=msp, part=self._part(XW, H, msp)),
+            # rows 250..499 of X^T dU1 / X^T dU2 (the content half of X) are W_c's and W2's gradients: second
+            # destination of the same problem, no copy kernels
+            pr([(self.X, XW, 1, self.dU1, None, HPp, 1, M)], XW, H, g["W_in"], H, splits=msp, part=self._part(XW, H, msp),
+               out2=g["W_c"], out2_row0=H),
             pr([(self.D, TH, 1, self.dU1, None, HPp, 1, M)], TH, H, g["W_i"], H, splits=msp, part=self._part(TH, H, msp)),
             pr([(self.P, PW, 1, self.dU2, None, HPp, 1, M)], PW, H, g["W1"], H, splits=msp, part=self._part(PW, H, msp)),
             pr([(self.X, XW, 1, self.dU2, None, HPp, 1, M)], XW, H, self.gW_tmp, H, splits=msp,
-               part=self._part(XW, H, msp)),
+               part=self._part(XW, H, msp), out2=g["W2"], out2_row0=H),
             pr([(self.dU1, HPp, 0, wh["W_in1"], None, 256, 0, H)], M, H, self.dXi, HPp, accumulate=True),
             pr([(self.dU1, HPp, 0, wh["W_i"], None, 256, 0, H)], M, TH, self.dD, TH),
             pr([(self.dU2, HPp, 0, wh["W1"], None, 256, 0, H)], M, PW, self.dP, PW, accumulate=True)])
-        g["W_c"].copy_(g["W_in"][H:])              # Xc^T dU1 is the bottom half of X^T dU1
-        g["W2"].copy_(self.gW_tmp[H:])             # Xc^T dU2 likewise
         # query path backward (modules.py:138-139)
-        dzq = self.dq
-        nv.counted_call("tcar_act_bwd_colsum", 1, p(dzq), p(self.q), p(dzq), p(g["bq2"]), B, XW, XW, 0)
         self._part_off = 0
         nv.gemm_group([
             pr([(self.h1, HPp, 1, dzq, None, XW, 1, B)], H, XW, g["Wq2"], XW, splits=ksp, part=self._part(H, XW, ksp)),
@@ -365,7 +373,7 @@ class Seq2SeqAttNN:
             pr([(self.CT, 2 * TH, 1, self.dh1, None, HPp, 1, B)], 2 * TH, H, g["Wq1"], H, splits=ksp,
                part=self._part(2 * TH, H, ksp)),
             pr([(self.dh1, HPp, 0, wh["Wq1"], None, 256, 0, H)], B, 2 * TH, self.dCT, 2 * TH)])
-        nv.counted_call("tcar_small_table_grads", 2, p(bt.idx), p(bt.ctx), p(self.dXi), p(self.dP), p(self.dD),
+        nv.counted_call("tcar_small_table_grads", 1, p(bt.idx), p(bt.ctx), p(self.dXi), p(self.dP), p(self.dD),
                         p(self.dCT), p(self.dTq), p(self.a_pt), p(w["pos"]), p(w["month"]), p(w["day"]),
                         p(w["week"]), p(w["hour"]), p(w["minute"]), p(w["dur"]), p(g["pos"]), p(g["month"]),
                         p(g["day"]), p(g["week"]), p(g["hour"]), p(g["minute"]), p(g["dur"]), p(self.table_part), B, T)
