@@ -226,6 +226,11 @@ int tcar_sqnorm_big(const float* x, float* partial, float* sqnorm, long long n, 
 /* squared norm of the item gradient WITHOUT re-reading it: out[0] = sum(a[0..na)) + sum(b[0..nb)) in a fixed order,
  * a = per-CTA sums of squares written by tcar_score_bwd_i, b = slot_sq of tcar_scatter_add_rows. */
 int tcar_sqnorm_combine(const float* a, int na, const float* b, int nb, float* out, void* stream);
+/* tcar_sqnorm_segments + tcar_sqnorm_combine + `step[0] += 1` in ONE launch (the single-GPU train step): item_part
+ * [TCAR_NORM_SPLIT] floats and ticket [1] int32 (zero before the first use, left at zero) are scratch. */
+int tcar_update_norms(const float* flat, const int32_t* seg_off, float* sqnorm_small, int nseg, const float* a, int na,
+                      const float* b, int nb, float* sqnorm_item, float* item_part, int32_t* ticket, int32_t* step,
+                      void* stream);
 
 /* Debug aid (not thread-safe, not used on the product path): when trace_buf != NULL every CTA of the following
  * tcar_gemm_tf32* launches writes 8 clock64() stamps to trace_buf[8 * cta + k]: 0 start, 1 prologue done, 2 last TMA

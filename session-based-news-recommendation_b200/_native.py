@@ -45,6 +45,7 @@ SIGNATURES = {
     "tcar_scatter_add_rows": [_P] * 13 + [_I] * 4 + [_P],
     "tcar_sqnorm_segments": [_P] * 3 + [_I, _P],
     "tcar_sqnorm_big": [_P] * 3 + [_LL, _P],
+    "tcar_update_norms": [_P, _P, _P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P],
     "tcar_adam_small": [_P] * 6 + [_I, _P, _F, _F, _P],
     "tcar_adam_item": [_P] * 6 + [_F, _F, _P, _I, _I, _P, _I, _P],
     "tcar_adam_item_rows": [_P] * 6 + [_F, _F, _P, _P, _I, _P, _I, _P, _I, _P],

@@ -10,6 +10,7 @@
 #include <math.h>
 #include <stdint.h>
 #include "tcar_b200.h"
+#include "launch.cuh"
 
 namespace tcar {
 
@@ -123,6 +124,7 @@ eval_topk_kernel(const float* __restrict__ chunkmax, const float* __restrict__ t
                  const float* __restrict__ Tq, const float* __restrict__ item, const float* __restrict__ content,
                  const int32_t* __restrict__ mwdhm, const int32_t* __restrict__ label, int32_t* __restrict__ top_ids,
                  float* __restrict__ top_scores, int32_t* __restrict__ n_greater, int N, int n_pad, int item_offset) {
+    PDL_ENTER();
     __shared__ float s_aic[XW], s_tq[NB + 1];
     __shared__ int s_hist[256];
     __shared__ int s_sel[NCH];
@@ -237,6 +239,7 @@ eval_topk_kernel(const float* __restrict__ chunkmax, const float* __restrict__ t
 __global__ void __launch_bounds__(256)
 topk_merge_kernel(const int32_t* __restrict__ ids, const float* __restrict__ scores, int32_t* __restrict__ out_ids,
                   float* __restrict__ out_scores, int G, int B) {
+    PDL_ENTER();
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (b >= B) return;
     const int n = G * TOPK;
@@ -279,7 +282,7 @@ extern "C" int tcar_eval_topk(const float* chunkmax, const float* tilemax, const
                               float* top_scores, int32_t* n_greater, int B, int N, int n_pad, int item_offset,
                               void* stream) {
     if (B < 1 || B > TCAR_QROWS || N < 1 || n_pad < N || !tilemax) return TCAR_ERR_ARG;
-    eval_topk_kernel<<<B, 256, 0, STREAM>>>(chunkmax, tilemax, a_ic, Tq, item, content, mwdhm, label, top_ids, top_scores,
+    launch_pdl(eval_topk_kernel, dim3(B), dim3(256), 0, STREAM, chunkmax, tilemax, a_ic, Tq, item, content, mwdhm, label, top_ids, top_scores,
                                             n_greater, N, n_pad, item_offset);
     return (int)cudaGetLastError();
 }
@@ -287,6 +290,6 @@ extern "C" int tcar_eval_topk(const float* chunkmax, const float* tilemax, const
 extern "C" int tcar_topk_merge(const int32_t* ids, const float* scores, int32_t* out_ids, float* out_scores, int G,
                                int B, void* stream) {
     if (G < 1 || G > 8 || B < 1) return TCAR_ERR_ARG;
-    topk_merge_kernel<<<(B + 7) / 8, 256, 0, STREAM>>>(ids, scores, out_ids, out_scores, G, B);
+    launch_pdl(topk_merge_kernel, dim3((B + 7) / 8), dim3(256), 0, STREAM, ids, scores, out_ids, out_scores, G, B);
     return (int)cudaGetLastError();
 }

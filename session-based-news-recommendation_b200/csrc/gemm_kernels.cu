@@ -15,11 +15,12 @@
 //   kernel without transposes; the reduction dimension can be split across CTAs (fixed-order second pass).
 #include "sm100_ptx.cuh"
 #include "tcar_b200.h"
+#include "launch.cuh"
 
 namespace tcar {
 
 #ifndef TCAR_GEMM_EPI_WARPS
-#define TCAR_GEMM_EPI_WARPS 16
+#define TCAR_GEMM_EPI_WARPS 8
 #endif
 constexpr int G_EPI_WARPS = TCAR_GEMM_EPI_WARPS;  // a multiple of 4: G_EPI_WARPS / 4 warps per TMEM lane quarter
 constexpr int G_THREADS = 128 + 32 * G_EPI_WARPS;   // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, then split + epilogue warps
@@ -119,6 +120,7 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_tf32_kernel(const __grid_constant__ GemmGroup grp) {
+    PDL_ENTER();
     int gi = 0;
     while (gi + 1 < grp.nprob && (int)blockIdx.x >= grp.cta_start[gi + 1]) ++gi;
     const GemmMaps& maps = grp.maps[gi];
@@ -352,6 +354,7 @@ gemm_tf32_kernel(const __grid_constant__ GemmGroup grp) {
 // out[r, c] = sum_s part[s][r][c]  (fixed order) for every split problem of the group
 __global__ void __launch_bounds__(256)
 gemm_reduce_splits_kernel(const __grid_constant__ GemmGroup grp) {
+    PDL_ENTER();
     int gi = 0;
     while (gi + 1 < grp.nprob && (int)blockIdx.x >= grp.red_start[gi + 1]) ++gi;
     const GemmParams& p = grp.prm[gi];
@@ -371,6 +374,7 @@ gemm_reduce_splits_kernel(const __grid_constant__ GemmGroup grp) {
 __global__ void __launch_bounds__(256)
 prep_weights_kernel(const float* __restrict__ theta, const int32_t* __restrict__ table, float* __restrict__ hi,
                     float* __restrict__ lo) {
+    PDL_ENTER();
     const int32_t* t = table + blockIdx.y * 7;
     const int src = t[0], rows = t[1], cols = t[2], dst = t[3], pitch = t[4], src2 = t[5], row0 = t[6];
     const int n = rows * pitch;
@@ -542,11 +546,11 @@ extern "C" int tcar_gemm_tf32_group(const tcar_gemm_problem* probs, int nprob, v
     }
     cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
     if (e != cudaSuccess) return (int)e;
-    gemm_tf32_kernel<<<ctas, G_THREADS, G_SMEM, stream>>>(grp);
+    launch_pdl(gemm_tf32_kernel, dim3(ctas), dim3(G_THREADS), G_SMEM, stream, grp);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     if (any_split) {
-        gemm_reduce_splits_kernel<<<red, 256, 0, stream>>>(grp);
+        launch_pdl(gemm_reduce_splits_kernel, dim3(red), dim3(256), 0, stream, grp);
         e = cudaGetLastError();
     }
     return (int)e;
@@ -580,6 +584,6 @@ extern "C" long long tcar_gemm_tf32_part_elems(int M, int N, int splits) {
 extern "C" int tcar_prep_weights(const float* theta, const int32_t* table, int ntensors, float* hi, float* lo,
                                  void* stream_) {
     if (ntensors < 1) return TCAR_ERR_ARG;
-    prep_weights_kernel<<<dim3(74, ntensors), 256, 0, static_cast<cudaStream_t>(stream_)>>>(theta, table, hi, lo);
+    launch_pdl(prep_weights_kernel, dim3(dim3(74, ntensors)), dim3(256), 0, static_cast<cudaStream_t>(stream_), theta, table, hi, lo);
     return (int)cudaGetLastError();
 }

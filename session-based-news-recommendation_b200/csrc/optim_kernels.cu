@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdint.h>
 #include "tcar_b200.h"
+#include "launch.cuh"
 
 namespace tcar {
 
@@ -15,6 +16,7 @@ __device__ __constant__ int kBinOffO[6] = {0, 13, 45, 53, 78, 139};
 __global__ void __launch_bounds__(256)
 build_iext_kernel(const float* __restrict__ item, const float* __restrict__ content,
                   const int32_t* __restrict__ mwdhm, __nv_bfloat16* __restrict__ iext, int N, int n_pad) {
+    PDL_ENTER();
     const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (n >= n_pad) return;
     uint4* dst = reinterpret_cast<uint4*>(iext + (size_t)n * KEXT);  // 80 x 16 B per row
@@ -43,6 +45,7 @@ build_iext_kernel(const float* __restrict__ item, const float* __restrict__ cont
 constexpr int kSplit = TCAR_NORM_SPLIT;
 __global__ void __launch_bounds__(512)
 sqnorm_segments_kernel(const float* __restrict__ flat, const int32_t* __restrict__ seg_off, float* __restrict__ out) {
+    PDL_ENTER();
     __shared__ float red[16];
     const int s = blockIdx.y, j = blockIdx.x;
     const int lo = seg_off[s], hi = seg_off[s + 1];           // 16-byte aligned starts (params.py pads to 4 floats)
@@ -73,9 +76,81 @@ sqnorm_segments_kernel(const float* __restrict__ flat, const int32_t* __restrict
     }
 }
 
+// All clip norms of one training step in one launch, plus the step counter: rows 0..nseg-1 of the grid are
+// sqnorm_segments_kernel; row nseg reduces the item-gradient norm from the per-CTA sums of the dense gradient GEMM (a)
+// and the per-row corrections of the scatter (b) -- kSplit CTAs write one partial each and the CTA that arrives last
+// adds the partials in index order (result independent of the arrival order); thread 0 of CTA (0, 0) increments the
+// step counter, which no thread of this kernel reads.
+__global__ void __launch_bounds__(512)
+update_norms_kernel(const float* __restrict__ flat, const int32_t* __restrict__ seg_off, float* __restrict__ out_small,
+                    int nseg, const float* __restrict__ a, int na, const float4* __restrict__ b, int nb4,
+                    float* __restrict__ out_item, float* __restrict__ item_part, int32_t* __restrict__ ticket,
+                    int32_t* __restrict__ step) {
+    PDL_ENTER();
+    __shared__ float red[16];
+    __shared__ int s_last;
+    const int s = blockIdx.y, j = blockIdx.x;
+    float acc0 = 0.f, acc1 = 0.f;
+    if (s < nseg) {
+        const int lo = seg_off[s], hi = seg_off[s + 1];
+        const int n4 = (hi - lo) >> 2;
+        const int per = (n4 + kSplit - 1) / kSplit;
+        const int p0 = j * per, p1 = min(p0 + per, n4);
+        const float4* x = reinterpret_cast<const float4*>(flat + lo);
+        int i = p0 + threadIdx.x;
+        for (; i + 512 < p1; i += 1024) {
+            const float4 u = x[i], v = x[i + 512];
+            acc0 += u.x * u.x + u.y * u.y + u.z * u.z + u.w * u.w;
+            acc1 += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        }
+        if (i < p1) {
+            const float4 u = x[i];
+            acc0 += u.x * u.x + u.y * u.y + u.z * u.z + u.w * u.w;
+        }
+    } else {
+        if (j == 0)
+            for (int i = threadIdx.x; i < na; i += 512) acc0 += a[i];
+        const int per = (nb4 + kSplit - 1) / kSplit;
+        const int p0 = j * per, p1 = min(p0 + per, nb4);
+        int i = p0 + threadIdx.x;
+        for (; i + 512 < p1; i += 1024) {
+            const float4 u = b[i], v = b[i + 512];
+            acc0 += (u.x + u.y) + (u.z + u.w);
+            acc1 += (v.x + v.y) + (v.z + v.w);
+        }
+        if (i < p1) {
+            const float4 u = b[i];
+            acc0 += (u.x + u.y) + (u.z + u.w);
+        }
+    }
+    float acc = acc0 + acc1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    float t = 0.f;
+    for (int k = 0; k < 16; ++k) t += red[k];
+    if (s < nseg) {
+        out_small[s * kSplit + j] = t;
+        if (s == 0 && j == 0) step[0] += 1;
+        return;
+    }
+    item_part[j] = t;
+    __threadfence();
+    if (atomicAdd(ticket, 1) == kSplit - 1) {
+        __threadfence();
+        float tot = 0.f;
+        for (int k = 0; k < kSplit; ++k) tot += __ldcg(item_part + k);
+        out_item[0] = tot;
+        *ticket = 0;
+    }
+}
+
 // item columns of Iext from the fp32 item table (rows owned by OTHER ranks after the sharded Adam + all-gather)
 __global__ void __launch_bounds__(256)
 refresh_iext_items_kernel(const float4* __restrict__ item, __nv_bfloat16* __restrict__ iext, long long n4) {
+    PDL_ENTER();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const long long row = i >> 6;
         const int c = (int)(i & 63) * 4;
@@ -91,6 +166,7 @@ refresh_iext_items_kernel(const float4* __restrict__ item, __nv_bfloat16* __rest
 constexpr int kNormBlocks = 1184;  // 8 x 148 SMs
 __global__ void __launch_bounds__(256)
 sqnorm_big_partial_kernel(const float4* __restrict__ x, float* __restrict__ partial, long long n4) {
+    PDL_ENTER();
     __shared__ float red[8];
     float acc = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -109,6 +185,7 @@ sqnorm_big_partial_kernel(const float4* __restrict__ x, float* __restrict__ part
 }
 __global__ void __launch_bounds__(1024)
 sqnorm_big_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int n) {
+    PDL_ENTER();
     __shared__ float red[32];
     float acc = 0.f;
     for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partial[i];
@@ -128,6 +205,7 @@ sqnorm_big_final_kernel(const float* __restrict__ partial, float* __restrict__ o
 __global__ void __launch_bounds__(1024)
 sqnorm_combine_kernel(const float* __restrict__ a, int na, const float4* __restrict__ b, int nb4,
                       float* __restrict__ out) {
+    PDL_ENTER();
     __shared__ float red[32];
     float acc = 0.f;
     for (int i = threadIdx.x; i < na; i += blockDim.x) acc += a[i];
@@ -173,6 +251,7 @@ __global__ void __launch_bounds__(256)
 adam_small_kernel(float* __restrict__ theta, float* __restrict__ m, float* __restrict__ v,
                   const float* __restrict__ g, const int32_t* __restrict__ seg_off,
                   const float* __restrict__ sqnorm, const int32_t* __restrict__ step, float lr, float max_grad) {
+    PDL_ENTER();
     const int s = blockIdx.y;
     const int lo = seg_off[s], hi = seg_off[s + 1];
     float sq = 0.f;
@@ -204,6 +283,7 @@ adam_item_kernel(float4* __restrict__ item, float4* __restrict__ m, float4* __re
                  const float4* __restrict__ g, const float* __restrict__ sqnorm, const int32_t* __restrict__ step,
                  float lr, float max_grad, __nv_bfloat16* __restrict__ iext, long long n4, long long row0,
                  const int32_t* __restrict__ flags) {
+    PDL_ENTER();
     const int t = step[0];
     const float cf = clip_factor(sqnorm[0], max_grad);
     const float lr_t = adam_lr_t(t, lr);
@@ -248,6 +328,7 @@ adam_item_rows_kernel(float4* __restrict__ item, float4* __restrict__ m, float4*
                       const int32_t* __restrict__ step, float lr, float max_grad, __nv_bfloat16* __restrict__ iext,
                       const int32_t* __restrict__ seq, int n_seq, const int32_t* __restrict__ label, int n_label,
                       int32_t* __restrict__ flags, int n_rows) {
+    PDL_ENTER();
     const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (e >= n_seq + n_label) return;
     const int row = e < n_seq ? seq[e] : label[e - n_seq] + 1;
@@ -290,7 +371,7 @@ using namespace tcar;
 extern "C" int tcar_build_iext(const float* item, const float* content, const int32_t* mwdhm, void* iext_bf16, int N,
                                int n_pad, void* stream) {
     if (N < 1 || n_pad < N || n_pad % 256) return TCAR_ERR_ARG;
-    build_iext_kernel<<<(n_pad + 7) / 8, 256, 0, STREAM>>>(item, content, mwdhm,
+    launch_pdl(build_iext_kernel, dim3((n_pad + 7) / 8), dim3(256), 0, STREAM, item, content, mwdhm,
                                                            static_cast<__nv_bfloat16*>(iext_bf16), N, n_pad);
     return (int)cudaGetLastError();
 }
@@ -298,22 +379,31 @@ extern "C" int tcar_build_iext(const float* item, const float* content, const in
 extern "C" int tcar_sqnorm_segments(const float* flat, const int32_t* seg_off, float* sqnorm, int nseg,
                                     void* stream) {
     if (nseg < 1) return TCAR_ERR_ARG;
-    sqnorm_segments_kernel<<<dim3(kSplit, nseg), 512, 0, STREAM>>>(flat, seg_off, sqnorm);
+    launch_pdl(sqnorm_segments_kernel, dim3(dim3(kSplit, nseg)), dim3(512), 0, STREAM, flat, seg_off, sqnorm);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int tcar_update_norms(const float* flat, const int32_t* seg_off, float* sqnorm_small, int nseg,
+                                 const float* a, int na, const float* b, int nb, float* sqnorm_item,
+                                 float* item_part, int32_t* ticket, int32_t* step, void* stream) {
+    if (nseg < 1 || na < 0 || nb < 0 || (nb & 3) || !sqnorm_item || !item_part || !ticket || !step) return TCAR_ERR_ARG;
+    launch_pdl(update_norms_kernel, dim3(kSplit, nseg + 1), dim3(512), 0, STREAM, flat, seg_off, sqnorm_small, nseg, a, na,
+               reinterpret_cast<const float4*>(b), nb / 4, sqnorm_item, item_part, ticket, step);
     return (int)cudaGetLastError();
 }
 
 extern "C" int tcar_sqnorm_big(const float* x, float* partial, float* sqnorm, long long n, void* stream) {
     if (n % 4) return TCAR_ERR_ARG;
-    sqnorm_big_partial_kernel<<<kNormBlocks, 256, 0, STREAM>>>(reinterpret_cast<const float4*>(x), partial, n / 4);
+    launch_pdl(sqnorm_big_partial_kernel, dim3(kNormBlocks), dim3(256), 0, STREAM, reinterpret_cast<const float4*>(x), partial, n / 4);
     int rc = (int)cudaGetLastError();
     if (rc) return rc;
-    sqnorm_big_final_kernel<<<1, 1024, 0, STREAM>>>(partial, sqnorm, kNormBlocks);
+    launch_pdl(sqnorm_big_final_kernel, dim3(1), dim3(1024), 0, STREAM, partial, sqnorm, kNormBlocks);
     return (int)cudaGetLastError();
 }
 
 extern "C" int tcar_refresh_iext_items(const float* item, void* iext_bf16, int N, void* stream) {
     if (N < 1) return TCAR_ERR_ARG;
-    refresh_iext_items_kernel<<<148 * 16, 256, 0, STREAM>>>(reinterpret_cast<const float4*>(item),
+    launch_pdl(refresh_iext_items_kernel, dim3(148 * 16), dim3(256), 0, STREAM, reinterpret_cast<const float4*>(item),
                                                             static_cast<__nv_bfloat16*>(iext_bf16),
                                                             (long long)(N + 1) * (HP / 4));
     return (int)cudaGetLastError();
@@ -321,7 +411,7 @@ extern "C" int tcar_refresh_iext_items(const float* item, void* iext_bf16, int N
 
 extern "C" int tcar_sqnorm_combine(const float* a, int na, const float* b, int nb, float* out, void* stream) {
     if (na < 0 || nb < 0 || (nb & 3) || !out) return TCAR_ERR_ARG;
-    sqnorm_combine_kernel<<<1, 1024, 0, STREAM>>>(a, na, reinterpret_cast<const float4*>(b), nb / 4, out);
+    launch_pdl(sqnorm_combine_kernel, dim3(1), dim3(1024), 0, STREAM, a, na, reinterpret_cast<const float4*>(b), nb / 4, out);
     return (int)cudaGetLastError();
 }
 
@@ -329,7 +419,7 @@ extern "C" int tcar_adam_small(float* theta, float* m, float* v, const float* g,
                                const float* sqnorm, int nseg, const int32_t* step, float lr, float max_grad,
                                void* stream) {
     if (nseg < 1) return TCAR_ERR_ARG;
-    adam_small_kernel<<<dim3(64, nseg), 256, 0, STREAM>>>(theta, m, v, g, seg_off, sqnorm, step, lr, max_grad);
+    launch_pdl(adam_small_kernel, dim3(dim3(64, nseg)), dim3(256), 0, STREAM, theta, m, v, g, seg_off, sqnorm, step, lr, max_grad);
     return (int)cudaGetLastError();
 }
 
@@ -339,7 +429,7 @@ extern "C" int tcar_adam_item(float* item, float* m, float* v, const float* g, c
     if (row0 < 0 || nrows < 1 || ctas_per_sm < 0 || ctas_per_sm > 1024) return TCAR_ERR_ARG;
     const long long n4 = (long long)nrows * (HP / 4);
     const int grid = 148 * (ctas_per_sm ? ctas_per_sm : 16);
-    adam_item_kernel<<<grid, 256, 0, STREAM>>>(reinterpret_cast<float4*>(item), reinterpret_cast<float4*>(m),
+    launch_pdl(adam_item_kernel, dim3(grid), dim3(256), 0, STREAM, reinterpret_cast<float4*>(item), reinterpret_cast<float4*>(m),
                                                reinterpret_cast<float4*>(v), reinterpret_cast<const float4*>(g),
                                                sqnorm, step, lr, max_grad, static_cast<__nv_bfloat16*>(iext_bf16), n4,
                                                (long long)row0, row_flags);
@@ -353,7 +443,7 @@ extern "C" int tcar_adam_item_rows(float* item, float* m, float* v, const float*
     if (n_seq < 0 || n_label < 0 || n_rows < 1 || !row_flags) return TCAR_ERR_ARG;
     const int entries = n_seq + n_label;
     if (entries == 0) return 0;
-    adam_item_rows_kernel<<<(entries + 7) / 8, 256, 0, STREAM>>>(
+    launch_pdl(adam_item_rows_kernel, dim3((entries + 7) / 8), dim3(256), 0, STREAM, 
         reinterpret_cast<float4*>(item), reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v),
         reinterpret_cast<const float4*>(g), sqnorm, step, lr, max_grad, static_cast<__nv_bfloat16*>(iext_bf16), seq,
         n_seq, label, n_label, row_flags, n_rows);

@@ -22,6 +22,7 @@
 //   score_bwd_i : dItem[n,c] = sum_b E[b,n] Qs[b,c]       (Qs = a_ic / sumexp_b in bf16, c < 256)
 #include "sm100_ptx.cuh"
 #include "tcar_b200.h"
+#include "launch.cuh"
 
 namespace tcar {
 
@@ -59,6 +60,7 @@ template <int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 score_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_i,
                  const FwdParams p) {
+    PDL_ENTER();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
@@ -300,6 +302,7 @@ template <int MODE>
 __global__ void __launch_bounds__(P_THREADS, 1)
 score_fwd_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_i,
                       const FwdParams p) {
+    PDL_ENTER();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
@@ -459,6 +462,7 @@ struct BwdQParams {
 __global__ void __launch_bounds__(kThreads, 1)
 score_bwd_q_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant__ CUtensorMap map_i,
                    const BwdQParams p) {
+    PDL_ENTER();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Q_STAGES * Q_STAGE);
@@ -566,6 +570,7 @@ score_bwd_q_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_const
 // Fixed-order reduction of the split partials: out[b, c] = sum_s part[s, b, c].
 __global__ void reduce_splits_kernel(const float* __restrict__ part, float* __restrict__ out, int splits,
                                      int stride, int n) {
+    PDL_ENTER();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float acc = 0.f;
@@ -592,6 +597,7 @@ struct BwdIParams {
 __global__ void __launch_bounds__(kThreads, 1)
 score_bwd_i_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant__ CUtensorMap map_qs,
                    const BwdIParams p) {
+    PDL_ENTER();
     __shared__ float sq_red[4];
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -803,13 +809,18 @@ static int launch_fwd(const CUtensorMap& mq, const CUtensorMap& mi, const FwdPar
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = F_SMEM;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+#ifndef TCAR_NO_PDL
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+#endif
     e = cudaLaunchKernelEx(&cfg, score_fwd_kernel<CL>, mq, mi, p);
     return (int)e;
 }
@@ -825,13 +836,18 @@ static int launch_fwd_pair(const CUtensorMap& mq, const CUtensorMap& mi, const F
     cfg.blockDim = dim3(P_THREADS);
     cfg.dynamicSmemBytes = P_SMEM;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+#ifndef TCAR_NO_PDL
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+#endif
     return (int)cudaLaunchKernelEx(&cfg, score_fwd_pair_kernel<MODE>, mq, mi, p);
 }
 
@@ -925,12 +941,12 @@ extern "C" int tcar_score_bwd_q(const void* e_bf16, const void* iext_bf16, float
     p.kb_per = (p.kb_total + p.splits - 1) / p.splits;
     cudaError_t e = cudaFuncSetAttribute(score_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM);
     if (e != cudaSuccess) return (int)e;
-    score_bwd_q_kernel<<<p.splits * p.mtiles * 2, kThreads, Q_SMEM, stream>>>(me, mi, p);
+    launch_pdl(score_bwd_q_kernel, dim3(p.splits * p.mtiles * 2), dim3(kThreads), Q_SMEM, stream, me, mi, p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     // partial layout is [split][512][640]; rows of m-tiles that were not computed are never read by callers
     const int total = p.mtiles * BM * KEXT;
-    reduce_splits_kernel<<<(total + 255) / 256, 256, 0, stream>>>(part, dq, p.splits, QROWS * KEXT, total);
+    launch_pdl(reduce_splits_kernel, dim3((total + 255) / 256), dim3(256), 0, stream, part, dq, p.splits, QROWS * KEXT, total);
     return (int)cudaGetLastError();
 }
 
@@ -961,6 +977,6 @@ extern "C" int tcar_score_bwd_i(const void* e_bf16, const void* qs_bf16, float* 
     cudaError_t e = cudaFuncSetAttribute(score_bwd_i_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I_SMEM);
     if (e != cudaSuccess) return (int)e;
     const int grid = bwd_i_grid(n_pad);
-    score_bwd_i_kernel<<<grid, kThreads, I_SMEM, stream>>>(me, mq, p);
+    launch_pdl(score_bwd_i_kernel, dim3(grid), dim3(kThreads), I_SMEM, stream, me, mq, p);
     return (int)cudaGetLastError();
 }

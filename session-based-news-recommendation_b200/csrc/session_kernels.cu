@@ -6,6 +6,7 @@
 #include <math.h>
 #include <stdint.h>
 #include "tcar_b200.h"
+#include "launch.cuh"
 
 namespace tcar {
 
@@ -50,6 +51,7 @@ gather_fwd_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ c
                   const float* __restrict__ hour, const float* __restrict__ minute, const float* __restrict__ dur,
                   float* __restrict__ X, float* __restrict__ P, float* __restrict__ D, float* __restrict__ CT, int B,
                   int T) {
+    PDL_ENTER();
     const int M = B * T;
     const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -156,6 +158,7 @@ pool_fwd_kernel(const float* __restrict__ X, const float* __restrict__ P, float*
                 float* __restrict__ U2, const float* __restrict__ q, const float* __restrict__ w_r,
                 const float* __restrict__ w_t, float* __restrict__ alpha, float* __restrict__ pooled,
                 float* __restrict__ pooled_t, int B, int T) {
+    PDL_ENTER();
     __shared__ float s_e[3][TCAR_MAXT];
     __shared__ float s_a[3][TCAR_MAXT];
     __shared__ __align__(16) float s_q[XW + 12];
@@ -241,6 +244,7 @@ pool_bwd_kernel(const float* __restrict__ X, const float* __restrict__ P, const 
                 const float* __restrict__ dpooled_t, float* __restrict__ dU1, float* __restrict__ dU2,
                 float* __restrict__ dXi, float* __restrict__ dP, float* __restrict__ dq, float* __restrict__ de,
                 int B, int T) {
+    PDL_ENTER();
     __shared__ __align__(16) float s_dp[XW + 12], s_dpt[PW], s_q[XW + 12];
     __shared__ __align__(16) float s_wr[HP], s_wt[HP];
     __shared__ float s_a[3][TCAR_MAXT], s_da[2][TCAR_MAXT], s_de[3][TCAR_MAXT];
@@ -353,6 +357,7 @@ __global__ void clip_time_tables_kernel(const float* __restrict__ month, const f
                                         const float* __restrict__ week, const float* __restrict__ hour,
                                         const float* __restrict__ minute, float* __restrict__ ct_tab,
                                         float* __restrict__ ct_scale) {
+    PDL_ENTER();
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (r >= NB) return;
     int k = 0;
@@ -394,6 +399,7 @@ build_query_kernel(const float* __restrict__ a_ic, const float* __restrict__ a_p
                    const float* __restrict__ item, const float* __restrict__ content,
                    const int32_t* __restrict__ mwdhm, const int32_t* __restrict__ label, float* __restrict__ Tq,
                    __nv_bfloat16* __restrict__ Q, float* __restrict__ c_ref, int B) {
+    PDL_ENTER();
     __shared__ float s_aic[XW], s_apt[PW], s_tq[NB + 1];
     const int b = blockIdx.x;
     __nv_bfloat16* qr = Q + (size_t)b * TCAR_KEXT;
@@ -433,6 +439,7 @@ build_query_kernel(const float* __restrict__ a_ic, const float* __restrict__ a_p
 __global__ void __launch_bounds__(1024)
 ce_finish_kernel(const float* __restrict__ part, float* __restrict__ sumexp, float* __restrict__ ce, int n_tiles,
                  int B) {
+    PDL_ENTER();
     __shared__ float s[32][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int b = blockIdx.x * 16 + (lane & 15);
@@ -479,6 +486,7 @@ __device__ __forceinline__ float col_term(const tcar_col_job& q, int r, int c) {
 
 __global__ void __launch_bounds__(1024)
 col_jobs_kernel(const __grid_constant__ ColJobs jobs) {
+    PDL_ENTER();
     const tcar_col_job& q = jobs.j[blockIdx.y];
     const int rsplit = jobs.rsplit[blockIdx.y];
     if ((int)blockIdx.x * 32 >= q.cols || (int)blockIdx.z >= rsplit) return;
@@ -534,6 +542,7 @@ __global__ void __launch_bounds__(256)
 neg_loss_kernel(const float* __restrict__ a_ic, const float* __restrict__ item, const float* __restrict__ content,
                 const int32_t* __restrict__ neg, const float* __restrict__ ce, float* __restrict__ negloss,
                 float* __restrict__ loss, float* __restrict__ coef, float* __restrict__ dA_neg, int B, int Nn) {
+    PDL_ENTER();
     __shared__ float s_v[XW];
     __shared__ float red[32];
     const int b = blockIdx.x;
@@ -567,6 +576,7 @@ score_bwd_finish_kernel(const float* __restrict__ dq_raw, const float* __restric
                         const float* __restrict__ content, const int32_t* __restrict__ mwdhm,
                         const int32_t* __restrict__ label, float* __restrict__ d_a_ic, float* __restrict__ d_a_pt,
                         float* __restrict__ dTq, __nv_bfloat16* __restrict__ Qs, int B) {
+    PDL_ENTER();
     __shared__ float s_dt[NB + 1];
     const int b = blockIdx.x;
     __nv_bfloat16* qs = Qs + (size_t)b * HP;
@@ -658,6 +668,7 @@ table_grads_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ 
                    float* __restrict__ g_pos, float* __restrict__ g_month, float* __restrict__ g_day,
                    float* __restrict__ g_week, float* __restrict__ g_hour, float* __restrict__ g_minute,
                    float* __restrict__ g_dur, int B, int T) {
+    PDL_ENTER();
     __shared__ __align__(16) float s_part[TGD_WARPS][256];
     __shared__ float s_g[256];
     __shared__ float red[32];
@@ -799,6 +810,7 @@ __global__ void __launch_bounds__(256)
 scatter_count_kernel(const int32_t* __restrict__ seq, const int32_t* __restrict__ label,
                      const int32_t* __restrict__ neg, int32_t* __restrict__ keys, int32_t* __restrict__ cnt,
                      int32_t* __restrict__ entry_slot, int mask, int B, int T, int Nn) {
+    PDL_ENTER();
     const int M = B * T;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= M + B + B * Nn) return;
@@ -816,6 +828,7 @@ scatter_accum_kernel(const int32_t* __restrict__ seq, const int32_t* __restrict_
                      const float* __restrict__ coef, const float* __restrict__ item, float* __restrict__ g_item,
                      const int32_t* __restrict__ cnt, const int32_t* __restrict__ entry_slot,
                      unsigned long long* __restrict__ acc, float* __restrict__ slot_sq, int B, int T, int Nn) {
+    PDL_ENTER();
     const int M = B * T;
     const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (e >= M + B + B * Nn) return;
@@ -906,6 +919,7 @@ scatter_accum_kernel(const int32_t* __restrict__ seq, const int32_t* __restrict_
 __global__ void __launch_bounds__(256)
 scatter_apply_kernel(int32_t* __restrict__ keys, int32_t* __restrict__ cnt, long long* __restrict__ acc,
                      float* __restrict__ g_item, float* __restrict__ slot_sq, int hash_size) {
+    PDL_ENTER();
     const int slot0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31, lane = threadIdx.x & 31;
     const int mine = slot0 + lane;
     const int row_mine = mine < hash_size ? keys[mine] : -1;
@@ -949,7 +963,7 @@ extern "C" int tcar_gather_fwd(const int32_t* idx, const int32_t* ctx, const flo
                                float* CT, int B, int T, void* stream) {
     if (B < 1 || T < 1 || T > TCAR_MAXT) return TCAR_ERR_ARG;
     const int warps = B * T + B;
-    gather_fwd_kernel<<<(warps + 3) / 4, 128, 0, STREAM>>>(idx, ctx, item, content, pos, month, day, week, hour,
+    launch_pdl(gather_fwd_kernel, dim3((warps + 3) / 4), dim3(128), 0, STREAM, idx, ctx, item, content, pos, month, day, week, hour,
                                                            minute, dur, X, P, D, CT, B, T);
     return LAUNCH_RC();
 }
@@ -958,7 +972,7 @@ extern "C" int tcar_pool_fwd(const float* X, const float* P, float* U1, float* U
                              const float* w_t, float* alpha, float* pooled, float* pooled_t, int B, int T,
                              void* stream) {
     if (B < 1 || T < 1 || T > TCAR_MAXT) return TCAR_ERR_ARG;
-    pool_fwd_kernel<<<B, 256, 0, STREAM>>>(X, P, U1, U2, q, w_r, w_t, alpha, pooled, pooled_t, B, T);
+    launch_pdl(pool_fwd_kernel, dim3(B), dim3(256), 0, STREAM, X, P, U1, U2, q, w_r, w_t, alpha, pooled, pooled_t, B, T);
     return LAUNCH_RC();
 }
 
@@ -967,14 +981,14 @@ extern "C" int tcar_pool_bwd(const float* X, const float* P, const float* S1, co
                              const float* dpooled_t, float* dU1, float* dU2, float* dXi, float* dP, float* dq,
                              float* de, int B, int T, void* stream) {
     if (B < 1 || T < 1 || T > TCAR_MAXT) return TCAR_ERR_ARG;
-    pool_bwd_kernel<<<B, 256, 0, STREAM>>>(X, P, S1, S2, q, w_r, w_t, alpha, dpooled, dpooled_t, dU1, dU2, dXi, dP,
+    launch_pdl(pool_bwd_kernel, dim3(B), dim3(256), 0, STREAM, X, P, S1, S2, q, w_r, w_t, alpha, dpooled, dpooled_t, dU1, dU2, dXi, dP,
                                            dq, de, B, T);
     return LAUNCH_RC();
 }
 
 extern "C" int tcar_clip_time_tables(const float* month, const float* day, const float* week, const float* hour,
                                      const float* minute, float* ct_tab, float* ct_scale, void* stream) {
-    clip_time_tables_kernel<<<(NB * 32 + 255) / 256, 256, 0, STREAM>>>(month, day, week, hour, minute, ct_tab,
+    launch_pdl(clip_time_tables_kernel, dim3((NB * 32 + 255) / 256), dim3(256), 0, STREAM, month, day, week, hour, minute, ct_tab,
                                                                         ct_scale);
     return LAUNCH_RC();
 }
@@ -983,14 +997,14 @@ extern "C" int tcar_build_query(const float* a_ic, const float* a_pt, const floa
                                 const float* content, const int32_t* mwdhm, const int32_t* label, float* Tq,
                                 void* q_bf16, float* c_ref, int B, void* stream) {
     if (B < 1 || B > TCAR_QROWS) return TCAR_ERR_ARG;
-    build_query_kernel<<<TCAR_QROWS, 256, 0, STREAM>>>(a_ic, a_pt, ct_tab, item, content, mwdhm, label, Tq,
+    launch_pdl(build_query_kernel, dim3(TCAR_QROWS), dim3(256), 0, STREAM, a_ic, a_pt, ct_tab, item, content, mwdhm, label, Tq,
                                                        static_cast<__nv_bfloat16*>(q_bf16), c_ref, B);
     return LAUNCH_RC();
 }
 
 extern "C" int tcar_ce_finish(const float* rowsum_part, float* sumexp, float* ce, int n_tiles, int B, void* stream) {
     if (B < 1 || B > TCAR_QROWS) return TCAR_ERR_ARG;
-    ce_finish_kernel<<<(B + 15) / 16, 1024, 0, STREAM>>>(rowsum_part, sumexp, ce, n_tiles, B);
+    launch_pdl(ce_finish_kernel, dim3((B + 15) / 16), dim3(1024), 0, STREAM, rowsum_part, sumexp, ce, n_tiles, B);
     return LAUNCH_RC();
 }
 
@@ -1011,7 +1025,7 @@ extern "C" int tcar_col_jobs(const tcar_col_job* jobs, int njobs, void* stream) 
         if (q.cols > maxcols) maxcols = q.cols;
         if (rs > maxsplit) maxsplit = rs;
     }
-    col_jobs_kernel<<<dim3((maxcols + 31) / 32, njobs, maxsplit), 1024, 0, STREAM>>>(js);
+    launch_pdl(col_jobs_kernel, dim3(dim3((maxcols + 31) / 32, njobs, maxsplit)), dim3(1024), 0, STREAM, js);
     return LAUNCH_RC();
 }
 
@@ -1026,7 +1040,7 @@ extern "C" int tcar_neg_loss(const float* a_ic, const float* item, const float* 
                              const float* ce, float* negloss, float* loss, float* coef, float* dA_neg, int B, int Nn,
                              void* stream) {
     if (B < 1 || Nn < 0) return TCAR_ERR_ARG;
-    neg_loss_kernel<<<B, 256, 0, STREAM>>>(a_ic, item, content, neg, ce, negloss, loss, coef, dA_neg, B, Nn);
+    launch_pdl(neg_loss_kernel, dim3(B), dim3(256), 0, STREAM, a_ic, item, content, neg, ce, negloss, loss, coef, dA_neg, B, Nn);
     return LAUNCH_RC();
 }
 
@@ -1035,7 +1049,7 @@ extern "C" int tcar_score_bwd_finish(const float* dq_raw, const float* sumexp, c
                                      const int32_t* mwdhm, const int32_t* label, float* d_a_ic, float* d_a_pt,
                                      float* dTq, void* qs_bf16, int B, void* stream) {
     if (B < 1 || B > TCAR_QROWS) return TCAR_ERR_ARG;
-    score_bwd_finish_kernel<<<TCAR_QROWS, 256, 0, STREAM>>>(dq_raw, sumexp, dA_neg, a_ic, ct_tab, item, content,
+    launch_pdl(score_bwd_finish_kernel, dim3(TCAR_QROWS), dim3(256), 0, STREAM, dq_raw, sumexp, dA_neg, a_ic, ct_tab, item, content,
                                                             mwdhm, label, d_a_ic, d_a_pt, dTq,
                                                             static_cast<__nv_bfloat16*>(qs_bf16), B);
     return LAUNCH_RC();
@@ -1049,7 +1063,7 @@ extern "C" int tcar_small_table_grads(const int32_t* idx, const int32_t* ctx, co
                                       float* g_dur, float* part, int B, int T, void* stream) {
     (void)part;      // scratch of the former two-pass version; kept in the signature, no longer touched
     if (B < 1 || T < 1 || T > TCAR_MAXT) return TCAR_ERR_ARG;
-    table_grads_kernel<<<TCAR_MAXT + NB + 11, TGD_THREADS, 0, STREAM>>>(
+    launch_pdl(table_grads_kernel, dim3(TCAR_MAXT + NB + 11), dim3(TGD_THREADS), 0, STREAM, 
         idx, ctx, dXi, dP, dD, dCT, dTq, a_pt, pos, month, day, week, hour, minute, dur, g_pos, g_month, g_day, g_week,
         g_hour, g_minute, g_dur, B, T);
     return LAUNCH_RC();
@@ -1061,16 +1075,16 @@ extern "C" int tcar_scatter_add_rows(const int32_t* seq, const int32_t* label, c
                                      float* slot_sq, int hash_size, int B, int T, int Nn, void* stream) {
     const int entries = B * T + B + B * Nn;
     if (hash_size < 2 * entries || (hash_size & (hash_size - 1))) return TCAR_ERR_ARG;
-    scatter_count_kernel<<<(entries + 255) / 256, 256, 0, STREAM>>>(seq, label, neg, hash_keys, hash_cnt, entry_slot,
+    launch_pdl(scatter_count_kernel, dim3((entries + 255) / 256), dim3(256), 0, STREAM, seq, label, neg, hash_keys, hash_cnt, entry_slot,
                                                                     hash_size - 1, B, T, Nn);
     int rc = LAUNCH_RC();
     if (rc) return rc;
-    scatter_accum_kernel<<<(entries + 7) / 8, 256, 0, STREAM>>>(
+    launch_pdl(scatter_accum_kernel, dim3((entries + 7) / 8), dim3(256), 0, STREAM, 
         seq, label, neg, dXi, a_ic, coef, item, g_item, hash_cnt, entry_slot,
         reinterpret_cast<unsigned long long*>(hash_acc), slot_sq, B, T, Nn);
     rc = LAUNCH_RC();
     if (rc) return rc;
-    scatter_apply_kernel<<<(hash_size + 255) / 256, 256, 0, STREAM>>>(hash_keys, hash_cnt, hash_acc, g_item, slot_sq,
+    launch_pdl(scatter_apply_kernel, dim3((hash_size + 255) / 256), dim3(256), 0, STREAM, hash_keys, hash_cnt, hash_acc, g_item, slot_sq,
                                                                   hash_size);
     return LAUNCH_RC();
 }

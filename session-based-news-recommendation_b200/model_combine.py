@@ -430,18 +430,19 @@ class Seq2SeqAttNN:
             ps.prep_weights()
             self._fused_norm = False
             return
-        nv.counted_call("tcar_sqnorm_segments", 1, p(ps.theta_g), p(ps.seg_off), p(ps.sqnorm_small), len(SMALL))
         if self.world == 1 and getattr(self, "_fused_norm", False):
-            # ||g_item||^2 from the per-CTA sums of the dense gradient GEMM + the per-row corrections of the scatter:
-            # no extra pass over the 364 MB gradient
-            nv.counted_call("tcar_sqnorm_combine", 1, p(self.sq_partial), nv.lib().tcar_score_bwd_i_ctas(ps.n_pad),
-                            p(self.slot_sq), self.hash_size, p(ps.sqnorm_item))
+            # every clip norm of the step + the step counter in one launch.  ||g_item||^2 comes from the per-CTA sums
+            # of the dense gradient GEMM + the per-row corrections of the scatter: no pass over the 364 MB gradient
+            nv.counted_call("tcar_update_norms", 1, p(ps.theta_g), p(ps.seg_off), p(ps.sqnorm_small), len(SMALL),
+                            p(self.sq_partial), nv.lib().tcar_score_bwd_i_ctas(ps.n_pad), p(self.slot_sq),
+                            self.hash_size, p(ps.sqnorm_item), p(ps.norm_partial), p(ps.norm_ticket), p(ps.step))
         else:
             # data parallel: the clip norm is the norm of the all-reduced gradient
+            nv.counted_call("tcar_sqnorm_segments", 1, p(ps.theta_g), p(ps.seg_off), p(ps.sqnorm_small), len(SMALL))
             nv.counted_call("tcar_sqnorm_big", 2, p(ps.item_g), p(ps.norm_partial), p(ps.sqnorm_item),
                             ps.item_g.numel())
+            ps.step.add_(1)
         self._fused_norm = False
-        ps.step.add_(1)
         self.global_step += 1
         nv.counted_call("tcar_adam_small", 1, p(ps.theta), p(ps.theta_m), p(ps.theta_v), p(ps.theta_g), p(ps.seg_off),
                         p(ps.sqnorm_small), len(SMALL), p(ps.step), self.lr, self.max_grad_f)

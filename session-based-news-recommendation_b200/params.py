@@ -89,6 +89,7 @@ class ParamStore:
         self.sqnorm_small = torch.zeros(len(SMALL), nv.NORM_SPLIT, device=dev)
         self.sqnorm_item = torch.zeros(1, device=dev)
         self.norm_partial = torch.zeros(1184, device=dev)
+        self.norm_ticket = torch.zeros(1, device=dev, dtype=torch.int32)
         self.step = torch.zeros(1, device=dev, dtype=torch.int32)
         # per-row "already updated in step t" marks of tcar_adam_item_rows (cleared whenever `step` is set from outside)
         self.row_flags = torch.zeros(self.rows_alloc, device=dev, dtype=torch.int32)
