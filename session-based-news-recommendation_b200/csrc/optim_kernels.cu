@@ -428,7 +428,7 @@ extern "C" int tcar_adam_item(float* item, float* m, float* v, const float* g, c
                               const int32_t* row_flags, int ctas_per_sm, void* stream) {
     if (row0 < 0 || nrows < 1 || ctas_per_sm < 0 || ctas_per_sm > 1024) return TCAR_ERR_ARG;
     const long long n4 = (long long)nrows * (HP / 4);
-    const int grid = 148 * (ctas_per_sm ? ctas_per_sm : 16);
+    const int grid = 148 * (ctas_per_sm ? ctas_per_sm : 64);
     launch_pdl(adam_item_kernel, dim3(grid), dim3(256), 0, STREAM, reinterpret_cast<float4*>(item), reinterpret_cast<float4*>(m),
                                                reinterpret_cast<float4*>(v), reinterpret_cast<const float4*>(g),
                                                sqnorm, step, lr, max_grad, static_cast<__nv_bfloat16*>(iext_bf16), n4,
