@@ -328,7 +328,9 @@ def run_b200(a):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local),
+                                timeout=datetime.timedelta(seconds=180))
     N, B, Nn, K, W = a.items, a.batch, a.neg_num, a.steps, a.warmup
     Ts = session_lengths(a)
     T = 20                     # worst-case length, used for the per-kernel pass and the `t20` line
@@ -446,20 +448,29 @@ def run_b200(a):
     if world > 1:
         lo, hi = model.shard_bounds(world)[rank]
         shard = (lo, hi, model.iext_shard(lo, hi))
+    # eval_step(bt, next_bt=...): the test loop's one-batch look-ahead (Seq2SeqAttNN.test)
+    look = not a.no_lookahead
+    enxt = (lambda i: edev[(i + 1) % nbatch]) if look else (lambda i: None)
     for i in range(W):
-        model.eval_step(edev[i % nbatch], shard=shard)
+        model.eval_step(edev[i % nbatch], shard=shard, next_bt=enxt(i))
+    model.sync_updates()
     barrier()
     e0.record()
-    for i in range(K):
-        model.eval_step(edev[i % nbatch], shard=shard)
+    for i in range(W, W + K):
+        model.eval_step(edev[i % nbatch], shard=shard, next_bt=enxt(i))
+    model.sync_updates()
     e1.record()
     barrier()
     eval_ms = max_over_ranks(e0.elapsed_time(e1))
     e0.record()
+    bt = model.to_device(ehost[0], B, Ts[0], 0)
     for i in range(K):
-        bt = model.to_device(ehost[i % nbatch], B, Ts[i % nbatch], 0)
-        top, ngt, ce = model.eval_step(bt, shard=shard)
+        j = (i + 1) % nbatch
+        nb = model.to_device(ehost[j], B, Ts[j], 0)              # H2D of the next batch, then this batch's step + D2H
+        top, ngt, ce = model.eval_step(bt, shard=shard, next_bt=nb if look else None)
         top.cpu(); ngt.cpu(); ce.cpu()
+        bt = nb
+    model.sync_updates()
     e1.record()
     barrier()
     eval_e2e_ms = max_over_ranks(e0.elapsed_time(e1))
@@ -484,7 +495,10 @@ def run_b200(a):
         import random as pyrandom
         from tcar_b200.model_combine import prefetch_packed
         from tcar_b200.sampler import Sampler
-        ld, sd, td, idict, impr = synth.make_sessions(N, a.loop_sessions, seed=2020 + rank)
+        # data parallel: every rank draws the SAME batches (same seeds, as main.py does) and keeps its slice of the
+        # sessions (parallel.shard_packed) -- all ranks therefore run the same number of steps / collectives
+        from tcar_b200 import parallel
+        ld, sd, td, idict, impr = synth.make_sessions(N, a.loop_sessions * world, seed=2020)
         pyrandom.seed(2020)
         np.random.seed(2020)
         t_h0 = time.perf_counter()
@@ -496,12 +510,20 @@ def run_b200(a):
         barrier()
         t_w0 = time.perf_counter()
         e0.record()
-        staged = (model.stage_to_device(*x) for x in prefetch_packed(smp))
+        def staged_batches():
+            for packed, Bb, Tb, Nb in prefetch_packed(smp):
+                if world > 1:
+                    packed, Bl, Tb, Nb = parallel.shard_packed(packed, Bb, Tb, Nb, rank, world)
+                else:
+                    Bl = Bb
+                yield Bb, model.stage_to_device(packed, Bl, Tb, Nb)
+
+        staged = staged_batches()
         cur = next(staged, None)
         while cur is not None:
             nx = next(staged, None)
-            loss_dev = model.train_step(cur, nx if pipe else None)
-            nsess += cur.B
+            loss_dev = model.train_step(cur[1], nx[1] if (pipe and nx is not None) else None)
+            nsess += cur[0]                              # sessions of the GLOBAL batch
             nb += 1
             cur = nx
         model.sync_updates()
@@ -511,8 +533,8 @@ def run_b200(a):
         loop_ms = max_over_ranks(e0.elapsed_time(e1))
         train_loop = {"note": "Sampler.next_packed (host thread) -> pinned ring -> H2D -> train_step over one epoch of "
                               "an in-memory synthetic split; length-bucketed batches, tail batches < 512 included",
-                      "value": world * nsess / (loop_ms * 1e-3), "unit": "sessions/s", "batches": nb,
-                      "sessions_per_rank": nsess, "ms_per_batch": loop_ms / nb,
+                      "value": nsess / (loop_ms * 1e-3), "unit": "sessions/s", "batches": nb,
+                      "sessions": nsess, "ms_per_batch": loop_ms / nb,
                       "wall_s": time.perf_counter() - t_w0, "columnar_cache_build_s": t_cache}
 
     kernels = {}

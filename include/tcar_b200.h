@@ -227,7 +227,9 @@ int tcar_sqnorm_big(const float* x, float* partial, float* sqnorm, long long n, 
  * a = per-CTA sums of squares written by tcar_score_bwd_i, b = slot_sq of tcar_scatter_add_rows. */
 int tcar_sqnorm_combine(const float* a, int na, const float* b, int nb, float* out, void* stream);
 /* tcar_sqnorm_segments + tcar_sqnorm_combine + `step[0] += 1` in ONE launch (the single-GPU train step): item_part
- * [TCAR_NORM_SPLIT] floats and ticket [1] int32 (zero before the first use, left at zero) are scratch. */
+ * [TCAR_NORM_SPLIT] floats and ticket [1] int32 (zero before the first use, left at zero) are scratch.  The two halves
+ * can also be launched separately (they are independent): sqnorm_item == NULL -> small tensors (+ step) only;
+ * nseg == 0 -> item norm only (step must be NULL). */
 int tcar_update_norms(const float* flat, const int32_t* seg_off, float* sqnorm_small, int nseg, const float* a, int na,
                       const float* b, int nb, float* sqnorm_item, float* item_part, int32_t* ticket, int32_t* step,
                       void* stream);

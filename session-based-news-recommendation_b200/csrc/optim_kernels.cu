@@ -133,7 +133,7 @@ update_norms_kernel(const float* __restrict__ flat, const int32_t* __restrict__ 
     for (int k = 0; k < 16; ++k) t += red[k];
     if (s < nseg) {
         out_small[s * kSplit + j] = t;
-        if (s == 0 && j == 0) step[0] += 1;
+        if (s == 0 && j == 0 && step) step[0] += 1;
         return;
     }
     item_part[j] = t;
@@ -386,8 +386,11 @@ extern "C" int tcar_sqnorm_segments(const float* flat, const int32_t* seg_off, f
 extern "C" int tcar_update_norms(const float* flat, const int32_t* seg_off, float* sqnorm_small, int nseg,
                                  const float* a, int na, const float* b, int nb, float* sqnorm_item,
                                  float* item_part, int32_t* ticket, int32_t* step, void* stream) {
-    if (nseg < 1 || na < 0 || nb < 0 || (nb & 3) || !sqnorm_item || !item_part || !ticket || !step) return TCAR_ERR_ARG;
-    launch_pdl(update_norms_kernel, dim3(kSplit, nseg + 1), dim3(512), 0, STREAM, flat, seg_off, sqnorm_small, nseg, a, na,
+    // sqnorm_item == NULL: small tensors only; nseg == 0: item norm only; step == NULL: no counter increment
+    if (nseg < 0 || na < 0 || nb < 0 || (nb & 3) || (nseg == 0 && !sqnorm_item) || (sqnorm_item && (!item_part || !ticket)) ||
+        (step && nseg == 0))
+        return TCAR_ERR_ARG;
+    launch_pdl(update_norms_kernel, dim3(kSplit, nseg + (sqnorm_item ? 1 : 0)), dim3(512), 0, STREAM, flat, seg_off, sqnorm_small, nseg, a, na,
                reinterpret_cast<const float4*>(b), nb / 4, sqnorm_item, item_part, ticket, step);
     return (int)cudaGetLastError();
 }

@@ -128,6 +128,11 @@ class Seq2SeqAttNN:
         # retire): the next batch's session forward
         self._side = torch.cuda.Stream(device=dev)
         self._ahead = torch.cuda.Stream(device=dev, priority=-1)
+        # `_aux`: independent branches of the backward / update (query-path gradients, small-tensor Adam) that run
+        # beside the main chain; joined by events, results do not depend on the interleaving (disjoint buffers)
+        self._aux = torch.cuda.Stream(device=dev)
+        self.branch_streams = os.environ.get("TCAR_BRANCH_STREAMS", "1") != "0"
+        self._la_events = None
         self._update_done = None           # event recorded on `_side` after the pending item update
         self._ahead_done = None            # event recorded on `_ahead` after the prefetched session forward
         self._prefetched = None            # the Batch whose session forward has already been launched
@@ -154,6 +159,7 @@ class Seq2SeqAttNN:
         self.a_ic, self.a_pt = f(Bm, XW), f(Bm, PW)
         self.d_a_ic, self.d_a_pt, self.dA_neg = f(Bm, XW), f(Bm, PW), f(Bm, XW)
         self.Tq, self.dTq = f(Bm, NB), f(Bm, NB)
+        self.a_ic_eval, self.Tq_eval = f(Bm, XW), f(Bm, NB)      # eval look-ahead: parked copies for the re-scoring
         self.c_ref, self.sumexp, self.ce = f(Bm), f(Bm), f(Bm)
         self.negloss, self.loss, self.coef = f(Bm), f(Bm), f(Bm)
         self.Q = torch.zeros(QROWS, KEXT, device=dev, dtype=torch.bfloat16)
@@ -310,8 +316,9 @@ class Seq2SeqAttNN:
                         p(self.negloss), p(self.loss), p(self.coef), p(self.dA_neg), B, bt.Nn)
         return self.loss[:B], self.ce[:B]
 
-    def backward(self, bt):
-        """Gradients of sum_b loss_b wrt all 23 tensors (model_combine.py:156) into ps.item_g / ps.theta_g."""
+    def backward(self, bt, scatter=True):
+        """Gradients of sum_b loss_b wrt all 23 tensors (model_combine.py:156) into ps.item_g / ps.theta_g.
+        scatter=False leaves the sparse item rows (clicks, labels, negatives) to a later _scatter_item_grads(bt)."""
         ps, w, g, p, B, T = self.ps, self.ps.w, self.ps.g, nv.ptr, bt.B, bt.T
         M = B * T
         ws = self._score_buffers(ps.n_pad, True)
@@ -342,10 +349,28 @@ class Seq2SeqAttNN:
                         p(self.dXi), p(self.dP), p(self.dq), p(self.de), B, T)
         de = self.de.view(-1)                      # kernel layout: [3][B*T] with the ACTUAL B*T as stride
         dzq = self.dq
-        # one launch: w_r / w_t gradients (S1^T de1, S2^T de_t) and the tanh backward of the query projection
-        nv.col_jobs([(de[:M], self.U1, None, g["w_r"], M, H, HPp, 2, self.col_scratch[0]),
-                     (de[2 * M: 3 * M], self.U2, None, g["w_t"], M, H, HPp, 2, self.col_scratch[1]),
-                     (dzq, self.q, dzq, g["bq2"], B, XW, XW, 0)])
+        main = torch.cuda.current_stream()
+        branch = self._aux if (self.branch_streams and self.world == 1) else main
+        if branch is not main:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            branch.wait_event(ev)
+        with torch.cuda.stream(branch):
+            # ---- branch B (independent of dU1 / dU2's consumers): w_r / w_t gradients (S1^T de1, S2^T de_t), the query
+            # path backward (modules.py:138-139) down to dCT.  ksp == 1 here, so no split scratch is shared with branch A
+            nv.col_jobs([(de[:M], self.U1, None, g["w_r"], M, H, HPp, 2, self.col_scratch[0]),
+                         (de[2 * M: 3 * M], self.U2, None, g["w_t"], M, H, HPp, 2, self.col_scratch[1]),
+                         (dzq, self.q, dzq, g["bq2"], B, XW, XW, 0)])
+            nv.gemm_group([
+                pr([(self.h1, HPp, 1, dzq, None, XW, 1, B)], H, XW, g["Wq2"], XW),
+                pr([(dzq, XW, 0, wh["Wq2"], None, 512, 0, XW)], B, H, self.dh1, HPp)])
+            nv.counted_call("tcar_act_bwd_colsum", 1, p(self.dh1), p(self.h1), p(self.dh1), p(g["bq1"]), B, H, HPp, 1)
+            nv.gemm_group([
+                pr([(self.CT, 2 * TH, 1, self.dh1, None, HPp, 1, B)], 2 * TH, H, g["Wq1"], H),
+                pr([(self.dh1, HPp, 0, wh["Wq1"], None, 256, 0, H)], B, 2 * TH, self.dCT, 2 * TH)])
+            if branch is not main:
+                ev_b = torch.cuda.Event()
+                ev_b.record(branch)
         # every gradient that consumes dU1 / dU2, one launch: four weight gradients (reduction over the B*T clicks
         # split across CTAs) and three data gradients
         msp = max(1, min(16, M // 512)) if old_policy else self._splits_for(M)
@@ -362,21 +387,18 @@ class Seq2SeqAttNN:
             pr([(self.dU1, HPp, 0, wh["W_in1"], None, 256, 0, H)], M, H, self.dXi, HPp, accumulate=True),
             pr([(self.dU1, HPp, 0, wh["W_i"], None, 256, 0, H)], M, TH, self.dD, TH),
             pr([(self.dU2, HPp, 0, wh["W1"], None, 256, 0, H)], M, PW, self.dP, PW, accumulate=True)])
-        # query path backward (modules.py:138-139)
-        self._part_off = 0
-        nv.gemm_group([
-            pr([(self.h1, HPp, 1, dzq, None, XW, 1, B)], H, XW, g["Wq2"], XW, splits=ksp, part=self._part(H, XW, ksp)),
-            pr([(dzq, XW, 0, wh["Wq2"], None, 512, 0, XW)], B, H, self.dh1, HPp)])
-        nv.counted_call("tcar_act_bwd_colsum", 1, p(self.dh1), p(self.h1), p(self.dh1), p(g["bq1"]), B, H, HPp, 1)
-        self._part_off = 0
-        nv.gemm_group([
-            pr([(self.CT, 2 * TH, 1, self.dh1, None, HPp, 1, B)], 2 * TH, H, g["Wq1"], H, splits=ksp,
-               part=self._part(2 * TH, H, ksp)),
-            pr([(self.dh1, HPp, 0, wh["Wq1"], None, 256, 0, H)], B, 2 * TH, self.dCT, 2 * TH)])
+        if branch is not main:
+            main.wait_event(ev_b)              # the table gradients consume dCT
         nv.counted_call("tcar_small_table_grads", 1, p(bt.idx), p(bt.ctx), p(self.dXi), p(self.dP), p(self.dD),
                         p(self.dCT), p(self.dTq), p(self.a_pt), p(w["pos"]), p(w["month"]), p(w["day"]),
                         p(w["week"]), p(w["hour"]), p(w["minute"]), p(w["dur"]), p(g["pos"]), p(g["month"]),
                         p(g["day"]), p(g["week"]), p(g["hour"]), p(g["minute"]), p(g["dur"]), p(self.table_part), B, T)
+        if scatter:
+            self._scatter_item_grads(bt)
+
+    def _scatter_item_grads(self, bt):
+        """Deterministic scatter-add of the sparse item-row gradients into the dense ps.item_g."""
+        ps, p, B, T = self.ps, nv.ptr, bt.B, bt.T
         entries = B * T + B + B * bt.Nn
         self._alloc_scatter(entries)
         nv.counted_call("tcar_scatter_add_rows", 3, p(bt.seq), p(bt.label), p(bt.neg), p(self.dXi), p(self.a_ic),
@@ -420,6 +442,7 @@ class Seq2SeqAttNN:
         With next_bt (single GPU): the item rows next_bt gathers are updated first, then the table-wide item update is
         forked onto the side stream and next_bt's session forward is launched behind it on the caller's stream."""
         ps, p = self.ps, nv.ptr
+        small_done, self._small_done = getattr(self, "_small_done", None), None
         if self._sharded_update():
             nv.counted_call("tcar_sqnorm_segments", 1, p(ps.theta_g), p(ps.seg_off), p(ps.sqnorm_small), len(SMALL))
             ps.step.add_(1)
@@ -430,7 +453,16 @@ class Seq2SeqAttNN:
             ps.prep_weights()
             self._fused_norm = False
             return
-        if self.world == 1 and getattr(self, "_fused_norm", False):
+        if small_done is not None:
+            # the small tensors were updated on the auxiliary stream beside the scatter (train_step): only the item
+            # norm is left -- per-CTA sums of the dense gradient GEMM + per-row corrections of the scatter
+            nv.counted_call("tcar_update_norms", 1, None, None, None, 0, p(self.sq_partial),
+                            nv.lib().tcar_score_bwd_i_ctas(ps.n_pad), p(self.slot_sq), self.hash_size,
+                            p(ps.sqnorm_item), p(ps.norm_partial), p(ps.norm_ticket), None)
+            torch.cuda.current_stream().wait_event(small_done)
+            self._fused_norm = False
+            self.global_step += 1
+        elif self.world == 1 and getattr(self, "_fused_norm", False):
             # every clip norm of the step + the step counter in one launch.  ||g_item||^2 comes from the per-CTA sums
             # of the dense gradient GEMM + the per-row corrections of the scatter: no pass over the 364 MB gradient
             nv.counted_call("tcar_update_norms", 1, p(ps.theta_g), p(ps.seg_off), p(ps.sqnorm_small), len(SMALL),
@@ -442,11 +474,10 @@ class Seq2SeqAttNN:
             nv.counted_call("tcar_sqnorm_big", 2, p(ps.item_g), p(ps.norm_partial), p(ps.sqnorm_item),
                             ps.item_g.numel())
             ps.step.add_(1)
-        self._fused_norm = False
-        self.global_step += 1
-        nv.counted_call("tcar_adam_small", 1, p(ps.theta), p(ps.theta_m), p(ps.theta_v), p(ps.theta_g), p(ps.seg_off),
-                        p(ps.sqnorm_small), len(SMALL), p(ps.step), self.lr, self.max_grad_f)
-        ps.prep_weights()
+        if small_done is None:
+            self._fused_norm = False
+            self.global_step += 1
+            self._update_small()
         item_args = (p(ps.item), p(ps.item_m), p(ps.item_v), p(ps.item_g), p(ps.sqnorm_item), p(ps.step), self.lr,
                      self.max_grad_f, p(ps.iext))
         if next_bt is None or next_bt.B == 0 or self.world != 1 or self.adam_overlap_ctas <= 0:
@@ -454,25 +485,35 @@ class Seq2SeqAttNN:
             return
         nv.counted_call("tcar_adam_item_rows", 1, *item_args, p(next_bt.seq), next_bt.B * next_bt.T, p(next_bt.label),
                         next_bt.B, p(ps.row_flags), ps.N + 1)
+        timed = self._la_events is not None         # tools/lookahead_times.py: how long both branches really take
         main = torch.cuda.current_stream()
-        fork = torch.cuda.Event()
+        fork = torch.cuda.Event(enable_timing=timed)
         fork.record(main)
         self._side.wait_event(fork)
         with torch.cuda.stream(self._side):
             nv.counted_call("tcar_adam_item", 1, *item_args, 0, ps.N + 1, p(ps.row_flags), self.adam_overlap_ctas)
-            done = torch.cuda.Event()
+            done = torch.cuda.Event(enable_timing=timed)
             done.record(self._side)
         self._update_done = done
         if self.ahead_priority:
             self._ahead.wait_event(fork)
             with torch.cuda.stream(self._ahead):
                 self._session_forward(next_bt, prefetch=True)
-                adone = torch.cuda.Event()
+                adone = torch.cuda.Event(enable_timing=timed)
                 adone.record(self._ahead)
             self._ahead_done = adone
+            if timed:
+                self._la_events.append((fork, done, adone))
         else:
             self._session_forward(next_bt, prefetch=True)
         self._prefetched = next_bt
+
+    def _update_small(self):
+        """clip + TF-Adam of the 22 small tensors (their norms and the step counter are ready) + tf32 hi/lo refresh."""
+        ps, p = self.ps, nv.ptr
+        nv.counted_call("tcar_adam_small", 1, p(ps.theta), p(ps.theta_m), p(ps.theta_v), p(ps.theta_g), p(ps.seg_off),
+                        p(ps.sqnorm_small), len(SMALL), p(ps.step), self.lr, self.max_grad_f)
+        ps.prep_weights()
 
     def train_step(self, bt, next_bt=None):
         """One `sess.run([loss, global_step, train_op])` (model_combine.py:231-234). Returns loss [B] (device).
@@ -488,17 +529,54 @@ class Seq2SeqAttNN:
             loss = self.loss[:0]
         else:
             loss, _ = self.forward_train(bt)
-            self.backward(bt)
+            if self.world == 1 and self.branch_streams:
+                # the small-tensor update (norms, step counter, Adam, weight split) needs theta_g only: it runs on the
+                # auxiliary stream beside the scatter-add of the sparse item rows
+                self.backward(bt, scatter=False)
+                ps, p = self.ps, nv.ptr
+                main = torch.cuda.current_stream()
+                ev = torch.cuda.Event()
+                ev.record(main)
+                self._aux.wait_event(ev)
+                with torch.cuda.stream(self._aux):
+                    nv.counted_call("tcar_update_norms", 1, p(ps.theta_g), p(ps.seg_off), p(ps.sqnorm_small), len(SMALL),
+                                    None, 0, None, 0, None, None, None, p(ps.step))
+                    self._update_small()
+                    self._small_done = torch.cuda.Event()
+                    self._small_done.record(self._aux)
+                self._scatter_item_grads(bt)
+            else:
+                self.backward(bt)
         self.allreduce_grads()
         self.apply_gradients(next_bt)
         return loss
 
     # ------------------------------------------------------------------------------------------- evaluation
-    def eval_step(self, bt, shard=None):
+    def _prefetch_forward(self, next_bt):
+        """Launch next_bt's session forward on the high-priority stream behind everything queued so far."""
+        main = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        self._ahead.wait_event(fork)
+        with torch.cuda.stream(self._ahead):
+            self._session_forward(next_bt, prefetch=True)
+            adone = torch.cuda.Event()
+            adone.record(self._ahead)
+        self._ahead_done = adone
+        self._prefetched = next_bt
+
+    def eval_step(self, bt, shard=None, next_bt=None):
         """Scores every candidate, returns (top20 ids [B,20], n_greater [B], cross_loss [B]) on the device.
-        shard = (item_lo, item_hi, iext_shard) restricts the scoring to a catalog shard (multi-GPU eval)."""
+        shard = (item_lo, item_hi, iext_shard) restricts the scoring to a catalog shard (multi-GPU eval).
+        next_bt (optional) = the batch of the following call: its session forward (latency-bound) is launched beside
+        this batch's top-20 selection (latency-bound too); identical results."""
         ps, p, B = self.ps, nv.ptr, bt.B
-        self._session_forward(bt)
+        if self._prefetched is bt:
+            self._prefetched = None
+            self.sync_updates()
+        else:
+            self._session_forward(bt)
+        ahead = next_bt is not None and next_bt.B > 0
         if shard is None:
             lo, n_loc, n_pad, iext = 0, ps.N, ps.n_pad, ps.iext
         else:
@@ -515,10 +593,21 @@ class Seq2SeqAttNN:
             nv.counted_call("tcar_score_fwd", 1, p(self.Q), p(iext), p(self.c_ref), None, p(ws["part"]), p(ws["cmax"]),
                             p(ws["tmax"]), B, n_loc, n_pad, 1, self._cluster_for(B))
             nv.counted_call("tcar_ce_finish", 1, p(ws["part"]), p(self.sumexp), p(self.ce), ws["tiles"], B)
-            nv.counted_call("tcar_eval_topk", 1, p(ws["cmax"]), p(ws["tmax"]), p(self.a_ic), p(self.Tq), p(ps.item),
+            a_ic, Tq = self.a_ic, self.Tq
+            if ahead:
+                # the exact re-scoring below reads this batch's session vectors: park them before next_bt's forward
+                # overwrites the live buffers
+                self.a_ic_eval[:B].copy_(self.a_ic[:B])
+                self.Tq_eval[:B].copy_(self.Tq[:B])
+                a_ic, Tq = self.a_ic_eval, self.Tq_eval
+                self._prefetch_forward(next_bt)
+                ahead = False
+            nv.counted_call("tcar_eval_topk", 1, p(ws["cmax"]), p(ws["tmax"]), p(a_ic), p(Tq), p(ps.item),
                             p(ps.content),
                             p(ps.mwdhm), p(bt.label), p(self.top_ids), p(self.top_scores), p(self.n_greater), B, n_loc,
                             n_pad, lo)
+        if ahead:
+            self._prefetch_forward(next_bt)
         if shard is not None and parallel.is_distributed(self.world):
             def merge(ids, sc):
                 nv.counted_call("tcar_topk_merge", 1, p(ids), p(sc), p(self.top_ids), p(self.top_scores),
@@ -658,17 +747,22 @@ class Seq2SeqAttNN:
         sampler = Sampler(len_dict_test, session_dict_test, session_time_dict_test, batch_size=self.batch_size)
         resultItemDict = {}
         batch = 0
-        for packed, B, T, Nn in prefetch_packed(sampler):
+        shard = None
+        if parallel.is_distributed(self.world):
+            # catalog-sharded evaluation: every rank scores all queries against its own item range
+            lo, hi = self.shard_bounds(self.world)[self.rank]
+            shard = (lo, hi, self.iext_shard(lo, hi))
+        # one batch of look-ahead (as in train): batch i+1 is staged before batch i is evaluated
+        staged = ((packed, B, T, self.stage_to_device(packed, B, T, Nn)) for packed, B, T, Nn in prefetch_packed(sampler))
+        cur = next(staged, None)
+        while cur is not None:
+            nxt = next(staged, None)
+            packed, B, T, bt = cur
+            cur = nxt
             batch += 1
             batch_in = packed[: B * T].reshape(B, T).tolist()
             batch_out = packed[7 * B * T + 2 * B: 7 * B * T + 3 * B].tolist()
-            bt = self.stage_to_device(packed, B, T, Nn)
-            shard = None
-            if parallel.is_distributed(self.world):
-                # catalog-sharded evaluation: every rank scores all queries against its own item range
-                lo, hi = self.shard_bounds(self.world)[self.rank]
-                shard = (lo, hi, self.iext_shard(lo, hi))
-            top, ngt, ce = self.eval_step(bt, shard=shard)
+            top, ngt, ce = self.eval_step(bt, shard=shard, next_bt=nxt[3] if nxt is not None else None)
             top, ngt, ce = top.cpu().numpy(), ngt.cpu().numpy(), ce.cpu().numpy()
             if batch < 3:
                 print("batch_in:", batch_in[0])

@@ -203,6 +203,33 @@ def test_lookahead_mismatched_next_batch_is_recomputed():
         assert torch.equal(a, b)
 
 
+def test_eval_lookahead_is_bit_identical():
+    """eval_step(bt, next_bt=...) -- next batch's session forward launched beside this batch's top-20 selection -- must
+    return exactly what the plain sequence of eval_step(bt) calls returns."""
+    N, B = 30000, 200
+    lens = [4, 1, 9, 2, 20]
+    model, content, mwdhm, _ = build(N, emb_scale=30.0)
+    bts = [batch_for(model, N, B, T, 0, mwdhm, seed=70 + i)[0] for i, T in enumerate(lens)]
+    plain = [[x.clone() for x in model.eval_step(bt)] for bt in bts]
+    ahead = []
+    for i, bt in enumerate(bts):
+        nxt = bts[i + 1] if i + 1 < len(bts) else None
+        ahead.append([x.clone() for x in model.eval_step(bt, next_bt=nxt)])
+    model.sync_updates()
+    torch.cuda.synchronize()
+    for a, b in zip(plain, ahead):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+    # a train step right after a prefetched-but-unused forward must still be correct (prefetch discarded)
+    model.eval_step(bts[0], next_bt=bts[1])
+    tb = batch_for(model, N, B, 3, 20, mwdhm, seed=99)[0]
+    loss = model.train_step(tb).clone()
+    model2, _, _, _ = build(N, emb_scale=30.0)
+    loss2 = model2.train_step(batch_for(model2, N, B, 3, 20, mwdhm, seed=99)[0]).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(loss, loss2)
+
+
 def margin_ok(scores, k=20, rel=2e-5):
     s = np.sort(scores, axis=1)[:, ::-1]
     gaps = np.abs(np.diff(s[:, : k + 1], axis=1)).min(1)
