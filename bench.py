@@ -537,6 +537,32 @@ def run_b200(a):
                       "sessions": nsess, "ms_per_batch": loop_ms / nb,
                       "wall_s": time.perf_counter() - t_w0, "columnar_cache_build_s": t_cache}
 
+        # the same loop with the GPU-resident sampler: bucket rows uploaded, batch assembled and
+        # negatives drawn (Philox) on the device
+        from tcar_b200.device_sampler import DeviceSampler
+        pyrandom.seed(2020)
+        dsm = DeviceSampler(model, ld, sd, td, impr, idict, Nn, batch_size=B, negatives="device", seed=2020,
+                            rank=rank, world=world, verbose=False)
+        nsess2, nb2 = 0, 0
+        barrier()
+        e0.record()
+        cur = dsm.next_device() if dsm.has_next() else None
+        while cur is not None:
+            nx = dsm.next_device() if dsm.has_next() else None
+            loss_dev = model.train_step(cur, nx if pipe else None)
+            nsess2 += cur.B * world
+            nb2 += 1
+            cur = nx
+        model.sync_updates()
+        loss_dev.cpu()
+        e1.record()
+        barrier()
+        dloop_ms = max_over_ranks(e0.elapsed_time(e1))
+        train_loop["device_sampler"] = {"note": "DeviceSampler(negatives='device'): host sends B bucket rows per batch; "
+                                                "gather of the 7 index planes + Philox negatives on the device",
+                                        "value": nsess2 / (dloop_ms * 1e-3), "unit": "sessions/s", "batches": nb2,
+                                        "ms_per_batch": dloop_ms / nb2}
+
     kernels = {}
     traffic = {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")

@@ -85,6 +85,15 @@ int tcar_build_query(const float* a_ic, const float* a_pt, const float* ct_tab, 
                      const float* content, const int32_t* mwdhm, const int32_t* label, float* Tq, void* q_bf16,
                      float* c_ref, int B, void* stream);
 
+/* (0) GPU-resident sampler (sampler.py:52-113): assemble the packed batch [7*B*T idx | 2*B ctx | B label
+ *     | B*Nn neg] on the device from the columnar cache of one session-length bucket (seq [n,T+1], feats [6,n,T],
+ *     ctx [2,n], all int32) and the batch's bucket rows [B].  neg_in != NULL: negatives copied from it (host-drawn,
+ *     the reference's NumPy stream); neg_in == NULL: negative e = (philox4x32_10(key = seed, counter = offset + e/4)
+ *     [e % 4] * item_num) >> 32, uniform in [0, item_num). */
+int tcar_assemble_batch(const int32_t* rows, const int32_t* seq, const int32_t* feats, const int32_t* ctx,
+                        int n_bucket, int B, int T, int Nn, const int32_t* neg_in, int item_num,
+                        unsigned long long seed, unsigned long long offset, int32_t* out, void* stream);
+
 /* (3c) full-catalog scoring S = Q . Iext^T on tcgen05 (model_combine.py:138), never materialising S.
  *   mode 0 (train): E = exp(S - c_ref) in bf16, logically [512, n_pad], stored in blocks of 8 items:
  *                   E[b, n] at element ((n / 8) * 512 + b) * 8 + n % 8 (coalesced epilogue stores; the backward

@@ -144,6 +144,61 @@ gather_fwd_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ c
     }
 }
 
+// ------------------------------------------------------------------------------------------------ (0) batch assembly
+// GPU-resident sampler: the packed batch [7*B*T idx | 2*B ctx | B label | B*Nn neg] that
+// Sampler.next_packed() builds on the host (sampler.py:52-113) is gathered on the device from the columnar cache of
+// one session-length bucket: seq [n, T+1], feats [6, n, T], ctx [2, n]; `rows` [B] = bucket rows of the batch.
+// Negatives are either copied from neg_in (host-drawn: the reference's NumPy stream, bit-exact) or drawn on the device:
+// Philox4x32-10 with key = seed, counter = (offset + element / 4), word element % 4, mapped to [0, item_num) by
+// (x * item_num) >> 32  (restated in oracle/philox_oracle.py).
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+__device__ __forceinline__ uint32_t philox_word(unsigned long long seed, unsigned long long ctr, int word) {
+    uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), 0u, 0u};
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        philox_round(c, k0, k1);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return c[word];
+}
+
+__global__ void __launch_bounds__(256)
+assemble_batch_kernel(const int32_t* __restrict__ rows, const int32_t* __restrict__ seq,
+                      const int32_t* __restrict__ feats, const int32_t* __restrict__ ctx, int n, int B, int T, int Nn,
+                      const int32_t* __restrict__ neg_in, int item_num, unsigned long long seed,
+                      unsigned long long offset, int32_t* __restrict__ out) {
+    PDL_ENTER();
+    const int M = B * T;
+    const int total = 7 * M + 3 * B + B * Nn;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int v;
+        if (i < 7 * M) {
+            const int k = i / M, m = i - k * M, b = m / T, t = m - b * T;
+            const int r = rows[b];
+            v = k == 0 ? seq[(size_t)r * (T + 1) + t] : feats[((size_t)(k - 1) * n + r) * T + t];
+        } else if (i < 7 * M + 2 * B) {
+            const int j = i - 7 * M, k = j / B, b = j - k * B;
+            v = ctx[(size_t)k * n + rows[b]];
+        } else if (i < 7 * M + 3 * B) {
+            const int b = i - 7 * M - 2 * B;
+            v = seq[(size_t)rows[b] * (T + 1) + T] - 1;                     // target, 0-based (sampler.py:72)
+        } else {
+            const int e = i - 7 * M - 3 * B;
+            if (neg_in) v = neg_in[e];
+            else v = (int)(((unsigned long long)philox_word(seed, offset + (unsigned long long)(e >> 2), e & 3) *
+                            (unsigned long long)item_num) >> 32);
+        }
+        out[i] = v;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ (2) pooling fwd
 // one CTA per session.  modules.py:126-142 (count_alpha_m), :94-100 (count_alpha_s), :116-117 / :82-83 (pool).
 // Every row is fetched with 128-bit loads that are all issued before the first use (8 independent loads per lane and
@@ -965,6 +1020,18 @@ extern "C" int tcar_gather_fwd(const int32_t* idx, const int32_t* ctx, const flo
     const int warps = B * T + B;
     launch_pdl(gather_fwd_kernel, dim3((warps + 3) / 4), dim3(128), 0, STREAM, idx, ctx, item, content, pos, month, day, week, hour,
                                                            minute, dur, X, P, D, CT, B, T);
+    return LAUNCH_RC();
+}
+
+extern "C" int tcar_assemble_batch(const int32_t* rows, const int32_t* seq, const int32_t* feats, const int32_t* ctx,
+                                   int n_bucket, int B, int T, int Nn, const int32_t* neg_in, int item_num,
+                                   unsigned long long seed, unsigned long long offset, int32_t* out, void* stream) {
+    if (B < 1 || T < 1 || T > TCAR_MAXT || Nn < 0 || n_bucket < 1 || !rows || !seq || !feats || !ctx || !out ||
+        (Nn > 0 && !neg_in && item_num < 1))
+        return TCAR_ERR_ARG;
+    const int total = 7 * B * T + 3 * B + B * Nn;
+    launch_pdl(assemble_batch_kernel, dim3((total + 255) / 256), dim3(256), 0, STREAM, rows, seq, feats, ctx, n_bucket, B, T,
+               Nn, neg_in, item_num, seed, offset, out);
     return LAUNCH_RC();
 }
 

@@ -79,6 +79,9 @@ def build_parser():
     parser.add_argument("--is_print", default=False, type=bool)
     parser.add_argument("--train", default=True, type=bool)
     parser.add_argument("--modelpath", default="./ckpt/", type=str)
+    # not a reference flag: GPU-resident sampler.  off = host Sampler; host = batches assembled on the
+    # device with the reference's NumPy negatives (identical batches); device = Philox negatives drawn on the device
+    parser.add_argument("--device_sampler", default="off", choices=["off", "host", "device"], type=str)
     parser.add_argument("--inputdata", default="test", type=str)
     parser.add_argument("--threshold_acc", default=0.27, type=float)
     # additions

@@ -700,12 +700,26 @@ class Seq2SeqAttNN:
             self.curEpoch = epoch
             print("Epoch {}".format(epoch))
             c = []
-            sampler = Sampler(len_dict_train, session_dict_train, session_time_dict_train, neighbor_dict, item_dict,
-                              args["neg_num"], batch_size=self.batch_size)
+            mode = args.get("device_sampler") or "off"
+            if mode != "off":
+                # GPU-resident sampler: "host" = negatives from the reference's NumPy stream (batches
+                # identical to the host sampler's), "device" = Philox negatives drawn on the device
+                from .device_sampler import DeviceSampler
+                sampler = DeviceSampler(self, len_dict_train, session_dict_train, session_time_dict_train,
+                                        neighbor_dict, item_dict, args["neg_num"], batch_size=self.batch_size,
+                                        negatives=mode, seed=2020 + epoch, rank=self.rank, world=self.world)
+            else:
+                sampler = Sampler(len_dict_train, session_dict_train, session_time_dict_train, neighbor_dict,
+                                  item_dict, args["neg_num"], batch_size=self.batch_size)
             batch = 0
 
             def staged():
                 nonlocal batch
+                if mode != "off":
+                    while sampler.has_next():
+                        batch += 1
+                        yield sampler.next_device()
+                    return
                 for packed, B, T, Nn in prefetch_packed(sampler):
                     batch += 1
                     if batch < 3 and Nn:
