@@ -39,6 +39,9 @@ def parse():
                     help="clicks per session; 0 = SURVEY 8d mix: one length per batch drawn from P(T) ~ 0.55^T, "
                          "T in [1,20] (Globo-like, prefix-augmented sessions are short); 20 = the reference --maxlen")
     ap.add_argument("--neg_num", type=int, default=20)
+    ap.add_argument("--train_parallel", default=os.environ.get("TCAR_TRAIN_PARALLEL", "dp"), choices=["dp", "catalog"],
+                    help="multi-GPU training layout: dp = data parallel + gradient all-reduce; catalog = softmax "
+                         "sharded over the item catalog (catalog_parallel.py).  Ignored at --gpus 1")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_kernels", action="store_true", help="skip the per-kernel roofline pass")
     ap.add_argument("--no_lookahead", action="store_true",
@@ -221,7 +224,9 @@ def workload_config(a, world):
             "items": a.items, "batch_per_gpu": a.batch, "global_batch": a.batch * world,
             "session_len": a.session_len if a.session_len > 0 else "mix", "mean_session_len": sum(Ts) / len(Ts),
             "neg_num": a.neg_num,
-            "parallelism": f"dp{world}" if world > 1 else "single",
+            "parallelism": (f"catalog{world} (softmax sharded over the item catalog, sessions of all ranks scored by every "
+                            f"rank; catalog_parallel.py)" if getattr(a, "train_parallel", "dp") == "catalog" else
+                            f"dp{world}") if world > 1 else "single",
             "l2": "inputs larger than L2: bf16 candidate matrix %d MB, E %d MB, item table + grad + Adam moments "
                   "4 x %d MB streamed every step (L2 = 126 MB)" % (a.items * 640 * 2 >> 20, a.items * 1024 >> 20,
                                                                   a.items * 1024 >> 20)}
@@ -338,7 +343,8 @@ def run_b200(a):
     np.random.seed(2020)
     margs = dict(publish_time_MWDHM=mwdhm, itemnum=N, category_id=None, item_freq_dict_norm={}, reverse_item=None,
                  content_emb=content, emb_stddev=0.002, stddev=0.05, hidden_size=250, time_hidden_size=64, l2_emb=0.0,
-                 batch_size=B, epoch=1, neg_num=Nn, lr=0.001, max_grad=150, rank=rank, world_size=world)
+                 batch_size=B, epoch=1, neg_num=Nn, lr=0.001, max_grad=150, rank=rank, world_size=world,
+                 train_parallel=a.train_parallel if world > 1 else "dp")
     model = Seq2SeqAttNN(margs)
     peaks = load_peaks()
     nbatch = len(Ts)
@@ -516,7 +522,9 @@ def run_b200(a):
                     packed, Bl, Tb, Nb = parallel.shard_packed(packed, Bb, Tb, Nb, rank, world)
                 else:
                     Bl = Bb
-                yield Bb, model.stage_to_device(packed, Bl, Tb, Nb)
+                sbt = model.stage_to_device(packed, Bl, Tb, Nb)
+                sbt.counts = parallel.catalog_counts(Bb, world)
+                yield Bb, sbt
 
         staged = staged_batches()
         cur = next(staged, None)
@@ -569,6 +577,7 @@ def run_b200(a):
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f)
+    model.sync_item_table()        # catalog-sharded training: every rank holds the whole table again (collective)
     if rank == 0 and not a.no_kernels:
         kernels = kernel_rooflines(torch, nv, model, dev20[0], peaks, traffic)
     cpu_baseline = None

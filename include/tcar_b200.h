@@ -136,6 +136,11 @@ int tcar_score_bwd_finish(const float* dq_raw, const float* sumexp, const float*
 int tcar_score_bwd_i(const void* e_bf16, const void* qs_bf16, float* g_item, float* sq_partial, int n_rows,
                      int n_items, int n_pad, void* stream);
 int tcar_score_bwd_i_ctas(int n_pad);
+/* Same with accumulate != 0: g_item += result.  A catalog-sharded train step scores several groups
+ * of <= 512 sessions (one per rank) against the rank's item range; groups after the first add to the dense gradient.
+ * sq_partial then holds the sums of squares of the ACCUMULATED values written by this call. */
+int tcar_score_bwd_i_acc(const void* e_bf16, const void* qs_bf16, float* g_item, float* sq_partial, int n_rows,
+                         int n_items, int n_pad, int accumulate, void* stream);
 
 /* (5a) gradients of the seven small embedding tables (pos, month, day, week, hour, minute, duration): sums the
  *      gather-side, click-context-side and scoring-side contributions per table row in a fixed order, applies the
@@ -227,6 +232,15 @@ int tcar_scatter_add_rows(const int32_t* seq, const int32_t* label, const int32_
                           int32_t* hash_keys, int32_t* hash_cnt, long long* hash_acc, int32_t* entry_slot,
                           float* slot_sq, int hash_size, int B, int T, int Nn, void* stream);
 
+/* Same, restricted to the table rows [row_lo, row_hi) of one catalog shard: entries whose row lies outside are
+ * ignored (the rank that owns them applies them).  Rows are table rows (1-based item ids: seq as is, label + 1,
+ * neg + 1).  Called once per source rank with that rank's all-gathered (seq, label, neg, dXi, a_ic, coef). */
+int tcar_scatter_add_rows_range(const int32_t* seq, const int32_t* label, const int32_t* neg, const float* dXi,
+                                const float* a_ic, const float* coef, const float* item, float* g_item,
+                                int32_t* hash_keys, int32_t* hash_cnt, long long* hash_acc, int32_t* entry_slot,
+                                float* slot_sq, int hash_size, int B, int T, int Nn, int row_lo, int row_hi,
+                                void* stream);
+
 /* (5c) per-tensor squared L2 norms (for tf.clip_by_norm, model_combine.py:158-160). seg_off [nseg+1], every
  *      segment start 16-byte aligned and zero padded to a multiple of 4 floats.  tcar_sqnorm_segments writes
  *      sqnorm [nseg][TCAR_NORM_SPLIT] partial sums (tcar_adam_small adds them in index order). */
@@ -271,6 +285,23 @@ int tcar_adam_item_rows(float* item, float* m, float* v, const float* g, const f
                         const int32_t* label, int n_label, int32_t* row_flags, int n_rows, void* stream);
 /* item columns of Iext from the fp32 item table (after all-gathering slices updated by other ranks). */
 int tcar_refresh_iext_items(const float* item, void* iext_bf16, int N, void* stream);
+
+/* (7) peer memory of the catalog-sharded train step (single node, NVLink / NVSwitch).  Every
+ *     rank owns the fp32 master copy of a contiguous range of item-table rows; the rows a rank's sessions read are
+ *     loaded directly from the owner's HBM.  The three functions below are the only ones of this library that are
+ *     synchronous host calls without a stream (they wrap cudaIpc*): export a device allocation (any pointer inside a
+ *     cudaMalloc'ed block: `handle` receives the 64-byte IPC handle of the block, `offset` the pointer's offset in
+ *     it), open another rank's export, close it again. */
+#define TCAR_MAX_PEERS 16
+#define TCAR_PEER_HANDLE_BYTES 64
+int tcar_peer_export(const void* ptr, unsigned char* handle, long long* offset);
+int tcar_peer_open(const unsigned char* handle, long long offset, void** ptr);
+int tcar_peer_close(void* ptr, long long offset);
+/* table[row] = peers[owner(row)][row] for row = rows[i] + row_add, i < n, for the rows owned by OTHER ranks (256-float
+ * rows).  peers [G] and row_bounds [G+1] are HOST arrays (rank g owns rows [row_bounds[g], row_bounds[g+1])); rows is
+ * a device array.  The caller orders this after the owners' updates (a collective on the same stream). */
+int tcar_peer_fetch_rows(const int32_t* rows, int n, int row_add, const void* const* peers, const int32_t* row_bounds,
+                         int G, int self, float* table, void* stream);
 
 /* (6) evaluation (model_combine.py:283-306, util.py:8-18): select the 32 best 128-item tiles per query from tilemax,
  *     then the 32 best 8-item chunks among their 512 chunks from chunkmax (exactly the 32 best chunks overall, ties

@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(HERE, "libtcar_b200.so")
 
 H, HP, TH, XW, PW, NBINS, KEXT, QROWS, MAXT, TOPK, CHUNK, NCAND_CHUNKS = 250, 256, 64, 500, 320, 139, 640, 512, 40, 20, 8, 32
 NORM_SPLIT = 8
+MAX_PEERS, PEER_HANDLE_BYTES = 16, 64      # TCAR_MAX_PEERS, TCAR_PEER_HANDLE_BYTES
 BIN_OFF = (0, 13, 45, 53, 78, 139)
 CLUSTER_PAIR = -2      # TCAR_CLUSTER_PAIR: tcar_score_fwd with tcgen05.mma.cta_group::2 CTA pairs
 
@@ -32,6 +33,7 @@ SIGNATURES = {
     "tcar_score_bwd_q": [_P] * 4 + [_I, _I, _P],
     "tcar_score_bwd_finish": [_P] * 13 + [_I, _P],
     "tcar_score_bwd_i": [_P] * 4 + [_I, _I, _I, _P],
+    "tcar_score_bwd_i_acc": [_P] * 4 + [_I, _I, _I, _I, _P],
     "tcar_score_bwd_i_ctas": [_I],
     "tcar_sqnorm_combine": [_P, _I, _P, _I, _P, _P],
     "tcar_small_table_grads": [_P] * 23 + [_I, _I, _P],
@@ -44,6 +46,11 @@ SIGNATURES = {
     "tcar_debug_gemm_trace": [_P],
     "tcar_prep_weights": [_P, _P, _I, _P, _P, _P],
     "tcar_scatter_add_rows": [_P] * 13 + [_I] * 4 + [_P],
+    "tcar_scatter_add_rows_range": [_P] * 13 + [_I] * 6 + [_P],
+    "tcar_peer_export": [_P, _P, _P],
+    "tcar_peer_open": [_P, _LL, _P],
+    "tcar_peer_close": [_P, _LL],
+    "tcar_peer_fetch_rows": [_P, _I, _I, _P, _P, _I, _I, _P, _P],
     "tcar_sqnorm_segments": [_P] * 3 + [_I, _P],
     "tcar_sqnorm_big": [_P] * 3 + [_LL, _P],
     "tcar_update_norms": [_P, _P, _P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P],

@@ -592,6 +592,7 @@ struct BwdIParams {
     int n_items;
     int n_tiles;     // ceil(Npad / 128)
     int nkb;         // ceil(B / 64)
+    int accumulate;  // != 0: g_item += result (second and later session groups of a catalog-sharded step)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -714,6 +715,13 @@ score_bwd_i_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_const
                         if (c + 1 >= TCAR_H) o.y = 0u;
                         if (c + 2 >= TCAR_H) o.z = 0u;
                         if (c + 3 >= TCAR_H) o.w = 0u;
+                        if (p.accumulate) {
+                            const float4 old = reinterpret_cast<const float4*>(dst + ch * 32)[g];
+                            o.x = __float_as_uint(old.x + __uint_as_float(o.x));
+                            o.y = __float_as_uint(old.y + __uint_as_float(o.y));
+                            o.z = __float_as_uint(old.z + __uint_as_float(o.z));
+                            o.w = __float_as_uint(old.w + __uint_as_float(o.w));
+                        }
                         reinterpret_cast<uint4*>(dst + ch * 32)[g] = o;
                         const float f0 = __uint_as_float(o.x), f1 = __uint_as_float(o.y);
                         const float f2 = __uint_as_float(o.z), f3 = __uint_as_float(o.w);
@@ -961,6 +969,11 @@ extern "C" int tcar_score_bwd_i_ctas(int n_pad) { return bwd_i_grid(n_pad); }
 
 extern "C" int tcar_score_bwd_i(const void* e_bf16, const void* qs_bf16, float* g_item, float* sq_partial, int n_rows,
                                 int n_items, int n_pad, void* stream_) {
+    return tcar_score_bwd_i_acc(e_bf16, qs_bf16, g_item, sq_partial, n_rows, n_items, n_pad, 0, stream_);
+}
+
+extern "C" int tcar_score_bwd_i_acc(const void* e_bf16, const void* qs_bf16, float* g_item, float* sq_partial,
+                                    int n_rows, int n_items, int n_pad, int accumulate, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (n_rows < 1 || n_rows > QROWS || n_pad % 256 != 0) return TCAR_ERR_ARG;
     CUtensorMap me, mq;
@@ -974,6 +987,7 @@ extern "C" int tcar_score_bwd_i(const void* e_bf16, const void* qs_bf16, float* 
     p.n_items = n_items;
     p.n_tiles = n_pad / BM;
     p.nkb = (n_rows + BK - 1) / BK;
+    p.accumulate = accumulate;
     cudaError_t e = cudaFuncSetAttribute(score_bwd_i_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I_SMEM);
     if (e != cudaSuccess) return (int)e;
     const int grid = bwd_i_grid(n_pad);

@@ -864,12 +864,15 @@ __device__ __forceinline__ int entry_row(int e, int M, int B, const int32_t* __r
 __global__ void __launch_bounds__(256)
 scatter_count_kernel(const int32_t* __restrict__ seq, const int32_t* __restrict__ label,
                      const int32_t* __restrict__ neg, int32_t* __restrict__ keys, int32_t* __restrict__ cnt,
-                     int32_t* __restrict__ entry_slot, int mask, int B, int T, int Nn) {
+                     int32_t* __restrict__ entry_slot, int mask, int B, int T, int Nn, int row_lo, int row_hi) {
     PDL_ENTER();
     const int M = B * T;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= M + B + B * Nn) return;
-    const int slot = hash_slot(keys, entry_row(e, M, B, seq, label, neg), mask);
+    const int row = entry_row(e, M, B, seq, label, neg);
+    // rows outside [row_lo, row_hi) belong to another catalog shard (tcar_scatter_add_rows_range): no slot
+    if (row < row_lo || row >= row_hi) { entry_slot[e] = -1; return; }
+    const int slot = hash_slot(keys, row, mask);
     atomicAdd(&cnt[slot], 1);
     entry_slot[e] = slot;
 }
@@ -887,6 +890,8 @@ scatter_accum_kernel(const int32_t* __restrict__ seq, const int32_t* __restrict_
     const int M = B * T;
     const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (e >= M + B + B * Nn) return;
+    const int slot = entry_slot[e];
+    if (slot < 0) return;                    // row of another catalog shard
     const int row = entry_row(e, M, B, seq, label, neg);
     float val[8];
     bool jac_on = false;
@@ -932,7 +937,6 @@ scatter_accum_kernel(const int32_t* __restrict__ seq, const int32_t* __restrict_
             val[j] = c < H ? scale * a_ic[(size_t)b * XW + c] : 0.f;
         }
     }
-    const int slot = entry_slot[e];
     if (cnt[slot] == 1) {
         float4* dst = reinterpret_cast<float4*>(g_item + (size_t)row * HP);
         float4 o0 = dst[lane], o1 = dst[32 + lane];
@@ -1136,14 +1140,15 @@ extern "C" int tcar_small_table_grads(const int32_t* idx, const int32_t* ctx, co
     return LAUNCH_RC();
 }
 
-extern "C" int tcar_scatter_add_rows(const int32_t* seq, const int32_t* label, const int32_t* neg, const float* dXi,
-                                     const float* a_ic, const float* coef, const float* item, float* g_item,
-                                     int32_t* hash_keys, int32_t* hash_cnt, long long* hash_acc, int32_t* entry_slot,
-                                     float* slot_sq, int hash_size, int B, int T, int Nn, void* stream) {
+extern "C" int tcar_scatter_add_rows_range(const int32_t* seq, const int32_t* label, const int32_t* neg,
+                                           const float* dXi, const float* a_ic, const float* coef, const float* item,
+                                           float* g_item, int32_t* hash_keys, int32_t* hash_cnt, long long* hash_acc,
+                                           int32_t* entry_slot, float* slot_sq, int hash_size, int B, int T, int Nn,
+                                           int row_lo, int row_hi, void* stream) {
     const int entries = B * T + B + B * Nn;
-    if (hash_size < 2 * entries || (hash_size & (hash_size - 1))) return TCAR_ERR_ARG;
+    if (B < 1 || T < 1 || Nn < 0 || hash_size < 2 * entries || (hash_size & (hash_size - 1))) return TCAR_ERR_ARG;
     launch_pdl(scatter_count_kernel, dim3((entries + 255) / 256), dim3(256), 0, STREAM, seq, label, neg, hash_keys, hash_cnt, entry_slot,
-                                                                    hash_size - 1, B, T, Nn);
+                                                                    hash_size - 1, B, T, Nn, row_lo, row_hi);
     int rc = LAUNCH_RC();
     if (rc) return rc;
     launch_pdl(scatter_accum_kernel, dim3((entries + 7) / 8), dim3(256), 0, STREAM, 
@@ -1154,4 +1159,12 @@ extern "C" int tcar_scatter_add_rows(const int32_t* seq, const int32_t* label, c
     launch_pdl(scatter_apply_kernel, dim3((hash_size + 255) / 256), dim3(256), 0, STREAM, hash_keys, hash_cnt, hash_acc, g_item, slot_sq,
                                                                   hash_size);
     return LAUNCH_RC();
+}
+
+extern "C" int tcar_scatter_add_rows(const int32_t* seq, const int32_t* label, const int32_t* neg, const float* dXi,
+                                     const float* a_ic, const float* coef, const float* item, float* g_item,
+                                     int32_t* hash_keys, int32_t* hash_cnt, long long* hash_acc, int32_t* entry_slot,
+                                     float* slot_sq, int hash_size, int B, int T, int Nn, void* stream) {
+    return tcar_scatter_add_rows_range(seq, label, neg, dXi, a_ic, coef, item, g_item, hash_keys, hash_cnt, hash_acc,
+                                       entry_slot, slot_sq, hash_size, B, T, Nn, 0, 0x7fffffff, stream);
 }

@@ -81,8 +81,14 @@ class DeviceSampler(Sampler):
         offset = self._counter
         if self.negatives == "device" and Nn:
             self._counter += (B_glob * Nn + 3) // 4
+        counts = None
+        if self.world > 1:
+            from .parallel import catalog_counts
+            counts = catalog_counts(B_glob, self.world)
         if B == 0:
-            return Batch(out[:0], 0, T, Nn)
+            bt = Batch(out[:0], 0, T, Nn)
+            bt.counts = counts
+            return bt
         host = model.stage_to_device(small, 0, 0, 0).buf          # pinned ring -> device, one copy
         rows_d = host[:B]
         neg_d = host[B:] if (Nn and self.negatives == "host") else None
@@ -92,4 +98,6 @@ class DeviceSampler(Sampler):
         nv.counted_call("tcar_assemble_batch", 1, p(rows_d), p(dev.seq[T]), p(dev.feats[T]), p(dev.ctx[T]),
                         int(dev.seq[T].shape[0]), B, T, Nn, p(neg_d), int(getattr(self, "item_num", 0) or 0),
                         self.seed, offset + first_neg // 4, p(out))
-        return Batch(out[:total], B, T, Nn)
+        bt = Batch(out[:total], B, T, Nn)
+        bt.counts = counts
+        return bt

@@ -37,6 +37,17 @@ def load_datas(args):
 def main(args):
     is_train, model_path, input_data, modelname = args.train, args.modelpath, args.inputdata, args.model
     train_data, test_data, neighbor, args, item_dict = load_datas(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        # launched with torchrun: one process per GPU (NCCL over NVLink); every rank loads the same data and draws the
+        # same batches (same seeds above), see parallel.py
+        import torch
+        import torch.distributed as dist
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        args["rank"], args["world_size"] = int(os.environ["RANK"]), world
     pkg = __package__ or "tcar_b200"
     module = importlib.import_module(pkg + "." + modelname)            # main.py:65-66 `__import__(args.model)`
     model = getattr(module, "Seq2SeqAttNN")(args)
@@ -82,6 +93,9 @@ def build_parser():
     # not a reference flag: GPU-resident sampler.  off = host Sampler; host = batches assembled on the
     # device with the reference's NumPy negatives (identical batches); device = Philox negatives drawn on the device
     parser.add_argument("--device_sampler", default="off", choices=["off", "host", "device"], type=str)
+    # not a reference flag: multi-GPU training layout under torchrun.  dp = data parallel + gradient all-reduce,
+    # catalog = softmax sharded over the item catalog (catalog_parallel.py)
+    parser.add_argument("--train_parallel", default="dp", choices=["dp", "catalog"], type=str)
     parser.add_argument("--inputdata", default="test", type=str)
     parser.add_argument("--threshold_acc", default=0.27, type=float)
     # additions

@@ -17,6 +17,7 @@ import torch
 
 from . import _native as nv
 from . import parallel
+from .catalog_parallel import CatalogShardedTraining
 from .params import ParamStore, SMALL
 from .sampler import Sampler, pack_batch
 
@@ -29,6 +30,7 @@ class Batch:
 
     def __init__(self, buf, B, T, Nn):
         self.buf, self.B, self.T, self.Nn = buf, B, T, Nn
+        self.counts = None       # sessions per rank of the global batch this slice was cut from (catalog_parallel.py)
         M = B * T
         self.idx = buf[: 7 * M]
         self.ctx = buf[7 * M: 7 * M + 2 * B]
@@ -84,7 +86,7 @@ class PinnedRing:
         return view, self.events[i]
 
 
-class Seq2SeqAttNN:
+class Seq2SeqAttNN(CatalogShardedTraining):
     def __init__(self, args):
         if not torch.cuda.is_available():
             raise RuntimeError("tcar_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
@@ -138,6 +140,15 @@ class Seq2SeqAttNN:
         self._prefetched = None            # the Batch whose session forward has already been launched
         self.adam_overlap_ctas = int(os.environ.get("TCAR_ADAM_OVERLAP_CTAS", "64"))
         self.ahead_priority = os.environ.get("TCAR_AHEAD_PRIORITY", "1") != "0"
+        # multi-GPU training layout: "dp" = data parallel + gradient all-reduce (north_star), "catalog" = the softmax
+        # sharded over the item catalog (catalog_parallel.py)
+        self.train_parallel = "dp"
+        self._item_table_synced = True
+        mode = args.get("train_parallel") or "dp"
+        if mode not in ("dp", "catalog"):
+            raise ValueError("train_parallel must be 'dp' or 'catalog'")
+        if mode == "catalog":
+            self.enable_catalog_training(int(args.get("catalog_virtual_shards") or 1))
 
     # ------------------------------------------------------------------------------------------- workspaces
     def _alloc(self):
@@ -319,8 +330,7 @@ class Seq2SeqAttNN:
     def backward(self, bt, scatter=True):
         """Gradients of sum_b loss_b wrt all 23 tensors (model_combine.py:156) into ps.item_g / ps.theta_g.
         scatter=False leaves the sparse item rows (clicks, labels, negatives) to a later _scatter_item_grads(bt)."""
-        ps, w, g, p, B, T = self.ps, self.ps.w, self.ps.g, nv.ptr, bt.B, bt.T
-        M = B * T
+        ps, p, B = self.ps, nv.ptr, bt.B
         ws = self._score_buffers(ps.n_pad, True)
         nv.counted_call("tcar_score_bwd_q", 2, p(ws["E"]), p(ps.iext), p(ws["qpart"]), p(self.dq_raw), B, ps.n_pad)
         nv.counted_call("tcar_score_bwd_finish", 1, p(self.dq_raw), p(self.sumexp), p(self.dA_neg), p(self.a_ic),
@@ -328,6 +338,15 @@ class Seq2SeqAttNN:
                         p(self.d_a_pt), p(self.dTq), p(self.Qs), B)
         nv.counted_call("tcar_score_bwd_i", 1, p(ws["E"]), p(self.Qs), p(ps.item_g), p(self.sq_partial), B, ps.N,
                         ps.n_pad)
+        self._session_backward(bt)
+        if scatter:
+            self._scatter_item_grads(bt)
+
+    def _session_backward(self, bt):
+        """Everything below the scoring layer: from d a_ic / d a_pt / dTq (tcar_score_bwd_finish) to the gradients of
+        the 22 small tensors (ps.theta_g) and dXi, the gradient wrt the gathered item rows."""
+        ps, w, g, p, B, T = self.ps, self.ps.w, self.ps.g, nv.ptr, bt.B, bt.T
+        M = B * T
         # ---- session-side backward: weight / data gradients on the tensor cores in single-pass TF32 (gradients carry
         # a 2e-2 norm-wise tolerance, dominated by the bf16 scoring GEMMs); operands are consumed in place, K-major or
         # MN-major as they lie, so no transposes are materialised.
@@ -393,8 +412,6 @@ class Seq2SeqAttNN:
                         p(self.dCT), p(self.dTq), p(self.a_pt), p(w["pos"]), p(w["month"]), p(w["day"]),
                         p(w["week"]), p(w["hour"]), p(w["minute"]), p(w["dur"]), p(g["pos"]), p(g["month"]),
                         p(g["day"]), p(g["week"]), p(g["hour"]), p(g["minute"]), p(g["dur"]), p(self.table_part), B, T)
-        if scatter:
-            self._scatter_item_grads(bt)
 
     def _scatter_item_grads(self, bt):
         """Deterministic scatter-add of the sparse item-row gradients into the dense ps.item_g."""
@@ -515,11 +532,14 @@ class Seq2SeqAttNN:
                         p(ps.sqnorm_small), len(SMALL), p(ps.step), self.lr, self.max_grad_f)
         ps.prep_weights()
 
-    def train_step(self, bt, next_bt=None):
+    def train_step(self, bt, next_bt=None, counts=None):
         """One `sess.run([loss, global_step, train_op])` (model_combine.py:231-234). Returns loss [B] (device).
         next_bt (optional) is the batch of the following call: its session forward is overlapped with this step's
         table-wide Adam pass.  Results are bit-identical with and without it; after a call with next_bt, parameters
-        must be read through this object's methods (or after sync_updates())."""
+        must be read through this object's methods (or after sync_updates()).
+        counts (catalog-sharded training only): sessions of every rank in this step, see train_step_catalog."""
+        if self.train_parallel == "catalog":
+            return self.train_step_catalog(bt, counts if counts is not None else getattr(bt, "counts", None))
         if bt.B == 0:
             # data-parallel tail batch with fewer sessions than ranks: contribute a zero gradient to the all-reduce
             self.sync_updates()
@@ -571,6 +591,8 @@ class Seq2SeqAttNN:
         next_bt (optional) = the batch of the following call: its session forward (latency-bound) is launched beside
         this batch's top-20 selection (latency-bound too); identical results."""
         ps, p, B = self.ps, nv.ptr, bt.B
+        if not self._item_table_synced:
+            self.sync_item_table()         # after catalog-sharded training every rank holds only its own rows
         if self._prefetched is bt:
             self._prefetched = None
             self.sync_updates()
@@ -724,10 +746,14 @@ class Seq2SeqAttNN:
                     batch += 1
                     if batch < 3 and Nn:
                         print(packed[7 * B * T + 3 * B: 7 * B * T + 3 * B + min(Nn, 10)].tolist())
+                    counts = None
                     if self.world > 1:
                         # every rank draws the same batch (same seeds, main.py:9-12) and keeps its slice of the sessions
+                        counts = parallel.catalog_counts(B, self.world)
                         packed, B, T, Nn = parallel.shard_packed(packed, B, T, Nn, self.rank, self.world)
-                    yield self.stage_to_device(packed, B, T, Nn)
+                    bt_ = self.stage_to_device(packed, B, T, Nn)
+                    bt_.counts = counts
+                    yield bt_
 
             # one batch of look-ahead: batch i+1 is on the device before step i is launched, so that its session
             # forward can overlap step i's table-wide Adam pass (train_step(bt, next_bt))
@@ -756,6 +782,7 @@ class Seq2SeqAttNN:
     def test(self, sess, test_data, args):
         """model_combine.py:254-315."""
         print("Measuring...")
+        self.sync_item_table()
         (len_dict_test, session_dict_test, session_time_dict_test) = test_data
         mrr20, recall20, ndcg20, ild20, unexp20, c_loss = [], [], [], [], [], []
         sampler = Sampler(len_dict_test, session_dict_test, session_time_dict_test, batch_size=self.batch_size)

@@ -5,6 +5,9 @@ partitionings below are the ones BASELINE.json's north_star prescribes:
   training    data parallel over the sessions of a length bucket, ONE all-reduce(SUM) of the gradients per step.
               SUM, not mean: the reference differentiates the batch SUM of the [B,1] loss (model_combine.py:156), and
               the per-tensor clip_by_norm (:158-160) must see the gradient of the whole global batch.
+  training    (catalog_parallel.py) alternatively the CATALOG is split for training too: every rank
+              owns the parameters, moments and gradient of a contiguous item range and scores all sessions against it;
+              only session-sized tensors are exchanged.
   evaluation  the item catalog is split into contiguous id ranges; every rank scores all B queries against its own
               range, then all-gather of the per-rank top-20 (score, id) lists + merge by (score desc, id asc), and
               all-reduce(SUM) of the rank counts #(S > S[label]) and of the softmax partial sums.
@@ -61,6 +64,22 @@ def shard_bounds(N, n_pad, G, align=256):
     tiles = n_pad // align
     per = (tiles + G - 1) // G
     return [(min(g * per * align, N), min((g + 1) * per * align, N)) for g in range(G)]
+
+
+def catalog_row_bounds(bounds, N):
+    """Item-TABLE row ranges of a catalog-sharded train step (catalog_parallel.py) from the 0-based item-id ranges of
+    shard_bounds(): table row = item id + 1, and the first shard also owns the pad row 0.  Returns [G + 1] row
+    boundaries: shard g owns rows [rb[g], rb[g + 1]); together they cover the N + 1 rows exactly once."""
+    rb = [0] + [hi + 1 for _, hi in bounds]
+    if rb[-1] != N + 1 or any(b < a for a, b in zip(rb, rb[1:])):
+        raise ValueError("shard bounds must be contiguous, ascending and end at N")
+    return rb
+
+
+def catalog_counts(B, world):
+    """Sessions per rank when one global batch of B sessions is split with shard_sessions (every rank computes the
+    same list without communicating)."""
+    return [hi - lo for lo, hi in (shard_sessions(B, g, world) for g in range(world))]
 
 
 def gather_merge_topk(top_ids, top_scores, n_greater, sumexp, world, merge):

@@ -55,6 +55,7 @@ def save_model(model, args, saver=None):
     os.makedirs(args["modelpath"], exist_ok=True)
     path = os.path.join(args["modelpath"], "model.ckpt-" + suf)
     model.sync_updates()
+    model.sync_item_table()                  # catalog-sharded training: collect every owner's rows first
     torch.save(model.ps.state_dict(), path)
     return path
 

@@ -321,3 +321,105 @@ def test_softmax_input_debug_fetch_and_reference_loops():
         assert not model.error_during_train
         m = model.last_metrics
         assert 0 <= m["recall"] <= 1 and np.isfinite(m["loss"]) and m["coverage"] > 0
+
+
+# ------------------------------------------------------------------------------------------- catalog-sharded training
+def _build_catalog(N, V, emb_scale=1.0, Nn=20, max_grad=150):
+    from tcar_b200 import synth
+    from tcar_b200.model_combine import Seq2SeqAttNN
+    content, mwdhm, category = synth.make_catalog(N, seed=3)
+    np.random.seed(2020)
+    args = dict(publish_time_MWDHM=mwdhm, itemnum=N, category_id=None, item_freq_dict_norm={}, reverse_item=None,
+                content_emb=content, emb_stddev=0.002 * emb_scale, stddev=0.05, hidden_size=250, time_hidden_size=64,
+                l2_emb=0.0, batch_size=512, epoch=1, neg_num=Nn, lr=0.001, max_grad=max_grad,
+                train_parallel="catalog", catalog_virtual_shards=V)
+    return Seq2SeqAttNN(args), mwdhm
+
+
+@pytest.mark.parametrize("N,V,B,T,scale,max_grad", [(3000, 1, 130, 3, 1.0, 150), (3000, 3, 512, 5, 100.0, 150),
+                                                    (1500, 4, 77, 20, 30.0, 0.05), (700, 8, 5, 1, 1.0, 150)])
+def test_catalog_sharded_train_step_equals_plain_step(N, V, B, T, scale, max_grad):
+    """SURVEY 8e row 2 / 8f-3 on one GPU: the process owns V catalog shards and walks them with the shard offsets the
+    multi-GPU step uses (score_fwd / bwd_q / bwd_i on row slices, ranged scatter, ranged Adam).  Must equal the plain
+    step: same loss (different summation order of the softmax partial sums only), gradients, parameters after Adam
+    (two steps, so that the second one reads what the first one's ranged Adam wrote)."""
+    Nn = 20
+    plain, content, mwdhm, _ = build(N, emb_scale=scale, Nn=Nn, max_grad=max_grad)
+    cat, _ = _build_catalog(N, V, emb_scale=scale, Nn=Nn, max_grad=max_grad)
+    assert len(cat._cat_shards) == V
+    for step in range(2):
+        bt_p, _ = batch_for(plain, N, B, T, Nn, mwdhm, seed=40 + step)
+        bt_c, _ = batch_for(cat, N, B, T, Nn, mwdhm, seed=40 + step)
+        lp = plain.train_step(bt_p).clone()
+        lc = cat.train_step(bt_c).clone()
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(lc.cpu().numpy(), lp.cpu().numpy(), rtol=1e-5, atol=1e-5)
+        assert relerr(cat.ps.theta_g, plain.ps.theta_g) < 1e-5
+        assert relerr(cat.ps.item_g, plain.ps.item_g) < 1e-5
+        assert (cat.ps.item_g[:, 250:] == 0).all() and (cat.ps.item_g[0] == 0).all()
+        assert (cat.hash_keys == -1).all() and (cat.hash_acc == 0).all() and (cat.hash_cnt == 0).all()
+        assert relerr(cat.ps.theta, plain.ps.theta) < 1e-6
+        assert relerr(cat.ps.item, plain.ps.item) < 1e-6
+        d = (cat.ps.iext.float() - plain.ps.iext.float()).abs()
+        assert float((d > 0).float().mean()) < 1e-3, "refreshed bf16 scoring operand differs in more than a few ulps"
+    assert int(cat.ps.step.item()) == 2 and cat.global_step == 2
+    # evaluation after catalog-sharded training (sync_item_table is a no-op on one rank besides the iext rebuild)
+    eb_p, _ = batch_for(plain, N, min(B, 64), T, 0, mwdhm, seed=99)
+    eb_c, _ = batch_for(cat, N, min(B, 64), T, 0, mwdhm, seed=99)
+    tp, np_, _ = plain.eval_step(eb_p)
+    tc, nc_, _ = cat.eval_step(eb_c)
+    torch.cuda.synchronize()
+    assert cat._item_table_synced
+    agree = float((tp == tc).float().mean())
+    assert agree > 0.98, f"top-20 lists after two steps agree on {agree:.3f} of the slots"
+
+
+def test_scatter_add_rows_range_partitions_the_unranged_call():
+    """Two ranged calls over complementary row ranges == one unranged call, bit for bit (every row is handled by
+    exactly one of them, with the same arithmetic)."""
+    from tcar_b200 import _native as nv
+    N, B, T, Nn = 900, 200, 6, 20
+    model, content, mwdhm, _ = build(N, emb_scale=100.0)
+    bt, _ = batch_for(model, N, B, T, Nn, mwdhm, seed=5)
+    model.forward_train(bt)
+    model.backward(bt, scatter=False)
+    base = model.ps.item_g.clone()
+    p = nv.ptr
+
+    def scatter(lo, hi):
+        nv.call("tcar_scatter_add_rows_range", p(bt.seq), p(bt.label), p(bt.neg), p(model.dXi), p(model.a_ic),
+                p(model.coef), p(model.ps.item), p(model.ps.item_g), p(model.hash_keys), p(model.hash_cnt),
+                p(model.hash_acc), p(model.entry_slot), None, model.hash_size, B, T, Nn, lo, hi)
+
+    scatter(0, N + 1)
+    full = model.ps.item_g.clone()
+    model.ps.item_g.copy_(base)
+    model._scatter_item_grads(bt)
+    assert torch.equal(model.ps.item_g, full), "range covering the table == unranged entry point"
+    model.ps.item_g.copy_(base)
+    cut = 257
+    scatter(0, cut)
+    assert torch.equal(model.ps.item_g[cut:], base[cut:]), "rows outside the range must not be touched"
+    scatter(cut, N + 1)
+    torch.cuda.synchronize()
+    assert torch.equal(model.ps.item_g, full)
+    assert (model.hash_keys == -1).all() and (model.hash_acc == 0).all() and (model.hash_cnt == 0).all()
+
+
+def test_score_bwd_i_accumulate():
+    """tcar_score_bwd_i_acc(accumulate=1) adds the second session group's dense gradient to the first one's."""
+    from tcar_b200 import _native as nv
+    N, B, T = 1100, 300, 2
+    model, content, mwdhm, _ = build(N, emb_scale=1.0)
+    bt, _ = batch_for(model, N, B, T, 20, mwdhm, seed=6)
+    model.forward_train(bt)
+    model.backward(bt, scatter=False)
+    ps, p = model.ps, nv.ptr
+    ws = model._score_buffers(ps.n_pad, True)
+    once = ps.item_g.clone()
+    nv.call("tcar_score_bwd_i_acc", p(ws["E"]), p(model.Qs), p(ps.item_g), p(model.sq_partial), B, ps.N, ps.n_pad, 1)
+    torch.cuda.synchronize()
+    assert torch.equal(ps.item_g, once + once)
+    ctas = nv_lib().tcar_score_bwd_i_ctas(ps.n_pad)
+    want = float((ps.item_g.double() ** 2).sum())
+    assert abs(float(model.sq_partial[:ctas].double().sum()) - want) <= 1e-4 * want + 1e-12

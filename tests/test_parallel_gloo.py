@@ -128,3 +128,78 @@ def test_catalog_sharded_eval_equals_unsharded():
         ref_rank = np.array([int((row[l] < row).sum()) for row, l in zip(S, label)])
         np.testing.assert_array_equal(ngt, ref_rank)
         np.testing.assert_allclose(sumexp, np.exp(S.astype(np.float64)).sum(1), rtol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------- catalog-sharded training
+@pytest.mark.parametrize("N,G", [(364047, 8), (364047, 2), (700, 8), (300, 4), (256, 2)])
+def test_catalog_row_bounds_cover_table(N, G):
+    """Table-row ownership of the catalog-sharded train step: every one of the N + 1 rows has exactly one owner, the
+    pad row 0 goes with the first shard, and a shard's rows are its item ids + 1."""
+    from tcar_b200 import parallel
+    n_pad = (N + 255) // 256 * 256
+    b = parallel.shard_bounds(N, n_pad, G)
+    rb = parallel.catalog_row_bounds(b, N)
+    assert len(rb) == G + 1 and rb[0] == 0 and rb[-1] == N + 1
+    assert all(x <= y for x, y in zip(rb, rb[1:]))
+    for g, (lo, hi) in enumerate(b):
+        if hi > lo:
+            assert rb[g + 1] == hi + 1 and (rb[g] == lo + 1 or (g == 0 and rb[g] == 0))
+    with pytest.raises(ValueError):
+        parallel.catalog_row_bounds([(0, 10), (10, 20)], 30)
+
+
+@pytest.mark.parametrize("B,world", [(512, 8), (7, 4), (1, 2), (0, 2)])
+def test_catalog_counts_match_shard_packed(B, world):
+    from tcar_b200 import parallel
+    c = parallel.catalog_counts(B, world)
+    assert sum(c) == B and len(c) == world
+    assert c == [hi - lo for lo, hi in (parallel.shard_sessions(B, r, world) for r in range(world))]
+
+
+def _catalog_softmax_worker(rank, world):
+    """The exchange pattern of catalog_parallel.train_step_catalog with CPU tensors (fp64): all-gather the sessions'
+    query rows, score against the OWN item range, all-reduce the softmax partial sums, sum the dQ partials over ranks
+    and keep the own sessions' rows, all-gather Qs, local dItems.  Compared with autograd on the full problem."""
+    from tcar_b200 import parallel
+    torch.manual_seed(0)
+    N, K, Bg = 700, 24, 5
+    n_pad = (N + 255) // 256 * 256
+    items = torch.randn(N, K, dtype=torch.float64)
+    Qall = torch.randn(world * Bg, K, dtype=torch.float64)
+    labels = torch.randint(0, N, (world * Bg,))
+    # full problem (every rank computes the same reference)
+    Qr, Ir = Qall.clone().requires_grad_(True), items.clone().requires_grad_(True)
+    S = Qr @ Ir.t()
+    ce = torch.logsumexp(S, 1) - S.gather(1, labels[:, None]).squeeze(1)
+    ce.sum().backward()
+    # sharded
+    lo, hi = parallel.shard_bounds(N, n_pad, world)[rank]
+    mine = slice(rank * Bg, (rank + 1) * Bg)
+    q_loc = Qall[mine].contiguous()
+    c_loc = (q_loc * items[labels[mine]]).sum(1)                       # label score: the fetched label rows
+    q_all = torch.empty(world * Bg, K, dtype=torch.float64)
+    c_all = torch.empty(world * Bg, dtype=torch.float64)
+    dist.all_gather_into_tensor(q_all, q_loc)
+    dist.all_gather_into_tensor(c_all, c_loc)
+    E = torch.exp(q_all @ items[lo:hi].t() - c_all[:, None])           # [R*Bg, n_loc]
+    sumexp = E.sum(1)
+    dist.all_reduce(sumexp)
+    dq = E @ items[lo:hi]                                              # partial over the own items
+    dist.all_reduce(dq)                                                # (reduce-scatter in the product)
+    dq_loc = dq[mine] / sumexp[mine, None] - items[labels[mine]]
+    qs_all = torch.empty(world * Bg, K, dtype=torch.float64)
+    dist.all_gather_into_tensor(qs_all, (q_loc / sumexp[mine, None]).contiguous())
+    d_items = E.t() @ qs_all                                           # dense rows of the own range, complete
+    # sparse label rows of EVERY rank's sessions that fall into the own range (ranged scatter)
+    for b in range(world * Bg):
+        n = int(labels[b])
+        if lo <= n < hi:
+            d_items[n - lo] -= q_all[b]
+    ok_ce = torch.allclose(torch.log(sumexp[mine]), ce[mine].detach(), rtol=1e-10, atol=1e-10)
+    ok_dq = torch.allclose(dq_loc, Qr.grad[mine], rtol=1e-9, atol=1e-11)
+    ok_di = torch.allclose(d_items, Ir.grad[lo:hi], rtol=1e-9, atol=1e-11)
+    return bool(ok_ce and ok_dq and ok_di)
+
+
+def test_catalog_sharded_softmax_exchange_is_exact():
+    assert all(_spawn(_catalog_softmax_worker, world=2))

@@ -19,10 +19,10 @@ from tcar_b200 import parallel, synth  # noqa: E402
 from tcar_b200.model_combine import Seq2SeqAttNN  # noqa: E402
 
 
-def build(N, rank, world):
+def build(N, rank, world, **extra):
     content, mwdhm, _ = synth.make_catalog(N, seed=3)
     np.random.seed(2020)
-    args = dict(publish_time_MWDHM=mwdhm, itemnum=N, category_id=None, item_freq_dict_norm={}, reverse_item=None,
+    args = dict(extra, publish_time_MWDHM=mwdhm, itemnum=N, category_id=None, item_freq_dict_norm={}, reverse_item=None,
                 content_emb=content, emb_stddev=0.04, stddev=0.05, hidden_size=250, time_hidden_size=64, l2_emb=0.0,
                 batch_size=512, epoch=1, neg_num=20, lr=0.001, max_grad=150, rank=rank, world_size=world)
     return Seq2SeqAttNN(args), mwdhm
@@ -75,7 +75,41 @@ def main():
     hit = n1 < 20
     res["rank_equal"] = bool(torch.equal(hit, ng < 20) and torch.equal(n1[hit], ng[hit]))
     res["ce_maxabs"] = float((ce1 - ceg).abs().max())
-    ok = (res["loss_maxabs"] < 1e-5 and res["g_item_rel"] < 1e-5 and res["g_theta_rel"] < 1e-5
+    # ---- catalog-sharded train steps (catalog_parallel.py) vs the same global batches on one GPU.  Two steps: the
+    # second one gathers rows that OTHER ranks updated in the first (peer loads), and B2 < world exercises empty slices
+    cat, _ = build(N, rank, world, train_parallel="catalog")
+    ref, _ = build(N, 0, 1)
+    rel = lambda a, b: float((a - b).double().norm() / (b.double().norm() + 1e-30))
+    cres = {"loss_maxabs": 0.0, "g_item_rel": 0.0, "g_theta_rel": 0.0}
+    rb = cat._cat_row_bounds
+    own = slice(rb[rank], rb[rank + 1])
+    for step, (Bs, Ts) in enumerate([(B, T), (world - 1, 3), (512, 2)]):
+        pk = synth.make_index_batch(N, Bs, Ts, Nn, mwdhm, seed=50 + step)
+        pl, Bl, _, _ = parallel.shard_packed(pk, Bs, Ts, Nn, rank, world)
+        cbt = cat.to_device(torch.from_numpy(pl).pin_memory(), Bl, Ts, Nn)
+        lc = cat.train_step(cbt, counts=parallel.catalog_counts(Bs, world)).clone()
+        lr_ = ref.train_step(ref.to_device(torch.from_numpy(pk).pin_memory(), Bs, Ts, Nn)).clone()
+        torch.cuda.synchronize()
+        lo, hi = parallel.shard_sessions(Bs, rank, world)
+        if hi > lo:
+            cres["loss_maxabs"] = max(cres["loss_maxabs"], float((lc - lr_[lo:hi]).abs().max()))
+        cres["g_item_rel"] = max(cres["g_item_rel"], rel(cat.ps.item_g_full[own], ref.ps.item_g_full[own]))
+        cres["g_theta_rel"] = max(cres["g_theta_rel"], rel(cat.ps.theta_g, ref.ps.theta_g))
+    cres["own_rows_rel"] = rel(cat.ps.item_full[own], ref.ps.item_full[own])
+    cat.sync_item_table()
+    torch.cuda.synchronize()
+    cres["item_after_rel"] = rel(cat.ps.item, ref.ps.item)
+    cres["theta_after_rel"] = rel(cat.ps.theta, ref.ps.theta)
+    cres["moments_rel"] = max(rel(cat.ps.item_m, ref.ps.item_m), rel(cat.ps.item_v, ref.ps.item_v))
+    cdiff = (cat.ps.iext.float() - ref.ps.iext.float()).abs()
+    cres["iext_mismatch_frac"] = float((cdiff > 0).float().mean())
+    cres["ok"] = bool(cres["loss_maxabs"] < 1e-4 and cres["g_item_rel"] < 1e-5 and cres["g_theta_rel"] < 1e-5
+                      and cres["own_rows_rel"] < 1e-6 and cres["item_after_rel"] < 1e-6
+                      and cres["theta_after_rel"] < 1e-6 and cres["moments_rel"] < 1e-5
+                      and cres["iext_mismatch_frac"] < 1e-3)
+    res["catalog"] = cres
+    cat.close_peers()
+    ok = (cres["ok"] and res["loss_maxabs"] < 1e-5 and res["g_item_rel"] < 1e-5 and res["g_theta_rel"] < 1e-5
           and res["item_after_rel"] < 1e-6 and res["iext_equal"] and res["top20_equal"] and res["rank_equal"] and res["ce_maxabs"] < 1e-4)
     res["ok"] = ok
     print(f"rank {rank}/{world}: " + json.dumps(res), flush=True)
