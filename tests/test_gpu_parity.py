@@ -358,8 +358,10 @@ def test_catalog_sharded_train_step_equals_plain_step(N, V, B, T, scale, max_gra
         assert relerr(cat.ps.item_g, plain.ps.item_g) < 1e-5
         assert (cat.ps.item_g[:, 250:] == 0).all() and (cat.ps.item_g[0] == 0).all()
         assert (cat.hash_keys == -1).all() and (cat.hash_acc == 0).all() and (cat.hash_cnt == 0).all()
-        assert relerr(cat.ps.theta, plain.ps.theta) < 1e-6
-        assert relerr(cat.ps.item, plain.ps.item) < 1e-6
+        # Adam normalises every element by its own |g|: last-bit differences of tiny gradients move those elements by a
+        # visible fraction of lr, hence a looser bound than on the gradients themselves
+        assert relerr(cat.ps.theta, plain.ps.theta) < 2e-5
+        assert relerr(cat.ps.item, plain.ps.item) < 2e-5
         d = (cat.ps.iext.float() - plain.ps.iext.float()).abs()
         assert float((d > 0).float().mean()) < 1e-3, "refreshed bf16 scoring operand differs in more than a few ulps"
     assert int(cat.ps.step.item()) == 2 and cat.global_step == 2

@@ -103,9 +103,11 @@ def main():
     cres["moments_rel"] = max(rel(cat.ps.item_m, ref.ps.item_m), rel(cat.ps.item_v, ref.ps.item_v))
     cdiff = (cat.ps.iext.float() - ref.ps.iext.float()).abs()
     cres["iext_mismatch_frac"] = float((cdiff > 0).float().mean())
-    cres["ok"] = bool(cres["loss_maxabs"] < 1e-4 and cres["g_item_rel"] < 1e-5 and cres["g_theta_rel"] < 1e-5
-                      and cres["own_rows_rel"] < 1e-6 and cres["item_after_rel"] < 1e-6
-                      and cres["theta_after_rel"] < 1e-6 and cres["moments_rel"] < 1e-5
+    # three consecutive steps: from the second one on the two runs start from parameters that already differ in the
+    # last bits (Adam normalises every element by its own |g|), so the bounds are looser than for a single step
+    cres["ok"] = bool(cres["loss_maxabs"] < 1e-4 and cres["g_item_rel"] < 5e-5 and cres["g_theta_rel"] < 5e-5
+                      and cres["own_rows_rel"] < 5e-6 and cres["item_after_rel"] < 5e-6
+                      and cres["theta_after_rel"] < 5e-6 and cres["moments_rel"] < 5e-5
                       and cres["iext_mismatch_frac"] < 1e-3)
     res["catalog"] = cres
     cat.close_peers()
