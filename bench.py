@@ -39,9 +39,11 @@ def parse():
                     help="clicks per session; 0 = SURVEY 8d mix: one length per batch drawn from P(T) ~ 0.55^T, "
                          "T in [1,20] (Globo-like, prefix-augmented sessions are short); 20 = the reference --maxlen")
     ap.add_argument("--neg_num", type=int, default=20)
-    ap.add_argument("--train_parallel", default=os.environ.get("TCAR_TRAIN_PARALLEL", "dp"), choices=["dp", "catalog"],
-                    help="multi-GPU training layout: dp = data parallel + gradient all-reduce; catalog = softmax "
-                         "sharded over the item catalog (catalog_parallel.py).  Ignored at --gpus 1")
+    ap.add_argument("--train_parallel", default=os.environ.get("TCAR_TRAIN_PARALLEL", "catalog"),
+                    choices=["dp", "catalog"],
+                    help="multi-GPU training layout: catalog (default) = softmax sharded over the item catalog, only "
+                         "session-sized exchanges (catalog_parallel.py); dp = data parallel + all-reduce of the dense "
+                         "364 MB item gradient.  Ignored at --gpus 1")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_kernels", action="store_true", help="skip the per-kernel roofline pass")
     ap.add_argument("--no_lookahead", action="store_true",

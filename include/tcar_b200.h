@@ -112,6 +112,8 @@ int tcar_score_fwd_tiles(int n_pad);
 /* (4a) softmax cross-entropy from the partial sums (model_combine.py:145): sumexp[b] = sum_tiles part,
  *      ce[b] = log(sumexp[b]) (because c_ref is the label score). Fixed summation order. */
 int tcar_ce_finish(const float* rowsum_part, float* sumexp, float* ce, int n_tiles, int B, void* stream);
+/* The same fixed-order sum only, stored with a stride: out[b * out_stride] = sum_tiles part[tile][b]. */
+int tcar_rowsum_finish(const float* rowsum_part, float* out, int out_stride, int n_tiles, int B, void* stream);
 
 /* (4b) negative-feedback loss (model_combine.py:142-143,147): neg[b] = -log(1 - sigmoid(sum_j I_ic[neg_bj].a_ic[b])
  *      + 1e-24); loss[b] = ce[b] + 0.01 neg[b]; coef[b] = 0.01 d neg/d z; dA_neg[b,500] = coef[b] sum_j I_ic[neg_bj]. */
@@ -297,11 +299,41 @@ int tcar_refresh_iext_items(const float* item, void* iext_bf16, int N, void* str
 int tcar_peer_export(const void* ptr, unsigned char* handle, long long* offset);
 int tcar_peer_open(const unsigned char* handle, long long offset, void** ptr);
 int tcar_peer_close(void* ptr, long long offset);
-/* table[row] = peers[owner(row)][row] for row = rows[i] + row_add, i < n, for the rows owned by OTHER ranks (256-float
- * rows).  peers [G] and row_bounds [G+1] are HOST arrays (rank g owns rows [row_bounds[g], row_bounds[g+1])); rows is
- * a device array.  The caller orders this after the owners' updates (a collective on the same stream). */
-int tcar_peer_fetch_rows(const int32_t* rows, int n, int row_add, const void* const* peers, const int32_t* row_bounds,
-                         int G, int self, float* table, void* stream);
+/* table[row] = peers[owner(row)][row] for the table rows one batch reads -- seq[0..B*T) as is, label[0..B) + 1,
+ * neg[0..B*Nn) + 1 -- that are owned by OTHER ranks (256-float rows).  peers [G] and row_bounds [G+1] are HOST arrays
+ * (rank g owns rows [row_bounds[g], row_bounds[g+1])); seq / label / neg are device arrays.  The caller orders this
+ * after the owners' updates (a collective on the same stream). */
+int tcar_peer_fetch_rows(const int32_t* seq, const int32_t* label, const int32_t* neg, int B, int T, int Nn,
+                         const void* const* peers, const int32_t* row_bounds, int G, int self, float* table,
+                         void* stream);
+
+/* (8) session groups of the catalog-sharded step.  Every rank scores the sessions of ALL ranks against its own item
+ *     range: group g = rank g's sessions, n_rows[g] <= 512 of them (HOST array; 0 = group absent), operands of
+ *     consecutive groups `*_stride` ELEMENTS apart.  Each function is the loop over groups around the single-group entry
+ *     point of the same name (one host call per phase).
+ *     fwd:   mode 0 of tcar_score_fwd with cluster as given.
+ *     bwd_q: tcar_score_bwd_q per group into dq + g * dq_stride; with rowsum_part != NULL the group's softmax partial
+ *            sums (fixed-order sum over n_tiles, as tcar_ce_finish) are stored in the zero pad column 639 of its dQ
+ *            rows, so that one reduce-scatter delivers dQ and sum exp to the sessions' rank.
+ *     bwd_i: the first present group overwrites g_item, later ones accumulate (tcar_score_bwd_i_acc); sq_partial
+ *            (nullable) is filled by the last group = sums of squares of the complete dense gradient.
+ *     scatter: tcar_scatter_add_rows_range per group; ids = packed batches [7*B*T idx | 2*B ctx | B label | B*Nn neg],
+ *            payload = [a_ic 512x500 | coef 512 | dXi B*T x 256] floats; slot_sq (nullable): [groups][hash_size]. */
+int tcar_score_fwd_groups(const void* q_bf16, long long q_stride, const float* c_ref, long long c_stride,
+                          const void* iext_bf16, void* e_out, long long e_stride, float* rowsum_part,
+                          long long part_stride, const int* n_rows, int groups, int n_items, int n_pad, int cluster,
+                          void* stream);
+int tcar_score_bwd_q_groups(const void* e_bf16, long long e_stride, const void* iext_bf16, float* part, float* dq,
+                            long long dq_stride, const float* rowsum_part, long long part_stride, int n_tiles,
+                            const int* n_rows, int groups, int n_pad, void* stream);
+int tcar_score_bwd_i_groups(const void* e_bf16, long long e_stride, const void* qs_bf16, long long qs_stride,
+                            float* g_item, float* sq_partial, const int* n_rows, int groups, int n_items, int n_pad,
+                            void* stream);
+int tcar_scatter_add_rows_groups(const int32_t* ids, long long ids_stride, const float* payload,
+                                 long long payload_stride, const float* item, float* g_item, int32_t* hash_keys,
+                                 int32_t* hash_cnt, long long* hash_acc, int32_t* entry_slot, float* slot_sq,
+                                 int hash_size, const int* n_rows, int groups, int T, int Nn, int row_lo, int row_hi,
+                                 void* stream);
 
 /* (6) evaluation (model_combine.py:283-306, util.py:8-18): select the 32 best 128-item tiles per query from tilemax,
  *     then the 32 best 8-item chunks among their 512 chunks from chunkmax (exactly the 32 best chunks overall, ties

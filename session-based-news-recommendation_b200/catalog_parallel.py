@@ -76,19 +76,26 @@ class CatalogShardedTraining:
         self._sumexp_all = torch.zeros(R, QROWS, device=dev)
         self._dq_all = torch.zeros(R, QROWS, KEXT, device=dev)
         self._qs_all = torch.zeros(R, QROWS, HP, device=dev, dtype=torch.bfloat16) if R > 1 else self.Qs.view(1, QROWS, HP)
-        self._se_tmp, self._ce_tmp, self._dq_tmp = torch.zeros(QROWS, device=dev), torch.zeros(QROWS, device=dev), None
-        if len(self._cat_shards) > 1:
-            self._dq_tmp = torch.zeros(QROWS, KEXT, device=dev)
+        self._dq_tmp = torch.zeros(R, QROWS, KEXT, device=dev) if len(self._cat_shards) > 1 else None
         self._sq_tmp = torch.zeros(1, device=dev)
-        # tail of the small-gradient all-reduce: [theta_g | squared norm of the owned item-gradient rows]
+        # one all-reduce carries [theta_g | squared norm of the owned item-gradient rows]: the small-tensor gradients
+        # now live at the front of that buffer (the kernels write them through ps.g / ps.theta_g as before)
         self._red = torch.zeros(ps.flat_size + 4, device=dev)
+        ps.theta_g = self._red[: ps.flat_size]
+        ps.g = {n: ps._view(ps.theta_g, i) for i, (n, _) in enumerate(SMALL)}
+        self._sq_slot = self._red[ps.flat_size: ps.flat_size + 1]
+        self._cat_trace = None          # tools/catalog_probe.py: list collecting (phase name, CUDA event)
         for sh in self._cat_shards:
             tiles = nv.lib().tcar_score_fwd_tiles(sh["n_pad"])
             sh["tiles"] = tiles
-            sh["E"] = [torch.zeros(QROWS, sh["n_pad"], device=dev, dtype=torch.bfloat16) for _ in range(R)]
-            sh["part"] = [torch.zeros(tiles, QROWS, device=dev) for _ in range(R)]
+            # one E / partial-sum block per session group, a fixed stride apart (tcar_score_*_groups)
+            sh["E"] = torch.zeros(R, QROWS * sh["n_pad"], device=dev, dtype=torch.bfloat16)
+            sh["part"] = torch.zeros(R, tiles * QROWS, device=dev)
             splits = max(nv.lib().tcar_score_bwd_q_splits(b, sh["n_pad"]) for b in (1, 129, 257, 385))
             sh["qpart"] = torch.zeros(splits, QROWS, KEXT, device=dev)
+            sh["ctas"] = nv.lib().tcar_score_bwd_i_ctas(sh["n_pad"])
+            sh["sqp"] = torch.zeros(sh["ctas"], device=dev)
+        self._slot_sq_g = None
         # peer pointers of the fp32 item table (single node, CUDA IPC): exported once, opened once
         self._peer_ptrs = (C.c_void_p * nv.MAX_PEERS)()
         self._peer_ptrs[self.rank if self._cat_dist else 0] = ps.item_full.data_ptr()
@@ -130,15 +137,13 @@ class CatalogShardedTraining:
     # ------------------------------------------------------------------------------------------- the step
     def _fetch_rows(self, bt):
         """Item rows this rank's sessions read (clicks, labels, negatives) from their owners' HBM."""
-        p, st = nv.ptr, nv.stream_ptr()
-        for ids, n, add in ((bt.seq, bt.B * bt.T, 0), (bt.label, bt.B, 1), (bt.neg, bt.B * bt.Nn if bt.Nn else 0, 1)):
-            if n == 0:
-                continue
-            nv.LAUNCHES["count"] += 1
-            rc = nv.lib().tcar_peer_fetch_rows(p(ids), n, add, self._peer_ptrs, self._peer_bounds, self._cat_R,
-                                               self.rank, p(self.ps.item_full), st)
-            if rc != 0:
-                raise nv.TcarNativeError(f"tcar_peer_fetch_rows failed with code {rc}")
+        p = nv.ptr
+        nv.LAUNCHES["count"] += 1
+        rc = nv.lib().tcar_peer_fetch_rows(p(bt.seq), p(bt.label), p(bt.neg), bt.B, bt.T, bt.Nn, self._peer_ptrs,
+                                           self._peer_bounds, self._cat_R, self.rank, p(self.ps.item_full),
+                                           nv.stream_ptr())
+        if rc != 0:
+            raise nv.TcarNativeError(f"tcar_peer_fetch_rows failed with code {rc}")
 
     def _gather(self, out_flat, inp_flat):
         """all_gather_into_tensor on flat views: out = [rank 0 | rank 1 | ...]."""
@@ -163,6 +168,15 @@ class CatalogShardedTraining:
         self._prefetched = None
         self._item_table_synced = False
         groups = [g for g in range(R) if counts[g] > 0]
+        trace = self._cat_trace
+
+        def mark(name):
+            if trace is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                trace.append((name, ev))
+
+        mark("start")
         L = 7 * Bmax * T + 3 * Bmax + Bmax * Nn
         # ---- packed ids of every rank (sparse-row scatter below); as the first collective of the step it also orders
         # every owner's previous Adam pass before the peer loads
@@ -173,113 +187,104 @@ class CatalogShardedTraining:
             if B > 0:
                 self._ids[: bt.buf.numel()].copy_(bt.buf)
             self._gather(self._ids_all[: R * L], self._ids[:L])
-            ids_of = lambda g: self._ids_all[g * L: (g + 1) * L]
             if B > 0:
                 self._fetch_rows(bt)
-        else:
-            ids_of = lambda g: bt.buf
+        mark("ids+fetch")
         # ---- session forward of the local sessions -> Q, c_ref (views of the send buffer)
         if B > 0:
             self._session_forward(bt)
+        mark("session_fwd")
         if on:
             self._gather(self._qc_all.view(-1), self._qc)
-        qc = self._qc_all
-        q_of = lambda g: qc[g, :Q_BYTES]
-        c_of = lambda g: qc[g, Q_BYTES:]
-        # ---- every session group against every owned item range
+        mark("gather_q")
+        # ---- every session group against every owned item range (one call per phase and shard: the loops over the
+        # groups are in the library)
+        cnt = (C.c_int * R)(*counts)
+        ng = len(groups)
+        qc_ptr = self._qc_all.data_ptr()
+        shards = [sh for sh in self._cat_shards if sh["hi"] > sh["lo"]]
         multi = len(self._cat_shards) > 1
-        if multi:
-            self._sumexp_all.zero_()
-        for sh in self._cat_shards:
-            if sh["hi"] <= sh["lo"]:
-                continue
-            for g in groups:
-                nv.counted_call("tcar_score_fwd", 1, p(q_of(g)), p(sh["iext"]), p(c_of(g)), p(sh["E"][g]),
-                                p(sh["part"][g]), None, None, counts[g], sh["hi"] - sh["lo"], sh["n_pad"], 0,
-                                self._cluster_for(counts[g]))
-                dst = self._se_tmp if multi else self._sumexp_all[g]
-                nv.counted_call("tcar_ce_finish", 1, p(sh["part"][g]), p(dst), p(self._ce_tmp), sh["tiles"], counts[g])
-                if multi:
-                    self._sumexp_all[g, : counts[g]] += self._se_tmp[: counts[g]]
-        if on:
-            dist.all_reduce(self._sumexp_all, op=dist.ReduceOp.SUM)
-        if B > 0:
-            self.sumexp[:B].copy_(self._sumexp_all[me, :B])
-            torch.log(self.sumexp[:B], out=self.ce[:B])
-            nv.counted_call("tcar_neg_loss", 1, p(self.a_ic), p(ps.item), p(ps.content), p(bt.neg), p(self.ce),
-                            p(self.negloss), p(self.loss), p(self.coef), p(self.dA_neg), B, Nn)
-        # ---- dQ: partial sums over the owned items for every group, reduce-scattered to the sessions' ranks
-        first = True
-        for sh in self._cat_shards:
-            if sh["hi"] <= sh["lo"]:
-                continue
-            for g in groups:
-                dst = self._dq_all[g] if first else self._dq_tmp
-                nv.counted_call("tcar_score_bwd_q", 2, p(sh["E"][g]), p(sh["iext"]), p(sh["qpart"]), p(dst), counts[g],
-                                sh["n_pad"])
-                if not first:
-                    rows = (counts[g] + 127) // 128 * 128
-                    self._dq_all[g, :rows] += self._dq_tmp[:rows]
-            first = False
+        for sh in shards:
+            nv.counted_call("tcar_score_fwd_groups", ng, C.c_void_p(qc_ptr), QC_BYTES // 2, C.c_void_p(qc_ptr + Q_BYTES),
+                            QC_BYTES // 4, p(sh["iext"]), p(sh["E"]), QROWS * sh["n_pad"], p(sh["part"]),
+                            sh["tiles"] * QROWS, cnt, R, sh["hi"] - sh["lo"], sh["n_pad"], self._cluster_for(Bmax))
+        mark("score_fwd")
+        # ---- dQ partial sums over the owned items for every group; the softmax partial sums travel in the zero pad
+        # column of dQ, so ONE reduce-scatter hands both to the sessions' ranks (model_combine.py:145: CE = log sum)
+        for k, sh in enumerate(shards):
+            dst = self._dq_all if k == 0 else self._dq_tmp
+            nv.counted_call("tcar_score_bwd_q_groups", 3 * ng, p(sh["E"]), QROWS * sh["n_pad"], p(sh["iext"]),
+                            p(sh["qpart"]), p(dst), QROWS * KEXT, p(sh["part"]), sh["tiles"] * QROWS, sh["tiles"], cnt, R,
+                            sh["n_pad"])
+            if k > 0:
+                self._dq_all += self._dq_tmp
+        mark("score_bwd_q")
         if on:
             dist.reduce_scatter_tensor(self.dq_raw, self._dq_all, op=dist.ReduceOp.SUM)
             dq_raw = self.dq_raw
         else:
             dq_raw = self._dq_all[0]
         if B > 0:
+            self.sumexp[:B].copy_(dq_raw[:B, KEXT - 1])
+            torch.log(self.sumexp[:B], out=self.ce[:B])
+            nv.counted_call("tcar_neg_loss", 1, p(self.a_ic), p(ps.item), p(ps.content), p(bt.neg), p(self.ce),
+                            p(self.negloss), p(self.loss), p(self.coef), p(self.dA_neg), B, Nn)
             nv.counted_call("tcar_score_bwd_finish", 1, p(dq_raw), p(self.sumexp), p(self.dA_neg), p(self.a_ic),
                             p(ps.ct_tab), p(ps.item), p(ps.content), p(ps.mwdhm), p(bt.label), p(self.d_a_ic),
                             p(self.d_a_pt), p(self.dTq), p(self.Qs), B)
-        if on:
-            self._gather(self._qs_all.view(-1), self.Qs.view(-1))
-        # ---- dense gradient of the owned item rows: complete after the last group (sum over ALL sessions)
-        for sh in self._cat_shards:
-            if sh["hi"] <= sh["lo"]:
-                continue
-            g_rows = ps.item_g_full[sh["lo"]:]            # the kernel writes table row n + 1 for local item n
-            for k, g in enumerate(groups):
-                nv.counted_call("tcar_score_bwd_i_acc", 1, p(sh["E"][g]), p(self._qs_all[g]), p(g_rows), None,
-                                counts[g], sh["hi"] - sh["lo"], sh["n_pad"], 1 if k > 0 else 0)
-        # ---- session-side backward of the local sessions, then the sparse rows of every rank's sessions
+        mark("loss+finish")
+        # Collectives are overlapped with chains of short kernels only, never with the persistent GEMMs: an NCCL kernel
+        # that gets a few SMs first delays the GEMM CTAs bound to them by its whole duration (static tile schedule)
+        w_qs = dist.all_gather_into_tensor(self._qs_all.view(-1), self.Qs.view(-1), async_op=True) if on else None
+        # ---- session-side backward of the local sessions (beside the all-gather of Qs)
         if B > 0:
             self._session_backward(bt)
         else:
             ps.theta_g.zero_()
+        mark("session_bwd")
         n_pay = PAY_HEAD + Bmax * T * HP
         if on:
             if self._pay_all is None or self._pay_all.numel() < R * n_pay:
                 self._pay_all = torch.zeros(R * n_pay, device=self.dev)
+            w_qs.wait()
             self._gather(self._pay_all[: R * n_pay], self._pay[:n_pay])
-            pay_of = lambda g: self._pay_all[g * n_pay: (g + 1) * n_pay]
+            ids_ptr, ids_stride, pay_ptr, pay_stride = self._ids_all.data_ptr(), L, self._pay_all.data_ptr(), n_pay
         else:
-            pay_of = lambda g: self._pay
+            ids_ptr, ids_stride, pay_ptr, pay_stride = bt.buf.data_ptr(), 0, self._pay.data_ptr(), 0
+        mark("gather_payload")
+        # ---- dense gradient of the owned item rows: complete after the last group (sum over ALL sessions)
+        for sh in shards:
+            # the kernel writes table row n + 1 for local item n
+            nv.counted_call("tcar_score_bwd_i_groups", ng, p(sh["E"]), QROWS * sh["n_pad"], p(self._qs_all), QROWS * HP,
+                            p(ps.item_g_full[sh["lo"]:]), p(sh["sqp"]), cnt, R, sh["hi"] - sh["lo"], sh["n_pad"])
+        mark("score_bwd_i")
+        # ---- the sparse rows (clicks, labels, negatives) of every rank's sessions that fall into the owned ranges
         self._alloc_scatter(Bmax * T + Bmax + Bmax * Nn)
+        if self._slot_sq_g is None or self._slot_sq_g.numel() != R * self.hash_size:
+            self._slot_sq_g = torch.zeros(R * self.hash_size, device=self.dev)
+        if multi:
+            self._sq_slot.zero_()
         for sh in self._cat_shards:
             if sh["row_hi"] <= sh["row_lo"]:
                 continue
-            for g in groups:
-                Bg, ids, pay = counts[g], ids_of(g), pay_of(g)
-                Mg = Bg * T
-                seq, label = ids[:Mg], ids[7 * Mg + 2 * Bg: 7 * Mg + 3 * Bg]
-                neg = ids[7 * Mg + 3 * Bg: 7 * Mg + 3 * Bg + Bg * Nn] if Nn else None
-                nv.counted_call("tcar_scatter_add_rows_range", 3, p(seq), p(label), p(neg), p(pay[PAY_HEAD:]),
-                                p(pay[: QROWS * XW]), p(pay[QROWS * XW: PAY_HEAD]), p(ps.item), p(ps.item_g),
-                                p(self.hash_keys), p(self.hash_cnt), p(self.hash_acc), p(self.entry_slot), None,
-                                self.hash_size, Bg, T, Nn, sh["row_lo"], sh["row_hi"])
-        # ---- clip norms: small tensors after their all-reduce; the item tensor from the owned rows, summed over ranks
-        red = self._red
-        red[: ps.flat_size].copy_(ps.theta_g)
-        red[ps.flat_size:].zero_()
-        for sh in self._cat_shards:
-            if sh["row_hi"] <= sh["row_lo"]:
-                continue
-            rows = ps.item_g_full[sh["row_lo"]: sh["row_hi"]]
-            nv.counted_call("tcar_sqnorm_big", 2, p(rows), p(ps.norm_partial), p(self._sq_tmp), rows.numel())
-            red[ps.flat_size: ps.flat_size + 1] += self._sq_tmp
+            nv.counted_call("tcar_scatter_add_rows_groups", 3 * ng, C.c_void_p(ids_ptr), ids_stride, C.c_void_p(pay_ptr),
+                            pay_stride, p(ps.item), p(ps.item_g), p(self.hash_keys), p(self.hash_cnt), p(self.hash_acc),
+                            p(self.entry_slot), p(self._slot_sq_g), self.hash_size, cnt, R, T, Nn, sh["row_lo"],
+                            sh["row_hi"])
+            # squared norm of the owned gradient rows without re-reading them: per-CTA sums of the dense GEMM (last
+            # group = accumulated values) + the per-slot corrections of the scatter passes
+            dense = sh["hi"] > sh["lo"]
+            nv.counted_call("tcar_update_norms", 1, None, None, None, 0, p(sh["sqp"]) if dense else None,
+                            sh["ctas"] if dense else 0, p(self._slot_sq_g), R * self.hash_size,
+                            p(self._sq_tmp if multi else self._sq_slot), p(ps.norm_partial), p(ps.norm_ticket), None)
+            if multi:
+                self._sq_slot += self._sq_tmp
+        mark("scatter+norm")
+        # ---- [small-tensor gradients | item-gradient norm] summed over ranks; per-tensor clip + Adam (model_combine.py:
+        # 155-163) on the replicated small tensors and on the owned item rows
         if on:
-            dist.all_reduce(red, op=dist.ReduceOp.SUM)
-        ps.theta_g.copy_(red[: ps.flat_size])
-        ps.sqnorm_item.copy_(red[ps.flat_size: ps.flat_size + 1])
+            dist.all_reduce(self._red, op=dist.ReduceOp.SUM)
+        mark("allreduce")
         nv.counted_call("tcar_sqnorm_segments", 1, p(ps.theta_g), p(ps.seg_off), p(ps.sqnorm_small), len(SMALL))
         ps.step.add_(1)
         self.global_step += 1
@@ -289,8 +294,9 @@ class CatalogShardedTraining:
             if n <= 0:
                 continue
             nv.counted_call("tcar_adam_item", 1, p(ps.item_full[lo:]), p(ps.item_m_full[lo:]), p(ps.item_v_full[lo:]),
-                            p(ps.item_g_full[lo:]), p(ps.sqnorm_item), p(ps.step), self.lr, self.max_grad_f,
+                            p(ps.item_g_full[lo:]), p(self._sq_slot), p(ps.step), self.lr, self.max_grad_f,
                             p(ps.iext), lo, n, None, 0)
+        mark("adam")
         self._fused_norm = False
         return self.loss[:B]
 

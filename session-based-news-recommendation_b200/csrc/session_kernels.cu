@@ -493,7 +493,7 @@ build_query_kernel(const float* __restrict__ a_ic, const float* __restrict__ a_p
 // stride over the partials with 8 independent loads in flight per thread, fixed combine order.
 __global__ void __launch_bounds__(1024)
 ce_finish_kernel(const float* __restrict__ part, float* __restrict__ sumexp, float* __restrict__ ce, int n_tiles,
-                 int B) {
+                 int B, int sum_stride) {
     PDL_ENTER();
     __shared__ float s[32][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -515,8 +515,8 @@ ce_finish_kernel(const float* __restrict__ part, float* __restrict__ sumexp, flo
     if (w == 0 && lane < 16 && b < B) {
         float tot = 0.f;
         for (int i = 0; i < 32; ++i) tot += s[i][lane] + s[i][lane + 16];
-        sumexp[b] = tot;
-        ce[b] = logf(tot);
+        sumexp[(size_t)b * sum_stride] = tot;
+        if (ce) ce[b] = logf(tot);
     }
 }
 
@@ -1075,7 +1075,15 @@ extern "C" int tcar_build_query(const float* a_ic, const float* a_pt, const floa
 
 extern "C" int tcar_ce_finish(const float* rowsum_part, float* sumexp, float* ce, int n_tiles, int B, void* stream) {
     if (B < 1 || B > TCAR_QROWS) return TCAR_ERR_ARG;
-    launch_pdl(ce_finish_kernel, dim3((B + 15) / 16), dim3(1024), 0, STREAM, rowsum_part, sumexp, ce, n_tiles, B);
+    launch_pdl(ce_finish_kernel, dim3((B + 15) / 16), dim3(1024), 0, STREAM, rowsum_part, sumexp, ce, n_tiles, B, 1);
+    return LAUNCH_RC();
+}
+
+extern "C" int tcar_rowsum_finish(const float* rowsum_part, float* out, int out_stride, int n_tiles, int B,
+                                  void* stream) {
+    if (B < 1 || B > TCAR_QROWS || out_stride < 1 || !out) return TCAR_ERR_ARG;
+    launch_pdl(ce_finish_kernel, dim3((B + 15) / 16), dim3(1024), 0, STREAM, rowsum_part, out,
+               static_cast<float*>(nullptr), n_tiles, B, out_stride);
     return LAUNCH_RC();
 }
 

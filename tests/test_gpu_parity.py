@@ -353,15 +353,19 @@ def test_catalog_sharded_train_step_equals_plain_step(N, V, B, T, scale, max_gra
         lp = plain.train_step(bt_p).clone()
         lc = cat.train_step(bt_c).clone()
         torch.cuda.synchronize()
-        np.testing.assert_allclose(lc.cpu().numpy(), lp.cpu().numpy(), rtol=1e-5, atol=1e-5)
-        assert relerr(cat.ps.theta_g, plain.ps.theta_g) < 1e-5
-        assert relerr(cat.ps.item_g, plain.ps.item_g) < 1e-5
+        # the second step starts from parameters that already differ in the last bits -> looser bounds
+        tol = 1e-5 if step == 0 else 2e-4
+        np.testing.assert_allclose(lc.cpu().numpy(), lp.cpu().numpy(), rtol=tol, atol=tol)
+        assert relerr(cat.ps.theta_g, plain.ps.theta_g) < tol, step
+        assert relerr(cat.ps.item_g, plain.ps.item_g) < tol, step
         assert (cat.ps.item_g[:, 250:] == 0).all() and (cat.ps.item_g[0] == 0).all()
         assert (cat.hash_keys == -1).all() and (cat.hash_acc == 0).all() and (cat.hash_cnt == 0).all()
+        want = float((plain.ps.item_g.double() ** 2).sum())
+        assert abs(float(cat._sq_slot.item()) - want) <= 1e-4 * want, "fused squared norm of the item gradient"
         # Adam normalises every element by its own |g|: last-bit differences of tiny gradients move those elements by a
         # visible fraction of lr, hence a looser bound than on the gradients themselves
-        assert relerr(cat.ps.theta, plain.ps.theta) < 2e-5
-        assert relerr(cat.ps.item, plain.ps.item) < 2e-5
+        assert relerr(cat.ps.theta, plain.ps.theta) < 2e-5 * (step + 1)
+        assert relerr(cat.ps.item, plain.ps.item) < 2e-5 * (step + 1)
         d = (cat.ps.iext.float() - plain.ps.iext.float()).abs()
         assert float((d > 0).float().mean()) < 1e-3, "refreshed bf16 scoring operand differs in more than a few ulps"
     assert int(cat.ps.step.item()) == 2 and cat.global_step == 2

@@ -95,6 +95,9 @@ def main():
             cres["loss_maxabs"] = max(cres["loss_maxabs"], float((lc - lr_[lo:hi]).abs().max()))
         cres["g_item_rel"] = max(cres["g_item_rel"], rel(cat.ps.item_g_full[own], ref.ps.item_g_full[own]))
         cres["g_theta_rel"] = max(cres["g_theta_rel"], rel(cat.ps.theta_g, ref.ps.theta_g))
+        # clip norm of the item gradient: fused (GEMM partials + scatter corrections of every group), summed over ranks
+        want = float((ref.ps.item_g.double() ** 2).sum())
+        cres["item_sqnorm_rel"] = max(cres.get("item_sqnorm_rel", 0.0), abs(float(cat._sq_slot.item()) - want) / want)
     cres["own_rows_rel"] = rel(cat.ps.item_full[own], ref.ps.item_full[own])
     cat.sync_item_table()
     torch.cuda.synchronize()
@@ -107,7 +110,7 @@ def main():
     # last bits (Adam normalises every element by its own |g|), so the bounds are looser than for a single step
     cres["ok"] = bool(cres["loss_maxabs"] < 1e-4 and cres["g_item_rel"] < 5e-5 and cres["g_theta_rel"] < 5e-5
                       and cres["own_rows_rel"] < 5e-6 and cres["item_after_rel"] < 5e-6
-                      and cres["theta_after_rel"] < 5e-6 and cres["moments_rel"] < 5e-5
+                      and cres["theta_after_rel"] < 5e-6 and cres["moments_rel"] < 5e-5 and cres["item_sqnorm_rel"] < 1e-4
                       and cres["iext_mismatch_frac"] < 1e-3)
     res["catalog"] = cres
     cat.close_peers()
