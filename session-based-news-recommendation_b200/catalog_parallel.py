@@ -107,27 +107,34 @@ class CatalogShardedTraining:
         self.train_parallel = "catalog"
 
     def _open_peers(self):
+        """Export the own fp32 item table and open every other rank's (CUDA IPC).  All ranks agree on the outcome before
+        anyone raises, so that a node without peer access fails cleanly instead of hanging in a later collective."""
         import torch.distributed as dist
+        err = None
         handle = (C.c_ubyte * nv.PEER_HANDLE_BYTES)()
         off = C.c_longlong(0)
         rc = nv.lib().tcar_peer_export(C.c_void_p(self.ps.item_full.data_ptr()), handle, C.byref(off))
         if rc != 0:
-            raise nv.TcarNativeError(f"tcar_peer_export failed with code {rc} (cudaIpcGetMemHandle; the item table "
-                                     "must live in a plain cudaMalloc block -- PYTORCH_CUDA_ALLOC_CONF=expandable_segments "
-                                     "is not supported)")
-        mine = (bytes(handle), int(off.value))
+            err = (f"tcar_peer_export failed with code {rc} (cudaIpcGetMemHandle; the item table must live in a plain "
+                   "cudaMalloc block -- PYTORCH_CUDA_ALLOC_CONF=expandable_segments is not supported)")
         everyone = [None] * self.world
-        dist.all_gather_object(everyone, mine)
-        for g, (hb, o) in enumerate(everyone):
-            if g == self.rank:
+        dist.all_gather_object(everyone, (bytes(handle), int(off.value), rc))
+        for g, (hb, o, rc_g) in enumerate(everyone):
+            if g == self.rank or rc_g != 0 or err is not None:
                 continue
             out = C.c_void_p()
             rc = nv.lib().tcar_peer_open((C.c_ubyte * nv.PEER_HANDLE_BYTES).from_buffer_copy(hb), o, C.byref(out))
             if rc != 0 or not out.value:
-                raise nv.TcarNativeError(f"tcar_peer_open(rank {g}) failed with code {rc}: catalog-sharded training "
-                                         "needs CUDA IPC peer access between the GPUs of the node")
+                err = (f"tcar_peer_open(rank {g}) failed with code {rc}: catalog-sharded training needs CUDA IPC peer "
+                       "access between the GPUs of the node")
+                break
             self._peer_ptrs[g] = out.value
             self._peer_opened.append((out.value, o))
+        bad = torch.tensor([0 if err is None else 1], device=self.dev, dtype=torch.int32)
+        dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+        if int(bad.item()):
+            self.close_peers()
+            raise nv.TcarNativeError(err or "another rank could not export / open the peer item tables")
 
     def close_peers(self):
         for ptr, off in self._peer_opened:
