@@ -56,7 +56,8 @@ def save_model(model, args, saver=None):
     path = os.path.join(args["modelpath"], "model.ckpt-" + suf)
     model.sync_updates()
     model.sync_item_table()                  # catalog-sharded training: collect every owner's rows first
-    torch.save(model.ps.state_dict(), path)
+    if getattr(model, "rank", 0) == 0:       # every rank holds the same state; one writer
+        torch.save(model.ps.state_dict(), path)
     return path
 
 
