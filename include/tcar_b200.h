@@ -323,6 +323,13 @@ int tcar_score_fwd_groups(const void* q_bf16, long long q_stride, const float* c
                           const void* iext_bf16, void* e_out, long long e_stride, float* rowsum_part,
                           long long part_stride, const int* n_rows, int groups, int n_items, int n_pad, int cluster,
                           void* stream);
+/* bwd_q of ALL present groups in one launch (what tcar_score_bwd_q_groups uses when more than one group is present):
+ * E_g at e_bf16 + g * e_stride, dq [groups][512][640] back to back, part >= tcar_score_bwd_q_multi_part_elems(groups)
+ * floats of scratch.  With R x 4 m-tiles of 128 session rows the reduction over the items needs only 148 / (8 R) splits:
+ * long K loops and one small split reduction instead of R short launches. */
+long long tcar_score_bwd_q_multi_part_elems(int groups);
+int tcar_score_bwd_q_multi(const void* e_bf16, long long e_stride, const void* iext_bf16, float* part, float* dq,
+                           const int* n_rows, int groups, int n_pad, void* stream);
 int tcar_score_bwd_q_groups(const void* e_bf16, long long e_stride, const void* iext_bf16, float* part, float* dq,
                             long long dq_stride, const float* rowsum_part, long long part_stride, int n_tiles,
                             const int* n_rows, int groups, int n_pad, void* stream);

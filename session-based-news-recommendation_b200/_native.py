@@ -53,6 +53,8 @@ SIGNATURES = {
     "tcar_peer_fetch_rows": [_P, _P, _P, _I, _I, _I, _P, _P, _I, _I, _P, _P],
     "tcar_rowsum_finish": [_P, _P, _I, _I, _I, _P],
     "tcar_score_fwd_groups": [_P, _LL, _P, _LL, _P, _P, _LL, _P, _LL, _P, _I, _I, _I, _I, _P],
+    "tcar_score_bwd_q_multi_part_elems": [_I],
+    "tcar_score_bwd_q_multi": [_P, _LL, _P, _P, _P, _P, _I, _I, _P],
     "tcar_score_bwd_q_groups": [_P, _LL, _P, _P, _P, _LL, _P, _LL, _I, _P, _I, _I, _P],
     "tcar_score_bwd_i_groups": [_P, _LL, _P, _LL, _P, _P, _P, _I, _I, _I, _P],
     "tcar_scatter_add_rows_groups": [_P, _LL, _P, _LL, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P],
@@ -85,7 +87,7 @@ def lib():
         for name, argtypes in SIGNATURES.items():
             fn = getattr(l, name)
             fn.argtypes = argtypes
-            fn.restype = C.c_longlong if name == "tcar_gemm_tf32_part_elems" else C.c_int
+            fn.restype = C.c_longlong if name.endswith("_part_elems") else C.c_int
         _lib = l
     return _lib
 

@@ -92,7 +92,10 @@ class CatalogShardedTraining:
             sh["E"] = torch.zeros(R, QROWS * sh["n_pad"], device=dev, dtype=torch.bfloat16)
             sh["part"] = torch.zeros(R, tiles * QROWS, device=dev)
             splits = max(nv.lib().tcar_score_bwd_q_splits(b, sh["n_pad"]) for b in (1, 129, 257, 385))
-            sh["qpart"] = torch.zeros(splits, QROWS, KEXT, device=dev)
+            qelems = splits * QROWS * KEXT
+            if R > 1:
+                qelems = max(qelems, int(nv.lib().tcar_score_bwd_q_multi_part_elems(R)))
+            sh["qpart"] = torch.zeros(qelems, device=dev)
             sh["ctas"] = nv.lib().tcar_score_bwd_i_ctas(sh["n_pad"])
             sh["sqp"] = torch.zeros(sh["ctas"], device=dev)
         self._slot_sq_g = None

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <cuda.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 #include "tcar_b200.h"
 #include "launch.cuh"
@@ -139,12 +140,26 @@ extern "C" int tcar_score_bwd_q_groups(const void* e_bf16, long long e_stride, c
                                        long long part_stride, int n_tiles, const int* n_rows, int groups, int n_pad,
                                        void* stream) {
     if (!n_rows || groups < 1) return TCAR_ERR_ARG;
+    int present = 0;
+    for (int g = 0; g < groups; ++g) present += n_rows[g] > 0;
+    // several groups: one launch over all of them (needs the groups' dQ blocks back to back and a part buffer of
+    // tcar_score_bwd_q_multi_part_elems floats); TCAR_BWDQ_LOOP=1 keeps the per-group launches (A/B switch)
+    const char* loop_env = getenv("TCAR_BWDQ_LOOP");
+    const bool multi = present > 1 && groups <= 16 && dq_stride == (long long)TCAR_QROWS * TCAR_KEXT &&
+                       !(loop_env && loop_env[0] == '1');
+    if (multi) {
+        const int rc = tcar_score_bwd_q_multi(e_bf16, e_stride, iext_bf16, part, dq, n_rows, groups, n_pad, stream);
+        if (rc) return rc;
+    }
     for (int g = 0; g < groups; ++g) {
         if (n_rows[g] <= 0) continue;
         float* dq_g = dq + g * dq_stride;
-        int rc = tcar_score_bwd_q(static_cast<const uint16_t*>(e_bf16) + g * e_stride, iext_bf16, part, dq_g,
+        int rc = 0;
+        if (!multi) {
+            rc = tcar_score_bwd_q(static_cast<const uint16_t*>(e_bf16) + g * e_stride, iext_bf16, part, dq_g,
                                   n_rows[g], n_pad, stream);
-        if (rc) return rc;
+            if (rc) return rc;
+        }
         // the zero pad column 639 of dQ carries the group's softmax partial sums through the same reduce-scatter
         if (rowsum_part) {
             rc = tcar_rowsum_finish(rowsum_part + g * part_stride, dq_g + (TCAR_KEXT - 1), TCAR_KEXT, n_tiles,

@@ -451,14 +451,24 @@ constexpr int Q_B_STAGE = Q_CH * BK * 2;  // 40960  Iext tile [64 n x 320 c], MN
 constexpr int Q_STAGE = Q_A_STAGE + Q_B_STAGE;
 constexpr int Q_SMEM = Q_STAGES * Q_STAGE + 1024 + 256;
 
+constexpr int Q_MAX_MTILES = 64;   // 16 session groups x 4 m-tiles
+
 struct BwdQParams {
-    float* part;     // [splits, 512, 640]
+    float* part;     // [splits, rows_total, 640]
     int kb_total;    // Npad / 64
     int kb_per;      // K blocks per split
     int splits;
-    int mtiles;
+    int mtiles;      // m-tiles of 128 session rows, over all groups
+    int rows_total;  // rows of one split's partial: 512 (one group) or groups x 512
+    unsigned char grp[Q_MAX_MTILES];   // MULTI: session group and m-tile inside the group of every global m-tile
+    unsigned char lmt[Q_MAX_MTILES];
 };
 
+// MULTI = false: one group of <= 512 sessions, E through a 3-D tensor map (the single-GPU / data-parallel step).
+// MULTI = true : the session groups of a catalog-sharded step in ONE launch -- E_g a fixed stride apart behind a 4-D
+// tensor map, unit = (split, global m-tile, column half): with R x 4 m-tiles the reduction over the items needs only
+// 148 / (2 x 4R) splits, i.e. long K loops and a small split reduction instead of R short launches.
+template <bool MULTI>
 __global__ void __launch_bounds__(kThreads, 1)
 score_bwd_q_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant__ CUtensorMap map_i,
                    const BwdQParams p) {
@@ -476,8 +486,10 @@ score_bwd_q_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_const
     // unit = (split, mtile, chalf)
     const uint32_t unit = blockIdx.x;
     const uint32_t chalf = unit & 1;
-    const uint32_t mtile = (unit >> 1) % p.mtiles;
+    const uint32_t gmt = (unit >> 1) % p.mtiles;
     const uint32_t split = (unit >> 1) / p.mtiles;
+    const uint32_t grp = MULTI ? p.grp[gmt] : 0u;
+    const uint32_t mtile = MULTI ? p.lmt[gmt] : gmt;
     const int kb0 = split * p.kb_per;
     const int kb1 = min(kb0 + p.kb_per, p.kb_total);
     const int nkb = max(kb1 - kb0, 0);
@@ -508,7 +520,8 @@ score_bwd_q_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_const
                 mbar_expect_tx(&full[stage], Q_STAGE);
                 uint8_t* sa = smem + stage * Q_STAGE;
                 uint8_t* sb = sa + Q_A_STAGE;
-                tma_load_3d(sa, &map_e, &full[stage], 0, mtile * (BM / 8), kb * (BK / 8));
+                if (MULTI) tma_load_4d(sa, &map_e, &full[stage], 0, mtile * (BM / 8), kb * (BK / 8), grp);
+                else tma_load_3d(sa, &map_e, &full[stage], 0, mtile * (BM / 8), kb * (BK / 8));
 #pragma unroll
                 for (int j = 0; j < Q_CH / 64; ++j)
                     tma_load_2d(sb + j * 8192, &map_i, &full[stage], chalf * Q_CH + j * 64, kb * BK);
@@ -541,8 +554,8 @@ score_bwd_q_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_const
         }
     } else if (warp >= 4) {
         const uint32_t q = warp - 4;
-        const uint32_t row = mtile * BM + q * 32 + lane;
-        float* dst = p.part + ((size_t)split * QROWS + row) * KEXT + chalf * Q_CH;
+        const uint32_t row = grp * QROWS + mtile * BM + q * 32 + lane;
+        float* dst = p.part + ((size_t)split * p.rows_total + row) * KEXT + chalf * Q_CH;
         if (nkb > 0) {
             mbar_wait(acc_full, 0);
             tc_fence_after();
@@ -797,6 +810,21 @@ static int make_map_e(CUtensorMap* m, const void* base, uint64_t n_pad, uint32_t
     return r == CUDA_SUCCESS ? 0 : TCAR_ERR_TENSORMAP;
 }
 
+// The E blocks of several session groups, `group_stride` elements apart, as a 4-D tensor (group outermost).
+static int make_map_e4(CUtensorMap* m, const void* base, uint64_t n_pad, uint32_t box_rows, uint32_t box_blocks,
+                       uint32_t groups, uint64_t group_stride) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return TCAR_ERR_DRIVER;
+    cuuint64_t dims[4] = {64, (cuuint64_t)QROWS / 8, n_pad / 8, groups};
+    cuuint64_t strides[3] = {128, (cuuint64_t)QROWS * 16, group_stride * 2};
+    cuuint32_t box[4] = {64, box_rows / 8, box_blocks, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : TCAR_ERR_TENSORMAP;
+}
+
 static int sm_count() {
     static int n = 0;
     if (!n) {
@@ -947,14 +975,65 @@ extern "C" int tcar_score_bwd_q(const void* e_bf16, const void* iext_bf16, float
     p.splits = tcar_score_bwd_q_splits(n_rows, n_pad);
     p.kb_total = n_pad / BK;
     p.kb_per = (p.kb_total + p.splits - 1) / p.splits;
-    cudaError_t e = cudaFuncSetAttribute(score_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM);
+    p.rows_total = QROWS;
+    cudaError_t e = cudaFuncSetAttribute(score_bwd_q_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM);
     if (e != cudaSuccess) return (int)e;
-    launch_pdl(score_bwd_q_kernel, dim3(p.splits * p.mtiles * 2), dim3(kThreads), Q_SMEM, stream, me, mi, p);
+    launch_pdl(score_bwd_q_kernel<false>, dim3(p.splits * p.mtiles * 2), dim3(kThreads), Q_SMEM, stream, me, mi, p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     // partial layout is [split][512][640]; rows of m-tiles that were not computed are never read by callers
     const int total = p.mtiles * BM * KEXT;
     launch_pdl(reduce_splits_kernel, dim3((total + 255) / 256), dim3(256), 0, stream, part, dq, p.splits, QROWS * KEXT, total);
+    return (int)cudaGetLastError();
+}
+
+// All session groups of a catalog-sharded step in one launch (see score_bwd_q_kernel<true>): dq [groups][512][640],
+// part >= tcar_score_bwd_q_multi_part_elems(groups) floats.  Groups with n_rows[g] <= 0 are skipped (their dq rows
+// receive whatever the unused partial rows hold -- never read by callers).
+extern "C" long long tcar_score_bwd_q_multi_part_elems(int groups) {
+    return (long long)(groups > 24 ? groups : 24) * QROWS * KEXT;
+}
+
+extern "C" int tcar_score_bwd_q_multi(const void* e_bf16, long long e_stride, const void* iext_bf16, float* part,
+                                      float* dq, const int* n_rows, int groups, int n_pad, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!n_rows || groups < 1 || groups > 16 || n_pad % 256 != 0 || e_stride < (long long)QROWS * n_pad ||
+        (e_stride & 7))
+        return TCAR_ERR_ARG;
+    BwdQParams p = {};
+    int mt = 0;
+    for (int g = 0; g < groups; ++g) {
+        if (n_rows[g] > QROWS) return TCAR_ERR_ARG;
+        const int m = n_rows[g] > 0 ? (n_rows[g] + BM - 1) / BM : 0;
+        for (int l = 0; l < m; ++l, ++mt) {
+            p.grp[mt] = (unsigned char)g;
+            p.lmt[mt] = (unsigned char)l;
+        }
+    }
+    if (mt == 0) return 0;
+    CUtensorMap me, mi;
+    int rc = make_map_e4(&me, e_bf16, n_pad, BM, BK / 8, groups, (uint64_t)e_stride);
+    if (rc) return rc;
+    rc = make_map_bf16(&mi, iext_bf16, n_pad, KEXT, KEXT, 64, BK);
+    if (rc) return rc;
+    p.part = part;
+    p.mtiles = mt;
+    p.kb_total = n_pad / BK;
+    int splits = sm_count() / (2 * mt);
+    const int cap = 24 / groups > 0 ? 24 / groups : 1;      // part holds 24 x 512 rows
+    if (splits > cap) splits = cap;
+    if (splits > p.kb_total) splits = p.kb_total;
+    if (splits < 1) splits = 1;
+    p.splits = splits;
+    p.kb_per = (p.kb_total + splits - 1) / splits;
+    p.rows_total = groups * QROWS;
+    cudaError_t e = cudaFuncSetAttribute(score_bwd_q_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    launch_pdl(score_bwd_q_kernel<true>, dim3(splits * mt * 2), dim3(kThreads), Q_SMEM, stream, me, mi, p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    const int total = groups * QROWS * KEXT;
+    launch_pdl(reduce_splits_kernel, dim3((total + 255) / 256), dim3(256), 0, stream, part, dq, splits, total, total);
     return (int)cudaGetLastError();
 }
 

@@ -130,3 +130,79 @@ def test_score_bwd_i(native, B, N):
     # the fused per-CTA sums of squares add up to ||g_item||^2
     want = float((gi.double() ** 2).sum())
     assert abs(float(sqp.double().sum()) - want) <= 1e-5 * want
+
+
+# ------------------------------------------------------------------------------------------- session groups (catalog-sharded step)
+@pytest.mark.parametrize("counts,N", [([512, 512], 5000), ([300, 0, 512, 77], 2333), ([512] * 8, 3000), ([1, 5], 300)])
+def test_score_groups_match_single_group_calls(native, counts, N, monkeypatch):
+    """tcar_score_fwd_groups / _bwd_q_groups (one launch over all groups, tcar_score_bwd_q_multi) / _bwd_i_groups
+    against the per-group entry points and a torch matmul over the same bf16 operands."""
+    import os
+    R = len(counts)
+    g = torch.Generator(device="cuda").manual_seed(N + R)
+    n_pad = (N + 255) // 256 * 256
+    lib = native.lib()
+    tiles = lib.tcar_score_fwd_tiles(n_pad)
+    I = torch.zeros(n_pad, KEXT, device="cuda", dtype=torch.bfloat16)
+    I[:N] = (torch.randn(N, KEXT, device="cuda", generator=g) * 0.1).bfloat16()
+    I[:, KEXT - 1] = 0                                # the pad column of the scoring operand is zero
+    Q = torch.zeros(R, QROWS, KEXT, device="cuda", dtype=torch.bfloat16)
+    c = torch.randn(R, QROWS, device="cuda", generator=g) * 0.3
+    for r, b in enumerate(counts):
+        Q[r, :b] = (torch.randn(b, KEXT, device="cuda", generator=g) * 0.5).bfloat16()
+    E = torch.zeros(R, QROWS * n_pad, device="cuda", dtype=torch.bfloat16)
+    part = torch.zeros(R, tiles * QROWS, device="cuda")
+    cnt = (C.c_int * R)(*counts)
+    p = native.ptr
+    native.call("tcar_score_fwd_groups", p(Q), QROWS * KEXT, p(c), QROWS, p(I), p(E), QROWS * n_pad, p(part),
+                tiles * QROWS, cnt, R, N, n_pad, -2)
+    torch.cuda.synchronize()
+    for r, b in enumerate(counts):
+        if b == 0:
+            assert (E[r] == 0).all()
+            continue
+        E1 = torch.zeros(QROWS, n_pad, device="cuda", dtype=torch.bfloat16)
+        p1 = torch.zeros(tiles, QROWS, device="cuda")
+        native.call("tcar_score_fwd", p(Q[r]), p(I), p(c[r]), p(E1), p(p1), None, None, b, N, n_pad, 0, -2)
+        torch.cuda.synchronize()
+        assert torch.equal(E1.view(-1), E[r]) and torch.equal(p1.view(-1)[: tiles * QROWS], part[r])
+    # ---- dQ: single launch over all groups vs per-group launches vs fp64 matmul
+    qelems = max(int(lib.tcar_score_bwd_q_multi_part_elems(R)),
+                 max(lib.tcar_score_bwd_q_splits(b, n_pad) for b in (1, 129, 257, 385)) * QROWS * KEXT)
+    qpart = torch.zeros(qelems, device="cuda")
+    dq = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("TCAR_BWDQ_LOOP", mode)
+        out = torch.zeros(R, QROWS, KEXT, device="cuda")
+        native.call("tcar_score_bwd_q_groups", p(E), QROWS * n_pad, p(I), p(qpart), p(out), QROWS * KEXT, p(part),
+                    tiles * QROWS, tiles, cnt, R, n_pad)
+        torch.cuda.synchronize()
+        dq[mode] = out
+    monkeypatch.delenv("TCAR_BWDQ_LOOP")
+    for r, b in enumerate(counts):
+        if b == 0:
+            continue
+        El = e_from_blocked(E[r], n_pad)[:b].double()
+        ref = (El @ I.double()).float()
+        ref[:, KEXT - 1] = El.float().sum(1)          # softmax partial sums ride in the pad column
+        scale = ref[:, : KEXT - 1].abs().max().item()
+        for mode in ("1", "0"):
+            got = dq[mode][r, :b]
+            assert (got[:, : KEXT - 1] - ref[:, : KEXT - 1]).abs().max().item() / scale < 1e-4, (mode, r)
+            rs = got[:, KEXT - 1]
+            assert ((rs - ref[:, KEXT - 1]).abs() / ref[:, KEXT - 1]).max().item() < 2e-3, (mode, r)
+        assert torch.equal(dq["0"][r, :b, KEXT - 1], dq["1"][r, :b, KEXT - 1])
+    # ---- dItems: first present group overwrites, later ones accumulate
+    Qs = torch.zeros(R, QROWS, 256, device="cuda", dtype=torch.bfloat16)
+    for r, b in enumerate(counts):
+        Qs[r, :b, :250] = (torch.randn(b, 250, device="cuda", generator=g) * 0.2).bfloat16()
+    gi = torch.full((N + 1, 256), float("nan"), device="cuda")
+    gi[0] = 0
+    sqp = torch.zeros(lib.tcar_score_bwd_i_ctas(n_pad), device="cuda")
+    native.call("tcar_score_bwd_i_groups", p(E), QROWS * n_pad, p(Qs), QROWS * 256, p(gi), p(sqp), cnt, R, N, n_pad)
+    torch.cuda.synchronize()
+    ref = sum(e_from_blocked(E[r], n_pad)[:b, :N].double().t() @ Qs[r, :b].double() for r, b in enumerate(counts) if b)
+    scale = ref.abs().max().item()
+    assert (gi[1:].double() - ref).abs().max().item() / scale < 1e-4
+    want = float((gi.double() ** 2).sum())
+    assert abs(float(sqp.double().sum()) - want) <= 1e-5 * want
