@@ -223,7 +223,9 @@ class CatalogShardedTraining:
         # column of dQ, so ONE reduce-scatter hands both to the sessions' ranks (model_combine.py:145: CE = log sum)
         for k, sh in enumerate(shards):
             dst = self._dq_all if k == 0 else self._dq_tmp
-            nv.counted_call("tcar_score_bwd_q_groups", 3 * ng, p(sh["E"]), QROWS * sh["n_pad"], p(sh["iext"]),
+            # launches: one GEMM + one split reduction over all groups (per group when only one is present) + one
+            # partial-sum kernel per group
+            nv.counted_call("tcar_score_bwd_q_groups", 2 + ng if ng > 1 else 3, p(sh["E"]), QROWS * sh["n_pad"], p(sh["iext"]),
                             p(sh["qpart"]), p(dst), QROWS * KEXT, p(sh["part"]), sh["tiles"] * QROWS, sh["tiles"], cnt, R,
                             sh["n_pad"])
             if k > 0:
