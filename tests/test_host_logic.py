@@ -181,3 +181,50 @@ def test_model_refuses_to_run_without_cuda():
     from tcar_b200.model_combine import Seq2SeqAttNN
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         Seq2SeqAttNN({"itemnum": 1})
+
+
+def test_cfg1_plumbing_epoch_on_cpu():
+    """BASELINE.json configs[0] (`main.py --foldnum=0 --epoch=1` on small synthetic Globo-shaped sessions, CPU): the
+    host side of the product (pickle loader, CLI args, Sampler / next_packed) drives the ORACLE's train step and eval
+    for one epoch -- the plumbing the reference runs around sess.run (model_combine.py:196-315), minus the device."""
+    import torch
+    from oracle import tcar_oracle as O
+    from tcar_b200 import main as tmain, synth
+    from tcar_b200.sampler import Sampler
+    with tempfile.TemporaryDirectory() as d:
+        synth.write_dataset(d + "/synth/TCAR-mid/Normal/", N=150, n_train=90, n_test=30, fold=0)
+        cli = tmain.build_parser().parse_args(["--datapath", d + "/", "--dataset", "synth/TCAR-mid/", "--foldnum", "0",
+                                               "--epoch", "1", "--batch_size", "32"])
+        train, test, neighbor, a, item_dict = tmain.load_datas(cli)
+    N = a["itemnum"]
+    content = torch.from_numpy(np.asarray(a["content_emb"], dtype=np.float64))
+    mwdhm = torch.from_numpy(np.asarray(a["publish_time_MWDHM"]).astype(np.int64))
+    np.random.seed(2020)
+    params = {k: v.double() for k, v in O.init_params(N, a["emb_stddev"], a["stddev"]).items()}
+    adam = O.TFAdam(params, a["lr"])
+    sampler = Sampler(*train, neighbor, item_dict, a["neg_num"], batch_size=a["batch_size"], verbose=False)
+    losses, sessions = [], 0
+    while sampler.has_next():
+        packed, B, T, Nn = sampler.next_packed()
+        batch = {k: torch.from_numpy(v) for k, v in synth.unpack(packed, B, T, Nn).items()}
+        assert B <= a["batch_size"] and Nn == a["neg_num"] and int(batch["seq"].min()) >= 1
+        out, _ = O.train_step(params, adam, content, mwdhm, batch, max_grad=float(a["max_grad"]))
+        losses.append(float(out["loss"].mean()))
+        sessions += B
+    assert sessions == sum(len(v) for v in train[0].values()) and np.isfinite(losses).all()
+    # cross-entropy of an untrained softmax over N items ~ log N; negative feedback adds 0.01 * ~log 2
+    assert abs(losses[0] - np.log(N)) < 0.5
+    # evaluation loop (model_combine.py:254-315): metrics of every test session, Recall/MRR in [0, 1]
+    ev = Sampler(*test, batch_size=a["batch_size"], verbose=False)
+    recall, mrr, n = [], [], 0
+    while ev.has_next():
+        packed, B, T, Nn = ev.next_packed()
+        assert Nn == 0
+        batch = {k: torch.from_numpy(v) for k, v in synth.unpack(packed, B, T, 0).items()}
+        with torch.no_grad():
+            res = O.eval_batch(params, content, mwdhm, batch, a["category_id"], a["reverse_item"])
+        recall += list(res["recall"])
+        mrr += list(res["mrr"])
+        n += B
+    assert n == sum(len(v) for v in test[0].values())
+    assert 0.0 <= float(np.mean(recall)) <= 1.0 and 0.0 <= float(np.mean(mrr)) <= 1.0
