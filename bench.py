@@ -402,7 +402,8 @@ def run_b200(a):
     # train_step(bt, next_bt): the train loop's one-batch look-ahead (Seq2SeqAttNN.train) -- the session forward of the
     # next batch overlaps this step's table-wide Adam pass.  Every timed step therefore contains exactly one session
     # forward (its successor's) and the step after the last timed one is launched the same way.
-    pipe = world == 1 and not a.no_lookahead
+    # (catalog layout: only with the opt-in look-ahead across ranks, TCAR_CATALOG_LOOKAHEAD=1)
+    pipe = (world == 1 or bool(getattr(model, "cat_lookahead", False))) and not a.no_lookahead
     nxt = (lambda lst, i: lst[(i + 1) % len(lst)]) if pipe else (lambda lst, i: None)
     for i in range(W):
         model.train_step(dev[i % nbatch], nxt(dev, i))

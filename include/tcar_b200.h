@@ -285,6 +285,14 @@ int tcar_adam_item(float* item, float* m, float* v, const float* g, const float*
 int tcar_adam_item_rows(float* item, float* m, float* v, const float* g, const float* sqnorm, const int32_t* step,
                         float lr, float max_grad, void* iext_bf16, const int32_t* seq, int n_seq,
                         const int32_t* label, int n_label, int32_t* row_flags, int n_rows, void* stream);
+/* The same for the batches of several ranks (catalog-sharded step with look-ahead): ids = packed batches [7*B*T idx |
+ * 2*B ctx | B label | B*Nn neg] of rank g at ids + g * ids_stride with B = n_rows[g] (HOST array); rows seq, label + 1
+ * and neg + 1 that fall into the caller's table rows [row_lo, row_hi) are updated (item / m / v / g address row 0 of the
+ * whole table), all others are ignored and NOT claimed in row_flags. */
+int tcar_adam_item_rows_groups(float* item, float* m, float* v, const float* g, const float* sqnorm,
+                               const int32_t* step, float lr, float max_grad, void* iext_bf16, const int32_t* ids,
+                               long long ids_stride, const int* n_rows, int groups, int T, int Nn, int32_t* row_flags,
+                               int row_lo, int row_hi, void* stream);
 /* item columns of Iext from the fp32 item table (after all-gathering slices updated by other ranks). */
 int tcar_refresh_iext_items(const float* item, void* iext_bf16, int N, void* stream);
 

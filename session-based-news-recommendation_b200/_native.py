@@ -64,6 +64,7 @@ SIGNATURES = {
     "tcar_adam_small": [_P] * 6 + [_I, _P, _F, _F, _P],
     "tcar_adam_item": [_P] * 6 + [_F, _F, _P, _I, _I, _P, _I, _P],
     "tcar_adam_item_rows": [_P] * 6 + [_F, _F, _P, _P, _I, _P, _I, _P, _I, _P],
+    "tcar_adam_item_rows_groups": [_P] * 6 + [_F, _F, _P, _P, _LL, _P, _I, _I, _I, _P, _I, _I, _P],
     "tcar_refresh_iext_items": [_P, _P, _I, _P],
     "tcar_eval_topk": [_P] * 11 + [_I] * 4 + [_P],
     "tcar_topk_merge": [_P] * 4 + [_I, _I, _P],

@@ -73,6 +73,14 @@ class CatalogShardedTraining:
         self._pay_all = None
         self._ids = torch.zeros(1, device=dev, dtype=torch.int32)
         self._ids_all = torch.zeros(1, device=dev, dtype=torch.int32)
+        # look-ahead across ranks (opt-in, TCAR_CATALOG_LOOKAHEAD=1; see train_step_catalog): the NEXT batch's ids are
+        # gathered one step early into the second buffer pair
+        import os
+        self.cat_lookahead = os.environ.get("TCAR_CATALOG_LOOKAHEAD", "0") == "1"
+        self._ids_n = torch.zeros(1, device=dev, dtype=torch.int32)
+        self._ids_all_n = torch.zeros(1, device=dev, dtype=torch.int32)
+        self._cat_pre = None               # {"bt", "counts", "L"} of the batch whose ids / rows / forward are ahead
+        self._bar = torch.zeros(1, device=dev)
         self._sumexp_all = torch.zeros(R, QROWS, device=dev)
         self._dq_all = torch.zeros(R, QROWS, KEXT, device=dev)
         self._qs_all = torch.zeros(R, QROWS, HP, device=dev, dtype=torch.bfloat16) if R > 1 else self.Qs.view(1, QROWS, HP)
@@ -160,10 +168,16 @@ class CatalogShardedTraining:
         import torch.distributed as dist
         dist.all_gather_into_tensor(out_flat, inp_flat)
 
-    def train_step_catalog(self, bt, counts=None):
+    def train_step_catalog(self, bt, counts=None, next_bt=None, next_counts=None):
         """One train step with the catalog sharded across ranks.  bt = this rank's sessions (B may be 0 for a tail
         batch); counts[g] = sessions of rank g in this step (default: bt.B on every rank) -- all ranks must pass the
-        same list, and the same T / Nn.  Returns this rank's loss [B]."""
+        same list, and the same T / Nn.  Returns this rank's loss [B].
+
+        next_bt / next_counts (used when self.cat_lookahead): the batch of the FOLLOWING call.  Its packed ids are
+        all-gathered at the end of this step, every owner first updates the rows those ids name (tcar_adam_item_rows_
+        groups on its own range), one barrier later the rest of the owned rows is updated on the side stream while the
+        peer loads and the session forward of next_bt run on the high-priority stream -- the look-ahead of
+        Seq2SeqAttNN.train_step, across ranks.  Same arithmetic per row whichever kernel applies it."""
         import torch.distributed as dist
         ps, p = self.ps, nv.ptr
         R, me, on = self._cat_R, (self.rank if self._cat_dist else 0), self._cat_dist
@@ -174,7 +188,9 @@ class CatalogShardedTraining:
         Bmax = max(counts)
         if Bmax == 0:
             return self.loss[:0]
-        self.sync_updates()
+        pre, self._cat_pre = self._cat_pre, None
+        ahead = pre is not None and pre["bt"] is bt and pre["counts"] == counts
+        self.sync_updates()                # pending table-wide Adam (side stream) / prefetched forward (ahead stream)
         self._prefetched = None
         self._item_table_synced = False
         groups = [g for g in range(R) if counts[g] > 0]
@@ -190,18 +206,18 @@ class CatalogShardedTraining:
         L = 7 * Bmax * T + 3 * Bmax + Bmax * Nn
         # ---- packed ids of every rank (sparse-row scatter below); as the first collective of the step it also orders
         # every owner's previous Adam pass before the peer loads
-        if on:
-            if self._ids.numel() < L:
-                self._ids = torch.zeros(L, device=self.dev, dtype=torch.int32)
-                self._ids_all = torch.zeros(R * L, device=self.dev, dtype=torch.int32)
-            if B > 0:
-                self._ids[: bt.buf.numel()].copy_(bt.buf)
-            self._gather(self._ids_all[: R * L], self._ids[:L])
-            if B > 0:
-                self._fetch_rows(bt)
+        if ahead:
+            # ids gathered, rows fetched and session forward launched by the previous call: take over its ids buffers
+            self._ids, self._ids_n = self._ids_n, self._ids
+            self._ids_all, self._ids_all_n = self._ids_all_n, self._ids_all
+        else:
+            if on:
+                self._gather_ids(bt, L, False)
+                if B > 0:
+                    self._fetch_rows(bt)
         mark("ids+fetch")
         # ---- session forward of the local sessions -> Q, c_ref (views of the send buffer)
-        if B > 0:
+        if B > 0 and not ahead:
             self._session_forward(bt)
         mark("session_fwd")
         if on:
@@ -301,16 +317,80 @@ class CatalogShardedTraining:
         ps.step.add_(1)
         self.global_step += 1
         self._update_small()
-        for sh in self._cat_shards:
-            lo, n = sh["row_lo"], sh["row_hi"] - sh["row_lo"]
-            if n <= 0:
-                continue
-            nv.counted_call("tcar_adam_item", 1, p(ps.item_full[lo:]), p(ps.item_m_full[lo:]), p(ps.item_v_full[lo:]),
-                            p(ps.item_g_full[lo:]), p(self._sq_slot), p(ps.step), self.lr, self.max_grad_f,
-                            p(ps.iext), lo, n, None, 0)
+        look = (self.cat_lookahead and next_bt is not None and self.adam_overlap_ctas > 0 and next_bt.T >= 1)
+        if look:
+            ncounts = [next_bt.B] * R if next_counts is None else [int(c) for c in next_counts]
+            look = len(ncounts) == R and ncounts[me] == next_bt.B and max(ncounts) > 0
+        flags = None
+        if look:
+            # (a) the next step's ids, one step early; (b) the rows they name inside the owned ranges first
+            nBmax, nT, nNn = max(ncounts), next_bt.T, next_bt.Nn
+            nL = 7 * nBmax * nT + 3 * nBmax + nBmax * nNn
+            if on:
+                self._gather_ids(next_bt, nL, True)
+                nids_ptr, nids_stride = self._ids_all_n.data_ptr(), nL
+            else:
+                nids_ptr, nids_stride = next_bt.buf.data_ptr(), 0
+            ncnt = (C.c_int * R)(*ncounts)
+            flags = ps.row_flags
+            for sh in self._cat_shards:
+                if sh["row_hi"] <= sh["row_lo"]:
+                    continue
+                nv.counted_call("tcar_adam_item_rows_groups", 2 * sum(1 for c in ncounts if c > 0), p(ps.item_full),
+                                p(ps.item_m_full), p(ps.item_v_full), p(ps.item_g_full), p(self._sq_slot), p(ps.step),
+                                self.lr, self.max_grad_f, p(ps.iext), C.c_void_p(nids_ptr), nids_stride, ncnt, R, nT,
+                                nNn, p(flags), sh["row_lo"], sh["row_hi"])
+            # (c) every owner has updated the rows anyone is about to load
+            if on:
+                dist.all_reduce(self._bar, op=dist.ReduceOp.SUM)
+            main = torch.cuda.current_stream()
+            fork = torch.cuda.Event()
+            fork.record(main)
+            self._side.wait_event(fork)
+            self._ahead.wait_event(fork)
+        # ---- the owned rows (all of them, or those not yet updated: on the side stream, beside the next forward)
+        with torch.cuda.stream(self._side if look else torch.cuda.current_stream()):
+            for sh in self._cat_shards:
+                lo, n = sh["row_lo"], sh["row_hi"] - sh["row_lo"]
+                if n <= 0:
+                    continue
+                nv.counted_call("tcar_adam_item", 1, p(ps.item_full[lo:]), p(ps.item_m_full[lo:]),
+                                p(ps.item_v_full[lo:]), p(ps.item_g_full[lo:]), p(self._sq_slot), p(ps.step), self.lr,
+                                self.max_grad_f, p(ps.iext), lo, n, p(flags) if look else None,
+                                self.adam_overlap_ctas if look else 0)
+            if look:
+                done = torch.cuda.Event()
+                done.record(self._side)
+                self._update_done = done
+        if look:
+            # (d) peer loads + session forward of the next batch on the high-priority stream
+            with torch.cuda.stream(self._ahead):
+                if next_bt.B > 0:
+                    if on:
+                        self._fetch_rows(next_bt)
+                    self._session_forward(next_bt, prefetch=True)
+                adone = torch.cuda.Event()
+                adone.record(self._ahead)
+            self._ahead_done = adone
+            self._cat_pre = {"bt": next_bt, "counts": ncounts, "L": nL}
         mark("adam")
         self._fused_norm = False
         return self.loss[:B]
+
+    def _gather_ids(self, bt, L, nxt):
+        """All-gather one packed batch (L int32 per rank, zero padded) into the current / the look-ahead ids buffers."""
+        R = self._cat_R
+        loc, allb = (self._ids_n, self._ids_all_n) if nxt else (self._ids, self._ids_all)
+        if loc.numel() < L:
+            loc = torch.zeros(L, device=self.dev, dtype=torch.int32)
+            allb = torch.zeros(R * L, device=self.dev, dtype=torch.int32)
+            if nxt:
+                self._ids_n, self._ids_all_n = loc, allb
+            else:
+                self._ids, self._ids_all = loc, allb
+        if bt.B > 0:
+            loc[: bt.buf.numel()].copy_(bt.buf)
+        self._gather(allb[: R * L], loc[:L])
 
     # ------------------------------------------------------------------------------------------- re-assembly
     def sync_item_table(self):

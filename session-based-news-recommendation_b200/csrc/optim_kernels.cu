@@ -327,12 +327,13 @@ adam_item_rows_kernel(float4* __restrict__ item, float4* __restrict__ m, float4*
                       const float4* __restrict__ g, const float* __restrict__ sqnorm,
                       const int32_t* __restrict__ step, float lr, float max_grad, __nv_bfloat16* __restrict__ iext,
                       const int32_t* __restrict__ seq, int n_seq, const int32_t* __restrict__ label, int n_label,
-                      int32_t* __restrict__ flags, int n_rows) {
+                      int32_t* __restrict__ flags, int row_lo, int n_rows) {
     PDL_ENTER();
     const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (e >= n_seq + n_label) return;
     const int row = e < n_seq ? seq[e] : label[e - n_seq] + 1;
-    if (row < 0 || row >= n_rows) return;
+    // rows outside [row_lo, n_rows) are not this caller's to update (other catalog shard) and are not claimed
+    if (row < row_lo || row >= n_rows) return;
     const int t = step[0];
     int old = 0;
     if (lane == 0) old = atomicExch(&flags[row], t);
@@ -449,6 +450,35 @@ extern "C" int tcar_adam_item_rows(float* item, float* m, float* v, const float*
     launch_pdl(adam_item_rows_kernel, dim3((entries + 7) / 8), dim3(256), 0, STREAM, 
         reinterpret_cast<float4*>(item), reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v),
         reinterpret_cast<const float4*>(g), sqnorm, step, lr, max_grad, static_cast<__nv_bfloat16*>(iext_bf16), seq,
-        n_seq, label, n_label, row_flags, n_rows);
+        n_seq, label, n_label, row_flags, 0, n_rows);
     return (int)cudaGetLastError();
+}
+
+extern "C" int tcar_adam_item_rows_groups(float* item, float* m, float* v, const float* g, const float* sqnorm,
+                                          const int32_t* step, float lr, float max_grad, void* iext_bf16,
+                                          const int32_t* ids, long long ids_stride, const int* n_rows, int groups,
+                                          int T, int Nn, int32_t* row_flags, int row_lo, int row_hi, void* stream) {
+    if (!ids || !n_rows || groups < 1 || T < 1 || Nn < 0 || !row_flags || row_lo < 0 || row_hi < row_lo)
+        return TCAR_ERR_ARG;
+    for (int gr = 0; gr < groups; ++gr) {
+        const int B = n_rows[gr];
+        if (B <= 0) continue;
+        // packed batch of rank gr: [7*B*T idx | 2*B ctx | B label | B*Nn neg]
+        const int32_t* base = ids + gr * ids_stride;
+        const size_t M = (size_t)B * T;
+        const int32_t* lists[2] = {base + 7 * M + 2 * (size_t)B, base + 7 * M + 3 * (size_t)B};
+        const int n_first[2] = {(int)M, 0}, n_second[2] = {B, B * Nn};
+        for (int k = 0; k < 2; ++k) {
+            const int entries = n_first[k] + n_second[k];
+            if (entries == 0) continue;
+            launch_pdl(adam_item_rows_kernel, dim3((entries + 7) / 8), dim3(256), 0, STREAM,
+                reinterpret_cast<float4*>(item), reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v),
+                reinterpret_cast<const float4*>(g), sqnorm, step, lr, max_grad,
+                static_cast<__nv_bfloat16*>(iext_bf16), base, n_first[k], lists[k], n_second[k], row_flags, row_lo,
+                row_hi);
+            const int rc = (int)cudaGetLastError();
+            if (rc) return rc;
+        }
+    }
+    return 0;
 }

@@ -539,7 +539,8 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         must be read through this object's methods (or after sync_updates()).
         counts (catalog-sharded training only): sessions of every rank in this step, see train_step_catalog."""
         if self.train_parallel == "catalog":
-            return self.train_step_catalog(bt, counts if counts is not None else getattr(bt, "counts", None))
+            return self.train_step_catalog(bt, counts if counts is not None else getattr(bt, "counts", None), next_bt,
+                                           getattr(next_bt, "counts", None) if next_bt is not None else None)
         if bt.B == 0:
             # data-parallel tail batch with fewer sessions than ranks: contribute a zero gradient to the all-reduce
             self.sync_updates()

@@ -380,6 +380,35 @@ def test_catalog_sharded_train_step_equals_plain_step(N, V, B, T, scale, max_gra
     assert agree > 0.98, f"top-20 lists after two steps agree on {agree:.3f} of the slots"
 
 
+@pytest.mark.parametrize("V,T", [(1, 4), (3, 2), (8, 20)])
+def test_catalog_lookahead_is_bit_identical(V, T, monkeypatch):
+    """Opt-in look-ahead of the catalog-sharded step (TCAR_CATALOG_LOOKAHEAD=1): the rows the next batch names are
+    updated first (tcar_adam_item_rows_groups on every owned range), the rest of the table on the side stream beside
+    the next batch's session forward.  Every row is updated exactly once per step with the same arithmetic, so losses
+    and parameters equal the plain catalog-sharded sequence bit for bit."""
+    N, B, Nn = 1500, 200, 20
+    monkeypatch.setenv("TCAR_CATALOG_LOOKAHEAD", "0")
+    base, mwdhm = _build_catalog(N, V, emb_scale=30.0)
+    monkeypatch.setenv("TCAR_CATALOG_LOOKAHEAD", "1")
+    look, _ = _build_catalog(N, V, emb_scale=30.0)
+    assert look.cat_lookahead and not base.cat_lookahead
+    bts_b = [batch_for(base, N, B, T, Nn, mwdhm, seed=70 + i)[0] for i in range(4)]
+    bts_l = [batch_for(look, N, B, T, Nn, mwdhm, seed=70 + i)[0] for i in range(4)]
+    for i in range(4):
+        lb = base.train_step(bts_b[i]).clone()
+        ll = look.train_step(bts_l[i], bts_l[i + 1] if i + 1 < 4 else None).clone()
+        torch.cuda.synchronize()
+        assert torch.equal(lb, ll), f"loss of step {i}"
+        if i + 1 < 4:
+            assert look._cat_pre is not None and look._cat_pre["bt"] is bts_l[i + 1]
+    look.sync_updates()
+    torch.cuda.synchronize()
+    assert torch.equal(base.ps.item, look.ps.item) and torch.equal(base.ps.theta, look.ps.theta)
+    assert torch.equal(base.ps.item_m, look.ps.item_m) and torch.equal(base.ps.item_v, look.ps.item_v)
+    assert torch.equal(base.ps.iext, look.ps.iext)
+    assert int(look.ps.step.item()) == 4
+
+
 def test_scatter_add_rows_range_partitions_the_unranged_call():
     """Two ranged calls over complementary row ranges == one unranged call, bit for bit (every row is handled by
     exactly one of them, with the same arithmetic)."""

@@ -83,11 +83,17 @@ def main():
     cres = {"loss_maxabs": 0.0, "g_item_rel": 0.0, "g_theta_rel": 0.0}
     rb = cat._cat_row_bounds
     own = slice(rb[rank], rb[rank + 1])
+    plan = []
     for step, (Bs, Ts) in enumerate([(B, T), (world - 1, 3), (512, 2)]):
         pk = synth.make_index_batch(N, Bs, Ts, Nn, mwdhm, seed=50 + step)
         pl, Bl, _, _ = parallel.shard_packed(pk, Bs, Ts, Nn, rank, world)
         cbt = cat.to_device(torch.from_numpy(pl).pin_memory(), Bl, Ts, Nn)
-        lc = cat.train_step(cbt, counts=parallel.catalog_counts(Bs, world)).clone()
+        cbt.counts = parallel.catalog_counts(Bs, world)
+        plan.append((Bs, Ts, pk, cbt))
+    cres["lookahead"] = bool(cat.cat_lookahead)        # TCAR_CATALOG_LOOKAHEAD=1: next batch passed to every step
+    for step, (Bs, Ts, pk, cbt) in enumerate(plan):
+        nxt = plan[step + 1][3] if (cat.cat_lookahead and step + 1 < len(plan)) else None
+        lc = cat.train_step(cbt, nxt).clone()
         lr_ = ref.train_step(ref.to_device(torch.from_numpy(pk).pin_memory(), Bs, Ts, Nn)).clone()
         torch.cuda.synchronize()
         lo, hi = parallel.shard_sessions(Bs, rank, world)
