@@ -271,6 +271,7 @@ int tcar_adam_small(float* theta, float* m, float* v, const float* g, const int3
 /* item table rows [row0, row0 + nrows) of [N+1,256] (the pointers address the first row of the slice; iext is the
  * whole operand): also refreshes the item columns of Iext (bf16) in the same pass.  Whole table: row0 = 0,
  * nrows = N + 1; data-parallel training updates one contiguous slice per rank (parallel.py).
+ * iext_bf16 may be NULL (no refresh: a slice that runs past row N, followed by tcar_refresh_iext_items).
  * The six pad columns of the 256-float pitch are not touched.  `row_flags` (optional, [N+1] int32, indexed by
  * absolute row): rows whose flag equals the step number t were already updated by tcar_adam_item_rows and are skipped.
  * `ctas_per_sm`: grid = 148 x ctas_per_sm CTAs of 256 threads (0 = 64).  Many short-lived CTAs measured faster than

@@ -3,4 +3,5 @@
 The directory name mirrors the reference repo; import it under the alias ``tcar_b200`` through
 ``__graft_entry__.load_package()`` (the hyphens make a plain ``import`` impossible).
 """
-__all__ = ["_native", "build", "params", "model_combine", "sampler", "util", "modules", "synth", "main"]
+__all__ = ["_native", "build", "params", "model_combine", "catalog_parallel", "parallel", "sampler", "device_sampler",
+           "util", "synth", "main"]

@@ -271,7 +271,7 @@ adam_small_kernel(float* __restrict__ theta, float* __restrict__ m, float* __res
 // `flags` (optional, one int32 per table row): rows whose flag equals the current step number were already updated by
 // adam_item_rows_kernel (the rows the next batch gathers, see Seq2SeqAttNN.train_step) and are skipped here.
 __device__ __forceinline__ void store_iext_items(__nv_bfloat16* __restrict__ iext, long long row, int c, const float4 p) {
-    if (row >= 1) {
+    if (iext && row >= 1) {       // iext == NULL: the caller rebuilds the scoring operand itself
         __nv_bfloat16* dst = iext + (size_t)(row - 1) * KEXT + c;
         *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(p.x, p.y);
         if (c + 2 < H) *reinterpret_cast<__nv_bfloat162*>(dst + 2) = __floats2bfloat162_rn(p.z, p.w);

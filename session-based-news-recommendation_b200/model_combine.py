@@ -3,8 +3,8 @@
 Same constructor (`Seq2SeqAttNN(args: dict)`), same `train(sess, item_dict, train_data, neighbor_dict, args,
 test_data, saver, threshold_acc)` / `test(sess, test_data, args)` methods and the same feed-dict vocabulary; the
 TensorFlow graph underneath is replaced by hand-written sm_100a kernels called through the C ABI in
-include/tcar_b200.h.  `sess` / `saver` are accepted and ignored.  PyTorch is used for device memory, streams,
-cuBLAS calls for the small dense projections (plain library GEMMs) and torch.distributed.
+include/tcar_b200.h (the dense projections too: tcar_gemm_tf32, tcgen05 kind::tf32).  `sess` / `saver` are accepted
+and ignored.  PyTorch is used for device memory, streams and torch.distributed only.
 
 There is no CPU path: constructing the model without CUDA + libtcar_b200.so raises.
 """
@@ -448,8 +448,10 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         nv.counted_call("tcar_sqnorm_big", 2, p(self._g_slice), p(ps.norm_partial), p(ps.sqnorm_item),
                         self._g_slice.numel())
         dist.all_reduce(ps.sqnorm_item, op=dist.ReduceOp.SUM)
+        # no bf16 refresh here (iext = NULL): the slice of the LAST rank runs over the alignment rows N+1 .. rows_alloc-1,
+        # which have no row in the scoring operand, and tcar_refresh_iext_items rebuilds it after the all-gather anyway
         nv.counted_call("tcar_adam_item", 1, p(ps.item_full[lo:]), p(ps.item_m_full[lo:]), p(ps.item_v_full[lo:]),
-                        p(self._g_slice), p(ps.sqnorm_item), p(ps.step), self.lr, self.max_grad_f, p(ps.iext), lo, per,
+                        p(self._g_slice), p(ps.sqnorm_item), p(ps.step), self.lr, self.max_grad_f, None, lo, per,
                         None, 0)
         dist.all_gather_into_tensor(ps.item_full, ps.item_full[lo: lo + per])
         nv.counted_call("tcar_refresh_iext_items", 1, p(ps.item), p(ps.iext), ps.N)

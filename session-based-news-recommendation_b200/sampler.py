@@ -11,7 +11,7 @@ Differences from the reference, all documented in DESIGN.md:
   * the dwell-time bucket is clamped to 10: `bucketized` returns 11 for active_t >= 1024 s, which is out of range
     for the 11-row duration table (sampler.py:18-21; TF-CPU would raise, TF-GPU returns zeros);
   * negatives of a batch come from one vectorised `np.random.randint` call per session -- the legacy global NumPy
-    stream yields the same values as the reference's scalar calls (tests/test_host_sampler.py).
+    stream yields the same values as the reference's scalar calls (tests/test_host_logic.py).
 """
 import math
 import random

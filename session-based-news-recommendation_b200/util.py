@@ -64,4 +64,5 @@ def save_model(model, args, saver=None):
 def restore_model(model, path):
     import torch
     model.sync_updates()
-    model.ps.load_state_dict(torch.load(path, weights_only=False))
+    # the state dict holds tensors, ints and a dict of tensors only: no pickled code is ever executed
+    model.ps.load_state_dict(torch.load(path, map_location="cpu", weights_only=True))
