@@ -278,8 +278,10 @@ def kernel_rooflines(torch, nv, model, bt, peaks, traffic):
         ("score_bwd_i", "tensor", 2.0 * B * N * K_DITEM,
          lambda: nv.call("tcar_score_bwd_i", p(ws["E"]), p(model.Qs), p(ps.item_g), p(model.sq_partial), B, N,
                          ps.n_pad)),
-        # reads p, m, v, g and writes p, m, v (7 x 250 floats per row) + the bf16 refresh of the scoring operand
-        ("adam_item", "hbm", (N + 1) * (7.0 * 250 * 4 + 250 * 2),
+        # SURVEY 8d unit: reads p, m, v, g and writes p, m, v = 7 x (N+1) x 250 x 4 bytes.  The kernel also rewrites the
+        # bf16 item columns of the scoring operand in the same pass (+ (N+1) x 250 x 2 bytes, reported separately as
+        # frac_with_operand_refresh)
+        ("adam_item", "hbm", (N + 1) * 7.0 * 250 * 4,
          lambda: nv.call("tcar_adam_item", p(ps.item), p(ps.item_m), p(ps.item_v), p(ps.item_g), p(ps.sqnorm_item),
                          p(ps.step), 0.0, model.max_grad_f, p(ps.iext), 0, N + 1, None, 0)),
         ("sqnorm_item_grad", "hbm", (N + 1) * 250 * 4.0,
@@ -300,11 +302,11 @@ def kernel_rooflines(torch, nv, model, bt, peaks, traffic):
                          p(model.coef), p(ps.item), p(ps.item_g), p(model.hash_keys), p(model.hash_cnt),
                          p(model.hash_acc), p(model.entry_slot), p(model.slot_sq), model.hash_size, B, T, Nn)),
     ]
-    # eval top-k: reads tilemax [B, n_pad/128] + 512 chunk maxima and re-scores 256 candidates x 2 KB of fp32 rows
+    # eval top-k (certified selection + widening of the queries it could not certify): reads tilemax [B, n_pad/128]
+    # + 512 chunk maxima and re-scores 256 candidates x 2 KB of fp32 rows
+    model._ensure_cat_stats()
     specs.append(("eval_topk", "hbm", B * (ps.n_pad / 128 + 512) * 4.0 + B * 256 * 2 * 250 * 4.0,
-                  lambda: nv.call("tcar_eval_topk", p(wse["cmax"]), p(wse["tmax"]), p(model.a_ic), p(model.Tq), p(ps.item),
-                                  p(ps.content), p(ps.mwdhm), p(bt.label), p(model.top_ids), p(model.top_scores),
-                                  p(model.n_greater), B, N, ps.n_pad, 0)))
+                  lambda: model._topk(wse, model.a_ic, model.Tq, bt.label, model._evblock, B, N, ps.n_pad, 0)))
     out = {}
     for name, bound, work, fn in specs:
         ms = time_kernel(torch, fn, 10, flush)
@@ -314,8 +316,75 @@ def kernel_rooflines(torch, nv, model, bt, peaks, traffic):
             ach, peak, unit = work / (ms * 1e-3) / 1e9, peaks["hbm"], "GB/s"
         out[name] = {"bound": bound, "ms": ms, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
                      "peak_source": peaks["source"], "work_per_launch": work, "traffic": traffic.get(name)}
+        if name == "adam_item":
+            out[name]["frac_with_operand_refresh"] = (work + (N + 1) * 250 * 2.0) / (ms * 1e-3) / 1e9 / peak
+        if bound == "tensor":
+            out[name]["note"] = ("credited with the REFERENCE's FLOPs (K = 820 scoring / dA, 570 dItems, SURVEY 8d); the "
+                                 "kernel multiplies K = 640 / 256 columns (time-term factorisation)")
+            k_exec = {"score_bwd_i": 256.0 / K_DITEM}.get(name, 640.0 / K_REF)
+            out[name]["frac_executed_flops"] = ach * k_exec / peak
     del flush
     return out
+
+
+def multi_gpu_parity(torch, dist, synth, Model, margs, model, mwdhm, rank, world):
+    """N-GPU step == 1-GPU step, checked inside the bench run (so the driver's SCALE record carries it): ONE train step
+    on a global batch of <= 512 sessions split over the ranks (the layout being benchmarked) against the same batch on a
+    single-GPU model built here with the same initial values, then one eval batch.  Returns the "parity" object."""
+    import numpy as np
+    from tcar_b200 import parallel
+    N, Nn = margs["itemnum"], margs["neg_num"]
+    Bg, T = 64 * world if 64 * world <= 512 else 512, 5
+    packed = synth.make_index_batch(N, Bg, T, Nn, mwdhm, seed=424242)
+    pl, Bl, _, _ = parallel.shard_packed(packed, Bg, T, Nn, rank, world)
+    # fresh models: the benchmarked one has trained already
+    np.random.seed(2020)
+    multi = Model(dict(margs))
+    np.random.seed(2020)
+    single = Model(dict(margs, rank=0, world_size=1, train_parallel="dp"))
+    bt = multi.to_device(torch.from_numpy(pl).pin_memory(), Bl, T, Nn)
+    bt.counts = parallel.catalog_counts(Bg, world)
+    loss_m = multi.train_step(bt).clone()
+    multi.sync_updates()
+    multi.sync_item_table()
+    btf = single.to_device(torch.from_numpy(packed).pin_memory(), Bg, T, Nn)
+    loss_s = single.train_step(btf).clone()
+    single.sync_updates()
+    lo, hi = parallel.shard_sessions(Bg, rank, world)
+    rel = lambda x, y: float((x - y).double().norm() / (y.double().norm() + 1e-30))
+    res = {"loss_maxabs": float((loss_m - loss_s[lo:hi]).abs().max()) if hi > lo else 0.0,
+           "theta_rel": rel(multi.ps.theta, single.ps.theta), "item_rel": rel(multi.ps.item, single.ps.item),
+           "item_moment_rel": rel(multi.ps.item_m, single.ps.item_m)}
+    # evaluation: catalog sharded across the ranks vs the single-GPU result on the SAME parameters
+    single.ps.load_state_dict(multi.ps.state_dict())
+    ep = synth.make_index_batch(N, 256, 3, 0, mwdhm, seed=434343)
+    eb_m = multi.to_device(torch.from_numpy(ep).pin_memory(), 256, 3, 0)
+    eb_s = single.to_device(torch.from_numpy(ep).pin_memory(), 256, 3, 0)
+    s_lo, s_hi = multi.shard_bounds(world)[rank]
+    top_m, ngt_m, ce_m = [x.clone() for x in multi.eval_step(eb_m, shard=(s_lo, s_hi, multi.iext_shard(s_lo, s_hi)))]
+    top_s, ngt_s, ce_s = single.eval_step(eb_s)
+    hit = ngt_s < 20
+    res["eval_top20_equal"] = bool(torch.equal(top_m, top_s))
+    res["eval_rank_equal"] = bool(torch.equal(hit, ngt_m < 20) and torch.equal(ngt_m[hit], ngt_s[hit]))
+    res["eval_ce_maxabs"] = float((ce_m - ce_s).abs().max())
+    ok = (res["loss_maxabs"] < 1e-4 and res["theta_rel"] < 1e-4 and res["item_rel"] < 1e-4 and res["eval_top20_equal"]
+          and res["eval_rank_equal"] and res["eval_ce_maxabs"] < 1e-3)
+    flag = torch.tensor([1 if ok else 0], device=model.dev, dtype=torch.int32)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    worst = torch.tensor([res["loss_maxabs"], res["theta_rel"], res["item_rel"], res["item_moment_rel"],
+                          res["eval_ce_maxabs"]], device=model.dev, dtype=torch.float64)
+    dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+    for k, v in zip(("loss_maxabs", "theta_rel", "item_rel", "item_moment_rel", "eval_ce_maxabs"), worst.tolist()):
+        res[k] = v
+    res["ok"] = bool(int(flag.item()))
+    res["what"] = (f"one {margs['train_parallel']} train step on a global batch of {Bg} sessions over {world} GPUs vs the same "
+                   f"batch on one GPU (loss, parameters after Adam), then one catalog-sharded eval batch of 256 queries vs "
+                   f"one GPU (top-20 ids bit-equal, ranks, cross loss); worst value over the ranks")
+    if getattr(multi, "close_peers", None):
+        multi.close_peers()
+    del multi, single
+    torch.cuda.empty_cache()
+    return res
 
 
 def run_b200(a):
@@ -482,6 +551,7 @@ def run_b200(a):
     e1.record()
     barrier()
     eval_ms = max_over_ranks(e0.elapsed_time(e1))
+    eval_uncertified = float(model.uncertain[:B].float().mean().item())      # last batch: share sent to the widening pass
     e0.record()
     bt = model.to_device(ehost[0], B, Ts[0], 0)
     for i in range(K):
@@ -507,6 +577,10 @@ def run_b200(a):
         barrier()
         eval_qp_ms = max_over_ranks(e0.elapsed_time(e1))
     clk = clocks.stop() if rank == 0 else None
+    eval_queries = B * K
+    eval_layout = ("catalog sharded across ranks, one all-gather of result blocks + merge per batch" if world > 1
+                   else "single GPU")
+    parity = multi_gpu_parity(torch, dist, synth, Seq2SeqAttNN, margs, model, mwdhm, rank, world) if world > 1 else None
 
     # ---- the loop a user runs (Seq2SeqAttNN.train): reference-API Sampler on a host thread -> pinned ring -> H2D ->
     # train_step, on an in-memory synthetic split with Globo-like session lengths
@@ -628,21 +702,23 @@ def run_b200(a):
                                                 **({"layout_note": layout_note} if layout_note else {})),
             "e2e": {"value": sessions / (e2e_ms * 1e-3), "unit": "sessions/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / K},
-            "eval": {"metric": "full-catalog top-20 eval queries/sec", "value": B * K / (eval_ms * 1e-3),
-                     "unit": "queries/s", "ms_per_step": eval_ms / K,
-                     "scaling": "strong (catalog sharded across ranks)" if world > 1 else "single",
-                     "e2e": {"value": B * K / (eval_e2e_ms * 1e-3), "unit": "queries/s",
-                             "h2d_bytes_per_step": sum(ehost[i % nbatch].numel() for i in range(K)) * 4 / K,
-                             "d2h_bytes_per_step": B * (20 + 1 + 1) * 4}},
-            "eval_query_parallel": None if eval_qp_ms is None else {
-                "note": "queries sharded across ranks instead of the catalog (no collective); not the north_star layout",
-                "value": world * B * K / (eval_qp_ms * 1e-3), "unit": "queries/s", "ms_per_step": eval_qp_ms / K},
             "t20": {"note": "same measurement with every batch at the reference --maxlen (T = 20)",
                     "value": sessions / (t20_ms * 1e-3), "ms_per_step": t20_ms / K,
                     "e2e_value": sessions / (t20_e2e_ms * 1e-3), "unit": "sessions/s"},
             "train_loop": train_loop,
             "gpu_launches": launches, "launches_per_step": launches / K, "loss_last_step": loss_last,
-            "clocks": clk, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu_baseline}
+            "clocks": clk, "kernels": kernels, "roofline": roof, "cpu_baseline": cpu_baseline,
+            "parity": parity,
+            "eval_query_parallel": None if eval_qp_ms is None else {
+                "note": "queries sharded across ranks instead of the catalog (no collective); not the north_star layout",
+                "value": world * B * K / (eval_qp_ms * 1e-3), "unit": "queries/s", "ms_per_step": eval_qp_ms / K},
+            # last, so that a consumer keeping only the tail of the line keeps the second half of BASELINE's metric
+            "eval": {"metric": "full-catalog top-20 eval queries/sec", "value": eval_queries / (eval_ms * 1e-3),
+                     "unit": "queries/s", "ms_per_step": eval_ms / K, "queries_per_step": eval_queries / K,
+                     "layout": eval_layout, "uncertified_share": eval_uncertified,
+                     "e2e": {"value": eval_queries / (eval_e2e_ms * 1e-3), "unit": "queries/s",
+                             "h2d_bytes_per_step": sum(ehost[i % nbatch].numel() for i in range(K)) * 4 / K,
+                             "d2h_bytes_per_step": B * (20 + 1 + 1) * 4}}}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

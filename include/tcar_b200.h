@@ -33,11 +33,26 @@ extern "C" {
 #define TCAR_TOPK 20      /* cutoff                          (model_combine.py:296,301)                */
 #define TCAR_CHUNK 8      /* items per eval chunk-max                                                   */
 #define TCAR_NCAND_CHUNKS 32 /* chunks re-scored per query (256 candidate items)                        */
+#define TCAR_MAX_EVAL_TILES 32768 /* 128-item tiles per catalog (shard) tcar_eval_topk_certified handles: 4.2 M items */
+/* One shard's evaluation results for <= 512 queries, as ONE contiguous block of 32-bit words (what a rank sends in the
+ * single exchange of the catalog-sharded evaluation): planes at fixed offsets, each in the layout the kernels write. */
+#define TCAR_EVAL_OFF_SCORES 0                          /* float [512][20]  top-20 scores                           */
+#define TCAR_EVAL_OFF_IDS (TCAR_QROWS * TCAR_TOPK)      /* int32 [512][20]  top-20 global item ids (-1 = empty)      */
+#define TCAR_EVAL_OFF_NGT (2 * TCAR_QROWS * TCAR_TOPK)  /* int32 [512]      #(S > S[label]) among the shard's items  */
+#define TCAR_EVAL_OFF_SUMEXP (TCAR_EVAL_OFF_NGT + TCAR_QROWS)   /* float [512] softmax partial sum                   */
+#define TCAR_EVAL_OFF_ROWMAX (TCAR_EVAL_OFF_SUMEXP + TCAR_QROWS) /* float [512] largest exponent argument (guard)    */
+#define TCAR_EVAL_BLOCK_WORDS (TCAR_EVAL_OFF_ROWMAX + TCAR_QROWS)
 #define TCAR_NORM_SPLIT 8    /* partial sums per tensor written by tcar_sqnorm_segments                     */
 #define TCAR_TABLE_GRAD_CHUNKS 148   /* max click chunks (CTAs) of tcar_small_table_grads pass 1               */
 #define TCAR_TABLE_GRAD_PART 19600   /* floats of partial sums per chunk: 139x64 + 11x64 + 40x250              */
 
 #define TCAR_CLUSTER_PAIR (-2) /* tcar_score_fwd `cluster` value: CTA pair, tcgen05.mma.cta_group::2 (M = 256)   */
+
+/* Overflow guard of the full-catalog softmax: the scoring kernel shifts the exponent by the label score c_b; a row
+ * whose largest argument (S - c_b) log2(e) exceeds this limit (55 nats) is re-run shifted by its maximum, which is what
+ * TF's sparse_softmax_cross_entropy_with_logits (model_combine.py:145) always does.  Below the limit the sums of up to
+ * 2^19 terms <= 2^80 and everything the backward GEMMs derive from them stay far inside fp32 / bf16 range. */
+#define TCAR_EXP_LIMIT2 80.0f
 
 #define TCAR_ERR_ARG (-1)
 #define TCAR_ERR_DRIVER (-2)
@@ -107,11 +122,27 @@ int tcar_assemble_batch(const int32_t* rows, const int32_t* seq, const int32_t* 
 int tcar_score_fwd(const void* q_bf16, const void* iext_bf16, const float* c_ref, void* e_out, float* rowsum_part,
                    float* chunkmax, float* tilemax, int n_rows, int n_items, int n_pad, int mode, int cluster,
                    void* stream);
+/* The same with the softmax overflow guard (TCAR_EXP_LIMIT2), run as two passes around tcar_ce_finish_guarded:
+ *   pass 1  rowmax_part [n_pad/128][512] != NULL, rowmax == NULL: also leaves the largest exponent argument
+ *           (S - c_ref) log2(e) of every (128-item block, session) pair;
+ *   pass 2  rowmax [512] != NULL (what tcar_ce_finish_guarded pass 1 reduced, or its maximum over the ranks of a
+ *           catalog-sharded step): rows above the limit are shifted by rowmax[b] on top of c_ref[b], so their largest
+ *           term is 2^0.  CTAs none of whose 256 session rows need it return immediately (the common case costs one
+ *           empty launch); the others rewrite E / rowsum_part / chunkmax -- identical values for the quiet rows. */
+int tcar_score_fwd_guarded(const void* q_bf16, const void* iext_bf16, const float* c_ref, void* e_out,
+                           float* rowsum_part, float* chunkmax, float* tilemax, float* rowmax_part, const float* rowmax,
+                           int n_rows, int n_items, int n_pad, int mode, int cluster, void* stream);
 int tcar_score_fwd_tiles(int n_pad);
 
 /* (4a) softmax cross-entropy from the partial sums (model_combine.py:145): sumexp[b] = sum_tiles part,
  *      ce[b] = log(sumexp[b]) (because c_ref is the label score). Fixed summation order. */
 int tcar_ce_finish(const float* rowsum_part, float* sumexp, float* ce, int n_tiles, int B, void* stream);
+/* With the overflow guard.  pass 1: sums + rowmax[b] = max_tiles rowmax_part (log2 units; ce may be inf for a row above
+ * TCAR_EXP_LIMIT2 until pass 2).  pass 2 (after tcar_score_fwd_guarded re-ran with `rowmax`): rows above the limit are
+ * summed again, ce[b] = log(sumexp[b]) + rowmax[b] ln 2 = logsumexp(S_b) - c_b; other rows keep their pass-1 values.
+ * pass 3: rowmax only (the catalog-sharded step reduces it over the ranks first).  pass 0 == tcar_ce_finish. */
+int tcar_ce_finish_guarded(const float* rowsum_part, const float* rowmax_part, float* sumexp, float* ce, float* rowmax,
+                           int n_tiles, int B, int pass, void* stream);
 /* The same fixed-order sum only, stored with a stride: out[b * out_stride] = sum_tiles part[tile][b]. */
 int tcar_rowsum_finish(const float* rowsum_part, float* out, int out_stride, int n_tiles, int B, void* stream);
 
@@ -351,6 +382,19 @@ int tcar_scatter_add_rows_groups(const int32_t* ids, long long ids_stride, const
                                  int hash_size, const int* n_rows, int groups, int T, int Nn, int row_lo, int row_hi,
                                  void* stream);
 
+/* Softmax overflow guard for the session groups of a catalog-sharded step (see tcar_score_fwd_guarded):
+ *   tcar_score_fwd_groups_guarded(..., rowmax_part, NULL, ...)     pass 1, also leaves per-block exponent maxima
+ *   tcar_rowmax_groups                                             rowmax [groups][512] = max over the blocks (1 launch)
+ *   -- across ranks: all-reduce(MAX) of rowmax, every owner must shift a session row by the same amount --
+ *   tcar_score_fwd_groups_guarded(..., NULL, rowmax, ...)          pass 2, empty launches unless a row is above the limit
+ * and the caller adds rowmax[b] ln 2 to log(sum) for the rows above TCAR_EXP_LIMIT2. */
+int tcar_score_fwd_groups_guarded(const void* q_bf16, long long q_stride, const float* c_ref, long long c_stride,
+                                  const void* iext_bf16, void* e_out, long long e_stride, float* rowsum_part,
+                                  long long part_stride, float* rowmax_part, const float* rowmax, const int* n_rows,
+                                  int groups, int n_items, int n_pad, int cluster, void* stream);
+int tcar_rowmax_groups(const float* rowmax_part, long long part_stride, float* rowmax, int n_tiles, const int* n_rows,
+                       int groups, void* stream);
+
 /* (6) evaluation (model_combine.py:283-306, util.py:8-18): select the 32 best 128-item tiles per query from tilemax,
  *     then the 32 best 8-item chunks among their 512 chunks from chunkmax (exactly the 32 best chunks overall, ties
  *     to the lower index), re-score their 256 items exactly in fp32, return top-20 ids/scores ordered by (score desc, id asc) and
@@ -361,9 +405,34 @@ int tcar_eval_topk(const float* chunkmax, const float* tilemax, const float* a_i
                    const float* content, const int32_t* mwdhm, const int32_t* label, int32_t* top_ids,
                    float* top_scores, int32_t* n_greater, int B, int N, int n_pad, int item_offset, void* stream);
 
+/* The same, CERTIFIED: cat_stats[2] (tcar_catalog_stats over the items this call scores, or any superset) bounds the
+ * bf16-GEMM error of every chunk maximum; a query whose best un-re-scored chunk could still reach its 20th exact score
+ * is flagged in uncertain[b] (1 / 0) with the bound tau[b], and tcar_eval_topk_widen completes it.  Together the two
+ * calls return the exact top-20 (np.argsort(pred)[::-1][:20], model_combine.py:301, ties to the lower id) and the exact
+ * rank whenever rank <= 20 -- not "with high probability". */
+int tcar_eval_topk_certified(const float* chunkmax, const float* tilemax, const float* a_ic, const float* Tq,
+                             const float* item, const float* content, const int32_t* mwdhm, const int32_t* label,
+                             int32_t* top_ids, float* top_scores, int32_t* n_greater, int B, int N, int n_pad,
+                             int item_offset, const float* cat_stats, int32_t* uncertain, float* tau, void* stream);
+/* Second stage: for every flagged query, re-scores ALL chunks whose maximum reaches tau[b] (any number of them, 32 at a
+ * time) and rewrites its top_ids / top_scores / n_greater; certified queries are untouched (their CTA returns). */
+int tcar_eval_topk_widen(const float* chunkmax, const float* tilemax, const float* a_ic, const float* Tq,
+                         const float* item, const float* content, const int32_t* mwdhm, const int32_t* label,
+                         const int32_t* uncertain, const float* tau, int32_t* top_ids, float* top_scores,
+                         int32_t* n_greater, int B, int N, int n_pad, int item_offset, void* stream);
+/* out2[0] = max ||[item | content] row||_2, out2[1] = max ||row - bf16(row)||_2 over table rows [row_lo, row_hi)
+ * (row = item id + 1).  Needed again only after the item table changed. */
+int tcar_catalog_stats(const float* item, const float* content, int row_lo, int row_hi, float* out2, void* stream);
+
 /* merge G per-shard top-20 lists [G][B][20] into the global top-20 (score desc, id asc). */
 int tcar_topk_merge(const int32_t* ids, const float* scores, int32_t* out_ids, float* out_scores, int G, int B,
                     void* stream);
+/* The whole reduction of the catalog-sharded evaluation in one launch: `blocks` = G result blocks (layout
+ * TCAR_EVAL_OFF_*, `block_words` 32-bit words apart -- the receive buffer of ONE all-gather / all-to-all) ->
+ * global top-20 (score desc, id asc), summed rank counts, and ce[b] = logsumexp(S_b) - S_b[label] combined from the
+ * shards' partial sums and their own exponent shifts (util.py:14, model_combine.py:145,301). */
+int tcar_eval_merge(const void* blocks, long long block_words, int32_t* out_ids, float* out_scores, int32_t* out_ngt,
+                    float* out_ce, int G, int B, void* stream);
 
 #ifdef __cplusplus
 }

@@ -83,8 +83,12 @@ def clip_rows(x: torch.Tensor) -> torch.Tensor:
     return x / torch.clamp(norm, min=1.0)
 
 
-def embedding_lookup(table: torch.Tensor, ids: torch.Tensor, max_norm: bool = True) -> torch.Tensor:
+def embedding_lookup(table: torch.Tensor, ids: torch.Tensor, max_norm: bool = True, tap=None) -> torch.Tensor:
+    """tap (optional list): collects the gathered rows, whose gradients are the VALUES of the tf.IndexedSlices
+    gradient this lookup contributes (one slice per looked-up id, duplicates not summed)."""
     rows = table[ids.long()]
+    if tap is not None:
+        tap.append(rows)
     return clip_rows(rows) if max_norm else rows
 
 
@@ -124,24 +128,31 @@ def count_alpha_s(p, P, C):
     return normalizer(e)
 
 
+LOOKUP_ONLY = ("pos", "month", "day", "week", "hour", "minute", "dur")   # read through embedding_lookup only
+
+
 def forward(p: Dict[str, torch.Tensor], content: torch.Tensor, mwdhm: torch.Tensor, batch: Dict[str, torch.Tensor],
-            want_scores: bool = True) -> Dict[str, torch.Tensor]:
+            want_scores: bool = True, taps: Optional[Dict[str, list]] = None) -> Dict[str, torch.Tensor]:
     """The TCAR graph, model_combine.py:52-147, in evaluation order.
 
     batch: seq [B,T] (1-based), pm pd pw ph pmi [B,T], cw ch [B], gap [B,T], label [B] (0-based),
            neg [B,Nn] (0-based, optional).  mwdhm [N,5] int.  content [N+1,250] frozen."""
     seq = batch["seq"].long()
     B, T = seq.shape
-    E_i = embedding_lookup(p["item"], seq) + embedding_lookup(p["pos"], torch.arange(T)).unsqueeze(0)   # :54-65
+
+    def look(name, ids):
+        return embedding_lookup(p[name], ids, tap=None if taps is None else taps.setdefault(name, []))
+
+    # the reference looks dec_pos up with a tiled [B,T] index (model_combine.py:57): B*T slices, not T
+    pos_ids = torch.arange(T).unsqueeze(0).expand(B, T)
+    E_i = embedding_lookup(p["item"], seq) + look("pos", pos_ids)                                       # :54-65
     E_c = embedding_lookup(content, seq)                                                                # :67-68
-    P = torch.cat([embedding_lookup(p["month"], batch["pm"]), embedding_lookup(p["day"], batch["pd"]),
-                   embedding_lookup(p["week"], batch["pw"]), embedding_lookup(p["hour"], batch["ph"]),
-                   embedding_lookup(p["minute"], batch["pmi"])], -1)                                    # :73-84
-    cand_t = torch.cat([embedding_lookup(p["month"], mwdhm[:, 0]), embedding_lookup(p["day"], mwdhm[:, 1]),
-                        embedding_lookup(p["week"], mwdhm[:, 2]), embedding_lookup(p["hour"], mwdhm[:, 3]),
-                        embedding_lookup(p["minute"], mwdhm[:, 4])], -1)                                # :86-92
-    ct = torch.cat([embedding_lookup(p["week"], batch["cw"]), embedding_lookup(p["hour"], batch["ch"])], -1)  # :94-97
-    D = embedding_lookup(p["dur"], batch["gap"])                                                        # :106-107
+    P = torch.cat([look("month", batch["pm"]), look("day", batch["pd"]), look("week", batch["pw"]),
+                   look("hour", batch["ph"]), look("minute", batch["pmi"])], -1)                        # :73-84
+    cand_t = torch.cat([look("month", mwdhm[:, 0]), look("day", mwdhm[:, 1]), look("week", mwdhm[:, 2]),
+                        look("hour", mwdhm[:, 3]), look("minute", mwdhm[:, 4])], -1)                    # :86-92
+    ct = torch.cat([look("week", batch["cw"]), look("hour", batch["ch"])], -1)                          # :94-97
+    D = look("dur", batch["gap"])                                                                       # :106-107
     X = torch.cat([E_i, E_c], -1)                                                                       # :111
     alpha = count_alpha_m(p, X, E_c, D, ct)                                                             # :112-117
     pooled = torch.matmul(alpha.unsqueeze(1), X).squeeze(1)                                             # modules.py:116-117
@@ -195,20 +206,48 @@ class TFAdam:
             params[k] -= lr_t * self.m[k] / (self.v[k].sqrt() + 1e-8)
 
 
-def loss_and_grads(p, content, mwdhm, batch):
-    """Gradients of sum_b loss_b (optimizer.compute_gradients on a [B,1] tensor sums it; model_combine.py:156)."""
+def loss_and_grads(p, content, mwdhm, batch, tf_slice_norms: bool = False):
+    """Gradients of sum_b loss_b (optimizer.compute_gradients on a [B,1] tensor sums it; model_combine.py:156).
+
+    tf_slice_norms=True additionally returns, per tensor, the norm tf.clip_by_norm (model_combine.py:158-160) sees
+    in TensorFlow 1.x: for the seven tables read only through embedding_lookup (LOOKUP_ONLY) the gradient is a
+    tf.IndexedSlices whose values are the per-lookup slices, CONCATENATED over the lookups (publish time of the
+    clicks, of the N candidates, click context) and not summed per row, and clip_by_norm norms those values; every
+    other tensor (item_emb included: it also feeds the dense [1:] slice) has a dense gradient."""
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
-    out = forward(leaves, content, mwdhm, batch, want_scores=False)
+    taps: Dict[str, list] = {} if tf_slice_norms else None
+    out = forward(leaves, content, mwdhm, batch, want_scores=False, taps=taps)
+    if tf_slice_norms:
+        for rows in (r for lst in taps.values() for r in lst):
+            rows.retain_grad()
     out["loss"].sum().backward()
     grads = {k: (leaves[k].grad if leaves[k].grad is not None else torch.zeros_like(leaves[k])) for k in PARAM_ORDER}
-    return {k: v.detach() for k, v in out.items()}, grads
+    outs = {k: v.detach() for k, v in out.items()}
+    if not tf_slice_norms:
+        return outs, grads
+    norms = {k: float(torch.sqrt((g.double() ** 2).sum())) for k, g in grads.items()}
+    for name in LOOKUP_ONLY:
+        norms[name] = math.sqrt(sum(float((r.grad.double() ** 2).sum()) for r in taps[name] if r.grad is not None))
+    return outs, grads, norms
 
 
-def train_step(p, adam: TFAdam, content, mwdhm, batch, max_grad: Optional[float] = 150.0):
-    """One sess.run([loss, global_step, train_op]) (model_combine.py:231-234); updates `p` in place."""
-    out, grads = loss_and_grads(p, content, mwdhm, batch)
+def train_step(p, adam: TFAdam, content, mwdhm, batch, max_grad: Optional[float] = 150.0,
+               tf_slice_norms: bool = False):
+    """One sess.run([loss, global_step, train_op]) (model_combine.py:231-234); updates `p` in place.
+
+    Clip norm: by default the norm of the aggregated (dense) gradient of every tensor -- what the CUDA path computes.
+    tf_slice_norms=True uses TensorFlow's reading for the lookup-only tables (see loss_and_grads).  The two agree
+    whenever neither norm exceeds max_grad (then nothing is clipped); when a clip fires on one of those seven tables
+    they differ in the clip FACTOR only.  This is a documented deviation of the product ("Oracle")."""
+    if tf_slice_norms:
+        out, grads, norms = loss_and_grads(p, content, mwdhm, batch, tf_slice_norms=True)
+    else:
+        out, grads = loss_and_grads(p, content, mwdhm, batch)
     if max_grad is not None:
-        grads = {k: clip_by_norm(g, float(max_grad)) for k, g in grads.items()}
+        if tf_slice_norms:
+            grads = {k: g * float(max_grad) / max(norms[k], float(max_grad)) for k, g in grads.items()}
+        else:
+            grads = {k: clip_by_norm(g, float(max_grad)) for k, g in grads.items()}
     adam.step(p, grads)
     return out, grads
 
@@ -287,3 +326,27 @@ def merge_topk(ids: np.ndarray, scores: np.ndarray, k: int = 20):
         out_i[b, : len(order)] = i[order]
         out_s[b, : len(order)] = s[order]
     return out_i, out_s
+
+
+EXP_LIMIT2 = 80.0          # TCAR_EXP_LIMIT2 (include/tcar_b200.h)
+
+
+def merge_eval_blocks(blocks: np.ndarray, B: int, k: int = 20):
+    """Reference of tcar_eval_merge: G result blocks (layout TCAR_EVAL_OFF_*: scores [512,k] f32 | ids [512,k] i32 |
+    n_greater [512] i32 | sumexp [512] f32 | rowmax [512] f32, as float32 words) -> global top-k (score desc, id asc),
+    summed rank counts (util.py:14) and CE = logsumexp(S) - S[label] (model_combine.py:145) from the shards' partial
+    sums, each relative to its own exponent shift (rowmax, log2 units, applied only above EXP_LIMIT2)."""
+    blocks = np.ascontiguousarray(blocks, dtype=np.float32)
+    G = blocks.shape[0]
+    bi = blocks.view(np.int32)
+    Q = 512
+    sc = blocks[:, : Q * k].reshape(G, Q, k)[:, :B]
+    ids = bi[:, Q * k: 2 * Q * k].reshape(G, Q, k)[:, :B]
+    ngt = bi[:, 2 * Q * k: 2 * Q * k + Q][:, :B].astype(np.int64).sum(0)
+    sumexp = blocks[:, 2 * Q * k + Q: 2 * Q * k + 2 * Q][:, :B].astype(np.float64)
+    rowmax = blocks[:, 2 * Q * k + 2 * Q: 2 * Q * k + 3 * Q][:, :B].astype(np.float64)
+    shift = np.where(rowmax > EXP_LIMIT2, rowmax, 0.0)
+    M = shift.max(0)
+    ce = np.log((sumexp * np.exp2(shift - M)).sum(0)) + M * math.log(2.0)
+    out_i, out_s = merge_topk(ids, sc, k)
+    return out_i, out_s, ngt, ce

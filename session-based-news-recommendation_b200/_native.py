@@ -10,6 +10,9 @@ LIB_PATH = os.path.join(HERE, "libtcar_b200.so")
 
 H, HP, TH, XW, PW, NBINS, KEXT, QROWS, MAXT, TOPK, CHUNK, NCAND_CHUNKS = 250, 256, 64, 500, 320, 139, 640, 512, 40, 20, 8, 32
 NORM_SPLIT = 8
+EXP_LIMIT2 = 80.0        # TCAR_EXP_LIMIT2
+EVAL_OFF_SCORES, EVAL_OFF_IDS, EVAL_OFF_NGT = 0, QROWS * TOPK, 2 * QROWS * TOPK      # TCAR_EVAL_OFF_*
+EVAL_OFF_SUMEXP, EVAL_OFF_ROWMAX, EVAL_BLOCK_WORDS = EVAL_OFF_NGT + QROWS, EVAL_OFF_NGT + 2 * QROWS, EVAL_OFF_NGT + 3 * QROWS
 MAX_PEERS, PEER_HANDLE_BYTES = 16, 64      # TCAR_MAX_PEERS, TCAR_PEER_HANDLE_BYTES
 BIN_OFF = (0, 13, 45, 53, 78, 139)
 CLUSTER_PAIR = -2      # TCAR_CLUSTER_PAIR: tcar_score_fwd with tcgen05.mma.cta_group::2 CTA pairs
@@ -26,8 +29,10 @@ SIGNATURES = {
     "tcar_clip_time_tables": [_P] * 7 + [_P],
     "tcar_build_query": [_P] * 10 + [_I, _P],
     "tcar_score_fwd": [_P] * 7 + [_I] * 5 + [_P],
+    "tcar_score_fwd_guarded": [_P] * 9 + [_I] * 5 + [_P],
     "tcar_score_fwd_tiles": [_I],
     "tcar_ce_finish": [_P] * 3 + [_I, _I, _P],
+    "tcar_ce_finish_guarded": [_P] * 5 + [_I, _I, _I, _P],
     "tcar_neg_loss": [_P] * 9 + [_I, _I, _P],
     "tcar_score_bwd_q_splits": [_I, _I],
     "tcar_score_bwd_q": [_P] * 4 + [_I, _I, _P],
@@ -53,6 +58,8 @@ SIGNATURES = {
     "tcar_peer_fetch_rows": [_P, _P, _P, _I, _I, _I, _P, _P, _I, _I, _P, _P],
     "tcar_rowsum_finish": [_P, _P, _I, _I, _I, _P],
     "tcar_score_fwd_groups": [_P, _LL, _P, _LL, _P, _P, _LL, _P, _LL, _P, _I, _I, _I, _I, _P],
+    "tcar_score_fwd_groups_guarded": [_P, _LL, _P, _LL, _P, _P, _LL, _P, _LL, _P, _P, _P, _I, _I, _I, _I, _P],
+    "tcar_rowmax_groups": [_P, _LL, _P, _I, _P, _I, _P],
     "tcar_score_bwd_q_multi_part_elems": [_I],
     "tcar_score_bwd_q_multi": [_P, _LL, _P, _P, _P, _P, _I, _I, _P],
     "tcar_score_bwd_q_groups": [_P, _LL, _P, _P, _P, _LL, _P, _LL, _I, _P, _I, _I, _P],
@@ -67,7 +74,11 @@ SIGNATURES = {
     "tcar_adam_item_rows_groups": [_P] * 6 + [_F, _F, _P, _P, _LL, _P, _I, _I, _I, _P, _I, _I, _P],
     "tcar_refresh_iext_items": [_P, _P, _I, _P],
     "tcar_eval_topk": [_P] * 11 + [_I] * 4 + [_P],
+    "tcar_eval_topk_certified": [_P] * 11 + [_I] * 4 + [_P] * 3 + [_P],
+    "tcar_eval_topk_widen": [_P] * 13 + [_I] * 4 + [_P],
+    "tcar_catalog_stats": [_P, _P, _I, _I, _P, _P],
     "tcar_topk_merge": [_P] * 4 + [_I, _I, _P],
+    "tcar_eval_merge": [_P, _LL, _P, _P, _P, _P, _I, _I, _P],
 }
 
 _lib = None

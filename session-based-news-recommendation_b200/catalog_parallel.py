@@ -24,6 +24,7 @@ or a checkpoint).  With world_size == 1, args["catalog_virtual_shards"] = V make
 walk them one after the other -- the same kernels with the same shard offsets, used by the single-GPU parity test.
 """
 import ctypes as C
+import math
 
 import torch
 
@@ -82,6 +83,8 @@ class CatalogShardedTraining:
         self._cat_pre = None               # {"bt", "counts", "L"} of the batch whose ids / rows / forward are ahead
         self._bar = torch.zeros(1, device=dev)
         self._sumexp_all = torch.zeros(R, QROWS, device=dev)
+        self._rowmax_all = torch.zeros(R, QROWS, device=dev)          # largest exponent argument of every session row
+        self._rowmax_tmp = torch.zeros(R, QROWS, device=dev) if len(self._cat_shards) > 1 else None
         self._dq_all = torch.zeros(R, QROWS, KEXT, device=dev)
         self._qs_all = torch.zeros(R, QROWS, HP, device=dev, dtype=torch.bfloat16) if R > 1 else self.Qs.view(1, QROWS, HP)
         self._dq_tmp = torch.zeros(R, QROWS, KEXT, device=dev) if len(self._cat_shards) > 1 else None
@@ -99,6 +102,7 @@ class CatalogShardedTraining:
             # one E / partial-sum block per session group, a fixed stride apart (tcar_score_*_groups)
             sh["E"] = torch.zeros(R, QROWS * sh["n_pad"], device=dev, dtype=torch.bfloat16)
             sh["part"] = torch.zeros(R, tiles * QROWS, device=dev)
+            sh["pmax"] = torch.zeros(R, tiles * QROWS, device=dev)          # softmax overflow guard, pass 1
             splits = max(nv.lib().tcar_score_bwd_q_splits(b, sh["n_pad"]) for b in (1, 129, 257, 385))
             qelems = splits * QROWS * KEXT
             if R > 1:
@@ -193,6 +197,7 @@ class CatalogShardedTraining:
         self.sync_updates()                # pending table-wide Adam (side stream) / prefetched forward (ahead stream)
         self._prefetched = None
         self._item_table_synced = False
+        ps.version += 1
         groups = [g for g in range(R) if counts[g] > 0]
         trace = self._cat_trace
 
@@ -230,10 +235,28 @@ class CatalogShardedTraining:
         qc_ptr = self._qc_all.data_ptr()
         shards = [sh for sh in self._cat_shards if sh["hi"] > sh["lo"]]
         multi = len(self._cat_shards) > 1
-        for sh in shards:
-            nv.counted_call("tcar_score_fwd_groups", ng, C.c_void_p(qc_ptr), QC_BYTES // 2, C.c_void_p(qc_ptr + Q_BYTES),
-                            QC_BYTES // 4, p(sh["iext"]), p(sh["E"]), QROWS * sh["n_pad"], p(sh["part"]),
-                            sh["tiles"] * QROWS, cnt, R, sh["hi"] - sh["lo"], sh["n_pad"], self._cluster_for(Bmax))
+        guard = self.softmax_guard
+
+        def score_fwd(sh, pmax, rowmax):
+            nv.counted_call("tcar_score_fwd_groups_guarded", ng, C.c_void_p(qc_ptr), QC_BYTES // 2,
+                            C.c_void_p(qc_ptr + Q_BYTES), QC_BYTES // 4, p(sh["iext"]), p(sh["E"]), QROWS * sh["n_pad"],
+                            p(sh["part"]), sh["tiles"] * QROWS, pmax, rowmax, cnt, R, sh["hi"] - sh["lo"], sh["n_pad"],
+                            self._cluster_for(Bmax))
+
+        for k, sh in enumerate(shards):
+            score_fwd(sh, p(sh["pmax"]) if guard else None, None)
+            if guard:
+                dst = self._rowmax_all if k == 0 else self._rowmax_tmp
+                nv.counted_call("tcar_rowmax_groups", 1, p(sh["pmax"]), sh["tiles"] * QROWS, p(dst), sh["tiles"], cnt, R)
+                if k > 0:
+                    torch.maximum(self._rowmax_all, self._rowmax_tmp, out=self._rowmax_all)
+        if guard:
+            # overflow guard of the softmax (TCAR_EXP_LIMIT2): every owner must shift a session row by the same amount,
+            # so the row maxima are reduced over the ranks; pass 2 is `ng` empty launches unless a row is above the limit
+            if on:
+                dist.all_reduce(self._rowmax_all, op=dist.ReduceOp.MAX)
+            for sh in shards:
+                score_fwd(sh, None, p(self._rowmax_all))
         mark("score_fwd")
         # ---- dQ partial sums over the owned items for every group; the softmax partial sums travel in the zero pad
         # column of dQ, so ONE reduce-scatter hands both to the sessions' ranks (model_combine.py:145: CE = log sum)
@@ -255,6 +278,10 @@ class CatalogShardedTraining:
         if B > 0:
             self.sumexp[:B].copy_(dq_raw[:B, KEXT - 1])
             torch.log(self.sumexp[:B], out=self.ce[:B])
+            if guard:
+                # rows the guard shifted: CE = log(sum) + shift ln 2 (shift in log2 units)
+                rm = self._rowmax_all[me, :B]
+                self.ce[:B].add_(torch.where(rm > nv.EXP_LIMIT2, rm, torch.zeros_like(rm)), alpha=math.log(2.0))
             nv.counted_call("tcar_neg_loss", 1, p(self.a_ic), p(ps.item), p(ps.content), p(bt.neg), p(self.ce),
                             p(self.negloss), p(self.loss), p(self.coef), p(self.dA_neg), B, Nn)
             nv.counted_call("tcar_score_bwd_finish", 1, p(dq_raw), p(self.sumexp), p(self.dA_neg), p(self.a_ic),

@@ -6,7 +6,15 @@
 // (12 chunks of slack for bf16 rounding), re-score their 256 items exactly in fp32 and sort those by
 // (score desc, id asc).  Ties therefore resolve to the lower item id (north_star), which agrees with the
 // reference on tie-free inputs.
+//
+// The slack is then CERTIFIED per query: with eps_b a rigorous bound on |bf16-GEMM score - exact fp32 score| (from the
+// query's own rounding error and the catalog's largest row norm / rounding-error norm, tcar_catalog_stats), an item
+// outside the re-scored chunks can only belong to the top-20 if its chunk maximum reaches s20 - eps_b (s20 = the 20th
+// exact score found).  Queries whose best unselected chunk stays below that bound are done; the others are flagged and
+// tcar_eval_topk_widen re-scores EVERY chunk at or above the bound (streaming, any number of them), so the result is
+// the exact top-20 either way.
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <math.h>
 #include <stdint.h>
 #include "tcar_b200.h"
@@ -113,6 +121,51 @@ __device__ __forceinline__ void select_top(const float* __restrict__ vals, int n
     __syncthreads();
 }
 
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
+
+__device__ __forceinline__ float block_sum_e(float v, float* red) {
+    v = warp_sum_e(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    return t;
+}
+
+// eps_b >= |S_gemm[b,n] - S_exact[b,n]| for every item n of the catalog the statistics were taken over:
+//   S_gemm = bf(q) . bf(i) + sum_k bf(Tq[k, idx_k])   (exact products, fp32 accumulation on the tensor cores)
+//   S_exact = q . i + sum_k Tq[k, idx_k]              (fp32 FMA chain, exact_score_e)
+//   q . i - bf(q) . bf(i) = dq . i + bf(q) . di  ->  <= ||dq|| max||i|| + ||bf(q)|| max||di||   (Cauchy-Schwarz)
+// plus the rounding of the five time terms and 2e-4 of the magnitudes for the two fp32 accumulations.
+__device__ __forceinline__ float score_error_bound(const float* s_aic, const float* s_tq, const float* cat_stats,
+                                                   float* red) {
+    float dq2 = 0.f, q2 = 0.f, f2 = 0.f;
+    for (int c = threadIdx.x; c < XW; c += blockDim.x) {
+        const float v = s_aic[c], r = bf16_round(v);
+        dq2 = fmaf(v - r, v - r, dq2);
+        q2 = fmaf(r, r, q2);
+        f2 = fmaf(v, v, f2);
+    }
+    dq2 = block_sum_e(dq2, red);
+    q2 = block_sum_e(q2, red);
+    f2 = block_sum_e(f2, red);
+    float terr = 0.f, tmag = 0.f;
+    for (int k = 0; k < 5; ++k) {
+        float e = 0.f, m = 0.f;
+        for (int r = kBinOffE[k]; r < kBinOffE[k + 1]; ++r) {
+            const float v = s_tq[r];
+            e = fmaxf(e, fabsf(v - bf16_round(v)));
+            m = fmaxf(m, fabsf(v));
+        }
+        terr += e;
+        tmag += m;
+    }
+    const float imax = cat_stats[0], dimax = cat_stats[1];
+    const float eps = sqrtf(dq2) * imax + sqrtf(q2) * dimax + terr + 2e-4f * (sqrtf(f2) * imax + tmag);
+    return eps * 1.0001f + 1e-30f;
+}
+
 constexpr int TILE_CH = 128 / CH;          // 16 chunks per 128-item tile
 constexpr int NCC = NCH * TILE_CH;         // 512 candidate chunks after the tile-level selection
 
@@ -123,9 +176,13 @@ __global__ void __launch_bounds__(256)
 eval_topk_kernel(const float* __restrict__ chunkmax, const float* __restrict__ tilemax, const float* __restrict__ a_ic,
                  const float* __restrict__ Tq, const float* __restrict__ item, const float* __restrict__ content,
                  const int32_t* __restrict__ mwdhm, const int32_t* __restrict__ label, int32_t* __restrict__ top_ids,
-                 float* __restrict__ top_scores, int32_t* __restrict__ n_greater, int N, int n_pad, int item_offset) {
+                 float* __restrict__ top_scores, int32_t* __restrict__ n_greater, int N, int n_pad, int item_offset,
+                 const float* __restrict__ cat_stats, int32_t* __restrict__ uncertain, float* __restrict__ tau) {
     PDL_ENTER();
     __shared__ float s_aic[XW], s_tq[NB + 1];
+    __shared__ float s_red[8];
+    __shared__ uint32_t s_tilebits[(TCAR_MAX_EVAL_TILES + 31) / 32];
+    float unsel_max = -INFINITY;         // largest bf16 score an item outside the re-scored chunks can have
     __shared__ int s_hist[256];
     __shared__ int s_sel[NCH];
     __shared__ int s_misc[4];
@@ -151,6 +208,22 @@ eval_topk_kernel(const float* __restrict__ chunkmax, const float* __restrict__ t
             __syncthreads();
         } else {
             select_top(tm, ntiles, s_sel, s_hist, s_warp, s_misc);
+            if (cat_stats) {
+                // best tile NOT selected: bitmap of the selected ones, then a max over the rest
+                for (int i = tid; i < (ntiles + 31) / 32; i += 256) s_tilebits[i] = 0u;
+                __syncthreads();
+                if (tid < NCH && s_sel[tid] >= 0) atomicOr(&s_tilebits[s_sel[tid] >> 5], 1u << (s_sel[tid] & 31));
+                __syncthreads();
+                float m = -INFINITY;
+                for (int i = tid; i < ntiles; i += 256)
+                    if (!((s_tilebits[i >> 5] >> (i & 31)) & 1u)) m = fmaxf(m, tm[i]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                if (lane == 0) s_red[w] = m;
+                __syncthreads();
+                for (int i = 0; i < 8; ++i) unsel_max = fmaxf(unsel_max, s_red[i]);
+                __syncthreads();
+            }
         }
         // ---- level 2: the 16 chunks of every selected tile, sorted by (max desc, chunk index asc)
         for (int i = tid; i < NCC; i += 256) {
@@ -176,6 +249,7 @@ eval_topk_kernel(const float* __restrict__ chunkmax, const float* __restrict__ t
             }
         }
         __syncthreads();
+        unsel_max = fmaxf(unsel_max, s_cv[NCH]);        // best chunk of the selected tiles that is NOT re-scored
         if (tid < NCH) s_sel[tid] = s_ci[tid] == 0x7fffffff ? -1 : s_ci[tid];
     } else {
         for (int i = tid; i < nchunks; i += 256) s_sel[i] = i;
@@ -233,15 +307,189 @@ eval_topk_kernel(const float* __restrict__ chunkmax, const float* __restrict__ t
         top_ids[(size_t)b * TOPK + tid] = s_id[tid] == 0x7fffffff ? -1 : s_id[tid];
         top_scores[(size_t)b * TOPK + tid] = s_sc[tid];
     }
+    if (cat_stats) {
+        // certification: nothing outside the re-scored chunks can reach the 20th exact score
+        const float s20 = s_sc[TOPK - 1];
+        const float eps = score_error_bound(s_aic, s_tq, cat_stats, s_red);
+        if (tid == 0) {
+            const float bound = s20 - eps;
+            // s20 == -inf: fewer than 20 candidates re-scored, i.e. every chunk of a tiny catalog was taken
+            uncertain[b] = (nchunks > NCH && !(unsel_max < bound)) ? 1 : 0;
+            tau[b] = bound;
+        }
+    }
+}
+
+// Second stage for the queries tcar_eval_topk could not certify: every chunk whose maximum reaches tau[b] = s20 - eps_b
+// is re-scored exactly (tiles below tau are skipped by their tile maximum), 32 chunks at a time, and merged into a
+// running top-20 by (score desc, id asc); n_greater is counted over the same exact scores.  The result is the exact
+// top-20 of the whole catalog (items below tau cannot reach the 20th score already found).  Cost grows with the number
+// of near-ties; a certified query costs nothing (its CTA returns at once).
+constexpr int WQ_CAP = 4096;        // chunk queue: one sweep of 256 tiles x 16 chunks
+
+__global__ void __launch_bounds__(256)
+eval_topk_widen_kernel(const float* __restrict__ chunkmax, const float* __restrict__ tilemax,
+                       const float* __restrict__ a_ic, const float* __restrict__ Tq, const float* __restrict__ item,
+                       const float* __restrict__ content, const int32_t* __restrict__ mwdhm,
+                       const int32_t* __restrict__ label, const int32_t* __restrict__ uncertain,
+                       const float* __restrict__ tau, int32_t* __restrict__ top_ids, float* __restrict__ top_scores,
+                       int32_t* __restrict__ n_greater, int N, int n_pad, int item_offset) {
+    PDL_ENTER();
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (!uncertain[b]) return;
+    __shared__ float s_aic[XW], s_tq[NB + 1];
+    __shared__ int s_q[WQ_CAP];
+    __shared__ int s_qn, s_ngt;
+    __shared__ float s_sc[NCAND];
+    __shared__ int s_id[NCAND];
+    __shared__ float s_top_sc[TOPK], s_new_sc[TOPK];
+    __shared__ int s_top_id[TOPK], s_new_id[TOPK];
+    __shared__ int s_warp[8];
+    const int nchunks = (N + CH - 1) / CH;
+    const int ntiles = (N + 127) / 128;
+    const float* cm = chunkmax + (size_t)b * (n_pad / CH);
+    const float* tm = tilemax + (size_t)b * (n_pad / 128);
+    const float bound = tau[b];
+    for (int c = tid; c < XW; c += 256) s_aic[c] = a_ic[(size_t)b * XW + c];
+    for (int c = tid; c < NB; c += 256) s_tq[c] = Tq[(size_t)b * NB + c];
+    if (tid < TOPK) { s_top_sc[tid] = -INFINITY; s_top_id[tid] = 0x7fffffff; }
+    if (tid == 0) { s_qn = 0; s_ngt = 0; }
+    __syncthreads();
+    const int lab = label[b];
+    const float lab_score = exact_score_e(s_aic, s_tq, item, content, mwdhm, lab, lane);
+    for (int t0 = 0; t0 < ntiles; t0 += 256) {
+        const int tile = t0 + tid;
+        if (tile < ntiles && tm[tile] >= bound) {
+            for (int c = 0; c < TILE_CH; ++c) {
+                const int chunk = tile * TILE_CH + c;
+                if (chunk < nchunks && cm[chunk] >= bound) s_q[atomicAdd(&s_qn, 1)] = chunk;
+            }
+        }
+        __syncthreads();
+        const int qn = s_qn;
+        for (int q0 = 0; q0 < qn; q0 += NCH) {
+            // exact scores of up to 32 queued chunks
+            for (int j = 0; j < 32; ++j) {
+                const int ci = w * 32 + j;
+                const int qi = q0 + ci / CH;
+                const int n = qi < qn ? s_q[qi] * CH + (ci % CH) : -1;
+                const bool ok = n >= 0 && n < N;
+                float sc = -INFINITY;
+                if (ok) sc = exact_score_e(s_aic, s_tq, item, content, mwdhm, n + item_offset, lane);
+                if (lane == 0) {
+                    s_sc[ci] = sc;
+                    s_id[ci] = ok ? n + item_offset : 0x7fffffff;
+                }
+            }
+            __syncthreads();
+            {
+                const bool gt = s_id[tid] != 0x7fffffff && s_id[tid] != lab && s_sc[tid] > lab_score;
+                const uint32_t bal = __ballot_sync(0xffffffffu, gt);
+                if (lane == 0) s_warp[w] = __popc(bal);
+            }
+            for (int k = 2; k <= NCAND; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    __syncthreads();
+                    const int ixj = tid ^ j;
+                    if (ixj > tid) {
+                        const float sa = s_sc[tid], sb = s_sc[ixj];
+                        const int ia = s_id[tid], ib = s_id[ixj];
+                        const bool up = (tid & k) == 0;
+                        const bool swap = up ? before(sb, ib, sa, ia) : before(sa, ia, sb, ib);
+                        if (swap) { s_sc[tid] = sb; s_sc[ixj] = sa; s_id[tid] = ib; s_id[ixj] = ia; }
+                    }
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                for (int j = 0; j < 8; ++j) s_ngt += s_warp[j];
+                // merge the running list with the 20 best of this batch (both sorted)
+                int ia = 0, ib = 0;
+                for (int r = 0; r < TOPK; ++r) {
+                    if (before(s_top_sc[ia], s_top_id[ia], s_sc[ib], s_id[ib])) {
+                        s_new_sc[r] = s_top_sc[ia]; s_new_id[r] = s_top_id[ia]; ++ia;
+                    } else {
+                        s_new_sc[r] = s_sc[ib]; s_new_id[r] = s_id[ib]; ++ib;
+                    }
+                }
+                for (int r = 0; r < TOPK; ++r) { s_top_sc[r] = s_new_sc[r]; s_top_id[r] = s_new_id[r]; }
+            }
+            __syncthreads();
+        }
+        if (tid == 0) s_qn = 0;
+        __syncthreads();
+    }
+    if (tid < TOPK) {
+        top_ids[(size_t)b * TOPK + tid] = s_top_id[tid] == 0x7fffffff ? -1 : s_top_id[tid];
+        top_scores[(size_t)b * TOPK + tid] = s_top_sc[tid];
+    }
+    if (tid == 0) n_greater[b] = s_ngt;
+}
+
+// Catalog statistics behind eps_b: out[0] = max_n ||[item | content] row n||_2, out[1] = max_n ||row n - bf16(row n)||_2
+// over table rows [row_lo, row_hi).  One warp per row; non-negative floats order like their bit patterns (atomicMax).
+__global__ void __launch_bounds__(256)
+catalog_stats_kernel(const float* __restrict__ item, const float* __restrict__ content, int row_lo, int row_hi,
+                     float* __restrict__ out) {
+    PDL_ENTER();
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    float mx = 0.f, dmx = 0.f;
+    for (int row = row_lo + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); row < row_hi; row += warps) {
+        float n2 = 0.f, d2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float4 iv = __ldg(reinterpret_cast<const float4*>(item + (size_t)row * HP) + j * 32 + lane);
+            const float4 cv = __ldg(reinterpret_cast<const float4*>(content + (size_t)row * HP) + j * 32 + lane);
+            const float v[8] = {iv.x, iv.y, iv.z, iv.w, cv.x, cv.y, cv.z, cv.w};
+            const int c = j * 128 + lane * 4;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (c + (u & 3) < H) {
+                    const float d = v[u] - bf16_round(v[u]);
+                    n2 = fmaf(v[u], v[u], n2);
+                    d2 = fmaf(d, d, d2);
+                }
+            }
+        }
+        n2 = warp_sum_e(n2);
+        d2 = warp_sum_e(d2);
+        mx = fmaxf(mx, n2);
+        dmx = fmaxf(dmx, d2);
+    }
+    if (lane == 0) {
+        atomicMax(reinterpret_cast<int*>(out), __float_as_int(sqrtf(mx) * 1.000001f));
+        atomicMax(reinterpret_cast<int*>(out) + 1, __float_as_int(sqrtf(dmx) * 1.000001f));
+    }
 }
 
 // merge G shard lists: one warp per query, serial selection (G*20 <= 160 entries)
 __global__ void __launch_bounds__(256)
 topk_merge_kernel(const int32_t* __restrict__ ids, const float* __restrict__ scores, int32_t* __restrict__ out_ids,
-                  float* __restrict__ out_scores, int G, int B) {
+                  float* __restrict__ out_scores, int G, int B, long long gstride, const int32_t* __restrict__ ngt,
+                  const float* __restrict__ sumexp, const float* __restrict__ rowmax, int32_t* __restrict__ out_ngt,
+                  float* __restrict__ out_ce) {
     PDL_ENTER();
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (b >= B) return;
+    if (ngt && lane == 0) {
+        // rank counts add up; the shards' softmax sums are relative to their own exponent shifts (overflow guard):
+        // sum_g sumexp_g 2^(shift_g - M) with M the largest shift, CE = log(sum) + M ln 2 = logsumexp(S_b) - S_b[label]
+        int cnt = 0;
+        float M = 0.f;
+        for (int g = 0; g < G; ++g) {
+            cnt += ngt[g * gstride + b];
+            const float r = rowmax ? rowmax[g * gstride + b] : 0.f;
+            M = fmaxf(M, r > TCAR_EXP_LIMIT2 ? r : 0.f);
+        }
+        float tot = 0.f;
+        for (int g = 0; g < G; ++g) {
+            const float r = rowmax ? rowmax[g * gstride + b] : 0.f;
+            tot += sumexp[g * gstride + b] * exp2f((r > TCAR_EXP_LIMIT2 ? r : 0.f) - M);
+        }
+        out_ngt[b] = cnt;
+        out_ce[b] = fmaf(M, 0.6931471805599453f, logf(tot));
+    }
     const int n = G * TOPK;
     // each lane owns entries lane, lane+32, ...; `taken` bit per owned entry
     uint32_t taken = 0;
@@ -250,8 +498,10 @@ topk_merge_kernel(const int32_t* __restrict__ ids, const float* __restrict__ sco
         for (int e = lane, s = 0; e < n; e += 32, ++s) {
             if (taken & (1u << s)) continue;
             const int g = e / TOPK, j = e % TOPK;
-            const float sc = scores[((size_t)g * B + b) * TOPK + j];
-            int id = ids[((size_t)g * B + b) * TOPK + j];
+            // shard lists: [G][B][20] back to back (gstride == 0) or one block of `gstride` words per shard
+            const size_t at = gstride ? (size_t)g * gstride + (size_t)b * TOPK + j : ((size_t)g * B + b) * TOPK + j;
+            const float sc = scores[at];
+            int id = ids[at];
             if (id < 0) id = 0x7fffffff;
             if (before(sc, id, bs, bi)) { bs = sc; bi = id; bslot = s; }
         }
@@ -281,15 +531,59 @@ extern "C" int tcar_eval_topk(const float* chunkmax, const float* tilemax, const
                               const float* content, const int32_t* mwdhm, const int32_t* label, int32_t* top_ids,
                               float* top_scores, int32_t* n_greater, int B, int N, int n_pad, int item_offset,
                               void* stream) {
+    return tcar_eval_topk_certified(chunkmax, tilemax, a_ic, Tq, item, content, mwdhm, label, top_ids, top_scores,
+                                    n_greater, B, N, n_pad, item_offset, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int tcar_eval_topk_certified(const float* chunkmax, const float* tilemax, const float* a_ic, const float* Tq,
+                                        const float* item, const float* content, const int32_t* mwdhm,
+                                        const int32_t* label, int32_t* top_ids, float* top_scores, int32_t* n_greater,
+                                        int B, int N, int n_pad, int item_offset, const float* cat_stats,
+                                        int32_t* uncertain, float* tau, void* stream) {
     if (B < 1 || B > TCAR_QROWS || N < 1 || n_pad < N || !tilemax) return TCAR_ERR_ARG;
-    launch_pdl(eval_topk_kernel, dim3(B), dim3(256), 0, STREAM, chunkmax, tilemax, a_ic, Tq, item, content, mwdhm, label, top_ids, top_scores,
-                                            n_greater, N, n_pad, item_offset);
+    if (cat_stats && (!uncertain || !tau || (N + 127) / 128 > TCAR_MAX_EVAL_TILES)) return TCAR_ERR_ARG;
+    launch_pdl(eval_topk_kernel, dim3(B), dim3(256), 0, STREAM, chunkmax, tilemax, a_ic, Tq, item, content, mwdhm,
+               label, top_ids, top_scores, n_greater, N, n_pad, item_offset, cat_stats, uncertain, tau);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int tcar_eval_topk_widen(const float* chunkmax, const float* tilemax, const float* a_ic, const float* Tq,
+                                    const float* item, const float* content, const int32_t* mwdhm,
+                                    const int32_t* label, const int32_t* uncertain, const float* tau,
+                                    int32_t* top_ids, float* top_scores, int32_t* n_greater, int B, int N, int n_pad,
+                                    int item_offset, void* stream) {
+    if (B < 1 || B > TCAR_QROWS || N < 1 || n_pad < N || !tilemax || !uncertain || !tau) return TCAR_ERR_ARG;
+    launch_pdl(eval_topk_widen_kernel, dim3(B), dim3(256), 0, STREAM, chunkmax, tilemax, a_ic, Tq, item, content,
+               mwdhm, label, uncertain, tau, top_ids, top_scores, n_greater, N, n_pad, item_offset);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int tcar_catalog_stats(const float* item, const float* content, int row_lo, int row_hi, float* out2,
+                                  void* stream) {
+    if (row_lo < 0 || row_hi <= row_lo || !out2) return TCAR_ERR_ARG;
+    cudaError_t e = cudaMemsetAsync(out2, 0, 2 * sizeof(float), STREAM);
+    if (e != cudaSuccess) return (int)e;
+    launch_pdl(catalog_stats_kernel, dim3(148 * 8), dim3(256), 0, STREAM, item, content, row_lo, row_hi, out2);
     return (int)cudaGetLastError();
 }
 
 extern "C" int tcar_topk_merge(const int32_t* ids, const float* scores, int32_t* out_ids, float* out_scores, int G,
                                int B, void* stream) {
-    if (G < 1 || G > 8 || B < 1) return TCAR_ERR_ARG;
-    launch_pdl(topk_merge_kernel, dim3((B + 7) / 8), dim3(256), 0, STREAM, ids, scores, out_ids, out_scores, G, B);
+    if (G < 1 || G > TCAR_MAX_PEERS || B < 1) return TCAR_ERR_ARG;
+    launch_pdl(topk_merge_kernel, dim3((B + 7) / 8), dim3(256), 0, STREAM, ids, scores, out_ids, out_scores, G, B,
+               0LL, static_cast<const int32_t*>(nullptr), static_cast<const float*>(nullptr),
+               static_cast<const float*>(nullptr), static_cast<int32_t*>(nullptr), static_cast<float*>(nullptr));
+    return (int)cudaGetLastError();
+}
+
+extern "C" int tcar_eval_merge(const void* blocks, long long block_words, int32_t* out_ids, float* out_scores,
+                               int32_t* out_ngt, float* out_ce, int G, int B, void* stream) {
+    if (G < 1 || G > TCAR_MAX_PEERS || B < 1 || B > TCAR_QROWS || block_words < TCAR_EVAL_BLOCK_WORDS || !blocks)
+        return TCAR_ERR_ARG;
+    const float* f = static_cast<const float*>(blocks);
+    const int32_t* i = static_cast<const int32_t*>(blocks);
+    launch_pdl(topk_merge_kernel, dim3((B + 7) / 8), dim3(256), 0, STREAM, i + TCAR_EVAL_OFF_IDS, f + TCAR_EVAL_OFF_SCORES,
+               out_ids, out_scores, G, B, block_words, i + TCAR_EVAL_OFF_NGT, f + TCAR_EVAL_OFF_SUMEXP,
+               f + TCAR_EVAL_OFF_ROWMAX, out_ngt, out_ce);
     return (int)cudaGetLastError();
 }

@@ -123,13 +123,27 @@ extern "C" int tcar_score_fwd_groups(const void* q_bf16, long long q_stride, con
                                      const void* iext_bf16, void* e_out, long long e_stride, float* rowsum_part,
                                      long long part_stride, const int* n_rows, int groups, int n_items, int n_pad,
                                      int cluster, void* stream) {
+    return tcar_score_fwd_groups_guarded(q_bf16, q_stride, c_ref, c_stride, iext_bf16, e_out, e_stride, rowsum_part,
+                                         part_stride, nullptr, nullptr, n_rows, groups, n_items, n_pad, cluster, stream);
+}
+
+// With the softmax overflow guard (tcar_score_fwd_guarded): pass 1 = rowmax_part given (group g's block part_stride
+// floats apart, like rowsum_part), pass 2 = rowmax given ([groups][512]; after tcar_rowmax_groups and, across ranks, an
+// all-reduce(MAX) -- every rank must shift a session row by the same amount).
+extern "C" int tcar_score_fwd_groups_guarded(const void* q_bf16, long long q_stride, const float* c_ref,
+                                             long long c_stride, const void* iext_bf16, void* e_out, long long e_stride,
+                                             float* rowsum_part, long long part_stride, float* rowmax_part,
+                                             const float* rowmax, const int* n_rows, int groups, int n_items, int n_pad,
+                                             int cluster, void* stream) {
     if (!n_rows || groups < 1) return TCAR_ERR_ARG;
     for (int g = 0; g < groups; ++g) {
         if (n_rows[g] <= 0) continue;
-        const int rc = tcar_score_fwd(static_cast<const uint16_t*>(q_bf16) + g * q_stride, iext_bf16,
-                                      c_ref + g * c_stride, static_cast<uint16_t*>(e_out) + g * e_stride,
-                                      rowsum_part + g * part_stride, nullptr, nullptr, n_rows[g], n_items, n_pad, 0,
-                                      cluster, stream);
+        const int rc = tcar_score_fwd_guarded(static_cast<const uint16_t*>(q_bf16) + g * q_stride, iext_bf16,
+                                              c_ref + g * c_stride, static_cast<uint16_t*>(e_out) + g * e_stride,
+                                              rowsum_part + g * part_stride, nullptr, nullptr,
+                                              rowmax_part ? rowmax_part + g * part_stride : nullptr,
+                                              rowmax ? rowmax + (size_t)g * TCAR_QROWS : nullptr, n_rows[g], n_items,
+                                              n_pad, 0, cluster, stream);
         if (rc) return rc;
     }
     return 0;

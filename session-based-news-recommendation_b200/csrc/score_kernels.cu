@@ -48,6 +48,11 @@ struct FwdParams {
     float* chunkmax;        // [512, e_pitch/8] (eval) or nullptr
     float* tilemax;         // [512, e_pitch/128] (eval, nullable): max of S over each 128 consecutive items
     const float* c_ref;     // [512] reference score per row (exp argument shift)
+    float* rowmax_part;     // [n_tiles, 512] (nullable) max over the tile's valid items of the exponent argument
+                            // (S - c_ref) * log2(e): pass 1 of the overflow guard (tcar_ce_finish reduces it)
+    const float* rowmax;    // [512] (nullable) pass 2: per-row maxima found by pass 1.  Rows above TCAR_EXP_LIMIT2 are
+                            // shifted by their maximum (TF's max-subtracted softmax, model_combine.py:145); CTAs none
+                            // of whose rows need it exit at once, the others rewrite identical values for quiet rows
     int n_items;            // valid items N
     int n_tiles;            // ceil(Npad / F_BN)
     int n_rows;             // valid sessions B
@@ -55,6 +60,26 @@ struct FwdParams {
     int groups;             // number of session groups (ceil(ceil(B/128)/CL))
     int mode;               // 0 = train, 1 = eval
 };
+
+// exponent shift of one session row in log2 units: the label score, plus -- in pass 2 of the overflow guard -- the
+// row maximum found by pass 1 when that exceeded TCAR_EXP_LIMIT2
+__device__ __forceinline__ float exp_shift(const FwdParams& p, uint32_t row) {
+    float sh = p.c_ref[row] * kLog2e;
+    if (p.rowmax) {
+        const float m = p.rowmax[row];
+        if (m > TCAR_EXP_LIMIT2) sh += m;
+    }
+    return sh;
+}
+
+// pass 2 of the overflow guard: does any of the `rows` session rows starting at row0 need the extra shift?  Called
+// by every thread of the CTA (and with the same arguments by every CTA of a cluster, so that they agree).
+__device__ __forceinline__ bool guard_pass_needed(const FwdParams& p, uint32_t row0, uint32_t rows) {
+    bool need = false;
+    for (uint32_t r = row0 + threadIdx.x; r < row0 + rows && r < (uint32_t)p.n_rows; r += blockDim.x)
+        need |= p.rowmax[r] > TCAR_EXP_LIMIT2;
+    return __syncthreads_or(need) != 0;
+}
 
 template <int CL>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -85,6 +110,7 @@ score_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     const uint32_t mtile = grp * CL + rank;
     const uint32_t my_tiles =
         tile0 < (uint32_t)p.n_tiles ? ((uint32_t)p.n_tiles - tile0 + tile_step - 1) / tile_step : 0u;
+    if (p.rowmax && !guard_pass_needed(p, grp * CL * BM, CL * BM)) return;
 
     if (warp == 0 && elect_one()) {
         tma_prefetch_desc(&map_q);
@@ -166,7 +192,7 @@ score_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         const bool row_ok = row < (uint32_t)p.n_rows;
         // rows in [B, round_up(B,64)) are stored as zeros: they are K-padding of the dItem GEMM
         const bool store_ok = row < (((uint32_t)p.n_rows + 63u) & ~63u);
-        const float cshift = row_ok ? p.c_ref[row] * kLog2e : 0.f;
+        const float cshift = row_ok ? exp_shift(p, row) : 0.f;
         for (uint32_t it = 0; it < my_tiles; ++it) {
             const uint32_t acc = it % F_NACC;
             const uint32_t acc_phase = (it / F_NACC) & 1;
@@ -174,7 +200,7 @@ score_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             const int n0 = tile * F_BN;
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
-            float psum = 0.f, tmax = -INFINITY;
+            float psum = 0.f, tmax = -INFINITY, amax = -INFINITY;
             const bool tail = n0 + F_BN > p.n_items;
 #pragma unroll 1
             for (int ch = 0; ch < F_BN / 32; ++ch) {
@@ -186,8 +212,10 @@ score_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float s = __uint_as_float(v[j]);
-                    float ex = exp2f(fmaf(s, kLog2e, -cshift));
+                    const float arg = fmaf(s, kLog2e, -cshift);
+                    float ex = exp2f(arg);
                     if (!row_ok || (tail && nb + j >= p.n_items)) ex = 0.f;
+                    else amax = fmaxf(amax, arg);
                     e[j] = ex;
                     psum += ex;
                 }
@@ -228,6 +256,7 @@ score_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[acc]);
             if (row_ok) p.rowsum_part[(size_t)tile * QROWS + row] = psum;
+            if (row_ok && p.rowmax_part) p.rowmax_part[(size_t)tile * QROWS + row] = amax;
             if (row_ok && p.mode == 1 && p.tilemax) p.tilemax[(size_t)row * (p.e_pitch / 128) + tile] = tmax;
         }
     }
@@ -256,12 +285,14 @@ constexpr int P_SMEM = F_A_BYTES + P_STAGES * P_B_STAGE + 1024 /*align*/ + 256 /
 template <int MODE>
 __device__ __forceinline__ void fwd_epilogue_chunk(const uint32_t (&v)[32], const FwdParams& p, float cshift,
                                                    bool row_ok, bool store_ok, bool tail, uint32_t row, int nb,
-                                                   float& psum, float& tmax) {
+                                                   float& psum, float& tmax, float& amax) {
     float e[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-        float ex = ex2_approx(fmaf(__uint_as_float(v[j]), kLog2e, -cshift));
+        const float arg = fmaf(__uint_as_float(v[j]), kLog2e, -cshift);
+        float ex = ex2_approx(arg);
         if (!row_ok || (tail && nb + j >= p.n_items)) ex = 0.f;
+        else if (MODE == 0) amax = fmaxf(amax, arg);     // eval mode derives it from tmax (monotone map)
         e[j] = ex;
         psum += ex;
     }
@@ -326,6 +357,7 @@ score_fwd_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     const uint32_t mtile = grp * 2 + rank;
     const uint32_t my_tiles =
         tile0 < (uint32_t)p.n_tiles ? ((uint32_t)p.n_tiles - tile0 + tile_step - 1) / tile_step : 0u;
+    if (p.rowmax && !guard_pass_needed(p, grp * 2 * BM, 2 * BM)) return;      // both CTAs of the pair decide alike
 
     if (warp == 0 && elect_one()) {
         tma_prefetch_desc(&map_q);
@@ -404,7 +436,7 @@ score_fwd_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
         const uint32_t row = mtile * BM + q * 32 + lane;
         const bool row_ok = row < (uint32_t)p.n_rows;
         const bool store_ok = row < (((uint32_t)p.n_rows + 63u) & ~63u);
-        const float cshift = row_ok ? p.c_ref[row] * kLog2e : 0.f;
+        const float cshift = row_ok ? exp_shift(p, row) : 0.f;
         const uint32_t acc_empty_l = mapa_u32(acc_empty, 0);
         for (uint32_t it = 0; it < my_tiles; ++it) {
             const uint32_t acc = it % P_NACC;
@@ -415,25 +447,27 @@ score_fwd_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((q * 32) << 16) + acc * P_BN + h * 128;
             const bool tail = n0 + 128 > p.n_items;
-            float psum = 0.f, tmax = -INFINITY;
+            float psum = 0.f, tmax = -INFINITY, amax = -INFINITY;
             uint32_t va[32], vb[32];
             tmem_ld32(taddr, va);
             tmem_ld_wait();
             tmem_ld32(taddr + 32, vb);
-            fwd_epilogue_chunk<MODE>(va, p, cshift, row_ok, store_ok, tail, row, n0, psum, tmax);
+            fwd_epilogue_chunk<MODE>(va, p, cshift, row_ok, store_ok, tail, row, n0, psum, tmax, amax);
             tmem_ld_wait();
             tmem_ld32(taddr + 64, va);
-            fwd_epilogue_chunk<MODE>(vb, p, cshift, row_ok, store_ok, tail, row, n0 + 32, psum, tmax);
+            fwd_epilogue_chunk<MODE>(vb, p, cshift, row_ok, store_ok, tail, row, n0 + 32, psum, tmax, amax);
             tmem_ld_wait();
             tmem_ld32(taddr + 96, vb);
-            fwd_epilogue_chunk<MODE>(va, p, cshift, row_ok, store_ok, tail, row, n0 + 64, psum, tmax);
+            fwd_epilogue_chunk<MODE>(va, p, cshift, row_ok, store_ok, tail, row, n0 + 64, psum, tmax, amax);
             tmem_ld_wait();
             // every TMEM read of this accumulator half is in registers -> hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(acc_empty_l + acc * 8);
-            fwd_epilogue_chunk<MODE>(vb, p, cshift, row_ok, store_ok, tail, row, n0 + 96, psum, tmax);
+            fwd_epilogue_chunk<MODE>(vb, p, cshift, row_ok, store_ok, tail, row, n0 + 96, psum, tmax, amax);
             if (row_ok) p.rowsum_part[(size_t)(tile * 2 + h) * QROWS + row] = psum;
+            if (row_ok && p.rowmax_part)
+                p.rowmax_part[(size_t)(tile * 2 + h) * QROWS + row] = MODE == 1 ? fmaf(tmax, kLog2e, -cshift) : amax;
             if (MODE == 1 && row_ok && p.tilemax) p.tilemax[(size_t)row * (p.e_pitch / 128) + tile * 2 + h] = tmax;
         }
     }
@@ -894,6 +928,14 @@ using namespace tcar;
 extern "C" int tcar_score_fwd(const void* q_bf16, const void* iext_bf16, const float* c_ref, void* e_out,
                               float* rowsum_part, float* chunkmax, float* tilemax, int n_rows, int n_items, int n_pad,
                               int mode, int cluster, void* stream_) {
+    return tcar_score_fwd_guarded(q_bf16, iext_bf16, c_ref, e_out, rowsum_part, chunkmax, tilemax, nullptr, nullptr,
+                                  n_rows, n_items, n_pad, mode, cluster, stream_);
+}
+
+extern "C" int tcar_score_fwd_guarded(const void* q_bf16, const void* iext_bf16, const float* c_ref, void* e_out,
+                                      float* rowsum_part, float* chunkmax, float* tilemax, float* rowmax_part,
+                                      const float* rowmax, int n_rows, int n_items, int n_pad, int mode, int cluster,
+                                      void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (n_rows < 1 || n_rows > QROWS || n_pad % 256 != 0 || n_items > n_pad) return TCAR_ERR_ARG;
     if (cluster != 1 && cluster != 2 && cluster != 4 && cluster != TCAR_CLUSTER_PAIR) return TCAR_ERR_ARG;
@@ -910,6 +952,8 @@ extern "C" int tcar_score_fwd(const void* q_bf16, const void* iext_bf16, const f
         p.chunkmax = chunkmax;
         p.tilemax = tilemax;
         p.c_ref = c_ref;
+        p.rowmax_part = rowmax_part;
+        p.rowmax = rowmax;
         p.n_items = n_items;
         p.n_tiles = n_pad / P_BN;
         p.n_rows = n_rows;
@@ -930,6 +974,8 @@ extern "C" int tcar_score_fwd(const void* q_bf16, const void* iext_bf16, const f
     p.chunkmax = chunkmax;
     p.tilemax = tilemax;
     p.c_ref = c_ref;
+    p.rowmax_part = rowmax_part;
+    p.rowmax = rowmax;
     p.n_items = n_items;
     p.n_tiles = n_pad / F_BN;
     p.n_rows = n_rows;

@@ -491,32 +491,80 @@ build_query_kernel(const float* __restrict__ a_ic, const float* __restrict__ a_p
 // ------------------------------------------------------------------------------------------------ (4a) CE finish
 // 16 rows per CTA (half-warp = 16 consecutive rows of one partial, the two half-warps take alternate partials), 32 warps
 // stride over the partials with 8 independent loads in flight per thread, fixed combine order.
+//
+// Overflow guard of the softmax (TF's sparse_softmax_cross_entropy_with_logits subtracts the row maximum,
+// model_combine.py:145; the scoring kernel shifts by the label score):
+//   pass 0  sums only (no guard)
+//   pass 1  sums, and rowmax[b] = max over the tiles of pmax (largest exponent argument of the row, log2 units)
+//   pass 2  after the scoring kernel re-ran with `rowmax` (rows above TCAR_EXP_LIMIT2 shifted by it): those rows are
+//           summed again and ce[b] = log(sum) + rowmax[b] ln 2; every other row keeps its pass-1 result, and CTAs
+//           without such a row exit at once
+//   pass 3  maxima only (rowmax[b]; catalog-sharded step, where the sums travel with dQ)
+struct GroupRows { int n[TCAR_MAX_PEERS]; long long part_stride; };   // blockIdx.y = session group (pass 3 only)
+
 __global__ void __launch_bounds__(1024)
-ce_finish_kernel(const float* __restrict__ part, float* __restrict__ sumexp, float* __restrict__ ce, int n_tiles,
-                 int B, int sum_stride) {
+ce_finish_kernel(const float* __restrict__ part, const float* __restrict__ pmax, float* __restrict__ sumexp,
+                 float* __restrict__ ce, float* __restrict__ rowmax, int n_tiles, int B, int sum_stride, int pass,
+                 const __grid_constant__ GroupRows gr) {
     PDL_ENTER();
     __shared__ float s[32][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int b = blockIdx.x * 16 + (lane & 15);
-    float a[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) a[k] = 0.f;
-    if (b < B) {
-        const float* src = part + b;
-        int t = 2 * w + (lane >> 4);
-        for (; t + 7 * 64 < n_tiles; t += 8 * 64) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) a[k] += src[(size_t)(t + 64 * k) * TCAR_QROWS];
-        }
-        for (; t < n_tiles; t += 64) a[0] += src[(size_t)t * TCAR_QROWS];
+    if (gridDim.y > 1 || gr.part_stride) {
+        // several session groups in one launch: group g's partials lie part_stride floats apart, its row maxima go
+        // to rowmax + g * 512
+        B = gr.n[blockIdx.y];
+        pmax += (size_t)blockIdx.y * gr.part_stride;
+        rowmax += (size_t)blockIdx.y * TCAR_QROWS;
+        if ((int)blockIdx.x * 16 >= B) return;
     }
-    s[w][lane] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
-    __syncthreads();
-    if (w == 0 && lane < 16 && b < B) {
-        float tot = 0.f;
-        for (int i = 0; i < 32; ++i) tot += s[i][lane] + s[i][lane + 16];
+    bool redo = false;
+    if (pass == 2) {
+        redo = b < B && rowmax[b] > TCAR_EXP_LIMIT2;
+        if (!__syncthreads_or(redo)) return;
+    }
+    float tot = 0.f;
+    if (pass != 3) {
+        float a[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] = 0.f;
+        if (b < B) {
+            const float* src = part + b;
+            int t = 2 * w + (lane >> 4);
+            for (; t + 7 * 64 < n_tiles; t += 8 * 64) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) a[k] += src[(size_t)(t + 64 * k) * TCAR_QROWS];
+            }
+            for (; t < n_tiles; t += 64) a[0] += src[(size_t)t * TCAR_QROWS];
+        }
+        s[w][lane] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+        __syncthreads();
+        if (w == 0 && lane < 16)
+            for (int i = 0; i < 32; ++i) tot += s[i][lane] + s[i][lane + 16];
+        __syncthreads();
+    }
+    if (pass == 1 || pass == 3) {
+        float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        if (b < B) {
+            const float* src = pmax + b;
+            int t = 2 * w + (lane >> 4);
+            for (; t + 3 * 64 < n_tiles; t += 4 * 64) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) m[k] = fmaxf(m[k], src[(size_t)(t + 64 * k) * TCAR_QROWS]);
+            }
+            for (; t < n_tiles; t += 64) m[0] = fmaxf(m[0], src[(size_t)t * TCAR_QROWS]);
+        }
+        s[w][lane] = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
+        __syncthreads();
+        if (w == 0 && lane < 16 && b < B) {
+            float mx = -INFINITY;
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(s[i][lane], s[i][lane + 16]));
+            rowmax[b] = mx;
+        }
+    }
+    if (pass != 3 && w == 0 && lane < 16 && b < B && (pass != 2 || redo)) {
         sumexp[(size_t)b * sum_stride] = tot;
-        if (ce) ce[b] = logf(tot);
+        if (ce) ce[b] = pass == 2 ? fmaf(rowmax[b], 0.6931471805599453f, logf(tot)) : logf(tot);
     }
 }
 
@@ -1074,16 +1122,45 @@ extern "C" int tcar_build_query(const float* a_ic, const float* a_pt, const floa
 }
 
 extern "C" int tcar_ce_finish(const float* rowsum_part, float* sumexp, float* ce, int n_tiles, int B, void* stream) {
-    if (B < 1 || B > TCAR_QROWS) return TCAR_ERR_ARG;
-    launch_pdl(ce_finish_kernel, dim3((B + 15) / 16), dim3(1024), 0, STREAM, rowsum_part, sumexp, ce, n_tiles, B, 1);
+    return tcar_ce_finish_guarded(rowsum_part, nullptr, sumexp, ce, nullptr, n_tiles, B, 0, stream);
+}
+
+extern "C" int tcar_ce_finish_guarded(const float* rowsum_part, const float* rowmax_part, float* sumexp, float* ce,
+                                      float* rowmax, int n_tiles, int B, int pass, void* stream) {
+    if (B < 1 || B > TCAR_QROWS || pass < 0 || pass > 3) return TCAR_ERR_ARG;
+    if ((pass == 1 || pass == 3) && (!rowmax_part || !rowmax)) return TCAR_ERR_ARG;
+    if (pass == 2 && !rowmax) return TCAR_ERR_ARG;
+    if (pass != 3 && (!rowsum_part || !sumexp)) return TCAR_ERR_ARG;
+    launch_pdl(ce_finish_kernel, dim3((B + 15) / 16), dim3(1024), 0, STREAM, rowsum_part, rowmax_part, sumexp, ce,
+               rowmax, n_tiles, B, 1, pass, GroupRows{});
+    return LAUNCH_RC();
+}
+
+extern "C" int tcar_rowmax_groups(const float* rowmax_part, long long part_stride, float* rowmax, int n_tiles,
+                                  const int* n_rows, int groups, void* stream) {
+    if (!rowmax_part || !rowmax || !n_rows || groups < 1 || groups > TCAR_MAX_PEERS || part_stride < 1)
+        return TCAR_ERR_ARG;
+    GroupRows gr = {};
+    int bmax = 0;
+    for (int g = 0; g < groups; ++g) {
+        if (n_rows[g] > TCAR_QROWS) return TCAR_ERR_ARG;
+        gr.n[g] = n_rows[g] > 0 ? n_rows[g] : 0;
+        if (gr.n[g] > bmax) bmax = gr.n[g];
+    }
+    if (bmax == 0) return 0;
+    gr.part_stride = part_stride;
+    launch_pdl(ce_finish_kernel, dim3((bmax + 15) / 16, groups), dim3(1024), 0, STREAM,
+               static_cast<const float*>(nullptr), rowmax_part, static_cast<float*>(nullptr),
+               static_cast<float*>(nullptr), rowmax, n_tiles, bmax, 1, 3, gr);
     return LAUNCH_RC();
 }
 
 extern "C" int tcar_rowsum_finish(const float* rowsum_part, float* out, int out_stride, int n_tiles, int B,
                                   void* stream) {
     if (B < 1 || B > TCAR_QROWS || out_stride < 1 || !out) return TCAR_ERR_ARG;
-    launch_pdl(ce_finish_kernel, dim3((B + 15) / 16), dim3(1024), 0, STREAM, rowsum_part, out,
-               static_cast<float*>(nullptr), n_tiles, B, out_stride);
+    launch_pdl(ce_finish_kernel, dim3((B + 15) / 16), dim3(1024), 0, STREAM, rowsum_part,
+               static_cast<const float*>(nullptr), out, static_cast<float*>(nullptr), static_cast<float*>(nullptr),
+               n_tiles, B, out_stride, 0, GroupRows{});
     return LAUNCH_RC();
 }
 

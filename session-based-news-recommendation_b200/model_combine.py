@@ -142,6 +142,10 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         self.ahead_priority = os.environ.get("TCAR_AHEAD_PRIORITY", "1") != "0"
         # multi-GPU training layout: "dp" = data parallel + gradient all-reduce (north_star), "catalog" = the softmax
         # sharded over the item catalog (catalog_parallel.py)
+        # overflow guard of the full-catalog softmax (TCAR_EXP_LIMIT2 in include/tcar_b200.h): TF subtracts the row
+        # maximum (model_combine.py:145), the scoring kernel shifts by the label score; rows whose best candidate
+        # outscores the label by more than 55 nats are re-run shifted by their maximum (two empty launches otherwise)
+        self.softmax_guard = bool(args.get("softmax_guard", os.environ.get("TCAR_SOFTMAX_GUARD", "1") != "0"))
         self.train_parallel = "dp"
         self._item_table_synced = True
         mode = args.get("train_parallel") or "dp"
@@ -171,7 +175,24 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         self.d_a_ic, self.d_a_pt, self.dA_neg = f(Bm, XW), f(Bm, PW), f(Bm, XW)
         self.Tq, self.dTq = f(Bm, NB), f(Bm, NB)
         self.a_ic_eval, self.Tq_eval = f(Bm, XW), f(Bm, NB)      # eval look-ahead: parked copies for the re-scoring
-        self.c_ref, self.sumexp, self.ce = f(Bm), f(Bm), f(Bm)
+        self.c_ref, self.ce = f(Bm), f(Bm)
+        # one shard's evaluation results as ONE block (TCAR_EVAL_OFF_* in include/tcar_b200.h): the kernels write its
+        # planes, the catalog-sharded evaluation exchanges the whole block in a single collective
+        self._evblock = f(nv.EVAL_BLOCK_WORDS)
+        ev_i = self._evblock.view(torch.int32)
+        self.top_scores = self._evblock[nv.EVAL_OFF_SCORES: nv.EVAL_OFF_SCORES + Bm * TOPK].view(Bm, TOPK)
+        self.top_ids = ev_i[nv.EVAL_OFF_IDS: nv.EVAL_OFF_IDS + Bm * TOPK].view(Bm, TOPK)
+        self.n_greater = ev_i[nv.EVAL_OFF_NGT: nv.EVAL_OFF_NGT + Bm]
+        self.sumexp = self._evblock[nv.EVAL_OFF_SUMEXP: nv.EVAL_OFF_SUMEXP + Bm]
+        self.rowmax = self._evblock[nv.EVAL_OFF_ROWMAX: nv.EVAL_OFF_ROWMAX + Bm]
+        # merged (global) results of a sharded evaluation
+        self.m_ids = torch.zeros(Bm, TOPK, device=dev, dtype=torch.int32)
+        self.m_scores, self.m_ce = f(Bm, TOPK), f(Bm)
+        self.m_ngt = torch.zeros(Bm, device=dev, dtype=torch.int32)
+        # certification of the top-20 candidate selection (tcar_eval_topk_certified / tcar_eval_topk_widen)
+        self.uncertain = torch.zeros(Bm, device=dev, dtype=torch.int32)
+        self.tau, self.cat_stats = f(Bm), f(2)
+        self._cat_stats_version = -1
         self.negloss, self.loss, self.coef = f(Bm), f(Bm), f(Bm)
         self.Q = torch.zeros(QROWS, KEXT, device=dev, dtype=torch.bfloat16)
         self.Qs = torch.zeros(QROWS, nv.HP, device=dev, dtype=torch.bfloat16)
@@ -182,9 +203,6 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         self._alloc_scatter(Bm * 20 + Bm + Bm * max(int(self.neg_num or 0), 20))   # reference defaults: T<=20, Nn=20
         self.sq_partial = f(256)
         self.table_part = f(148 * 19600)            # TCAR_TABLE_GRAD_CHUNKS x TCAR_TABLE_GRAD_PART
-        self.top_ids = torch.zeros(Bm, TOPK, device=dev, dtype=torch.int32)
-        self.top_scores = f(Bm, TOPK)
-        self.n_greater = torch.zeros(Bm, device=dev, dtype=torch.int32)
 
     def _alloc_scatter(self, entries):
         """Scratch of the deterministic scatter-add, sized for `entries` sparse rows (clicks + labels + negatives):
@@ -217,7 +235,8 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         if key not in self._score_ws:
             dev = self.dev
             tiles = nv.lib().tcar_score_fwd_tiles(n_pad)
-            ws = {"part": torch.zeros(tiles, QROWS, device=dev), "tiles": tiles}
+            ws = {"part": torch.zeros(tiles, QROWS, device=dev), "pmax": torch.zeros(tiles, QROWS, device=dev),
+                  "tiles": tiles}
             if train:
                 ws["E"] = torch.zeros(QROWS, n_pad, device=dev, dtype=torch.bfloat16)
                 splits = max(nv.lib().tcar_score_bwd_q_splits(b, n_pad) for b in (1, 129, 257, 385))
@@ -320,12 +339,28 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         else:
             self._session_forward(bt)
         ws = self._score_buffers(ps.n_pad, True)
-        nv.counted_call("tcar_score_fwd", 1, p(self.Q), p(ps.iext), p(self.c_ref), p(ws["E"]), p(ws["part"]), None, None,
-                        B, ps.N, ps.n_pad, 0, self._cluster_for(B))
-        nv.counted_call("tcar_ce_finish", 1, p(ws["part"]), p(self.sumexp), p(self.ce), ws["tiles"], B)
+        self._score_and_sum(ws, ps.iext, p(ws["E"]), None, None, B, ps.N, ps.n_pad, 0)
         nv.counted_call("tcar_neg_loss", 1, p(self.a_ic), p(ps.item), p(ps.content), p(bt.neg), p(self.ce),
                         p(self.negloss), p(self.loss), p(self.coef), p(self.dA_neg), B, bt.Nn)
         return self.loss[:B], self.ce[:B]
+
+    def _score_and_sum(self, ws, iext, e_ptr, cmax_ptr, tmax_ptr, B, n_items, n_pad, mode):
+        """Scoring GEMM + softmax sums: E / chunk maxima, self.sumexp, self.ce = logsumexp(S) - S[label], with the
+        overflow guard (pass 2 is two empty launches unless a row's best score beats the label by > 55 nats)."""
+        p, cl = nv.ptr, self._cluster_for(B)
+        q, c, part = p(self.Q), p(self.c_ref), p(ws["part"])
+        if not self.softmax_guard:
+            nv.counted_call("tcar_score_fwd", 1, q, p(iext), c, e_ptr, part, cmax_ptr, tmax_ptr, B, n_items, n_pad,
+                            mode, cl)
+            nv.counted_call("tcar_ce_finish", 1, part, p(self.sumexp), p(self.ce), ws["tiles"], B)
+            return
+        pmax, rowmax = p(ws["pmax"]), p(self.rowmax)
+        nv.counted_call("tcar_score_fwd_guarded", 1, q, p(iext), c, e_ptr, part, cmax_ptr, tmax_ptr, pmax, None, B,
+                        n_items, n_pad, mode, cl)
+        nv.counted_call("tcar_ce_finish_guarded", 1, part, pmax, p(self.sumexp), p(self.ce), rowmax, ws["tiles"], B, 1)
+        nv.counted_call("tcar_score_fwd_guarded", 1, q, p(iext), c, e_ptr, part, cmax_ptr, tmax_ptr, None, rowmax, B,
+                        n_items, n_pad, mode, cl)
+        nv.counted_call("tcar_ce_finish_guarded", 1, part, None, p(self.sumexp), p(self.ce), rowmax, ws["tiles"], B, 2)
 
     def backward(self, bt, scatter=True):
         """Gradients of sum_b loss_b wrt all 23 tensors (model_combine.py:156) into ps.item_g / ps.theta_g.
@@ -461,6 +496,7 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         With next_bt (single GPU): the item rows next_bt gathers are updated first, then the table-wide item update is
         forked onto the side stream and next_bt's session forward is launched behind it on the caller's stream."""
         ps, p = self.ps, nv.ptr
+        ps.version += 1                    # the item table changes: statistics derived from it are stale
         small_done, self._small_done = getattr(self, "_small_done", None), None
         if self._sharded_update():
             nv.counted_call("tcar_sqnorm_segments", 1, p(ps.theta_g), p(ps.seg_off), p(ps.sqnorm_small), len(SMALL))
@@ -613,11 +649,11 @@ class Seq2SeqAttNN(CatalogShardedTraining):
             self.top_scores[:B].fill_(float("-inf"))
             self.n_greater[:B].zero_()
             self.sumexp[:B].zero_()
+            self.rowmax[:B].zero_()
         else:
+            self._ensure_cat_stats()
             ws = self._score_buffers(n_pad, False)
-            nv.counted_call("tcar_score_fwd", 1, p(self.Q), p(iext), p(self.c_ref), None, p(ws["part"]), p(ws["cmax"]),
-                            p(ws["tmax"]), B, n_loc, n_pad, 1, self._cluster_for(B))
-            nv.counted_call("tcar_ce_finish", 1, p(ws["part"]), p(self.sumexp), p(self.ce), ws["tiles"], B)
+            self._score_and_sum(ws, iext, None, p(ws["cmax"]), p(ws["tmax"]), B, n_loc, n_pad, 1)
             a_ic, Tq = self.a_ic, self.Tq
             if ahead:
                 # the exact re-scoring below reads this batch's session vectors: park them before next_bt's forward
@@ -627,21 +663,46 @@ class Seq2SeqAttNN(CatalogShardedTraining):
                 a_ic, Tq = self.a_ic_eval, self.Tq_eval
                 self._prefetch_forward(next_bt)
                 ahead = False
-            nv.counted_call("tcar_eval_topk", 1, p(ws["cmax"]), p(ws["tmax"]), p(a_ic), p(Tq), p(ps.item),
-                            p(ps.content),
-                            p(ps.mwdhm), p(bt.label), p(self.top_ids), p(self.top_scores), p(self.n_greater), B, n_loc,
-                            n_pad, lo)
+            self._topk(ws, a_ic, Tq, bt.label, self._evblock, B, n_loc, n_pad, lo)
         if ahead:
             self._prefetch_forward(next_bt)
         if shard is not None and parallel.is_distributed(self.world):
-            def merge(ids, sc):
-                nv.counted_call("tcar_topk_merge", 1, p(ids), p(sc), p(self.top_ids), p(self.top_scores),
-                                self.world, B)
-                return self.top_ids[:B], self.top_scores[:B]
-            parallel.gather_merge_topk(self.top_ids[:B], self.top_scores[:B], self.n_greater[:B], self.sumexp[:B],
-                                       self.world, merge)
-            torch.log(self.sumexp[:B], out=self.ce[:B])
+            # ONE collective: every rank's result block (top-20 pairs, rank counts, softmax partial sums and their
+            # exponent shifts), then one merge kernel
+            if getattr(self, "_evblocks", None) is None or self._evblocks.shape[0] != self.world:
+                self._evblocks = torch.zeros(self.world, nv.EVAL_BLOCK_WORDS, device=self.dev)
+            parallel.gather_eval_blocks(self._evblock, self.world, out=self._evblocks)
+            return self._merge_blocks(self._evblocks, self.world, B)
         return self.top_ids[:B], self.n_greater[:B], self.ce[:B]
+
+    def _ensure_cat_stats(self):
+        """Largest row norm / bf16 rounding-error norm of the candidate rows (the error bound behind the certified
+        top-20): recomputed only after the item table changed."""
+        ps = self.ps
+        if self._cat_stats_version != ps.version:
+            nv.counted_call("tcar_catalog_stats", 1, nv.ptr(ps.item), nv.ptr(ps.content), 1, ps.N + 1,
+                            nv.ptr(self.cat_stats))
+            self._cat_stats_version = ps.version
+
+    def _topk(self, ws, a_ic, Tq, label, block, B, n_loc, n_pad, lo):
+        """Certified top-20 + rank counts of B queries over the n_loc items behind ws's chunk / tile maxima, written
+        into the result block `block` (TCAR_EVAL_OFF_* planes)."""
+        ps, p = self.ps, nv.ptr
+        bi = block.view(torch.int32)
+        ids, sc, ngt = p(bi[nv.EVAL_OFF_IDS:]), p(block[nv.EVAL_OFF_SCORES:]), p(bi[nv.EVAL_OFF_NGT:])
+        nv.counted_call("tcar_eval_topk_certified", 1, p(ws["cmax"]), p(ws["tmax"]), p(a_ic), p(Tq), p(ps.item),
+                        p(ps.content), p(ps.mwdhm), p(label), ids, sc, ngt, B, n_loc, n_pad, lo, p(self.cat_stats),
+                        p(self.uncertain), p(self.tau))
+        nv.counted_call("tcar_eval_topk_widen", 1, p(ws["cmax"]), p(ws["tmax"]), p(a_ic), p(Tq), p(ps.item),
+                        p(ps.content), p(ps.mwdhm), p(label), p(self.uncertain), p(self.tau), ids, sc, ngt, B, n_loc,
+                        n_pad, lo)
+
+    def _merge_blocks(self, blocks, G, B):
+        """G shard result blocks -> global top-20 ids, rank counts, cross_loss (one launch)."""
+        p = nv.ptr
+        nv.counted_call("tcar_eval_merge", 1, p(blocks), blocks.stride(0), p(self.m_ids), p(self.m_scores),
+                        p(self.m_ngt), p(self.m_ce), G, B)
+        return self.m_ids[:B], self.m_ngt[:B], self.m_ce[:B]
 
     def shard_bounds(self, G):
         """Contiguous item-id ranges [lo, hi) per shard, aligned to 256 rows so that a shard of the bf16 scoring
@@ -655,27 +716,16 @@ class Seq2SeqAttNN(CatalogShardedTraining):
     def eval_step_virtual_shards(self, bt, G):
         """Single-GPU emulation of the catalog-sharded evaluation: every shard is scored in turn and the per-shard
         top-20 lists are merged with the same kernel the NCCL path uses (tests the merge logic without G GPUs)."""
-        B, p = bt.B, nv.ptr
-        ids = torch.empty(G, B, TOPK, device=self.dev, dtype=torch.int32)
-        sc = torch.empty(G, B, TOPK, device=self.dev)
-        ngt = torch.zeros(B, device=self.dev, dtype=torch.int32)
-        sumexp = torch.zeros(B, device=self.dev)
+        B = bt.B
+        blocks = torch.zeros(G, nv.EVAL_BLOCK_WORDS, device=self.dev)
         world, self.world = self.world, 1
         try:
             for g, (lo, hi) in enumerate(self.shard_bounds(G)):
-                if hi <= lo:
-                    ids[g].fill_(-1)
-                    sc[g].fill_(float("-inf"))
-                    continue
-                t, n, _ = self.eval_step(bt, shard=(lo, hi, self.iext_shard(lo, hi)))
-                ids[g].copy_(t)
-                sc[g].copy_(self.top_scores[:B])
-                ngt += n
-                sumexp += self.sumexp[:B]
+                self.eval_step(bt, shard=(lo, hi, self.iext_shard(lo, hi)))
+                blocks[g].copy_(self._evblock)
         finally:
             self.world = world
-        nv.counted_call("tcar_topk_merge", 1, p(ids), p(sc), p(self.top_ids), p(self.top_scores), G, B)
-        return self.top_ids[:B], ngt, torch.log(sumexp)
+        return self._merge_blocks(blocks, G, B)
 
     def softmax_input(self, bt):
         """Debug aid mirroring the reference's `softmax_input` fetch (model_combine.py:138): materialises the

@@ -82,18 +82,32 @@ def catalog_counts(B, world):
     return [hi - lo for lo, hi in (shard_sessions(B, g, world) for g in range(world))]
 
 
-def gather_merge_topk(top_ids, top_scores, n_greater, sumexp, world, merge):
-    """All-gather the per-rank top-20 lists and merge them; sum the rank counts and the softmax partial sums.
-    `merge(ids [G,B,20] int32, scores [G,B,20] f32) -> (ids [B,20], scores [B,20])` must order by
-    (score desc, id asc) and treat id < 0 as an empty slot."""
-    import torch.distributed as dist
+# One shard's evaluation results for <= 512 queries as ONE block of 32-bit words (TCAR_EVAL_OFF_* in
+# include/tcar_b200.h): [scores 512x20 f32 | ids 512x20 i32 | n_greater 512 i32 | sumexp 512 f32 | rowmax 512 f32].
+QROWS = 512
+EVAL_OFF_SCORES, EVAL_OFF_IDS, EVAL_OFF_NGT = 0, QROWS * TOPK, 2 * QROWS * TOPK
+EVAL_OFF_SUMEXP, EVAL_OFF_ROWMAX, EVAL_BLOCK_WORDS = EVAL_OFF_NGT + QROWS, EVAL_OFF_NGT + 2 * QROWS, EVAL_OFF_NGT + 3 * QROWS
+
+
+def pack_eval_block(top_ids, top_scores, n_greater, sumexp, rowmax=None):
+    """Build a result block from separate tensors (the CUDA path writes the planes in place; CPU tests use this)."""
     B = top_ids.shape[0]
-    ids = torch.empty(world * B, TOPK, device=top_ids.device, dtype=torch.int32)
-    sc = torch.empty(world * B, TOPK, device=top_ids.device, dtype=torch.float32)
-    dist.all_gather_into_tensor(ids, top_ids.contiguous())          # rank-major concatenation along dim 0
-    dist.all_gather_into_tensor(sc, top_scores.contiguous())
-    ids, sc = ids.view(world, B, TOPK), sc.view(world, B, TOPK)
-    dist.all_reduce(n_greater, op=dist.ReduceOp.SUM)
-    dist.all_reduce(sumexp, op=dist.ReduceOp.SUM)
-    out_ids, out_sc = merge(ids, sc)
-    return out_ids, out_sc, n_greater, sumexp
+    blk = torch.zeros(EVAL_BLOCK_WORDS, dtype=torch.float32, device=top_ids.device)
+    bi = blk.view(torch.int32)
+    blk[EVAL_OFF_SCORES: EVAL_OFF_SCORES + B * TOPK] = top_scores.reshape(-1).float()
+    bi[EVAL_OFF_IDS: EVAL_OFF_IDS + B * TOPK] = top_ids.reshape(-1).int()
+    bi[EVAL_OFF_NGT: EVAL_OFF_NGT + B] = n_greater.int()
+    blk[EVAL_OFF_SUMEXP: EVAL_OFF_SUMEXP + B] = sumexp.float()
+    if rowmax is not None:
+        blk[EVAL_OFF_ROWMAX: EVAL_OFF_ROWMAX + B] = rowmax.float()
+    return blk
+
+
+def gather_eval_blocks(block, world, out=None):
+    """THE exchange of the catalog-sharded evaluation: one all-gather of every rank's result block -> [world, WORDS]
+    (rank-major).  The merge (tcar_eval_merge in the product path) then runs locally on every rank."""
+    import torch.distributed as dist
+    if out is None:
+        out = torch.empty(world, EVAL_BLOCK_WORDS, dtype=torch.float32, device=block.device)
+    dist.all_gather_into_tensor(out.view(-1), block.contiguous())
+    return out

@@ -91,6 +91,7 @@ class ParamStore:
         self.norm_partial = torch.zeros(1184, device=dev)
         self.norm_ticket = torch.zeros(1, device=dev, dtype=torch.int32)
         self.step = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.version = 0        # bumped whenever the item table changes (load, train step): cached statistics key on it
         # per-row "already updated in step t" marks of tcar_adam_item_rows (cleared whenever `step` is set from outside)
         self.row_flags = torch.zeros(self.rows_alloc, device=dev, dtype=torch.int32)
         self.w = {n: self._view(self.theta, i) for i, (n, _) in enumerate(SMALL)}
@@ -147,6 +148,7 @@ class ParamStore:
             t.zero_()
         self.step.zero_()
         self.row_flags.zero_()
+        self.version += 1
         self.rebuild_iext()
         self.prep_weights()
 

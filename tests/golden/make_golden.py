@@ -46,9 +46,24 @@ def load_reference_model():
     return mod
 
 
-def make_case(mod, name, N, B, T, Nn, emb_stddev, max_grad, seed, hidden=24):
-    """hidden_size is a free flag in the reference (main.py:109) as long as it equals the content width; the
-    fixtures use a small value so they stay a few hundred KB.  time_hidden_size must be 64 (modules.py:138)."""
+DENSE = NAMES[8:]          # the 15 dense tensors, each one tf.random_normal call, in creation order
+
+
+def pack16(a):
+    """float16 with a per-tensor scale (max |a| -> 1): 5e-4 relative per element, enough for the norm-wise 2e-2
+    comparisons the big fixture is used for, at half the bytes."""
+    a = np.asarray(a, dtype=np.float64)
+    s = float(np.abs(a).max()) or 1.0
+    return (a / s).astype(np.float16), np.float64(s)
+
+
+def make_case(mod, name, N, B, T, Nn, emb_stddev, max_grad, seed, hidden=24, compact=False):
+    """hidden_size is a free flag in the reference (main.py:109) as long as it equals the content width; the small
+    fixtures use 24 so they stay a few hundred KB.  time_hidden_size must be 64 (modules.py:138).
+    compact=True (the hidden=250 fixture the CUDA path is compared with directly): initial values are NOT stored --
+    the embedding tables come from the legacy NumPy stream under seed 2020 (modules.py:32) and the dense weights from
+    tf1_shim.rn_values(seed, k, ...), both reproducible from NumPy alone; checksums are stored instead -- and
+    gradients / updates are stored as scaled float16."""
     rs = np.random.RandomState(seed)
     content = rs.normal(0, 0.2, (N + 1, hidden))
     big = rs.choice(np.arange(1, N + 1), N // 4, replace=False)          # a quarter of the rows get norm in (1,3]
@@ -87,18 +102,32 @@ def make_case(mod, name, N, B, T, Nn, emb_stddev, max_grad, seed, hidden=24):
     for k, v in feed.items():
         if k != "is_training":
             out["feed_" + k] = v
+    out["seed"], out["emb_stddev"], out["hidden"] = np.int64(seed), np.float64(emb_stddev), np.int64(hidden)
     for n, v, g, c in zip(NAMES, tv, tf.STATE["grads"], tf.STATE["capped"]):
         init = tf.STATE["init"][id(v)].numpy()
         assert (init.astype(np.float32).astype(np.float64) == init).all()   # variables are float32 in the reference
-        out["init_" + n] = init.astype(np.float32)
-        out["grad_" + n] = g.numpy().astype(np.float32)                     # raw d(sum loss)/d var
-        out["delta_" + n] = (v.detach().numpy() - init).astype(np.float32)  # Adam update after clip_by_norm
+        delta = v.detach().numpy() - init
+        if compact:
+            out["initsum_" + n] = np.array([init.sum(), (init * init).sum()])
+            out["grad16_" + n], out["gradscale_" + n] = pack16(g.numpy())
+            if n not in DENSE or init.ndim == 1:
+                out["delta16_" + n], out["deltascale_" + n] = pack16(delta)
+        else:
+            out["init_" + n] = init.astype(np.float32)
+            out["grad_" + n] = g.numpy().astype(np.float32)                 # raw d(sum loss)/d var
+            out["delta_" + n] = delta.astype(np.float32)                    # Adam update after clip_by_norm
+        out["gradnorm_" + n] = np.float64(np.linalg.norm(g.numpy()))
         out["capnorm_" + n] = np.float64(np.linalg.norm(c.numpy()))         # ||clip_by_norm(g)||
+        sq = tf.STATE["slices_sq"][id(v)]
+        # norm tf.clip_by_norm sees: un-aggregated IndexedSlices values for lookup-only tables, else the dense norm
+        out["clipnorm_" + n] = np.float64(np.sqrt(sq)) if sq is not None else out["gradnorm_" + n]
+        out["sliced_" + n] = np.bool_(sq is not None)
     out["softmax_input"] = model.softmax_input.detach().numpy()
     out["cross_loss"] = model.cross_loss.detach().numpy()
     out["loss"] = model.loss.detach().numpy()
     np.savez_compressed(os.path.join(HERE, name), **out)
-    print(name, "loss", out["loss"].ravel()[:3], "|g_item|", np.linalg.norm(out["grad_item"]))
+    print(name, "loss", out["loss"].ravel()[:3], "|g_item|", float(out["gradnorm_item"]), "clip norms TF / dense:",
+          {n: (round(float(out["clipnorm_" + n]), 4), round(float(out["gradnorm_" + n]), 4)) for n in NAMES[1:8]})
     return model
 
 
@@ -186,5 +215,8 @@ if __name__ == "__main__":
     make_case(mod, "tcar_ref_default.npz", N=300, B=6, T=4, Nn=5, emb_stddev=0.002, max_grad=150, seed=1)
     make_case(mod, "tcar_ref_clip.npz", N=257, B=7, T=3, Nn=4, emb_stddev=0.2, max_grad=0.5, seed=2)
     make_case(mod, "tcar_ref_t1.npz", N=120, B=3, T=1, Nn=2, emb_stddev=0.05, max_grad=150, seed=3)
+    # the product's own width (hidden_size 250): compared DIRECTLY with the CUDA path (tests/test_gpu_golden.py)
+    make_case(mod, "tcar_ref_h250.npz", N=300, B=6, T=4, Nn=5, emb_stddev=0.05, max_grad=150, seed=4, hidden=250,
+              compact=True)
     make_sampler_golden()
     make_metrics_golden(mod)

@@ -458,3 +458,248 @@ def test_score_bwd_i_accumulate():
     ctas = nv_lib().tcar_score_bwd_i_ctas(ps.n_pad)
     want = float((ps.item_g.double() ** 2).sum())
     assert abs(float(model.sq_partial[:ctas].double().sum()) - want) <= 1e-4 * want + 1e-12
+
+
+# ------------------------------------------------------------------------------------------- softmax overflow guard
+def _overflow_setup(N, B, T, Nn, gap_lo=100.0, gap_hi=250.0, catalog_shards=0):
+    """A catalog in which a few un-clicked items outscore every label by 100-250 nats (scaled content rows): with the
+    label score as the only exponent shift exp(S - c) overflows fp32; TF's max-subtracted softmax
+    (tf.nn.sparse_softmax_cross_entropy_with_logits, model_combine.py:145) stays finite."""
+    from tcar_b200 import synth
+    from tcar_b200.model_combine import Seq2SeqAttNN
+    content, mwdhm, category = synth.make_catalog(N, seed=3)
+    packed = synth.make_index_batch(N, B, T, Nn, mwdhm, seed=21)
+    batch = {k: torch.from_numpy(v) for k, v in synth.unpack(packed, B, T, Nn).items()}
+    used = set(batch["seq"].numpy().ravel().tolist()) | set((batch["label"].numpy() + 1).tolist())
+    hot = [r for r in range(1, N + 1) if r not in used][:6]
+    scale = 40.0
+    for _ in range(12):
+        c2 = content.copy()
+        c2[hot] *= scale / np.linalg.norm(c2[hot], axis=1, keepdims=True)
+        np.random.seed(2020)
+        args = dict(publish_time_MWDHM=mwdhm, itemnum=N, category_id=None, item_freq_dict_norm={}, reverse_item=None,
+                    content_emb=c2, emb_stddev=0.05, stddev=0.05, hidden_size=250, time_hidden_size=64, l2_emb=0.0,
+                    batch_size=512, epoch=1, neg_num=Nn, lr=0.001, max_grad=150)
+        if catalog_shards:
+            args.update(train_parallel="catalog", catalog_virtual_shards=catalog_shards)
+        model = Seq2SeqAttNN(args)
+        params, c64, m64 = oracle_inputs(model, c2, mwdhm)
+        with torch.no_grad():
+            S = O.forward(params, c64, m64, batch)["softmax_input"]
+        gap = (S.max(1).values - S.gather(1, batch["label"][:, None]).squeeze(1))
+        if float(gap.max()) > gap_hi:
+            scale *= 0.7
+        elif float(gap.max()) < gap_lo:
+            scale *= 1.6
+        else:
+            break
+    assert gap_lo <= float(gap.max()) <= gap_hi, float(gap.max())
+    bt = model.to_device(torch.from_numpy(packed).pin_memory(), B, T, Nn)
+    return model, bt, batch, params, c64, m64, gap
+
+
+@pytest.mark.parametrize("shards", [0, 3])
+def test_softmax_overflow_guard_train_step_stays_finite_and_exact(shards):
+    N, B, T, Nn = 3000, 96, 3, 20
+    model, bt, batch, params, c64, m64, gap = _overflow_setup(N, B, T, Nn, catalog_shards=shards)
+    assert float(gap.max()) > 100 and float(gap.min()) < 60, "rows above and below the limit in one batch"
+    out, grads = O.loss_and_grads(params, c64, m64, batch)
+    if shards:
+        loss = model.train_step(bt)
+        ce = model.ce[:B]
+    else:
+        loss, ce = model.forward_train(bt)
+        model.backward(bt)
+    torch.cuda.synchronize()
+    assert torch.isfinite(ce).all() and torch.isfinite(loss).all()
+    # CE = logsumexp - label score ~ the margin itself: bf16 rounding of a score of ~150 is ~0.3 -> relative bound
+    np.testing.assert_allclose(ce.cpu().double().numpy(), out["cross_loss"].numpy().ravel(), rtol=5e-3, atol=2e-2)
+    shifted = (model.rowmax[:B] > 80.0).cpu().numpy() if not shards else (model._rowmax_all[0, :B] > 80.0).cpu().numpy()
+    assert shifted.any() and not shifted.all()
+    assert ((gap.numpy() * np.log2(np.e) > 85) <= shifted).all()
+    got = model.ps.export_grads()
+    assert all(torch.isfinite(v).all() for v in got.values())
+    if not shards:
+        # softmax mass sits on one or two items whose bf16 scores are ~0.3 off: the gradient is dominated by those
+        # rows; require the direction (cosine) rather than 2e-2 norm-wise
+        for k in ("item", "W_a", "b_a", "W_in"):
+            a, b = got[k].double().flatten(), grads[k].double().flatten()
+            cos = float((a @ b) / (a.norm() * b.norm() + 1e-30))
+            assert cos > 0.9, (k, cos)
+
+
+def test_softmax_overflow_guard_is_a_noop_below_the_limit():
+    """Same batch with and without the guard: bit-identical loss, E and gradients when no row is above the limit."""
+    N, B, T = 3000, 130, 4
+    outs = []
+    for guard in (True, False):
+        model, content, mwdhm, _ = build(N, emb_scale=20.0)
+        model.softmax_guard = guard
+        bt, _ = batch_for(model, N, B, T, 20, mwdhm, seed=8)
+        loss, ce = model.forward_train(bt)
+        model.backward(bt)
+        torch.cuda.synchronize()
+        if guard:
+            assert float(model.rowmax[:B].max()) < 80.0
+        outs.append((loss.clone(), ce.clone(), model._score_buffers(model.ps.n_pad, True)["E"].clone(),
+                     model.ps.item_g.clone(), model.ps.theta_g.clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
+def test_softmax_overflow_guard_eval_loss():
+    N, B, T = 3000, 64, 3
+    model, bt, batch, params, c64, m64, gap = _overflow_setup(N, B, T, 0)
+    with torch.no_grad():
+        ref = O.forward(params, c64, m64, batch)["cross_loss"].numpy().ravel()
+    for G in (1, 4):
+        _, _, ce = model.eval_step(bt) if G == 1 else model.eval_step_virtual_shards(bt, G)
+        torch.cuda.synchronize()
+        assert torch.isfinite(ce).all()
+        np.testing.assert_allclose(ce.cpu().double().numpy(), ref, rtol=5e-3, atol=2e-2)
+
+
+# ------------------------------------------------------------------------------------------- certified top-20
+def test_eval_topk_widening_reproduces_the_certified_result():
+    """Forcing every query through tcar_eval_topk_widen (a huge error bound: tau falls below every chunk maximum, i.e.
+    a full exact scan) must give the ids the certified fast path gives, and exact ranks."""
+    N, B, T = 6000, 64, 3
+    model, content, mwdhm, args = build(N, emb_scale=20.0)
+    bt, batch = batch_for(model, N, B, T, 0, mwdhm, seed=12)
+    top1, n1, _ = [x.clone() for x in model.eval_step(bt)]
+    unc1 = model.uncertain[:B].clone()
+    model.cat_stats.fill_(1e4)                      # eps_b ~ 1e4 ||q||: nothing can be certified
+    top2, n2, _ = [x.clone() for x in model.eval_step(bt)]
+    torch.cuda.synchronize()
+    assert int(model.uncertain[:B].sum()) == B and int(unc1.sum()) < B
+    assert torch.equal(top1, top2)
+    # after the full scan n_greater is the exact count over the whole catalog
+    params, c64, m64 = oracle_inputs(model, content, mwdhm)
+    ref = O.eval_batch(params, c64, m64, batch, args["category_id"], args["reverse_item"])
+    labels = batch["label"].numpy()
+    ref_cnt = np.array([int((row[l] < row).sum()) for row, l in zip(ref["scores"], labels)])
+    lab_s = ref["scores"][np.arange(B), labels]
+    near = np.array([np.abs(row - s).min(initial=np.inf, where=np.arange(N) != l) < 2e-5 * max(1.0, abs(s))
+                     for row, s, l in zip(ref["scores"], lab_s, labels)])
+    assert (n2.cpu().numpy() == ref_cnt)[~near].all()
+    hit = n1 < 20
+    assert torch.equal(n1[hit], n2[hit])
+
+
+def test_eval_topk_certification_catches_near_ties_outside_the_candidates():
+    """40 catalog rows per 'cluster' made nearly identical (scores within the bf16 error of each other): the 32-chunk
+    candidate set cannot be certified, the widened pass must still return the exact top-20 (ties to the lower id)."""
+    N, B, T = 20000, 48, 2
+    model, content, mwdhm, args = build(N, emb_scale=20.0)
+    p = model.ps.export()
+    rs = np.random.RandomState(1)
+    cont, mw = content.copy(), mwdhm.copy()
+    # clusters of 40 copies spread over distinct 8-item chunks, each copy perturbed by ~1e-4 relative
+    for c in range(6):
+        src = int(rs.randint(0, N))
+        dst = rs.choice(N // 8, 40, replace=False) * 8 + rs.randint(0, 8, 40)
+        for d_ in dst:
+            p["item"][d_ + 1] = p["item"][src + 1] * (1 + 1e-4 * float(rs.randn()))
+            cont[d_ + 1] = cont[src + 1] * (1 + 1e-4 * float(rs.randn()))
+            mw[d_] = mw[src]
+    from tcar_b200.params import ParamStore
+    model.ps = ParamStore(N, cont, mw, model.dev)
+    model.ps.load(p)
+    bt, batch = batch_for(model, N, B, T, 0, mw, seed=13)
+    params, c64, m64 = oracle_inputs(model, cont, mw)
+    ref = O.eval_batch(params, c64, m64, batch, args["category_id"], args["reverse_item"])
+    top, _, _ = model.eval_step(bt)
+    torch.cuda.synchronize()
+    top = top.cpu().numpy()
+    # fp32 exact re-scoring vs fp64 oracle: compare as sets with a score tolerance at the boundary
+    S = ref["scores"]
+    for b in range(B):
+        got = set(top[b].tolist())
+        kth = np.sort(S[b])[::-1][19]
+        must = set(np.nonzero(S[b] > kth + 1e-4 * max(1.0, abs(kth)))[0].tolist())
+        may = set(np.nonzero(S[b] >= kth - 1e-4 * max(1.0, abs(kth)))[0].tolist())
+        assert must <= got <= may, b
+    assert int(model.uncertain[:B].sum()) > 0, "fixture should defeat the plain 32-chunk certificate for some queries"
+
+
+# ------------------------------------------------------------------------------------------- benchmarked size
+GLOBO_N = 364047
+
+
+@pytest.mark.parametrize("T", [1, 20])
+def test_eval_at_the_benchmarked_catalog_size(T):
+    """BASELINE config 2/3 size: N = 364 047 (1 423 item tiles of 256, tail tile of 47 items), B = 64."""
+    N, B = GLOBO_N, 64
+    model, content, mwdhm, args = build(N, emb_scale=20.0)
+    bt, batch = batch_for(model, N, B, T, 0, mwdhm, seed=31 + T)
+    params, c64, m64 = oracle_inputs(model, content, mwdhm)
+    with torch.no_grad():
+        out = O.forward(params, c64, m64, batch)
+    S = out["softmax_input"].numpy()
+    top, ngt, ce = model.eval_step(bt)
+    torch.cuda.synchronize()
+    top, ngt = top.cpu().numpy(), ngt.cpu().numpy()
+    ok = margin_ok(S)
+    assert ok.mean() > 0.5
+    ref_top = O.top20(S)
+    assert (top[ok] == ref_top[ok]).all(), "top-20 ids bit-exact on margin-checked queries at N = 364 047"
+    labels = batch["label"].numpy()
+    ref_rank = np.array([int((row[l] < row).sum()) + 1 for row, l in zip(S, labels)])
+    hit = ref_rank <= 20
+    assert ((ngt + 1 <= 20) == hit)[ok].all() and (ngt + 1 == ref_rank)[ok & hit].all()
+    np.testing.assert_allclose(ce.cpu().numpy(), out["cross_loss"].numpy().ravel(), rtol=5e-3, atol=2e-2)
+    # the tail tile: an item among the last 47 must be reachable
+    assert (top < N).all() and (top >= 0).all()
+
+
+def test_train_step_at_the_benchmarked_catalog_size():
+    N, B, T, Nn = GLOBO_N, 64, 5, 20
+    model, content, mwdhm, _ = build(N, emb_scale=20.0)
+    bt, batch = batch_for(model, N, B, T, Nn, mwdhm, seed=41)
+    # a label and a negative inside the 47-item tail tile
+    params, c64, m64 = oracle_inputs(model, content, mwdhm)
+    out, grads = O.loss_and_grads(params, c64, m64, batch)
+    loss, ce = model.forward_train(bt)
+    model.backward(bt)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(loss.cpu().double().numpy(), out["loss"].numpy().ravel(), rtol=5e-3, atol=2e-2)
+    got = model.ps.export_grads()
+    total = float(torch.sqrt(sum((grads[k].double() ** 2).sum() for k in O.PARAM_ORDER)))
+    errs = {k: float((got[k].double() - grads[k].double()).norm()) / (float(grads[k].double().norm()) + 5e-6 * total)
+            for k in O.PARAM_ORDER}
+    bad = {k: v for k, v in errs.items() if v > 2e-2}
+    assert not bad, f"gradient norm-wise rel err too large at N = {N}: {bad}"
+    # rows of the tail tile (items N-47 .. N-1) carry a dense softmax gradient like every other row
+    tail = got["item"][N - 46:].double()
+    ref_tail = grads["item"][N - 46:].double()
+    assert float((tail - ref_tail).norm()) <= 2e-2 * float(ref_tail.norm()) + 1e-9
+
+
+# ------------------------------------------------------------------------------------------- checkpoint / dump (8f-4)
+def test_checkpoint_save_restore_gives_identical_eval_and_training(tmp_path):
+    """util.save_model / restore_model (the reference's own save_model is broken, util.py:102-106): parameters, Adam
+    moments and the step counter round-trip, so evaluation AND the next train step are bit-identical."""
+    from tcar_b200 import util
+    N, B, T = 4000, 96, 4
+    model, content, mwdhm, args = build(N, emb_scale=20.0)
+    bts = [batch_for(model, N, B, T, 20, mwdhm, seed=60 + i)[0] for i in range(3)]
+    for bt in bts[:2]:
+        model.train_step(bt)
+    cargs = dict(args, dataset="synth/TCAR-mid/", split_way="Normal/", foldnum=0, modelpath=str(tmp_path) + "/")
+    path = util.save_model(model, cargs)
+    eb, _ = batch_for(model, N, B, T, 0, mwdhm, seed=70)
+    want_eval = [x.clone() for x in model.eval_step(eb)]
+    want_loss = model.train_step(bts[2]).clone()
+    model.sync_updates()
+    want_item, want_m = model.ps.item.clone(), model.ps.item_m.clone()
+    fresh, _, _, _ = build(N, emb_scale=3.0)             # different initial values on purpose
+    util.restore_model(fresh, path)
+    assert int(fresh.ps.step.item()) == 2
+    got_eval = fresh.eval_step(batch_for(fresh, N, B, T, 0, mwdhm, seed=70)[0])
+    for a, b in zip(want_eval, got_eval):
+        assert torch.equal(a, b)
+    got_loss = fresh.train_step(batch_for(fresh, N, B, T, 20, mwdhm, seed=62)[0])
+    fresh.sync_updates()
+    torch.cuda.synchronize()
+    assert torch.equal(want_loss, got_loss)
+    assert torch.equal(want_item, fresh.ps.item) and torch.equal(want_m, fresh.ps.item_m)

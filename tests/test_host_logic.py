@@ -228,3 +228,25 @@ def test_cfg1_plumbing_epoch_on_cpu():
         n += B
     assert n == sum(len(v) for v in test[0].values())
     assert 0.0 <= float(np.mean(recall)) <= 1.0 and 0.0 <= float(np.mean(mrr)) <= 1.0
+
+
+def test_print_data_dump_parses_with_the_reference_evaluation_script(tmp_path, monkeypatch):
+    """--is_print dump (model_combine.py:165-169): every line must split the way data_process/evaluation_predict.py:16-26
+    splits it (restated below: the script itself reads a hard-coded path and cannot be imported as a function of text)."""
+    from tcar_b200.model_combine import Seq2SeqAttNN
+    monkeypatch.chdir(tmp_path)
+    batch_in = [[5, 17, 3], [9, 9, 1]]
+    batch_out = [41, 0]
+    batch_pred = [[7, 41, 2, 300000], []]                 # an empty recommendation list is legal (pred_split[0] == '')
+    Seq2SeqAttNN.printData(None, "0_3", batch_in, batch_out, batch_pred)
+    Seq2SeqAttNN.printData(None, "0_3", batch_in[:1], batch_out[:1], batch_pred[:1])      # appended ('a+')
+    lines = open(tmp_path / "saved" / "CAR+P_Normal_predict_exa_0_3.txt").readlines()
+    assert len(lines) == 3
+    got = []
+    for line in lines:
+        in_ = [int(x) for x in line.split("# batch in: [")[1].split("]")[0].split(", ")]       # evaluation_predict.py:16
+        out_ = int(line.split("# batch out: ")[1].split(" #")[0])                              # :18
+        pred_split = line.split("# batch pred: [")[1].split("]")[0].split(", ")                # :19
+        pred_ = [] if pred_split[0] == "" else [int(x) for x in pred_split]                    # :20-23
+        got.append((in_, out_, pred_))
+    assert got == [(batch_in[0], 41, batch_pred[0]), (batch_in[1], 0, []), (batch_in[0], 41, batch_pred[0])]

@@ -110,24 +110,37 @@ def _sharded_eval(rank, world):
         top_i[b, : len(o)] = ids[o]
         top_s[b, : len(o)] = loc[b, o]
     ngt = torch.from_numpy((loc > S[np.arange(B), label][:, None]).sum(1).astype(np.int32))
-    sumexp = torch.from_numpy(np.exp(loc.astype(np.float64)).sum(1).astype(np.float32))
-
-    def merge(i, s):
-        oi, os_ = O.merge_topk(i.numpy(), s.numpy())
-        return torch.from_numpy(oi), torch.from_numpy(os_)
-
-    oi, os_, ngt, sumexp = parallel.gather_merge_topk(torch.from_numpy(top_i), torch.from_numpy(top_s), ngt, sumexp,
-                                                      world, merge)
-    return oi.numpy(), ngt.numpy(), sumexp.numpy(), S, label
+    # softmax partial sums relative to the label score; the second rank's are additionally shifted by its row maximum
+    # (what the overflow guard does for a shard whose best score beats the label by more than the limit)
+    c = S[np.arange(B), label].astype(np.float64)
+    arg2 = (loc.astype(np.float64) - c[:, None]) * np.log2(np.e)
+    rowmax = arg2.max(1)
+    if rank == 1:
+        rowmax += 100.0                               # pretend huge margins: forces the shifted representation
+        arg2 += 100.0
+    shift = np.where(rowmax > O.EXP_LIMIT2, rowmax, 0.0)
+    sumexp = torch.from_numpy(np.exp2(arg2 - shift[:, None]).sum(1).astype(np.float32))
+    blk = parallel.pack_eval_block(torch.from_numpy(top_i), torch.from_numpy(top_s), ngt, sumexp,
+                                   torch.from_numpy(rowmax.astype(np.float32)))
+    blocks = parallel.gather_eval_blocks(blk, world)                  # ONE collective
+    oi, os_, ngt, ce = O.merge_eval_blocks(blocks.numpy(), B)
+    return oi, ngt, ce, S, label, lo, hi
 
 
 def test_catalog_sharded_eval_equals_unsharded():
     out = _spawn(_sharded_eval, 2)
-    for oi, ngt, sumexp, S, label in out:
+    for oi, ngt, ce, S, label, lo, hi in out:
         np.testing.assert_array_equal(oi, O.top20(S))
         ref_rank = np.array([int((row[l] < row).sum()) for row, l in zip(S, label)])
         np.testing.assert_array_equal(ngt, ref_rank)
-        np.testing.assert_allclose(sumexp, np.exp(S.astype(np.float64)).sum(1), rtol=1e-5)
+        # reference CE with the second shard's scores raised by 100 log2 units (as the worker pretended)
+        S2 = S.astype(np.float64).copy()
+        lo1, hi1 = out[1][5], out[1][6]
+        S2[:, lo1:hi1] += 100.0 * np.log(2.0)
+        c = S[np.arange(len(label)), label].astype(np.float64)
+        m = S2.max(1)
+        want = np.log(np.exp(S2 - m[:, None]).sum(1)) + m - c
+        np.testing.assert_allclose(ce, want, rtol=1e-5)
 
 
 # ---------------------------------------------------------------------------------------------- catalog-sharded training
