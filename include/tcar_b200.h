@@ -42,6 +42,7 @@ extern "C" {
 #define TCAR_EVAL_OFF_SUMEXP (TCAR_EVAL_OFF_NGT + TCAR_QROWS)   /* float [512] softmax partial sum                   */
 #define TCAR_EVAL_OFF_ROWMAX (TCAR_EVAL_OFF_SUMEXP + TCAR_QROWS) /* float [512] largest exponent argument (guard)    */
 #define TCAR_EVAL_BLOCK_WORDS (TCAR_EVAL_OFF_ROWMAX + TCAR_QROWS)
+#define TCAR_WIDEN_SPLITS 16      /* CTAs sharing one flagged query in tcar_eval_topk_widen                       */
 #define TCAR_NORM_SPLIT 8    /* partial sums per tensor written by tcar_sqnorm_segments                     */
 #define TCAR_TABLE_GRAD_CHUNKS 148   /* max click chunks (CTAs) of tcar_small_table_grads pass 1               */
 #define TCAR_TABLE_GRAD_PART 19600   /* floats of partial sums per chunk: 139x64 + 11x64 + 40x250              */
@@ -414,12 +415,15 @@ int tcar_eval_topk_certified(const float* chunkmax, const float* tilemax, const 
                              const float* item, const float* content, const int32_t* mwdhm, const int32_t* label,
                              int32_t* top_ids, float* top_scores, int32_t* n_greater, int B, int N, int n_pad,
                              int item_offset, const float* cat_stats, int32_t* uncertain, float* tau, void* stream);
-/* Second stage: for every flagged query, re-scores ALL chunks whose maximum reaches tau[b] (any number of them, 32 at a
- * time) and rewrites its top_ids / top_scores / n_greater; certified queries are untouched (their CTA returns). */
+/* Second stage: for every flagged query, re-scores ALL chunks whose maximum reaches tau[b] (any number of them -- in
+ * the limit a full exact scan, so the work of one query is spread over TCAR_WIDEN_SPLITS CTAs and their partial lists
+ * are merged by a second launch) and rewrites its top_ids / top_scores / n_greater; certified queries are untouched
+ * (their CTAs return).  workspace: tcar_eval_topk_widen_ws_bytes(B) bytes. */
+long long tcar_eval_topk_widen_ws_bytes(int B);
 int tcar_eval_topk_widen(const float* chunkmax, const float* tilemax, const float* a_ic, const float* Tq,
                          const float* item, const float* content, const int32_t* mwdhm, const int32_t* label,
                          const int32_t* uncertain, const float* tau, int32_t* top_ids, float* top_scores,
-                         int32_t* n_greater, int B, int N, int n_pad, int item_offset, void* stream);
+                         int32_t* n_greater, int B, int N, int n_pad, int item_offset, void* workspace, void* stream);
 /* out2[0] = max ||[item | content] row||_2, out2[1] = max ||row - bf16(row)||_2 over table rows [row_lo, row_hi)
  * (row = item id + 1).  Needed again only after the item table changed. */
 int tcar_catalog_stats(const float* item, const float* content, int row_lo, int row_hi, float* out2, void* stream);

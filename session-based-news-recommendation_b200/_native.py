@@ -75,7 +75,8 @@ SIGNATURES = {
     "tcar_refresh_iext_items": [_P, _P, _I, _P],
     "tcar_eval_topk": [_P] * 11 + [_I] * 4 + [_P],
     "tcar_eval_topk_certified": [_P] * 11 + [_I] * 4 + [_P] * 3 + [_P],
-    "tcar_eval_topk_widen": [_P] * 13 + [_I] * 4 + [_P],
+    "tcar_eval_topk_widen": [_P] * 13 + [_I] * 4 + [_P, _P],
+    "tcar_eval_topk_widen_ws_bytes": [_I],
     "tcar_catalog_stats": [_P, _P, _I, _I, _P, _P],
     "tcar_topk_merge": [_P] * 4 + [_I, _I, _P],
     "tcar_eval_merge": [_P, _LL, _P, _P, _P, _P, _I, _I, _P],
@@ -99,7 +100,7 @@ def lib():
         for name, argtypes in SIGNATURES.items():
             fn = getattr(l, name)
             fn.argtypes = argtypes
-            fn.restype = C.c_longlong if name.endswith("_part_elems") else C.c_int
+            fn.restype = C.c_longlong if name.endswith(("_part_elems", "_ws_bytes")) else C.c_int
         _lib = l
     return _lib
 

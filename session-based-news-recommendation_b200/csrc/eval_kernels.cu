@@ -123,47 +123,55 @@ __device__ __forceinline__ void select_top(const float* __restrict__ vals, int n
 
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
-__device__ __forceinline__ float block_sum_e(float v, float* red) {
-    v = warp_sum_e(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    float t = 0.f;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
-    return t;
-}
-
 // eps_b >= |S_gemm[b,n] - S_exact[b,n]| for every item n of the catalog the statistics were taken over:
 //   S_gemm = bf(q) . bf(i) + sum_k bf(Tq[k, idx_k])   (exact products, fp32 accumulation on the tensor cores)
 //   S_exact = q . i + sum_k Tq[k, idx_k]              (fp32 FMA chain, exact_score_e)
 //   q . i - bf(q) . bf(i) = dq . i + bf(q) . di  ->  <= ||dq|| max||i|| + ||bf(q)|| max||di||   (Cauchy-Schwarz)
 // plus the rounding of the five time terms and 2e-4 of the magnitudes for the two fp32 accumulations.
+// Block-wide (256 threads); `red` = 32 floats of scratch.  One pass over the session vector, one over the 139 bins.
 __device__ __forceinline__ float score_error_bound(const float* s_aic, const float* s_tq, const float* cat_stats,
                                                    float* red) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     float dq2 = 0.f, q2 = 0.f, f2 = 0.f;
-    for (int c = threadIdx.x; c < XW; c += blockDim.x) {
+    for (int c = tid; c < XW; c += 256) {
         const float v = s_aic[c], r = bf16_round(v);
         dq2 = fmaf(v - r, v - r, dq2);
         q2 = fmaf(r, r, q2);
         f2 = fmaf(v, v, f2);
     }
-    dq2 = block_sum_e(dq2, red);
-    q2 = block_sum_e(q2, red);
-    f2 = block_sum_e(f2, red);
+    dq2 = warp_sum_e(dq2);
+    q2 = warp_sum_e(q2);
+    f2 = warp_sum_e(f2);
+    // time bins: thread r < 139 owns one bin; per-table maxima of |rounding error| and |value| by warp 0 afterwards
+    __syncthreads();
+    if (lane == 0) { red[w] = dq2; red[8 + w] = q2; red[16 + w] = f2; }
+    __shared__ float s_te[NB + 1], s_tm[NB + 1];
+    if (tid < NB) {
+        const float v = s_tq[tid];
+        s_te[tid] = fabsf(v - bf16_round(v));
+        s_tm[tid] = fabsf(v);
+    }
+    __syncthreads();
+    dq2 = q2 = f2 = 0.f;
+    for (int i = 0; i < 8; ++i) { dq2 += red[i]; q2 += red[8 + i]; f2 += red[16 + i]; }
     float terr = 0.f, tmag = 0.f;
-    for (int k = 0; k < 5; ++k) {
-        float e = 0.f, m = 0.f;
-        for (int r = kBinOffE[k]; r < kBinOffE[k + 1]; ++r) {
-            const float v = s_tq[r];
-            e = fmaxf(e, fabsf(v - bf16_round(v)));
-            m = fmaxf(m, fabsf(v));
+    if (w == 0) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            float e = 0.f, m = 0.f;
+            for (int r = kBinOffE[k] + lane; r < kBinOffE[k + 1]; r += 32) { e = fmaxf(e, s_te[r]); m = fmaxf(m, s_tm[r]); }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                e = fmaxf(e, __shfl_xor_sync(0xffffffffu, e, o));
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            }
+            terr += e;
+            tmag += m;
         }
-        terr += e;
-        tmag += m;
     }
     const float imax = cat_stats[0], dimax = cat_stats[1];
     const float eps = sqrtf(dq2) * imax + sqrtf(q2) * dimax + terr + 2e-4f * (sqrtf(f2) * imax + tmag);
-    return eps * 1.0001f + 1e-30f;
+    return eps * 1.0001f + 1e-30f;          // valid in warp 0 (thread 0 consumes it)
 }
 
 constexpr int TILE_CH = 128 / CH;          // 16 chunks per 128-item tile
@@ -180,7 +188,7 @@ eval_topk_kernel(const float* __restrict__ chunkmax, const float* __restrict__ t
                  const float* __restrict__ cat_stats, int32_t* __restrict__ uncertain, float* __restrict__ tau) {
     PDL_ENTER();
     __shared__ float s_aic[XW], s_tq[NB + 1];
-    __shared__ float s_red[8];
+    __shared__ float s_red[32];
     __shared__ uint32_t s_tilebits[(TCAR_MAX_EVAL_TILES + 31) / 32];
     float unsel_max = -INFINITY;         // largest bf16 score an item outside the re-scored chunks can have
     __shared__ int s_hist[256];
@@ -264,6 +272,9 @@ eval_topk_kernel(const float* __restrict__ chunkmax, const float* __restrict__ t
         lab_score = ls;
     }
     for (int j = 0; j < 32; ++j) {
+        // one candidate per warp iteration: 3-4 CTAs per SM x 8 warps keep ~50 KB of row loads in flight per SM, which
+        // already saturates L2/HBM for these 2 KB random rows (a 4-way unrolled variant needed 110 registers, fell to
+        // 2 CTAs per SM and was slower: 151 vs 121 us)
         const int ci = w * 32 + j;
         const int chunk = s_sel[ci / CH];
         const int n = chunk < 0 ? -1 : chunk * CH + (ci % CH);          // local item id
@@ -324,8 +335,12 @@ eval_topk_kernel(const float* __restrict__ chunkmax, const float* __restrict__ t
 // is re-scored exactly (tiles below tau are skipped by their tile maximum), 32 chunks at a time, and merged into a
 // running top-20 by (score desc, id asc); n_greater is counted over the same exact scores.  The result is the exact
 // top-20 of the whole catalog (items below tau cannot reach the 20th score already found).  Cost grows with the number
-// of near-ties; a certified query costs nothing (its CTA returns at once).
+// of near-ties (in the limit a full exact scan), so a flagged query is spread over TCAR_WIDEN_SPLITS CTAs, each taking
+// a contiguous range of tiles and leaving a partial list in the workspace; the merge kernel behind it combines them.
+// A certified query costs nothing (its CTAs return at once).
 constexpr int WQ_CAP = 4096;        // chunk queue: one sweep of 256 tiles x 16 chunks
+constexpr int WSPLIT = TCAR_WIDEN_SPLITS;
+constexpr int WIDEN_SLOTS = 37;     // x 16 splits = 592 CTAs = 4 per SM: one wave
 
 __global__ void __launch_bounds__(256)
 eval_topk_widen_kernel(const float* __restrict__ chunkmax, const float* __restrict__ tilemax,
@@ -333,10 +348,28 @@ eval_topk_widen_kernel(const float* __restrict__ chunkmax, const float* __restri
                        const float* __restrict__ content, const int32_t* __restrict__ mwdhm,
                        const int32_t* __restrict__ label, const int32_t* __restrict__ uncertain,
                        const float* __restrict__ tau, int32_t* __restrict__ top_ids, float* __restrict__ top_scores,
-                       int32_t* __restrict__ n_greater, int N, int n_pad, int item_offset) {
+                       int32_t* __restrict__ n_greater, int N, int n_pad, int item_offset, int B) {
     PDL_ENTER();
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    if (!uncertain[b]) return;
+    const int split = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    // compact list of the flagged queries (ascending, built identically by every CTA): the grid is WIDEN_SLOTS x
+    // WSPLIT CTAs whatever B is, CTA (i, s) takes the flagged queries i, i + WIDEN_SLOTS, ...
+    __shared__ int s_flag[TCAR_QROWS];
+    __shared__ int s_unc[TCAR_QROWS];
+    __shared__ int s_nflag;
+    for (int i = tid; i < TCAR_QROWS; i += 256) s_unc[i] = i < B ? uncertain[i] : 0;    // two loads in flight per thread
+    __syncthreads();
+    if (w == 0) {
+        int cnt = 0;
+        for (int base = 0; base < B; base += 32) {
+            const bool f = s_unc[base + lane] != 0;
+            const uint32_t bal = __ballot_sync(0xffffffffu, f);
+            if (f) s_flag[cnt + __popc(bal & ((1u << lane) - 1u))] = base + lane;
+            cnt += __popc(bal);
+        }
+        if (lane == 0) s_nflag = cnt;
+    }
+    __syncthreads();
+    if ((int)blockIdx.x >= s_nflag) return;
     __shared__ float s_aic[XW], s_tq[NB + 1];
     __shared__ int s_q[WQ_CAP];
     __shared__ int s_qn, s_ngt;
@@ -347,9 +380,12 @@ eval_topk_widen_kernel(const float* __restrict__ chunkmax, const float* __restri
     __shared__ int s_warp[8];
     const int nchunks = (N + CH - 1) / CH;
     const int ntiles = (N + 127) / 128;
+  for (int fi = blockIdx.x; fi < s_nflag; fi += gridDim.x) {
+    const int b = s_flag[fi];
     const float* cm = chunkmax + (size_t)b * (n_pad / CH);
     const float* tm = tilemax + (size_t)b * (n_pad / 128);
     const float bound = tau[b];
+    __syncthreads();                     // previous query's shared state fully consumed
     for (int c = tid; c < XW; c += 256) s_aic[c] = a_ic[(size_t)b * XW + c];
     for (int c = tid; c < NB; c += 256) s_tq[c] = Tq[(size_t)b * NB + c];
     if (tid < TOPK) { s_top_sc[tid] = -INFINITY; s_top_id[tid] = 0x7fffffff; }
@@ -357,41 +393,49 @@ eval_topk_widen_kernel(const float* __restrict__ chunkmax, const float* __restri
     __syncthreads();
     const int lab = label[b];
     const float lab_score = exact_score_e(s_aic, s_tq, item, content, mwdhm, lab, lane);
-    for (int t0 = 0; t0 < ntiles; t0 += 256) {
+    const int per = (ntiles + WSPLIT - 1) / WSPLIT;
+    const int t_lo = split * per, t_hi = min(t_lo + per, ntiles);
+    for (int t0 = t_lo; t0 < t_hi; t0 += 256) {
         const int tile = t0 + tid;
-        if (tile < ntiles && tm[tile] >= bound) {
+        if (tile < t_hi && tm[tile] >= bound) {
+            // the tile's 16 chunk maxima: four 16-byte loads issued together (cm rows are 16-byte aligned: n_pad % 256 == 0)
+            float4 v[TILE_CH / 4];
+#pragma unroll
+            for (int c = 0; c < TILE_CH / 4; ++c) v[c] = reinterpret_cast<const float4*>(cm + (size_t)tile * TILE_CH)[c];
+#pragma unroll
             for (int c = 0; c < TILE_CH; ++c) {
                 const int chunk = tile * TILE_CH + c;
-                if (chunk < nchunks && cm[chunk] >= bound) s_q[atomicAdd(&s_qn, 1)] = chunk;
+                const float cv = c % 4 == 0 ? v[c / 4].x : c % 4 == 1 ? v[c / 4].y : c % 4 == 2 ? v[c / 4].z : v[c / 4].w;
+                if (chunk < nchunks && cv >= bound) s_q[atomicAdd(&s_qn, 1)] = chunk;
             }
         }
         __syncthreads();
         const int qn = s_qn;
         for (int q0 = 0; q0 < qn; q0 += NCH) {
             // exact scores of up to 32 queued chunks
-            for (int j = 0; j < 32; ++j) {
-                const int ci = w * 32 + j;
-                const int qi = q0 + ci / CH;
-                const int n = qi < qn ? s_q[qi] * CH + (ci % CH) : -1;
-                const bool ok = n >= 0 && n < N;
-                float sc = -INFINITY;
-                if (ok) sc = exact_score_e(s_aic, s_tq, item, content, mwdhm, n + item_offset, lane);
-                if (lane == 0) {
-                    s_sc[ci] = sc;
-                    s_id[ci] = ok ? n + item_offset : 0x7fffffff;
+            const int ncand = min(qn - q0, NCH) * CH;            // candidates of this batch
+            int P = 32;                                           // sort size: power of two >= max(ncand, 20)
+            while (P < ncand) P <<= 1;
+            if (tid < P) { s_sc[tid] = -INFINITY; s_id[tid] = 0x7fffffff; }
+            __syncthreads();
+            for (int ci = w; ci < ncand; ci += 8) {               // interleaved: few candidates -> few iterations
+                const int n = s_q[q0 + ci / CH] * CH + (ci % CH);
+                if (n < N) {
+                    const float sc = exact_score_e(s_aic, s_tq, item, content, mwdhm, n + item_offset, lane);
+                    if (lane == 0) { s_sc[ci] = sc; s_id[ci] = n + item_offset; }
                 }
             }
             __syncthreads();
             {
-                const bool gt = s_id[tid] != 0x7fffffff && s_id[tid] != lab && s_sc[tid] > lab_score;
+                const bool gt = tid < P && s_id[tid] != 0x7fffffff && s_id[tid] != lab && s_sc[tid] > lab_score;
                 const uint32_t bal = __ballot_sync(0xffffffffu, gt);
                 if (lane == 0) s_warp[w] = __popc(bal);
             }
-            for (int k = 2; k <= NCAND; k <<= 1) {
+            for (int k = 2; k <= P; k <<= 1) {
                 for (int j = k >> 1; j > 0; j >>= 1) {
                     __syncthreads();
                     const int ixj = tid ^ j;
-                    if (ixj > tid) {
+                    if (tid < P && ixj > tid) {
                         const float sa = s_sc[tid], sb = s_sc[ixj];
                         const int ia = s_id[tid], ib = s_id[ixj];
                         const bool up = (tid & k) == 0;
@@ -419,11 +463,14 @@ eval_topk_widen_kernel(const float* __restrict__ chunkmax, const float* __restri
         if (tid == 0) s_qn = 0;
         __syncthreads();
     }
+    // partial lists [WSPLIT][B][20] / counts [WSPLIT][B] in the workspace
+    const size_t slot = (size_t)split * B + b;
     if (tid < TOPK) {
-        top_ids[(size_t)b * TOPK + tid] = s_top_id[tid] == 0x7fffffff ? -1 : s_top_id[tid];
-        top_scores[(size_t)b * TOPK + tid] = s_top_sc[tid];
+        top_ids[slot * TOPK + tid] = s_top_id[tid] == 0x7fffffff ? -1 : s_top_id[tid];
+        top_scores[slot * TOPK + tid] = s_top_sc[tid];
     }
-    if (tid == 0) n_greater[b] = s_ngt;
+    if (tid == 0) n_greater[slot] = s_ngt;
+  }
 }
 
 // Catalog statistics behind eps_b: out[0] = max_n ||[item | content] row n||_2, out[1] = max_n ||row n - bf16(row n)||_2
@@ -468,11 +515,18 @@ __global__ void __launch_bounds__(256)
 topk_merge_kernel(const int32_t* __restrict__ ids, const float* __restrict__ scores, int32_t* __restrict__ out_ids,
                   float* __restrict__ out_scores, int G, int B, long long gstride, const int32_t* __restrict__ ngt,
                   const float* __restrict__ sumexp, const float* __restrict__ rowmax, int32_t* __restrict__ out_ngt,
-                  float* __restrict__ out_ce) {
+                  float* __restrict__ out_ce, const int32_t* __restrict__ only_if) {
     PDL_ENTER();
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (b >= B) return;
-    if (ngt && lane == 0) {
+    if (only_if && !only_if[b]) return;      // widening pass: certified queries keep their result
+    if (ngt && !sumexp && lane == 0) {
+        // partial rank counts of the widening pass ([G][B], like the lists)
+        int cnt = 0;
+        for (int g = 0; g < G; ++g) cnt += ngt[(size_t)g * B + b];
+        out_ngt[b] = cnt;
+    }
+    if (ngt && sumexp && lane == 0) {
         // rank counts add up; the shards' softmax sums are relative to their own exponent shifts (overflow guard):
         // sum_g sumexp_g 2^(shift_g - M) with M the largest shift, CE = log(sum) + M ln 2 = logsumexp(S_b) - S_b[label]
         int cnt = 0;
@@ -547,14 +601,29 @@ extern "C" int tcar_eval_topk_certified(const float* chunkmax, const float* tile
     return (int)cudaGetLastError();
 }
 
+extern "C" long long tcar_eval_topk_widen_ws_bytes(int B) {
+    return (long long)TCAR_WIDEN_SPLITS * (B > 0 ? B : 0) * (2 * TCAR_TOPK + 1) * 4;
+}
+
 extern "C" int tcar_eval_topk_widen(const float* chunkmax, const float* tilemax, const float* a_ic, const float* Tq,
                                     const float* item, const float* content, const int32_t* mwdhm,
                                     const int32_t* label, const int32_t* uncertain, const float* tau,
                                     int32_t* top_ids, float* top_scores, int32_t* n_greater, int B, int N, int n_pad,
-                                    int item_offset, void* stream) {
-    if (B < 1 || B > TCAR_QROWS || N < 1 || n_pad < N || !tilemax || !uncertain || !tau) return TCAR_ERR_ARG;
-    launch_pdl(eval_topk_widen_kernel, dim3(B), dim3(256), 0, STREAM, chunkmax, tilemax, a_ic, Tq, item, content,
-               mwdhm, label, uncertain, tau, top_ids, top_scores, n_greater, N, n_pad, item_offset);
+                                    int item_offset, void* workspace, void* stream) {
+    if (B < 1 || B > TCAR_QROWS || N < 1 || n_pad < N || !tilemax || !uncertain || !tau || !workspace)
+        return TCAR_ERR_ARG;
+    // workspace: ids [S][B][20] | scores [S][B][20] | counts [S][B]
+    int32_t* w_ids = static_cast<int32_t*>(workspace);
+    float* w_sc = reinterpret_cast<float*>(w_ids + (size_t)WSPLIT * B * TOPK);
+    int32_t* w_ngt = reinterpret_cast<int32_t*>(w_sc + (size_t)WSPLIT * B * TOPK);
+    launch_pdl(eval_topk_widen_kernel, dim3(B < WIDEN_SLOTS ? B : WIDEN_SLOTS, WSPLIT), dim3(256), 0, STREAM, chunkmax, tilemax, a_ic, Tq, item,
+               content, mwdhm, label, uncertain, tau, w_ids, w_sc, w_ngt, N, n_pad, item_offset, B);
+    int rc = (int)cudaGetLastError();
+    if (rc) return rc;
+    launch_pdl(topk_merge_kernel, dim3((B + 7) / 8), dim3(256), 0, STREAM, static_cast<const int32_t*>(w_ids),
+               static_cast<const float*>(w_sc), top_ids, top_scores, WSPLIT, B, 0LL,
+               static_cast<const int32_t*>(w_ngt), static_cast<const float*>(nullptr),
+               static_cast<const float*>(nullptr), n_greater, static_cast<float*>(nullptr), uncertain);
     return (int)cudaGetLastError();
 }
 
@@ -572,7 +641,8 @@ extern "C" int tcar_topk_merge(const int32_t* ids, const float* scores, int32_t*
     if (G < 1 || G > TCAR_MAX_PEERS || B < 1) return TCAR_ERR_ARG;
     launch_pdl(topk_merge_kernel, dim3((B + 7) / 8), dim3(256), 0, STREAM, ids, scores, out_ids, out_scores, G, B,
                0LL, static_cast<const int32_t*>(nullptr), static_cast<const float*>(nullptr),
-               static_cast<const float*>(nullptr), static_cast<int32_t*>(nullptr), static_cast<float*>(nullptr));
+               static_cast<const float*>(nullptr), static_cast<int32_t*>(nullptr), static_cast<float*>(nullptr),
+               static_cast<const int32_t*>(nullptr));
     return (int)cudaGetLastError();
 }
 
@@ -584,6 +654,6 @@ extern "C" int tcar_eval_merge(const void* blocks, long long block_words, int32_
     const int32_t* i = static_cast<const int32_t*>(blocks);
     launch_pdl(topk_merge_kernel, dim3((B + 7) / 8), dim3(256), 0, STREAM, i + TCAR_EVAL_OFF_IDS, f + TCAR_EVAL_OFF_SCORES,
                out_ids, out_scores, G, B, block_words, i + TCAR_EVAL_OFF_NGT, f + TCAR_EVAL_OFF_SUMEXP,
-               f + TCAR_EVAL_OFF_ROWMAX, out_ngt, out_ce);
+               f + TCAR_EVAL_OFF_ROWMAX, out_ngt, out_ce, static_cast<const int32_t*>(nullptr));
     return (int)cudaGetLastError();
 }

@@ -146,6 +146,7 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         # maximum (model_combine.py:145), the scoring kernel shifts by the label score; rows whose best candidate
         # outscores the label by more than 55 nats are re-run shifted by their maximum (two empty launches otherwise)
         self.softmax_guard = bool(args.get("softmax_guard", os.environ.get("TCAR_SOFTMAX_GUARD", "1") != "0"))
+        self.eval_certify = os.environ.get("TCAR_EVAL_CERTIFY", "1") != "0"
         self.train_parallel = "dp"
         self._item_table_synced = True
         mode = args.get("train_parallel") or "dp"
@@ -192,6 +193,7 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         # certification of the top-20 candidate selection (tcar_eval_topk_certified / tcar_eval_topk_widen)
         self.uncertain = torch.zeros(Bm, device=dev, dtype=torch.int32)
         self.tau, self.cat_stats = f(Bm), f(2)
+        self.widen_ws = torch.zeros(int(nv.lib().tcar_eval_topk_widen_ws_bytes(Bm)), device=dev, dtype=torch.uint8)
         self._cat_stats_version = -1
         self.negloss, self.loss, self.coef = f(Bm), f(Bm), f(Bm)
         self.Q = torch.zeros(QROWS, KEXT, device=dev, dtype=torch.bfloat16)
@@ -690,12 +692,16 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         ps, p = self.ps, nv.ptr
         bi = block.view(torch.int32)
         ids, sc, ngt = p(bi[nv.EVAL_OFF_IDS:]), p(block[nv.EVAL_OFF_SCORES:]), p(bi[nv.EVAL_OFF_NGT:])
+        if not self.eval_certify:            # A/B switch (TCAR_EVAL_CERTIFY=0): the uncertified 32-chunk selection
+            nv.counted_call("tcar_eval_topk", 1, p(ws["cmax"]), p(ws["tmax"]), p(a_ic), p(Tq), p(ps.item),
+                            p(ps.content), p(ps.mwdhm), p(label), ids, sc, ngt, B, n_loc, n_pad, lo)
+            return
         nv.counted_call("tcar_eval_topk_certified", 1, p(ws["cmax"]), p(ws["tmax"]), p(a_ic), p(Tq), p(ps.item),
                         p(ps.content), p(ps.mwdhm), p(label), ids, sc, ngt, B, n_loc, n_pad, lo, p(self.cat_stats),
                         p(self.uncertain), p(self.tau))
-        nv.counted_call("tcar_eval_topk_widen", 1, p(ws["cmax"]), p(ws["tmax"]), p(a_ic), p(Tq), p(ps.item),
+        nv.counted_call("tcar_eval_topk_widen", 2, p(ws["cmax"]), p(ws["tmax"]), p(a_ic), p(Tq), p(ps.item),
                         p(ps.content), p(ps.mwdhm), p(label), p(self.uncertain), p(self.tau), ids, sc, ngt, B, n_loc,
-                        n_pad, lo)
+                        n_pad, lo, p(self.widen_ws))
 
     def _merge_blocks(self, blocks, G, B):
         """G shard result blocks -> global top-20 ids, rank counts, cross_loss (one launch)."""

@@ -63,10 +63,10 @@ def build_model(z, init, N):
                 max_grad=float(z["max_grad"]))
     model = Seq2SeqAttNN(args)
     model.ps.load(init)
-    pt = [z["feed_publish_" + k] for k in ("month", "day", "week", "hour", "minute")]
-    ct = [None, None, z["feed_click_week"], z["feed_click_hour"], None]
-    packed, B, T, Nn = pack_batch(z["feed_inputs_seq"], z["feed_lab_input"], pt, ct, z["feed_lab_neg"],
-                                  z["feed_active_time"])
+    pt = [z["feed_publish_" + k].tolist() for k in ("month", "day", "week", "hour", "minute")]
+    ct = [None, None, z["feed_click_week"].tolist(), z["feed_click_hour"].tolist(), None]
+    packed, B, T, Nn = pack_batch(z["feed_inputs_seq"].tolist(), z["feed_lab_input"].tolist(), pt, ct,
+                                  z["feed_lab_neg"].tolist(), z["feed_active_time"].tolist())
     bt = model.to_device(torch.from_numpy(packed).pin_memory(), B, T, Nn)
     return model, bt, B
 

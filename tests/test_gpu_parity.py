@@ -498,6 +498,16 @@ def _overflow_setup(N, B, T, Nn, gap_lo=100.0, gap_hi=250.0, catalog_shards=0):
     return model, bt, batch, params, c64, m64, gap
 
 
+def _assert_ce_close(ce, want, params, c64, m64, batch):
+    """CE = logsumexp(S) - S[label] where the logsumexp is dominated by one huge score that went through the bf16
+    GEMM: the stated tolerance on raw bf16 scores (rtol 2e-2) applies to |S|max of the row, not to CE.
+    We hold it to 6e-3 |S|max (+ the usual 2e-2 absolute)."""
+    with torch.no_grad():
+        smax = O.forward(params, c64, m64, batch)["softmax_input"].abs().max(1).values.numpy()
+    err = np.abs(ce.cpu().double().numpy() - want)
+    assert (err <= 2e-2 + 6e-3 * smax).all(), float((err / (2e-2 + 6e-3 * smax)).max())
+
+
 @pytest.mark.parametrize("shards", [0, 3])
 def test_softmax_overflow_guard_train_step_stays_finite_and_exact(shards):
     N, B, T, Nn = 3000, 96, 3, 20
@@ -512,8 +522,7 @@ def test_softmax_overflow_guard_train_step_stays_finite_and_exact(shards):
         model.backward(bt)
     torch.cuda.synchronize()
     assert torch.isfinite(ce).all() and torch.isfinite(loss).all()
-    # CE = logsumexp - label score ~ the margin itself: bf16 rounding of a score of ~150 is ~0.3 -> relative bound
-    np.testing.assert_allclose(ce.cpu().double().numpy(), out["cross_loss"].numpy().ravel(), rtol=5e-3, atol=2e-2)
+    _assert_ce_close(ce, out["cross_loss"].numpy().ravel(), params, c64, m64, batch)
     shifted = (model.rowmax[:B] > 80.0).cpu().numpy() if not shards else (model._rowmax_all[0, :B] > 80.0).cpu().numpy()
     assert shifted.any() and not shifted.all()
     assert ((gap.numpy() * np.log2(np.e) > 85) <= shifted).all()
@@ -556,7 +565,7 @@ def test_softmax_overflow_guard_eval_loss():
         _, _, ce = model.eval_step(bt) if G == 1 else model.eval_step_virtual_shards(bt, G)
         torch.cuda.synchronize()
         assert torch.isfinite(ce).all()
-        np.testing.assert_allclose(ce.cpu().double().numpy(), ref, rtol=5e-3, atol=2e-2)
+        _assert_ce_close(ce, ref, params, c64, m64, batch)
 
 
 # ------------------------------------------------------------------------------------------- certified top-20
