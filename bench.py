@@ -23,6 +23,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 GLOBO_N = 364047           # Globo articles_metadata.csv row count
+MIND_N = 103630            # SURVEY 8d cfg 4: articles_timeDict_103630.pkl (data_process/mind_preprocess.py:358)
+ADRESSA_N = 20000          # SURVEY 8d cfg 5 (our choice; the reference does not ship Adressa statistics)
+SHAPE = {"globo": ("Globo", GLOBO_N), "mind": ("MIND", MIND_N), "adressa": ("Adressa", ADRESSA_N)}
 K_REF = 820                # scoring K of the reference graph (2H + 5Th, model_combine.py:132-136)
 K_DITEM = 570              # columns of the candidate matrix that carry trainable parameters (250 item + 320 time)
 
@@ -33,12 +36,19 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--items", type=int, default=GLOBO_N)
+    ap.add_argument("--items", type=int, default=0, help="catalog size; 0 = the workload's (364 047 / 103 630 / 20 000)")
     ap.add_argument("--batch", type=int, default=512)
     ap.add_argument("--session_len", type=int, default=0,
                     help="clicks per session; 0 = SURVEY 8d mix: one length per batch drawn from P(T) ~ 0.55^T, "
                          "T in [1,20] (Globo-like, prefix-augmented sessions are short); 20 = the reference --maxlen")
     ap.add_argument("--neg_num", type=int, default=20)
+    ap.add_argument("--negative_mode", default="uniform", choices=["uniform", "impression"],
+                    help="negatives of the sampler-inclusive train_loop lines: uniform (what the reference ships, "
+                         "sampler.py:98-99) or drawn from the sessions' impression lists (sampler.py:118-131, MIND)")
+    ap.add_argument("--workload", default="globo", choices=["globo", "mind", "adressa"],
+                    help="globo = BASELINE config 2/3 (default; what the driver measures); mind = config 4: MIND shape "
+                         "(103 630 articles, impression-list negatives, neg_num sweep 20/50/100); adressa = config 5: "
+                         "Adressa shape (20 000 articles), sweep over the session length T = 1..40")
     ap.add_argument("--train_parallel", default=os.environ.get("TCAR_TRAIN_PARALLEL", "catalog"),
                     choices=["dp", "catalog"],
                     help="multi-GPU training layout: catalog (default) = softmax sharded over the item catalog, only "
@@ -54,7 +64,12 @@ def parse():
     ap.add_argument("--profile_region", action="store_true",
                     help="for `ncu --profile-from-start off`: warm up, then ONE train step (T=20) and ONE eval step "
                          "between cudaProfilerStart/Stop; prints nothing")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.items <= 0:
+        a.items = SHAPE[a.workload][1]
+    if a.workload == "mind":
+        a.negative_mode = "impression"
+    return a
 
 
 # ----------------------------------------------------------------------------------------------------- helpers
@@ -207,7 +222,7 @@ def run_reference(a):
     rate, ms, threads = oracle_train_rate(a.items, Bs, Ts, a.neg_num, a.steps, a.warmup, content, mwdhm)
     sample = (f"{a.steps} train steps of {Bs} sessions (session lengths {Ts[:min(a.steps, len(Ts))]}, Nn={a.neg_num}) "
               f"against the full {a.items}-item catalog, torch CPU fp32")
-    line = {"impl": "reference", "metric": "TCAR train sessions/sec (Globo shape)", "value": rate,
+    line = {"impl": "reference", "metric": f"TCAR train sessions/sec ({SHAPE[a.workload][0]} shape)", "value": rate,
             "unit": "sessions/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(a, 1),
@@ -221,8 +236,13 @@ def workload_config(a, world):
     Ts = session_lengths(a)
     tdesc = (f"session length {a.session_len} for every batch" if a.session_len > 0 else
              f"one session length per batch drawn from P(T)~0.55^T on [1,20] (SURVEY 8d; cycle {Ts})")
-    return {"workload": f"TCAR train step, Globo shape: {a.items} articles x 250-d content, batch {a.batch} "
-                        f"sessions/GPU, {tdesc}, {a.neg_num} negatives",
+    extra = {"mind": "; sampler-inclusive lines draw impression-list negatives (sampler.py:118-131), neg_sweep = "
+                     "neg_num 20 / 50 / 100",
+             "adressa": "; len_sweep = every batch at T = 1, 2, 4, 8, 16, 20, 30, 40 (position table limit, "
+                        "model_combine.py:57)"}.get(a.workload, "")
+    return {"workload": f"TCAR train step, {SHAPE[a.workload][0]} shape: {a.items} articles x 250-d content, batch "
+                        f"{a.batch} sessions/GPU, {tdesc}, {a.neg_num} negatives{extra}",
+            "name": a.workload,
             "items": a.items, "batch_per_gpu": a.batch, "global_batch": a.batch * world,
             "session_len": a.session_len if a.session_len > 0 else "mix", "mean_session_len": sum(Ts) / len(Ts),
             "neg_num": a.neg_num,
@@ -493,15 +513,22 @@ def run_b200(a):
 
     # ---- end to end through the public API: pinned host batch -> H2D -> train_step -> D2H of the loss -------
     def e2e_loop(hosts, lens, n):
-        """n steps, each: H2D of the NEXT batch (pinned -> device), train_step, D2H of this step's loss."""
+        """n steps through the public API, each: H2D of the NEXT batch (pinned -> device), train_step, D2H of this
+        step's [B] loss into pinned memory (Seq2SeqAttNN.fetch_async); the host READS a step's loss one step later, so
+        that it never stalls the launch queue.  Every loss is read inside the timed region."""
         bt = model.to_device(hosts[0], B, lens[0], Nn)
+        pending, total = None, 0.0
         for i in range(n):
             j = (i + 1) % len(hosts)
             nb = model.to_device(hosts[j], B, lens[j], Nn)
-            loss_host = model.train_step(bt, nb if pipe else None).cpu()
+            h = model.fetch_async(model.train_step(bt, nb if pipe else None))
+            if pending is not None:
+                total += float(pending.get().sum())
+            pending = h
             bt = nb
         model.sync_updates()
-        return loss_host
+        total += float(pending.get().sum())
+        return total
 
     e2e_loop(host, Ts, 2)
     barrier()
@@ -530,6 +557,64 @@ def run_b200(a):
     barrier()
     t20_e2e_ms = max_over_ranks(e0.elapsed_time(e1))
 
+    def time_train(batches, steps, warm=3):
+        n = len(batches)
+        for i in range(warm):
+            model.train_step(batches[i % n], nxt(batches, i))
+        model.sync_updates()
+        barrier()
+        e0.record()
+        for i in range(warm, warm + steps):
+            model.train_step(batches[i % n], nxt(batches, i))
+        model.sync_updates()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps
+
+    def time_eval(batches, steps, shard_, warm=3):
+        n = len(batches)
+        nx = (lambda i: batches[(i + 1) % n]) if not a.no_lookahead else (lambda i: None)
+        for i in range(warm):
+            model.eval_step(batches[i % n], shard=shard_, next_bt=nx(i))
+        model.sync_updates()
+        barrier()
+        e0.record()
+        for i in range(warm, warm + steps):
+            model.eval_step(batches[i % n], shard=shard_, next_bt=nx(i))
+        model.sync_updates()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps
+
+    sweeps = {}
+    if a.workload == "mind":
+        # BASELINE config 4: heavier negative-feedback sampling -- the same step at neg_num 20 / 50 / 100
+        sweeps["neg_sweep"] = {}
+        for nn in (20, 50, 100):
+            hb = make_batches(synth, N, B, Ts, nn, mwdhm, seed0=7000 * (rank + 1) + nn)
+            db = [model.to_device(h, B, t, nn) for h, t in zip(hb, Ts)]
+            ms = time_train(db, K)
+            sweeps["neg_sweep"][str(nn)] = {"ms_per_step": ms, "value": world * B / (ms * 1e-3), "unit": "sessions/s"}
+            del db
+    if a.workload == "adressa":
+        # BASELINE config 5: throughput over the session length (every batch at one T)
+        sweeps["len_sweep"] = {}
+        sh = None
+        if world > 1:
+            s_lo, s_hi = model.shard_bounds(world)[rank]
+            sh = (s_lo, s_hi, model.iext_shard(s_lo, s_hi))
+        for tt in (1, 2, 4, 8, 16, 20, 30, 40):
+            hb = make_batches(synth, N, B, [tt] * 4, Nn, mwdhm, seed0=9000 * (rank + 1) + tt)
+            db = [model.to_device(h, B, tt, Nn) for h in hb]
+            ms = time_train(db, K)
+            he = make_batches(synth, N, B, [tt] * 4, 0, mwdhm, seed0=9100 + tt)
+            de = [model.to_device(h, B, tt, 0) for h in he]
+            model.sync_item_table()
+            ems = time_eval(de, K, sh)
+            sweeps["len_sweep"][str(tt)] = {"train_ms_per_step": ms, "train_sessions_per_s": world * B / (ms * 1e-3),
+                                            "eval_ms_per_step": ems, "eval_queries_per_s": B / (ems * 1e-3)}
+            del db, de
+
     # ---- evaluation: full-catalog top-20, catalog sharded across ranks when N > 1 ----------------------------
     ehost = make_batches(synth, N, B, Ts, 0, mwdhm, seed0=77)               # same queries on every rank
     edev = [model.to_device(h, B, t, 0) for h, t in zip(ehost, Ts)]
@@ -554,13 +639,18 @@ def run_b200(a):
     eval_uncertified = float(model.uncertain[:B].float().mean().item())      # last batch: share sent to the widening pass
     e0.record()
     bt = model.to_device(ehost[0], B, Ts[0], 0)
+    pend = None
     for i in range(K):
         j = (i + 1) % nbatch
         nb = model.to_device(ehost[j], B, Ts[j], 0)              # H2D of the next batch, then this batch's step + D2H
         top, ngt, ce = model.eval_step(bt, shard=shard, next_bt=nb if look else None)
-        top.cpu(); ngt.cpu(); ce.cpu()
+        hs = [model.fetch_async(top), model.fetch_async(ngt), model.fetch_async(ce)]
+        if pend is not None:
+            [h.get() for h in pend]                              # read one step late: the launch queue never drains
+        pend = hs
         bt = nb
     model.sync_updates()
+    [h.get() for h in pend]
     e1.record()
     barrier()
     eval_e2e_ms = max_over_ranks(e0.elapsed_time(e1))
@@ -589,27 +679,30 @@ def run_b200(a):
         import random as pyrandom
         from tcar_b200.model_combine import prefetch_packed
         from tcar_b200.sampler import Sampler
-        # data parallel: every rank draws the SAME batches (same seeds, as main.py does) and keeps its slice of the
-        # sessions (parallel.shard_packed) -- all ranks therefore run the same number of steps / collectives
+        # multi-GPU: the loop of Seq2SeqAttNN.train with dist_batch="per_rank" -- every rank walks the same GLOBAL
+        # batches of world x B sessions (same `random` seed, as main.py does) and its host thread gathers only its own
+        # share of <= B sessions (Sampler.restrict_to_rank): all ranks run the same number of steps / collectives
         from tcar_b200 import parallel
-        ld, sd, td, idict, impr = synth.make_sessions(N, a.loop_sessions * world, seed=2020)
+        ld, sd, td, idict, impr = synth.make_sessions(N, a.loop_sessions * world, seed=2020,
+                                                      impressions="mind" if a.negative_mode == "impression" else "few")
         pyrandom.seed(2020)
-        np.random.seed(2020)
+        np.random.seed(2020 + 7919 * rank)
         t_h0 = time.perf_counter()
-        smp = Sampler(ld, sd, td, impr, idict, Nn, batch_size=B, verbose=False)
+        smp = Sampler(ld, sd, td, impr, idict, Nn, batch_size=B * world, negative_mode=a.negative_mode, verbose=False)
         smp.next_packed()                                    # builds the columnar cache (once per split)
         t_cache = time.perf_counter() - t_h0
-        smp = Sampler(ld, sd, td, impr, idict, Nn, batch_size=B, verbose=False)
+        pyrandom.seed(2020)
+        smp = Sampler(ld, sd, td, impr, idict, Nn, batch_size=B * world, negative_mode=a.negative_mode, verbose=False)
+        if world > 1:
+            smp.restrict_to_rank(rank, world)
+        gsizes = getattr(smp, "global_sizes", None)
         nsess, nb = 0, 0
         barrier()
         t_w0 = time.perf_counter()
         e0.record()
         def staged_batches():
-            for packed, Bb, Tb, Nb in prefetch_packed(smp):
-                if world > 1:
-                    packed, Bl, Tb, Nb = parallel.shard_packed(packed, Bb, Tb, Nb, rank, world)
-                else:
-                    Bl = Bb
+            for i, (packed, Bl, Tb, Nb) in enumerate(prefetch_packed(smp)):
+                Bb = gsizes[i] if gsizes is not None else Bl
                 sbt = model.stage_to_device(packed, Bl, Tb, Nb)
                 sbt.counts = parallel.catalog_counts(Bb, world)
                 yield Bb, sbt
@@ -628,7 +721,10 @@ def run_b200(a):
         barrier()
         loop_ms = max_over_ranks(e0.elapsed_time(e1))
         train_loop = {"note": "Sampler.next_packed (host thread) -> pinned ring -> H2D -> train_step over one epoch of "
-                              "an in-memory synthetic split; length-bucketed batches, tail batches < 512 included",
+                              "an in-memory synthetic split; length-bucketed batches, tail batches included; "
+                              "multi-GPU: one batch of <= %d sessions per rank and step (global batch = GPUs x %d), "
+                              "each rank's host thread samples only its own sessions" % (B, B),
+                      "negative_mode": a.negative_mode,
                       "value": nsess / (loop_ms * 1e-3), "unit": "sessions/s", "batches": nb,
                       "sessions": nsess, "ms_per_batch": loop_ms / nb,
                       "wall_s": time.perf_counter() - t_w0, "columnar_cache_build_s": t_cache}
@@ -637,8 +733,8 @@ def run_b200(a):
         # negatives drawn (Philox) on the device
         from tcar_b200.device_sampler import DeviceSampler
         pyrandom.seed(2020)
-        dsm = DeviceSampler(model, ld, sd, td, impr, idict, Nn, batch_size=B, negatives="device", seed=2020,
-                            rank=rank, world=world, verbose=False)
+        dsm = DeviceSampler(model, ld, sd, td, impr, idict, Nn, batch_size=B * world, negative_mode=a.negative_mode,
+                            negatives="device", seed=2020, rank=rank, world=world, verbose=False)
         nsess2, nb2 = 0, 0
         barrier()
         e0.record()
@@ -646,7 +742,7 @@ def run_b200(a):
         while cur is not None:
             nx = dsm.next_device() if dsm.has_next() else None
             loss_dev = model.train_step(cur, nx if pipe else None)
-            nsess2 += cur.B * world
+            nsess2 += sum(cur.counts) if cur.counts is not None else cur.B
             nb2 += 1
             cur = nx
         model.sync_updates()
@@ -655,7 +751,8 @@ def run_b200(a):
         barrier()
         dloop_ms = max_over_ranks(e0.elapsed_time(e1))
         train_loop["device_sampler"] = {"note": "DeviceSampler(negatives='device'): host sends B bucket rows per batch; "
-                                                "gather of the 7 index planes + Philox negatives on the device",
+                                                "gather of the 7 index planes + Philox negatives (uniform, or the "
+                                                "impression-list algorithm of sampler.py:118-131) on the device",
                                         "value": nsess2 / (dloop_ms * 1e-3), "unit": "sessions/s", "batches": nb2,
                                         "ms_per_batch": dloop_ms / nb2}
 
@@ -695,7 +792,7 @@ def run_b200(a):
         roof = {"kernel": top, "bound": kk["bound"], "achieved": kk["achieved"], "peak": kk["peak"],
                 "unit": kk["unit"], "frac": kk["frac"], "traffic": kk["traffic"], "peak_source": kk["peak_source"],
                 "ms_per_launch": kk["ms"]}
-    line = {"metric": "TCAR train sessions/sec (Globo shape)", "value": value, "unit": "sessions/s", "n_gpus": world,
+    line = {"metric": f"TCAR train sessions/sec ({SHAPE[a.workload][0]} shape)", "value": value, "unit": "sessions/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": train_ms / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16 tensor-core scoring GEMMs (fp32 accumulate), fp32 elsewhere",
             "data": "synthetic", "config": dict(workload_config(a, world), lookahead=bool(pipe),
@@ -705,7 +802,7 @@ def run_b200(a):
             "t20": {"note": "same measurement with every batch at the reference --maxlen (T = 20)",
                     "value": sessions / (t20_ms * 1e-3), "ms_per_step": t20_ms / K,
                     "e2e_value": sessions / (t20_e2e_ms * 1e-3), "unit": "sessions/s"},
-            "train_loop": train_loop,
+            "train_loop": train_loop, **sweeps,
             "gpu_launches": launches, "launches_per_step": launches / K, "loss_last_step": loss_last,
             "clocks": clk, "kernels": kernels, "roofline": roof, "cpu_baseline": cpu_baseline,
             "parity": parity,

@@ -110,6 +110,17 @@ int tcar_assemble_batch(const int32_t* rows, const int32_t* seq, const int32_t* 
                         int n_bucket, int B, int T, int Nn, const int32_t* neg_in, int item_num,
                         unsigned long long seed, unsigned long long offset, int32_t* out, void* stream);
 
+/* Impression-list negatives on the device (sampler.py:118-131, the MIND configuration): for session b (bucket row
+ * rows[b]) up to 21 uniform draws from its impression list impr_ids[impr_off[row] .. impr_off[row + 1]) -- entries are
+ * 0-based item ids, -1 for an article that is not in item_dict -- the first Nn hits are kept, the remaining slots are
+ * filled with uniform draws from [0, item_num).  Philox4x32-10 keyed by `seed`; session b owns TCAR_IMPR_BLOCKS(Nn)
+ * counters from offset + b * TCAR_IMPR_BLOCKS(Nn): word j < 21 = try j, word 21 + k = fill of slot k.
+ * neg_out [B, Nn] is then passed to tcar_assemble_batch as neg_in. */
+#define TCAR_IMPR_BLOCKS(Nn) ((21 + (Nn) + 3) / 4)
+int tcar_impression_negatives(const int32_t* rows, const int32_t* impr_off, const int32_t* impr_ids, int B, int Nn,
+                              int item_num, unsigned long long seed, unsigned long long offset, int32_t* neg_out,
+                              void* stream);
+
 /* (3c) full-catalog scoring S = Q . Iext^T on tcgen05 (model_combine.py:138), never materialising S.
  *   mode 0 (train): E = exp(S - c_ref) in bf16, logically [512, n_pad], stored in blocks of 8 items:
  *                   E[b, n] at element ((n / 8) * 512 + b) * 8 + n % 8 (coalesced epilogue stores; the backward

@@ -32,3 +32,33 @@ def device_negatives(seed, offset, count, item_num):
     words = philox4x32_10(seed, np.uint64(offset) + (e >> np.uint64(2)))
     x = words[np.arange(count), (e & np.uint64(3)).astype(np.int64)].astype(np.uint64)
     return ((x * np.uint64(item_num)) >> np.uint64(32)).astype(np.int32)
+
+
+def impr_blocks(neg_num):
+    """TCAR_IMPR_BLOCKS: Philox counters one session owns in tcar_impression_negatives."""
+    return (21 + neg_num + 3) // 4
+
+
+def device_impression_negatives(seed, offset, rows, impr_off, impr_ids, neg_num, item_num):
+    """Restatement of tcar_impression_negatives = sampler.py:118-131 (neg_neighbor_from_impre) driven by the Philox
+    stream: <= 21 draws `random.choice(neighbor_set)`, kept when the article is in item_dict (impr_ids >= 0, 0-based
+    item id), until neg_num are found; then `np.random.randint(0, item_num)` fills the rest.  Returns [B, neg_num]."""
+    B = len(rows)
+    nb = impr_blocks(neg_num)
+    out = np.zeros((B, neg_num), dtype=np.int32)
+    for b, r in enumerate(rows):
+        words = philox4x32_10(seed, np.uint64(offset) + np.uint64(b * nb) + np.arange(nb, dtype=np.uint64)).reshape(-1)
+        lo, ln = int(impr_off[r]), int(impr_off[r + 1] - impr_off[r])
+        neg, cnt = [], 0
+        if ln > 0:
+            while len(neg) < neg_num:                       # sampler.py:121
+                cnt += 1
+                pick = int(impr_ids[lo + ((int(words[cnt - 1]) * ln) >> 32)])      # random.choice(neighor_set)
+                if pick >= 0:                               # `if randomid in self.item_dict`
+                    neg.append(pick)
+                if cnt > 20:                                # sampler.py:126-127
+                    break
+        while len(neg) < neg_num:                           # sampler.py:128-129
+            neg.append((int(words[21 + len(neg)]) * item_num) >> 32)
+        out[b] = neg
+    return out

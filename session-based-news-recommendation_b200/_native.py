@@ -23,6 +23,7 @@ _P, _I, _F, _LL = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 SIGNATURES = {
     "tcar_gather_fwd": [_P] * 15 + [_I, _I, _P],
     "tcar_assemble_batch": [_P] * 4 + [_I] * 4 + [_P, _I, C.c_ulonglong, C.c_ulonglong, _P, _P],
+    "tcar_impression_negatives": [_P, _P, _P, _I, _I, _I, C.c_ulonglong, C.c_ulonglong, _P, _P],
     "tcar_pool_fwd": [_P] * 10 + [_I, _I, _P],
     "tcar_pool_bwd": [_P] * 16 + [_I, _I, _P],
     "tcar_build_iext": [_P] * 4 + [_I, _I, _P],

@@ -199,6 +199,38 @@ assemble_batch_kernel(const int32_t* __restrict__ rows, const int32_t* __restric
     }
 }
 
+// Impression-list negatives (sampler.py:118-131, neg_neighbor_from_impre) on the device, one thread per session:
+// up to 21 uniform draws from the session's impression list (`random.choice`), a draw counts when the article is in
+// item_dict (impr_ids >= 0, already mapped to 0-based item ids) until Nn are found; the rest is filled with uniform
+// draws from [0, item_num) (np.random.randint).  Same algorithm, counter-based stream instead of Python's Mersenne
+// twister: session b of the batch owns the TCAR_IMPR_BLOCKS(Nn) Philox counters from offset + b * TCAR_IMPR_BLOCKS(Nn);
+// word j < 21 drives try j, word 21 + k fills slot k (restated in oracle/philox_oracle.py).
+__global__ void __launch_bounds__(128)
+impression_negatives_kernel(const int32_t* __restrict__ rows, const int32_t* __restrict__ impr_off,
+                            const int32_t* __restrict__ impr_ids, int B, int Nn, int item_num,
+                            unsigned long long seed, unsigned long long offset, int32_t* __restrict__ out) {
+    PDL_ENTER();
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int r = rows[b];
+    const int lo = impr_off[r], len = impr_off[r + 1] - lo;
+    const unsigned long long base = offset + (unsigned long long)b * TCAR_IMPR_BLOCKS(Nn);
+    int32_t* neg = out + (size_t)b * Nn;
+    int found = 0;
+    if (len > 0) {
+        for (int j = 0; j < 21 && found < Nn; ++j) {
+            const uint32_t wv = philox_word(seed, base + (unsigned long long)(j >> 2), j & 3);
+            const int id = impr_ids[lo + (int)(((unsigned long long)wv * (unsigned long long)len) >> 32)];
+            if (id >= 0) neg[found++] = id;
+        }
+    }
+    for (int k = found; k < Nn; ++k) {
+        const int j = 21 + k;
+        const uint32_t wv = philox_word(seed, base + (unsigned long long)(j >> 2), j & 3);
+        neg[k] = (int)(((unsigned long long)wv * (unsigned long long)item_num) >> 32);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ (2) pooling fwd
 // one CTA per session.  modules.py:126-142 (count_alpha_m), :94-100 (count_alpha_s), :116-117 / :82-83 (pool).
 // Every row is fetched with 128-bit loads that are all issued before the first use (8 independent loads per lane and
@@ -1084,6 +1116,15 @@ extern "C" int tcar_assemble_batch(const int32_t* rows, const int32_t* seq, cons
     const int total = 7 * B * T + 3 * B + B * Nn;
     launch_pdl(assemble_batch_kernel, dim3((total + 255) / 256), dim3(256), 0, STREAM, rows, seq, feats, ctx, n_bucket, B, T,
                Nn, neg_in, item_num, seed, offset, out);
+    return LAUNCH_RC();
+}
+
+extern "C" int tcar_impression_negatives(const int32_t* rows, const int32_t* impr_off, const int32_t* impr_ids, int B,
+                                         int Nn, int item_num, unsigned long long seed, unsigned long long offset,
+                                         int32_t* neg_out, void* stream) {
+    if (B < 1 || Nn < 1 || item_num < 1 || !rows || !impr_off || !impr_ids || !neg_out) return TCAR_ERR_ARG;
+    launch_pdl(impression_negatives_kernel, dim3((B + 127) / 128), dim3(128), 0, STREAM, rows, impr_off, impr_ids, B,
+               Nn, item_num, seed, offset, neg_out);
     return LAUNCH_RC();
 }
 

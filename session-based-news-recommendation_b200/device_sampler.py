@@ -4,7 +4,10 @@ the reference's sampler.py:24-50), but the per-batch gather of the 7 index plane
 host sends only the batch's B bucket rows -- plus, in `negatives="host"` mode, the B x Nn negatives it drew from the
 reference's NumPy stream (np.random.randint, sampler.py:98-99), which makes every batch bit-identical to
 `Sampler.next_packed()`.  `negatives="device"` draws them on the device (Philox4x32-10 keyed by `seed`; restated in
-oracle/philox_oracle.py): 2 KB of host->device traffic per batch instead of 83 KB, no per-batch NumPy work."""
+oracle/philox_oracle.py): 2 KB of host->device traffic per batch instead of 83 KB, no per-batch NumPy work.  With
+`negative_mode="impression"` (the MIND configuration, sampler.py:96,118-131) the device mode runs the reference's
+impression-list algorithm in `tcar_impression_negatives` from a CSR copy of the sessions' impression lists, already
+mapped through item_dict; the host mode keeps Python's `random.choice` stream and stays bit-identical to the reference."""
 import numpy as np
 import torch
 
@@ -29,6 +32,36 @@ def _device_columnar(col, device):
     return ent[1]
 
 
+def impression_csr(col, session_dict, neighbor_dict, item_dict):
+    """Per session-length bucket L: CSR (offsets [n + 1], ids) of every session's impression list in bucket-row order,
+    mapped through item_dict to 0-based item ids (-1 = article not in item_dict; sampler.py:119,124-125).  The list
+    of session key "<sid>_<len>" is neighbor_dict[int(sid)] (sampler.py:96); a session without a list gets an empty
+    one (all its negatives are then uniform fills)."""
+    keys = {}
+    for key, r in col.row.items():
+        keys.setdefault(len(session_dict[key]) - 1, {})[r] = key
+    out = {}
+    for L, rows in keys.items():
+        off = np.zeros(len(rows) + 1, dtype=np.int32)
+        ids = []
+        for r in range(len(rows)):
+            lst = neighbor_dict.get(int(str(rows[r]).split("_")[0]), ())
+            ids.extend(item_dict.get(x, 0) - 1 for x in lst)
+            off[r + 1] = len(ids)
+        out[L] = (off, np.asarray(ids if ids else [-1], dtype=np.int32))
+    return out
+
+
+def _device_impressions(col, session_dict, neighbor_dict, item_dict, device):
+    key = (id(col), id(neighbor_dict), id(item_dict), str(device))
+    ent = _DEVICE_CACHE.get(key)
+    if ent is None or ent[0] is not col or ent[2] is not neighbor_dict or ent[3] is not item_dict:
+        csr = impression_csr(col, session_dict, neighbor_dict, item_dict)
+        ent = _DEVICE_CACHE[key] = (col, {L: (torch.from_numpy(o).to(device), torch.from_numpy(i).to(device))
+                                          for L, (o, i) in csr.items()}, neighbor_dict, item_dict)
+    return ent[1]
+
+
 class DeviceSampler(Sampler):
     def __init__(self, model, len_dict, session_dict, session_time_dict=None, neighbor_dict=None, item_dict=None,
                  neg_num=None, batch_size=1024, negative_mode="uniform", negatives="host", seed=2020, rank=0, world=1,
@@ -37,13 +70,14 @@ class DeviceSampler(Sampler):
                          negative_mode, verbose)
         if negatives not in ("host", "device"):
             raise ValueError("negatives must be 'host' (reference NumPy stream) or 'device' (Philox)")
-        if negatives == "device" and negative_mode != "uniform":
-            raise ValueError("impression-list negatives (sampler.py:118-131) are drawn on the host")
         self.model, self.negatives, self.seed = model, negatives, int(seed)
         self.rank, self.world = rank, world
         self._col = _columnar(session_dict, session_time_dict)
         self._dev = _device_columnar(self._col, model.dev)
         self._counter = 0                     # Philox counter blocks consumed so far (device negatives)
+        self._impr = None
+        if negatives == "device" and negative_mode == "impression" and neighbor_dict and neg_num:
+            self._impr = _device_impressions(self._col, session_dict, neighbor_dict, item_dict, model.dev)
 
     def host_part(self):
         """Bucket rows (and host-drawn negatives) of the next batch: (small int32 array, B, T, Nn).  Consumes the
@@ -79,8 +113,9 @@ class DeviceSampler(Sampler):
         total = 7 * B * T + 3 * B + B * Nn
         out = torch.empty(max(total, 1), device=model.dev, dtype=torch.int32)
         offset = self._counter
+        impr_blocks = (21 + Nn + 3) // 4                 # TCAR_IMPR_BLOCKS(Nn)
         if self.negatives == "device" and Nn:
-            self._counter += (B_glob * Nn + 3) // 4
+            self._counter += B_glob * impr_blocks if self._impr is not None else (B_glob * Nn + 3) // 4
         counts = None
         if self.world > 1:
             from .parallel import catalog_counts
@@ -93,7 +128,13 @@ class DeviceSampler(Sampler):
         rows_d = host[:B]
         neg_d = host[B:] if (Nn and self.negatives == "host") else None
         dev = self._dev
-        if first_neg % 4:
+        if self._impr is not None and Nn:
+            # impression-list negatives (sampler.py:118-131) drawn on the device, then handed to the assembly kernel
+            off_d, ids_d = self._impr[T]
+            neg_d = torch.empty(B * Nn, device=model.dev, dtype=torch.int32)
+            nv.counted_call("tcar_impression_negatives", 1, p(rows_d), p(off_d), p(ids_d), B, Nn, int(self.item_num),
+                            self.seed, offset + (first_neg // Nn) * impr_blocks, p(neg_d))
+        elif first_neg % 4:
             raise ValueError("device negatives need shard boundaries on 4-element Philox blocks (B * Nn % 4 == 0)")
         nv.counted_call("tcar_assemble_batch", 1, p(rows_d), p(dev.seq[T]), p(dev.feats[T]), p(dev.ctx[T]),
                         int(dev.seq[T].shape[0]), B, T, Nn, p(neg_d), int(getattr(self, "item_num", 0) or 0),

@@ -96,6 +96,13 @@ def build_parser():
     # not a reference flag: multi-GPU training layout under torchrun.  dp = data parallel + gradient all-reduce,
     # catalog = softmax sharded over the item catalog (catalog_parallel.py)
     parser.add_argument("--train_parallel", default="dp", choices=["dp", "catalog"], type=str)
+    # not a reference flag: what a step is under torchrun.  per_rank = every GPU its own batch of --batch_size sessions
+    # (global batch = GPUs x batch_size: weak scaling, a different optimisation trajectory than one GPU); split = ONE
+    # batch of --batch_size sessions split over the GPUs (the single-GPU trajectory)
+    parser.add_argument("--dist_batch", default="per_rank", choices=["per_rank", "split"], type=str)
+    # not a reference flag: the reference ships uniform negatives (sampler.py:98-99) and keeps the impression-list
+    # sampler of the MIND experiments commented out (sampler.py:96,118-131); this switch selects it
+    parser.add_argument("--negative_mode", default="uniform", choices=["uniform", "impression"], type=str)
     parser.add_argument("--inputdata", default="test", type=str)
     parser.add_argument("--threshold_acc", default=0.27, type=float)
     # additions

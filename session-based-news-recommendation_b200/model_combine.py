@@ -86,6 +86,37 @@ class PinnedRing:
         return view, self.events[i]
 
 
+class HostFetch:
+    """Device -> host hand-off of a small per-step result (the [B] loss, the top-20 block) WITHOUT stalling the launch
+    queue: the copy goes into a slot of a pinned ring on the producing stream and an event is recorded behind it;
+    `get()` waits for that one event only.  Reading step i's loss while step i+1 is being enqueued keeps the GPU fed
+    (a blocking `.cpu()` per step leaves it idle for the host's whole enqueue time of the next step)."""
+
+    def __init__(self, slots=16):
+        self.slots, self.bufs, self.i = slots, [None] * slots, 0
+
+    class Handle:
+        def __init__(self, view, event):
+            self.view, self.event = view, event
+
+        def get(self):
+            self.event.synchronize()
+            return self.view
+
+    def fetch(self, t):
+        i = self.i
+        self.i = (i + 1) % self.slots
+        n = t.numel()
+        buf = self.bufs[i]
+        if buf is None or buf.numel() < n or buf.dtype != t.dtype:
+            buf = self.bufs[i] = torch.empty(max(n, 1024), dtype=t.dtype).pin_memory()
+        view = buf[:n].view(t.shape)
+        view.copy_(t, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return HostFetch.Handle(view, ev)
+
+
 class Seq2SeqAttNN(CatalogShardedTraining):
     def __init__(self, args):
         if not torch.cuda.is_available():
@@ -264,6 +295,13 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         bt = self.to_device(view, B, T, Nn)
         ev.record()
         return bt
+
+    def fetch_async(self, t):
+        """Start the device -> host copy of a result tensor into pinned memory; returns a handle whose .get() blocks
+        only until THAT copy is done (see HostFetch).  A slot is reused after 16 further fetches."""
+        if getattr(self, "_fetch", None) is None:
+            self._fetch = HostFetch()
+        return self._fetch.fetch(t)
 
     def make_batch(self, batch_in, batch_out, batch_pt, batch_ct, neg, gap):
         """From the reference sampler's 6-tuple of Python lists (sampler.py:113) to a device Batch."""
@@ -492,6 +530,22 @@ class Seq2SeqAttNN(CatalogShardedTraining):
                         None, 0)
         dist.all_gather_into_tensor(ps.item_full, ps.item_full[lo: lo + per])
         nv.counted_call("tcar_refresh_iext_items", 1, p(ps.item), p(ps.iext), ps.N)
+        self._moments_synced = False       # every rank holds the Adam moments of its own row slice only
+
+    def sync_optimizer_state(self):
+        """Data-parallel training with the sharded update keeps the item table's Adam moments distributed (rank r owns
+        the rows of its slice).  A checkpoint is 'parameters + moments + step': gather the slices first, so that the
+        writer holds the moments of EVERY row (a resumed run would otherwise restart Adam for (world-1)/world of them)."""
+        if getattr(self, "_moments_synced", True) or not self._sharded_update():
+            return
+        import torch.distributed as dist
+        ps = self.ps
+        per = ps.rows_alloc // self.world
+        lo = self.rank * per
+        self.sync_updates()
+        for t in (ps.item_m_full, ps.item_v_full):
+            dist.all_gather_into_tensor(t, t[lo: lo + per])
+        self._moments_synced = True
 
     def apply_gradients(self, next_bt=None):
         """per-tensor clip_by_norm + TF Adam (model_combine.py:155-163); also refreshes the bf16 scoring operand.
@@ -777,6 +831,19 @@ class Seq2SeqAttNN(CatalogShardedTraining):
     def train(self, sess, item_dict, train_data, neighbor_dict, args, test_data=None, saver=None, threshold_acc=0.99):
         """model_combine.py:196-252."""
         (len_dict_train, session_dict_train, session_time_dict_train) = train_data
+        # Multi-GPU (torchrun): "per_rank" (default) = every rank trains on its OWN batch of <= batch_size sessions of
+        # the same length bucket, i.e. the global batch is world x batch_size -- this changes the optimisation
+        # trajectory against the single-GPU loop (model_combine.py:196-252 sees batch_size sessions per step), which is
+        # what weak scaling means; "split" = ONE batch of batch_size sessions split over the ranks: the single-GPU
+        # trajectory, no throughput gain from more GPUs.
+        dist_batch = (args.get("dist_batch") or "per_rank") if self.world > 1 else "single"
+        if dist_batch not in ("per_rank", "split", "single"):
+            raise ValueError("dist_batch must be 'per_rank' or 'split'")
+        gbatch = self.batch_size * (self.world if dist_batch == "per_rank" else 1)
+        neg_mode = args.get("negative_mode") or "uniform"
+        if dist_batch == "per_rank":
+            print("rank {}: global batch = {} x {} sessions".format(self.rank, self.world, self.batch_size))
+            np.random.seed(2020 + 7919 * self.rank)       # distinct uniform negatives per rank (main.py:11-12 seeds 2020)
         for epoch in range(self.epoch):
             self.curEpoch = epoch
             print("Epoch {}".format(epoch))
@@ -787,11 +854,14 @@ class Seq2SeqAttNN(CatalogShardedTraining):
                 # identical to the host sampler's), "device" = Philox negatives drawn on the device
                 from .device_sampler import DeviceSampler
                 sampler = DeviceSampler(self, len_dict_train, session_dict_train, session_time_dict_train,
-                                        neighbor_dict, item_dict, args["neg_num"], batch_size=self.batch_size,
-                                        negatives=mode, seed=2020 + epoch, rank=self.rank, world=self.world)
+                                        neighbor_dict, item_dict, args["neg_num"], batch_size=gbatch,
+                                        negative_mode=neg_mode, negatives=mode, seed=2020 + epoch, rank=self.rank,
+                                        world=self.world)
             else:
                 sampler = Sampler(len_dict_train, session_dict_train, session_time_dict_train, neighbor_dict,
-                                  item_dict, args["neg_num"], batch_size=self.batch_size)
+                                  item_dict, args["neg_num"], batch_size=gbatch, negative_mode=neg_mode)
+                if self.world > 1:
+                    sampler.restrict_to_rank(self.rank, self.world)
             batch = 0
 
             def staged():
@@ -801,17 +871,15 @@ class Seq2SeqAttNN(CatalogShardedTraining):
                         batch += 1
                         yield sampler.next_device()
                     return
+                sizes = getattr(sampler, "global_sizes", None)
                 for packed, B, T, Nn in prefetch_packed(sampler):
-                    batch += 1
-                    if batch < 3 and Nn:
+                    if batch < 2 and Nn and B:
                         print(packed[7 * B * T + 3 * B: 7 * B * T + 3 * B + min(Nn, 10)].tolist())
-                    counts = None
-                    if self.world > 1:
-                        # every rank draws the same batch (same seeds, main.py:9-12) and keeps its slice of the sessions
-                        counts = parallel.catalog_counts(B, self.world)
-                        packed, B, T, Nn = parallel.shard_packed(packed, B, T, Nn, self.rank, self.world)
+                    # every rank walks the same global batches (same `random` seed, main.py:9-10) and has gathered
+                    # only its own share of the sessions (Sampler.restrict_to_rank)
                     bt_ = self.stage_to_device(packed, B, T, Nn)
-                    bt_.counts = counts
+                    bt_.counts = parallel.catalog_counts(sizes[batch], self.world) if sizes is not None else None
+                    batch += 1
                     yield bt_
 
             # one batch of look-ahead: batch i+1 is on the device before step i is launched, so that its session

@@ -114,6 +114,26 @@ class Sampler(object):
     def has_next(self):
         return self.batch_i < self.batch_num
 
+    def restrict_to_rank(self, rank, world):
+        """Multi-GPU training with one batch PER RANK (global batch = world x batch_size): this sampler was built with
+        batch_size = world x the per-GPU batch, identically on every rank (same `random` seed, main.py:9-10); keep only
+        this rank's contiguous share of every global batch (parallel.shard_sessions), so that each rank's host thread
+        gathers features / draws negatives for its own <= batch_size sessions only.  `global_sizes[i]` keeps the size
+        of global batch i (all ranks derive the same per-rank counts from it), `batch_T[i]` its session length (a
+        rank's share of a small tail batch may be empty).  Impression negatives switch to a per-rank `random.Random`
+        so that the global `random` stream -- which shuffles the next epoch's batches -- stays identical on all ranks;
+        the NumPy stream of the uniform negatives is per process anyway (reseed it per rank for distinct draws)."""
+        from .parallel import shard_sessions
+        self.global_sizes = [len(b) for b in self.session_id_batches]
+        self.batch_T = [len(self.session_dict[b[0]]) - 1 for b in self.session_id_batches]
+        out = []
+        for b in self.session_id_batches:
+            lo, hi = shard_sessions(len(b), rank, world)
+            out.append(b[lo:hi])
+        self.session_id_batches = out
+        self._choice = random.Random(2020 + 7919 * rank).choice
+        return self
+
     def _features(self, sid):
         f = self._cache.get(sid)
         if f is None:
@@ -158,7 +178,7 @@ class Sampler(object):
         yields exactly the values of the reference's B consecutive calls of size Nn (sampler.py:98-99)."""
         ids = self.session_id_batches[self.batch_i]
         B = len(ids)
-        T = len(self.session_dict[ids[0]]) - 1
+        T = self.batch_T[self.batch_i] if getattr(self, "batch_T", None) else len(self.session_dict[ids[0]]) - 1
         Nn = self.neg_num if (self.neighbor_dict and self.neg_num) else 0
         M = B * T
         col = _columnar(self.session_dict, self.session_time_dict)
@@ -196,9 +216,10 @@ class Sampler(object):
         """sampler.py:118-131."""
         neighor_set = self.neighbor_dict[sessionid]
         neg, cnt = [], 0
+        choice = getattr(self, "_choice", None) or random.choice
         while len(neg) < self.neg_num:
             cnt += 1
-            randomid = random.choice(neighor_set)
+            randomid = choice(neighor_set)
             if randomid in self.item_dict:
                 neg.append(self.item_dict[randomid] - 1)
             if cnt > 20:

@@ -68,9 +68,28 @@ def unpack(packed, B, T, Nn):
     return d
 
 
-def make_sessions(N, n_sessions, max_len=20, seed=2020, p_len=0.55, train=True):
+def make_impressions(N, n_sessions, seed=2020, mean_len=37.0, miss=0.15):
+    """MIND-shaped impression lists (SURVEY 8d cfg 4): one list per session id, length ~ LogNormal with mean
+    `mean_len` (at least 2), article ids uniform; a share `miss` of the entries are articles outside item_dict
+    (mind_preprocess.py:275-280: the impression logs name more articles than the clicked-item dictionary), which the
+    sampler's `if randomid in self.item_dict` (sampler.py:124) rejects."""
+    rs = np.random.RandomState(seed + 17)
+    sigma = 0.6
+    mu = np.log(mean_len) - sigma * sigma / 2
+    lens = np.maximum(2, rs.lognormal(mu, sigma, n_sessions).astype(np.int64))
+    out = {}
+    for sidx in range(n_sessions):
+        ids = rs.randint(0, N, lens[sidx])
+        gone = rs.random_sample(lens[sidx]) < miss
+        out[sidx] = [("x%d" if g else "a%d") % int(i) for i, g in zip(ids, gone)]
+    return out
+
+
+def make_sessions(N, n_sessions, max_len=20, seed=2020, p_len=0.55, train=True, impressions="few"):
     """In-memory session split in the reference's dict layout: (len_dict, session_dict, session_time_dict, item_dict,
-    impressions).  Lengths follow P(T) ~ p_len^T on [1, max_len], items Zipf(1.1)."""
+    impressions).  Lengths follow P(T) ~ p_len^T on [1, max_len], items Zipf(1.1).
+    impressions="few": 8-entry lists for the first 64 sessions (the Globo runs only need a non-empty neighbour dict);
+    "mind": make_impressions() for every session."""
     rs = np.random.RandomState(seed)
     t0 = datetime.datetime(2017, 10, 1)
     publish_dt = [t0 + datetime.timedelta(minutes=int(m)) for m in rs.randint(0, 60 * 24 * 30, N)]
@@ -88,8 +107,11 @@ def make_sessions(N, n_sessions, max_len=20, seed=2020, p_len=0.55, train=True):
                       for j, it in enumerate(items)]
         len_dict.setdefault(L, []).append(key)
     item_dict = {"a%d" % i: i + 1 for i in range(N)}
-    impressions = {sidx: ["a%d" % int(x) for x in rs.randint(0, N, 8)] for sidx in range(min(n_sessions, 64))}
-    return len_dict, sdict, tdict, item_dict, impressions
+    if impressions == "mind":
+        impr = make_impressions(N, n_sessions, seed)
+    else:
+        impr = {sidx: ["a%d" % int(x) for x in rs.randint(0, N, 8)] for sidx in range(min(n_sessions, 64))}
+    return len_dict, sdict, tdict, item_dict, impr
 
 
 def write_dataset(root, N=2000, n_train=5000, n_test=600, max_len=8, fold=0, seed=2020):

@@ -55,8 +55,9 @@ def save_model(model, args, saver=None):
     os.makedirs(args["modelpath"], exist_ok=True)
     path = os.path.join(args["modelpath"], "model.ckpt-" + suf)
     model.sync_updates()
-    model.sync_item_table()                  # catalog-sharded training: collect every owner's rows first
-    if getattr(model, "rank", 0) == 0:       # every rank holds the same state; one writer
+    model.sync_item_table()                  # catalog-sharded training: collect every owner's rows (and moments) first
+    model.sync_optimizer_state()             # data-parallel sharded update: collect every rank's moment slices
+    if getattr(model, "rank", 0) == 0:       # now every rank holds the same state; one writer
         torch.save(model.ps.state_dict(), path)
     return path
 

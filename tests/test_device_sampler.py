@@ -116,3 +116,87 @@ def test_training_with_device_sampler_matches_host_sampler():
         torch.cuda.synchronize()
         losses.append(torch.cat(out))
     assert torch.equal(losses[0], losses[1])
+
+
+# ------------------------------------------------------------------------------------------- impression-list negatives
+def test_impression_oracle_is_the_reference_algorithm_on_another_stream(monkeypatch):
+    """oracle.philox_oracle.device_impression_negatives restates sampler.py:118-131 with Philox words in place of
+    random.choice / np.random.randint.  Drive the product's host implementation (pinned on the reference's own output
+    by test_host_logic / sampler_ref.json) with the SAME words: the two must produce the same negatives."""
+    from tcar_b200 import sampler as S, synth
+    from tcar_b200.device_sampler import impression_csr
+    N, Nn, seed, offset = 500, 12, 99, 5
+    ld, sd, td, idict, _ = synth.make_sessions(N, 300, seed=4)
+    impr = synth.make_impressions(N, 300, seed=4, mean_len=6.0, miss=0.6)        # many misses: tries run out
+    impr[3] = ["x1", "x2"]                                                        # nothing usable: all fills
+    impr[5] = ["a7"]                                                              # a single usable article
+    smp = S.Sampler({k: list(v) for k, v in ld.items()}, sd, td, impr, idict, Nn, batch_size=64, verbose=False)
+    col = S._columnar(sd, td)
+    csr = impression_csr(col, sd, impr, idict)
+    nb = PO.impr_blocks(Nn)
+    for L in sorted(csr)[:4]:
+        keys = [k for k in sd if len(sd[k]) - 1 == L][:40]
+        rows = np.array([col.row[k] for k in keys])
+        want = PO.device_impression_negatives(seed, offset, rows, csr[L][0], csr[L][1], Nn, smp.item_num)
+        for b, key in enumerate(keys):
+            words = PO.philox4x32_10(seed, np.uint64(offset + b * nb) + np.arange(nb, dtype=np.uint64)).reshape(-1)
+            st = {"tries": 0, "found": 0, "fills": 0}
+
+            def choice(seq):
+                pick = seq[(int(words[st["tries"]]) * len(seq)) >> 32]
+                st["tries"] += 1
+                st["found"] += pick in idict
+                return pick
+
+            def randint(lo, hi):
+                v = (int(words[21 + st["found"] + st["fills"]]) * hi) >> 32
+                st["fills"] += 1
+                return v
+
+            monkeypatch.setattr(S.random, "choice", choice)
+            monkeypatch.setattr(S.np.random, "randint", randint)
+            got = smp.neg_neighbor_from_impre(int(key.split("_")[0]))
+            assert got == want[b].tolist(), (L, b, key)
+            assert st["tries"] <= 21
+
+
+@pytest.mark.gpu
+def test_device_impression_negatives_match_the_oracle_and_shard_consistently():
+    from tcar_b200 import synth
+    from tcar_b200.device_sampler import DeviceSampler, impression_csr
+    from tcar_b200.sampler import Sampler, _columnar
+    import copy
+    N, Nn = 3000, 50
+    ld, sd, td, idict, impr = synth.make_sessions(N, 2500, seed=6, impressions="mind")
+    impr[0] = ["x1"]                              # a session whose list holds no known article
+    model = _model(N)
+    random.seed(9)
+    full = DeviceSampler(model, copy.deepcopy(ld), sd, td, impr, idict, Nn, batch_size=128, negative_mode="impression",
+                         negatives="device", seed=13, verbose=False)
+    random.seed(9)
+    half = DeviceSampler(model, copy.deepcopy(ld), sd, td, impr, idict, Nn, batch_size=128, negative_mode="impression",
+                         negatives="device", seed=13, rank=1, world=2, verbose=False)
+    random.seed(9)
+    host = Sampler(copy.deepcopy(ld), sd, td, impr, idict, Nn, batch_size=128, negative_mode="impression", verbose=False)
+    col = _columnar(sd, td)
+    csr = impression_csr(col, sd, impr, idict)
+    offset, in_list = 0, 0
+    for _ in range(8):
+        ids = full.session_id_batches[full.batch_i]
+        bt = full.next_device()
+        packed, B, T, _ = host.next_packed()
+        assert (bt.B, bt.T, bt.Nn) == (B, T, Nn)
+        assert np.array_equal(bt.buf[: 7 * B * T + 3 * B].cpu().numpy(), packed[: 7 * B * T + 3 * B])
+        rows = np.array([col.row[k] for k in ids])
+        want = PO.device_impression_negatives(13, offset, rows, csr[T][0], csr[T][1], Nn, full.item_num)
+        got = bt.neg.cpu().numpy().reshape(B, Nn)
+        assert np.array_equal(got, want)
+        offset += B * PO.impr_blocks(Nn)
+        for b, k in enumerate(ids):
+            allowed = {idict[x] - 1 for x in impr.get(int(k.split("_")[0]), ()) if x in idict}
+            in_list += sum(int(v) in allowed for v in got[b][:3])
+        hb = half.next_device()
+        from tcar_b200.parallel import shard_sessions
+        lo, hi = shard_sessions(B, 1, 2)
+        assert np.array_equal(hb.neg.cpu().numpy().reshape(-1, Nn), got[lo:hi])
+    assert in_list > 0

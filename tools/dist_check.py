@@ -63,6 +63,21 @@ def main():
     res["iext_equal"] = bool(res["iext_mismatch_frac"] < 1e-3 and float(diff.max()) <= 2 ** -7 * float(single.ps.iext.float().abs().max()))
     res["g_theta_rel"] = rel(g_theta, single.ps.theta_g)
     res["item_after_rel"] = rel(item_after, single.ps.item)
+    # checkpoint under the sharded data-parallel update: every rank owns the Adam moments of its row slice only;
+    # save_model must gather them (util.save_model -> sync_optimizer_state) so that the file equals a 1-GPU checkpoint
+    import tempfile
+    from tcar_b200 import util
+    with tempfile.TemporaryDirectory() as d:
+        path = util.save_model(model, dict(dataset="synth/", split_way="Normal/", foldnum=0, modelpath=d + "/r%d/" % rank))
+        dist.barrier()
+        if rank == 0:
+            sd = torch.load(path, map_location="cpu", weights_only=True)
+            want_m, want_v = single.ps.item_m[:, :250].cpu(), single.ps.item_v[:, :250].cpu()
+            res["ckpt_moments_rel"] = max(rel(sd["item_m"], want_m), rel(sd["item_v"], want_v))
+            res["ckpt_nonzero_rows"] = int((sd["item_v"].abs().sum(1) > 0).sum())
+        else:
+            res["ckpt_moments_rel"] = 0.0
+        dist.barrier()
     # ---- catalog-sharded eval vs single GPU
     epacked = synth.make_index_batch(N, B, T, 0, mwdhm, seed=8)
     ebt = single.to_device(torch.from_numpy(epacked).pin_memory(), B, T, 0)
@@ -121,7 +136,8 @@ def main():
     res["catalog"] = cres
     cat.close_peers()
     ok = (cres["ok"] and res["loss_maxabs"] < 1e-5 and res["g_item_rel"] < 1e-5 and res["g_theta_rel"] < 1e-5
-          and res["item_after_rel"] < 1e-6 and res["iext_equal"] and res["top20_equal"] and res["rank_equal"] and res["ce_maxabs"] < 1e-4)
+          and res["item_after_rel"] < 1e-6 and res["iext_equal"] and res["top20_equal"] and res["rank_equal"]
+          and res["ce_maxabs"] < 1e-4 and res["ckpt_moments_rel"] < 1e-5)
     res["ok"] = ok
     print(f"rank {rank}/{world}: " + json.dumps(res), flush=True)
     dist.barrier()
