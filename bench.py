@@ -387,8 +387,20 @@ def multi_gpu_parity(torch, dist, synth, Model, margs, model, mwdhm, rank, world
     res["eval_top20_equal"] = bool(torch.equal(top_m, top_s))
     res["eval_rank_equal"] = bool(torch.equal(hit, ngt_m < 20) and torch.equal(ngt_m[hit], ngt_s[hit]))
     res["eval_ce_maxabs"] = float((ce_m - ce_s).abs().max())
+    # the layout the bench times (eval_round): every rank its OWN batch, two collectives per round
+    Br = 200 + 7 * rank
+    er = synth.make_index_batch(N, Br, 2 + rank % 3, 0, mwdhm, seed=444444 + rank)
+    er_m = multi.to_device(torch.from_numpy(er).pin_memory(), Br, 2 + rank % 3, 0)
+    er_s = single.to_device(torch.from_numpy(er).pin_memory(), Br, 2 + rank % 3, 0)
+    top_r, ngt_r, ce_r = [x.clone() for x in multi.eval_round(er_m, [200 + 7 * g for g in range(world)])]
+    top_s, ngt_s, ce_s = single.eval_step(er_s)
+    hit = ngt_s < 20
+    res["round_top20_equal"] = bool(torch.equal(top_r, top_s))
+    res["round_rank_equal"] = bool(torch.equal(hit, ngt_r < 20) and torch.equal(ngt_r[hit], ngt_s[hit]))
+    res["eval_ce_maxabs"] = max(res["eval_ce_maxabs"], float((ce_r - ce_s).abs().max()))
     ok = (res["loss_maxabs"] < 1e-4 and res["theta_rel"] < 1e-4 and res["item_rel"] < 1e-4 and res["eval_top20_equal"]
-          and res["eval_rank_equal"] and res["eval_ce_maxabs"] < 1e-3)
+          and res["eval_rank_equal"] and res["round_top20_equal"] and res["round_rank_equal"]
+          and res["eval_ce_maxabs"] < 1e-3)
     flag = torch.tensor([1 if ok else 0], device=model.dev, dtype=torch.int32)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     worst = torch.tensor([res["loss_maxabs"], res["theta_rel"], res["item_rel"], res["item_moment_rel"],
@@ -397,6 +409,10 @@ def multi_gpu_parity(torch, dist, synth, Model, margs, model, mwdhm, rank, world
     for k, v in zip(("loss_maxabs", "theta_rel", "item_rel", "item_moment_rel", "eval_ce_maxabs"), worst.tolist()):
         res[k] = v
     res["ok"] = bool(int(flag.item()))
+    for k in ("eval_top20_equal", "eval_rank_equal", "round_top20_equal", "round_rank_equal"):
+        f2 = torch.tensor([1 if res[k] else 0], device=model.dev, dtype=torch.int32)
+        dist.all_reduce(f2, op=dist.ReduceOp.MIN)
+        res[k] = bool(int(f2.item()))
     res["what"] = (f"one {margs['train_parallel']} train step on a global batch of {Bg} sessions over {world} GPUs vs the same "
                    f"batch on one GPU (loss, parameters after Adam), then one catalog-sharded eval batch of 256 queries vs "
                    f"one GPU (top-20 ids bit-equal, ranks, cross loss); worst value over the ranks")
@@ -574,13 +590,15 @@ def run_b200(a):
     def time_eval(batches, steps, shard_, warm=3):
         n = len(batches)
         nx = (lambda i: batches[(i + 1) % n]) if not a.no_lookahead else (lambda i: None)
+        ev = (lambda b, nb: model.eval_round(b, [B] * world, shard=shard_)) if world > 1 else \
+            (lambda b, nb: model.eval_step(b, next_bt=nb))
         for i in range(warm):
-            model.eval_step(batches[i % n], shard=shard_, next_bt=nx(i))
+            ev(batches[i % n], nx(i))
         model.sync_updates()
         barrier()
         e0.record()
         for i in range(warm, warm + steps):
-            model.eval_step(batches[i % n], shard=shard_, next_bt=nx(i))
+            ev(batches[i % n], nx(i))
         model.sync_updates()
         e1.record()
         barrier()
@@ -607,31 +625,39 @@ def run_b200(a):
             hb = make_batches(synth, N, B, [tt] * 4, Nn, mwdhm, seed0=9000 * (rank + 1) + tt)
             db = [model.to_device(h, B, tt, Nn) for h in hb]
             ms = time_train(db, K)
-            he = make_batches(synth, N, B, [tt] * 4, 0, mwdhm, seed0=9100 + tt)
+            he = make_batches(synth, N, B, [tt] * 4, 0, mwdhm, seed0=9100 + tt + 100 * rank)
             de = [model.to_device(h, B, tt, 0) for h in he]
             model.sync_item_table()
             ems = time_eval(de, K, sh)
             sweeps["len_sweep"][str(tt)] = {"train_ms_per_step": ms, "train_sessions_per_s": world * B / (ms * 1e-3),
-                                            "eval_ms_per_step": ems, "eval_queries_per_s": B / (ems * 1e-3)}
+                                            "eval_ms_per_step": ems, "eval_queries_per_s": world * B / (ems * 1e-3)}
             del db, de
 
     # ---- evaluation: full-catalog top-20, catalog sharded across ranks when N > 1 ----------------------------
-    ehost = make_batches(synth, N, B, Ts, 0, mwdhm, seed0=77)               # same queries on every rank
+    # one batch of 512 queries per rank and step (Seq2SeqAttNN.test: batch i goes to rank i mod world; eval_round)
+    ehost = make_batches(synth, N, B, Ts, 0, mwdhm, seed0=77 + 1000 * rank)
     edev = [model.to_device(h, B, t, 0) for h, t in zip(ehost, Ts)]
     shard = None
     if world > 1:
         lo, hi = model.shard_bounds(world)[rank]
         shard = (lo, hi, model.iext_shard(lo, hi))
+    ecounts = [B] * world
     # eval_step(bt, next_bt=...): the test loop's one-batch look-ahead (Seq2SeqAttNN.test)
     look = not a.no_lookahead
     enxt = (lambda i: edev[(i + 1) % nbatch]) if look else (lambda i: None)
+
+    def estep(bt_, nxt_):
+        if world > 1:
+            return model.eval_round(bt_, ecounts, shard=shard)
+        return model.eval_step(bt_, next_bt=nxt_)
+
     for i in range(W):
-        model.eval_step(edev[i % nbatch], shard=shard, next_bt=enxt(i))
+        estep(edev[i % nbatch], enxt(i))
     model.sync_updates()
     barrier()
     e0.record()
     for i in range(W, W + K):
-        model.eval_step(edev[i % nbatch], shard=shard, next_bt=enxt(i))
+        estep(edev[i % nbatch], enxt(i))
     model.sync_updates()
     e1.record()
     barrier()
@@ -643,7 +669,7 @@ def run_b200(a):
     for i in range(K):
         j = (i + 1) % nbatch
         nb = model.to_device(ehost[j], B, Ts[j], 0)              # H2D of the next batch, then this batch's step + D2H
-        top, ngt, ce = model.eval_step(bt, shard=shard, next_bt=nb if look else None)
+        top, ngt, ce = estep(bt, nb if look else None)
         hs = [model.fetch_async(top), model.fetch_async(ngt), model.fetch_async(ce)]
         if pend is not None:
             [h.get() for h in pend]                              # read one step late: the launch queue never drains
@@ -667,9 +693,11 @@ def run_b200(a):
         barrier()
         eval_qp_ms = max_over_ranks(e0.elapsed_time(e1))
     clk = clocks.stop() if rank == 0 else None
-    eval_queries = B * K
-    eval_layout = ("catalog sharded across ranks, one all-gather of result blocks + merge per batch" if world > 1
-                   else "single GPU")
+    eval_queries = world * B * K
+    eval_layout = ("item catalog sharded across the ranks; per step every rank brings its own batch of %d queries: one "
+                   "all-gather of the query blocks, every rank scores all %d queries against its item range (certified "
+                   "local top-20), one all-to-all of the result blocks, merge (Seq2SeqAttNN.eval_round)" % (B, world * B)
+                   if world > 1 else "single GPU")
     parity = multi_gpu_parity(torch, dist, synth, Seq2SeqAttNN, margs, model, mwdhm, rank, world) if world > 1 else None
 
     # ---- the loop a user runs (Seq2SeqAttNN.train): reference-API Sampler on a host thread -> pinned ring -> H2D ->
@@ -815,7 +843,8 @@ def run_b200(a):
                      "layout": eval_layout, "uncertified_share": eval_uncertified,
                      "e2e": {"value": eval_queries / (eval_e2e_ms * 1e-3), "unit": "queries/s",
                              "h2d_bytes_per_step": sum(ehost[i % nbatch].numel() for i in range(K)) * 4 / K,
-                             "d2h_bytes_per_step": B * (20 + 1 + 1) * 4}}}
+                             "d2h_bytes_per_step": B * (20 + 1 + 1) * 4},
+                     "scaling": "weak (512 queries per GPU and step)" if world > 1 else "single"}}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

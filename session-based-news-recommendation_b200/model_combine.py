@@ -106,11 +106,11 @@ class HostFetch:
     def fetch(self, t):
         i = self.i
         self.i = (i + 1) % self.slots
-        n = t.numel()
+        nbytes = t.numel() * t.element_size()
         buf = self.bufs[i]
-        if buf is None or buf.numel() < n or buf.dtype != t.dtype:
-            buf = self.bufs[i] = torch.empty(max(n, 1024), dtype=t.dtype).pin_memory()
-        view = buf[:n].view(t.shape)
+        if buf is None or buf.numel() < nbytes:
+            buf = self.bufs[i] = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8).pin_memory()
+        view = buf[:nbytes].view(t.dtype).view(t.shape)
         view.copy_(t, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
@@ -384,23 +384,29 @@ class Seq2SeqAttNN(CatalogShardedTraining):
                         p(self.negloss), p(self.loss), p(self.coef), p(self.dA_neg), B, bt.Nn)
         return self.loss[:B], self.ce[:B]
 
-    def _score_and_sum(self, ws, iext, e_ptr, cmax_ptr, tmax_ptr, B, n_items, n_pad, mode):
-        """Scoring GEMM + softmax sums: E / chunk maxima, self.sumexp, self.ce = logsumexp(S) - S[label], with the
-        overflow guard (pass 2 is two empty launches unless a row's best score beats the label by > 55 nats)."""
+    def _score_and_sum(self, ws, iext, e_ptr, cmax_ptr, tmax_ptr, B, n_items, n_pad, mode, q=None, c=None, sumexp=None,
+                       ce=None, rowmax=None):
+        """Scoring GEMM + softmax sums: E / chunk maxima, sumexp, ce = logsumexp(S) - S[label], with the overflow
+        guard (pass 2 is two empty launches unless a row's best score beats the label by > 55 nats).  q / c / sumexp /
+        ce / rowmax default to this model's own buffers (another rank's queries in the sharded evaluation)."""
         p, cl = nv.ptr, self._cluster_for(B)
-        q, c, part = p(self.Q), p(self.c_ref), p(ws["part"])
+        q, c, part = p(self.Q if q is None else q), p(self.c_ref if c is None else c), p(ws["part"])
+        sumexp, ce = p(self.sumexp if sumexp is None else sumexp), p(self.ce if ce is None else ce)
+        rowmax_t = self.rowmax if rowmax is None else rowmax
         if not self.softmax_guard:
             nv.counted_call("tcar_score_fwd", 1, q, p(iext), c, e_ptr, part, cmax_ptr, tmax_ptr, B, n_items, n_pad,
                             mode, cl)
-            nv.counted_call("tcar_ce_finish", 1, part, p(self.sumexp), p(self.ce), ws["tiles"], B)
+            nv.counted_call("tcar_ce_finish", 1, part, sumexp, ce, ws["tiles"], B)
+            if mode == 1:
+                rowmax_t[:B].zero_()       # result blocks carry the shift: none here
             return
-        pmax, rowmax = p(ws["pmax"]), p(self.rowmax)
+        pmax, rowmax = p(ws["pmax"]), p(rowmax_t)
         nv.counted_call("tcar_score_fwd_guarded", 1, q, p(iext), c, e_ptr, part, cmax_ptr, tmax_ptr, pmax, None, B,
                         n_items, n_pad, mode, cl)
-        nv.counted_call("tcar_ce_finish_guarded", 1, part, pmax, p(self.sumexp), p(self.ce), rowmax, ws["tiles"], B, 1)
+        nv.counted_call("tcar_ce_finish_guarded", 1, part, pmax, sumexp, ce, rowmax, ws["tiles"], B, 1)
         nv.counted_call("tcar_score_fwd_guarded", 1, q, p(iext), c, e_ptr, part, cmax_ptr, tmax_ptr, None, rowmax, B,
                         n_items, n_pad, mode, cl)
-        nv.counted_call("tcar_ce_finish_guarded", 1, part, None, p(self.sumexp), p(self.ce), rowmax, ws["tiles"], B, 2)
+        nv.counted_call("tcar_ce_finish_guarded", 1, part, None, sumexp, ce, rowmax, ws["tiles"], B, 2)
 
     def backward(self, bt, scatter=True):
         """Gradients of sum_b loss_b wrt all 23 tensors (model_combine.py:156) into ps.item_g / ps.theta_g.
@@ -764,6 +770,127 @@ class Seq2SeqAttNN(CatalogShardedTraining):
                         p(self.m_ngt), p(self.m_ce), G, B)
         return self.m_ids[:B], self.m_ngt[:B], self.m_ce[:B]
 
+    # ------------------------------------------------------------- catalog-sharded evaluation, one batch per rank
+    EQ_Q, EQ_C = QROWS * KEXT * 2, QROWS * 4
+    EQ_A, EQ_T = QROWS * XW * 4, QROWS * NB * 4
+    EQ_BYTES = EQ_Q + EQ_C + EQ_A + EQ_T + QROWS * 4
+
+    def _alloc_eval_round(self, R):
+        if getattr(self, "_eq", None) is not None and self._eq_all.shape[0] == R:
+            return
+        dev = self.dev
+        self._eq = torch.zeros(self.EQ_BYTES, device=dev, dtype=torch.uint8)
+        self._eq_all = torch.zeros(R, self.EQ_BYTES, device=dev, dtype=torch.uint8) if R > 1 else self._eq.view(1, -1)
+        self._ev_send = torch.zeros(R, nv.EVAL_BLOCK_WORDS, device=dev)
+        self._ev_recv = torch.zeros(R, nv.EVAL_BLOCK_WORDS, device=dev) if R > 1 else self._ev_send
+        self._ce_scratch = torch.zeros(QROWS, device=dev)
+
+    def _eq_views(self, blk):
+        """(Q bf16 [512,640], c_ref [512], a_ic [512,500], Tq [512,139], label int32 [512]) inside one exchange block."""
+        o1 = self.EQ_Q
+        o2 = o1 + self.EQ_C
+        o3 = o2 + self.EQ_A
+        o4 = o3 + self.EQ_T
+        return (blk[:o1].view(torch.bfloat16).view(QROWS, KEXT), blk[o1:o2].view(torch.float32),
+                blk[o2:o3].view(torch.float32).view(QROWS, XW), blk[o3:o4].view(torch.float32).view(QROWS, NB),
+                blk[o4:].view(torch.int32))
+
+    def _round_forward(self, bt, block):
+        """Step 1 of eval_round: session forward of the local queries, written straight into an exchange block."""
+        if bt.B == 0:
+            return
+        if self._prefetched is bt:
+            raise RuntimeError("eval_round does not take prefetched batches")
+        mine = self._eq_views(block)
+        keep = (self.Q, self.c_ref, self.a_ic, self.Tq)
+        self.Q, self.c_ref, self.a_ic, self.Tq = mine[:4]
+        try:
+            self._session_forward(bt)
+        finally:
+            self.Q, self.c_ref, self.a_ic, self.Tq = keep
+        mine[4][:bt.B].copy_(bt.label)
+
+    def _round_score(self, eq_all, counts, shard, send):
+        """Step 3 of eval_round: every rank's queries (exchange blocks eq_all [R, EQ_BYTES]) against the item range
+        `shard` = (lo, hi, iext rows): scoring GEMM + guarded softmax sums + certified top-20 -> result blocks send[g]."""
+        p = nv.ptr
+        lo, hi, iext = shard
+        n_loc, n_pad = hi - lo, iext.shape[0]
+        if n_loc > 0:
+            ws = self._score_buffers(n_pad, False)
+            self._ensure_cat_stats()
+        for g, Bg in enumerate(counts):
+            if Bg == 0:
+                continue
+            blk = send[g]
+            if n_loc <= 0:                                   # empty item range of a small catalog: empty lists
+                bi = blk.view(torch.int32)
+                bi[nv.EVAL_OFF_IDS: nv.EVAL_OFF_IDS + Bg * TOPK].fill_(-1)
+                blk[nv.EVAL_OFF_SCORES: nv.EVAL_OFF_SCORES + Bg * TOPK].fill_(float("-inf"))
+                blk[nv.EVAL_OFF_NGT: nv.EVAL_OFF_NGT + 3 * QROWS].zero_()
+                continue
+            Qg, cg, ag, Tg, lg = self._eq_views(eq_all[g])
+            self._score_and_sum(ws, iext, None, p(ws["cmax"]), p(ws["tmax"]), Bg, n_loc, n_pad, 1, q=Qg, c=cg,
+                                sumexp=blk[nv.EVAL_OFF_SUMEXP:], ce=self._ce_scratch, rowmax=blk[nv.EVAL_OFF_ROWMAX:])
+            self._topk(ws, ag, Tg, lg, blk, Bg, n_loc, n_pad, lo)
+
+    def eval_round(self, bt, counts, shard=None):
+        """Catalog-sharded evaluation that SCALES: every rank brings its OWN batch of <= 512 queries (bt; B may be 0 in
+        the last round), so one round evaluates sum(counts) queries.  counts[g] = queries of rank g (the same list on
+        every rank).  Per round:
+          1. session forward of the local queries -> [Q | label scores | a_ic | Tq | labels] (1.97 MB, written in place)
+          2. ONE all-gather of those blocks: every rank now holds every rank's queries
+          3. for every rank g: scoring GEMM of g's queries against the LOCAL item range (+ softmax partial sums with
+             the overflow guard), certified local top-20 and rank counts -> result block g
+          4. ONE all-to-all: rank g receives the blocks about ITS queries from every item range
+          5. tcar_eval_merge: global top-20 (score desc, id asc), summed rank counts, cross loss
+        Same results as eval_step(bt) on one GPU, bit for bit on the ids (model_combine.py:283-306, util.py:8-18)."""
+        import torch.distributed as dist
+        if not self._item_table_synced:
+            self.sync_item_table()
+        on = parallel.is_distributed(self.world)
+        R, me = (self.world, self.rank) if on else (1, 0)
+        counts = [int(c) for c in counts]
+        B = bt.B
+        if len(counts) != R or counts[me] != B:
+            raise ValueError("counts must list the queries of every rank (and counts[rank] == bt.B)")
+        self._alloc_eval_round(R)
+        if shard is None:
+            lo, hi = self.shard_bounds(R)[me]
+            shard = (lo, hi, self.iext_shard(lo, hi))
+        self._round_forward(bt, self._eq)
+        if on:
+            dist.all_gather_into_tensor(self._eq_all.view(-1), self._eq)
+        self._round_score(self._eq_all, counts, shard, self._ev_send)
+        if on:
+            dist.all_to_all_single(self._ev_recv.view(-1), self._ev_send.view(-1))
+        if B == 0:
+            return self.m_ids[:0], self.m_ngt[:0], self.m_ce[:0]
+        return self._merge_blocks(self._ev_recv, R, B)
+
+    def eval_round_virtual(self, bts):
+        """Single-GPU emulation of eval_round over V = len(bts) ranks (tests): the same kernels with the same shard
+        offsets and block layouts, the two collectives replaced by copies.  Returns the per-rank results."""
+        V = len(bts)
+        counts = [b.B for b in bts]
+        self._alloc_eval_round(1)
+        eq_all = torch.zeros(V, self.EQ_BYTES, device=self.dev, dtype=torch.uint8)
+        for v, bt in enumerate(bts):                      # step 1 of every rank + "all-gather"
+            self._round_forward(bt, eq_all[v])
+        sends = []
+        for v, (lo, hi) in enumerate(self.shard_bounds(V)):      # step 3 of every rank
+            send = torch.zeros(V, nv.EVAL_BLOCK_WORDS, device=self.dev)
+            self._round_score(eq_all, counts, (lo, hi, self.iext_shard(lo, hi)), send)
+            sends.append(send)
+        outs = []
+        for v in range(V):                                # "all-to-all" + merge of every rank
+            if counts[v] == 0:
+                outs.append(None)
+                continue
+            recv = torch.stack([sends[src][v] for src in range(V)])
+            outs.append(tuple(x.clone() for x in self._merge_blocks(recv, V, counts[v])))
+        return outs
+
     def shard_bounds(self, G):
         """Contiguous item-id ranges [lo, hi) per shard, aligned to 256 rows so that a shard of the bf16 scoring
         operand is a plain row-slice of ps.iext."""
@@ -907,58 +1034,102 @@ class Seq2SeqAttNN(CatalogShardedTraining):
                     print("Model saved - {}".format(save_model(self, args)))
 
     def test(self, sess, test_data, args):
-        """model_combine.py:254-315."""
+        """model_combine.py:254-315.  Under torchrun the catalog is sharded across the ranks AND every rank evaluates
+        its own batches (eval_round: batch i goes to rank i mod world); the metric sums are then reduced over the
+        ranks, so every rank prints / returns the metrics of the whole test set."""
         print("Measuring...")
         self.sync_item_table()
         (len_dict_test, session_dict_test, session_time_dict_test) = test_data
-        mrr20, recall20, ndcg20, ild20, unexp20, c_loss = [], [], [], [], [], []
+        acc = {"mrr": [], "recall": [], "ndcg": [], "ild": [], "unexp": [], "loss": [], "items": {}}
         sampler = Sampler(len_dict_test, session_dict_test, session_time_dict_test, batch_size=self.batch_size)
-        resultItemDict = {}
+        dist_on = parallel.is_distributed(self.world)
+        R, me = (self.world, self.rank) if dist_on else (1, 0)
+        sizes = [len(b) for b in sampler.session_id_batches]
+        lens = [len(sampler.session_dict[b[0]]) - 1 for b in sampler.session_id_batches]
+        rounds = (len(sizes) + R - 1) // R
+        if dist_on:
+            # this rank's batches: me, me + R, ... (the producer thread packs only those)
+            sampler.session_id_batches = sampler.session_id_batches[me::R]
+            sampler.batch_num = len(sampler.session_id_batches)
         batch = 0
-        shard = None
-        if parallel.is_distributed(self.world):
-            # catalog-sharded evaluation: every rank scores all queries against its own item range
-            lo, hi = self.shard_bounds(self.world)[self.rank]
-            shard = (lo, hi, self.iext_shard(lo, hi))
-        # one batch of look-ahead (as in train): batch i+1 is staged before batch i is evaluated
-        staged = ((packed, B, T, self.stage_to_device(packed, B, T, Nn)) for packed, B, T, Nn in prefetch_packed(sampler))
-        cur = next(staged, None)
-        while cur is not None:
-            nxt = next(staged, None)
-            packed, B, T, bt = cur
-            cur = nxt
+
+        def consume(packed, B, T, top, ngt, ce):
+            nonlocal batch
             batch += 1
             batch_in = packed[: B * T].reshape(B, T).tolist()
             batch_out = packed[7 * B * T + 2 * B: 7 * B * T + 3 * B].tolist()
-            top, ngt, ce = self.eval_step(bt, shard=shard, next_bt=nxt[3] if nxt is not None else None)
-            top, ngt, ce = top.cpu().numpy(), ngt.cpu().numpy(), ce.cpu().numpy()
+            top, ngt, ce = top.get().numpy(), ngt.get().numpy(), ce.get().numpy()
             if batch < 3:
                 print("batch_in:", batch_in[0])
                 print("batch_out:", batch_out[0])
                 print("batch pred:", top[0][:10].tolist())
             ranks = ngt.astype(np.int64) + 1                                    # util.py:14
             hit = ranks <= 20
-            recall20 += hit.tolist()
-            mrr20 += np.where(hit, 1.0 / ranks, 0.0).tolist()
-            ndcg20 += np.where(hit, 1.0 / np.log2(ranks + 1.0), 0.0).tolist()
-            c_loss += ce.tolist()
+            acc["recall"] += hit.tolist()
+            acc["mrr"] += np.where(hit, 1.0 / ranks, 0.0).tolist()
+            acc["ndcg"] += np.where(hit, 1.0 / np.log2(ranks + 1.0), 0.0).tolist()
+            acc["loss"] += ce.tolist()
             batch_pred = [[int(x) for x in row if x >= 0] for row in top]
             for idx, pred in enumerate(batch_pred):
                 if self.category_id is not None and len(pred) > 1:
-                    ild20.append(self.getILD(pred))
-                    unexp20.append(self.getUnexp(batch_in[idx], pred))
+                    acc["ild"].append(self.getILD(pred))
+                    acc["unexp"].append(self.getUnexp(batch_in[idx], pred))
                 for pi in pred:
-                    resultItemDict[pi] = resultItemDict.get(pi, 0) + 1
+                    acc["items"][pi] = acc["items"].get(pi, 0) + 1
             if args.get("is_print"):
                 self.printData(str(args["foldnum"]) + "_" + str(self.curEpoch), batch_in, batch_out, batch_pred)
-        self.last_metrics = {"loss": float(np.mean(c_loss)), "ild": float(np.mean(ild20)) if ild20 else 0.0,
-                             "unexp": float(np.mean(unexp20)) if unexp20 else 0.0, "coverage": len(resultItemDict),
-                             "mrr": float(np.mean(mrr20)), "recall": float(np.mean(recall20)),
-                             "ndcg": float(np.mean(ndcg20))}
+
+        # one batch of look-ahead (as in train): batch i+1 is staged before batch i is evaluated, and batch i's results
+        # are read from pinned memory while batch i+1 runs
+        staged = ((packed, B, T, self.stage_to_device(packed, B, T, Nn)) for packed, B, T, Nn in prefetch_packed(sampler))
+        pending = None
+        if dist_on:
+            for r in range(rounds):
+                counts = [sizes[r * R + g] if r * R + g < len(sizes) else 0 for g in range(R)]
+                if counts[me]:
+                    packed, B, T, bt = next(staged)
+                else:
+                    packed, B, T = None, 0, lens[0]
+                    bt = Batch(torch.zeros(0, device=self.dev, dtype=torch.int32), 0, T, 0)
+                top, ngt, ce = self.eval_round(bt, counts)
+                handles = [self.fetch_async(x) for x in (top, ngt, ce)] if B else None
+                if pending is not None:
+                    consume(*pending)
+                pending = (packed, B, T, *handles) if B else None
+        else:
+            cur = next(staged, None)
+            while cur is not None:
+                nxt = next(staged, None)
+                packed, B, T, bt = cur
+                cur = nxt
+                top, ngt, ce = self.eval_step(bt, next_bt=nxt[3] if nxt is not None else None)
+                handles = [self.fetch_async(x) for x in (top, ngt, ce)]
+                if pending is not None:
+                    consume(*pending)
+                pending = (packed, B, T, *handles)
+        if pending is not None:
+            consume(*pending)
+        sums = np.array([np.sum(acc["loss"]), len(acc["loss"]), np.sum(acc["ild"]), len(acc["ild"]), np.sum(acc["unexp"]),
+                         np.sum(acc["mrr"]), np.sum(acc["recall"]), np.sum(acc["ndcg"])], dtype=np.float64)
+        coverage = len(acc["items"])
+        if dist_on:
+            import torch.distributed as dist
+            t = torch.from_numpy(sums).to(self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            sums = t.cpu().numpy()
+            seen = torch.zeros(self.N, device=self.dev, dtype=torch.int32)
+            if acc["items"]:
+                seen[torch.tensor(list(acc["items"].keys()), device=self.dev, dtype=torch.long)] = 1
+            dist.all_reduce(seen, op=dist.ReduceOp.MAX)
+            coverage = int(seen.sum().item())
+        n = max(sums[1], 1.0)
+        self.last_metrics = {"loss": float(sums[0] / n), "ild": float(sums[2] / sums[3]) if sums[3] else 0.0,
+                             "unexp": float(sums[4] / sums[3]) if sums[3] else 0.0, "coverage": coverage,
+                             "mrr": float(sums[5] / n), "recall": float(sums[6] / n), "ndcg": float(sums[7] / n)}
         print("avg loss...", self.last_metrics["loss"])
         print("avg ILD...", self.last_metrics["ild"])
         print("avg unexp...", self.last_metrics["unexp"])
-        print("len of result dict: ", len(resultItemDict))
+        print("len of result dict: ", coverage)
         print("MRR@20: {}, Recall@20: {}, nDCG@20: {}".format(self.last_metrics["mrr"], self.last_metrics["recall"],
                                                                 self.last_metrics["ndcg"]))
         return self.last_metrics["recall"]

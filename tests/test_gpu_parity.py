@@ -712,3 +712,43 @@ def test_checkpoint_save_restore_gives_identical_eval_and_training(tmp_path):
     torch.cuda.synchronize()
     assert torch.equal(want_loss, got_loss)
     assert torch.equal(want_item, fresh.ps.item) and torch.equal(want_m, fresh.ps.item_m)
+
+
+# ------------------------------------------------------------------------------------------- eval rounds (8e eval)
+@pytest.mark.parametrize("V", [2, 3, 8])
+def test_eval_round_virtual_ranks_equal_single_device(V):
+    """Seq2SeqAttNN.eval_round on one GPU with V virtual ranks (same kernels, shard offsets and block layouts; the
+    all-gather and the all-to-all replaced by copies): every rank's OWN batch -- different sizes and session lengths,
+    one of them empty -- must come back exactly as eval_step returns it on one device."""
+    N = 9000
+    model, content, mwdhm, _ = build(N, emb_scale=20.0)
+    sizes = [150, 37, 0, 512, 1, 64, 300, 5][:V]
+    bts = []
+    for v, Bv in enumerate(sizes):
+        if Bv == 0:
+            from tcar_b200.model_combine import Batch
+            bts.append(Batch(torch.zeros(0, device=model.dev, dtype=torch.int32), 0, 3, 0))
+        else:
+            bts.append(batch_for(model, N, Bv, 1 + (v * 5) % 11, 0, mwdhm, seed=200 + v)[0])
+    want = [None if b.B == 0 else [x.clone() for x in model.eval_step(b)] for b in bts]
+    got = model.eval_round_virtual(bts)
+    torch.cuda.synchronize()
+    for v, (w, g) in enumerate(zip(want, got)):
+        if w is None:
+            assert g is None
+            continue
+        assert torch.equal(w[0], g[0]), f"rank {v}: top-20 ids"
+        hit = w[1] < 20
+        assert torch.equal(hit, g[1] < 20) and torch.equal(w[1][hit], g[1][hit]), f"rank {v}: ranks"
+        np.testing.assert_allclose(g[2].cpu().numpy(), w[2].cpu().numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_eval_round_single_process_equals_eval_step():
+    N, B = 5000, 100
+    model, content, mwdhm, _ = build(N, emb_scale=20.0)
+    bt = batch_for(model, N, B, 4, 0, mwdhm, seed=3)[0]
+    want = [x.clone() for x in model.eval_step(bt)]
+    got = model.eval_round(bt, [B])
+    torch.cuda.synchronize()
+    assert torch.equal(want[0], got[0]) and torch.equal(want[1], got[1])
+    np.testing.assert_allclose(got[2].cpu().numpy(), want[2].cpu().numpy(), rtol=1e-6)
