@@ -662,7 +662,13 @@ def run_b200(a):
     e1.record()
     barrier()
     eval_ms = max_over_ranks(e0.elapsed_time(e1))
-    eval_uncertified = float(model.uncertain[:B].float().mean().item())      # last batch: share sent to the widening pass
+    # share of the queries the certified selection handed to the widening pass, averaged over the batches
+    unc = []
+    for b_ in edev:
+        estep(b_, None)
+        unc.append(float(model.uncertain[:B].float().mean().item()))
+    model.sync_updates()
+    eval_uncertified = sum(unc) / len(unc)
     e0.record()
     bt = model.to_device(ehost[0], B, Ts[0], 0)
     pend = None

@@ -92,8 +92,13 @@ class HostFetch:
     `get()` waits for that one event only.  Reading step i's loss while step i+1 is being enqueued keeps the GPU fed
     (a blocking `.cpu()` per step leaves it idle for the host's whole enqueue time of the next step)."""
 
+    SLOT_BYTES = 1 << 16           # a [512, 20] int32 block is 40 KB
+
     def __init__(self, slots=16):
-        self.slots, self.bufs, self.i = slots, [None] * slots, 0
+        # ONE pinned allocation up front (cudaHostAlloc synchronises the device: never inside the step loop)
+        self.slots, self.i = slots, 0
+        self._pool = torch.empty(slots * self.SLOT_BYTES, dtype=torch.uint8).pin_memory()
+        self.bufs = [self._pool[k * self.SLOT_BYTES: (k + 1) * self.SLOT_BYTES] for k in range(slots)]
 
     class Handle:
         def __init__(self, view, event):
@@ -108,8 +113,8 @@ class HostFetch:
         self.i = (i + 1) % self.slots
         nbytes = t.numel() * t.element_size()
         buf = self.bufs[i]
-        if buf is None or buf.numel() < nbytes:
-            buf = self.bufs[i] = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8).pin_memory()
+        if buf.numel() < nbytes:           # unusually large result: give this slot its own (one-off) allocation
+            buf = self.bufs[i] = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
         view = buf[:nbytes].view(t.dtype).view(t.shape)
         view.copy_(t, non_blocking=True)
         ev = torch.cuda.Event()

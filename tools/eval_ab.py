@@ -59,6 +59,11 @@ def main():
         model.eval_step(bt)
         shares.append(int(model.uncertain[:B].sum().item()))
     print("queries sent to the widening pass per batch of 512 (T per batch", Ts, "):", shares, flush=True)
+    eps = (model.top_scores[:B, 19] - model.tau[:B]).cpu().numpy()
+    s = model.top_scores[:B].cpu().numpy()
+    print("last batch: eps median %.3e, s20 median %.3e, s1-s20 median %.3e, s19-s20 median %.3e, cat_stats %s"
+          % (np.median(eps), np.median(s[:, 19]), np.median(s[:, 0] - s[:, 19]), np.median(s[:, 18] - s[:, 19]),
+             model.cat_stats.cpu().numpy()), flush=True)
     orig = nv.counted_call
     marks = []
 
