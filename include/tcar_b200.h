@@ -404,6 +404,13 @@ int tcar_score_fwd_groups_guarded(const void* q_bf16, long long q_stride, const 
                                   const void* iext_bf16, void* e_out, long long e_stride, float* rowsum_part,
                                   long long part_stride, float* rowmax_part, const float* rowmax, const int* n_rows,
                                   int groups, int n_items, int n_pad, int cluster, void* stream);
+/* All groups in ONE launch (what tcar_score_fwd_groups_guarded does for more than one group with CTA pairs): work unit =
+ * (256-session row block, 256-item tile), every CTA pair takes a contiguous run of units and swaps its resident session
+ * rows when the run crosses into the next row block.  Train mode only. */
+int tcar_score_fwd_multi(const void* q_bf16, long long q_stride, const float* c_ref, long long c_stride,
+                         const void* iext_bf16, void* e_out, long long e_stride, float* rowsum_part,
+                         long long part_stride, float* rowmax_part, const float* rowmax, const int* n_rows, int groups,
+                         int n_items, int n_pad, void* stream);
 int tcar_rowmax_groups(const float* rowmax_part, long long part_stride, float* rowmax, int n_tiles, const int* n_rows,
                        int groups, void* stream);
 

@@ -60,6 +60,7 @@ SIGNATURES = {
     "tcar_rowsum_finish": [_P, _P, _I, _I, _I, _P],
     "tcar_score_fwd_groups": [_P, _LL, _P, _LL, _P, _P, _LL, _P, _LL, _P, _I, _I, _I, _I, _P],
     "tcar_score_fwd_groups_guarded": [_P, _LL, _P, _LL, _P, _P, _LL, _P, _LL, _P, _P, _P, _I, _I, _I, _I, _P],
+    "tcar_score_fwd_multi": [_P, _LL, _P, _LL, _P, _P, _LL, _P, _LL, _P, _P, _P, _I, _I, _I, _P],
     "tcar_rowmax_groups": [_P, _LL, _P, _I, _P, _I, _P],
     "tcar_score_bwd_q_multi_part_elems": [_I],
     "tcar_score_bwd_q_multi": [_P, _LL, _P, _P, _P, _P, _I, _I, _P],

@@ -136,6 +136,15 @@ extern "C" int tcar_score_fwd_groups_guarded(const void* q_bf16, long long q_str
                                              const float* rowmax, const int* n_rows, int groups, int n_items, int n_pad,
                                              int cluster, void* stream) {
     if (!n_rows || groups < 1) return TCAR_ERR_ARG;
+    int present = 0;
+    for (int g = 0; g < groups; ++g) present += n_rows[g] > 0;
+    // several groups (or TCAR_FWD_MULTI=1): one launch over all of them; TCAR_FWD_MULTI=0 keeps the per-group launches
+    const char* env = getenv("TCAR_FWD_MULTI");
+    const bool multi = cluster == TCAR_CLUSTER_PAIR && groups <= TCAR_MAX_PEERS && (q_stride & 7) == 0 &&
+                       (env ? env[0] == '1' : present > 1);
+    if (multi)
+        return tcar_score_fwd_multi(q_bf16, q_stride, c_ref, c_stride, iext_bf16, e_out, e_stride, rowsum_part,
+                                    part_stride, rowmax_part, rowmax, n_rows, groups, n_items, n_pad, stream);
     for (int g = 0; g < groups; ++g) {
         if (n_rows[g] <= 0) continue;
         const int rc = tcar_score_fwd_guarded(static_cast<const uint16_t*>(q_bf16) + g * q_stride, iext_bf16,

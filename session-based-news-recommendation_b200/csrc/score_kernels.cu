@@ -477,6 +477,247 @@ score_fwd_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     if (warp == 2) tmem_dealloc_pair(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------------ forward, all groups
+// The session groups of a catalog-sharded step (group g = rank g's <= 512 sessions, scored against the caller's item
+// range) in ONE launch of the CTA-pair kernel.  Work unit = (row block of 256 sessions, item tile of 256); the units are
+// numbered row-block major and every pair takes one contiguous run of them, so it changes its resident 2 x 160 KB
+// session operand at most a few times (one TMA reload from L2 each, waited for by a `q_empty` barrier the MMA warp
+// commits behind the last MMA that reads the old rows).  Replaces one launch per group (R x pipeline ramp, R x resident
+// operand load per pair, and pairs left idle when 74 is not a multiple of the row blocks).
+// Pass 2 of the overflow guard: row blocks none of whose rows are above the limit are skipped unit by unit.
+constexpr int M_MAX_RB = 2 * TCAR_MAX_PEERS;       // row blocks: 16 groups x 2
+
+struct FwdMultiParams {
+    __nv_bfloat16* E;          // group g at E + g * e_stride
+    float* rowsum_part;        // group g at rowsum_part + g * part_stride
+    float* rowmax_part;        // same stride (nullable)
+    const float* c_ref;        // group g at c_ref + g * c_stride
+    const float* rowmax;       // [groups][512] (nullable: pass 1)
+    long long e_stride, part_stride, c_stride;
+    int n_items, n_tiles, e_pitch, n_rb;
+    unsigned char rb_group[M_MAX_RB], rb_block[M_MAX_RB];
+    short rb_rows[M_MAX_RB];   // sessions of the row block's GROUP
+};
+
+__global__ void __launch_bounds__(P_THREADS, 1)
+score_fwd_multi_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_i,
+                       const __grid_constant__ FwdMultiParams p) {
+    PDL_ENTER();
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ int s_need[M_MAX_RB];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + F_A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + P_STAGES * P_B_STAGE);
+    uint64_t* full = bars;                      // [P_STAGES]  leader
+    uint64_t* empty = bars + P_STAGES;          // [P_STAGES]  per CTA, MMA commit multicast
+    uint64_t* acc_full = bars + 2 * P_STAGES;   // [P_NACC]    per CTA, MMA commit multicast
+    uint64_t* acc_empty = acc_full + P_NACC;    // [P_NACC]    leader, 16 epilogue-warp arrivals
+    uint64_t* a_full = acc_empty + P_NACC;      // [1]         leader: resident session rows landed
+    uint64_t* q_empty = a_full + 1;             // [1]         per CTA, MMA commit multicast: old session rows retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_empty + 1);
+
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t lane = lane_id();
+    const uint32_t rank = cluster_ctarank();    // 0 = leader
+    const uint32_t pair_id = blockIdx.x >> 1;
+    const uint32_t n_pairs = gridDim.x >> 1;
+    const uint32_t units = (uint32_t)p.n_rb * (uint32_t)p.n_tiles;
+    const uint32_t u0 = (uint32_t)(((uint64_t)pair_id * units) / n_pairs);
+    const uint32_t u1 = (uint32_t)(((uint64_t)(pair_id + 1) * units) / n_pairs);
+
+    // which row blocks does this pass touch?  (same answer in both CTAs of the pair)
+    for (int rb = 0; rb < p.n_rb; ++rb) {
+        bool need = p.rowmax == nullptr;
+        if (p.rowmax) {
+            const int g = p.rb_group[rb], r0 = p.rb_block[rb] * 2 * BM;
+            for (int r = r0 + threadIdx.x; r < r0 + 2 * BM && r < p.rb_rows[rb]; r += blockDim.x)
+                need |= p.rowmax[(size_t)g * QROWS + r] > TCAR_EXP_LIMIT2;
+        }
+        const int any = __syncthreads_or(need);
+        if (threadIdx.x == 0) s_need[rb] = any;
+    }
+    __syncthreads();
+    bool work = false;
+    for (uint32_t u = u0; u < u1; u += (uint32_t)p.n_tiles - (u % (uint32_t)p.n_tiles)) work |= s_need[u / p.n_tiles] != 0;
+    if (!work) return;
+
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&map_q);
+        tma_prefetch_desc(&map_i);
+    }
+    if (warp == 1 && elect_one()) {
+        for (int i = 0; i < P_STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < P_NACC; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 16);
+        }
+        mbar_init(a_full, 1);
+        mbar_init(q_empty, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc_pair(tmem_slot, 512);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer (both CTAs; completion bytes land on the LEADER's barriers) =================
+        if (elect_one()) {
+            const uint32_t a_full_l = mapa_u32(a_full, 0);
+            uint32_t stage = 0, phase = 0, qe_par = 0;
+            int cur_rb = -1;
+            for (uint32_t u = u0; u < u1; ++u) {
+                const int rb = u / p.n_tiles, tile = u % p.n_tiles;
+                if (!s_need[rb]) continue;
+                if (rb != cur_rb) {
+                    if (cur_rb >= 0) {                       // every MMA reading the old rows has retired
+                        mbar_wait(q_empty, qe_par);
+                        qe_par ^= 1;
+                    }
+                    if (rank == 0) mbar_expect_tx(a_full, 2 * F_A_BYTES);
+                    for (int kb = 0; kb < NKB; ++kb)
+                        tma_load_3d_pair(smem_a + kb * (BM * BK * 2), &map_q, a_full_l, kb * BK,
+                                         p.rb_block[rb] * 2 * BM + rank * BM, p.rb_group[rb]);
+                    cur_rb = rb;
+                }
+                const int n0 = tile * P_BN + rank * P_HALF;
+                for (int kb = 0; kb < NKB; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    if (rank == 0) mbar_expect_tx(&full[stage], 2 * P_B_STAGE);
+                    tma_load_2d_pair(smem_b + stage * P_B_STAGE, &map_i, mapa_u32(&full[stage], 0), kb * BK, n0);
+                    if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader CTA only) =================
+        if (rank == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(2 * BM, P_BN, 0, 0);
+            uint32_t stage = 0, phase = 0, q_par = 0, it = 0;
+            int cur_rb = -1;
+            for (uint32_t u = u0; u < u1; ++u) {
+                const int rb = u / p.n_tiles;
+                if (!s_need[rb]) continue;
+                if (rb != cur_rb) {
+                    mbar_wait(a_full, q_par);
+                    q_par ^= 1;
+                    tc_fence_after();
+                    cur_rb = rb;
+                }
+                // does a later unit of this pair use other session rows?  then they may be overwritten once the MMAs
+                // of THIS unit have retired, provided this is the last unit of the current row block
+                bool last_of_rb = true, more = false;
+                for (uint32_t v = u + 1; v < u1; ++v) {
+                    const int rv = v / p.n_tiles;
+                    if (!s_need[rv]) continue;
+                    if (rv == rb) last_of_rb = false; else more = true;
+                    break;
+                }
+                const uint32_t acc = it % P_NACC;
+                const uint32_t acc_phase = (it / P_NACC) & 1;
+                ++it;
+                mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < NKB; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a_addr = smem_u32(smem_a + kb * (BM * BK * 2));
+                        const uint32_t b_addr = smem_u32(smem_b + stage * P_B_STAGE);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_bf16_pair(tmem_base + acc * P_BN, sdesc_kmajor(a_addr + k * 32),
+                                           sdesc_kmajor(b_addr + k * 32), idesc, (kb | k) != 0);
+                        umma_commit_pair(&empty[stage], 3);
+                        if (kb == NKB - 1) {
+                            umma_commit_pair(&acc_full[acc], 3);
+                            if (last_of_rb && more) umma_commit_pair(q_empty, 3);
+                        }
+                    }
+                    __syncwarp();
+                    if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue: thread <-> session row, warp <-> (TMEM lane quarter, column half) =================
+        const uint32_t e = warp - 4;
+        const uint32_t q = e & 3, h = e >> 2;
+        const uint32_t acc_empty_l = mapa_u32(acc_empty, 0);
+        uint32_t it = 0;
+        int cur_rb = -1;
+        uint32_t row = 0;
+        bool row_ok = false, store_ok = false;
+        float cshift = 0.f;
+        FwdParams pg;                      // the per-group view fwd_epilogue_chunk works on
+        pg.n_items = p.n_items;
+        pg.e_pitch = p.e_pitch;
+        pg.E = p.E;
+        size_t part_off = 0;
+        for (uint32_t u = u0; u < u1; ++u) {
+            const int rb = u / p.n_tiles;
+            const uint32_t tile = u % p.n_tiles;
+            if (!s_need[rb]) continue;
+            if (rb != cur_rb) {
+                cur_rb = rb;
+                const int g = p.rb_group[rb];
+                const uint32_t n_rows = (uint32_t)p.rb_rows[rb];
+                row = p.rb_block[rb] * 2 * BM + rank * BM + q * 32 + lane;
+                row_ok = row < n_rows;
+                store_ok = row < ((n_rows + 63u) & ~63u);
+                cshift = 0.f;
+                if (row_ok) {
+                    cshift = p.c_ref[(size_t)g * p.c_stride + row] * kLog2e;
+                    if (p.rowmax) {
+                        const float m = p.rowmax[(size_t)g * QROWS + row];
+                        if (m > TCAR_EXP_LIMIT2) cshift += m;
+                    }
+                }
+                pg.E = p.E + (size_t)g * p.e_stride;
+                part_off = (size_t)g * p.part_stride;
+            }
+            const uint32_t acc = it % P_NACC;
+            const uint32_t acc_phase = (it / P_NACC) & 1;
+            ++it;
+            const int n0 = tile * P_BN + h * 128;
+            mbar_wait(&acc_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((q * 32) << 16) + acc * P_BN + h * 128;
+            const bool tail = n0 + 128 > p.n_items;
+            float psum = 0.f, tmax = -INFINITY, amax = -INFINITY;
+            uint32_t va[32], vb[32];
+            tmem_ld32(taddr, va);
+            tmem_ld_wait();
+            tmem_ld32(taddr + 32, vb);
+            fwd_epilogue_chunk<0>(va, pg, cshift, row_ok, store_ok, tail, row, n0, psum, tmax, amax);
+            tmem_ld_wait();
+            tmem_ld32(taddr + 64, va);
+            fwd_epilogue_chunk<0>(vb, pg, cshift, row_ok, store_ok, tail, row, n0 + 32, psum, tmax, amax);
+            tmem_ld_wait();
+            tmem_ld32(taddr + 96, vb);
+            fwd_epilogue_chunk<0>(va, pg, cshift, row_ok, store_ok, tail, row, n0 + 64, psum, tmax, amax);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc_empty_l + acc * 8);
+            fwd_epilogue_chunk<0>(vb, pg, cshift, row_ok, store_ok, tail, row, n0 + 96, psum, tmax, amax);
+            if (row_ok) {
+                p.rowsum_part[part_off + (size_t)(tile * 2 + h) * QROWS + row] = psum;
+                if (p.rowmax_part) p.rowmax_part[part_off + (size_t)(tile * 2 + h) * QROWS + row] = amax;
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) tmem_dealloc_pair(tmem_base, 512);
+}
+
 // ------------------------------------------------------------------------------------------------ dQ = E . Iext
 constexpr int Q_CH = 320;                 // feature columns per CTA (half of KEXT): one N=256 + one N=64 MMA
 constexpr int Q_STAGES = 4;
@@ -859,6 +1100,20 @@ static int make_map_e4(CUtensorMap* m, const void* base, uint64_t n_pad, uint32_
     return r == CUDA_SUCCESS ? 0 : TCAR_ERR_TENSORMAP;
 }
 
+// Session operands of several groups, `group_stride` bf16 elements apart, as a 3-D tensor (k | row | group), SW128.
+static int make_map_q3(CUtensorMap* m, const void* base, uint32_t groups, uint64_t group_stride) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return TCAR_ERR_DRIVER;
+    cuuint64_t dims[3] = {KEXT, QROWS, groups};
+    cuuint64_t strides[2] = {KEXT * 2, group_stride * 2};
+    cuuint32_t box[3] = {BK, BM, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : TCAR_ERR_TENSORMAP;
+}
+
 static int sm_count() {
     static int n = 0;
     if (!n) {
@@ -996,6 +1251,69 @@ extern "C" int tcar_score_fwd_guarded(const void* q_bf16, const void* iext_bf16,
 }
 
 extern "C" int tcar_score_fwd_tiles(int n_pad) { return n_pad / F_BN; }
+
+// All session groups in one launch (score_fwd_multi_kernel): train mode, CTA pairs.  Strides in ELEMENTS of the
+// respective arrays; rowmax_part shares part_stride; rowmax is [groups][512].
+extern "C" int tcar_score_fwd_multi(const void* q_bf16, long long q_stride, const float* c_ref, long long c_stride,
+                                    const void* iext_bf16, void* e_out, long long e_stride, float* rowsum_part,
+                                    long long part_stride, float* rowmax_part, const float* rowmax, const int* n_rows,
+                                    int groups, int n_items, int n_pad, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!n_rows || groups < 1 || groups > TCAR_MAX_PEERS || n_pad % 256 != 0 || n_items > n_pad || !e_out ||
+        !rowsum_part || q_stride < (long long)QROWS * KEXT || (q_stride & 7) || e_stride < (long long)QROWS * n_pad)
+        return TCAR_ERR_ARG;
+    FwdMultiParams p = {};
+    int nrb = 0;
+    for (int g = 0; g < groups; ++g) {
+        if (n_rows[g] > QROWS) return TCAR_ERR_ARG;
+        if (n_rows[g] <= 0) continue;
+        for (int b = 0; b * 2 * BM < n_rows[g]; ++b, ++nrb) {
+            p.rb_group[nrb] = (unsigned char)g;
+            p.rb_block[nrb] = (unsigned char)b;
+            p.rb_rows[nrb] = (short)n_rows[g];
+        }
+    }
+    if (nrb == 0) return 0;
+    CUtensorMap mq, mi;
+    int rc = make_map_q3(&mq, q_bf16, (uint32_t)groups, (uint64_t)q_stride);
+    if (rc) return rc;
+    rc = make_map_bf16(&mi, iext_bf16, n_pad, KEXT, KEXT, BK, P_HALF);
+    if (rc) return rc;
+    p.E = static_cast<__nv_bfloat16*>(e_out);
+    p.rowsum_part = rowsum_part;
+    p.rowmax_part = rowmax_part;
+    p.c_ref = c_ref;
+    p.rowmax = rowmax;
+    p.e_stride = e_stride;
+    p.part_stride = part_stride;
+    p.c_stride = c_stride;
+    p.n_items = n_items;
+    p.n_tiles = n_pad / P_BN;
+    p.e_pitch = n_pad;
+    p.n_rb = nrb;
+    int n_pairs = sm_count() / 2;
+    if ((long long)n_pairs > (long long)nrb * p.n_tiles) n_pairs = nrb * p.n_tiles;
+    cudaError_t e = cudaFuncSetAttribute(score_fwd_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_pairs * 2);
+    cfg.blockDim = dim3(P_THREADS);
+    cfg.dynamicSmemBytes = P_SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+#ifndef TCAR_NO_PDL
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+#endif
+    return (int)cudaLaunchKernelEx(&cfg, score_fwd_multi_kernel, mq, mi, p);
+}
 
 extern "C" int tcar_score_bwd_q_splits(int n_rows, int n_pad) {
     const int mtiles = (n_rows + BM - 1) / BM;

@@ -7,6 +7,7 @@ test_gpu_parity.py).  Tolerances: fp32 accumulation of bf16 products -> rtol 2e-
 """
 import ctypes as C
 
+import numpy as np
 import pytest
 import torch
 
@@ -206,3 +207,62 @@ def test_score_groups_match_single_group_calls(native, counts, N, monkeypatch):
     assert (gi[1:].double() - ref).abs().max().item() / scale < 1e-4
     want = float((gi.double() ** 2).sum())
     assert abs(float(sqp.double().sum()) - want) <= 1e-5 * want
+
+
+@pytest.mark.parametrize("counts,N", [([512, 200, 512], 4000), ([77, 512], 1500)])
+def test_score_groups_overflow_guard_matches_single_group_calls(native, counts, N):
+    """Both passes of the softmax overflow guard over several session groups in one launch each
+    (tcar_score_fwd_groups_guarded -> score_fwd_multi_kernel, tcar_rowmax_groups) against the single-group entry points:
+    E, partial sums and row maxima bit-identical; rows whose label score lies ~200 nats below their best candidate get
+    the extra shift (finite E, largest term 2^0), quiet rows keep their pass-1 values."""
+    R = len(counts)
+    g = torch.Generator(device="cuda").manual_seed(N + R)
+    n_pad = (N + 255) // 256 * 256
+    lib = native.lib()
+    tiles = lib.tcar_score_fwd_tiles(n_pad)
+    I = torch.zeros(n_pad, KEXT, device="cuda", dtype=torch.bfloat16)
+    I[:N] = (torch.randn(N, KEXT, device="cuda", generator=g) * 0.1).bfloat16()
+    Q = torch.zeros(R, QROWS, KEXT, device="cuda", dtype=torch.bfloat16)
+    c = torch.randn(R, QROWS, device="cuda", generator=g) * 0.3
+    for r, b in enumerate(counts):
+        Q[r, :b] = (torch.randn(b, KEXT, device="cuda", generator=g) * 0.5).bfloat16()
+        c[r, 3:b:37] -= 200.0                      # these rows overflow exp(S - c) without the guard
+    E = torch.zeros(R, QROWS * n_pad, device="cuda", dtype=torch.bfloat16)
+    part = torch.zeros(R, tiles * QROWS, device="cuda")
+    pmax = torch.zeros(R, tiles * QROWS, device="cuda")
+    rowmax = torch.zeros(R, QROWS, device="cuda")
+    cnt = (C.c_int * R)(*counts)
+    p = native.ptr
+    args = (p(Q), QROWS * KEXT, p(c), QROWS, p(I), p(E), QROWS * n_pad, p(part), tiles * QROWS)
+    native.call("tcar_score_fwd_groups_guarded", *args, p(pmax), None, cnt, R, N, n_pad, -2)
+    native.call("tcar_rowmax_groups", p(pmax), tiles * QROWS, p(rowmax), tiles, cnt, R)
+    torch.cuda.synchronize()
+    E_pass1 = E.clone()
+    native.call("tcar_score_fwd_groups_guarded", *args, None, p(rowmax), cnt, R, N, n_pad, -2)
+    torch.cuda.synchronize()
+    assert torch.isfinite(E.float()).all() and torch.isfinite(part).all()
+    for r, b in enumerate(counts):
+        E1 = torch.zeros(QROWS, n_pad, device="cuda", dtype=torch.bfloat16)
+        p1 = torch.zeros(tiles, QROWS, device="cuda")
+        m1 = torch.zeros(tiles, QROWS, device="cuda")
+        rm1 = torch.zeros(QROWS, device="cuda")
+        se, ce = torch.zeros(QROWS, device="cuda"), torch.zeros(QROWS, device="cuda")
+        native.call("tcar_score_fwd_guarded", p(Q[r]), p(I), p(c[r]), p(E1), p(p1), None, None, p(m1), None, b, N, n_pad, 0, -2)
+        native.call("tcar_ce_finish_guarded", p(p1), p(m1), p(se), p(ce), p(rm1), tiles, b, 1)
+        torch.cuda.synchronize()
+        assert torch.equal(m1.view(-1), pmax[r]) and torch.equal(rm1[:b], rowmax[r, :b])
+        hot = rm1[:b] > 80.0
+        assert int(hot.sum()) == len(range(3, b, 37)) and bool(hot[3])
+        native.call("tcar_score_fwd_guarded", p(Q[r]), p(I), p(c[r]), p(E1), p(p1), None, None, None, p(rm1), b, N, n_pad, 0, -2)
+        native.call("tcar_ce_finish_guarded", p(p1), None, p(se), p(ce), p(rm1), tiles, b, 2)
+        torch.cuda.synchronize()
+        assert torch.equal(E1.view(-1), E[r]) and torch.equal(p1.view(-1), part[r])
+        # CE of a shifted row = logsumexp(S) - c, against fp64 over the same bf16 operands
+        S = Q[r, :b].double() @ I[:N].double().t()
+        want = torch.logsumexp(S, 1) - c[r, :b].double()
+        np.testing.assert_allclose(ce[:b].cpu().double().numpy(), want.cpu().numpy(), rtol=2e-5, atol=2e-4)
+        # quiet rows: pass 2 left their E untouched
+        Eb1 = E_pass1[r].view(n_pad // 8, QROWS, 8)
+        Eb2 = E[r].view(n_pad // 8, QROWS, 8)
+        quiet = (~hot).nonzero().flatten()
+        assert torch.equal(Eb1[:, quiet], Eb2[:, quiet])
