@@ -42,6 +42,7 @@ extern "C" {
 #define TCAR_EVAL_OFF_SUMEXP (TCAR_EVAL_OFF_NGT + TCAR_QROWS)   /* float [512] softmax partial sum                   */
 #define TCAR_EVAL_OFF_ROWMAX (TCAR_EVAL_OFF_SUMEXP + TCAR_QROWS) /* float [512] largest exponent argument (guard)    */
 #define TCAR_EVAL_BLOCK_WORDS (TCAR_EVAL_OFF_ROWMAX + TCAR_QROWS)
+#define TCAR_EVAL_NSEL 33         /* entries of a (query, item range) candidate list: 32 chunks + 1 bound carrier     */
 #define TCAR_WIDEN_SPLITS 16      /* CTAs sharing one flagged query in tcar_eval_topk_widen                       */
 #define TCAR_NORM_SPLIT 8    /* partial sums per tensor written by tcar_sqnorm_segments                     */
 #define TCAR_TABLE_GRAD_CHUNKS 148   /* max click chunks (CTAs) of tcar_small_table_grads pass 1               */
@@ -433,6 +434,21 @@ int tcar_eval_topk_certified(const float* chunkmax, const float* tilemax, const 
                              const float* item, const float* content, const int32_t* mwdhm, const int32_t* label,
                              int32_t* top_ids, float* top_scores, int32_t* n_greater, int B, int N, int n_pad,
                              int item_offset, const float* cat_stats, int32_t* uncertain, float* tau, void* stream);
+/* The two halves of tcar_eval_topk_certified for the catalog-sharded evaluation, where the chunk maxima of an item
+ * range and the queries' owner live on different GPUs (Seq2SeqAttNN.eval_round):
+ *   tcar_eval_select   (item range)  sel_vals / sel_ids [B][TCAR_EVAL_NSEL]: the range's 32 best chunks per query as
+ *                      (bf16-GEMM chunk maximum, GLOBAL chunk id = (item_offset + local item) / 8; -1 = none), and a
+ *                      33rd entry (id -2) whose value bounds every chunk of the range that is NOT listed.  No re-scoring.
+ *   tcar_eval_rescore  (query owner) `lists` such lists per query, list_stride words apart: the 32 best entries overall
+ *                      are re-scored exactly from the fp32 tables (global ids, N_total items), top-20 / n_greater as in
+ *                      tcar_eval_topk; the 33rd best value bounds everything else, queries it cannot certify are flagged
+ *                      (uncertain, tau) for tcar_eval_topk_widen on every item range.  lists * 33 <= 512. */
+int tcar_eval_select(const float* chunkmax, const float* tilemax, float* sel_vals, int32_t* sel_ids, int B, int N,
+                     int n_pad, int item_offset, void* stream);
+int tcar_eval_rescore(const float* sel_vals, const int32_t* sel_ids, int lists, long long list_stride, const float* a_ic,
+                      const float* Tq, const float* item, const float* content, const int32_t* mwdhm,
+                      const int32_t* label, int32_t* top_ids, float* top_scores, int32_t* n_greater, int B, int N_total,
+                      const float* cat_stats, int32_t* uncertain, float* tau, void* stream);
 /* Second stage: for every flagged query, re-scores ALL chunks whose maximum reaches tau[b] (any number of them -- in
  * the limit a full exact scan, so the work of one query is spread over TCAR_WIDEN_SPLITS CTAs and their partial lists
  * are merged by a second launch) and rewrites its top_ids / top_scores / n_greater; certified queries are untouched
@@ -455,6 +471,13 @@ int tcar_topk_merge(const int32_t* ids, const float* scores, int32_t* out_ids, f
  * shards' partial sums and their own exponent shifts (util.py:14, model_combine.py:145,301). */
 int tcar_eval_merge(const void* blocks, long long block_words, int32_t* out_ids, float* out_scores, int32_t* out_ngt,
                     float* out_ce, int G, int B, void* stream);
+/* Pieces of the same reduction for the two-stage sharded evaluation: the cross loss from G ranges' (sumexp, rowmax)
+ * vectors `gstride` words apart; and the list / rank-count merge restricted to the queries flagged in only_if[b] (the
+ * widening pass of every item range), all other queries keep what out_* hold. */
+int tcar_eval_ce_combine(const float* sumexp, const float* rowmax, long long gstride, float* out_ce, int G, int B,
+                         void* stream);
+int tcar_eval_merge_flagged(const void* blocks, long long block_words, const int32_t* only_if, int32_t* out_ids,
+                            float* out_scores, int32_t* out_ngt, int G, int B, void* stream);
 
 #ifdef __cplusplus
 }

@@ -13,6 +13,11 @@ NORM_SPLIT = 8
 EXP_LIMIT2 = 80.0        # TCAR_EXP_LIMIT2
 EVAL_OFF_SCORES, EVAL_OFF_IDS, EVAL_OFF_NGT = 0, QROWS * TOPK, 2 * QROWS * TOPK      # TCAR_EVAL_OFF_*
 EVAL_OFF_SUMEXP, EVAL_OFF_ROWMAX, EVAL_BLOCK_WORDS = EVAL_OFF_NGT + QROWS, EVAL_OFF_NGT + 2 * QROWS, EVAL_OFF_NGT + 3 * QROWS
+EVAL_NSEL = 33           # TCAR_EVAL_NSEL
+# candidate-list block of one (item range, query owner) pair in the two-stage sharded evaluation:
+# [vals 512x33 f32 | chunk ids 512x33 i32 | sumexp 512 f32 | rowmax 512 f32]
+SEL_OFF_IDS, SEL_OFF_SUMEXP = QROWS * EVAL_NSEL, 2 * QROWS * EVAL_NSEL
+SEL_OFF_ROWMAX, SEL_BLOCK_WORDS = SEL_OFF_SUMEXP + QROWS, SEL_OFF_SUMEXP + 2 * QROWS
 MAX_PEERS, PEER_HANDLE_BYTES = 16, 64      # TCAR_MAX_PEERS, TCAR_PEER_HANDLE_BYTES
 BIN_OFF = (0, 13, 45, 53, 78, 139)
 CLUSTER_PAIR = -2      # TCAR_CLUSTER_PAIR: tcar_score_fwd with tcgen05.mma.cta_group::2 CTA pairs
@@ -77,11 +82,15 @@ SIGNATURES = {
     "tcar_refresh_iext_items": [_P, _P, _I, _P],
     "tcar_eval_topk": [_P] * 11 + [_I] * 4 + [_P],
     "tcar_eval_topk_certified": [_P] * 11 + [_I] * 4 + [_P] * 3 + [_P],
+    "tcar_eval_select": [_P] * 4 + [_I] * 4 + [_P],
+    "tcar_eval_rescore": [_P, _P, _I, _LL] + [_P] * 9 + [_I, _I] + [_P] * 3 + [_P],
     "tcar_eval_topk_widen": [_P] * 13 + [_I] * 4 + [_P, _P],
     "tcar_eval_topk_widen_ws_bytes": [_I],
     "tcar_catalog_stats": [_P, _P, _I, _I, _P, _P],
     "tcar_topk_merge": [_P] * 4 + [_I, _I, _P],
     "tcar_eval_merge": [_P, _LL, _P, _P, _P, _P, _I, _I, _P],
+    "tcar_eval_ce_combine": [_P, _P, _LL, _P, _I, _I, _P],
+    "tcar_eval_merge_flagged": [_P, _LL, _P, _P, _P, _P, _I, _I, _P],
 }
 
 _lib = None

@@ -177,6 +177,47 @@ __device__ __forceinline__ float score_error_bound(const float* s_aic, const flo
 constexpr int TILE_CH = 128 / CH;          // 16 chunks per 128-item tile
 constexpr int NCC = NCH * TILE_CH;         // 512 candidate chunks after the tile-level selection
 
+constexpr int NSEL = TCAR_EVAL_NSEL;       // 33 entries per (query, shard) list: 32 candidate chunks + 1 bound carrier
+
+// The two halves of the kernel can run on different GPUs (catalog-sharded evaluation, Seq2SeqAttNN.eval_round):
+//   select-only  (out_vals != NULL): the item range's 32 best chunks of every query as (bf16-GEMM chunk maximum, GLOBAL
+//                chunk id) + a 33rd entry whose value bounds every chunk NOT listed (33rd chunk of the selected tiles /
+//                best unselected tile) -- no re-scoring;
+//   re-score     (in_vals != NULL): `in_lists` such lists per query (one per item range, `in_stride` words apart) are
+//                merged: the 32 best entries overall are re-scored exactly from the (replicated) fp32 tables; the 33rd
+//                best value bounds everything that is not (a range's 33rd entry can never be among the 32 best overall:
+//                its own 32 predecessors would all be, too).
+struct SelIO {
+    float* out_vals;
+    int32_t* out_ids;
+    int chunk_base;
+    const float* in_vals;
+    const int32_t* in_ids;
+    int in_lists;
+    long long in_stride;
+};
+
+// bitonic sort of the NCC (value, chunk id) candidates by (value desc, id asc); ends with a barrier
+__device__ __forceinline__ void sort_chunk_candidates(float* s_cv, int* s_ci) {
+    const int tid = threadIdx.x;
+    for (int k = 2; k <= NCC; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            __syncthreads();
+            for (int i = tid; i < NCC; i += 256) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const float sa = s_cv[i], sb = s_cv[ixj];
+                    const int ia = s_ci[i], ib = s_ci[ixj];
+                    const bool up = (i & k) == 0;
+                    const bool swap = up ? before(sb, ib, sa, ia) : before(sa, ia, sb, ib);
+                    if (swap) { s_cv[i] = sb; s_cv[ixj] = sa; s_ci[i] = ib; s_ci[ixj] = ia; }
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
 // one CTA (256 threads) per query.  Two-level selection: the 32 best 128-item tiles by tile max (every one of the 32
 // best chunks lives in one of them: the 32 largest tile maxima are 32 distinct chunk values, so the 32nd largest chunk
 // is >= the 32nd largest tile max), then the 32 best of their 512 chunks, then the exact fp32 re-scoring.
@@ -185,7 +226,8 @@ eval_topk_kernel(const float* __restrict__ chunkmax, const float* __restrict__ t
                  const float* __restrict__ Tq, const float* __restrict__ item, const float* __restrict__ content,
                  const int32_t* __restrict__ mwdhm, const int32_t* __restrict__ label, int32_t* __restrict__ top_ids,
                  float* __restrict__ top_scores, int32_t* __restrict__ n_greater, int N, int n_pad, int item_offset,
-                 const float* __restrict__ cat_stats, int32_t* __restrict__ uncertain, float* __restrict__ tau) {
+                 const float* __restrict__ cat_stats, int32_t* __restrict__ uncertain, float* __restrict__ tau,
+                 const __grid_constant__ SelIO io) {
     PDL_ENTER();
     __shared__ float s_aic[XW], s_tq[NB + 1];
     __shared__ float s_red[32];
@@ -204,19 +246,40 @@ eval_topk_kernel(const float* __restrict__ chunkmax, const float* __restrict__ t
     const int ntiles = (N + 127) / 128;
     const float* cm = chunkmax + (size_t)b * (n_pad / CH);
     const float* tm = tilemax + (size_t)b * (n_pad / 128);
-    for (int c = tid; c < XW; c += 256) s_aic[c] = a_ic[(size_t)b * XW + c];
-    for (int c = tid; c < NB; c += 256) s_tq[c] = Tq[(size_t)b * NB + c];
+    const bool sel_only = io.out_vals != nullptr, from_lists = io.in_vals != nullptr;
+    if (!sel_only) {
+        for (int c = tid; c < XW; c += 256) s_aic[c] = a_ic[(size_t)b * XW + c];
+        for (int c = tid; c < NB; c += 256) s_tq[c] = Tq[(size_t)b * NB + c];
+    }
     for (int i = tid; i < NCH; i += 256) s_sel[i] = -1;
     __syncthreads();
 
-    if (nchunks > NCH) {
+    if (from_lists) {
+        // ---- the item ranges' candidate lists (global chunk ids): the 32 best overall, the 33rd as the bound
+        const int n_in = io.in_lists * NSEL;
+        for (int i = tid; i < NCC; i += 256) {
+            float v = -INFINITY;
+            int id = 0x7fffffff;
+            if (i < n_in) {
+                const size_t at = (size_t)(i / NSEL) * io.in_stride + (size_t)b * NSEL + (i % NSEL);
+                const int cid = io.in_ids[at];
+                if (cid >= 0) { v = io.in_vals[at]; id = cid; }
+                else if (cid == -2) { v = io.in_vals[at]; }       // bound carrier without a chunk
+            }
+            s_cv[i] = v;
+            s_ci[i] = id;
+        }
+        sort_chunk_candidates(s_cv, s_ci);
+        unsel_max = s_cv[NCH];
+        if (tid < NCH) s_sel[tid] = s_ci[tid] == 0x7fffffff ? -1 : s_ci[tid];
+    } else if (nchunks > NCH) {
         // ---- level 1: tiles
         if (ntiles <= NCH) {
             for (int i = tid; i < ntiles; i += 256) s_sel[i] = i;
             __syncthreads();
         } else {
             select_top(tm, ntiles, s_sel, s_hist, s_warp, s_misc);
-            if (cat_stats) {
+            if (cat_stats || sel_only) {
                 // best tile NOT selected: bitmap of the selected ones, then a max over the rest
                 for (int i = tid; i < (ntiles + 31) / 32; i += 256) s_tilebits[i] = 0u;
                 __syncthreads();
@@ -241,28 +304,32 @@ eval_topk_kernel(const float* __restrict__ chunkmax, const float* __restrict__ t
             s_cv[i] = ok ? cm[chunk] : -INFINITY;
             s_ci[i] = ok ? chunk : 0x7fffffff;
         }
-        for (int k = 2; k <= NCC; k <<= 1) {
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                __syncthreads();
-                for (int i = tid; i < NCC; i += 256) {
-                    const int ixj = i ^ j;
-                    if (ixj > i) {
-                        const float sa = s_cv[i], sb = s_cv[ixj];
-                        const int ia = s_ci[i], ib = s_ci[ixj];
-                        const bool up = (i & k) == 0;
-                        const bool swap = up ? before(sb, ib, sa, ia) : before(sa, ia, sb, ib);
-                        if (swap) { s_cv[i] = sb; s_cv[ixj] = sa; s_ci[i] = ib; s_ci[ixj] = ia; }
-                    }
-                }
-            }
-        }
-        __syncthreads();
+        sort_chunk_candidates(s_cv, s_ci);
         unsel_max = fmaxf(unsel_max, s_cv[NCH]);        // best chunk of the selected tiles that is NOT re-scored
         if (tid < NCH) s_sel[tid] = s_ci[tid] == 0x7fffffff ? -1 : s_ci[tid];
     } else {
+        for (int i = tid; i < NCC; i += 256) {           // tiny item range: every chunk is a candidate
+            s_cv[i] = i < nchunks ? cm[i] : -INFINITY;
+            s_ci[i] = i < nchunks ? i : 0x7fffffff;
+        }
         for (int i = tid; i < nchunks; i += 256) s_sel[i] = i;
     }
     __syncthreads();
+    if (sel_only) {
+        // 32 candidates (value, GLOBAL chunk id; -1 = none) + the bound on everything not listed (id -2)
+        if (tid < NSEL) {
+            const size_t at = (size_t)b * NSEL + tid;
+            if (tid < NCH) {
+                const bool ok = s_ci[tid] != 0x7fffffff;
+                io.out_vals[at] = ok ? s_cv[tid] : -INFINITY;
+                io.out_ids[at] = ok ? s_ci[tid] + io.chunk_base : -1;
+            } else {
+                io.out_vals[at] = nchunks > NCH ? unsel_max : -INFINITY;
+                io.out_ids[at] = -2;
+            }
+        }
+        return;
+    }
 
     // exact re-scoring: warp w handles candidates w*32 .. w*32+31
     const int lab = label[b];
@@ -325,7 +392,7 @@ eval_topk_kernel(const float* __restrict__ chunkmax, const float* __restrict__ t
         if (tid == 0) {
             const float bound = s20 - eps;
             // s20 == -inf: fewer than 20 candidates re-scored, i.e. every chunk of a tiny catalog was taken
-            uncertain[b] = (nchunks > NCH && !(unsel_max < bound)) ? 1 : 0;
+            uncertain[b] = ((nchunks > NCH || from_lists) && unsel_max > -INFINITY && !(unsel_max < bound)) ? 1 : 0;
             tau[b] = bound;
         }
     }
@@ -523,7 +590,7 @@ topk_merge_kernel(const int32_t* __restrict__ ids, const float* __restrict__ sco
     if (ngt && !sumexp && lane == 0) {
         // partial rank counts of the widening pass ([G][B], like the lists)
         int cnt = 0;
-        for (int g = 0; g < G; ++g) cnt += ngt[(size_t)g * B + b];
+        for (int g = 0; g < G; ++g) cnt += ngt[gstride ? (size_t)g * gstride + b : (size_t)g * B + b];
         out_ngt[b] = cnt;
     }
     if (ngt && sumexp && lane == 0) {
@@ -597,7 +664,44 @@ extern "C" int tcar_eval_topk_certified(const float* chunkmax, const float* tile
     if (B < 1 || B > TCAR_QROWS || N < 1 || n_pad < N || !tilemax) return TCAR_ERR_ARG;
     if (cat_stats && (!uncertain || !tau || (N + 127) / 128 > TCAR_MAX_EVAL_TILES)) return TCAR_ERR_ARG;
     launch_pdl(eval_topk_kernel, dim3(B), dim3(256), 0, STREAM, chunkmax, tilemax, a_ic, Tq, item, content, mwdhm,
-               label, top_ids, top_scores, n_greater, N, n_pad, item_offset, cat_stats, uncertain, tau);
+               label, top_ids, top_scores, n_greater, N, n_pad, item_offset, cat_stats, uncertain, tau, SelIO{});
+    return (int)cudaGetLastError();
+}
+
+extern "C" int tcar_eval_select(const float* chunkmax, const float* tilemax, float* sel_vals, int32_t* sel_ids, int B,
+                                int N, int n_pad, int item_offset, void* stream) {
+    if (B < 1 || B > TCAR_QROWS || N < 1 || n_pad < N || !chunkmax || !tilemax || !sel_vals || !sel_ids ||
+        item_offset % CH || (N + 127) / 128 > TCAR_MAX_EVAL_TILES)
+        return TCAR_ERR_ARG;
+    SelIO io = {};
+    io.out_vals = sel_vals;
+    io.out_ids = sel_ids;
+    io.chunk_base = item_offset / CH;
+    launch_pdl(eval_topk_kernel, dim3(B), dim3(256), 0, STREAM, chunkmax, tilemax, static_cast<const float*>(nullptr),
+               static_cast<const float*>(nullptr), static_cast<const float*>(nullptr),
+               static_cast<const float*>(nullptr), static_cast<const int32_t*>(nullptr),
+               static_cast<const int32_t*>(nullptr), static_cast<int32_t*>(nullptr), static_cast<float*>(nullptr),
+               static_cast<int32_t*>(nullptr), N, n_pad, item_offset, static_cast<const float*>(nullptr),
+               static_cast<int32_t*>(nullptr), static_cast<float*>(nullptr), io);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int tcar_eval_rescore(const float* sel_vals, const int32_t* sel_ids, int lists, long long list_stride,
+                                 const float* a_ic, const float* Tq, const float* item, const float* content,
+                                 const int32_t* mwdhm, const int32_t* label, int32_t* top_ids, float* top_scores,
+                                 int32_t* n_greater, int B, int N_total, const float* cat_stats, int32_t* uncertain,
+                                 float* tau, void* stream) {
+    if (B < 1 || B > TCAR_QROWS || N_total < 1 || !sel_vals || !sel_ids || lists < 1 || lists * NSEL > NCC ||
+        list_stride < (long long)B * NSEL || !cat_stats || !uncertain || !tau)
+        return TCAR_ERR_ARG;
+    SelIO io = {};
+    io.in_vals = sel_vals;
+    io.in_ids = sel_ids;
+    io.in_lists = lists;
+    io.in_stride = list_stride;
+    launch_pdl(eval_topk_kernel, dim3(B), dim3(256), 0, STREAM, static_cast<const float*>(nullptr),
+               static_cast<const float*>(nullptr), a_ic, Tq, item, content, mwdhm, label, top_ids, top_scores,
+               n_greater, N_total, 0, 0, cat_stats, uncertain, tau, io);
     return (int)cudaGetLastError();
 }
 
@@ -643,6 +747,47 @@ extern "C" int tcar_topk_merge(const int32_t* ids, const float* scores, int32_t*
                0LL, static_cast<const int32_t*>(nullptr), static_cast<const float*>(nullptr),
                static_cast<const float*>(nullptr), static_cast<int32_t*>(nullptr), static_cast<float*>(nullptr),
                static_cast<const int32_t*>(nullptr));
+    return (int)cudaGetLastError();
+}
+
+// cross loss of B queries from G item ranges' softmax partial sums, each relative to its own exponent shift
+__global__ void __launch_bounds__(256)
+ce_combine_kernel(const float* __restrict__ sumexp, const float* __restrict__ rowmax, long long gstride,
+                  float* __restrict__ out_ce, int G, int B) {
+    PDL_ENTER();
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float M = 0.f;
+    for (int g = 0; g < G; ++g) {
+        const float r = rowmax[g * gstride + b];
+        M = fmaxf(M, r > TCAR_EXP_LIMIT2 ? r : 0.f);
+    }
+    float tot = 0.f;
+    for (int g = 0; g < G; ++g) {
+        const float r = rowmax[g * gstride + b];
+        tot += sumexp[g * gstride + b] * exp2f((r > TCAR_EXP_LIMIT2 ? r : 0.f) - M);
+    }
+    out_ce[b] = fmaf(M, 0.6931471805599453f, logf(tot));
+}
+
+extern "C" int tcar_eval_ce_combine(const float* sumexp, const float* rowmax, long long gstride, float* out_ce, int G,
+                                    int B, void* stream) {
+    if (G < 1 || G > TCAR_MAX_PEERS || B < 1 || !sumexp || !rowmax || !out_ce) return TCAR_ERR_ARG;
+    launch_pdl(ce_combine_kernel, dim3((B + 255) / 256), dim3(256), 0, STREAM, sumexp, rowmax, gstride, out_ce, G, B);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int tcar_eval_merge_flagged(const void* blocks, long long block_words, const int32_t* only_if,
+                                       int32_t* out_ids, float* out_scores, int32_t* out_ngt, int G, int B,
+                                       void* stream) {
+    if (G < 1 || G > TCAR_MAX_PEERS || B < 1 || B > TCAR_QROWS || block_words < TCAR_EVAL_BLOCK_WORDS || !blocks ||
+        !only_if)
+        return TCAR_ERR_ARG;
+    const float* f = static_cast<const float*>(blocks);
+    const int32_t* i = static_cast<const int32_t*>(blocks);
+    launch_pdl(topk_merge_kernel, dim3((B + 7) / 8), dim3(256), 0, STREAM, i + TCAR_EVAL_OFF_IDS, f + TCAR_EVAL_OFF_SCORES,
+               out_ids, out_scores, G, B, block_words, i + TCAR_EVAL_OFF_NGT, static_cast<const float*>(nullptr),
+               static_cast<const float*>(nullptr), out_ngt, static_cast<float*>(nullptr), only_if);
     return (int)cudaGetLastError();
 }
 

@@ -183,6 +183,7 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         # outscores the label by more than 55 nats are re-run shifted by their maximum (two empty launches otherwise)
         self.softmax_guard = bool(args.get("softmax_guard", os.environ.get("TCAR_SOFTMAX_GUARD", "1") != "0"))
         self.eval_certify = os.environ.get("TCAR_EVAL_CERTIFY", "1") != "0"
+        self.eval_two_stage = os.environ.get("TCAR_EVAL_TWO_STAGE", "1") != "0"
         self.train_parallel = "dp"
         self._item_table_synced = True
         mode = args.get("train_parallel") or "dp"
@@ -815,9 +816,100 @@ class Seq2SeqAttNN(CatalogShardedTraining):
             self.Q, self.c_ref, self.a_ic, self.Tq = keep
         mine[4][:bt.B].copy_(bt.label)
 
+    # Two-stage round (default, `eval_two_stage`): an item range only SELECTS its 32 best chunks per query (bf16 chunk
+    # maxima, no re-scoring); the query's owner merges the ranges' lists and re-scores the 32 best chunks overall from
+    # the replicated fp32 tables -- the exact re-scoring (256 candidate rows per query, the bandwidth-heavy part) is done
+    # once per query instead of once per (query, item range).  Queries the owner cannot certify are widened by every
+    # range (tcar_eval_topk_widen with the owner's bound) and merged: still the exact top-20.
+    def _group_ws(self, n_pad, g):
+        key = (n_pad, "eval-group", g)
+        if key not in self._score_ws:
+            tiles = nv.lib().tcar_score_fwd_tiles(n_pad)
+            f = lambda *s_: torch.zeros(*s_, device=self.dev)
+            self._score_ws[key] = {"part": f(tiles, QROWS), "pmax": f(tiles, QROWS), "tiles": tiles,
+                                   "cmax": f(QROWS, n_pad // nv.CHUNK), "tmax": f(QROWS, n_pad // 128)}
+        return self._score_ws[key]
+
+    def _round_select(self, eq_all, counts, shard, sel_send):
+        """Stage 1 on an item range: every rank's queries -> chunk / tile maxima (kept per group for a later widening),
+        guarded softmax partial sums and the candidate lists, written into sel_send[g] (layout nv.SEL_OFF_*)."""
+        p = nv.ptr
+        lo, hi, iext = shard
+        n_loc, n_pad = hi - lo, iext.shape[0]
+        for g, Bg in enumerate(counts):
+            if Bg == 0:
+                continue
+            blk = sel_send[g]
+            bi = blk.view(torch.int32)
+            if n_loc <= 0:                                   # empty item range: no candidates, no softmax mass
+                bi[nv.SEL_OFF_IDS: nv.SEL_OFF_IDS + Bg * nv.EVAL_NSEL].fill_(-1)
+                blk[: Bg * nv.EVAL_NSEL].fill_(float("-inf"))
+                blk[nv.SEL_OFF_SUMEXP:].zero_()
+                continue
+            ws = self._group_ws(n_pad, g)
+            Qg, cg, _, _, _ = self._eq_views(eq_all[g])
+            self._score_and_sum(ws, iext, None, p(ws["cmax"]), p(ws["tmax"]), Bg, n_loc, n_pad, 1, q=Qg, c=cg,
+                                sumexp=blk[nv.SEL_OFF_SUMEXP:], ce=self._ce_scratch, rowmax=blk[nv.SEL_OFF_ROWMAX:])
+            nv.counted_call("tcar_eval_select", 1, p(ws["cmax"]), p(ws["tmax"]), p(blk), p(bi[nv.SEL_OFF_IDS:]), Bg,
+                            n_loc, n_pad, lo)
+
+    def _round_rescore(self, sel_recv, R, eq_block, B, flags):
+        """Stage 2 at the queries' owner: merge the R candidate lists, exact re-scoring, top-20 / rank counts into
+        m_ids / m_scores / m_ngt, cross loss into m_ce, uncertified queries flagged in `flags` (uncertain | tau)."""
+        p = nv.ptr
+        ps = self.ps
+        self._ensure_cat_stats()
+        _, _, a_ic, Tq, lab = self._eq_views(eq_block)
+        si = sel_recv.view(torch.int32)
+        fi = flags.view(torch.int32)
+        nv.counted_call("tcar_eval_rescore", 1, p(sel_recv), p(si[:, nv.SEL_OFF_IDS:]), R, sel_recv.stride(0), p(a_ic),
+                        p(Tq), p(ps.item), p(ps.content), p(ps.mwdhm), p(lab), p(self.m_ids), p(self.m_scores),
+                        p(self.m_ngt), B, ps.N, p(self.cat_stats), p(fi[:QROWS]), p(flags[QROWS:]))
+        nv.counted_call("tcar_eval_ce_combine", 1, p(sel_recv[:, nv.SEL_OFF_SUMEXP:]), p(sel_recv[:, nv.SEL_OFF_ROWMAX:]),
+                        sel_recv.stride(0), p(self.m_ce), R, B)
+
+    def _round_widen(self, eq_all, counts, shard, flag_all, send):
+        """Stage 3 on an item range: for the flagged queries of every rank, ALL local chunks at or above the owner's
+        bound re-scored exactly -> partial top-20 lists and rank counts in send[g] (result-block planes)."""
+        p = nv.ptr
+        ps = self.ps
+        lo, hi, iext = shard
+        n_loc, n_pad = hi - lo, iext.shape[0]
+        for g, Bg in enumerate(counts):
+            if Bg == 0:
+                continue
+            blk = send[g]
+            bi = blk.view(torch.int32)
+            if n_loc <= 0:
+                bi[nv.EVAL_OFF_IDS: nv.EVAL_OFF_IDS + Bg * TOPK].fill_(-1)
+                blk[nv.EVAL_OFF_SCORES: nv.EVAL_OFF_SCORES + Bg * TOPK].fill_(float("-inf"))
+                blk[nv.EVAL_OFF_NGT: nv.EVAL_OFF_NGT + QROWS].zero_()
+                continue
+            ws = self._group_ws(n_pad, g)
+            _, _, ag, Tg, lg = self._eq_views(eq_all[g])
+            fl = flag_all[g]
+            nv.counted_call("tcar_eval_topk_widen", 2, p(ws["cmax"]), p(ws["tmax"]), p(ag), p(Tg), p(ps.item),
+                            p(ps.content), p(ps.mwdhm), p(lg), p(fl.view(torch.int32)[:QROWS]), p(fl[QROWS:]),
+                            p(bi[nv.EVAL_OFF_IDS:]), p(blk[nv.EVAL_OFF_SCORES:]), p(bi[nv.EVAL_OFF_NGT:]), Bg, n_loc,
+                            n_pad, lo, p(self.widen_ws))
+
+    def _round_finish(self, recv, R, B, flags):
+        nv.counted_call("tcar_eval_merge_flagged", 1, nv.ptr(recv), recv.stride(0),
+                        nv.ptr(flags.view(torch.int32)[:QROWS]), nv.ptr(self.m_ids), nv.ptr(self.m_scores),
+                        nv.ptr(self.m_ngt), R, B)
+        return self.m_ids[:B], self.m_ngt[:B], self.m_ce[:B]
+
+    def _alloc_two_stage(self, R):
+        if getattr(self, "_sel_send", None) is not None and self._sel_send.shape[0] == R:
+            return
+        f = lambda *s_: torch.zeros(*s_, device=self.dev)
+        self._sel_send, self._flag = f(R, nv.SEL_BLOCK_WORDS), f(2 * QROWS)
+        self._sel_recv = f(R, nv.SEL_BLOCK_WORDS) if R > 1 else self._sel_send
+        self._flag_all = f(R, 2 * QROWS) if R > 1 else self._flag.view(1, -1)
+
     def _round_score(self, eq_all, counts, shard, send):
-        """Step 3 of eval_round: every rank's queries (exchange blocks eq_all [R, EQ_BYTES]) against the item range
-        `shard` = (lo, hi, iext rows): scoring GEMM + guarded softmax sums + certified top-20 -> result blocks send[g]."""
+        """Step 3 of the one-stage eval_round: every rank's queries (exchange blocks eq_all [R, EQ_BYTES]) against the
+        item range `shard` = (lo, hi, iext rows): scoring GEMM + guarded softmax sums + certified top-20 -> send[g]."""
         p = nv.ptr
         lo, hi, iext = shard
         n_loc, n_pad = hi - lo, iext.shape[0]
@@ -839,22 +931,29 @@ class Seq2SeqAttNN(CatalogShardedTraining):
                                 sumexp=blk[nv.EVAL_OFF_SUMEXP:], ce=self._ce_scratch, rowmax=blk[nv.EVAL_OFF_ROWMAX:])
             self._topk(ws, ag, Tg, lg, blk, Bg, n_loc, n_pad, lo)
 
-    def eval_round(self, bt, counts, shard=None):
+    def eval_round(self, bt, counts, shard=None, two_stage=None):
         """Catalog-sharded evaluation that SCALES: every rank brings its OWN batch of <= 512 queries (bt; B may be 0 in
         the last round), so one round evaluates sum(counts) queries.  counts[g] = queries of rank g (the same list on
-        every rank).  Per round:
+        every rank).  Per round (two-stage form, the default):
           1. session forward of the local queries -> [Q | label scores | a_ic | Tq | labels] (1.97 MB, written in place)
-          2. ONE all-gather of those blocks: every rank now holds every rank's queries
-          3. for every rank g: scoring GEMM of g's queries against the LOCAL item range (+ softmax partial sums with
-             the overflow guard), certified local top-20 and rank counts -> result block g
-          4. ONE all-to-all: rank g receives the blocks about ITS queries from every item range
-          5. tcar_eval_merge: global top-20 (score desc, id asc), summed rank counts, cross loss
-        Same results as eval_step(bt) on one GPU, bit for bit on the ids (model_combine.py:283-306, util.py:8-18)."""
+          2. all-gather of those blocks: every rank now holds every rank's queries
+          3. for every rank g: scoring GEMM of g's queries against the LOCAL item range, guarded softmax partial sums,
+             and the range's 32 best chunks per query (tcar_eval_select: no re-scoring) -> candidate block g
+          4. all-to-all: rank g receives the candidate blocks about ITS queries from every item range
+          5. the owner merges the lists and re-scores the 32 best chunks overall exactly (tcar_eval_rescore) -> top-20,
+             rank counts, cross loss; queries it cannot certify are flagged with their bound
+          6. all-gather of the flags; every range widens the flagged queries (tcar_eval_topk_widen); all-to-all of the
+             partial lists; the owner merges them (tcar_eval_merge_flagged)
+        two_stage=False: the one-stage form (every range computes its certified local top-20; one all-gather + one
+        all-to-all).  Same results as eval_step(bt) on one GPU either way, bit for bit on the ids
+        (model_combine.py:283-306, util.py:8-18)."""
         import torch.distributed as dist
         if not self._item_table_synced:
             self.sync_item_table()
         on = parallel.is_distributed(self.world)
         R, me = (self.world, self.rank) if on else (1, 0)
+        two_stage = self.eval_two_stage if two_stage is None else two_stage
+        two_stage = two_stage and R * nv.EVAL_NSEL <= 512
         counts = [int(c) for c in counts]
         B = bt.B
         if len(counts) != R or counts[me] != B:
@@ -866,34 +965,91 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         self._round_forward(bt, self._eq)
         if on:
             dist.all_gather_into_tensor(self._eq_all.view(-1), self._eq)
-        self._round_score(self._eq_all, counts, shard, self._ev_send)
+        if not two_stage:
+            self._round_score(self._eq_all, counts, shard, self._ev_send)
+            if on:
+                dist.all_to_all_single(self._ev_recv.view(-1), self._ev_send.view(-1))
+            if B == 0:
+                return self.m_ids[:0], self.m_ngt[:0], self.m_ce[:0]
+            return self._merge_blocks(self._ev_recv, R, B)
+        self._alloc_two_stage(R)
+        self._round_select(self._eq_all, counts, shard, self._sel_send)
+        if on:
+            dist.all_to_all_single(self._sel_recv.view(-1), self._sel_send.view(-1))
+        if B > 0:
+            self._round_rescore(self._sel_recv, R, self._eq, B, self._flag)
+        else:
+            self._flag.zero_()
+        if on:
+            dist.all_gather_into_tensor(self._flag_all.view(-1), self._flag)
+        self._round_widen(self._eq_all, counts, shard, self._flag_all, self._ev_send)
         if on:
             dist.all_to_all_single(self._ev_recv.view(-1), self._ev_send.view(-1))
         if B == 0:
             return self.m_ids[:0], self.m_ngt[:0], self.m_ce[:0]
-        return self._merge_blocks(self._ev_recv, R, B)
+        return self._round_finish(self._ev_recv, R, B, self._flag)
 
-    def eval_round_virtual(self, bts):
+    def eval_round_virtual(self, bts, two_stage=None):
         """Single-GPU emulation of eval_round over V = len(bts) ranks (tests): the same kernels with the same shard
-        offsets and block layouts, the two collectives replaced by copies.  Returns the per-rank results."""
+        offsets and block layouts, the collectives replaced by copies.  Returns the per-rank results."""
         V = len(bts)
         counts = [b.B for b in bts]
+        two_stage = self.eval_two_stage if two_stage is None else two_stage
+        two_stage = two_stage and V * nv.EVAL_NSEL <= 512
         self._alloc_eval_round(1)
         eq_all = torch.zeros(V, self.EQ_BYTES, device=self.dev, dtype=torch.uint8)
         for v, bt in enumerate(bts):                      # step 1 of every rank + "all-gather"
             self._round_forward(bt, eq_all[v])
-        sends = []
-        for v, (lo, hi) in enumerate(self.shard_bounds(V)):      # step 3 of every rank
-            send = torch.zeros(V, nv.EVAL_BLOCK_WORDS, device=self.dev)
-            self._round_score(eq_all, counts, (lo, hi, self.iext_shard(lo, hi)), send)
-            sends.append(send)
+        shards = [(lo, hi, self.iext_shard(lo, hi)) for lo, hi in self.shard_bounds(V)]
+        f = lambda *s_: torch.zeros(*s_, device=self.dev)
         outs = []
-        for v in range(V):                                # "all-to-all" + merge of every rank
+        if not two_stage:
+            sends = []
+            for v in range(V):                            # step 3 of every rank
+                send = f(V, nv.EVAL_BLOCK_WORDS)
+                self._round_score(eq_all, counts, shards[v], send)
+                sends.append(send)
+            for v in range(V):                            # "all-to-all" + merge of every rank
+                if counts[v] == 0:
+                    outs.append(None)
+                    continue
+                recv = torch.stack([sends[src][v] for src in range(V)])
+                outs.append(tuple(x.clone() for x in self._merge_blocks(recv, V, counts[v])))
+            return outs
+        # two-stage: the chunk / tile maxima of (range v, group g) must survive until the widening -> one workspace
+        # set per virtual range
+        saved_ws = self._score_ws
+        ws_of = [dict() for _ in range(V)]
+        sel = []
+        for v in range(V):
+            self._score_ws = ws_of[v]
+            blk = f(V, nv.SEL_BLOCK_WORDS)
+            self._round_select(eq_all, counts, shards[v], blk)
+            sel.append(blk)
+        flags, firsts = f(V, 2 * QROWS), []
+        for v in range(V):
+            if counts[v] == 0:
+                firsts.append(None)
+                continue
+            recv = torch.stack([sel[src][v] for src in range(V)])
+            self._round_rescore(recv, V, eq_all[v], counts[v], flags[v])
+            firsts.append((self.m_ids.clone(), self.m_scores.clone(), self.m_ngt.clone(), self.m_ce.clone()))
+        wid = []
+        for v in range(V):
+            self._score_ws = ws_of[v]
+            send = f(V, nv.EVAL_BLOCK_WORDS)
+            self._round_widen(eq_all, counts, shards[v], flags, send)
+            wid.append(send)
+        self._score_ws = saved_ws
+        for v in range(V):
             if counts[v] == 0:
                 outs.append(None)
                 continue
-            recv = torch.stack([sends[src][v] for src in range(V)])
-            outs.append(tuple(x.clone() for x in self._merge_blocks(recv, V, counts[v])))
+            ids, sc, ngt, ce = firsts[v]
+            self.m_ids.copy_(ids); self.m_scores.copy_(sc); self.m_ngt.copy_(ngt); self.m_ce.copy_(ce)
+            recv = torch.stack([wid[src][v] for src in range(V)])
+            outs.append(tuple(x.clone() for x in self._round_finish(recv, V, counts[v], flags[v])))
+        self.last_round_flagged = int(flags.view(torch.int32)[:, :QROWS].sum().item())
         return outs
 
     def shard_bounds(self, G):
