@@ -250,3 +250,66 @@ def test_print_data_dump_parses_with_the_reference_evaluation_script(tmp_path, m
         pred_ = [] if pred_split[0] == "" else [int(x) for x in pred_split]                    # :20-23
         got.append((in_, out_, pred_))
     assert got == [(batch_in[0], 41, batch_pred[0]), (batch_in[1], 0, []), (batch_in[0], 41, batch_pred[0])]
+
+
+def test_restrict_to_rank_partitions_every_global_batch():
+    """Per-rank batches of the multi-GPU train loop (Seq2SeqAttNN.train, dist_batch='per_rank'): samplers built alike
+    on every rank (same `random` seed) and restricted to their rank must partition every global batch -- same order,
+    same session length, shares of at most batch_size sessions -- and the shares' packed planes must be the rows of
+    the global batch's."""
+    import random
+    from tcar_b200 import parallel, synth
+    from tcar_b200.sampler import Sampler
+    N, world, B = 400, 4, 16
+    ld, sd, td, idict, impr = synth.make_sessions(N, 700, seed=8)
+    random.seed(5)
+    np.random.seed(5)
+    ref = Sampler({k: list(v) for k, v in ld.items()}, sd, td, impr, idict, 3, batch_size=B * world, verbose=False)
+    global_ids = [list(b) for b in ref.session_id_batches]
+    parts = []
+    for r in range(world):
+        random.seed(5)
+        s = Sampler({k: list(v) for k, v in ld.items()}, sd, td, impr, idict, 3, batch_size=B * world, verbose=False)
+        s.restrict_to_rank(r, world)
+        assert s.global_sizes == [len(b) for b in global_ids]
+        parts.append(s)
+    for i, ids in enumerate(global_ids):
+        got = []
+        for r, s in enumerate(parts):
+            share = s.session_id_batches[i]
+            assert len(share) <= B
+            assert len(share) == parallel.catalog_counts(len(ids), world)[r]
+            got += share
+        assert got == ids
+    # packed shares: sequence plane and labels are slices of the global batch's
+    full = [ref.next_packed() for _ in range(3)]
+    for r, s in enumerate(parts):
+        for i in range(3):
+            packed, Bl, T, Nn = s.next_packed()
+            gp, Bg, Tg, _ = full[i]
+            lo, hi = parallel.shard_sessions(Bg, r, world)
+            assert (Bl, T) == (hi - lo, Tg)
+            np.testing.assert_array_equal(packed[: Bl * T].reshape(Bl, T), gp[: Bg * Tg].reshape(Bg, Tg)[lo:hi])
+            np.testing.assert_array_equal(packed[7 * Bl * T + 2 * Bl: 7 * Bl * T + 3 * Bl],
+                                          gp[7 * Bg * Tg + 2 * Bg: 7 * Bg * Tg + 3 * Bg][lo:hi])
+
+
+def test_restrict_to_rank_keeps_the_global_random_stream_in_lockstep():
+    """Impression negatives of a restricted sampler use a private random.Random: the global `random` stream -- which
+    shuffles the next epoch's batches and must stay identical on all ranks -- is not consumed by sampling."""
+    import random
+    from tcar_b200 import synth
+    from tcar_b200.sampler import Sampler
+    N = 300
+    ld, sd, td, idict, _ = synth.make_sessions(N, 200, seed=9)
+    impr = synth.make_impressions(N, 200, seed=9, mean_len=5.0, miss=0.3)
+    states = []
+    for r in range(2):
+        random.seed(11)
+        s = Sampler({k: list(v) for k, v in ld.items()}, sd, td, impr, idict, 4, batch_size=32,
+                    negative_mode="impression", verbose=False)
+        s.restrict_to_rank(r, 2)
+        while s.has_next():
+            s.next_packed()
+        states.append(random.getstate())
+    assert states[0] == states[1]
