@@ -412,8 +412,19 @@ int tcar_score_fwd_multi(const void* q_bf16, long long q_stride, const float* c_
                          const void* iext_bf16, void* e_out, long long e_stride, float* rowsum_part,
                          long long part_stride, float* rowmax_part, const float* rowmax, const int* n_rows, int groups,
                          int n_items, int n_pad, void* stream);
+/* The same in eval mode: chunk / tile maxima of group g at chunkmax + g * cm_stride / tilemax + g * tm_stride. */
+int tcar_score_fwd_multi_eval(const void* q_bf16, long long q_stride, const float* c_ref, long long c_stride,
+                              const void* iext_bf16, float* chunkmax, long long cm_stride, float* tilemax,
+                              long long tm_stride, float* rowsum_part, long long part_stride, float* rowmax_part,
+                              const float* rowmax, long long rowmax_stride, const int* n_rows, int groups, int n_items,
+                              int n_pad, void* stream);
 int tcar_rowmax_groups(const float* rowmax_part, long long part_stride, float* rowmax, int n_tiles, const int* n_rows,
                        int groups, void* stream);
+/* Pass 1 / 2 of tcar_ce_finish_guarded for several groups in one launch: group g's partials at + g * part_stride, its
+ * sumexp / rowmax vectors at + g * out_stride (catalog-sharded evaluation; the queries' owner combines the sums). */
+int tcar_ce_finish_groups(const float* rowsum_part, const float* rowmax_part, long long part_stride, float* sumexp,
+                          float* rowmax, long long out_stride, int n_tiles, const int* n_rows, int groups, int pass,
+                          void* stream);
 
 /* (6) evaluation (model_combine.py:283-306, util.py:8-18): select the 32 best 128-item tiles per query from tilemax,
  *     then the 32 best 8-item chunks among their 512 chunks from chunkmax (exactly the 32 best chunks overall, ties
@@ -452,12 +463,25 @@ int tcar_eval_rescore(const float* sel_vals, const int32_t* sel_ids, int lists, 
 /* Second stage: for every flagged query, re-scores ALL chunks whose maximum reaches tau[b] (any number of them -- in
  * the limit a full exact scan, so the work of one query is spread over TCAR_WIDEN_SPLITS CTAs and their partial lists
  * are merged by a second launch) and rewrites its top_ids / top_scores / n_greater; certified queries are untouched
- * (their CTAs return).  workspace: tcar_eval_topk_widen_ws_bytes(B) bytes. */
-long long tcar_eval_topk_widen_ws_bytes(int B);
+ * (their CTAs return).  workspace: tcar_eval_topk_widen_ws_bytes(1) bytes (x groups for the _groups form). */
+long long tcar_eval_topk_widen_ws_bytes(int groups);
 int tcar_eval_topk_widen(const float* chunkmax, const float* tilemax, const float* a_ic, const float* Tq,
                          const float* item, const float* content, const int32_t* mwdhm, const int32_t* label,
                          const int32_t* uncertain, const float* tau, int32_t* top_ids, float* top_scores,
                          int32_t* n_greater, int B, int N, int n_pad, int item_offset, void* workspace, void* stream);
+/* tcar_eval_select / tcar_eval_topk_widen for the session groups of a catalog-sharded evaluation round in ONE launch
+ * (pair) each: group g has n_rows[g] queries (HOST array); its chunk / tile maxima lie cm_stride / tm_stride floats
+ * apart; its a_ic / Tq / label planes q_stride 32-bit words apart (one exchange block per group); its (uncertain, tau)
+ * vectors flag_stride words apart; its outputs out_stride words apart. */
+int tcar_eval_select_groups(const float* chunkmax, long long cm_stride, const float* tilemax, long long tm_stride,
+                            float* sel_vals, int32_t* sel_ids, long long out_stride, const int* n_rows, int groups,
+                            int N, int n_pad, int item_offset, void* stream);
+int tcar_eval_topk_widen_groups(const float* chunkmax, long long cm_stride, const float* tilemax, long long tm_stride,
+                                const float* a_ic, const float* Tq, const int32_t* label, long long q_stride,
+                                const float* item, const float* content, const int32_t* mwdhm,
+                                const int32_t* uncertain, const float* tau, long long flag_stride, int32_t* top_ids,
+                                float* top_scores, int32_t* n_greater, long long out_stride, const int* n_rows,
+                                int groups, int N, int n_pad, int item_offset, void* workspace, void* stream);
 /* out2[0] = max ||[item | content] row||_2, out2[1] = max ||row - bf16(row)||_2 over table rows [row_lo, row_hi)
  * (row = item id + 1).  Needed again only after the item table changed. */
 int tcar_catalog_stats(const float* item, const float* content, int row_lo, int row_hi, float* out2, void* stream);

@@ -66,7 +66,9 @@ SIGNATURES = {
     "tcar_score_fwd_groups": [_P, _LL, _P, _LL, _P, _P, _LL, _P, _LL, _P, _I, _I, _I, _I, _P],
     "tcar_score_fwd_groups_guarded": [_P, _LL, _P, _LL, _P, _P, _LL, _P, _LL, _P, _P, _P, _I, _I, _I, _I, _P],
     "tcar_score_fwd_multi": [_P, _LL, _P, _LL, _P, _P, _LL, _P, _LL, _P, _P, _P, _I, _I, _I, _P],
+    "tcar_score_fwd_multi_eval": [_P, _LL, _P, _LL, _P, _P, _LL, _P, _LL, _P, _LL, _P, _P, _LL, _P, _I, _I, _I, _P],
     "tcar_rowmax_groups": [_P, _LL, _P, _I, _P, _I, _P],
+    "tcar_ce_finish_groups": [_P, _P, _LL, _P, _P, _LL, _I, _P, _I, _I, _P],
     "tcar_score_bwd_q_multi_part_elems": [_I],
     "tcar_score_bwd_q_multi": [_P, _LL, _P, _P, _P, _P, _I, _I, _P],
     "tcar_score_bwd_q_groups": [_P, _LL, _P, _P, _P, _LL, _P, _LL, _I, _P, _I, _I, _P],
@@ -86,6 +88,9 @@ SIGNATURES = {
     "tcar_eval_rescore": [_P, _P, _I, _LL] + [_P] * 9 + [_I, _I] + [_P] * 3 + [_P],
     "tcar_eval_topk_widen": [_P] * 13 + [_I] * 4 + [_P, _P],
     "tcar_eval_topk_widen_ws_bytes": [_I],
+    "tcar_eval_select_groups": [_P, _LL, _P, _LL, _P, _P, _LL, _P, _I, _I, _I, _I, _P],
+    "tcar_eval_topk_widen_groups": [_P, _LL, _P, _LL, _P, _P, _P, _LL, _P, _P, _P, _P, _P, _LL, _P, _P, _P, _LL, _P,
+                                    _I, _I, _I, _I, _P, _P],
     "tcar_catalog_stats": [_P, _P, _I, _I, _P, _P],
     "tcar_topk_merge": [_P] * 4 + [_I, _I, _P],
     "tcar_eval_merge": [_P, _LL, _P, _P, _P, _P, _I, _I, _P],

@@ -195,6 +195,11 @@ struct SelIO {
     const int32_t* in_ids;
     int in_lists;
     long long in_stride;
+    // select-only over several session groups in one launch (blockIdx.y = group): group g has gn[g] queries, its chunk /
+    // tile maxima lie cm_gs / tm_gs floats apart and its output lists out_gs words apart
+    int groups;
+    int gn[TCAR_MAX_PEERS];
+    long long cm_gs, tm_gs, out_gs;
 };
 
 // bitonic sort of the NCC (value, chunk id) candidates by (value desc, id asc); ends with a barrier
@@ -222,7 +227,7 @@ __device__ __forceinline__ void sort_chunk_candidates(float* s_cv, int* s_ci) {
 // best chunks lives in one of them: the 32 largest tile maxima are 32 distinct chunk values, so the 32nd largest chunk
 // is >= the 32nd largest tile max), then the 32 best of their 512 chunks, then the exact fp32 re-scoring.
 __global__ void __launch_bounds__(256)
-eval_topk_kernel(const float* __restrict__ chunkmax, const float* __restrict__ tilemax, const float* __restrict__ a_ic,
+eval_topk_kernel(const float* chunkmax, const float* tilemax, const float* __restrict__ a_ic,
                  const float* __restrict__ Tq, const float* __restrict__ item, const float* __restrict__ content,
                  const int32_t* __restrict__ mwdhm, const int32_t* __restrict__ label, int32_t* __restrict__ top_ids,
                  float* __restrict__ top_scores, int32_t* __restrict__ n_greater, int N, int n_pad, int item_offset,
@@ -244,9 +249,19 @@ eval_topk_kernel(const float* __restrict__ chunkmax, const float* __restrict__ t
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int nchunks = (N + CH - 1) / CH;
     const int ntiles = (N + 127) / 128;
+    const bool sel_only = io.out_vals != nullptr, from_lists = io.in_vals != nullptr;
+    float* sel_vals = io.out_vals;
+    int32_t* sel_ids = io.out_ids;
+    if (io.groups > 0) {
+        const int g = blockIdx.y;
+        if (b >= io.gn[g]) return;
+        chunkmax += (size_t)g * io.cm_gs;
+        tilemax += (size_t)g * io.tm_gs;
+        sel_vals += (size_t)g * io.out_gs;
+        sel_ids += (size_t)g * io.out_gs;
+    }
     const float* cm = chunkmax + (size_t)b * (n_pad / CH);
     const float* tm = tilemax + (size_t)b * (n_pad / 128);
-    const bool sel_only = io.out_vals != nullptr, from_lists = io.in_vals != nullptr;
     if (!sel_only) {
         for (int c = tid; c < XW; c += 256) s_aic[c] = a_ic[(size_t)b * XW + c];
         for (int c = tid; c < NB; c += 256) s_tq[c] = Tq[(size_t)b * NB + c];
@@ -321,11 +336,11 @@ eval_topk_kernel(const float* __restrict__ chunkmax, const float* __restrict__ t
             const size_t at = (size_t)b * NSEL + tid;
             if (tid < NCH) {
                 const bool ok = s_ci[tid] != 0x7fffffff;
-                io.out_vals[at] = ok ? s_cv[tid] : -INFINITY;
-                io.out_ids[at] = ok ? s_ci[tid] + io.chunk_base : -1;
+                sel_vals[at] = ok ? s_cv[tid] : -INFINITY;
+                sel_ids[at] = ok ? s_ci[tid] + io.chunk_base : -1;
             } else {
-                io.out_vals[at] = nchunks > NCH ? unsel_max : -INFINITY;
-                io.out_ids[at] = -2;
+                sel_vals[at] = nchunks > NCH ? unsel_max : -INFINITY;
+                sel_ids[at] = -2;
             }
         }
         return;
@@ -407,17 +422,44 @@ eval_topk_kernel(const float* __restrict__ chunkmax, const float* __restrict__ t
 // A certified query costs nothing (its CTAs return at once).
 constexpr int WQ_CAP = 4096;        // chunk queue: one sweep of 256 tiles x 16 chunks
 constexpr int WSPLIT = TCAR_WIDEN_SPLITS;
+constexpr size_t W_GROUP_WORDS = (size_t)TCAR_WIDEN_SPLITS * TCAR_QROWS * (2 * TCAR_TOPK + 1);   // workspace per group
+
+// several session groups in one launch of the widening pass / its merge (blockIdx.z resp. blockIdx.y = group)
+struct WidenGroups {
+    int groups;
+    int n[TCAR_MAX_PEERS];
+    long long cm_gs, tm_gs;      // floats between the groups' chunk / tile maxima
+    long long q_gs;              // words between the groups' a_ic / Tq / label planes (one exchange block per group)
+    long long flag_gs;           // words between the groups' uncertain / tau vectors
+    long long out_gs;            // words between the groups' result planes (top_ids / top_scores / n_greater)
+};
 constexpr int WIDEN_SLOTS = 37;     // x 16 splits = 592 CTAs = 4 per SM: one wave
 
 __global__ void __launch_bounds__(256)
-eval_topk_widen_kernel(const float* __restrict__ chunkmax, const float* __restrict__ tilemax,
-                       const float* __restrict__ a_ic, const float* __restrict__ Tq, const float* __restrict__ item,
-                       const float* __restrict__ content, const int32_t* __restrict__ mwdhm,
-                       const int32_t* __restrict__ label, const int32_t* __restrict__ uncertain,
-                       const float* __restrict__ tau, int32_t* __restrict__ top_ids, float* __restrict__ top_scores,
-                       int32_t* __restrict__ n_greater, int N, int n_pad, int item_offset, int B) {
+eval_topk_widen_kernel(const float* chunkmax, const float* tilemax, const float* a_ic, const float* Tq,
+                       const float* __restrict__ item, const float* __restrict__ content,
+                       const int32_t* __restrict__ mwdhm, const int32_t* label, const int32_t* uncertain,
+                       const float* tau, int32_t* wspace, int N, int n_pad, int item_offset, int B,
+                       const __grid_constant__ WidenGroups wg) {
     PDL_ENTER();
     const int split = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (wg.groups > 0) {
+        const int g = blockIdx.z;
+        B = wg.n[g];
+        if (B <= 0) return;
+        chunkmax += (size_t)g * wg.cm_gs;
+        tilemax += (size_t)g * wg.tm_gs;
+        a_ic += (size_t)g * wg.q_gs;
+        Tq += (size_t)g * wg.q_gs;
+        label += (size_t)g * wg.q_gs;
+        uncertain += (size_t)g * wg.flag_gs;
+        tau += (size_t)g * wg.flag_gs;
+        wspace += (size_t)g * W_GROUP_WORDS;
+    }
+    // partial lists of this launch: ids [S][B][20] | scores [S][B][20] | counts [S][B]
+    int32_t* top_ids = wspace;
+    float* top_scores = reinterpret_cast<float*>(wspace + (size_t)WSPLIT * TCAR_QROWS * TOPK);
+    int32_t* n_greater = wspace + 2 * (size_t)WSPLIT * TCAR_QROWS * TOPK;
     // compact list of the flagged queries (ascending, built identically by every CTA): the grid is WIDEN_SLOTS x
     // WSPLIT CTAs whatever B is, CTA (i, s) takes the flagged queries i, i + WIDEN_SLOTS, ...
     __shared__ int s_flag[TCAR_QROWS];
@@ -579,12 +621,26 @@ catalog_stats_kernel(const float* __restrict__ item, const float* __restrict__ c
 
 // merge G shard lists: one warp per query, serial selection (G*20 <= 160 entries)
 __global__ void __launch_bounds__(256)
-topk_merge_kernel(const int32_t* __restrict__ ids, const float* __restrict__ scores, int32_t* __restrict__ out_ids,
-                  float* __restrict__ out_scores, int G, int B, long long gstride, const int32_t* __restrict__ ngt,
-                  const float* __restrict__ sumexp, const float* __restrict__ rowmax, int32_t* __restrict__ out_ngt,
-                  float* __restrict__ out_ce, const int32_t* __restrict__ only_if) {
+topk_merge_kernel(const int32_t* ids, const float* scores, int32_t* out_ids, float* out_scores, int G, int B,
+                  long long gstride, const int32_t* ngt, const float* __restrict__ sumexp,
+                  const float* __restrict__ rowmax, int32_t* out_ngt, float* __restrict__ out_ce,
+                  const int32_t* only_if,
+                  const __grid_constant__ WidenGroups wg) {
     PDL_ENTER();
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wg.groups > 0) {
+        // the widening pass's own merge, one group per blockIdx.y: inputs in the group's workspace, outputs and flags
+        // in the group's result block
+        const int g = blockIdx.y;
+        B = wg.n[g];
+        ids += (size_t)g * W_GROUP_WORDS;
+        scores += (size_t)g * W_GROUP_WORDS;
+        ngt += (size_t)g * W_GROUP_WORDS;
+        out_ids += (size_t)g * wg.out_gs;
+        out_scores += (size_t)g * wg.out_gs;
+        out_ngt += (size_t)g * wg.out_gs;
+        only_if += (size_t)g * wg.flag_gs;
+    }
     if (b >= B) return;
     if (only_if && !only_if[b]) return;      // widening pass: certified queries keep their result
     if (ngt && !sumexp && lane == 0) {
@@ -705,8 +761,28 @@ extern "C" int tcar_eval_rescore(const float* sel_vals, const int32_t* sel_ids, 
     return (int)cudaGetLastError();
 }
 
-extern "C" long long tcar_eval_topk_widen_ws_bytes(int B) {
-    return (long long)TCAR_WIDEN_SPLITS * (B > 0 ? B : 0) * (2 * TCAR_TOPK + 1) * 4;
+static int launch_widen(const float* chunkmax, const float* tilemax, const float* a_ic, const float* Tq,
+                        const float* item, const float* content, const int32_t* mwdhm, const int32_t* label,
+                        const int32_t* uncertain, const float* tau, int32_t* top_ids, float* top_scores,
+                        int32_t* n_greater, int B, int N, int n_pad, int item_offset, void* workspace,
+                        const WidenGroups& wg, void* stream) {
+    // workspace per group: ids [S][512][20] | scores [S][512][20] | counts [S][512] (rows of a launch use its own B)
+    int32_t* w = static_cast<int32_t*>(workspace);
+    const int groups = wg.groups > 0 ? wg.groups : 1;
+    launch_pdl(eval_topk_widen_kernel, dim3(B < WIDEN_SLOTS ? B : WIDEN_SLOTS, WSPLIT, groups), dim3(256), 0, STREAM,
+               chunkmax, tilemax, a_ic, Tq, item, content, mwdhm, label, uncertain, tau, w, N, n_pad, item_offset, B, wg);
+    int rc = (int)cudaGetLastError();
+    if (rc) return rc;
+    launch_pdl(topk_merge_kernel, dim3((B + 7) / 8, groups), dim3(256), 0, STREAM, static_cast<const int32_t*>(w),
+               reinterpret_cast<const float*>(w + (size_t)WSPLIT * TCAR_QROWS * TOPK), top_ids, top_scores, WSPLIT, B,
+               0LL, static_cast<const int32_t*>(w + 2 * (size_t)WSPLIT * TCAR_QROWS * TOPK),
+               static_cast<const float*>(nullptr), static_cast<const float*>(nullptr), n_greater,
+               static_cast<float*>(nullptr), uncertain, wg);
+    return (int)cudaGetLastError();
+}
+
+extern "C" long long tcar_eval_topk_widen_ws_bytes(int groups) {
+    return (long long)(groups > 0 ? groups : 1) * W_GROUP_WORDS * 4;
 }
 
 extern "C" int tcar_eval_topk_widen(const float* chunkmax, const float* tilemax, const float* a_ic, const float* Tq,
@@ -716,18 +792,72 @@ extern "C" int tcar_eval_topk_widen(const float* chunkmax, const float* tilemax,
                                     int item_offset, void* workspace, void* stream) {
     if (B < 1 || B > TCAR_QROWS || N < 1 || n_pad < N || !tilemax || !uncertain || !tau || !workspace)
         return TCAR_ERR_ARG;
-    // workspace: ids [S][B][20] | scores [S][B][20] | counts [S][B]
-    int32_t* w_ids = static_cast<int32_t*>(workspace);
-    float* w_sc = reinterpret_cast<float*>(w_ids + (size_t)WSPLIT * B * TOPK);
-    int32_t* w_ngt = reinterpret_cast<int32_t*>(w_sc + (size_t)WSPLIT * B * TOPK);
-    launch_pdl(eval_topk_widen_kernel, dim3(B < WIDEN_SLOTS ? B : WIDEN_SLOTS, WSPLIT), dim3(256), 0, STREAM, chunkmax, tilemax, a_ic, Tq, item,
-               content, mwdhm, label, uncertain, tau, w_ids, w_sc, w_ngt, N, n_pad, item_offset, B);
-    int rc = (int)cudaGetLastError();
-    if (rc) return rc;
-    launch_pdl(topk_merge_kernel, dim3((B + 7) / 8), dim3(256), 0, STREAM, static_cast<const int32_t*>(w_ids),
-               static_cast<const float*>(w_sc), top_ids, top_scores, WSPLIT, B, 0LL,
-               static_cast<const int32_t*>(w_ngt), static_cast<const float*>(nullptr),
-               static_cast<const float*>(nullptr), n_greater, static_cast<float*>(nullptr), uncertain);
+    return launch_widen(chunkmax, tilemax, a_ic, Tq, item, content, mwdhm, label, uncertain, tau, top_ids, top_scores,
+                        n_greater, B, N, n_pad, item_offset, workspace, WidenGroups{}, stream);
+}
+
+// The widening pass for the session groups of a catalog-sharded evaluation round in one launch pair: group g (n_rows[g]
+// queries) has its chunk / tile maxima cm_stride / tm_stride floats apart, its a_ic / Tq / label planes q_stride words
+// apart (one exchange block per group), its (uncertain, tau) vectors flag_stride words apart and its result planes
+// (top_ids / top_scores / n_greater) out_stride words apart.  workspace: tcar_eval_topk_widen_ws_bytes(groups).
+extern "C" int tcar_eval_topk_widen_groups(const float* chunkmax, long long cm_stride, const float* tilemax,
+                                           long long tm_stride, const float* a_ic, const float* Tq,
+                                           const int32_t* label, long long q_stride, const float* item,
+                                           const float* content, const int32_t* mwdhm, const int32_t* uncertain,
+                                           const float* tau, long long flag_stride, int32_t* top_ids,
+                                           float* top_scores, int32_t* n_greater, long long out_stride,
+                                           const int* n_rows, int groups, int N, int n_pad, int item_offset,
+                                           void* workspace, void* stream) {
+    if (!n_rows || groups < 1 || groups > TCAR_MAX_PEERS || N < 1 || n_pad < N || !tilemax || !uncertain || !tau ||
+        !workspace)
+        return TCAR_ERR_ARG;
+    WidenGroups wg = {};
+    wg.groups = groups;
+    int bmax = 0;
+    for (int g = 0; g < groups; ++g) {
+        if (n_rows[g] > TCAR_QROWS) return TCAR_ERR_ARG;
+        wg.n[g] = n_rows[g] > 0 ? n_rows[g] : 0;
+        if (wg.n[g] > bmax) bmax = wg.n[g];
+    }
+    if (bmax == 0) return 0;
+    wg.cm_gs = cm_stride;
+    wg.tm_gs = tm_stride;
+    wg.q_gs = q_stride;
+    wg.flag_gs = flag_stride;
+    wg.out_gs = out_stride;
+    return launch_widen(chunkmax, tilemax, a_ic, Tq, item, content, mwdhm, label, uncertain, tau, top_ids, top_scores,
+                        n_greater, bmax, N, n_pad, item_offset, workspace, wg, stream);
+}
+
+// tcar_eval_select for several session groups in one launch (see tcar_eval_topk_widen_groups for the strides).
+extern "C" int tcar_eval_select_groups(const float* chunkmax, long long cm_stride, const float* tilemax,
+                                       long long tm_stride, float* sel_vals, int32_t* sel_ids, long long out_stride,
+                                       const int* n_rows, int groups, int N, int n_pad, int item_offset, void* stream) {
+    if (!n_rows || groups < 1 || groups > TCAR_MAX_PEERS || N < 1 || n_pad < N || !chunkmax || !tilemax || !sel_vals ||
+        !sel_ids || item_offset % CH || (N + 127) / 128 > TCAR_MAX_EVAL_TILES)
+        return TCAR_ERR_ARG;
+    SelIO io = {};
+    io.out_vals = sel_vals;
+    io.out_ids = sel_ids;
+    io.chunk_base = item_offset / CH;
+    io.groups = groups;
+    int bmax = 0;
+    for (int g = 0; g < groups; ++g) {
+        if (n_rows[g] > TCAR_QROWS) return TCAR_ERR_ARG;
+        io.gn[g] = n_rows[g] > 0 ? n_rows[g] : 0;
+        if (io.gn[g] > bmax) bmax = io.gn[g];
+    }
+    if (bmax == 0) return 0;
+    io.cm_gs = cm_stride;
+    io.tm_gs = tm_stride;
+    io.out_gs = out_stride;
+    launch_pdl(eval_topk_kernel, dim3(bmax, groups), dim3(256), 0, STREAM, chunkmax, tilemax,
+               static_cast<const float*>(nullptr), static_cast<const float*>(nullptr),
+               static_cast<const float*>(nullptr), static_cast<const float*>(nullptr),
+               static_cast<const int32_t*>(nullptr), static_cast<const int32_t*>(nullptr),
+               static_cast<int32_t*>(nullptr), static_cast<float*>(nullptr), static_cast<int32_t*>(nullptr), N, n_pad,
+               item_offset, static_cast<const float*>(nullptr), static_cast<int32_t*>(nullptr),
+               static_cast<float*>(nullptr), io);
     return (int)cudaGetLastError();
 }
 
@@ -746,7 +876,7 @@ extern "C" int tcar_topk_merge(const int32_t* ids, const float* scores, int32_t*
     launch_pdl(topk_merge_kernel, dim3((B + 7) / 8), dim3(256), 0, STREAM, ids, scores, out_ids, out_scores, G, B,
                0LL, static_cast<const int32_t*>(nullptr), static_cast<const float*>(nullptr),
                static_cast<const float*>(nullptr), static_cast<int32_t*>(nullptr), static_cast<float*>(nullptr),
-               static_cast<const int32_t*>(nullptr));
+               static_cast<const int32_t*>(nullptr), WidenGroups{});
     return (int)cudaGetLastError();
 }
 
@@ -787,7 +917,7 @@ extern "C" int tcar_eval_merge_flagged(const void* blocks, long long block_words
     const int32_t* i = static_cast<const int32_t*>(blocks);
     launch_pdl(topk_merge_kernel, dim3((B + 7) / 8), dim3(256), 0, STREAM, i + TCAR_EVAL_OFF_IDS, f + TCAR_EVAL_OFF_SCORES,
                out_ids, out_scores, G, B, block_words, i + TCAR_EVAL_OFF_NGT, static_cast<const float*>(nullptr),
-               static_cast<const float*>(nullptr), out_ngt, static_cast<float*>(nullptr), only_if);
+               static_cast<const float*>(nullptr), out_ngt, static_cast<float*>(nullptr), only_if, WidenGroups{});
     return (int)cudaGetLastError();
 }
 
@@ -799,6 +929,6 @@ extern "C" int tcar_eval_merge(const void* blocks, long long block_words, int32_
     const int32_t* i = static_cast<const int32_t*>(blocks);
     launch_pdl(topk_merge_kernel, dim3((B + 7) / 8), dim3(256), 0, STREAM, i + TCAR_EVAL_OFF_IDS, f + TCAR_EVAL_OFF_SCORES,
                out_ids, out_scores, G, B, block_words, i + TCAR_EVAL_OFF_NGT, f + TCAR_EVAL_OFF_SUMEXP,
-               f + TCAR_EVAL_OFF_ROWMAX, out_ngt, out_ce, static_cast<const int32_t*>(nullptr));
+               f + TCAR_EVAL_OFF_ROWMAX, out_ngt, out_ce, static_cast<const int32_t*>(nullptr), WidenGroups{});
     return (int)cudaGetLastError();
 }

@@ -488,17 +488,21 @@ score_fwd_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
 constexpr int M_MAX_RB = 2 * TCAR_MAX_PEERS;       // row blocks: 16 groups x 2
 
 struct FwdMultiParams {
-    __nv_bfloat16* E;          // group g at E + g * e_stride
+    float* chunkmax;           // MODE 1: group g at chunkmax + g * cm_stride ([512, e_pitch/8] each)
+    float* tilemax;            // MODE 1: group g at tilemax + g * tm_stride ([512, e_pitch/128] each)
+    long long cm_stride, tm_stride;
+    __nv_bfloat16* E;          // MODE 0: group g at E + g * e_stride
     float* rowsum_part;        // group g at rowsum_part + g * part_stride
     float* rowmax_part;        // same stride (nullable)
     const float* c_ref;        // group g at c_ref + g * c_stride
-    const float* rowmax;       // [groups][512] (nullable: pass 1)
-    long long e_stride, part_stride, c_stride;
+    const float* rowmax;       // group g at rowmax + g * rm_stride (nullable: pass 1)
+    long long e_stride, part_stride, c_stride, rm_stride;
     int n_items, n_tiles, e_pitch, n_rb;
     unsigned char rb_group[M_MAX_RB], rb_block[M_MAX_RB];
     short rb_rows[M_MAX_RB];   // sessions of the row block's GROUP
 };
 
+template <int MODE>
 __global__ void __launch_bounds__(P_THREADS, 1)
 score_fwd_multi_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_i,
                        const __grid_constant__ FwdMultiParams p) {
@@ -532,7 +536,7 @@ score_fwd_multi_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         if (p.rowmax) {
             const int g = p.rb_group[rb], r0 = p.rb_block[rb] * 2 * BM;
             for (int r = r0 + threadIdx.x; r < r0 + 2 * BM && r < p.rb_rows[rb]; r += blockDim.x)
-                need |= p.rowmax[(size_t)g * QROWS + r] > TCAR_EXP_LIMIT2;
+                need |= p.rowmax[(size_t)g * p.rm_stride + r] > TCAR_EXP_LIMIT2;
         }
         const int any = __syncthreads_or(need);
         if (threadIdx.x == 0) s_need[rb] = any;
@@ -658,6 +662,8 @@ score_fwd_multi_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         pg.n_items = p.n_items;
         pg.e_pitch = p.e_pitch;
         pg.E = p.E;
+        pg.chunkmax = p.chunkmax;
+        float* tmax_row = nullptr;
         size_t part_off = 0;
         for (uint32_t u = u0; u < u1; ++u) {
             const int rb = u / p.n_tiles;
@@ -674,11 +680,15 @@ score_fwd_multi_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 if (row_ok) {
                     cshift = p.c_ref[(size_t)g * p.c_stride + row] * kLog2e;
                     if (p.rowmax) {
-                        const float m = p.rowmax[(size_t)g * QROWS + row];
+                        const float m = p.rowmax[(size_t)g * p.rm_stride + row];
                         if (m > TCAR_EXP_LIMIT2) cshift += m;
                     }
                 }
-                pg.E = p.E + (size_t)g * p.e_stride;
+                if (MODE == 0) pg.E = p.E + (size_t)g * p.e_stride;
+                else {
+                    pg.chunkmax = p.chunkmax + (size_t)g * p.cm_stride;
+                    tmax_row = p.tilemax + (size_t)g * p.tm_stride + (size_t)row * (p.e_pitch / 128);
+                }
                 part_off = (size_t)g * p.part_stride;
             }
             const uint32_t acc = it % P_NACC;
@@ -694,21 +704,24 @@ score_fwd_multi_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             tmem_ld32(taddr, va);
             tmem_ld_wait();
             tmem_ld32(taddr + 32, vb);
-            fwd_epilogue_chunk<0>(va, pg, cshift, row_ok, store_ok, tail, row, n0, psum, tmax, amax);
+            fwd_epilogue_chunk<MODE>(va, pg, cshift, row_ok, store_ok, tail, row, n0, psum, tmax, amax);
             tmem_ld_wait();
             tmem_ld32(taddr + 64, va);
-            fwd_epilogue_chunk<0>(vb, pg, cshift, row_ok, store_ok, tail, row, n0 + 32, psum, tmax, amax);
+            fwd_epilogue_chunk<MODE>(vb, pg, cshift, row_ok, store_ok, tail, row, n0 + 32, psum, tmax, amax);
             tmem_ld_wait();
             tmem_ld32(taddr + 96, vb);
-            fwd_epilogue_chunk<0>(va, pg, cshift, row_ok, store_ok, tail, row, n0 + 64, psum, tmax, amax);
+            fwd_epilogue_chunk<MODE>(va, pg, cshift, row_ok, store_ok, tail, row, n0 + 64, psum, tmax, amax);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(acc_empty_l + acc * 8);
-            fwd_epilogue_chunk<0>(vb, pg, cshift, row_ok, store_ok, tail, row, n0 + 96, psum, tmax, amax);
+            fwd_epilogue_chunk<MODE>(vb, pg, cshift, row_ok, store_ok, tail, row, n0 + 96, psum, tmax, amax);
             if (row_ok) {
                 p.rowsum_part[part_off + (size_t)(tile * 2 + h) * QROWS + row] = psum;
-                if (p.rowmax_part) p.rowmax_part[part_off + (size_t)(tile * 2 + h) * QROWS + row] = amax;
+                if (p.rowmax_part)
+                    p.rowmax_part[part_off + (size_t)(tile * 2 + h) * QROWS + row] =
+                        MODE == 1 ? fmaf(tmax, kLog2e, -cshift) : amax;
+                if (MODE == 1) tmax_row[tile * 2 + h] = tmax;
             }
         }
     }
@@ -1252,15 +1265,44 @@ extern "C" int tcar_score_fwd_guarded(const void* q_bf16, const void* iext_bf16,
 
 extern "C" int tcar_score_fwd_tiles(int n_pad) { return n_pad / F_BN; }
 
+static int score_fwd_multi_impl(const void* q_bf16, long long q_stride, const float* c_ref, long long c_stride,
+                                const void* iext_bf16, void* e_out, long long e_stride, float* chunkmax,
+                                long long cm_stride, float* tilemax, long long tm_stride, float* rowsum_part,
+                                long long part_stride, float* rowmax_part, const float* rowmax, long long rm_stride,
+                                const int* n_rows, int groups, int n_items, int n_pad, void* stream_);
+
 // All session groups in one launch (score_fwd_multi_kernel): train mode, CTA pairs.  Strides in ELEMENTS of the
 // respective arrays; rowmax_part shares part_stride; rowmax is [groups][512].
 extern "C" int tcar_score_fwd_multi(const void* q_bf16, long long q_stride, const float* c_ref, long long c_stride,
                                     const void* iext_bf16, void* e_out, long long e_stride, float* rowsum_part,
                                     long long part_stride, float* rowmax_part, const float* rowmax, const int* n_rows,
                                     int groups, int n_items, int n_pad, void* stream_) {
+    if (!e_out || e_stride < (long long)QROWS * n_pad) return TCAR_ERR_ARG;
+    return score_fwd_multi_impl(q_bf16, q_stride, c_ref, c_stride, iext_bf16, e_out, e_stride, nullptr, 0, nullptr, 0,
+                                rowsum_part, part_stride, rowmax_part, rowmax, QROWS, n_rows, groups, n_items, n_pad,
+                                stream_);
+}
+
+extern "C" int tcar_score_fwd_multi_eval(const void* q_bf16, long long q_stride, const float* c_ref, long long c_stride,
+                                         const void* iext_bf16, float* chunkmax, long long cm_stride, float* tilemax,
+                                         long long tm_stride, float* rowsum_part, long long part_stride,
+                                         float* rowmax_part, const float* rowmax, long long rowmax_stride,
+                                         const int* n_rows, int groups, int n_items, int n_pad, void* stream_) {
+    if (!chunkmax || !tilemax || cm_stride < (long long)QROWS * (n_pad / 8) || tm_stride < (long long)QROWS * (n_pad / 128))
+        return TCAR_ERR_ARG;
+    return score_fwd_multi_impl(q_bf16, q_stride, c_ref, c_stride, iext_bf16, nullptr, 0, chunkmax, cm_stride, tilemax,
+                                tm_stride, rowsum_part, part_stride, rowmax_part, rowmax, rowmax_stride, n_rows, groups,
+                                n_items, n_pad, stream_);
+}
+
+static int score_fwd_multi_impl(const void* q_bf16, long long q_stride, const float* c_ref, long long c_stride,
+                                const void* iext_bf16, void* e_out, long long e_stride, float* chunkmax,
+                                long long cm_stride, float* tilemax, long long tm_stride, float* rowsum_part,
+                                long long part_stride, float* rowmax_part, const float* rowmax, long long rm_stride,
+                                const int* n_rows, int groups, int n_items, int n_pad, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (!n_rows || groups < 1 || groups > TCAR_MAX_PEERS || n_pad % 256 != 0 || n_items > n_pad || !e_out ||
-        !rowsum_part || q_stride < (long long)QROWS * KEXT || (q_stride & 7) || e_stride < (long long)QROWS * n_pad)
+    if (!n_rows || groups < 1 || groups > TCAR_MAX_PEERS || n_pad % 256 != 0 || n_items > n_pad ||
+        !rowsum_part || q_stride < (long long)QROWS * KEXT || (q_stride & 7))
         return TCAR_ERR_ARG;
     FwdMultiParams p = {};
     int nrb = 0;
@@ -1280,12 +1322,17 @@ extern "C" int tcar_score_fwd_multi(const void* q_bf16, long long q_stride, cons
     rc = make_map_bf16(&mi, iext_bf16, n_pad, KEXT, KEXT, BK, P_HALF);
     if (rc) return rc;
     p.E = static_cast<__nv_bfloat16*>(e_out);
+    p.chunkmax = chunkmax;
+    p.tilemax = tilemax;
+    p.cm_stride = cm_stride;
+    p.tm_stride = tm_stride;
     p.rowsum_part = rowsum_part;
     p.rowmax_part = rowmax_part;
     p.c_ref = c_ref;
     p.rowmax = rowmax;
     p.e_stride = e_stride;
     p.part_stride = part_stride;
+    p.rm_stride = rm_stride;
     p.c_stride = c_stride;
     p.n_items = n_items;
     p.n_tiles = n_pad / P_BN;
@@ -1293,7 +1340,10 @@ extern "C" int tcar_score_fwd_multi(const void* q_bf16, long long q_stride, cons
     p.n_rb = nrb;
     int n_pairs = sm_count() / 2;
     if ((long long)n_pairs > (long long)nrb * p.n_tiles) n_pairs = nrb * p.n_tiles;
-    cudaError_t e = cudaFuncSetAttribute(score_fwd_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
+    const bool eval_mode = e_out == nullptr;
+    cudaError_t e = eval_mode
+        ? cudaFuncSetAttribute(score_fwd_multi_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM)
+        : cudaFuncSetAttribute(score_fwd_multi_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
     if (e != cudaSuccess) return (int)e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(n_pairs * 2);
@@ -1312,7 +1362,8 @@ extern "C" int tcar_score_fwd_multi(const void* q_bf16, long long q_stride, cons
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.numAttrs = 2;
 #endif
-    return (int)cudaLaunchKernelEx(&cfg, score_fwd_multi_kernel, mq, mi, p);
+    return eval_mode ? (int)cudaLaunchKernelEx(&cfg, score_fwd_multi_kernel<1>, mq, mi, p)
+                     : (int)cudaLaunchKernelEx(&cfg, score_fwd_multi_kernel<0>, mq, mi, p);
 }
 
 extern "C" int tcar_score_bwd_q_splits(int n_rows, int n_pad) {

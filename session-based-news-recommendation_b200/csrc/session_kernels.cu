@@ -532,7 +532,8 @@ build_query_kernel(const float* __restrict__ a_ic, const float* __restrict__ a_p
 //           summed again and ce[b] = log(sum) + rowmax[b] ln 2; every other row keeps its pass-1 result, and CTAs
 //           without such a row exit at once
 //   pass 3  maxima only (rowmax[b]; catalog-sharded step, where the sums travel with dQ)
-struct GroupRows { int n[TCAR_MAX_PEERS]; long long part_stride; };   // blockIdx.y = session group (pass 3 only)
+// blockIdx.y = session group: partials of group g part_stride floats apart, outputs (sumexp, rowmax) out_stride apart
+struct GroupRows { int n[TCAR_MAX_PEERS]; long long part_stride; long long out_stride; };
 
 __global__ void __launch_bounds__(1024)
 ce_finish_kernel(const float* __restrict__ part, const float* __restrict__ pmax, float* __restrict__ sumexp,
@@ -546,8 +547,10 @@ ce_finish_kernel(const float* __restrict__ part, const float* __restrict__ pmax,
         // several session groups in one launch: group g's partials lie part_stride floats apart, its row maxima go
         // to rowmax + g * 512
         B = gr.n[blockIdx.y];
-        pmax += (size_t)blockIdx.y * gr.part_stride;
-        rowmax += (size_t)blockIdx.y * TCAR_QROWS;
+        if (part) part += (size_t)blockIdx.y * gr.part_stride;
+        if (pmax) pmax += (size_t)blockIdx.y * gr.part_stride;
+        if (sumexp) sumexp += (size_t)blockIdx.y * gr.out_stride;
+        if (rowmax) rowmax += (size_t)blockIdx.y * gr.out_stride;
         if ((int)blockIdx.x * 16 >= B) return;
     }
     bool redo = false;
@@ -1190,9 +1193,34 @@ extern "C" int tcar_rowmax_groups(const float* rowmax_part, long long part_strid
     }
     if (bmax == 0) return 0;
     gr.part_stride = part_stride;
+    gr.out_stride = TCAR_QROWS;
     launch_pdl(ce_finish_kernel, dim3((bmax + 15) / 16, groups), dim3(1024), 0, STREAM,
                static_cast<const float*>(nullptr), rowmax_part, static_cast<float*>(nullptr),
                static_cast<float*>(nullptr), rowmax, n_tiles, bmax, 1, 3, gr);
+    return LAUNCH_RC();
+}
+
+// Guarded softmax sums of several session groups in one launch (catalog-sharded evaluation): pass 1 / 2 of
+// tcar_ce_finish_guarded per group; group g reads its partials at + g * part_stride and writes sumexp / rowmax at
+// + g * out_stride (no ce output: the owner of the queries combines the ranges' sums).
+extern "C" int tcar_ce_finish_groups(const float* rowsum_part, const float* rowmax_part, long long part_stride,
+                                     float* sumexp, float* rowmax, long long out_stride, int n_tiles, const int* n_rows,
+                                     int groups, int pass, void* stream) {
+    if (!rowsum_part || !sumexp || !rowmax || !n_rows || groups < 1 || groups > TCAR_MAX_PEERS || part_stride < 1 ||
+        out_stride < 1 || (pass != 1 && pass != 2) || (pass == 1 && !rowmax_part))
+        return TCAR_ERR_ARG;
+    GroupRows gr = {};
+    int bmax = 0;
+    for (int g = 0; g < groups; ++g) {
+        if (n_rows[g] > TCAR_QROWS) return TCAR_ERR_ARG;
+        gr.n[g] = n_rows[g] > 0 ? n_rows[g] : 0;
+        if (gr.n[g] > bmax) bmax = gr.n[g];
+    }
+    if (bmax == 0) return 0;
+    gr.part_stride = part_stride;
+    gr.out_stride = out_stride;
+    launch_pdl(ce_finish_kernel, dim3((bmax + 15) / 16, groups), dim3(1024), 0, STREAM, rowsum_part, rowmax_part,
+               sumexp, static_cast<float*>(nullptr), rowmax, n_tiles, bmax, 1, pass, gr);
     return LAUNCH_RC();
 }
 

@@ -184,6 +184,7 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         self.softmax_guard = bool(args.get("softmax_guard", os.environ.get("TCAR_SOFTMAX_GUARD", "1") != "0"))
         self.eval_certify = os.environ.get("TCAR_EVAL_CERTIFY", "1") != "0"
         self.eval_two_stage = os.environ.get("TCAR_EVAL_TWO_STAGE", "1") != "0"
+        self.eval_group_launch = os.environ.get("TCAR_EVAL_GROUP_LAUNCH", "1") != "0"
         self.train_parallel = "dp"
         self._item_table_synced = True
         mode = args.get("train_parallel") or "dp"
@@ -230,7 +231,7 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         # certification of the top-20 candidate selection (tcar_eval_topk_certified / tcar_eval_topk_widen)
         self.uncertain = torch.zeros(Bm, device=dev, dtype=torch.int32)
         self.tau, self.cat_stats = f(Bm), f(2)
-        self.widen_ws = torch.zeros(int(nv.lib().tcar_eval_topk_widen_ws_bytes(Bm)), device=dev, dtype=torch.uint8)
+        self.widen_ws = torch.zeros(int(nv.lib().tcar_eval_topk_widen_ws_bytes(1)), device=dev, dtype=torch.uint8)
         self._cat_stats_version = -1
         self.negloss, self.loss, self.coef = f(Bm), f(Bm), f(Bm)
         self.Q = torch.zeros(QROWS, KEXT, device=dev, dtype=torch.bfloat16)
@@ -830,12 +831,51 @@ class Seq2SeqAttNN(CatalogShardedTraining):
                                    "cmax": f(QROWS, n_pad // nv.CHUNK), "tmax": f(QROWS, n_pad // 128)}
         return self._score_ws[key]
 
+    def _groups_ws(self, n_pad, R):
+        """Chunk / tile maxima and softmax partials of R session groups against one item range, group-major."""
+        key = (n_pad, "eval-groups", R)
+        if key not in self._score_ws:
+            tiles = nv.lib().tcar_score_fwd_tiles(n_pad)
+            f = lambda *s_: torch.zeros(*s_, device=self.dev)
+            self._score_ws[key] = {"part": f(R, tiles * QROWS), "pmax": f(R, tiles * QROWS), "tiles": tiles,
+                                   "cmax": f(R, QROWS * (n_pad // nv.CHUNK)), "tmax": f(R, QROWS * (n_pad // 128)),
+                                   "widen": torch.zeros(int(nv.lib().tcar_eval_topk_widen_ws_bytes(R)), device=self.dev,
+                                                        dtype=torch.uint8)}
+        return self._score_ws[key]
+
     def _round_select(self, eq_all, counts, shard, sel_send):
         """Stage 1 on an item range: every rank's queries -> chunk / tile maxima (kept per group for a later widening),
-        guarded softmax partial sums and the candidate lists, written into sel_send[g] (layout nv.SEL_OFF_*)."""
+        guarded softmax partial sums and the candidate lists, written into sel_send[g] (layout nv.SEL_OFF_*).  With
+        CTA pairs (the production configuration) the groups share ONE launch per phase: scoring GEMM (both guard
+        passes), partial-sum reduction, selection."""
         p = nv.ptr
         lo, hi, iext = shard
         n_loc, n_pad = hi - lo, iext.shape[0]
+        R = len(counts)
+        if n_loc > 0 and self.cluster == nv.CLUSTER_PAIR and self.eval_group_launch and eq_all.is_contiguous():
+            ws = self._groups_ws(n_pad, R)
+            cnt = (nv.C.c_int * R)(*counts)
+            qs, cs = self.EQ_BYTES // 2, self.EQ_BYTES // 4
+            q0 = nv.C.c_void_p(eq_all.data_ptr())
+            c0 = nv.C.c_void_p(eq_all.data_ptr() + self.EQ_Q)
+            cm_s, tm_s, pt_s = ws["cmax"].stride(0), ws["tmax"].stride(0), ws["part"].stride(0)
+            sumexp, rowmax = p(sel_send[0, nv.SEL_OFF_SUMEXP:]), p(sel_send[0, nv.SEL_OFF_ROWMAX:])
+            guard = self.softmax_guard
+            nv.counted_call("tcar_score_fwd_multi_eval", 1, q0, qs, c0, cs, p(iext), p(ws["cmax"]), cm_s, p(ws["tmax"]),
+                            tm_s, p(ws["part"]), pt_s, p(ws["pmax"]), None, sel_send.stride(0), cnt, R, n_loc, n_pad)
+            nv.counted_call("tcar_ce_finish_groups", 1, p(ws["part"]), p(ws["pmax"]), pt_s, sumexp, rowmax,
+                            sel_send.stride(0), ws["tiles"], cnt, R, 1)
+            if guard:
+                nv.counted_call("tcar_score_fwd_multi_eval", 1, q0, qs, c0, cs, p(iext), p(ws["cmax"]), cm_s,
+                                p(ws["tmax"]), tm_s, p(ws["part"]), pt_s, None, rowmax, sel_send.stride(0), cnt, R, n_loc,
+                                n_pad)
+                nv.counted_call("tcar_ce_finish_groups", 1, p(ws["part"]), None, pt_s, sumexp, rowmax,
+                                sel_send.stride(0), ws["tiles"], cnt, R, 2)
+            else:
+                sel_send[:, nv.SEL_OFF_ROWMAX:].zero_()
+            nv.counted_call("tcar_eval_select_groups", 1, p(ws["cmax"]), cm_s, p(ws["tmax"]), tm_s, p(sel_send),
+                            p(sel_send.view(torch.int32)[0, nv.SEL_OFF_IDS:]), sel_send.stride(0), cnt, R, n_loc, n_pad, lo)
+            return
         for g, Bg in enumerate(counts):
             if Bg == 0:
                 continue
@@ -875,6 +915,22 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         ps = self.ps
         lo, hi, iext = shard
         n_loc, n_pad = hi - lo, iext.shape[0]
+        R = len(counts)
+        if (n_loc > 0 and self.cluster == nv.CLUSTER_PAIR and self.eval_group_launch and eq_all.is_contiguous()
+                and flag_all.is_contiguous()):
+            ws = self._groups_ws(n_pad, R)
+            cnt = (nv.C.c_int * R)(*counts)
+            base = eq_all.data_ptr()
+            o_a = self.EQ_Q + self.EQ_C
+            o_t, o_l = o_a + self.EQ_A, o_a + self.EQ_A + self.EQ_T
+            si = send.view(torch.int32)
+            nv.counted_call("tcar_eval_topk_widen_groups", 2, p(ws["cmax"]), ws["cmax"].stride(0), p(ws["tmax"]),
+                            ws["tmax"].stride(0), nv.C.c_void_p(base + o_a), nv.C.c_void_p(base + o_t),
+                            nv.C.c_void_p(base + o_l), self.EQ_BYTES // 4, p(ps.item), p(ps.content), p(ps.mwdhm),
+                            p(flag_all.view(torch.int32)), p(flag_all[0, QROWS:]), flag_all.stride(0),
+                            p(si[0, nv.EVAL_OFF_IDS:]), p(send[0, nv.EVAL_OFF_SCORES:]), p(si[0, nv.EVAL_OFF_NGT:]),
+                            send.stride(0), cnt, R, n_loc, n_pad, lo, p(ws["widen"]))
+            return
         for g, Bg in enumerate(counts):
             if Bg == 0:
                 continue

@@ -715,9 +715,9 @@ def test_checkpoint_save_restore_gives_identical_eval_and_training(tmp_path):
 
 
 # ------------------------------------------------------------------------------------------- eval rounds (8e eval)
-@pytest.mark.parametrize("two_stage", [True, False])
+@pytest.mark.parametrize("two_stage,grouped", [(True, True), (True, False), (False, False)])
 @pytest.mark.parametrize("V", [2, 3, 8])
-def test_eval_round_virtual_ranks_equal_single_device(V, two_stage):
+def test_eval_round_virtual_ranks_equal_single_device(V, two_stage, grouped):
     """Seq2SeqAttNN.eval_round on one GPU with V virtual ranks (same kernels, shard offsets and block layouts; the
     all-gather and the all-to-all replaced by copies): every rank's OWN batch -- different sizes and session lengths,
     one of them empty -- must come back exactly as eval_step returns it on one device."""
@@ -732,6 +732,7 @@ def test_eval_round_virtual_ranks_equal_single_device(V, two_stage):
         else:
             bts.append(batch_for(model, N, Bv, 1 + (v * 5) % 11, 0, mwdhm, seed=200 + v)[0])
     want = [None if b.B == 0 else [x.clone() for x in model.eval_step(b)] for b in bts]
+    model.eval_group_launch = grouped          # one launch per phase over all groups vs one per group
     got = model.eval_round_virtual(bts, two_stage=two_stage)
     torch.cuda.synchronize()
     for v, (w, g) in enumerate(zip(want, got)):
