@@ -1018,9 +1018,20 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         if shard is None:
             lo, hi = self.shard_bounds(R)[me]
             shard = (lo, hi, self.iext_shard(lo, hi))
+        trace = getattr(self, "_round_trace", None)       # tools/eval_round_probe.py: (phase, CUDA event) pairs
+
+        def mark(name):
+            if trace is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                trace.append((name, ev))
+
+        mark("start")
         self._round_forward(bt, self._eq)
+        mark("forward")
         if on:
             dist.all_gather_into_tensor(self._eq_all.view(-1), self._eq)
+        mark("gather_queries")
         if not two_stage:
             self._round_score(self._eq_all, counts, shard, self._ev_send)
             if on:
@@ -1030,20 +1041,28 @@ class Seq2SeqAttNN(CatalogShardedTraining):
             return self._merge_blocks(self._ev_recv, R, B)
         self._alloc_two_stage(R)
         self._round_select(self._eq_all, counts, shard, self._sel_send)
+        mark("score+select")
         if on:
             dist.all_to_all_single(self._sel_recv.view(-1), self._sel_send.view(-1))
+        mark("exchange_lists")
         if B > 0:
             self._round_rescore(self._sel_recv, R, self._eq, B, self._flag)
         else:
             self._flag.zero_()
+        mark("rescore")
         if on:
             dist.all_gather_into_tensor(self._flag_all.view(-1), self._flag)
+        mark("gather_flags")
         self._round_widen(self._eq_all, counts, shard, self._flag_all, self._ev_send)
+        mark("widen")
         if on:
             dist.all_to_all_single(self._ev_recv.view(-1), self._ev_send.view(-1))
+        mark("exchange_widened")
         if B == 0:
             return self.m_ids[:0], self.m_ngt[:0], self.m_ce[:0]
-        return self._round_finish(self._ev_recv, R, B, self._flag)
+        out = self._round_finish(self._ev_recv, R, B, self._flag)
+        mark("merge")
+        return out
 
     def eval_round_virtual(self, bts, two_stage=None):
         """Single-GPU emulation of eval_round over V = len(bts) ranks (tests): the same kernels with the same shard
