@@ -987,7 +987,7 @@ class Seq2SeqAttNN(CatalogShardedTraining):
                                 sumexp=blk[nv.EVAL_OFF_SUMEXP:], ce=self._ce_scratch, rowmax=blk[nv.EVAL_OFF_ROWMAX:])
             self._topk(ws, ag, Tg, lg, blk, Bg, n_loc, n_pad, lo)
 
-    def eval_round(self, bt, counts, shard=None, two_stage=None):
+    def eval_round(self, bt, counts, shard=None, two_stage=None, next_bt=None):
         """Catalog-sharded evaluation that SCALES: every rank brings its OWN batch of <= 512 queries (bt; B may be 0 in
         the last round), so one round evaluates sum(counts) queries.  counts[g] = queries of rank g (the same list on
         every rank).  Per round (two-stage form, the default):
@@ -1002,7 +1002,10 @@ class Seq2SeqAttNN(CatalogShardedTraining):
              partial lists; the owner merges them (tcar_eval_merge_flagged)
         two_stage=False: the one-stage form (every range computes its certified local top-20; one all-gather + one
         all-to-all).  Same results as eval_step(bt) on one GPU either way, bit for bit on the ids
-        (model_combine.py:283-306, util.py:8-18)."""
+        (model_combine.py:283-306, util.py:8-18).
+        next_bt (two-stage form): this rank's batch of the FOLLOWING round; its session forward (a latency-bound chain
+        of small kernels) is launched on the high-priority stream beside this round's owner-side phases (re-scoring,
+        widening, merge) into the second exchange block.  Identical results."""
         import torch.distributed as dist
         if not self._item_table_synced:
             self.sync_item_table()
@@ -1027,7 +1030,13 @@ class Seq2SeqAttNN(CatalogShardedTraining):
                 trace.append((name, ev))
 
         mark("start")
-        self._round_forward(bt, self._eq)
+        pre, self._round_pre = getattr(self, "_round_pre", None), None
+        if pre is not None and pre[0] is bt:
+            torch.cuda.current_stream().wait_event(pre[1])       # forward already launched by the previous round
+            self._eq, self._eq_next = self._eq_next, self._eq
+            self._prefetched = None
+        else:
+            self._round_forward(bt, self._eq)
         mark("forward")
         if on:
             dist.all_gather_into_tensor(self._eq_all.view(-1), self._eq)
@@ -1045,6 +1054,19 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         if on:
             dist.all_to_all_single(self._sel_recv.view(-1), self._sel_send.view(-1))
         mark("exchange_lists")
+        if next_bt is not None and next_bt.B > 0:
+            if getattr(self, "_eq_next", None) is None:
+                self._eq_next = torch.zeros_like(self._eq)
+            main = torch.cuda.current_stream()
+            fork = torch.cuda.Event()
+            fork.record(main)
+            self._ahead.wait_event(fork)
+            with torch.cuda.stream(self._ahead):
+                self._round_forward(next_bt, self._eq_next)
+                done = torch.cuda.Event()
+                done.record(self._ahead)
+            self._round_pre = (next_bt, done)
+            self._ahead_done = done            # any other entry point waits for it too (sync_updates)
         if B > 0:
             self._round_rescore(self._sel_recv, R, self._eq, B, self._flag)
         else:

@@ -45,6 +45,20 @@ def main():
         for i in range(20):
             model.eval_round(bts[i % 16], counts, two_stage=two_stage)
         e1.record()
+        if two_stage:
+            torch.cuda.synchronize()
+            dist.barrier()
+            e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e2.record()
+            for i in range(20):
+                model.eval_round(bts[i % 16], counts, two_stage=True, next_bt=bts[(i + 1) % 16])
+            model.sync_updates()
+            e3.record()
+            torch.cuda.synchronize()
+            t2 = torch.tensor([e2.elapsed_time(e3) / 20], device=model.dev, dtype=torch.float64)
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                print(f"two_stage=True + look-ahead: {float(t2) * 1e3:.1f} us/round, {world * B / (float(t2) * 1e-3):.0f} queries/s", flush=True)
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1) / 20], device=model.dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
