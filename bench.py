@@ -590,7 +590,7 @@ def run_b200(a):
     def time_eval(batches, steps, shard_, warm=3):
         n = len(batches)
         nx = (lambda i: batches[(i + 1) % n]) if not a.no_lookahead else (lambda i: None)
-        ev = (lambda b, nb: model.eval_round(b, [B] * world, shard=shard_, next_bt=nb)) if world > 1 else \
+        ev = (lambda b, nb: model.eval_round(b, [B] * world, shard=shard_)) if world > 1 else \
             (lambda b, nb: model.eval_step(b, next_bt=nb))
         for i in range(warm):
             ev(batches[i % n], nx(i))
@@ -648,7 +648,7 @@ def run_b200(a):
 
     def estep(bt_, nxt_):
         if world > 1:
-            return model.eval_round(bt_, ecounts, shard=shard, next_bt=nxt_)
+            return model.eval_round(bt_, ecounts, shard=shard)
         return model.eval_step(bt_, next_bt=nxt_)
 
     for i in range(W):

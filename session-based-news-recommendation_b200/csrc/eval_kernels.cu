@@ -223,6 +223,176 @@ __device__ __forceinline__ void sort_chunk_candidates(float* s_cv, int* s_ci) {
     __syncthreads();
 }
 
+// ------------------------------------------------------------------------------------------------ warp-per-query selection
+// The selection half (32 best chunks of a query by bf16 chunk maximum + a bound on the rest) needs no block-wide
+// cooperation: a CTA of 256 threads spends it in ~75 barriers.  Here ONE WARP owns a query: a 4-pass radix select over
+// the tile maxima (warp-private 256-bin histogram in shared memory, bins scanned with shuffles) finds the 32 best tiles,
+// lane l then holds tile l's 16 chunk maxima in registers, chunks below the 32nd tile maximum are pruned (they cannot
+// be among the 32 best chunks), and the 32 best survivors are extracted with 32 warp arg-max steps.  8 queries per CTA,
+// >= 32 queries in flight per SM instead of 3-4.
+struct SelGroups {
+    int groups;                          // 0: one group of B queries
+    int n[TCAR_MAX_PEERS];
+    long long cm_gs, tm_gs, out_gs;
+};
+
+__global__ void __launch_bounds__(256)
+eval_select_warp_kernel(const float* chunkmax, const float* tilemax, float* sel_vals, int32_t* sel_ids, int B, int N,
+                        int n_pad, int chunk_base, const __grid_constant__ SelGroups sg) {
+    PDL_ENTER();
+    __shared__ int s_hist[8][256];
+    __shared__ int s_tile[8][NCH];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int b = blockIdx.x * 8 + w;
+    if (sg.groups > 0) {
+        const int g = blockIdx.y;
+        B = sg.n[g];
+        chunkmax += (size_t)g * sg.cm_gs;
+        tilemax += (size_t)g * sg.tm_gs;
+        sel_vals += (size_t)g * sg.out_gs;
+        sel_ids += (size_t)g * sg.out_gs;
+    }
+    if (b >= B) return;                  // warp-uniform; no block-wide barrier below
+    const int nchunks = (N + CH - 1) / CH;
+    const int ntiles = (N + 127) / 128;
+    const float* cm = chunkmax + (size_t)b * (n_pad / CH);
+    const float* tm = tilemax + (size_t)b * (n_pad / 128);
+    int* hist = s_hist[w];
+    int* tiles = s_tile[w];
+    float thr = -INFINITY;               // 32nd largest tile maximum: chunks below it are not candidates
+    float rest_tile_max = -INFINITY;     // best tile NOT taken
+    int ntake = ntiles < NCH ? ntiles : NCH;
+    if (ntiles <= NCH) {
+        if (lane < ntiles) tiles[lane] = lane;
+    } else {
+        uint32_t prefix = 0, mask = 0;
+        int kth = NCH;
+        for (int shift = 24; shift >= 0; shift -= 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) hist[lane * 8 + j] = 0;
+            __syncwarp();
+            for (int i = lane; i < ntiles; i += 32) {
+                const uint32_t k = fkey(tm[i]);
+                if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1);
+            }
+            __syncwarp();
+            int cnt[8], tot = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { cnt[j] = hist[lane * 8 + j]; tot += cnt[j]; }
+            int suf = tot;               // inclusive suffix sum over the lanes (bins of higher lanes are larger digits)
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_down_sync(0xffffffffu, suf, o);
+                if (lane + o < 32) suf += v;
+            }
+            const int above_lane = suf - tot;
+            const bool mine = above_lane < kth && kth <= suf;
+            int d = 0, above = 0;
+            if (mine) {
+                int a = above_lane;
+                for (int j = 7; j >= 0; --j) {
+                    if (a + cnt[j] >= kth) { d = lane * 8 + j; above = a; break; }
+                    a += cnt[j];
+                }
+            }
+            const uint32_t who = __ballot_sync(0xffffffffu, mine);
+            const int src = __ffs(who) - 1;
+            d = __shfl_sync(0xffffffffu, d, src);
+            above = __shfl_sync(0xffffffffu, above, src);
+            prefix |= (uint32_t)d << shift;
+            mask |= 255u << shift;
+            kth -= above;
+            __syncwarp();
+        }
+        // prefix = key of the 32nd largest tile maximum; kth = how many tiles equal to it are still needed
+        int taken = 0, eq_left = kth;
+        float below = -INFINITY;
+        bool eq_rest = false;
+        for (int i0 = 0; i0 < ntiles; i0 += 32) {
+            const int i = i0 + lane;
+            const float v = i < ntiles ? tm[i] : -INFINITY;
+            const uint32_t k = i < ntiles ? fkey(v) : 0u;
+            const bool gt = i < ntiles && k > prefix, eq = i < ntiles && k == prefix;
+            const uint32_t bg = __ballot_sync(0xffffffffu, gt), be = __ballot_sync(0xffffffffu, eq);
+            if (gt) tiles[taken + __popc(bg & ((1u << lane) - 1u))] = i;
+            taken += __popc(bg);
+            const int rank_eq = __popc(be & ((1u << lane) - 1u));
+            if (eq && rank_eq < eq_left) tiles[taken + rank_eq] = i;
+            const int take_eq = min(__popc(be), eq_left);
+            if (__popc(be) > eq_left) eq_rest = true;
+            taken += take_eq;
+            eq_left -= take_eq;
+            if (i < ntiles && k < prefix) below = fmaxf(below, v);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) below = fmaxf(below, __shfl_xor_sync(0xffffffffu, below, o));
+        // value of the prefix key (the 32nd largest tile maximum)
+        const uint32_t pu = (prefix & 0x80000000u) ? (prefix & 0x7fffffffu) : ~prefix;
+        thr = __uint_as_float(pu);
+        rest_tile_max = eq_rest ? thr : below;
+        __syncwarp();
+    }
+    // ---- lane l <- tile l: its 16 chunk maxima, pruned by thr
+    float v[TILE_CH];
+    uint32_t alive = 0;
+    float pruned = -INFINITY;
+    const int tile = lane < ntake ? tiles[lane] : -1;
+    if (tile >= 0) {
+        const float4* src = reinterpret_cast<const float4*>(cm + (size_t)tile * TILE_CH);
+#pragma unroll
+        for (int c = 0; c < TILE_CH / 4; ++c) {
+            const float4 q = src[c];
+            v[4 * c] = q.x; v[4 * c + 1] = q.y; v[4 * c + 2] = q.z; v[4 * c + 3] = q.w;
+        }
+#pragma unroll
+        for (int c = 0; c < TILE_CH; ++c) {
+            const bool ok = tile * TILE_CH + c < nchunks;
+            if (ok && v[c] >= thr) alive |= 1u << c;
+            else if (ok) pruned = fmaxf(pruned, v[c]);
+        }
+    }
+    // ---- 32 arg-max extractions by (value desc, chunk id asc)
+    float* out_v = sel_vals + (size_t)b * NSEL;
+    int32_t* out_i = sel_ids + (size_t)b * NSEL;
+    float my_v = -INFINITY;
+    int my_c = 0x7fffffff;
+    auto refresh = [&]() {
+        my_v = -INFINITY;
+        my_c = 0x7fffffff;
+#pragma unroll
+        for (int c = 0; c < TILE_CH; ++c)
+            if (((alive >> c) & 1u) && before(v[c], tile * TILE_CH + c, my_v, my_c)) { my_v = v[c]; my_c = tile * TILE_CH + c; }
+    };
+    refresh();
+    for (int r = 0; r < NCH; ++r) {
+        float bv = my_v;
+        int bc = my_c;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+            if (before(ov, oc, bv, bc)) { bv = ov; bc = oc; }
+        }
+        if (lane == 0) {
+            out_v[r] = bc == 0x7fffffff ? -INFINITY : bv;
+            out_i[r] = bc == 0x7fffffff ? -1 : bc + chunk_base;
+        }
+        if (bc != 0x7fffffff && bc == my_c) {           // the winner retires its entry
+            alive &= ~(1u << (bc - tile * TILE_CH));
+            refresh();
+        }
+    }
+    // ---- bound on every chunk that is not listed: best survivor left, best pruned chunk, best tile not taken
+    float rest = fmaxf(my_v, pruned);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rest = fmaxf(rest, __shfl_xor_sync(0xffffffffu, rest, o));
+    rest = fmaxf(rest, rest_tile_max);
+    if (lane == 0) {
+        out_v[NCH] = rest;
+        out_i[NCH] = -2;
+    }
+}
+
 // one CTA (256 threads) per query.  Two-level selection: the 32 best 128-item tiles by tile max (every one of the 32
 // best chunks lives in one of them: the 32 largest tile maxima are 32 distinct chunk values, so the 32nd largest chunk
 // is >= the 32nd largest tile max), then the 32 best of their 512 chunks, then the exact fp32 re-scoring.
@@ -269,7 +439,15 @@ eval_topk_kernel(const float* chunkmax, const float* tilemax, const float* __res
     for (int i = tid; i < NCH; i += 256) s_sel[i] = -1;
     __syncthreads();
 
-    if (from_lists) {
+    if (from_lists && io.in_lists == 1) {
+        // ---- one list (single GPU): its 32 entries are the candidates, the 33rd is the bound
+        const size_t at = (size_t)b * NSEL + tid;
+        if (tid < NCH) {
+            const int cid = io.in_ids[at];
+            s_sel[tid] = cid >= 0 ? cid : -1;
+        }
+        unsel_max = io.in_vals[(size_t)b * NSEL + NCH];
+    } else if (from_lists) {
         // ---- the item ranges' candidate lists (global chunk ids): the 32 best overall, the 33rd as the bound
         const int n_in = io.in_lists * NSEL;
         for (int i = tid; i < NCC; i += 256) {
@@ -727,18 +905,10 @@ extern "C" int tcar_eval_topk_certified(const float* chunkmax, const float* tile
 extern "C" int tcar_eval_select(const float* chunkmax, const float* tilemax, float* sel_vals, int32_t* sel_ids, int B,
                                 int N, int n_pad, int item_offset, void* stream) {
     if (B < 1 || B > TCAR_QROWS || N < 1 || n_pad < N || !chunkmax || !tilemax || !sel_vals || !sel_ids ||
-        item_offset % CH || (N + 127) / 128 > TCAR_MAX_EVAL_TILES)
+        item_offset % CH)
         return TCAR_ERR_ARG;
-    SelIO io = {};
-    io.out_vals = sel_vals;
-    io.out_ids = sel_ids;
-    io.chunk_base = item_offset / CH;
-    launch_pdl(eval_topk_kernel, dim3(B), dim3(256), 0, STREAM, chunkmax, tilemax, static_cast<const float*>(nullptr),
-               static_cast<const float*>(nullptr), static_cast<const float*>(nullptr),
-               static_cast<const float*>(nullptr), static_cast<const int32_t*>(nullptr),
-               static_cast<const int32_t*>(nullptr), static_cast<int32_t*>(nullptr), static_cast<float*>(nullptr),
-               static_cast<int32_t*>(nullptr), N, n_pad, item_offset, static_cast<const float*>(nullptr),
-               static_cast<int32_t*>(nullptr), static_cast<float*>(nullptr), io);
+    launch_pdl(eval_select_warp_kernel, dim3((B + 7) / 8), dim3(256), 0, STREAM, chunkmax, tilemax, sel_vals, sel_ids,
+               B, N, n_pad, item_offset / CH, SelGroups{});
     return (int)cudaGetLastError();
 }
 
@@ -834,30 +1004,22 @@ extern "C" int tcar_eval_select_groups(const float* chunkmax, long long cm_strid
                                        long long tm_stride, float* sel_vals, int32_t* sel_ids, long long out_stride,
                                        const int* n_rows, int groups, int N, int n_pad, int item_offset, void* stream) {
     if (!n_rows || groups < 1 || groups > TCAR_MAX_PEERS || N < 1 || n_pad < N || !chunkmax || !tilemax || !sel_vals ||
-        !sel_ids || item_offset % CH || (N + 127) / 128 > TCAR_MAX_EVAL_TILES)
+        !sel_ids || item_offset % CH)
         return TCAR_ERR_ARG;
-    SelIO io = {};
-    io.out_vals = sel_vals;
-    io.out_ids = sel_ids;
-    io.chunk_base = item_offset / CH;
-    io.groups = groups;
+    SelGroups sg = {};
+    sg.groups = groups;
     int bmax = 0;
     for (int g = 0; g < groups; ++g) {
         if (n_rows[g] > TCAR_QROWS) return TCAR_ERR_ARG;
-        io.gn[g] = n_rows[g] > 0 ? n_rows[g] : 0;
-        if (io.gn[g] > bmax) bmax = io.gn[g];
+        sg.n[g] = n_rows[g] > 0 ? n_rows[g] : 0;
+        if (sg.n[g] > bmax) bmax = sg.n[g];
     }
     if (bmax == 0) return 0;
-    io.cm_gs = cm_stride;
-    io.tm_gs = tm_stride;
-    io.out_gs = out_stride;
-    launch_pdl(eval_topk_kernel, dim3(bmax, groups), dim3(256), 0, STREAM, chunkmax, tilemax,
-               static_cast<const float*>(nullptr), static_cast<const float*>(nullptr),
-               static_cast<const float*>(nullptr), static_cast<const float*>(nullptr),
-               static_cast<const int32_t*>(nullptr), static_cast<const int32_t*>(nullptr),
-               static_cast<int32_t*>(nullptr), static_cast<float*>(nullptr), static_cast<int32_t*>(nullptr), N, n_pad,
-               item_offset, static_cast<const float*>(nullptr), static_cast<int32_t*>(nullptr),
-               static_cast<float*>(nullptr), io);
+    sg.cm_gs = cm_stride;
+    sg.tm_gs = tm_stride;
+    sg.out_gs = out_stride;
+    launch_pdl(eval_select_warp_kernel, dim3((bmax + 7) / 8, groups), dim3(256), 0, STREAM, chunkmax, tilemax, sel_vals,
+               sel_ids, bmax, N, n_pad, item_offset / CH, sg);
     return (int)cudaGetLastError();
 }
 

@@ -185,6 +185,7 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         self.eval_certify = os.environ.get("TCAR_EVAL_CERTIFY", "1") != "0"
         self.eval_two_stage = os.environ.get("TCAR_EVAL_TWO_STAGE", "1") != "0"
         self.eval_group_launch = os.environ.get("TCAR_EVAL_GROUP_LAUNCH", "1") != "0"
+        self.eval_warp_select = os.environ.get("TCAR_EVAL_WARP_SELECT", "1") != "0"
         self.train_parallel = "dp"
         self._item_table_synced = True
         mode = args.get("train_parallel") or "dp"
@@ -231,6 +232,7 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         # certification of the top-20 candidate selection (tcar_eval_topk_certified / tcar_eval_topk_widen)
         self.uncertain = torch.zeros(Bm, device=dev, dtype=torch.int32)
         self.tau, self.cat_stats = f(Bm), f(2)
+        self._sel1 = f(2 * Bm * nv.EVAL_NSEL)            # candidate list of the single-range evaluation (vals | ids)
         self.widen_ws = torch.zeros(int(nv.lib().tcar_eval_topk_widen_ws_bytes(1)), device=dev, dtype=torch.uint8)
         self._cat_stats_version = -1
         self.negloss, self.loss, self.coef = f(Bm), f(Bm), f(Bm)
@@ -763,9 +765,18 @@ class Seq2SeqAttNN(CatalogShardedTraining):
             nv.counted_call("tcar_eval_topk", 1, p(ws["cmax"]), p(ws["tmax"]), p(a_ic), p(Tq), p(ps.item),
                             p(ps.content), p(ps.mwdhm), p(label), ids, sc, ngt, B, n_loc, n_pad, lo)
             return
-        nv.counted_call("tcar_eval_topk_certified", 1, p(ws["cmax"]), p(ws["tmax"]), p(a_ic), p(Tq), p(ps.item),
-                        p(ps.content), p(ps.mwdhm), p(label), ids, sc, ngt, B, n_loc, n_pad, lo, p(self.cat_stats),
-                        p(self.uncertain), p(self.tau))
+        if self.eval_warp_select:
+            # selection by one warp per query (tcar_eval_select), exact re-scoring + certification by one CTA per query
+            sel = self._sel1
+            nv.counted_call("tcar_eval_select", 1, p(ws["cmax"]), p(ws["tmax"]), p(sel), p(sel.view(torch.int32)[QROWS * nv.EVAL_NSEL:]),
+                            B, n_loc, n_pad, lo)
+            nv.counted_call("tcar_eval_rescore", 1, p(sel), p(sel.view(torch.int32)[QROWS * nv.EVAL_NSEL:]), 1,
+                            QROWS * nv.EVAL_NSEL, p(a_ic), p(Tq), p(ps.item), p(ps.content), p(ps.mwdhm), p(label), ids, sc,
+                            ngt, B, ps.N, p(self.cat_stats), p(self.uncertain), p(self.tau))
+        else:
+            nv.counted_call("tcar_eval_topk_certified", 1, p(ws["cmax"]), p(ws["tmax"]), p(a_ic), p(Tq), p(ps.item),
+                            p(ps.content), p(ps.mwdhm), p(label), ids, sc, ngt, B, n_loc, n_pad, lo, p(self.cat_stats),
+                            p(self.uncertain), p(self.tau))
         nv.counted_call("tcar_eval_topk_widen", 2, p(ws["cmax"]), p(ws["tmax"]), p(a_ic), p(Tq), p(ps.item),
                         p(ps.content), p(ps.mwdhm), p(label), p(self.uncertain), p(self.tau), ids, sc, ngt, B, n_loc,
                         n_pad, lo, p(self.widen_ws))

@@ -236,9 +236,11 @@ def margin_ok(scores, k=20, rel=2e-5):
     return gaps > rel * np.abs(s[:, :k + 1]).max(1)
 
 
+@pytest.mark.parametrize("warp_select", [True, False])
 @pytest.mark.parametrize("B,T,N", [(3, 1, 300), (200, 4, 5000), (512, 20, 9000), (64, 3, 70000)])
-def test_eval_top20_rank_and_loss(B, T, N):
+def test_eval_top20_rank_and_loss(B, T, N, warp_select):
     model, content, mwdhm, args = build(N, emb_scale=20.0)
+    model.eval_warp_select = warp_select       # warp-per-query selection + re-score kernel vs the fused CTA kernel
     bt, batch = batch_for(model, N, B, T, 0, mwdhm, seed=B)
     params, c64, m64 = oracle_inputs(model, content, mwdhm)
     ref = O.eval_batch(params, c64, m64, batch, args["category_id"], args["reverse_item"])

@@ -52,6 +52,10 @@ def main():
             for look in (False, True):
                 model.softmax_guard, model.eval_certify = guard, cert
                 print(f"guard={int(guard)} certify={int(cert)} lookahead={int(look)}: {loop(look):7.1f} us/step", flush=True)
+    model.softmax_guard = model.eval_certify = True
+    for ws_ in (False, True):
+        model.eval_warp_select = ws_
+        print(f"guard=1 certify=1 lookahead=1 warp_select={int(ws_)}: {loop(True):7.1f} us/step", flush=True)
     # phases of one step (no look-ahead), events between the calls
     model.softmax_guard = model.eval_certify = True
     shares = []
