@@ -271,9 +271,24 @@ eval_select_warp_kernel(const float* chunkmax, const float* tilemax, float* sel_
 #pragma unroll
             for (int j = 0; j < 8; ++j) hist[lane * 8 + j] = 0;
             __syncwarp();
-            for (int i = lane; i < ntiles; i += 32) {
-                const uint32_t k = fkey(tm[i]);
-                if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1);
+            for (int base = 0; base < ntiles; base += 32 * 8) {      // warp-uniform trip count (match_any below)
+                const int i0 = base + lane;
+                // eight independent loads in flight per lane (one warp per query: nothing else hides the latency)
+                float t[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) t[u] = i0 + 32 * u < ntiles ? tm[i0 + 32 * u] : 0.f;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    // scores of one query sit in a narrow range: most lanes hit the SAME bin, and a shared-memory
+                    // atomic would serialise them (47 us per launch).  Lanes with equal bins are matched instead and
+                    // one of them adds their count: the leaders of one step have distinct bins.
+                    const uint32_t k = fkey(t[u]);
+                    const bool act = i0 + 32 * u < ntiles && (k & mask) == prefix;
+                    const uint32_t bin = act ? ((k >> shift) & 255u) : 256u;
+                    const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+                    if (act && lane == __ffs(peers) - 1) hist[bin] += __popc(peers);
+                    __syncwarp();
+                }
             }
             __syncwarp();
             int cnt[8], tot = 0;
@@ -308,9 +323,15 @@ eval_select_warp_kernel(const float* chunkmax, const float* tilemax, float* sel_
         int taken = 0, eq_left = kth;
         float below = -INFINITY;
         bool eq_rest = false;
-        for (int i0 = 0; i0 < ntiles; i0 += 32) {
-            const int i = i0 + lane;
-            const float v = i < ntiles ? tm[i] : -INFINITY;
+        for (int i00 = 0; i00 < ntiles; i00 += 32 * 4) {
+          float t4[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) t4[u] = i00 + 32 * u + lane < ntiles ? tm[i00 + 32 * u + lane] : -INFINITY;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i00 + 32 * u + lane;
+            if (i00 + 32 * u >= ntiles) break;                      // warp-uniform
+            const float v = t4[u];
             const uint32_t k = i < ntiles ? fkey(v) : 0u;
             const bool gt = i < ntiles && k > prefix, eq = i < ntiles && k == prefix;
             const uint32_t bg = __ballot_sync(0xffffffffu, gt), be = __ballot_sync(0xffffffffu, eq);
@@ -323,6 +344,7 @@ eval_select_warp_kernel(const float* chunkmax, const float* tilemax, float* sel_
             taken += take_eq;
             eq_left -= take_eq;
             if (i < ntiles && k < prefix) below = fmaxf(below, v);
+          }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) below = fmaxf(below, __shfl_xor_sync(0xffffffffu, below, o));

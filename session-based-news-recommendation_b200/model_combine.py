@@ -185,7 +185,10 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         self.eval_certify = os.environ.get("TCAR_EVAL_CERTIFY", "1") != "0"
         self.eval_two_stage = os.environ.get("TCAR_EVAL_TWO_STAGE", "1") != "0"
         self.eval_group_launch = os.environ.get("TCAR_EVAL_GROUP_LAUNCH", "1") != "0"
-        self.eval_warp_select = os.environ.get("TCAR_EVAL_WARP_SELECT", "1") != "0"
+        # single item range, <= 512 queries: the fused CTA-per-query kernel (121 us) beats warp-per-query selection +
+        # re-scoring (63 + 72 us: 512 warps cannot fill the GPU); the sharded rounds select for world x 512 queries per
+        # launch, where the warp kernel's time stays flat (tcar_eval_select_groups)
+        self.eval_warp_select = os.environ.get("TCAR_EVAL_WARP_SELECT", "0") != "0"
         self.train_parallel = "dp"
         self._item_table_synced = True
         mode = args.get("train_parallel") or "dp"
