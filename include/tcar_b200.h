@@ -187,6 +187,13 @@ int tcar_score_bwd_i_ctas(int n_pad);
  * sq_partial then holds the sums of squares of the ACCUMULATED values written by this call. */
 int tcar_score_bwd_i_acc(const void* e_bf16, const void* qs_bf16, float* g_item, float* sq_partial, int n_rows,
                          int n_items, int n_pad, int accumulate, void* stream);
+/* dItems of ALL present session groups in one launch (what tcar_score_bwd_i / tcar_score_bwd_i_groups run): the groups
+ * (E_g at e_bf16 + g * e_stride, Qs_g at qs_bf16 + g * qs_stride, n_rows[g] sessions, 0 = absent) are concatenated along
+ * the reduction dimension, the gradient of the item range is accumulated in TMEM and written ONCE through
+ * shared-memory staging + TMA stores (full 128-byte row segments).  groups <= TCAR_MAX_PEERS; sq_partial as above. */
+int tcar_score_bwd_i_multi(const void* e_bf16, long long e_stride, const void* qs_bf16, long long qs_stride,
+                           float* g_item, float* sq_partial, const int* n_rows, int groups, int n_items, int n_pad,
+                           void* stream);
 
 /* (5a) gradients of the seven small embedding tables (pos, month, day, week, hour, minute, duration): sums the
  *      gather-side, click-context-side and scoring-side contributions per table row in a fixed order, applies the
@@ -368,8 +375,9 @@ int tcar_peer_fetch_rows(const int32_t* seq, const int32_t* label, const int32_t
  *     bwd_q: tcar_score_bwd_q per group into dq + g * dq_stride; with rowsum_part != NULL the group's softmax partial
  *            sums (fixed-order sum over n_tiles, as tcar_ce_finish) are stored in the zero pad column 639 of its dQ
  *            rows, so that one reduce-scatter delivers dQ and sum exp to the sessions' rank.
- *     bwd_i: the first present group overwrites g_item, later ones accumulate (tcar_score_bwd_i_acc); sq_partial
- *            (nullable) is filled by the last group = sums of squares of the complete dense gradient.
+ *     bwd_i: one launch over all present groups (tcar_score_bwd_i_multi); sq_partial (nullable) = sums of squares of
+ *            the complete dense gradient.  (TCAR_BWDI_LEGACY=1: the first present group overwrites g_item, later ones
+ *            accumulate through tcar_score_bwd_i_acc.)
  *     scatter: tcar_scatter_add_rows_range per group; ids = packed batches [7*B*T idx | 2*B ctx | B label | B*Nn neg],
  *            payload = [a_ic 512x500 | coef 512 | dXi B*T x 256] floats; slot_sq (nullable): [groups][hash_size]. */
 int tcar_score_fwd_groups(const void* q_bf16, long long q_stride, const float* c_ref, long long c_stride,

@@ -45,6 +45,7 @@ SIGNATURES = {
     "tcar_score_bwd_finish": [_P] * 13 + [_I, _P],
     "tcar_score_bwd_i": [_P] * 4 + [_I, _I, _I, _P],
     "tcar_score_bwd_i_acc": [_P] * 4 + [_I, _I, _I, _I, _P],
+    "tcar_score_bwd_i_multi": [_P, _LL, _P, _LL, _P, _P, _P, _I, _I, _I, _P],
     "tcar_score_bwd_i_ctas": [_I],
     "tcar_sqnorm_combine": [_P, _I, _P, _I, _P, _P],
     "tcar_small_table_grads": [_P] * 23 + [_I, _I, _P],

@@ -152,7 +152,7 @@ class CatalogShardedTraining:
             raise nv.TcarNativeError(err or "another rank could not export / open the peer item tables")
 
     def close_peers(self):
-        for ptr, off in self._peer_opened:
+        for ptr, off in getattr(self, "_peer_opened", ()):     # data-parallel models never opened any
             nv.lib().tcar_peer_close(C.c_void_p(ptr), off)
         self._peer_opened = []
 

@@ -197,6 +197,12 @@ extern "C" int tcar_score_bwd_i_groups(const void* e_bf16, long long e_stride, c
                                        float* g_item, float* sq_partial, const int* n_rows, int groups, int n_items,
                                        int n_pad, void* stream) {
     if (!n_rows || groups < 1) return TCAR_ERR_ARG;
+    // all groups concatenated along K in ONE launch, the gradient written once (score_bwd_i_tma_kernel<MULTI>);
+    // TCAR_BWDI_LEGACY=1 keeps one launch per group with read-modify-write accumulation (A/B switch)
+    const char* legacy = getenv("TCAR_BWDI_LEGACY");
+    if (groups <= TCAR_MAX_PEERS && !(legacy && legacy[0] == '1'))
+        return tcar_score_bwd_i_multi(e_bf16, e_stride, qs_bf16, qs_stride, g_item, sq_partial, n_rows, groups, n_items,
+                                      n_pad, stream);
     int done = 0, last = -1;
     for (int g = 0; g < groups; ++g)
         if (n_rows[g] > 0) last = g;

@@ -1047,6 +1047,208 @@ score_bwd_i_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_const
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------ dItem, TMA-store epilogue
+// The kernel above writes the gradient with thread <-> item row: every warp store touches 32 rows (32 half-written
+// sectors), 4 096 sector requests per 128 x 128 tile against 1.5 us of MMA work -- the L1 store path, not HBM or the
+// tensor pipe, set its 171 us (DRAM 50 %, tensor pipe 28 %).  Here the epilogue stages [128 rows x 32 columns] fp32
+// blocks in shared memory (128-byte swizzle, conflict-free 16-byte stores) and one thread hands each block to the
+// TMA: full 128-byte row segments, no LSU traffic.  MULTI: the session groups of a catalog-sharded step are
+// concatenated along K (E and Qs blocks both streamed, 32 KB per stage), so that the gradient of the owned rows is
+// accumulated in TMEM and written ONCE instead of overwritten by the first group and re-read + re-written by the others.
+constexpr int I2_OUT = 2;
+constexpr int I2_OUT_BYTES = BM * 32 * 4;                      // 16384
+constexpr int I2_STAGES_ONE = 4;                               // single group: Qs half resident (128 KB) + E stages
+constexpr int I2_STAGES_MULTI = 6;                             // several groups: (E | Qs) stages
+constexpr int I2_SMEM_ONE = 8 * I_B_KB + I2_STAGES_ONE * I_A_STAGE + I2_OUT * I2_OUT_BYTES + 1024 + 256;
+constexpr int I2_SMEM_MULTI = I2_STAGES_MULTI * (I_A_STAGE + I_B_KB) + I2_OUT * I2_OUT_BYTES + 1024 + 256;
+
+struct BwdI2Params {
+    float* sq_partial;            // [gridDim.x] per-CTA sum of squares of the written gradient (nullable)
+    int n_items;
+    int n_tiles;                  // ceil(Npad / 128)
+    int groups;
+    int nkb[TCAR_MAX_PEERS];      // 64-session K blocks of every group (0 = absent group)
+};
+
+template <bool MULTI>
+__global__ void __launch_bounds__(kThreads, 1)
+score_bwd_i_tma_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_constant__ CUtensorMap map_qs,
+                       const __grid_constant__ CUtensorMap map_g, const __grid_constant__ BwdI2Params p) {
+    PDL_ENTER();
+    constexpr int STAGES = MULTI ? I2_STAGES_MULTI : I2_STAGES_ONE;
+    constexpr int STAGE_BYTES = MULTI ? I_A_STAGE + I_B_KB : I_A_STAGE;
+    __shared__ float sq_red[4];
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_b = smem;                                   // !MULTI: resident Qs half, nkb x 16 KB
+    uint8_t* smem_a = smem + (MULTI ? 0 : 8 * I_B_KB);        // stages
+    uint8_t* smem_o = smem_a + STAGES * STAGE_BYTES;          // output staging (1024-byte aligned)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_o + I2_OUT * I2_OUT_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* acc_full = bars + 2 * STAGES;
+    uint64_t* acc_empty = acc_full + I_NACC;
+    uint64_t* b_full = acc_empty + I_NACC;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t lane = lane_id();
+    const uint32_t chalf = blockIdx.x & 1;
+    const uint32_t tile0 = blockIdx.x >> 1;
+    const uint32_t tile_step = gridDim.x >> 1;
+    const uint32_t my_tiles =
+        tile0 < (uint32_t)p.n_tiles ? ((uint32_t)p.n_tiles - tile0 + tile_step - 1) / tile_step : 0u;
+    int kb_total = 0;                 // >= 1 (the host returns early when every group is absent)
+    for (int g = 0; g < p.groups; ++g) kb_total += p.nkb[g];
+
+    if (warp == 0 && elect_one()) {
+        tma_prefetch_desc(&map_e);
+        tma_prefetch_desc(&map_qs);
+        tma_prefetch_desc(&map_g);
+    }
+    if (warp == 1 && elect_one()) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 1);
+        }
+        for (int i = 0; i < I_NACC; ++i) {
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&acc_empty[i], 4);
+        }
+        mbar_init(b_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            if (!MULTI) {
+                mbar_expect_tx(b_full, p.nkb[0] * I_B_KB);
+                for (int kb = 0; kb < p.nkb[0]; ++kb)
+                    for (int j = 0; j < 2; ++j)
+                        tma_load_3d(smem_b + kb * I_B_KB + j * 8192, &map_qs, b_full, chalf * I_BN + j * 64, kb * BK, 0);
+            }
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t it = 0; it < my_tiles; ++it) {
+                const int n0 = (tile0 + it * tile_step) * BM;
+                for (int g = 0; g < p.groups; ++g) {
+                    for (int kb = 0; kb < p.nkb[g]; ++kb) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        mbar_expect_tx(&full[stage], STAGE_BYTES);
+                        uint8_t* sa = smem_a + stage * STAGE_BYTES;
+                        tma_load_4d(sa, &map_e, &full[stage], 0, kb * (BK / 8), n0 / 8, g);
+                        if (MULTI) {
+                            for (int j = 0; j < 2; ++j)
+                                tma_load_3d(sa + I_A_STAGE + j * 8192, &map_qs, &full[stage], chalf * I_BN + j * 64,
+                                            kb * BK, g);
+                        }
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc_bf16(BM, I_BN, 1, 1);
+        if (!MULTI) {
+            mbar_wait(b_full, 0);
+            tc_fence_after();
+        }
+        uint32_t stage = 0, phase = 0;
+        for (uint32_t it = 0; it < my_tiles; ++it) {
+            const uint32_t acc = it % I_NACC;
+            const uint32_t acc_phase = (it / I_NACC) & 1;
+            mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            int kidx = 0;
+            for (int g = 0; g < p.groups; ++g) {
+                const int nkb = p.nkb[g];
+                for (int kb = 0; kb < nkb; ++kb, ++kidx) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a_addr = smem_u32(smem_a + stage * STAGE_BYTES);
+                        const uint32_t b_addr = MULTI ? a_addr + I_A_STAGE : smem_u32(smem_b + kb * I_B_KB);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_bf16(tmem_base + acc * I_BN, make_sdesc_nosw(a_addr + k * 256, 128, 1024),
+                                      sdesc_mnmajor(b_addr + k * 2048, 8192), idesc, (kidx | k) != 0);
+                        umma_commit(&empty[stage]);
+                        if (kidx == kb_total - 1) umma_commit(&acc_full[acc]);
+                    }
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // thread <-> item row (TMEM lane); the 128 rows x 128 columns of a tile leave in four staged blocks
+        const uint32_t q = warp - 4;
+        const uint32_t r = q * 32 + lane;
+        const bool issuer = (q == 0 && lane == 0);
+        float sq = 0.f;
+        uint32_t chunk = 0;
+        for (uint32_t it = 0; it < my_tiles; ++it) {
+            const uint32_t acc = it % I_NACC;
+            const uint32_t acc_phase = (it / I_NACC) & 1;
+            const int n0 = (tile0 + it * tile_step) * BM;
+            const bool valid = n0 + (int)r < p.n_items;
+            mbar_wait(&acc_full[acc], acc_phase);
+            tc_fence_after();
+#pragma unroll 1
+            for (int ch = 0; ch < I_BN / 32; ++ch, ++chunk) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((q * 32) << 16) + acc * I_BN + ch * 32, v);
+                tmem_ld_wait();
+                uint8_t* ob = smem_o + (chunk & 1) * I2_OUT_BYTES;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    uint4 o = make_uint4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+                    const int c = chalf * I_BN + ch * 32 + g * 4;
+                    if (c + 0 >= TCAR_H) o.x = 0u;   // pad columns 250..255 carry no parameter
+                    if (c + 1 >= TCAR_H) o.y = 0u;
+                    if (c + 2 >= TCAR_H) o.z = 0u;
+                    if (c + 3 >= TCAR_H) o.w = 0u;
+                    // 128-byte swizzle: 16-byte piece g of row r lives at piece g ^ (r & 7)
+                    *reinterpret_cast<uint4*>(ob + r * 128 + ((g ^ (r & 7)) << 4)) = o;
+                    if (valid) {
+                        const float f0 = __uint_as_float(o.x), f1 = __uint_as_float(o.y);
+                        const float f2 = __uint_as_float(o.z), f3 = __uint_as_float(o.w);
+                        sq += (f0 * f0 + f1 * f1) + (f2 * f2 + f3 * f3);
+                    }
+                }
+                fence_proxy_async();
+                // the block staged two chunks ago used the other buffer; the one before this (same parity as the
+                // NEXT chunk) must have left shared memory before anybody passes the barrier
+                if (issuer) bulk_wait_read0();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (issuer) {
+                    // rows beyond the table (tail tile) are clipped by the tensor map; row 0 is the pad item
+                    tma_store_2d(&map_g, ob, chalf * I_BN + ch * 32, n0 + 1);
+                    bulk_commit();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        }
+        if (issuer) bulk_wait0();
+        // fixed-order reduction of the 128 per-thread sums of squares -> one partial per CTA
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (lane == 0) sq_red[q] = sq;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (issuer && p.sq_partial)
+            p.sq_partial[blockIdx.x] = (sq_red[0] + sq_red[1]) + (sq_red[2] + sq_red[3]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1452,8 +1654,42 @@ extern "C" int tcar_score_bwd_q_multi(const void* e_bf16, long long e_stride, co
     return (int)cudaGetLastError();
 }
 
+// Qs blocks of several session groups, `group_stride` bf16 elements apart: (feature column | session | group), SW128.
+static int make_map_qs3(CUtensorMap* m, const void* base, uint32_t groups, uint64_t group_stride) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return TCAR_ERR_DRIVER;
+    cuuint64_t dims[3] = {256, QROWS, groups};
+    cuuint64_t strides[2] = {256 * 2, group_stride * 2};
+    cuuint32_t box[3] = {64, BK, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : TCAR_ERR_TENSORMAP;
+}
+
+// Dense item gradient [rows, 256] fp32 as the destination of the staged [128 rows x 32 columns] blocks (SW128).
+static int make_map_g(CUtensorMap* m, float* base, uint64_t rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return TCAR_ERR_DRIVER;
+    cuuint64_t dims[2] = {256, rows};
+    cuuint64_t strides[1] = {256 * 4};
+    cuuint32_t box[2] = {32, BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : TCAR_ERR_TENSORMAP;
+}
+
 static int bwd_i_grid(int n_pad) {
     int grid = (sm_count() / 2) * 2;
+    // TCAR_BWD_I_CTAS=n: leave SMs free for the session-side backward running beside this GEMM (train_step's
+    // bwd_overlap); read per call so that one process can A/B it
+    const char* e = getenv("TCAR_BWD_I_CTAS");
+    if (e && e[0]) {
+        const int v = atoi(e) & ~1;
+        if (v >= 2 && v < grid) grid = v;
+    }
     const int n_tiles = n_pad / BM;
     if (grid > 2 * n_tiles) grid = 2 * n_tiles;
     return grid;
@@ -1466,10 +1702,69 @@ extern "C" int tcar_score_bwd_i(const void* e_bf16, const void* qs_bf16, float* 
     return tcar_score_bwd_i_acc(e_bf16, qs_bf16, g_item, sq_partial, n_rows, n_items, n_pad, 0, stream_);
 }
 
+// TCAR_BWDI_LEGACY=1 keeps the first kernel (thread <-> row stores, one launch per group): the A/B switch
+static bool bwd_i_legacy() {
+    const char* e = getenv("TCAR_BWDI_LEGACY");
+    return e && e[0] == '1';
+}
+
+extern "C" int tcar_score_bwd_i_multi(const void* e_bf16, long long e_stride, const void* qs_bf16, long long qs_stride,
+                                      float* g_item, float* sq_partial, const int* n_rows, int groups, int n_items,
+                                      int n_pad, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!n_rows || groups < 1 || groups > TCAR_MAX_PEERS || n_pad % 256 != 0 || n_items < 1 || n_items > n_pad)
+        return TCAR_ERR_ARG;
+    BwdI2Params p;
+    p.sq_partial = sq_partial;
+    p.n_items = n_items;
+    p.n_tiles = n_pad / BM;
+    p.groups = groups;
+    int present = 0, only = -1;
+    for (int g = 0; g < TCAR_MAX_PEERS; ++g) {
+        const int b = g < groups ? n_rows[g] : 0;
+        if (b < 0 || b > QROWS) return TCAR_ERR_ARG;
+        p.nkb[g] = (b + BK - 1) / BK;
+        if (b > 0) { ++present; only = g; }
+    }
+    if (present == 0) return 0;
+    const bool multi = present > 1;
+    const uint16_t* e0 = static_cast<const uint16_t*>(e_bf16);
+    const uint16_t* q0 = static_cast<const uint16_t*>(qs_bf16);
+    if (!multi) {              // one group: its Qs half stays resident, group index 0 of maps based at that group
+        e0 += (long long)only * e_stride;
+        q0 += (long long)only * qs_stride;
+        p.nkb[0] = p.nkb[only];
+        for (int g = 1; g < TCAR_MAX_PEERS; ++g) p.nkb[g] = 0;
+        p.groups = 1;
+    }
+    CUtensorMap me, mq, mg;
+    int rc = make_map_e4(&me, e0, n_pad, BK, BM / 8, multi ? groups : 1, multi ? (uint64_t)e_stride : (uint64_t)QROWS * n_pad);
+    if (rc) return rc;
+    rc = make_map_qs3(&mq, q0, multi ? groups : 1, multi ? (uint64_t)qs_stride : (uint64_t)QROWS * 256);
+    if (rc) return rc;
+    rc = make_map_g(&mg, g_item, (uint64_t)n_items + 1);
+    if (rc) return rc;
+    const int grid = bwd_i_grid(n_pad);
+    if (multi) {
+        cudaError_t e = cudaFuncSetAttribute(score_bwd_i_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             I2_SMEM_MULTI);
+        if (e != cudaSuccess) return (int)e;
+        launch_pdl(score_bwd_i_tma_kernel<true>, dim3(grid), dim3(kThreads), I2_SMEM_MULTI, stream, me, mq, mg, p);
+    } else {
+        cudaError_t e = cudaFuncSetAttribute(score_bwd_i_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             I2_SMEM_ONE);
+        if (e != cudaSuccess) return (int)e;
+        launch_pdl(score_bwd_i_tma_kernel<false>, dim3(grid), dim3(kThreads), I2_SMEM_ONE, stream, me, mq, mg, p);
+    }
+    return (int)cudaGetLastError();
+}
+
 extern "C" int tcar_score_bwd_i_acc(const void* e_bf16, const void* qs_bf16, float* g_item, float* sq_partial,
                                     int n_rows, int n_items, int n_pad, int accumulate, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (n_rows < 1 || n_rows > QROWS || n_pad % 256 != 0) return TCAR_ERR_ARG;
+    if (!accumulate && !bwd_i_legacy())
+        return tcar_score_bwd_i_multi(e_bf16, 0, qs_bf16, 0, g_item, sq_partial, &n_rows, 1, n_items, n_pad, stream_);
     CUtensorMap me, mq;
     int rc = make_map_e(&me, e_bf16, n_pad, BK, BM / 8);
     if (rc) return rc;

@@ -170,6 +170,8 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         # beside the main chain; joined by events, results do not depend on the interleaving (disjoint buffers)
         self._aux = torch.cuda.Stream(device=dev)
         self.branch_streams = os.environ.get("TCAR_BRANCH_STREAMS", "1") != "0"
+        # session-side backward beside the dense item-gradient GEMM (see backward()); A/B: tools/step_ab.py
+        self.bwd_overlap = os.environ.get("TCAR_BWD_OVERLAP", "0") == "1"
         self._la_events = None
         self._update_done = None           # event recorded on `_side` after the pending item update
         self._ahead_done = None            # event recorded on `_ahead` after the prefetched session forward
@@ -429,9 +431,25 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         nv.counted_call("tcar_score_bwd_finish", 1, p(self.dq_raw), p(self.sumexp), p(self.dA_neg), p(self.a_ic),
                         p(ps.ct_tab), p(ps.item), p(ps.content), p(ps.mwdhm), p(bt.label), p(self.d_a_ic),
                         p(self.d_a_pt), p(self.dTq), p(self.Qs), B)
-        nv.counted_call("tcar_score_bwd_i", 1, p(ws["E"]), p(self.Qs), p(ps.item_g), p(self.sq_partial), B, ps.N,
-                        ps.n_pad)
-        self._session_backward(bt)
+        if self.bwd_overlap and self.world == 1:
+            # the dense item gradient GEMM (HBM-bound, persistent CTAs) on the side stream, the session-side backward
+            # (a chain of short latency-bound kernels that only needs d a_ic / d a_pt / dTq) beside it on this stream;
+            # TCAR_BWD_I_CTAS < 148 leaves whole SMs to the chain's GEMMs (the persistent CTAs own all shared memory)
+            main = torch.cuda.current_stream()
+            fork = torch.cuda.Event()
+            fork.record(main)
+            self._side.wait_event(fork)
+            with torch.cuda.stream(self._side):
+                nv.counted_call("tcar_score_bwd_i", 1, p(ws["E"]), p(self.Qs), p(ps.item_g), p(self.sq_partial), B,
+                                ps.N, ps.n_pad)
+                join = torch.cuda.Event()
+                join.record(self._side)
+            self._session_backward(bt)
+            main.wait_event(join)
+        else:
+            nv.counted_call("tcar_score_bwd_i", 1, p(ws["E"]), p(self.Qs), p(ps.item_g), p(self.sq_partial), B, ps.N,
+                            ps.n_pad)
+            self._session_backward(bt)
         if scatter:
             self._scatter_item_grads(bt)
 

@@ -133,6 +133,31 @@ def test_score_bwd_i(native, B, N):
     assert abs(float(sqp.double().sum()) - want) <= 1e-5 * want
 
 
+@pytest.mark.parametrize("B,N", [(512, 5000), (77, 2333)])
+def test_score_bwd_i_tma_epilogue_equals_the_row_store_kernel(native, B, N, monkeypatch):
+    """The staged TMA-store epilogue (default) and the first kernel (thread <-> row stores, TCAR_BWDI_LEGACY=1) run the
+    same MMAs in the same order: gradient and per-CTA sums of squares bit-identical; rows beyond the table untouched."""
+    g = torch.Generator(device="cuda").manual_seed(B + N)
+    n_pad = (N + 255) // 256 * 256
+    E = torch.zeros(QROWS, n_pad, device="cuda", dtype=torch.bfloat16)
+    E[:B, :N] = torch.rand(B, N, device="cuda", generator=g).bfloat16()
+    Qs = torch.zeros(QROWS, 256, device="cuda", dtype=torch.bfloat16)
+    Qs[:B, :250] = (torch.randn(B, 250, device="cuda", generator=g) * 0.2).bfloat16()
+    Eb = e_to_blocked(E)
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("TCAR_BWDI_LEGACY", mode)
+        gi = torch.full((N + 1 + 300, 256), 7.0, device="cuda")          # 300 guard rows behind the table
+        sqp = torch.zeros(native.lib().tcar_score_bwd_i_ctas(n_pad), device="cuda")
+        native.call("tcar_score_bwd_i", native.ptr(Eb), native.ptr(Qs), native.ptr(gi), native.ptr(sqp), B, N, n_pad)
+        torch.cuda.synchronize()
+        out[mode] = (gi, sqp)
+    monkeypatch.delenv("TCAR_BWDI_LEGACY")
+    assert torch.equal(out["0"][0][1: N + 1], out["1"][0][1: N + 1])
+    assert torch.equal(out["0"][1], out["1"][1])
+    assert (out["0"][0][0] == 7.0).all() and (out["0"][0][N + 1:] == 7.0).all()
+
+
 # ------------------------------------------------------------------------------------------- session groups (catalog-sharded step)
 @pytest.mark.parametrize("counts,N", [([512, 512], 5000), ([300, 0, 512, 77], 2333), ([512] * 8, 3000), ([1, 5], 300)])
 def test_score_groups_match_single_group_calls(native, counts, N, monkeypatch):

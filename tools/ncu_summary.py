@@ -1,7 +1,8 @@
 """Summarise an `ncu --set full` report of `bench.py --profile_region` into profiles/: per-launch time, DRAM traffic,
 DRAM / tensor-pipe utilisation, registers -> <out>.json + <out>.md, and the per-kernel DRAM traffic table
 profiles/traffic.json that bench.py copies into `roofline.traffic` / `kernels[*].traffic`.
-usage: python tools/ncu_summary.py gpurun_out/prof_step.ncu-rep [gpurun_out/prof_bwd_q.ncu-rep] --out profiles/r1_f_ncu_full"""
+usage: python tools/ncu_summary.py gpurun_out/prof_step_raw.csv [gpurun_out/prof_bwd_q_raw.csv] --out profiles/r2_a_ncu_full
+(.ncu-rep files are accepted too)"""
 import argparse, csv, io, json, os, subprocess
 
 ap = argparse.ArgumentParser()
@@ -17,7 +18,10 @@ COLS = {"time_us": "gpu__time_duration.sum", "dram_read": "dram__bytes_read.sum"
 SCALE = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 rows_out = []
 for rep in a.reports:
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):           # raw page exported on the GPU box (a full-set .ncu-rep exceeds gpurun's 64 MiB)
+        txt = open(rep).read()
+    else:
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
