@@ -59,6 +59,7 @@ struct FwdParams {
     int e_pitch;            // Npad
     int groups;             // number of session groups (ceil(ceil(B/128)/CL))
     int mode;               // 0 = train, 1 = eval
+    int prefetch;           // pair kernel: L2 prefetch distance of the streamed item operand in stages (0 = off)
 };
 
 // exponent shift of one session row in log2 units: the label score, plus -- in pass 2 of the overflow guard -- the
@@ -282,17 +283,25 @@ constexpr int P_NACC = 2;
 constexpr int P_B_STAGE = P_HALF * BK * 2;      // 16384
 constexpr int P_SMEM = F_A_BYTES + P_STAGES * P_B_STAGE + 1024 /*align*/ + 256 /*barriers*/;
 
-template <int MODE>
-__device__ __forceinline__ void fwd_epilogue_chunk(const uint32_t (&v)[32], const FwdParams& p, float cshift,
-                                                   bool row_ok, bool store_ok, bool tail, uint32_t row, int nb,
-                                                   float& psum, float& tmax, float& amax) {
+// TAIL = false: every item of the chunk exists (all tiles but the last one or two) -- no per-element bounds logic, which
+// was half of the epilogue's instructions (2 ISETP + 2 PLOP3 + FSEL per element beside FFMA / MUFU / FMNMX / FADD).
+template <int MODE, bool TAIL>
+__device__ __forceinline__ void fwd_epilogue_chunk_t(const uint32_t (&v)[32], const FwdParams& p, float cshift,
+                                                     bool row_ok, bool store_ok, uint32_t row, int nb,
+                                                     float& psum, float& tmax, float& amax) {
+    constexpr bool tail = TAIL;
     float e[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
         const float arg = fmaf(__uint_as_float(v[j]), kLog2e, -cshift);
         float ex = ex2_approx(arg);
-        if (!row_ok || (tail && nb + j >= p.n_items)) ex = 0.f;
-        else if (MODE == 0) amax = fmaxf(amax, arg);     // eval mode derives it from tmax (monotone map)
+        if (TAIL) {
+            if (!row_ok || nb + j >= p.n_items) ex = 0.f;
+            else if (MODE == 0) amax = fmaxf(amax, arg);     // eval mode derives it from tmax (monotone map)
+        } else {
+            ex = row_ok ? ex : 0.f;
+            if (MODE == 0) amax = fmaxf(amax, arg);          // rows beyond the batch never store it
+        }
         e[j] = ex;
         psum += ex;
     }
@@ -327,6 +336,14 @@ __device__ __forceinline__ void fwd_epilogue_chunk(const uint32_t (&v)[32], cons
         }
         if (row_ok) *reinterpret_cast<float4*>(p.chunkmax + (size_t)row * (p.e_pitch / 8) + nb / 8) = m;
     }
+}
+
+template <int MODE>
+__device__ __forceinline__ void fwd_epilogue_chunk(const uint32_t (&v)[32], const FwdParams& p, float cshift,
+                                                   bool row_ok, bool store_ok, bool tail, uint32_t row, int nb,
+                                                   float& psum, float& tmax, float& amax) {
+    if (tail) fwd_epilogue_chunk_t<MODE, true>(v, p, cshift, row_ok, store_ok, row, nb, psum, tmax, amax);
+    else fwd_epilogue_chunk_t<MODE, false>(v, p, cshift, row_ok, store_ok, row, nb, psum, tmax, amax);
 }
 
 template <int MODE>
@@ -389,9 +406,20 @@ score_fwd_pair_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             for (int kb = 0; kb < NKB; ++kb)
                 tma_load_2d_pair(smem_a + kb * (BM * BK * 2), &map_q, a_full_l, kb * BK, mtile * BM);
             uint32_t stage = 0, phase = 0;
+            // L2 prefetch `pf` stages ahead of the loads (same boxes, same order)
+            const uint32_t pf = (uint32_t)p.prefetch, total = my_tiles * NKB;
+            auto prefetch_stage = [&](uint32_t s) {
+                if (s < total) {
+                    const uint32_t pit = s / NKB, pkb = s - pit * NKB;
+                    tma_prefetch_2d(&map_i, pkb * BK, (tile0 + pit * tile_step) * P_BN + rank * P_HALF);
+                }
+            };
+            for (uint32_t s = 0; s < pf; ++s) prefetch_stage(s);
+            uint32_t sidx = 0;
             for (uint32_t it = 0; it < my_tiles; ++it) {
                 const int n0 = (tile0 + it * tile_step) * P_BN + rank * P_HALF;
-                for (int kb = 0; kb < NKB; ++kb) {
+                for (int kb = 0; kb < NKB; ++kb, ++sidx) {
+                    if (pf) prefetch_stage(sidx + pf);
                     mbar_wait(&empty[stage], phase ^ 1);
                     if (rank == 0) mbar_expect_tx(&full[stage], 2 * P_B_STAGE);
                     tma_load_2d_pair(smem_b + stage * P_B_STAGE, &map_i, mapa_u32(&full[stage], 0), kb * BK, n0);
@@ -498,6 +526,7 @@ struct FwdMultiParams {
     const float* rowmax;       // group g at rowmax + g * rm_stride (nullable: pass 1)
     long long e_stride, part_stride, c_stride, rm_stride;
     int n_items, n_tiles, e_pitch, n_rb;
+    int prefetch;              // L2 prefetch distance of the streamed item operand in stages (0 = off)
     unsigned char rb_group[M_MAX_RB], rb_block[M_MAX_RB];
     short rb_rows[M_MAX_RB];   // sessions of the row block's GROUP
 };
@@ -575,6 +604,14 @@ score_fwd_multi_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             const uint32_t a_full_l = mapa_u32(a_full, 0);
             uint32_t stage = 0, phase = 0, qe_par = 0;
             int cur_rb = -1;
+            // L2 prefetch `pf` stages ahead over the flattened (unit, K block) sequence of this pair
+            const uint32_t pf = (uint32_t)p.prefetch;
+            auto prefetch_stage = [&](uint32_t flat) {
+                const uint32_t pu = u0 + flat / NKB, pkb = flat % NKB;
+                if (pu < u1 && s_need[pu / p.n_tiles])
+                    tma_prefetch_2d(&map_i, pkb * BK, (pu % p.n_tiles) * P_BN + rank * P_HALF);
+            };
+            for (uint32_t f = 0; f < pf; ++f) prefetch_stage(f);
             for (uint32_t u = u0; u < u1; ++u) {
                 const int rb = u / p.n_tiles, tile = u % p.n_tiles;
                 if (!s_need[rb]) continue;
@@ -591,6 +628,7 @@ score_fwd_multi_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
                 }
                 const int n0 = tile * P_BN + rank * P_HALF;
                 for (int kb = 0; kb < NKB; ++kb) {
+                    if (pf) prefetch_stage((u - u0) * NKB + kb + pf);
                     mbar_wait(&empty[stage], phase ^ 1);
                     if (rank == 0) mbar_expect_tx(&full[stage], 2 * P_B_STAGE);
                     tma_load_2d_pair(smem_b + stage * P_B_STAGE, &map_i, mapa_u32(&full[stage], 0), kb * BK, n0);
@@ -748,6 +786,7 @@ struct BwdQParams {
     int splits;
     int mtiles;      // m-tiles of 128 session rows, over all groups
     int rows_total;  // rows of one split's partial: 512 (one group) or groups x 512
+    int prefetch;    // L2 prefetch distance of both streamed operands in stages (0 = off)
     unsigned char grp[Q_MAX_MTILES];   // MULTI: session group and m-tile inside the group of every global m-tile
     unsigned char lmt[Q_MAX_MTILES];
 };
@@ -803,7 +842,18 @@ score_bwd_q_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_const
     if (warp == 0) {
         if (elect_one()) {
             uint32_t stage = 0, phase = 0;
+            const int pf = p.prefetch;
+            auto prefetch_stage = [&](int kb) {
+                if (kb < kb1) {
+                    if (MULTI) tma_prefetch_4d(&map_e, 0, mtile * (BM / 8), kb * (BK / 8), grp);
+                    else tma_prefetch_3d(&map_e, 0, mtile * (BM / 8), kb * (BK / 8));
+#pragma unroll
+                    for (int j = 0; j < Q_CH / 64; ++j) tma_prefetch_2d(&map_i, chalf * Q_CH + j * 64, kb * BK);
+                }
+            };
+            for (int kb = kb0; kb < kb0 + pf; ++kb) prefetch_stage(kb);
             for (int kb = kb0; kb < kb1; ++kb) {
+                if (pf) prefetch_stage(kb + pf);
                 mbar_wait(&empty[stage], phase ^ 1);
                 mbar_expect_tx(&full[stage], Q_STAGE);
                 uint8_t* sa = smem + stage * Q_STAGE;
@@ -1067,6 +1117,7 @@ struct BwdI2Params {
     int n_items;
     int n_tiles;                  // ceil(Npad / 128)
     int groups;
+    int prefetch;                 // L2 prefetch distance of the streamed E tiles in stages (0 = off)
     int nkb[TCAR_MAX_PEERS];      // 64-session K blocks of every group (0 = absent group)
 };
 
@@ -1133,10 +1184,26 @@ score_bwd_i_tma_kernel(const __grid_constant__ CUtensorMap map_e, const __grid_c
                         tma_load_3d(smem_b + kb * I_B_KB + j * 8192, &map_qs, b_full, chalf * I_BN + j * 64, kb * BK, 0);
             }
             uint32_t stage = 0, phase = 0;
+            // L2 prefetch of the E boxes `pf` stages ahead: a second cursor (tile, group, K block) runs in front
+            const int pf = p.prefetch;
+            uint32_t p_it = 0;
+            int p_g = 0, p_kb = 0;
+            auto prefetch_next = [&]() {
+                while (p_it < my_tiles && p_kb >= p.nkb[p_g]) {
+                    p_kb = 0;
+                    if (++p_g == p.groups) { p_g = 0; ++p_it; }
+                }
+                if (p_it < my_tiles) {
+                    tma_prefetch_4d(&map_e, 0, p_kb * (BK / 8), (int)((tile0 + p_it * tile_step) * BM) / 8, p_g);
+                    ++p_kb;
+                }
+            };
+            for (int s = 0; s < pf; ++s) prefetch_next();
             for (uint32_t it = 0; it < my_tiles; ++it) {
                 const int n0 = (tile0 + it * tile_step) * BM;
                 for (int g = 0; g < p.groups; ++g) {
                     for (int kb = 0; kb < p.nkb[g]; ++kb) {
+                        if (pf) prefetch_next();
                         mbar_wait(&empty[stage], phase ^ 1);
                         mbar_expect_tx(&full[stage], STAGE_BYTES);
                         uint8_t* sa = smem_a + stage * STAGE_BYTES;
@@ -1339,6 +1406,18 @@ static int sm_count() {
     return n;
 }
 
+// L2 prefetch distance (stages) of the streamed GEMM operands; TCAR_TMA_PREFETCH_<FWD|BWDQ|BWDI>=n, else
+// TCAR_TMA_PREFETCH=n, overrides the default (0 = off); read per call so that one process can A/B it
+static int tma_prefetch_depth(int dflt, const char* which) {
+    const char* e = getenv(which);
+    if (!(e && e[0])) e = getenv("TCAR_TMA_PREFETCH");
+    if (e && e[0]) {
+        const int v = atoi(e);
+        return v < 0 ? 0 : (v > 64 ? 64 : v);
+    }
+    return dflt;
+}
+
 template <int CL>
 static int launch_fwd(const CUtensorMap& mq, const CUtensorMap& mi, const FwdParams& p, int n_clusters,
                       cudaStream_t stream) {
@@ -1431,6 +1510,7 @@ extern "C" int tcar_score_fwd_guarded(const void* q_bf16, const void* iext_bf16,
         const int mtiles = (n_rows + BM - 1) / BM;
         p.groups = (mtiles + 1) / 2;
         p.mode = mode;
+        p.prefetch = tma_prefetch_depth(12, "TCAR_TMA_PREFETCH_FWD");
         int n_pairs = ((sm_count() / 2) / p.groups) * p.groups;
         if (n_pairs < p.groups) n_pairs = p.groups;
         if (n_pairs / p.groups > p.n_tiles) n_pairs = p.n_tiles * p.groups;
@@ -1453,6 +1533,7 @@ extern "C" int tcar_score_fwd_guarded(const void* q_bf16, const void* iext_bf16,
     const int mtiles = (n_rows + BM - 1) / BM;
     p.groups = (mtiles + cluster - 1) / cluster;
     p.mode = mode;
+    p.prefetch = 0;
     // cluster size 4 can only be co-scheduled on 132 of the 148 SMs (GPCs with 18 SMs strand two)
     int max_clusters = sm_count() / cluster;
     if (cluster == 4) max_clusters = (sm_count() * 132 / 148) / 4;
@@ -1540,6 +1621,7 @@ static int score_fwd_multi_impl(const void* q_bf16, long long q_stride, const fl
     p.n_tiles = n_pad / P_BN;
     p.e_pitch = n_pad;
     p.n_rb = nrb;
+    p.prefetch = tma_prefetch_depth(12, "TCAR_TMA_PREFETCH_FWD");
     int n_pairs = sm_count() / 2;
     if ((long long)n_pairs > (long long)nrb * p.n_tiles) n_pairs = nrb * p.n_tiles;
     const bool eval_mode = e_out == nullptr;
@@ -1590,6 +1672,7 @@ extern "C" int tcar_score_bwd_q(const void* e_bf16, const void* iext_bf16, float
     p.part = part;
     p.mtiles = (n_rows + BM - 1) / BM;
     p.splits = tcar_score_bwd_q_splits(n_rows, n_pad);
+    p.prefetch = tma_prefetch_depth(0, "TCAR_TMA_PREFETCH_BWDQ");
     p.kb_total = n_pad / BK;
     p.kb_per = (p.kb_total + p.splits - 1) / p.splits;
     p.rows_total = QROWS;
@@ -1642,6 +1725,7 @@ extern "C" int tcar_score_bwd_q_multi(const void* e_bf16, long long e_stride, co
     if (splits > p.kb_total) splits = p.kb_total;
     if (splits < 1) splits = 1;
     p.splits = splits;
+    p.prefetch = tma_prefetch_depth(0, "TCAR_TMA_PREFETCH_BWDQ");
     p.kb_per = (p.kb_total + splits - 1) / splits;
     p.rows_total = groups * QROWS;
     cudaError_t e = cudaFuncSetAttribute(score_bwd_q_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM);
@@ -1719,6 +1803,7 @@ extern "C" int tcar_score_bwd_i_multi(const void* e_bf16, long long e_stride, co
     p.n_items = n_items;
     p.n_tiles = n_pad / BM;
     p.groups = groups;
+    p.prefetch = tma_prefetch_depth(8, "TCAR_TMA_PREFETCH_BWDI");
     int present = 0, only = -1;
     for (int g = 0; g < TCAR_MAX_PEERS; ++g) {
         const int b = g < groups ? n_rows[g] : 0;

@@ -1,7 +1,8 @@
 """A/B of train-step variants on ONE GPU inside one process (same clocks, same batches): GPU ms/step of the
 kernel-resident loop with the look-ahead, for
+  * the L2 prefetch distance of the streamed GEMM operands (TCAR_TMA_PREFETCH),
   * the dense item-gradient GEMM: TMA-store epilogue (default) vs the first kernel (TCAR_BWDI_LEGACY=1),
-  * the session-side backward beside that GEMM (Seq2SeqAttNN.bwd_overlap) with 148 / fewer persistent CTAs
+  * the session-side backward beside that GEMM (Seq2SeqAttNN.bwd_overlap) with fewer persistent CTAs
     (TCAR_BWD_I_CTAS).
 Both switches are read per call, so one model serves every variant.
 
@@ -60,23 +61,63 @@ def main():
             best = ms if best is None else min(best, ms)
         return best
 
-    variants = [("legacy bwd_i", "1", False, None), ("tma bwd_i", "0", False, None),
-                ("tma + overlap, 148 CTAs", "0", True, None), ("tma + overlap, 140 CTAs", "0", True, 140),
-                ("tma + overlap, 132 CTAs", "0", True, 132), ("tma + overlap, 124 CTAs", "0", True, 124),
-                ("tma + overlap, 116 CTAs", "0", True, 116), ("tma, 132 CTAs, no overlap", "0", False, 132),
-                ("legacy + overlap, 132 CTAs", "1", True, 132), ("tma bwd_i (again)", "0", False, None)]
-    for name, legacy, overlap, ctas in variants:
-        os.environ["TCAR_BWDI_LEGACY"] = legacy
-        if ctas is None:
-            os.environ.pop("TCAR_BWD_I_CTAS", None)
-        else:
-            os.environ["TCAR_BWD_I_CTAS"] = str(ctas)
-        model.bwd_overlap = overlap
-        out = {"variant": name}
-        for key, dev in sets.items():
-            out[key + "_ms"] = round(time_loop(dev), 4)
-        out["loss"] = float(model.loss[:B].mean().item())
-        print("step_ab " + json.dumps(out), flush=True)
+    # (name, environment overrides read per call by the library, bwd_overlap)
+    F, Q, I = "TCAR_TMA_PREFETCH_FWD", "TCAR_TMA_PREFETCH_BWDQ", "TCAR_TMA_PREFETCH_BWDI"
+    variants = [("prefetch off", {F: "0", Q: "0", I: "0"}, False),
+                ("fwd 12", {F: "12", Q: "0", I: "0"}, False),
+                ("fwd 6", {F: "6", Q: "0", I: "0"}, False),
+                ("bwd_i 8", {F: "0", Q: "0", I: "8"}, False),
+                ("bwd_i 4", {F: "0", Q: "0", I: "4"}, False),
+                ("bwd_q 8", {F: "0", Q: "8", I: "0"}, False),
+                ("bwd_q 2", {F: "0", Q: "2", I: "0"}, False),
+                ("fwd 12 + bwd_i 8", {F: "12", Q: "0", I: "8"}, False),
+                ("fwd 6 + bwd_i 4", {F: "6", Q: "0", I: "4"}, False),
+                ("default", {}, False),
+                ("prefetch off, legacy bwd_i", {F: "0", Q: "0", I: "0", "TCAR_BWDI_LEGACY": "1"}, False)]
+    keys = (F, Q, I, "TCAR_TMA_PREFETCH", "TCAR_BWDI_LEGACY", "TCAR_BWD_I_CTAS")
+    res = {}
+    for rnd in range(2):                       # two rounds over all variants: clock / thermal drift shows up as a spread
+        for name, env, overlap in variants:
+            for k in keys:
+                os.environ.pop(k, None)
+            os.environ.update(env)
+            model.bwd_overlap = overlap
+            for key, dev in sets.items():
+                res.setdefault(name, {}).setdefault(key, []).append(round(time_loop(dev), 4))
+    for k in keys:
+        os.environ.pop(k, None)
+    for name, _, _ in variants:
+        print("step_ab " + json.dumps({"variant": name, **{k + "_ms": v for k, v in res[name].items()}}), flush=True)
+
+    # the three scoring GEMMs alone (L2 flushed before every launch, as bench.py's `kernels` pass), per prefetch distance
+    from bench import time_kernel
+    from tcar_b200 import _native as nv
+    ps, p = model.ps, nv.ptr
+    bt = sets["T20"][0]
+    model.sync_updates()
+    model.forward_train(bt)
+    model.backward(bt)
+    torch.cuda.synchronize()
+    ws = model._score_buffers(ps.n_pad, True)
+    wse = model._score_buffers(ps.n_pad, False)
+    cl = model._cluster_for(B)
+    flush = torch.zeros(64 * 1024 * 1024, device=model.dev, dtype=torch.int32)
+    calls = {
+        "score_fwd_train": lambda: nv.call("tcar_score_fwd", p(model.Q), p(ps.iext), p(model.c_ref), p(ws["E"]),
+                                           p(ws["part"]), None, None, B, N, ps.n_pad, 0, cl),
+        "score_fwd_eval": lambda: nv.call("tcar_score_fwd", p(model.Q), p(ps.iext), p(model.c_ref), None, p(wse["part"]),
+                                          p(wse["cmax"]), p(wse["tmax"]), B, N, ps.n_pad, 1, cl),
+        "score_bwd_q": lambda: nv.call("tcar_score_bwd_q", p(ws["E"]), p(ps.iext), p(ws["qpart"]), p(model.dq_raw), B,
+                                       ps.n_pad),
+        "score_bwd_i": lambda: nv.call("tcar_score_bwd_i", p(ws["E"]), p(model.Qs), p(ps.item_g), p(model.sq_partial), B,
+                                       N, ps.n_pad)}
+    for pf in ("0", "4", "8", "12", "16", "24", "40"):
+        os.environ["TCAR_TMA_PREFETCH"] = pf
+        out = {"prefetch": int(pf)}
+        for name, fn in calls.items():
+            out[name + "_us"] = round(time_kernel(torch, fn, 10, flush) * 1e3, 1)
+        print("kernel_ab " + json.dumps(out), flush=True)
+    os.environ.pop("TCAR_TMA_PREFETCH", None)
 
 
 if __name__ == "__main__":
