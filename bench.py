@@ -375,6 +375,8 @@ def multi_gpu_parity(torch, dist, synth, Model, margs, model, mwdhm, rank, world
     loss_m = multi.train_step(bt).clone()
     multi.sync_updates()
     multi.sync_item_table()
+    if getattr(multi, "sync_optimizer_state", None):
+        multi.sync_optimizer_state()      # data-parallel sharded update: every rank holds the moments of its own rows only
     btf = single.to_device(torch.from_numpy(packed).pin_memory(), Bg, T, Nn)
     loss_s = single.train_step(btf).clone()
     single.sync_updates()
@@ -406,7 +408,8 @@ def multi_gpu_parity(torch, dist, synth, Model, margs, model, mwdhm, rank, world
     res["round_top20_equal"] = bool(torch.equal(top_r, top_s))
     res["round_rank_equal"] = bool(torch.equal(hit, ngt_r < 20) and torch.equal(ngt_r[hit], ngt_s[hit]))
     res["eval_ce_maxabs"] = max(res["eval_ce_maxabs"], float((ce_r - ce_s).abs().max()))
-    ok = (res["loss_maxabs"] < 1e-4 and res["theta_rel"] < 1e-4 and res["item_rel"] < 1e-4 and res["eval_top20_equal"]
+    ok = (res["loss_maxabs"] < 1e-4 and res["theta_rel"] < 1e-4 and res["item_rel"] < 1e-4
+          and res["item_moment_rel"] < 1e-3 and res["eval_top20_equal"]
           and res["eval_rank_equal"] and res["round_top20_equal"] and res["round_rank_equal"]
           and res["eval_ce_maxabs"] < 1e-3)
     flag = torch.tensor([1 if ok else 0], device=model.dev, dtype=torch.int32)

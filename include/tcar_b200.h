@@ -160,9 +160,12 @@ int tcar_ce_finish_guarded(const float* rowsum_part, const float* rowmax_part, f
 int tcar_rowsum_finish(const float* rowsum_part, float* out, int out_stride, int n_tiles, int B, void* stream);
 
 /* (4b) negative-feedback loss (model_combine.py:142-143,147): neg[b] = -log(1 - sigmoid(sum_j I_ic[neg_bj].a_ic[b])
- *      + 1e-24); loss[b] = ce[b] + 0.01 neg[b]; coef[b] = 0.01 d neg/d z; dA_neg[b,500] = coef[b] sum_j I_ic[neg_bj]. */
+ *      + 1e-24); loss[b] = ce[b] + 0.01 neg[b]; coef[b] = 0.01 d neg/d z; dA_neg[b,500] = coef[b] sum_j I_ic[neg_bj].
+ *      ce == NULL: loss is not written (the kernel needs none of the scoring GEMM's results and may run beside it);
+ *      tcar_loss_combine writes loss[b] = ce[b] + 0.01 negloss[b] once the cross loss is known. */
 int tcar_neg_loss(const float* a_ic, const float* item, const float* content, const int32_t* neg, const float* ce,
                   float* negloss, float* loss, float* coef, float* dA_neg, int B, int Nn, void* stream);
+int tcar_loss_combine(const float* ce, const float* negloss, float* loss, int B, void* stream);
 
 /* (3d) scoring backward wrt the query operand: dq_raw [512,640] = E . Iext (split-K partials in `part`,
  *      [tcar_score_bwd_q_splits()][512][640], reduced in fixed order). */

@@ -416,7 +416,7 @@ static int make_map_f32(CUtensorMap* m, const void* base, uint64_t rows, uint64_
     cuuint64_t strides[1] = {pitch_elems * 4};
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = tmap_encode_cached(fn, m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE,
                     mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -544,10 +544,9 @@ extern "C" int tcar_gemm_tf32_group(const tcar_gemm_problem* probs, int nprob, v
         grp.cta_start[g] = ctas;
         grp.red_start[g] = red;
     }
-    cudaError_t e = cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
-    if (e != cudaSuccess) return (int)e;
+    TCAR_SET_SMEM_ONCE(gemm_tf32_kernel, G_SMEM);
     launch_pdl(gemm_tf32_kernel, dim3(ctas), dim3(G_THREADS), G_SMEM, stream, grp);
-    e = cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     if (any_split) {
         launch_pdl(gemm_reduce_splits_kernel, dim3(red), dim3(256), 0, stream, grp);

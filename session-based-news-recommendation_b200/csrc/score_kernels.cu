@@ -1343,7 +1343,7 @@ static int make_map_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64
     cuuint64_t strides[1] = {pitch_elems * 2};
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = tmap_encode_cached(fn, m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : TCAR_ERR_TENSORMAP;
@@ -1361,7 +1361,7 @@ static int make_map_e(CUtensorMap* m, const void* base, uint64_t n_pad, uint32_t
     cuuint64_t strides[2] = {128, (cuuint64_t)QROWS * 16};
     cuuint32_t box[3] = {64, box_rows / 8, box_blocks};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = tmap_encode_cached(fn, m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : TCAR_ERR_TENSORMAP;
@@ -1376,7 +1376,7 @@ static int make_map_e4(CUtensorMap* m, const void* base, uint64_t n_pad, uint32_
     cuuint64_t strides[3] = {128, (cuuint64_t)QROWS * 16, group_stride * 2};
     cuuint32_t box[4] = {64, box_rows / 8, box_blocks, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = tmap_encode_cached(fn, m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : TCAR_ERR_TENSORMAP;
@@ -1390,7 +1390,7 @@ static int make_map_q3(CUtensorMap* m, const void* base, uint32_t groups, uint64
     cuuint64_t strides[2] = {KEXT * 2, group_stride * 2};
     cuuint32_t box[3] = {BK, BM, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = tmap_encode_cached(fn, m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : TCAR_ERR_TENSORMAP;
@@ -1421,8 +1421,7 @@ static int tma_prefetch_depth(int dflt, const char* which) {
 template <int CL>
 static int launch_fwd(const CUtensorMap& mq, const CUtensorMap& mi, const FwdParams& p, int n_clusters,
                       cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(score_fwd_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM);
-    if (e != cudaSuccess) return (int)e;
+    TCAR_SET_SMEM_ONCE(score_fwd_kernel<CL>, F_SMEM);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(n_clusters * CL);
     cfg.blockDim = dim3(kThreads);
@@ -1440,16 +1439,14 @@ static int launch_fwd(const CUtensorMap& mq, const CUtensorMap& mi, const FwdPar
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.numAttrs = 2;
 #endif
-    e = cudaLaunchKernelEx(&cfg, score_fwd_kernel<CL>, mq, mi, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, score_fwd_kernel<CL>, mq, mi, p);
     return (int)e;
 }
 
 template <int MODE>
 static int launch_fwd_pair(const CUtensorMap& mq, const CUtensorMap& mi, const FwdParams& p, int n_pairs,
                            cudaStream_t stream) {
-    cudaError_t e =
-        cudaFuncSetAttribute(score_fwd_pair_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
-    if (e != cudaSuccess) return (int)e;
+    TCAR_SET_SMEM_ONCE(score_fwd_pair_kernel<MODE>, P_SMEM);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(n_pairs * 2);
     cfg.blockDim = dim3(P_THREADS);
@@ -1625,10 +1622,8 @@ static int score_fwd_multi_impl(const void* q_bf16, long long q_stride, const fl
     int n_pairs = sm_count() / 2;
     if ((long long)n_pairs > (long long)nrb * p.n_tiles) n_pairs = nrb * p.n_tiles;
     const bool eval_mode = e_out == nullptr;
-    cudaError_t e = eval_mode
-        ? cudaFuncSetAttribute(score_fwd_multi_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM)
-        : cudaFuncSetAttribute(score_fwd_multi_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM);
-    if (e != cudaSuccess) return (int)e;
+    if (eval_mode) TCAR_SET_SMEM_ONCE(score_fwd_multi_kernel<1>, P_SMEM);
+    else TCAR_SET_SMEM_ONCE(score_fwd_multi_kernel<0>, P_SMEM);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(n_pairs * 2);
     cfg.blockDim = dim3(P_THREADS);
@@ -1676,10 +1671,9 @@ extern "C" int tcar_score_bwd_q(const void* e_bf16, const void* iext_bf16, float
     p.kb_total = n_pad / BK;
     p.kb_per = (p.kb_total + p.splits - 1) / p.splits;
     p.rows_total = QROWS;
-    cudaError_t e = cudaFuncSetAttribute(score_bwd_q_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM);
-    if (e != cudaSuccess) return (int)e;
+    TCAR_SET_SMEM_ONCE(score_bwd_q_kernel<false>, Q_SMEM);
     launch_pdl(score_bwd_q_kernel<false>, dim3(p.splits * p.mtiles * 2), dim3(kThreads), Q_SMEM, stream, me, mi, p);
-    e = cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     // partial layout is [split][512][640]; rows of m-tiles that were not computed are never read by callers
     const int total = p.mtiles * BM * KEXT;
@@ -1728,10 +1722,9 @@ extern "C" int tcar_score_bwd_q_multi(const void* e_bf16, long long e_stride, co
     p.prefetch = tma_prefetch_depth(0, "TCAR_TMA_PREFETCH_BWDQ");
     p.kb_per = (p.kb_total + splits - 1) / splits;
     p.rows_total = groups * QROWS;
-    cudaError_t e = cudaFuncSetAttribute(score_bwd_q_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM);
-    if (e != cudaSuccess) return (int)e;
+    TCAR_SET_SMEM_ONCE(score_bwd_q_kernel<true>, Q_SMEM);
     launch_pdl(score_bwd_q_kernel<true>, dim3(splits * mt * 2), dim3(kThreads), Q_SMEM, stream, me, mi, p);
-    e = cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;
     const int total = groups * QROWS * KEXT;
     launch_pdl(reduce_splits_kernel, dim3((total + 255) / 256), dim3(256), 0, stream, part, dq, splits, total, total);
@@ -1746,7 +1739,7 @@ static int make_map_qs3(CUtensorMap* m, const void* base, uint32_t groups, uint6
     cuuint64_t strides[2] = {256 * 2, group_stride * 2};
     cuuint32_t box[3] = {64, BK, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = tmap_encode_cached(fn, m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : TCAR_ERR_TENSORMAP;
@@ -1760,7 +1753,7 @@ static int make_map_g(CUtensorMap* m, float* base, uint64_t rows) {
     cuuint64_t strides[1] = {256 * 4};
     cuuint32_t box[2] = {32, BM};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = tmap_encode_cached(fn, m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : TCAR_ERR_TENSORMAP;
 }
@@ -1831,14 +1824,10 @@ extern "C" int tcar_score_bwd_i_multi(const void* e_bf16, long long e_stride, co
     if (rc) return rc;
     const int grid = bwd_i_grid(n_pad);
     if (multi) {
-        cudaError_t e = cudaFuncSetAttribute(score_bwd_i_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             I2_SMEM_MULTI);
-        if (e != cudaSuccess) return (int)e;
+        TCAR_SET_SMEM_ONCE(score_bwd_i_tma_kernel<true>, I2_SMEM_MULTI);
         launch_pdl(score_bwd_i_tma_kernel<true>, dim3(grid), dim3(kThreads), I2_SMEM_MULTI, stream, me, mq, mg, p);
     } else {
-        cudaError_t e = cudaFuncSetAttribute(score_bwd_i_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             I2_SMEM_ONE);
-        if (e != cudaSuccess) return (int)e;
+        TCAR_SET_SMEM_ONCE(score_bwd_i_tma_kernel<false>, I2_SMEM_ONE);
         launch_pdl(score_bwd_i_tma_kernel<false>, dim3(grid), dim3(kThreads), I2_SMEM_ONE, stream, me, mq, mg, p);
     }
     return (int)cudaGetLastError();
@@ -1862,8 +1851,7 @@ extern "C" int tcar_score_bwd_i_acc(const void* e_bf16, const void* qs_bf16, flo
     p.n_tiles = n_pad / BM;
     p.nkb = (n_rows + BK - 1) / BK;
     p.accumulate = accumulate;
-    cudaError_t e = cudaFuncSetAttribute(score_bwd_i_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I_SMEM);
-    if (e != cudaSuccess) return (int)e;
+    TCAR_SET_SMEM_ONCE(score_bwd_i_kernel, I_SMEM);
     const int grid = bwd_i_grid(n_pad);
     launch_pdl(score_bwd_i_kernel, dim3(grid), dim3(kThreads), I_SMEM, stream, me, mq, p);
     return (int)cudaGetLastError();

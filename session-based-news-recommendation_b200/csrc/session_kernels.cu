@@ -521,8 +521,9 @@ build_query_kernel(const float* __restrict__ a_ic, const float* __restrict__ a_p
 }
 
 // ------------------------------------------------------------------------------------------------ (4a) CE finish
-// 16 rows per CTA (half-warp = 16 consecutive rows of one partial, the two half-warps take alternate partials), 32 warps
-// stride over the partials with 8 independent loads in flight per thread, fixed combine order.
+// 8 rows per CTA (a quarter-warp = 8 consecutive rows = one 32-byte sector of a partial, the four quarter-warps take
+// consecutive partials), 32 warps stride over the partials with 8 independent loads in flight per thread, fixed combine
+// order.  (16 rows per CTA left 116 of the 148 SMs idle: 17 us for 23 MB of partials at B = 512.)
 //
 // Overflow guard of the softmax (TF's sparse_softmax_cross_entropy_with_logits subtracts the row maximum,
 // model_combine.py:145; the scoring kernel shifts by the label score):
@@ -542,7 +543,7 @@ ce_finish_kernel(const float* __restrict__ part, const float* __restrict__ pmax,
     PDL_ENTER();
     __shared__ float s[32][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int b = blockIdx.x * 16 + (lane & 15);
+    const int b = blockIdx.x * 8 + (lane & 7);
     if (gridDim.y > 1 || gr.part_stride) {
         // several session groups in one launch: group g's partials lie part_stride floats apart, its row maxima go
         // to rowmax + g * 512
@@ -551,7 +552,7 @@ ce_finish_kernel(const float* __restrict__ part, const float* __restrict__ pmax,
         if (pmax) pmax += (size_t)blockIdx.y * gr.part_stride;
         if (sumexp) sumexp += (size_t)blockIdx.y * gr.out_stride;
         if (rowmax) rowmax += (size_t)blockIdx.y * gr.out_stride;
-        if ((int)blockIdx.x * 16 >= B) return;
+        if ((int)blockIdx.x * 8 >= B) return;
     }
     bool redo = false;
     if (pass == 2) {
@@ -565,39 +566,40 @@ ce_finish_kernel(const float* __restrict__ part, const float* __restrict__ pmax,
         for (int k = 0; k < 8; ++k) a[k] = 0.f;
         if (b < B) {
             const float* src = part + b;
-            int t = 2 * w + (lane >> 4);
-            for (; t + 7 * 64 < n_tiles; t += 8 * 64) {
+            int t = 4 * w + (lane >> 3);
+            for (; t + 7 * 128 < n_tiles; t += 8 * 128) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) a[k] += src[(size_t)(t + 64 * k) * TCAR_QROWS];
+                for (int k = 0; k < 8; ++k) a[k] += src[(size_t)(t + 128 * k) * TCAR_QROWS];
             }
-            for (; t < n_tiles; t += 64) a[0] += src[(size_t)t * TCAR_QROWS];
+            for (; t < n_tiles; t += 128) a[0] += src[(size_t)t * TCAR_QROWS];
         }
         s[w][lane] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
         __syncthreads();
-        if (w == 0 && lane < 16)
-            for (int i = 0; i < 32; ++i) tot += s[i][lane] + s[i][lane + 16];
+        if (w == 0 && lane < 8)
+            for (int i = 0; i < 32; ++i) tot += (s[i][lane] + s[i][lane + 8]) + (s[i][lane + 16] + s[i][lane + 24]);
         __syncthreads();
     }
     if (pass == 1 || pass == 3) {
         float m[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         if (b < B) {
             const float* src = pmax + b;
-            int t = 2 * w + (lane >> 4);
-            for (; t + 3 * 64 < n_tiles; t += 4 * 64) {
+            int t = 4 * w + (lane >> 3);
+            for (; t + 3 * 128 < n_tiles; t += 4 * 128) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) m[k] = fmaxf(m[k], src[(size_t)(t + 64 * k) * TCAR_QROWS]);
+                for (int k = 0; k < 4; ++k) m[k] = fmaxf(m[k], src[(size_t)(t + 128 * k) * TCAR_QROWS]);
             }
-            for (; t < n_tiles; t += 64) m[0] = fmaxf(m[0], src[(size_t)t * TCAR_QROWS]);
+            for (; t < n_tiles; t += 128) m[0] = fmaxf(m[0], src[(size_t)t * TCAR_QROWS]);
         }
         s[w][lane] = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
         __syncthreads();
-        if (w == 0 && lane < 16 && b < B) {
+        if (w == 0 && lane < 8 && b < B) {
             float mx = -INFINITY;
-            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fmaxf(s[i][lane], s[i][lane + 16]));
+            for (int i = 0; i < 32; ++i)
+                mx = fmaxf(mx, fmaxf(fmaxf(s[i][lane], s[i][lane + 8]), fmaxf(s[i][lane + 16], s[i][lane + 24])));
             rowmax[b] = mx;
         }
     }
-    if (pass != 3 && w == 0 && lane < 16 && b < B && (pass != 2 || redo)) {
+    if (pass != 3 && w == 0 && lane < 8 && b < B && (pass != 2 || redo)) {
         sumexp[(size_t)b * sum_stride] = tot;
         if (ce) ce[b] = pass == 2 ? fmaf(rowmax[b], 0.6931471805599453f, logf(tot)) : logf(tot);
     }
@@ -676,22 +678,29 @@ col_jobs_kernel(const __grid_constant__ ColJobs jobs) {
 }
 
 // ------------------------------------------------------------------------------------------------ (4b) neg loss
+// ce == NULL: the cross loss is not known yet (the kernel runs beside the scoring GEMM, see Seq2SeqAttNN.forward_train);
+// loss[] is then left to tcar_loss_combine.  No shared memory beyond the reduction scratch (the two columns a thread owns
+// stay in registers), so that a CTA fits beside a scoring-GEMM CTA that holds all but 1.7 KB of the SM's shared memory.
 __global__ void __launch_bounds__(256)
 neg_loss_kernel(const float* __restrict__ a_ic, const float* __restrict__ item, const float* __restrict__ content,
                 const int32_t* __restrict__ neg, const float* __restrict__ ce, float* __restrict__ negloss,
                 float* __restrict__ loss, float* __restrict__ coef, float* __restrict__ dA_neg, int B, int Nn) {
     PDL_ENTER();
-    __shared__ float s_v[XW];
     __shared__ float red[32];
     const int b = blockIdx.x;
     float partial = 0.f;
-    for (int c = threadIdx.x; c < XW; c += blockDim.x) {
-        const float* tab = c < H ? item : content;
-        const int cc = c < H ? c : c - H;
-        float v = 0.f;
-        for (int j = 0; j < Nn; ++j) v += tab[((size_t)neg[(size_t)b * Nn + j] + 1) * HP + cc];
-        s_v[c] = v;
-        partial = fmaf(v, a_ic[(size_t)b * XW + c], partial);
+    float sv[2] = {0.f, 0.f};                       // columns threadIdx.x and threadIdx.x + 256 (XW = 500 <= 512)
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int c = threadIdx.x + k * 256;
+        if (c < XW) {
+            const float* tab = c < H ? item : content;
+            const int cc = c < H ? c : c - H;
+            float v = 0.f;
+            for (int j = 0; j < Nn; ++j) v += tab[((size_t)neg[(size_t)b * Nn + j] + 1) * HP + cc];
+            sv[k] = v;
+            partial = fmaf(v, a_ic[(size_t)b * XW + c], partial);
+        }
     }
     const float z = block_sum(partial, red);
     const float s = 1.f / (1.f + expf(-z));
@@ -700,10 +709,22 @@ neg_loss_kernel(const float* __restrict__ a_ic, const float* __restrict__ item, 
     if (threadIdx.x == 0) {
         const float nl = -logf(u);
         negloss[b] = nl;
-        loss[b] = ce[b] + 0.01f * nl;
+        if (ce) loss[b] = ce[b] + 0.01f * nl;
         coef[b] = cf;
     }
-    for (int c = threadIdx.x; c < XW; c += blockDim.x) dA_neg[(size_t)b * XW + c] = cf * s_v[c];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int c = threadIdx.x + k * 256;
+        if (c < XW) dA_neg[(size_t)b * XW + c] = cf * sv[k];
+    }
+}
+
+// loss = cross loss + 0.01 * negative-feedback loss (model_combine.py:146-147), for tcar_neg_loss(ce = NULL)
+__global__ void __launch_bounds__(256)
+loss_combine_kernel(const float* __restrict__ ce, const float* __restrict__ negloss, float* __restrict__ loss, int B) {
+    PDL_ENTER();
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) loss[b] = ce[b] + 0.01f * negloss[b];
 }
 
 // ------------------------------------------------------------------------------------------------ (3e) finish
@@ -1175,7 +1196,7 @@ extern "C" int tcar_ce_finish_guarded(const float* rowsum_part, const float* row
     if ((pass == 1 || pass == 3) && (!rowmax_part || !rowmax)) return TCAR_ERR_ARG;
     if (pass == 2 && !rowmax) return TCAR_ERR_ARG;
     if (pass != 3 && (!rowsum_part || !sumexp)) return TCAR_ERR_ARG;
-    launch_pdl(ce_finish_kernel, dim3((B + 15) / 16), dim3(1024), 0, STREAM, rowsum_part, rowmax_part, sumexp, ce,
+    launch_pdl(ce_finish_kernel, dim3((B + 7) / 8), dim3(1024), 0, STREAM, rowsum_part, rowmax_part, sumexp, ce,
                rowmax, n_tiles, B, 1, pass, GroupRows{});
     return LAUNCH_RC();
 }
@@ -1194,7 +1215,7 @@ extern "C" int tcar_rowmax_groups(const float* rowmax_part, long long part_strid
     if (bmax == 0) return 0;
     gr.part_stride = part_stride;
     gr.out_stride = TCAR_QROWS;
-    launch_pdl(ce_finish_kernel, dim3((bmax + 15) / 16, groups), dim3(1024), 0, STREAM,
+    launch_pdl(ce_finish_kernel, dim3((bmax + 7) / 8, groups), dim3(1024), 0, STREAM,
                static_cast<const float*>(nullptr), rowmax_part, static_cast<float*>(nullptr),
                static_cast<float*>(nullptr), rowmax, n_tiles, bmax, 1, 3, gr);
     return LAUNCH_RC();
@@ -1219,7 +1240,7 @@ extern "C" int tcar_ce_finish_groups(const float* rowsum_part, const float* rowm
     if (bmax == 0) return 0;
     gr.part_stride = part_stride;
     gr.out_stride = out_stride;
-    launch_pdl(ce_finish_kernel, dim3((bmax + 15) / 16, groups), dim3(1024), 0, STREAM, rowsum_part, rowmax_part,
+    launch_pdl(ce_finish_kernel, dim3((bmax + 7) / 8, groups), dim3(1024), 0, STREAM, rowsum_part, rowmax_part,
                sumexp, static_cast<float*>(nullptr), rowmax, n_tiles, bmax, 1, pass, gr);
     return LAUNCH_RC();
 }
@@ -1227,7 +1248,7 @@ extern "C" int tcar_ce_finish_groups(const float* rowsum_part, const float* rowm
 extern "C" int tcar_rowsum_finish(const float* rowsum_part, float* out, int out_stride, int n_tiles, int B,
                                   void* stream) {
     if (B < 1 || B > TCAR_QROWS || out_stride < 1 || !out) return TCAR_ERR_ARG;
-    launch_pdl(ce_finish_kernel, dim3((B + 15) / 16), dim3(1024), 0, STREAM, rowsum_part,
+    launch_pdl(ce_finish_kernel, dim3((B + 7) / 8), dim3(1024), 0, STREAM, rowsum_part,
                static_cast<const float*>(nullptr), out, static_cast<float*>(nullptr), static_cast<float*>(nullptr),
                n_tiles, B, out_stride, 0, GroupRows{});
     return LAUNCH_RC();
@@ -1266,6 +1287,12 @@ extern "C" int tcar_neg_loss(const float* a_ic, const float* item, const float* 
                              void* stream) {
     if (B < 1 || Nn < 0) return TCAR_ERR_ARG;
     launch_pdl(neg_loss_kernel, dim3(B), dim3(256), 0, STREAM, a_ic, item, content, neg, ce, negloss, loss, coef, dA_neg, B, Nn);
+    return LAUNCH_RC();
+}
+
+extern "C" int tcar_loss_combine(const float* ce, const float* negloss, float* loss, int B, void* stream) {
+    if (B < 1 || !ce || !negloss || !loss) return TCAR_ERR_ARG;
+    launch_pdl(loss_combine_kernel, dim3((B + 255) / 256), dim3(256), 0, STREAM, ce, negloss, loss, B);
     return LAUNCH_RC();
 }
 

@@ -171,7 +171,7 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         self._aux = torch.cuda.Stream(device=dev)
         self.branch_streams = os.environ.get("TCAR_BRANCH_STREAMS", "1") != "0"
         # session-side backward beside the dense item-gradient GEMM (see backward()); A/B: tools/step_ab.py
-        self.bwd_overlap = os.environ.get("TCAR_BWD_OVERLAP", "0") == "1"
+        self.bwd_overlap = os.environ.get("TCAR_BWD_OVERLAP", "1") != "0"
         self._la_events = None
         self._update_done = None           # event recorded on `_side` after the pending item update
         self._ahead_done = None            # event recorded on `_ahead` after the prefetched session forward
@@ -334,10 +334,10 @@ class Seq2SeqAttNN(CatalogShardedTraining):
             cur.wait_event(self._ahead_done)
             self._ahead_done = None
 
-    def _session_forward(self, bt, prefetch=False):
+    def _session_forward(self, bt, prefetch=False, query=True):
         """Everything up to a_ic / a_pt / Q: model_combine.py:52-127.  With prefetch=True the caller guarantees that
         the rows of the item table this batch reads (clicks, labels) are already up to date, so the pending table-wide
-        update is NOT waited for."""
+        update is NOT waited for.  query=False stops after a_ic / a_pt (the caller runs _session_query later)."""
         if not prefetch:
             self.sync_updates()
             self._prefetched = None
@@ -366,6 +366,14 @@ class Seq2SeqAttNN(CatalogShardedTraining):
                precise=True),
             pr([(self.pooled_t, PW, 0, wh["W_p"], wl["W_p"], 320, 1, PW)], B, PW, self.a_pt, PW, bias=w["b_p"], act=2,
                precise=True)])
+        if not query:
+            return
+        self._session_query(bt)
+
+    def _session_query(self, bt):
+        """Second half of the session forward: Tq, the bf16 session operand Q and the exact label scores c_ref (the
+        buffers the scoring GEMM and its overflow-guard pass read)."""
+        ps, w, p, B = self.ps, self.ps.w, nv.ptr, bt.B
         nv.counted_call("tcar_clip_time_tables", 1, p(w["month"]), p(w["day"]), p(w["week"]), p(w["hour"]),
                         p(w["minute"]), p(ps.ct_tab), p(ps.ct_scale))
         nv.counted_call("tcar_build_query", 1, p(self.a_ic), p(self.a_pt), p(ps.ct_tab), p(ps.item), p(ps.content),
@@ -393,13 +401,32 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         else:
             self._session_forward(bt)
         ws = self._score_buffers(ps.n_pad, True)
-        self._score_and_sum(ws, ps.iext, p(ws["E"]), None, None, B, ps.N, ps.n_pad, 0)
-        nv.counted_call("tcar_neg_loss", 1, p(self.a_ic), p(ps.item), p(ps.content), p(bt.neg), p(self.ce),
-                        p(self.negloss), p(self.loss), p(self.coef), p(self.dA_neg), B, bt.Nn)
+        if self.branch_streams and self.world == 1:
+            # the negative-feedback term needs a_ic and item rows only: beside the scoring GEMM on the auxiliary stream
+            # (its CTAs use no shared memory to speak of, so they fit next to the GEMM's), off the critical path
+            main = torch.cuda.current_stream()
+            ev = torch.cuda.Event()
+            ev.record(main)
+
+            def neg_side():
+                self._aux.wait_event(ev)
+                with torch.cuda.stream(self._aux):
+                    nv.counted_call("tcar_neg_loss", 1, p(self.a_ic), p(ps.item), p(ps.content), p(bt.neg), None,
+                                    p(self.negloss), p(self.loss), p(self.coef), p(self.dA_neg), B, bt.Nn)
+                    self._neg_done = torch.cuda.Event()
+                    self._neg_done.record(self._aux)
+
+            self._score_and_sum(ws, ps.iext, p(ws["E"]), None, None, B, ps.N, ps.n_pad, 0, after_gemm=neg_side)
+            main.wait_event(self._neg_done)
+            nv.counted_call("tcar_loss_combine", 1, p(self.ce), p(self.negloss), p(self.loss), B)
+        else:
+            self._score_and_sum(ws, ps.iext, p(ws["E"]), None, None, B, ps.N, ps.n_pad, 0)
+            nv.counted_call("tcar_neg_loss", 1, p(self.a_ic), p(ps.item), p(ps.content), p(bt.neg), p(self.ce),
+                            p(self.negloss), p(self.loss), p(self.coef), p(self.dA_neg), B, bt.Nn)
         return self.loss[:B], self.ce[:B]
 
     def _score_and_sum(self, ws, iext, e_ptr, cmax_ptr, tmax_ptr, B, n_items, n_pad, mode, q=None, c=None, sumexp=None,
-                       ce=None, rowmax=None):
+                       ce=None, rowmax=None, after_gemm=None):
         """Scoring GEMM + softmax sums: E / chunk maxima, sumexp, ce = logsumexp(S) - S[label], with the overflow
         guard (pass 2 is two empty launches unless a row's best score beats the label by > 55 nats).  q / c / sumexp /
         ce / rowmax default to this model's own buffers (another rank's queries in the sharded evaluation)."""
@@ -410,6 +437,8 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         if not self.softmax_guard:
             nv.counted_call("tcar_score_fwd", 1, q, p(iext), c, e_ptr, part, cmax_ptr, tmax_ptr, B, n_items, n_pad,
                             mode, cl)
+            if after_gemm is not None:
+                after_gemm()
             nv.counted_call("tcar_ce_finish", 1, part, sumexp, ce, ws["tiles"], B)
             if mode == 1:
                 rowmax_t[:B].zero_()       # result blocks carry the shift: none here
@@ -417,6 +446,8 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         pmax, rowmax = p(ws["pmax"]), p(rowmax_t)
         nv.counted_call("tcar_score_fwd_guarded", 1, q, p(iext), c, e_ptr, part, cmax_ptr, tmax_ptr, pmax, None, B,
                         n_items, n_pad, mode, cl)
+        if after_gemm is not None:
+            after_gemm()           # pass 2 below still reads q / c: the hook must not let anything overwrite them
         nv.counted_call("tcar_ce_finish_guarded", 1, part, pmax, sumexp, ce, rowmax, ws["tiles"], B, 1)
         nv.counted_call("tcar_score_fwd_guarded", 1, q, p(iext), c, e_ptr, part, cmax_ptr, tmax_ptr, None, rowmax, B,
                         n_items, n_pad, mode, cl)
@@ -703,16 +734,40 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         return loss
 
     # ------------------------------------------------------------------------------------------- evaluation
-    def _prefetch_forward(self, next_bt):
-        """Launch next_bt's session forward on the high-priority stream behind everything queued so far."""
+    def _etrace(self, name, stream=None):
+        """Timing mark for tools/eval_probe.py (self._eval_trace = [] switches it on)."""
+        tr = getattr(self, "_eval_trace", None)
+        if tr is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream if stream is not None else torch.cuda.current_stream())
+            tr.append((name, ev))
+
+    def _prefetch_forward(self, next_bt, query=True):
+        """Launch next_bt's session forward on the high-priority stream behind everything queued so far.  query=False:
+        everything but the last two kernels (_prefetch_query launches those behind a later point of this stream)."""
         main = torch.cuda.current_stream()
         fork = torch.cuda.Event()
         fork.record(main)
         self._ahead.wait_event(fork)
         with torch.cuda.stream(self._ahead):
-            self._session_forward(next_bt, prefetch=True)
+            self._session_forward(next_bt, prefetch=True, query=query)
             adone = torch.cuda.Event()
             adone.record(self._ahead)
+            self._etrace("ahead: session forward" + ("" if query else " (first half)"))
+        self._ahead_done = adone
+        self._prefetched = next_bt if query else None
+
+    def _prefetch_query(self, next_bt):
+        """Second half of a _prefetch_forward(next_bt, query=False): ordered behind everything queued so far."""
+        main = torch.cuda.current_stream()
+        fork = torch.cuda.Event()
+        fork.record(main)
+        self._ahead.wait_event(fork)
+        with torch.cuda.stream(self._ahead):
+            self._session_query(next_bt)
+            adone = torch.cuda.Event()
+            adone.record(self._ahead)
+            self._etrace("ahead: query")
         self._ahead_done = adone
         self._prefetched = next_bt
 
@@ -724,6 +779,7 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         ps, p, B = self.ps, nv.ptr, bt.B
         if not self._item_table_synced:
             self.sync_item_table()         # after catalog-sharded training every rank holds only its own rows
+        self._etrace("begin")
         if self._prefetched is bt:
             self._prefetched = None
             self.sync_updates()
@@ -745,17 +801,22 @@ class Seq2SeqAttNN(CatalogShardedTraining):
         else:
             self._ensure_cat_stats()
             ws = self._score_buffers(n_pad, False)
-            self._score_and_sum(ws, iext, None, p(ws["cmax"]), p(ws["tmax"]), B, n_loc, n_pad, 1)
             a_ic, Tq = self.a_ic, self.Tq
+            self._etrace("session forward (or wait for the prefetched one)")
+            self._score_and_sum(ws, iext, None, p(ws["cmax"]), p(ws["tmax"]), B, n_loc, n_pad, 1)
+            self._etrace("scoring GEMM + softmax sums + guard")
             if ahead:
                 # the exact re-scoring below reads this batch's session vectors: park them before next_bt's forward
-                # overwrites the live buffers
+                # overwrites the live buffers.  (Starting that forward right behind the GEMM, beside the softmax sums,
+                # was measured and bought nothing: the window between two GEMMs is set by the top-20 selection +
+                # widening, 180 us in situ, not by the 130 us session forward -- tools/eval_probe.py.)
                 self.a_ic_eval[:B].copy_(self.a_ic[:B])
                 self.Tq_eval[:B].copy_(self.Tq[:B])
                 a_ic, Tq = self.a_ic_eval, self.Tq_eval
                 self._prefetch_forward(next_bt)
                 ahead = False
             self._topk(ws, a_ic, Tq, bt.label, self._evblock, B, n_loc, n_pad, lo)
+            self._etrace("top-20")
         if ahead:
             self._prefetch_forward(next_bt)
         if shard is not None and parallel.is_distributed(self.world):
@@ -798,6 +859,7 @@ class Seq2SeqAttNN(CatalogShardedTraining):
             nv.counted_call("tcar_eval_topk_certified", 1, p(ws["cmax"]), p(ws["tmax"]), p(a_ic), p(Tq), p(ps.item),
                             p(ps.content), p(ps.mwdhm), p(label), ids, sc, ngt, B, n_loc, n_pad, lo, p(self.cat_stats),
                             p(self.uncertain), p(self.tau))
+        self._etrace("top-20: certified selection")
         nv.counted_call("tcar_eval_topk_widen", 2, p(ws["cmax"]), p(ws["tmax"]), p(a_ic), p(Tq), p(ps.item),
                         p(ps.content), p(ps.mwdhm), p(label), p(self.uncertain), p(self.tau), ids, sc, ngt, B, n_loc,
                         n_pad, lo, p(self.widen_ws))
