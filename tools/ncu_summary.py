@@ -54,7 +54,8 @@ traffic = {}
 for k, name in MAP.items():
     if name is None:
         continue
-    hit = [d for d in rows_out if d["kernel"] == name and d["dram_read"] is not None]
+    names = {"score_bwd_i_kernel": ("score_bwd_i_tma_kernel<0>", "score_bwd_i_tma_kernel<false>", "score_bwd_i_kernel")}.get(name, (name,))
+    hit = [d for d in rows_out if d["kernel"] in names and d["dram_read"] is not None]
     traffic[k] = (hit[0]["dram_read"] + hit[0]["dram_write"]) if hit else None
 sc = [d for d in rows_out if d["kernel"].startswith("scatter_") and d["dram_read"] is not None]
 if sc:
