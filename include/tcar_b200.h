@@ -405,6 +405,15 @@ int tcar_scatter_add_rows_groups(const int32_t* ids, long long ids_stride, const
                                  int32_t* hash_cnt, long long* hash_acc, int32_t* entry_slot, float* slot_sq,
                                  int hash_size, const int* n_rows, int groups, int T, int Nn, int row_lo, int row_hi,
                                  void* stream);
+/* The same scatter-add for ALL groups against one hash table in three launches (count over every group first, so
+ * "touched once" is a global property; shared rows add up in order-independent fixed point): hash_size >= 2 x the
+ * entries of all groups together, entry_slot >= groups x (largest group's entries) words, slot_sq ONE block of
+ * hash_size floats (nullable).  Same arguments otherwise; TCAR_ERR_ARG when the table is too small. */
+int tcar_scatter_add_rows_multi(const int32_t* ids, long long ids_stride, const float* payload,
+                                long long payload_stride, const float* item, float* g_item, int32_t* hash_keys,
+                                int32_t* hash_cnt, long long* hash_acc, int32_t* entry_slot, float* slot_sq,
+                                int hash_size, const int* n_rows, int groups, int T, int Nn, int row_lo, int row_hi,
+                                void* stream);
 
 /* Softmax overflow guard for the session groups of a catalog-sharded step (see tcar_score_fwd_guarded):
  *   tcar_score_fwd_groups_guarded(..., rowmax_part, NULL, ...)     pass 1, also leaves per-block exponent maxima
@@ -472,9 +481,10 @@ int tcar_eval_rescore(const float* sel_vals, const int32_t* sel_ids, int lists, 
                       const int32_t* label, int32_t* top_ids, float* top_scores, int32_t* n_greater, int B, int N_total,
                       const float* cat_stats, int32_t* uncertain, float* tau, void* stream);
 /* Second stage: for every flagged query, re-scores ALL chunks whose maximum reaches tau[b] (any number of them -- in
- * the limit a full exact scan, so the work of one query is spread over TCAR_WIDEN_SPLITS CTAs and their partial lists
- * are merged by a second launch) and rewrites its top_ids / top_scores / n_greater; certified queries are untouched
- * (their CTAs return).  workspace: tcar_eval_topk_widen_ws_bytes(1) bytes (x groups for the _groups form). */
+ * the limit a full exact scan, so the work of one query is spread over TCAR_WIDEN_SPLITS CTAs; the CTA that finishes
+ * last merges their partial lists) and rewrites its top_ids / top_scores / n_greater; certified queries are untouched
+ * (their CTAs return).  workspace: tcar_eval_topk_widen_ws_bytes(1) bytes (x groups for the _groups form), ZERO before
+ * the first call (it ends with one ticket counter per query, which every call leaves at zero again). */
 long long tcar_eval_topk_widen_ws_bytes(int groups);
 int tcar_eval_topk_widen(const float* chunkmax, const float* tilemax, const float* a_ic, const float* Tq,
                          const float* item, const float* content, const int32_t* mwdhm, const int32_t* label,

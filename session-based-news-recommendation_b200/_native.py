@@ -76,6 +76,7 @@ SIGNATURES = {
     "tcar_score_bwd_q_groups": [_P, _LL, _P, _P, _P, _LL, _P, _LL, _I, _P, _I, _I, _P],
     "tcar_score_bwd_i_groups": [_P, _LL, _P, _LL, _P, _P, _P, _I, _I, _I, _P],
     "tcar_scatter_add_rows_groups": [_P, _LL, _P, _LL, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P],
+    "tcar_scatter_add_rows_multi": [_P, _LL, _P, _LL, _P, _P, _P, _P, _P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P],
     "tcar_sqnorm_segments": [_P] * 3 + [_I, _P],
     "tcar_sqnorm_big": [_P] * 3 + [_LL, _P],
     "tcar_update_norms": [_P, _P, _P, _I, _P, _I, _P, _I, _P, _P, _P, _P, _P],

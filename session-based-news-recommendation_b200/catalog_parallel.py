@@ -78,6 +78,7 @@ class CatalogShardedTraining:
         # gathered one step early into the second buffer pair
         import os
         self.cat_lookahead = os.environ.get("TCAR_CATALOG_LOOKAHEAD", "0") == "1"
+        self._scatter_merged = os.environ.get("TCAR_SCATTER_LOOP", "0") != "1"
         self._ids_n = torch.zeros(1, device=dev, dtype=torch.int32)
         self._ids_all_n = torch.zeros(1, device=dev, dtype=torch.int32)
         self._cat_pre = None               # {"bt", "counts", "L"} of the batch whose ids / rows / forward are ahead
@@ -314,15 +315,21 @@ class CatalogShardedTraining:
                             p(ps.item_g_full[sh["lo"]:]), p(sh["sqp"]), cnt, R, sh["hi"] - sh["lo"], sh["n_pad"])
         mark("score_bwd_i")
         # ---- the sparse rows (clicks, labels, negatives) of every rank's sessions that fall into the owned ranges
-        self._alloc_scatter(Bmax * T + Bmax + Bmax * Nn)
-        if self._slot_sq_g is None or self._slot_sq_g.numel() != R * self.hash_size:
-            self._slot_sq_g = torch.zeros(R * self.hash_size, device=self.dev)
+        # all source ranks against ONE hash table (tcar_scatter_add_rows_multi: three launches per step instead of
+        # three per source rank); TCAR_SCATTER_LOOP=1 keeps the per-rank passes (A/B switch)
+        merged = self._scatter_merged and ng > 1
+        ent = Bmax * T + Bmax + Bmax * Nn
+        self._alloc_scatter(R * ent if merged else ent)
+        nsq = self.hash_size if merged else R * self.hash_size
+        if self._slot_sq_g is None or self._slot_sq_g.numel() != nsq:
+            self._slot_sq_g = torch.zeros(nsq, device=self.dev)
         if multi:
             self._sq_slot.zero_()
         for sh in self._cat_shards:
             if sh["row_hi"] <= sh["row_lo"]:
                 continue
-            nv.counted_call("tcar_scatter_add_rows_groups", 3 * ng, C.c_void_p(ids_ptr), ids_stride, C.c_void_p(pay_ptr),
+            nv.counted_call("tcar_scatter_add_rows_multi" if merged else "tcar_scatter_add_rows_groups",
+                            3 if merged else 3 * ng, C.c_void_p(ids_ptr), ids_stride, C.c_void_p(pay_ptr),
                             pay_stride, p(ps.item), p(ps.item_g), p(self.hash_keys), p(self.hash_cnt), p(self.hash_acc),
                             p(self.entry_slot), p(self._slot_sq_g), self.hash_size, cnt, R, T, Nn, sh["row_lo"],
                             sh["row_hi"])
@@ -330,7 +337,7 @@ class CatalogShardedTraining:
             # group = accumulated values) + the per-slot corrections of the scatter passes
             dense = sh["hi"] > sh["lo"]
             nv.counted_call("tcar_update_norms", 1, None, None, None, 0, p(sh["sqp"]) if dense else None,
-                            sh["ctas"] if dense else 0, p(self._slot_sq_g), R * self.hash_size,
+                            sh["ctas"] if dense else 0, p(self._slot_sq_g), nsq,
                             p(self._sq_tmp if multi else self._sq_slot), p(ps.norm_partial), p(ps.norm_ticket), None)
             if multi:
                 self._sq_slot += self._sq_tmp

@@ -622,7 +622,10 @@ eval_topk_kernel(const float* chunkmax, const float* tilemax, const float* __res
 // A certified query costs nothing (its CTAs return at once).
 constexpr int WQ_CAP = 4096;        // chunk queue: one sweep of 256 tiles x 16 chunks
 constexpr int WSPLIT = TCAR_WIDEN_SPLITS;
-constexpr size_t W_GROUP_WORDS = (size_t)TCAR_WIDEN_SPLITS * TCAR_QROWS * (2 * TCAR_TOPK + 1);   // workspace per group
+// workspace per group: partial lists [S][512][20] ids | scores, counts [S][512], then one ticket per query (zero between
+// launches: the split CTA that arrives last merges the query's partial lists and resets it)
+constexpr size_t W_LIST_WORDS = (size_t)TCAR_WIDEN_SPLITS * TCAR_QROWS * (2 * TCAR_TOPK + 1);
+constexpr size_t W_GROUP_WORDS = W_LIST_WORDS + TCAR_QROWS;
 
 // several session groups in one launch of the widening pass / its merge (blockIdx.z resp. blockIdx.y = group)
 struct WidenGroups {
@@ -635,12 +638,17 @@ struct WidenGroups {
 };
 constexpr int WIDEN_SLOTS = 37;     // x 16 splits = 592 CTAs = 4 per SM: one wave
 
+__device__ __forceinline__ void warp_merge_lists(const int32_t* ids, const float* scores, int G, int B, long long gstride,
+                                                 int b, int lane, int32_t* out_ids, float* out_scores);
+
+// The WSPLIT CTAs of a flagged query each scan their share of the item range; the one that finishes last (ticket
+// counter behind the partial lists) merges the WSPLIT partial lists into the query's result -- no second launch.
 __global__ void __launch_bounds__(256)
 eval_topk_widen_kernel(const float* chunkmax, const float* tilemax, const float* a_ic, const float* Tq,
                        const float* __restrict__ item, const float* __restrict__ content,
                        const int32_t* __restrict__ mwdhm, const int32_t* label, const int32_t* uncertain,
-                       const float* tau, int32_t* wspace, int N, int n_pad, int item_offset, int B,
-                       const __grid_constant__ WidenGroups wg) {
+                       const float* tau, int32_t* wspace, int32_t* out_ids, float* out_scores, int32_t* out_ngt, int N,
+                       int n_pad, int item_offset, int B, const __grid_constant__ WidenGroups wg) {
     PDL_ENTER();
     const int split = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     if (wg.groups > 0) {
@@ -655,11 +663,16 @@ eval_topk_widen_kernel(const float* chunkmax, const float* tilemax, const float*
         uncertain += (size_t)g * wg.flag_gs;
         tau += (size_t)g * wg.flag_gs;
         wspace += (size_t)g * W_GROUP_WORDS;
+        out_ids += (size_t)g * wg.out_gs;
+        out_scores += (size_t)g * wg.out_gs;
+        out_ngt += (size_t)g * wg.out_gs;
     }
     // partial lists of this launch: ids [S][B][20] | scores [S][B][20] | counts [S][B]
     int32_t* top_ids = wspace;
     float* top_scores = reinterpret_cast<float*>(wspace + (size_t)WSPLIT * TCAR_QROWS * TOPK);
     int32_t* n_greater = wspace + 2 * (size_t)WSPLIT * TCAR_QROWS * TOPK;
+    int32_t* ticket = wspace + W_LIST_WORDS;
+    __shared__ int s_last;
     // compact list of the flagged queries (ascending, built identically by every CTA): the grid is WIDEN_SLOTS x
     // WSPLIT CTAs whatever B is, CTA (i, s) takes the flagged queries i, i + WIDEN_SLOTS, ...
     __shared__ int s_flag[TCAR_QROWS];
@@ -727,11 +740,24 @@ eval_topk_widen_kernel(const float* chunkmax, const float* tilemax, const float*
             while (P < ncand) P <<= 1;
             if (tid < P) { s_sc[tid] = -INFINITY; s_id[tid] = 0x7fffffff; }
             __syncthreads();
-            for (int ci = w; ci < ncand; ci += 8) {               // interleaved: few candidates -> few iterations
-                const int n = s_q[q0 + ci / CH] * CH + (ci % CH);
-                if (n < N) {
-                    const float sc = exact_score_e(s_aic, s_tq, item, content, mwdhm, n + item_offset, lane);
-                    if (lane == 0) { s_sc[ci] = sc; s_id[ci] = n + item_offset; }
+            for (int ci = w; ci < ncand; ci += 32) {              // interleaved: few candidates -> few iterations
+                // four candidates per warp and iteration, branch-free, so that the 16 row loads of a lane are all in
+                // flight before the first dot product (a candidate costs one DRAM round trip otherwise)
+                int nn[4];
+                float sc[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int cu = ci + 8 * u;
+                    const int n = cu < ncand ? s_q[q0 + cu / CH] * CH + (cu % CH) : N;
+                    nn[u] = n < N ? n + item_offset : -1;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    sc[u] = exact_score_e(s_aic, s_tq, item, content, mwdhm, nn[u] >= 0 ? nn[u] : 0, lane);
+                if (lane == 0) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (nn[u] >= 0) { s_sc[ci + 8 * u] = sc[u]; s_id[ci + 8 * u] = nn[u]; }
                 }
             }
             __syncthreads();
@@ -779,6 +805,23 @@ eval_topk_widen_kernel(const float* chunkmax, const float* tilemax, const float*
         top_scores[slot * TOPK + tid] = s_top_sc[tid];
     }
     if (tid == 0) n_greater[slot] = s_ngt;
+    // last split CTA of this query: merge the WSPLIT partial lists (written by other CTAs: fence, ticket, fence)
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(&ticket[b], 1) == WSPLIT - 1;
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        if (w == 0) {
+            if (lane == 0) {
+                int cnt = 0;
+                for (int g = 0; g < WSPLIT; ++g) cnt += n_greater[(size_t)g * B + b];
+                out_ngt[b] = cnt;
+                ticket[b] = 0;
+            }
+            warp_merge_lists(top_ids, top_scores, WSPLIT, B, 0LL, b, lane, out_ids, out_scores);
+        }
+    }
   }
 }
 
@@ -816,6 +859,38 @@ catalog_stats_kernel(const float* __restrict__ item, const float* __restrict__ c
     if (lane == 0) {
         atomicMax(reinterpret_cast<int*>(out), __float_as_int(sqrtf(mx) * 1.000001f));
         atomicMax(reinterpret_cast<int*>(out) + 1, __float_as_int(sqrtf(dmx) * 1.000001f));
+    }
+}
+
+// One warp merges the G sorted lists of query b (G * 20 <= 32 * 32 entries) into the 20 best by (score desc, id asc).
+// Lists: [G][B][20] back to back (gstride == 0) or one block of `gstride` words per list owner.
+__device__ __forceinline__ void warp_merge_lists(const int32_t* ids, const float* scores, int G, int B, long long gstride,
+                                                 int b, int lane, int32_t* out_ids, float* out_scores) {
+    const int n = G * TOPK;
+    uint32_t taken = 0;           // each lane owns entries lane, lane + 32, ...: one `taken` bit per owned entry
+    for (int r = 0; r < TOPK; ++r) {
+        float bs = -INFINITY; int bi = 0x7fffffff, bslot = -1;
+        for (int e = lane, s = 0; e < n; e += 32, ++s) {
+            if (taken & (1u << s)) continue;
+            const int g = e / TOPK, j = e % TOPK;
+            const size_t at = gstride ? (size_t)g * gstride + (size_t)b * TOPK + j : ((size_t)g * B + b) * TOPK + j;
+            const float sc = scores[at];
+            int id = ids[at];
+            if (id < 0) id = 0x7fffffff;
+            if (before(sc, id, bs, bi)) { bs = sc; bi = id; bslot = s; }
+        }
+        float ws = bs; int wi = bi;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float os = __shfl_xor_sync(0xffffffffu, ws, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+            if (before(os, oi, ws, wi)) { ws = os; wi = oi; }
+        }
+        if (bslot >= 0 && bs == ws && bi == wi && wi != 0x7fffffff) taken |= 1u << bslot;
+        if (lane == 0) {
+            out_ids[(size_t)b * TOPK + r] = wi == 0x7fffffff ? -1 : wi;
+            out_scores[(size_t)b * TOPK + r] = ws;
+        }
     }
 }
 
@@ -867,35 +942,7 @@ topk_merge_kernel(const int32_t* ids, const float* scores, int32_t* out_ids, flo
         out_ngt[b] = cnt;
         out_ce[b] = fmaf(M, 0.6931471805599453f, logf(tot));
     }
-    const int n = G * TOPK;
-    // each lane owns entries lane, lane+32, ...; `taken` bit per owned entry
-    uint32_t taken = 0;
-    for (int r = 0; r < TOPK; ++r) {
-        float bs = -INFINITY; int bi = 0x7fffffff, bslot = -1;
-        for (int e = lane, s = 0; e < n; e += 32, ++s) {
-            if (taken & (1u << s)) continue;
-            const int g = e / TOPK, j = e % TOPK;
-            // shard lists: [G][B][20] back to back (gstride == 0) or one block of `gstride` words per shard
-            const size_t at = gstride ? (size_t)g * gstride + (size_t)b * TOPK + j : ((size_t)g * B + b) * TOPK + j;
-            const float sc = scores[at];
-            int id = ids[at];
-            if (id < 0) id = 0x7fffffff;
-            if (before(sc, id, bs, bi)) { bs = sc; bi = id; bslot = s; }
-        }
-        // warp arg-best
-        float ws = bs; int wi = bi;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float os = __shfl_xor_sync(0xffffffffu, ws, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
-            if (before(os, oi, ws, wi)) { ws = os; wi = oi; }
-        }
-        if (bslot >= 0 && bs == ws && bi == wi && wi != 0x7fffffff) taken |= 1u << bslot;
-        if (lane == 0) {
-            out_ids[(size_t)b * TOPK + r] = wi == 0x7fffffff ? -1 : wi;
-            out_scores[(size_t)b * TOPK + r] = ws;
-        }
-    }
+    warp_merge_lists(ids, scores, G, B, gstride, b, lane, out_ids, out_scores);
 }
 
 }  // namespace tcar
@@ -962,14 +1009,8 @@ static int launch_widen(const float* chunkmax, const float* tilemax, const float
     int32_t* w = static_cast<int32_t*>(workspace);
     const int groups = wg.groups > 0 ? wg.groups : 1;
     launch_pdl(eval_topk_widen_kernel, dim3(B < WIDEN_SLOTS ? B : WIDEN_SLOTS, WSPLIT, groups), dim3(256), 0, STREAM,
-               chunkmax, tilemax, a_ic, Tq, item, content, mwdhm, label, uncertain, tau, w, N, n_pad, item_offset, B, wg);
-    int rc = (int)cudaGetLastError();
-    if (rc) return rc;
-    launch_pdl(topk_merge_kernel, dim3((B + 7) / 8, groups), dim3(256), 0, STREAM, static_cast<const int32_t*>(w),
-               reinterpret_cast<const float*>(w + (size_t)WSPLIT * TCAR_QROWS * TOPK), top_ids, top_scores, WSPLIT, B,
-               0LL, static_cast<const int32_t*>(w + 2 * (size_t)WSPLIT * TCAR_QROWS * TOPK),
-               static_cast<const float*>(nullptr), static_cast<const float*>(nullptr), n_greater,
-               static_cast<float*>(nullptr), uncertain, wg);
+               chunkmax, tilemax, a_ic, Tq, item, content, mwdhm, label, uncertain, tau, w, top_ids, top_scores,
+               n_greater, N, n_pad, item_offset, B, wg);
     return (int)cudaGetLastError();
 }
 

@@ -965,13 +965,12 @@ __device__ __forceinline__ int entry_row(int e, int M, int B, const int32_t* __r
 
 // pass 1 -- one thread per sparse entry (clicks [0,M), labels [M,M+B), negatives [M+B, M+B+B*Nn)): claim the hash
 // slot of its item row and count how many entries share it.
-__global__ void __launch_bounds__(256)
-scatter_count_kernel(const int32_t* __restrict__ seq, const int32_t* __restrict__ label,
-                     const int32_t* __restrict__ neg, int32_t* __restrict__ keys, int32_t* __restrict__ cnt,
-                     int32_t* __restrict__ entry_slot, int mask, int B, int T, int Nn, int row_lo, int row_hi) {
-    PDL_ENTER();
+__device__ __forceinline__ void scatter_count_body(int e, const int32_t* __restrict__ seq,
+                                                   const int32_t* __restrict__ label, const int32_t* __restrict__ neg,
+                                                   int32_t* __restrict__ keys, int32_t* __restrict__ cnt,
+                                                   int32_t* __restrict__ entry_slot, int mask, int B, int T, int Nn,
+                                                   int row_lo, int row_hi) {
     const int M = B * T;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= M + B + B * Nn) return;
     const int row = entry_row(e, M, B, seq, label, neg);
     // rows outside [row_lo, row_hi) belong to another catalog shard (tcar_scatter_add_rows_range): no slot
@@ -981,18 +980,54 @@ scatter_count_kernel(const int32_t* __restrict__ seq, const int32_t* __restrict_
     entry_slot[e] = slot;
 }
 
+__global__ void __launch_bounds__(256)
+scatter_count_kernel(const int32_t* __restrict__ seq, const int32_t* __restrict__ label,
+                     const int32_t* __restrict__ neg, int32_t* __restrict__ keys, int32_t* __restrict__ cnt,
+                     int32_t* __restrict__ entry_slot, int mask, int B, int T, int Nn, int row_lo, int row_hi) {
+    PDL_ENTER();
+    scatter_count_body(blockIdx.x * blockDim.x + threadIdx.x, seq, label, neg, keys, cnt, entry_slot, mask, B, T, Nn,
+                       row_lo, row_hi);
+}
+
+// The sparse rows of SEVERAL session groups (the ranks of a catalog-sharded step) against ONE hash table: blockIdx.y =
+// group, packed batch of group g at ids + g * ids_stride ([7*B*T idx | 2*B ctx | B label | B*Nn neg]), payload at
+// payload + g * pay_stride ([a_ic 512x500 | coef 512 | dXi B*T x 256]), its entries' slots at entry_slot + g * es_stride.
+// Counting ALL groups before any accumulation makes "touched once" a global property, so the in-place path stays
+// race-free and the shared rows still add up in order-independent fixed point: three launches per step instead of
+// three per source rank.
+struct ScatterGroups {
+    const int32_t* ids;
+    const float* payload;
+    long long ids_stride, pay_stride, es_stride;
+    int n[TCAR_MAX_PEERS];
+};
+
+__global__ void __launch_bounds__(256)
+scatter_count_groups_kernel(const __grid_constant__ ScatterGroups sg, int32_t* __restrict__ keys,
+                            int32_t* __restrict__ cnt, int32_t* __restrict__ entry_slot, int mask, int T, int Nn,
+                            int row_lo, int row_hi) {
+    PDL_ENTER();
+    const int g = blockIdx.y, B = sg.n[g];
+    if (B <= 0) return;
+    const int32_t* base = sg.ids + (size_t)g * sg.ids_stride;
+    const size_t M = (size_t)B * T;
+    scatter_count_body(blockIdx.x * blockDim.x + threadIdx.x, base, base + 7 * M + 2 * (size_t)B,
+                       base + 7 * M + 3 * (size_t)B, keys, cnt, entry_slot + (size_t)g * sg.es_stride, mask, B, T, Nn,
+                       row_lo, row_hi);
+}
+
 // pass 2 -- one warp per entry.  A row touched by exactly one entry (the common case: uniform negatives, labels, tail
 // items) is updated in place with plain 128-bit read-modify-writes; rows shared by several entries accumulate in exact
 // int64 fixed point (2^-40) so that the sum does not depend on the arrival order.
-__global__ void __launch_bounds__(256)
-scatter_accum_kernel(const int32_t* __restrict__ seq, const int32_t* __restrict__ label,
-                     const int32_t* __restrict__ neg, const float* __restrict__ dXi, const float* __restrict__ a_ic,
-                     const float* __restrict__ coef, const float* __restrict__ item, float* __restrict__ g_item,
-                     const int32_t* __restrict__ cnt, const int32_t* __restrict__ entry_slot,
-                     unsigned long long* __restrict__ acc, float* __restrict__ slot_sq, int B, int T, int Nn) {
-    PDL_ENTER();
+__device__ __forceinline__ void scatter_accum_body(int e, int lane, const int32_t* __restrict__ seq,
+                                                   const int32_t* __restrict__ label, const int32_t* __restrict__ neg,
+                                                   const float* __restrict__ dXi, const float* __restrict__ a_ic,
+                                                   const float* __restrict__ coef, const float* __restrict__ item,
+                                                   float* __restrict__ g_item, const int32_t* __restrict__ cnt,
+                                                   const int32_t* __restrict__ entry_slot,
+                                                   unsigned long long* __restrict__ acc, float* __restrict__ slot_sq,
+                                                   int B, int T, int Nn) {
     const int M = B * T;
-    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (e >= M + B + B * Nn) return;
     const int slot = entry_slot[e];
     if (slot < 0) return;                    // row of another catalog shard
@@ -1074,6 +1109,34 @@ scatter_accum_kernel(const int32_t* __restrict__ seq, const int32_t* __restrict_
             }
         }
     }
+}
+
+__global__ void __launch_bounds__(256)
+scatter_accum_kernel(const int32_t* __restrict__ seq, const int32_t* __restrict__ label,
+                     const int32_t* __restrict__ neg, const float* __restrict__ dXi, const float* __restrict__ a_ic,
+                     const float* __restrict__ coef, const float* __restrict__ item, float* __restrict__ g_item,
+                     const int32_t* __restrict__ cnt, const int32_t* __restrict__ entry_slot,
+                     unsigned long long* __restrict__ acc, float* __restrict__ slot_sq, int B, int T, int Nn) {
+    PDL_ENTER();
+    scatter_accum_body((blockIdx.x * blockDim.x + threadIdx.x) >> 5, threadIdx.x & 31, seq, label, neg, dXi, a_ic, coef,
+                       item, g_item, cnt, entry_slot, acc, slot_sq, B, T, Nn);
+}
+
+__global__ void __launch_bounds__(256)
+scatter_accum_groups_kernel(const __grid_constant__ ScatterGroups sg, const float* __restrict__ item,
+                            float* __restrict__ g_item, const int32_t* __restrict__ cnt,
+                            const int32_t* __restrict__ entry_slot, unsigned long long* __restrict__ acc,
+                            float* __restrict__ slot_sq, int T, int Nn) {
+    PDL_ENTER();
+    const int g = blockIdx.y, B = sg.n[g];
+    if (B <= 0) return;
+    const int32_t* base = sg.ids + (size_t)g * sg.ids_stride;
+    const float* pay = sg.payload + (size_t)g * sg.pay_stride;
+    const size_t M = (size_t)B * T;
+    scatter_accum_body((blockIdx.x * blockDim.x + threadIdx.x) >> 5, threadIdx.x & 31, base,
+                       base + 7 * M + 2 * (size_t)B, Nn > 0 ? base + 7 * M + 3 * (size_t)B : nullptr,
+                       pay + TCAR_QROWS * TCAR_XW + TCAR_QROWS, pay, pay + TCAR_QROWS * TCAR_XW, item, g_item, cnt,
+                       entry_slot + (size_t)g * sg.es_stride, acc, slot_sq, B, T, Nn);
 }
 
 // pass 3 -- one thread per hash slot (most slots are empty or hold a row touched once: nothing to add); the slots of
@@ -1339,6 +1402,47 @@ extern "C" int tcar_scatter_add_rows_range(const int32_t* seq, const int32_t* la
     if (rc) return rc;
     launch_pdl(scatter_apply_kernel, dim3((hash_size + 255) / 256), dim3(256), 0, STREAM, hash_keys, hash_cnt, hash_acc, g_item, slot_sq,
                                                                   hash_size);
+    return LAUNCH_RC();
+}
+
+extern "C" int tcar_scatter_add_rows_multi(const int32_t* ids, long long ids_stride, const float* payload,
+                                           long long payload_stride, const float* item, float* g_item,
+                                           int32_t* hash_keys, int32_t* hash_cnt, long long* hash_acc,
+                                           int32_t* entry_slot, float* slot_sq, int hash_size, const int* n_rows,
+                                           int groups, int T, int Nn, int row_lo, int row_hi, void* stream) {
+    if (!n_rows || groups < 1 || groups > TCAR_MAX_PEERS || !ids || !payload || T < 1 || Nn < 0 ||
+        (hash_size & (hash_size - 1)))
+        return TCAR_ERR_ARG;
+    ScatterGroups sg = {};
+    sg.ids = ids;
+    sg.payload = payload;
+    sg.ids_stride = ids_stride;
+    sg.pay_stride = payload_stride;
+    long long total = 0;
+    int emax = 0;
+    for (int g = 0; g < groups; ++g) {
+        const int B = n_rows[g] > 0 ? n_rows[g] : 0;
+        if (B > TCAR_QROWS) return TCAR_ERR_ARG;
+        sg.n[g] = B;
+        const int e = B * T + B + B * Nn;
+        total += e;
+        if (e > emax) emax = e;
+    }
+    sg.es_stride = emax;
+    // every entry may fall into [row_lo, row_hi): the table must hold them all at load factor <= 1/2, entry_slot needs
+    // groups * emax words
+    if (total == 0 || (long long)hash_size < 2 * total) return TCAR_ERR_ARG;
+    launch_pdl(scatter_count_groups_kernel, dim3((emax + 255) / 256, groups), dim3(256), 0, STREAM, sg, hash_keys,
+               hash_cnt, entry_slot, hash_size - 1, T, Nn, row_lo, row_hi);
+    int rc = LAUNCH_RC();
+    if (rc) return rc;
+    launch_pdl(scatter_accum_groups_kernel, dim3((emax + 7) / 8, groups), dim3(256), 0, STREAM, sg, item, g_item,
+               static_cast<const int32_t*>(hash_cnt), static_cast<const int32_t*>(entry_slot),
+               reinterpret_cast<unsigned long long*>(hash_acc), slot_sq, T, Nn);
+    rc = LAUNCH_RC();
+    if (rc) return rc;
+    launch_pdl(scatter_apply_kernel, dim3((hash_size + 255) / 256), dim3(256), 0, STREAM, hash_keys, hash_cnt, hash_acc,
+               g_item, slot_sq, hash_size);
     return LAUNCH_RC();
 }
 

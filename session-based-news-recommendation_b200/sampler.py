@@ -182,7 +182,7 @@ class Sampler(object):
         Nn = self.neg_num if (self.neighbor_dict and self.neg_num) else 0
         M = B * T
         col = _columnar(self.session_dict, self.session_time_dict)
-        rows = np.fromiter((col.row[k] for k in ids), dtype=np.int64, count=B)
+        rows = np.fromiter(map(col.row.__getitem__, ids), dtype=np.int64, count=B)
         seq = col.seq[T][rows]                                    # [B, T+1]
         out = np.empty(7 * M + 3 * B + B * Nn, dtype=np.int32)
         idx = out[: 7 * M].reshape(7, B, T)

@@ -411,6 +411,70 @@ def test_catalog_lookahead_is_bit_identical(V, T, monkeypatch):
     assert int(look.ps.step.item()) == 4
 
 
+@pytest.mark.parametrize("counts,T,Nn", [([200, 512, 77], 6, 20), ([64, 0, 64, 3, 64, 64, 0, 512], 2, 5)])
+def test_scatter_add_rows_multi_equals_the_per_group_passes(counts, T, Nn):
+    """All source ranks of a catalog-sharded step against ONE hash table (tcar_scatter_add_rows_multi: count over every
+    group first, then accumulate, then apply) == one pass per rank (tcar_scatter_add_rows_groups): rows touched once get
+    the same single fp32 add, rows shared inside or across groups differ only by the rounding of the summation order;
+    the per-slot norm corrections add up to ||after||^2 - ||before||^2; scratch restored."""
+    import ctypes as C
+    from tcar_b200 import _native as nv
+    N, R = 700, len(counts)
+    QROWS, XW, HP = 512, 500, 256
+    g = torch.Generator(device="cuda").manual_seed(7 + R)
+    Bmax = max(counts)
+    L = 7 * Bmax * T + 3 * Bmax + Bmax * Nn
+    n_pay = QROWS * XW + QROWS + Bmax * T * HP
+    ids = torch.zeros(R, L, device="cuda", dtype=torch.int32)
+    pay = torch.zeros(R, n_pay, device="cuda")
+    for r, B in enumerate(counts):
+        if B == 0:
+            continue
+        M = B * T
+        # clicks are table rows 1..N from a small hot set (many rows shared inside and across the groups), labels and
+        # negatives item ids 0..N-1
+        ids[r, :M] = torch.randint(1, 60, (M,), device="cuda", generator=g, dtype=torch.int32)
+        ids[r, 7 * M + 2 * B: 7 * M + 3 * B] = torch.randint(0, N, (B,), device="cuda", generator=g, dtype=torch.int32)
+        ids[r, 7 * M + 3 * B: 7 * M + 3 * B + B * Nn] = torch.randint(0, N, (B * Nn,), device="cuda", generator=g,
+                                                                 dtype=torch.int32)
+        pay[r, : B * XW] = torch.randn(B * XW, device="cuda", generator=g) * 0.3            # a_ic rows
+        pay[r, QROWS * XW: QROWS * XW + B] = torch.rand(B, device="cuda", generator=g) * 0.01  # coef
+        dxi = torch.randn(M, HP, device="cuda", generator=g) * 0.1
+        dxi[:, 250:] = 0
+        pay[r, QROWS * XW + QROWS: QROWS * XW + QROWS + M * HP] = dxi.view(-1)
+    item = torch.zeros(N + 1, HP, device="cuda")
+    item[:, :250] = torch.randn(N + 1, 250, device="cuda", generator=g) * 0.1               # norms > 1: Jacobian active
+    base = torch.zeros(N + 1, HP, device="cuda")
+    base[:, :250] = torch.randn(N + 1, 250, device="cuda", generator=g)
+    ent = Bmax * T + Bmax + Bmax * Nn
+    hs = 1 << max(16, (2 * R * ent - 1).bit_length())
+    keys = torch.full((hs,), -1, device="cuda", dtype=torch.int32)
+    cnt_t = torch.zeros(hs, device="cuda", dtype=torch.int32)
+    acc = torch.zeros(hs, HP, device="cuda", dtype=torch.int64)
+    eslot = torch.zeros(R * ent, device="cuda", dtype=torch.int32)
+    cnt = (C.c_int * R)(*counts)
+    p = nv.ptr
+    out = {}
+    for name in ("tcar_scatter_add_rows_groups", "tcar_scatter_add_rows_multi"):
+        for lo, hi in ((0, N + 1), (100, 431)):
+            gi = base.clone()
+            sq = torch.zeros(R * hs if name.endswith("groups") else hs, device="cuda")
+            nv.call(name, p(ids), L, p(pay), n_pay, p(item), p(gi), p(keys), p(cnt_t), p(acc), p(eslot), p(sq), hs, cnt, R,
+                    T, Nn, lo, hi)
+            torch.cuda.synchronize()
+            assert (keys == -1).all() and (acc == 0).all() and (cnt_t == 0).all(), "scratch restored"
+            assert torch.equal(gi[:lo], base[:lo]) and torch.equal(gi[hi:], base[hi:])
+            out[(name, lo)] = (gi, float(sq.double().sum()))
+    for lo in (0, 100):
+        a, sa = out[("tcar_scatter_add_rows_groups", lo)]
+        b, sb = out[("tcar_scatter_add_rows_multi", lo)]
+        np.testing.assert_allclose(b.cpu().numpy(), a.cpu().numpy(), rtol=2e-5, atol=2e-5)
+        want = float((b.double() ** 2).sum() - (base.double() ** 2).sum())
+        assert abs(sb - want) <= 2e-4 * abs(want) + 1e-3 and abs(sa - want) <= 2e-4 * abs(want) + 1e-3
+        touched = (a != base).any(1)
+        assert int(touched.sum()) > 100 and torch.equal(touched, (b != base).any(1))
+
+
 def test_scatter_add_rows_range_partitions_the_unranged_call():
     """Two ranged calls over complementary row ranges == one unranged call, bit for bit (every row is handled by
     exactly one of them, with the same arithmetic)."""
