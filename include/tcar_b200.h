@@ -166,6 +166,10 @@ int tcar_rowsum_finish(const float* rowsum_part, float* out, int out_stride, int
 int tcar_neg_loss(const float* a_ic, const float* item, const float* content, const int32_t* neg, const float* ce,
                   float* negloss, float* loss, float* coef, float* dA_neg, int B, int Nn, void* stream);
 int tcar_loss_combine(const float* ce, const float* negloss, float* loss, int B, void* stream);
+/* Catalog-sharded step: sumexp[b] = sums[b * stride] (the softmax sums ride in the pad column of the reduce-scattered
+ * dQ), ce[b] = log(sumexp[b]) + (rowmax[b] > TCAR_EXP_LIMIT2 ? rowmax[b] ln 2 : 0); rowmax nullable. */
+int tcar_ce_from_sums(const float* sums, int stride, const float* rowmax, float* sumexp, float* ce, int B,
+                      void* stream);
 
 /* (3d) scoring backward wrt the query operand: dq_raw [512,640] = E . Iext (split-K partials in `part`,
  *      [tcar_score_bwd_q_splits()][512][640], reduced in fixed order). */

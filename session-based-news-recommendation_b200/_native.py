@@ -41,6 +41,7 @@ SIGNATURES = {
     "tcar_ce_finish_guarded": [_P] * 5 + [_I, _I, _I, _P],
     "tcar_neg_loss": [_P] * 9 + [_I, _I, _P],
     "tcar_loss_combine": [_P, _P, _P, _I, _P],
+    "tcar_ce_from_sums": [_P, _I, _P, _P, _P, _I, _P],
     "tcar_score_bwd_q_splits": [_I, _I],
     "tcar_score_bwd_q": [_P] * 4 + [_I, _I, _P],
     "tcar_score_bwd_finish": [_P] * 13 + [_I, _P],

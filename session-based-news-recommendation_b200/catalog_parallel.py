@@ -24,7 +24,6 @@ or a checkpoint).  With world_size == 1, args["catalog_virtual_shards"] = V make
 walk them one after the other -- the same kernels with the same shard offsets, used by the single-GPU parity test.
 """
 import ctypes as C
-import math
 
 import torch
 
@@ -226,6 +225,19 @@ class CatalogShardedTraining:
         if B > 0 and not ahead:
             self._session_forward(bt)
         mark("session_fwd")
+        neg_done = None
+        if B > 0:
+            # negative-feedback loss + its gradient wrt a_ic: needs a_ic and the (fetched) item rows only -- on the
+            # auxiliary stream beside the exchanges and the scoring GEMMs
+            main = torch.cuda.current_stream()
+            fork = torch.cuda.Event()
+            fork.record(main)
+            self._aux.wait_event(fork)
+            with torch.cuda.stream(self._aux):
+                nv.counted_call("tcar_neg_loss", 1, p(self.a_ic), p(ps.item), p(ps.content), p(bt.neg), None,
+                                p(self.negloss), p(self.loss), p(self.coef), p(self.dA_neg), B, Nn)
+                neg_done = torch.cuda.Event()
+                neg_done.record(self._aux)
         if on:
             self._gather(self._qc_all.view(-1), self._qc)
         mark("gather_q")
@@ -277,14 +289,12 @@ class CatalogShardedTraining:
         else:
             dq_raw = self._dq_all[0]
         if B > 0:
-            self.sumexp[:B].copy_(dq_raw[:B, KEXT - 1])
-            torch.log(self.sumexp[:B], out=self.ce[:B])
-            if guard:
-                # rows the guard shifted: CE = log(sum) + shift ln 2 (shift in log2 units)
-                rm = self._rowmax_all[me, :B]
-                self.ce[:B].add_(torch.where(rm > nv.EXP_LIMIT2, rm, torch.zeros_like(rm)), alpha=math.log(2.0))
-            nv.counted_call("tcar_neg_loss", 1, p(self.a_ic), p(ps.item), p(ps.content), p(bt.neg), p(self.ce),
-                            p(self.negloss), p(self.loss), p(self.coef), p(self.dA_neg), B, Nn)
+            # CE = log(sum) (+ shift ln 2 for rows the guard shifted) from the strided sums column; the negative-feedback
+            # term was launched beside the scoring phases (neg_done)
+            nv.counted_call("tcar_ce_from_sums", 1, p(dq_raw[:, KEXT - 1:]), KEXT,
+                            p(self._rowmax_all[me]) if guard else None, p(self.sumexp), p(self.ce), B)
+            torch.cuda.current_stream().wait_event(neg_done)
+            nv.counted_call("tcar_loss_combine", 1, p(self.ce), p(self.negloss), p(self.loss), B)
             nv.counted_call("tcar_score_bwd_finish", 1, p(dq_raw), p(self.sumexp), p(self.dA_neg), p(self.a_ic),
                             p(ps.ct_tab), p(ps.item), p(ps.content), p(ps.mwdhm), p(bt.label), p(self.d_a_ic),
                             p(self.d_a_pt), p(self.dTq), p(self.Qs), B)

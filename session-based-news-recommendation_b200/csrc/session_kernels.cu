@@ -719,6 +719,25 @@ neg_loss_kernel(const float* __restrict__ a_ic, const float* __restrict__ item, 
     }
 }
 
+// Catalog-sharded step: the softmax sums of a rank's sessions arrive in a strided column (the pad column of the
+// reduce-scattered dQ): sumexp[b] = sums[b * stride], ce[b] = log(sumexp[b]) (+ shift ln 2 for rows the overflow guard
+// shifted by rowmax[b] > TCAR_EXP_LIMIT2, log2 units).  One launch instead of six elementwise torch kernels.
+__global__ void __launch_bounds__(256)
+ce_from_sums_kernel(const float* __restrict__ sums, int stride, const float* __restrict__ rowmax,
+                    float* __restrict__ sumexp, float* __restrict__ ce, int B) {
+    PDL_ENTER();
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float s = sums[(size_t)b * stride];
+    sumexp[b] = s;
+    float c = logf(s);
+    if (rowmax) {
+        const float m = rowmax[b];
+        if (m > TCAR_EXP_LIMIT2) c = fmaf(m, 0.6931471805599453f, c);
+    }
+    ce[b] = c;
+}
+
 // loss = cross loss + 0.01 * negative-feedback loss (model_combine.py:146-147), for tcar_neg_loss(ce = NULL)
 __global__ void __launch_bounds__(256)
 loss_combine_kernel(const float* __restrict__ ce, const float* __restrict__ negloss, float* __restrict__ loss, int B) {
@@ -1350,6 +1369,13 @@ extern "C" int tcar_neg_loss(const float* a_ic, const float* item, const float* 
                              void* stream) {
     if (B < 1 || Nn < 0) return TCAR_ERR_ARG;
     launch_pdl(neg_loss_kernel, dim3(B), dim3(256), 0, STREAM, a_ic, item, content, neg, ce, negloss, loss, coef, dA_neg, B, Nn);
+    return LAUNCH_RC();
+}
+
+extern "C" int tcar_ce_from_sums(const float* sums, int stride, const float* rowmax, float* sumexp, float* ce, int B,
+                                 void* stream) {
+    if (B < 1 || stride < 1 || !sums || !sumexp || !ce) return TCAR_ERR_ARG;
+    launch_pdl(ce_from_sums_kernel, dim3((B + 255) / 256), dim3(256), 0, STREAM, sums, stride, rowmax, sumexp, ce, B);
     return LAUNCH_RC();
 }
 
