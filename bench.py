@@ -530,13 +530,22 @@ def run_b200(a):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    marks = []
     for i in range(W, W + K):
         model.train_step(dev[i % nbatch], nxt(dev, i))
+        ev = torch.cuda.Event(enable_timing=True)      # per-step marks on the launching stream: spread of the K steps
+        ev.record()
+        marks.append(ev)
     model.sync_updates()
     e1.record()
     barrier()
     train_ms = max_over_ranks(e0.elapsed_time(e1))
     launches = nv.LAUNCHES["count"]
+    seq_ms = [a_.elapsed_time(b_) for a_, b_ in zip([e0] + marks[:-1], marks)]
+    per_step = sorted(seq_ms)
+    step_spread = {"min_ms": per_step[0], "median_ms": per_step[len(per_step) // 2], "max_ms": per_step[-1],
+                   "first_ms": [round(x, 3) for x in seq_ms[:12]], "last_ms": [round(x, 3) for x in seq_ms[-6:]],
+                   "note": "rank 0, time between consecutive steps' last launches on the main stream"}
     loss_last = float(model.loss[:B].mean().item())
 
     # ---- end to end through the public API: pinned host batch -> H2D -> train_step -> D2H of the loss -------
@@ -846,7 +855,8 @@ def run_b200(a):
                 "unit": kk["unit"], "frac": kk["frac"], "traffic": kk["traffic"], "peak_source": kk["peak_source"],
                 "ms_per_launch": kk["ms"]}
     line = {"metric": f"TCAR train sessions/sec ({SHAPE[a.workload][0]} shape)", "value": value, "unit": "sessions/s", "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": train_ms / K, "higher_is_better": True, "scaling": "weak",
+            "steps": K, "warmup": W, "ms_per_step": train_ms / K, "ms_per_step_spread": step_spread,
+            "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16 tensor-core scoring GEMMs (fp32 accumulate), fp32 elsewhere",
             "data": "synthetic", "config": dict(workload_config(a, world), lookahead=bool(pipe),
                                                 **({"layout_note": layout_note} if layout_note else {})),

@@ -78,6 +78,7 @@ class CatalogShardedTraining:
         import os
         self.cat_lookahead = os.environ.get("TCAR_CATALOG_LOOKAHEAD", "0") == "1"
         self._scatter_merged = os.environ.get("TCAR_SCATTER_LOOP", "0") != "1"
+        self._neg_side = os.environ.get("TCAR_CAT_NEG_SIDE", "0") == "1"     # opt-in: negative-feedback loss on the auxiliary stream
         self._ids_n = torch.zeros(1, device=dev, dtype=torch.int32)
         self._ids_all_n = torch.zeros(1, device=dev, dtype=torch.int32)
         self._cat_pre = None               # {"bt", "counts", "L"} of the batch whose ids / rows / forward are ahead
@@ -226,7 +227,10 @@ class CatalogShardedTraining:
             self._session_forward(bt)
         mark("session_fwd")
         neg_done = None
-        if B > 0:
+        if B > 0 and not self._neg_side:
+            nv.counted_call("tcar_neg_loss", 1, p(self.a_ic), p(ps.item), p(ps.content), p(bt.neg), None,
+                            p(self.negloss), p(self.loss), p(self.coef), p(self.dA_neg), B, Nn)
+        elif B > 0:
             # negative-feedback loss + its gradient wrt a_ic: needs a_ic and the (fetched) item rows only -- on the
             # auxiliary stream beside the exchanges and the scoring GEMMs
             main = torch.cuda.current_stream()
@@ -293,7 +297,8 @@ class CatalogShardedTraining:
             # term was launched beside the scoring phases (neg_done)
             nv.counted_call("tcar_ce_from_sums", 1, p(dq_raw[:, KEXT - 1:]), KEXT,
                             p(self._rowmax_all[me]) if guard else None, p(self.sumexp), p(self.ce), B)
-            torch.cuda.current_stream().wait_event(neg_done)
+            if neg_done is not None:
+                torch.cuda.current_stream().wait_event(neg_done)
             nv.counted_call("tcar_loss_combine", 1, p(self.ce), p(self.negloss), p(self.loss), B)
             nv.counted_call("tcar_score_bwd_finish", 1, p(dq_raw), p(self.sumexp), p(self.dA_neg), p(self.a_ic),
                             p(ps.ct_tab), p(ps.item), p(ps.content), p(ps.mwdhm), p(bt.label), p(self.d_a_ic),
