@@ -1,7 +1,7 @@
 #!/bin/bash
 # `ncu --set full` capture of every hot kernel of ONE train step (T = 20) + ONE eval step (bench.py --profile_region)
 mkdir -p gpurun_out
-K='regex:score_fwd_pair|score_bwd_i|adam_item|gather_fwd|pool_fwd|pool_bwd|scatter_|table_grads|gemm_tf32_kernel|eval_topk|build_query|col_jobs|update_norms|adam_small|neg_loss|score_bwd_finish|ce_finish|prep_weights'
+K='regex:score_fwd_pair|score_bwd_i|adam_item|gather_fwd|pool_fwd|pool_bwd|scatter_|table_grads|gemm_tf32_kernel|eval_topk|build_query|col_jobs|update_norms|adam_small|neg_loss|loss_combine|score_bwd_finish|ce_finish|prep_weights'
 timeout -s KILL 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k "$K" -f -o gpurun_out/prof_step \
   python bench.py --profile_region > gpurun_out/ncu_full.log 2>&1
 echo "ncu A exit $?"; tail -2 gpurun_out/ncu_full.log
