@@ -344,10 +344,10 @@ class Seq2SeqAttNN(CatalogShardedTraining):
             cur.wait_event(self._ahead_done)
             self._ahead_done = None
 
-    def _session_forward(self, bt, prefetch=False, query=True):
+    def _session_forward(self, bt, prefetch=False):
         """Everything up to a_ic / a_pt / Q: model_combine.py:52-127.  With prefetch=True the caller guarantees that
         the rows of the item table this batch reads (clicks, labels) are already up to date, so the pending table-wide
-        update is NOT waited for.  query=False stops after a_ic / a_pt (the caller runs _session_query later)."""
+        update is NOT waited for."""
         if not prefetch:
             self.sync_updates()
             self._prefetched = None
@@ -376,8 +376,6 @@ class Seq2SeqAttNN(CatalogShardedTraining):
                precise=True),
             pr([(self.pooled_t, PW, 0, wh["W_p"], wl["W_p"], 320, 1, PW)], B, PW, self.a_pt, PW, bias=w["b_p"], act=2,
                precise=True)])
-        if not query:
-            return
         self._session_query(bt)
 
     def _session_query(self, bt):
@@ -752,32 +750,17 @@ class Seq2SeqAttNN(CatalogShardedTraining):
             ev.record(stream if stream is not None else torch.cuda.current_stream())
             tr.append((name, ev))
 
-    def _prefetch_forward(self, next_bt, query=True):
-        """Launch next_bt's session forward on the high-priority stream behind everything queued so far.  query=False:
-        everything but the last two kernels (_prefetch_query launches those behind a later point of this stream)."""
+    def _prefetch_forward(self, next_bt):
+        """Launch next_bt's session forward on the high-priority stream behind everything queued so far."""
         main = torch.cuda.current_stream()
         fork = torch.cuda.Event()
         fork.record(main)
         self._ahead.wait_event(fork)
         with torch.cuda.stream(self._ahead):
-            self._session_forward(next_bt, prefetch=True, query=query)
+            self._session_forward(next_bt, prefetch=True)
             adone = torch.cuda.Event()
             adone.record(self._ahead)
-            self._etrace("ahead: session forward" + ("" if query else " (first half)"))
-        self._ahead_done = adone
-        self._prefetched = next_bt if query else None
-
-    def _prefetch_query(self, next_bt):
-        """Second half of a _prefetch_forward(next_bt, query=False): ordered behind everything queued so far."""
-        main = torch.cuda.current_stream()
-        fork = torch.cuda.Event()
-        fork.record(main)
-        self._ahead.wait_event(fork)
-        with torch.cuda.stream(self._ahead):
-            self._session_query(next_bt)
-            adone = torch.cuda.Event()
-            adone.record(self._ahead)
-            self._etrace("ahead: query")
+            self._etrace("ahead: session forward")
         self._ahead_done = adone
         self._prefetched = next_bt
 

@@ -85,6 +85,31 @@ def test_prefetcher_preserves_order_and_content():
         np.testing.assert_array_equal(a, b)
 
 
+def test_prefetcher_lowers_the_gil_switch_interval_only_while_it_runs():
+    """The producer thread and the launching thread share the GIL: prefetch_packed shortens CPython's switch interval
+    for the lifetime of the iterator (also when the consumer abandons it early) and restores the caller's value."""
+    import sys
+    from tcar_b200.model_combine import prefetch_packed
+    from tcar_b200.sampler import Sampler
+    d, len_dict, session_dict, time_dict, item_dict, impressions = _datasets()
+    run = d["runs"][0]
+    before = sys.getswitchinterval()
+    for abandon in (False, True):
+        random.seed(5)
+        np.random.seed(5)
+        s = Sampler({k: list(v) for k, v in len_dict.items()}, session_dict, time_dict, impressions, item_dict,
+                    run["neg_num"], batch_size=run["batch_size"], verbose=False)
+        it = prefetch_packed(s, depth=2)
+        next(it)
+        assert sys.getswitchinterval() <= 1e-4 + 1e-12
+        if abandon:
+            it.close()
+        else:
+            for _ in it:
+                pass
+        assert sys.getswitchinterval() == before
+
+
 def test_next_packed_is_the_same_batch_in_one_buffer():
     from tcar_b200.sampler import Sampler, pack_batch
     d, len_dict, session_dict, time_dict, item_dict, impressions = _datasets()
